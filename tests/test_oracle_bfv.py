@@ -1,0 +1,214 @@
+"""Pin the RNS / BFV part of the CPU oracle against exact Python big-integer arithmetic."""
+from math import prod
+
+import numpy as np
+import pytest
+
+from bigint_ref import centred, crt, negacyclic_mul, poly_from_rns, poly_to_rns, round_half_up
+
+
+def _rand_big(rng, lo, hi):
+    span = hi - lo
+    nbytes = (span.bit_length() + 7) // 8 + 8
+    return lo + int.from_bytes(rng.bytes(nbytes), "little") % span
+
+
+@pytest.mark.parametrize("S,T", [(1, 3), (2, 3), (4, 5), (8, 24), (24, 25)])
+def test_exact_base_conversion(oracle, chain, S, T):
+    src, dst = chain[:S], chain[S:S + T]
+    Q = prod(src)
+    lc = oracle.LinComb.conv(src, dst)
+    rng = np.random.default_rng(10 + S)
+    n = 64
+    xs = [_rand_big(rng, -(Q // 2), Q - Q // 2 - 1) for _ in range(n - 4)] + [0, 1, -1, Q // 2 - 1]
+    inp = np.array([[x % q for x in xs] for q in src], dtype=np.uint64)
+    out = lc.apply(inp)
+    for k, m in enumerate(dst):
+        assert [int(v) for v in out[k]] == [x % m for x in xs]
+    # constants against their definitions
+    cst = lc.constants()
+    for i, q in enumerate(src):
+        assert int(cst["pre"][i]) == pow(Q // q, -1, q)
+        assert (int(cst["th_hi"][i]) << 64) | int(cst["th_lo"][i]) == (1 << 128) // q
+        for k, m in enumerate(dst):
+            assert int(cst["M"][i, k]) == (Q // q) % m
+    for k, m in enumerate(dst):
+        assert int(cst["c"][k]) == (-Q) % m
+
+
+@pytest.mark.parametrize("L,R,t", [(1, 2, 65537), (2, 3, 65537), (4, 5, 786433), (3, 4, 1 << 20)])
+def test_scale_and_round_hps(oracle, chain, L, R, t):
+    qs, ps = chain[:L], chain[L:L + R]
+    Q, P = prod(qs), prod(ps)
+    lc = oracle.LinComb.scale(qs, ps, t, ps, True)
+    rng = np.random.default_rng(20 + L)
+    n = 64
+    bound = Q * P // (4 * t)   # keeps |t/Q d| < P/2
+    ds = [_rand_big(rng, -bound, bound) for _ in range(n - 3)] + [0, 1, -1]
+    dq = np.array([[d % q for d in ds] for q in qs], dtype=np.uint64)
+    dp = np.array([[d % p for d in ds] for p in ps], dtype=np.uint64)
+    out = lc.apply(dq, extra=dp)
+    for k, p in enumerate(ps):
+        assert [int(v) for v in out[k]] == [round_half_up(t * d, Q) % p for d in ds]
+
+
+@pytest.mark.parametrize("L,t", [(1, 65537), (2, 65537), (4, 256), (24, 65537)])
+def test_decrypt_scaling(oracle, chain, L, t):
+    qs = chain[:L]
+    Q = prod(qs)
+    lc = oracle.LinComb.scale(qs, [], t, [t], False)
+    rng = np.random.default_rng(30 + L)
+    xs = [_rand_big(rng, 0, Q) for _ in range(64)]
+    inp = np.array([[x % q for x in xs] for q in qs], dtype=np.uint64)
+    out = lc.apply(inp)
+    assert [int(v) for v in out[0]] == [round_half_up(t * x, Q) % t for x in xs]
+
+
+def test_modswitch_drop_last(oracle, chain):
+    mods = chain[:3]
+    Q = prod(mods)
+    rng = np.random.default_rng(40)
+    xs = [_rand_big(rng, 0, Q) for _ in range(32)]
+    inp = np.array([[x % q for x in xs] for q in mods], dtype=np.uint64)
+    out = oracle.modswitch_drop_last(inp, mods)
+    ql = mods[-1]
+    for i, q in enumerate(mods[:-1]):
+        # round(x / q_last) with ties (r == q_last/2 impossible: q_last odd)
+        assert [int(v) for v in out[i]] == [((x - centred_rem(x, ql)) // ql) % q for x in xs]
+
+
+def centred_rem(x, q):
+    r = x % q
+    return r - q if r > q // 2 else r
+
+
+def test_samplers(oracle):
+    n = 4096
+    s = oracle.sample_ternary_hw(n, 7, 0, 64)
+    assert (s != 0).sum() == 64 and set(np.unique(s)) <= {-1, 0, 1}
+    u = oracle.sample_ternary(n, 7, 0)
+    assert set(np.unique(u)) == {-1, 0, 1} and abs((u != 0).mean() - 0.5) < 0.05
+    cdt = oracle.gaussian_cdt(3.2)
+    assert int(cdt[-1]) == 1 << 63 and all(int(cdt[i]) < int(cdt[i + 1]) for i in range(len(cdt) - 1))
+    e = oracle.sample_gaussian(1 << 16, 7, 1, cdt)
+    assert abs(e.mean()) < 0.1 and abs(e.std() - 3.2) < 0.1 and np.abs(e).max() <= 20
+    # python restatement of the generator
+    def mix(z):
+        z &= (1 << 64) - 1
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & ((1 << 64) - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & ((1 << 64) - 1)
+        return z ^ (z >> 31)
+    G = 0x9E3779B97F4A7C15
+    for seed, st, idx in [(0, 0, 0), (12345, 3, 99), (2**63, 1024, 2**40)]:
+        assert oracle.rng64(seed, st, idx) == mix(mix(seed + G * (st + 1)) + G * (idx + 1))
+    q = 0xFFFFFFFFFFC0001
+    a = oracle.sample_uniform(8, q, 5, 16)
+    for j in range(8):
+        assert int(a[j]) == ((oracle.rng64(5, 16, 2 * j) << 64) | oracle.rng64(5, 16, 2 * j + 1)) % q
+
+
+@pytest.fixture(scope="module")
+def small_bfv(oracle, chain):
+    n, L, R, K, dnum, t = 32, 4, 5, 2, 2, 65537
+    ctx = oracle.Bfv(n, L, R, K, dnum, t, chain[:L + R], sigma=3.2, hw=8)
+    s, sk = ctx.secret_keygen(101)
+    pk = ctx.public_keygen(102, sk)
+    rlk = ctx.relin_keygen(103, sk)
+    return ctx, s, sk, pk, rlk
+
+
+def test_bfv_keys_are_rlwe_samples(oracle, chain, small_bfv):
+    ctx, s, sk, pk, rlk = small_bfv
+    n, L, K = ctx.n, ctx.L, ctx.K
+    qs = chain[:L]
+    Q = prod(qs)
+    sl = [int(v) for v in s]
+    # pk0 + pk1*s = e (small)
+    pk0 = poly_from_rns([oracle.ntt_inverse(pk[0, i], qs[i]) for i in range(L)], qs)
+    pk1 = poly_from_rns([oracle.ntt_inverse(pk[1, i], qs[i]) for i in range(L)], qs)
+    e = [centred(a + b, Q) for a, b in zip(pk0, negacyclic_mul(pk1, sl, n))]
+    assert max(abs(v) for v in e) <= 20
+    # rlk_d: b + a*s - P*B_d*s^2 = e_d (small) mod QP
+    W = chain[:L + K]
+    QP = prod(W); P = prod(chain[L:L + K])
+    s2 = negacyclic_mul(sl, sl, n)
+    for d in range(ctx.dnum):
+        grp = qs[d * ctx.alpha:(d + 1) * ctx.alpha]
+        Qd = prod(grp); Qh = Q // Qd
+        B = Qh * pow(Qh, -1, Qd)
+        b = poly_from_rns([oracle.ntt_inverse(rlk[d, 0, i], W[i]) for i in range(L + K)], W)
+        a = poly_from_rns([oracle.ntt_inverse(rlk[d, 1, i], W[i]) for i in range(L + K)], W)
+        as_ = negacyclic_mul(a, sl, n)
+        e = [centred(bb + aa - P * B * ss, QP) for bb, aa, ss in zip(b, as_, s2)]
+        assert max(abs(v) for v in e) <= 20
+
+
+def test_bfv_encrypt_decrypt_add(oracle, chain, small_bfv):
+    ctx, s, sk, pk, rlk = small_bfv
+    # reference examples: examples/basic_encryption.cu:46,90-106 ; tests/test_fhe.cu:201-202,264
+    m = ctx.encode([42, 100, 255, 1337])
+    ct = ctx.encrypt(201, m, pk)
+    assert np.array_equal(ctx.decrypt(ct, sk), m)
+    m1 = ctx.encode([5, 10, 15, 20]); m2 = ctx.encode([3, 6, 9, 12])
+    c1 = ctx.encrypt(202, m1, pk); c2 = ctx.encrypt(203, m2, pk)
+    assert [int(v) for v in ctx.decrypt(ctx.add(c1, c2), sk)[:4]] == [8, 16, 24, 32]
+    # ciphertext really is (pk0 u + e1 + Delta m, pk1 u + e2): c0 + c1 s = Delta m + small
+    qs = chain[:ctx.L]; Q = prod(qs)
+    sl = [int(v) for v in s]
+    c0 = poly_from_rns(ct[0], qs); c1p = poly_from_rns(ct[1], qs)
+    x = [centred(a + b, Q) for a, b in zip(c0, negacyclic_mul(c1p, sl, ctx.n))]
+    delta = Q // ctx.t
+    noise = [centred(xx - delta * int(mm), Q) for xx, mm in zip(x, m)]
+    assert max(abs(v) for v in noise) < 2**12
+    assert [int(v) for v in ctx.consts()["delta"]] == [delta % q for q in qs]
+
+
+def test_bfv_multiply_relin_exact(oracle, chain, small_bfv):
+    ctx, s, sk, pk, rlk = small_bfv
+    n, L, R, K, t = ctx.n, ctx.L, ctx.R, ctx.K, ctx.t
+    qs = chain[:L]; Q = prod(qs)
+    rng = np.random.default_rng(50)
+    m1 = rng.integers(0, t, n, dtype=np.uint64); m2 = rng.integers(0, t, n, dtype=np.uint64)
+    ca = ctx.encrypt(301, m1, pk); cb = ctx.encrypt(302, m2, pk)
+    out, sc = ctx.multiply_relin(ca, cb, rlk, want_scaled=True)
+    # decrypts to the negacyclic product mod t  (BASELINE.json config 2 check)
+    expect = [v % t for v in negacyclic_mul([int(v) for v in m1], [int(v) for v in m2], n)]
+    assert [int(v) for v in ctx.decrypt(out, sk)] == expect
+    # step-exact: scaled tensor == round(t/Q * tensor over Z) reduced mod q_i
+    a0, a1 = poly_from_rns(ca[0], qs), poly_from_rns(ca[1], qs)
+    b0, b1 = poly_from_rns(cb[0], qs), poly_from_rns(cb[1], qs)
+    d = [negacyclic_mul(a0, b0, n),
+         [x + y for x, y in zip(negacyclic_mul(a0, b1, n), negacyclic_mul(a1, b0, n))],
+         negacyclic_mul(a1, b1, n)]
+    ds = [[round_half_up(t * v, Q) for v in poly] for poly in d]
+    for p in range(3):
+        for i, q in enumerate(qs):
+            assert [int(v) for v in sc[p, i]] == [v % q for v in ds[p]]
+    # step-exact: hybrid key switching with exact ModUp / ModDown
+    W = chain[:L + K]; QP = prod(W); P = prod(chain[L:L + K])
+    acc0 = [0] * n; acc1 = [0] * n
+    for dg in range(ctx.dnum):
+        grp = qs[dg * ctx.alpha:(dg + 1) * ctx.alpha]; Qd = prod(grp)
+        D = [centred(v, Qd) for v in ds[2]]
+        kb = poly_from_rns([oracle.ntt_inverse(rlk[dg, 0, i], W[i]) for i in range(L + K)], W, centre=False)
+        ka = poly_from_rns([oracle.ntt_inverse(rlk[dg, 1, i], W[i]) for i in range(L + K)], W, centre=False)
+        acc0 = [(x + y) % QP for x, y in zip(acc0, negacyclic_mul(D, kb, n))]
+        acc1 = [(x + y) % QP for x, y in zip(acc1, negacyclic_mul(D, ka, n))]
+    for p, acc in enumerate((acc0, acc1)):
+        down = [(v - centred(v, P)) // P for v in acc]            # round(acc / P)
+        for i, q in enumerate(qs):
+            assert [int(v) for v in out[p, i]] == [(a + b) % q for a, b in zip(ds[p], down)]
+
+
+def test_bfv_reference_style_products(oracle, chain):
+    # BASELINE.json config 2 shape at reduced N: L=2 (log_q 120), t=65537
+    n, L, R, K, dnum, t = 64, 2, 3, 1, 2, 65537
+    ctx = oracle.Bfv(n, L, R, K, dnum, t, chain[:L + R], hw=16)
+    s, sk = ctx.secret_keygen(1); pk = ctx.public_keygen(2, sk); rlk = ctx.relin_keygen(3, sk)
+    m1 = ctx.encode([5, 10, 15, 20]); m2 = ctx.encode([3, 6, 9, 12])
+    c = ctx.multiply_relin(ctx.encrypt(4, m1, pk), ctx.encrypt(5, m2, pk), rlk)
+    # coefficient encoding => negacyclic polynomial product (15,60,150,300,375,360,240; SURVEY section 4 prints 355 for x^4, a typo: 10*12+15*9+20*6 = 375)
+    assert [int(v) for v in ctx.decrypt(c, sk)[:8]] == [15, 60, 150, 300, 375, 360, 240, 0]
+    # depth 2
+    c2 = ctx.multiply_relin(c, ctx.encrypt(6, ctx.encode([2]), pk), rlk)
+    assert [int(v) for v in ctx.decrypt(c2, sk)[:7]] == [30, 120, 300, 600, 750, 720, 480]
