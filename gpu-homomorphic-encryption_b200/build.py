@@ -1,0 +1,67 @@
+"""Build libfhe_b200.so (sm_100a only) in-tree with nvcc.  Used by __graft_entry__.build() and by hand:
+    python gpu-homomorphic-encryption_b200/build.py [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
+LIB = os.path.join(HERE, "libfhe_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+HOSTCXX = "/usr/bin/g++"
+
+CU_SOURCES = ["ntt_kernels.cu", "elementwise.cu", "capi.cu", "lincomb.cu", "samplers.cu", "bfv.cu"]
+CPP_SOURCES = ["tables.cpp", "rns_consts.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h"))] + \
+           [os.path.join(HERE, "..", "include", "fhe_b200.h")]
+
+
+def _stale(out, srcs):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, os.path.basename(src) + ".o")
+    if not _stale(obj, [src] + _deps()):
+        return obj
+    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        with open(obj + ".ptxas.log", "w") as f:
+            f.write(r.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = [os.path.join(CSRC, f) for f in CU_SOURCES + CPP_SOURCES if os.path.exists(os.path.join(CSRC, f))]
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    if force or _stale(LIB, objs):
+        cmd = [NVCC, "-shared", "-ccbin", HOSTCXX, "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,69 @@
+// Shared host-side plumbing of libfhe_b200.so: error reporting, the plan object, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../include/fhe_b200.h"
+#include "modarith.cuh"
+
+namespace fhe_b200 {
+
+void set_error(const char* fmt, ...);
+
+#define FHE_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            fhe_b200::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return FHE_B200_ECUDA;                                                                  \
+        }                                                                                           \
+    } while (0)
+
+#define FHE_REQUIRE(cond, ...)                                  \
+    do {                                                        \
+        if (!(cond)) { fhe_b200::set_error(__VA_ARGS__); return FHE_B200_EINVAL; } \
+    } while (0)
+
+#define FHE_TRY(expr)                       \
+    do { int rc__ = (expr); if (rc__ != 0) return rc__; } while (0)
+
+void count_launch();
+// checks the launch that has just been issued (and counts it)
+#define FHE_LAUNCH_CHECK() do { fhe_b200::count_launch(); FHE_CUDA(cudaGetLastError()); } while (0)
+
+// optional per-kernel event timing (fhe_b200_profile_enable)
+bool profile_on();
+void profile_begin(int kind, uint64_t units, cudaStream_t st);
+void profile_end(cudaStream_t st);
+
+}  // namespace fhe_b200
+
+// The plan: ring degree, moduli, device tables.  (C struct name = the opaque handle of the C ABI.)
+struct fhe_b200_plan {
+    uint32_t n = 0, logn = 0, limbs = 0;
+    int device = 0;
+    int hb = 16;                                   // lazy head-room (16: all q < 2^60, 8: all q < 2^61)
+    std::vector<uint64_t> moduli;
+    fhe_b200::Twiddle* d_fwd = nullptr;            // [limbs][n]
+    fhe_b200::Twiddle* d_inv = nullptr;            // [limbs][n]
+    fhe_b200::LimbParams* d_params = nullptr;      // [limbs]
+    std::vector<fhe_b200::LimbParams> h_params;
+    size_t chunk_bytes = 32u << 20;                // L2-resident working set between pass A and pass B
+    int sm_count = 148;
+    // host-buffer pipeline (lazy)
+    cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+    uint64_t* d_stage[3] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes = 0;
+};
+
+namespace fhe_b200 {
+// kernels/launchers implemented in ntt_kernels.cu / elementwise.cu
+int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t batch, uint32_t limb_begin,
+               uint32_t limb_count, bool inverse, cudaStream_t st);
+enum EwOp { EW_ADD = 0, EW_SUB, EW_MUL, EW_MAC, EW_MUL_SCALAR, EW_ADD_SCALAR, EW_NEG };
+int launch_elementwise(fhe_b200_plan* plan, EwOp op, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
+                       const uint64_t* d_c, uint32_t batch, uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
+int check_range(const fhe_b200_plan* plan, uint32_t batch, uint32_t limb_begin, uint32_t limb_count);
+}  // namespace fhe_b200

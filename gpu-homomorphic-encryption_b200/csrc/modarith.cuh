@@ -1,0 +1,150 @@
+// 64-bit modular arithmetic for the B200 RNS-NTT engine.
+//
+// Replaces the reference's 256-bit path on the per-limb hot loop:
+//   fhe::add_mod / sub_mod / mul_mod_montgomery   /root/reference/include/bigint.cuh:27-140
+//   fhe::ptx::* carry-chain wrappers              /root/reference/kernels/ptx_bigint.cuh:8-117
+//   fhe::ct_butterfly / gs_butterfly              /root/reference/include/ntt.cuh:147-167
+// with Shoup (precomputed-quotient) twiddle multiplication, Harvey-style lazy
+// butterflies and a 128->64 Barrett reduction.  All moduli are odd primes
+// below 2^61.
+//
+// Every function is __host__ __device__: the kernels are thin __global__
+// wrappers around these bodies, and tests/emul/ runs the very same bodies on
+// the CPU (thread by thread) so index maps can be validated without a GPU.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define FHE_HD __host__ __device__ __forceinline__
+#define FHE_D __device__ __forceinline__
+#define FHE_HDC __host__ __device__ constexpr
+#else
+#define FHE_HD inline
+#define FHE_D inline
+#define FHE_HDC constexpr
+#endif
+
+namespace fhe_b200 {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+// (w, floor(w * 2^64 / q)) -- one 128-bit load per twiddle
+struct alignas(16) Twiddle { u64 w, ws; };
+
+// per-limb constants, one 64-byte record per modulus
+struct alignas(64) LimbParams {
+    u64 q;        // modulus
+    u64 mu_hi;    // floor(2^128 / q) high word
+    u64 mu_lo;    // floor(2^128 / q) low word
+    u64 ninv;     // N^-1 mod q
+    u64 ninv_s;   // Shoup companion of ninv
+    u64 w1ninv;   // inv_tab[1] * N^-1 mod q (last inverse stage, bottom output)
+    u64 w1ninv_s; // its Shoup companion
+    u64 qbits;    // bit length of q
+};
+
+FHE_HD u64 mulhi64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+FHE_HD void mul128(u64 a, u64 b, u64& hi, u64& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b; hi = __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    lo = (u64)p; hi = (u64)(p >> 64);
+#endif
+}
+
+// acc(hi:lo) += a*b ; 128-bit wrap-around accumulate (callers guarantee no overflow)
+FHE_HD void mac128(u64& hi, u64& lo, u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    // one carry chain, one asm statement (the CC flag does not survive across statements)
+    asm("{\n\t"
+        ".reg .u64 pl, ph;\n\t"
+        "mul.lo.u64 pl, %2, %3;\n\t"
+        "mul.hi.u64 ph, %2, %3;\n\t"
+        "add.cc.u64 %0, %0, pl;\n\t"
+        "addc.u64 %1, %1, ph;\n\t"
+        "}"
+        : "+l"(lo), "+l"(hi) : "l"(a), "l"(b));
+#else
+    unsigned __int128 acc = ((unsigned __int128)hi << 64) | lo;
+    acc += (unsigned __int128)a * b;
+    lo = (u64)acc; hi = (u64)(acc >> 64);
+#endif
+}
+
+// (hi:lo) += (bh:bl)
+FHE_HD void add128(u64& hi, u64& lo, u64 bh, u64 bl) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(bl), "l"(bh));
+#else
+    unsigned __int128 acc = (((unsigned __int128)hi << 64) | lo) + (((unsigned __int128)bh << 64) | bl);
+    lo = (u64)acc; hi = (u64)(acc >> 64);
+#endif
+}
+
+// 192-bit accumulate: (a2:a1:a0) += (b1:b0)
+FHE_HD void add192(u64& a2, u64& a1, u64& a0, u64 b1, u64 b0) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, 0;"
+        : "+l"(a0), "+l"(a1), "+l"(a2) : "l"(b0), "l"(b1));
+#else
+    unsigned __int128 lo = ((unsigned __int128)a1 << 64) | a0;
+    unsigned __int128 s = lo + (((unsigned __int128)b1 << 64) | b0);
+    if (s < lo) a2++;
+    a0 = (u64)s; a1 = (u64)(s >> 64);
+#endif
+}
+
+// x - m if x >= m else x
+FHE_HD u64 csub(u64 x, u64 m) { return x >= m ? x - m : x; }
+
+FHE_HD u64 add_mod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
+FHE_HD u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+FHE_HD u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }
+
+// Shoup multiplication, lazy: returns x*w mod q + {0,q}, i.e. a value in [0, 2q).  Valid for ANY 64-bit x.
+FHE_HD u64 shoup_mul_lazy(u64 x, u64 w, u64 ws, u64 q) {
+    u64 h = mulhi64(x, ws);
+    return x * w - h * q;
+}
+FHE_HD u64 shoup_mul(u64 x, u64 w, u64 ws, u64 q) { return csub(shoup_mul_lazy(x, w, ws, q), q); }
+
+// (hi:lo) mod q for any 128-bit input; mu = floor(2^128/q), q < 2^63.
+// Quotient estimate from the three high partial products; it is low by at most 3, fixed by two conditional
+// subtractions (2q then q).  Needs 4q < 2^64.
+FHE_HD u64 barrett128(u64 hi, u64 lo, u64 q, u64 mu_hi, u64 mu_lo) {
+    // qhat = floor( (hi:lo) * (mu_hi:mu_lo) / 2^128 )  (low 64 bits are all that is needed)
+    u64 t1 = mulhi64(lo, mu_hi);
+    u64 t2 = mulhi64(hi, mu_lo);
+    // dropped: the fractional parts of the two cross terms and lo*mu_lo/2^128 (< 3 in total), and
+    // floor(x/q) - floor(x*mu/2^128) <= 1  ==>  0 <= floor(x/q) - qhat <= 3  ==>  r in [0, 4q)
+    u64 qhat = hi * mu_hi + t1 + t2;
+    u64 r = lo - qhat * q;
+    r = csub(r, 2 * q);
+    return csub(r, q);
+}
+
+FHE_HD u64 mul_mod(u64 a, u64 b, const LimbParams& P) {
+    u64 hi, lo;
+    mul128(a, b, hi, lo);
+    return barrett128(hi, lo, P.q, P.mu_hi, P.mu_lo);
+}
+
+// ---- counter-based generator shared (by specification) with oracle/orc_math.h ----
+FHE_HD u64 mix64(u64 z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+FHE_HD u64 rng_key(u64 seed, u64 stream) { return mix64(seed + 0x9E3779B97F4A7C15ULL * (stream + 1)); }
+FHE_HD u64 rng_at(u64 key, u64 idx) { return mix64(key + 0x9E3779B97F4A7C15ULL * (idx + 1)); }
+
+}  // namespace fhe_b200

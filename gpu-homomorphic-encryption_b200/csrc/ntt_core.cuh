@@ -1,0 +1,300 @@
+// Negacyclic NTT bodies for the B200 engine (host+device so tests/emul can run them on the CPU).
+//
+// Replaces /root/reference/kernels/ntt_kernels.cu:7-121 (ntt_forward/inverse_optimized_kernel, one
+// butterfly per thread per stage, 256-bit Montgomery, single block) and :140-161 (bit_reverse_kernel,
+// eliminated: forward leaves X[k] at position bitrev(k), inverse consumes that order).
+//
+// Decomposition of an N = 2^logN point transform of one limb (one modulus):
+//   pass A  "row pass"   : the first K1 = logN - LB stages (strides N/2 .. NB).  Registers only:
+//                          a thread owns V adjacent columns x 2^K1 rows (row stride NB = 2^LB elements).
+//   pass B  "tile pass"  : the remaining LB stages on each contiguous tile of NB elements, in shared
+//                          memory, as three register rounds of radix 16 / 16 / 2^(LB-8).
+//   N <= 4096 uses pass B alone (K1 = 0).  The inverse runs the mirror image (B' then A').
+//
+// Twiddle index of the butterfly group g at stage s (m = 2^s groups) is m + g in the bit-reversed
+// psi-power table (Twiddle{w, floor(w 2^64 / q)}); a tile with index b starts from "root" 2^K1 + b and every
+// sub-transform a thread performs is addressed as (root << v) + key.
+//
+// Lazy arithmetic: values live in [0, B*q) with the bound B tracked at compile time (all loops are
+// unrolled).  HB = floor(2^64 / q_max) rounded down to a power of two is the head-room (16 for q < 2^60).
+//   forward (CT):  X' = X + T, Y' = X + 2q - T with T = Shoup(Y) in [0,2q): the bound grows by 2 per stage; a
+//                  conditional subtraction of (HB/2) q is inserted only when B + 2 would exceed HB.
+//   inverse (GS):  X' = X + Y, Y' = Shoup(X + Bq - Y): the sum bound doubles; one conditional subtraction
+//                  per butterfly once 2B would exceed HB/2 (i.e. Harvey's rule, but skipped while there is room).
+#pragma once
+#include "modarith.cuh"
+
+namespace fhe_b200 {
+
+FHE_HD Twiddle ld_tw(const Twiddle* p) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    Twiddle t; t.w = v.x; t.ws = v.y; return t;
+#else
+    return *p;
+#endif
+}
+
+// shared-memory swizzle: 128-byte rows of 16 elements, 16-byte chunk index XOR (row & 7)
+FHE_HD u32 swz(u32 idx) { return idx ^ (((idx >> 4) & 7u) << 1); }
+
+// 16-byte (two element) accesses; p must be 16-byte aligned
+FHE_HD void ld2(const u64* p, u64& a, u64& b) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+FHE_HD void st2(u64* p, u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
+FHE_HDC int fwd_bound_after(int B, int stages, int HB) {
+    for (int i = 0; i < stages; i++) { if (B + 2 > HB) B = HB / 2; B += 2; }
+    return B;
+}
+FHE_HDC int inv_bound_after(int B, int stages, int HB) {
+    for (int i = 0; i < stages; i++) { B = 2 * B; if (2 * B > HB) B = B / 2; }
+    return B;
+}
+
+// ---- forward stages on a register array of E = 2^LE elements: R stages, active bits = low R bits of e ----
+// B (template) is the bound on entry in units of q; the bound on exit is fwd_bound_after(B, R, HB).
+// Compile-time recursion over the stage index V keeps every array index and every bound a constant.
+template <int LE, int R, int HB, int B, int V = 0>
+FHE_HD void fwd_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, u64 q) {
+    if constexpr (V < R) {
+        constexpr int st = 1 << (R - 1 - V);
+        constexpr int sh = LE - R + V;
+        constexpr bool red = (B + 2 > HB);
+        const u64 twoq = 2 * q;
+        const u64 hq = (u64)(HB / 2) * q;
+#pragma unroll
+        for (int key = 0; key < (1 << sh); key++) {
+            const Twiddle w = ld_tw(tw + ((root << sh) + key));
+#pragma unroll
+            for (int j = 0; j < st; j++) {
+                const int e = (key << (R - V)) | j;
+                u64 X = x[e];
+                if (red) X = csub(X, hq);
+                const u64 T = shoup_mul_lazy(x[e + st], w.w, w.ws, q);
+                x[e] = X + T;
+                x[e + st] = X + twoq - T;
+            }
+        }
+        fwd_stages<LE, R, HB, (red ? HB / 2 : B) + 2, V + 1>(x, tw, root, q);
+    }
+}
+
+// ---- inverse stages (mirror order: V runs R-1 .. 0).  LAST: the final stage of the whole transform folds N^-1 in.
+// exit bound: inv_bound_after(B, R, HB), or 2 when LAST.
+template <int LE, int R, int HB, bool LAST, int B, int V = R - 1>
+FHE_HD void inv_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, const LimbParams& P) {
+    if constexpr (V >= 0) {
+        constexpr int st = 1 << (R - 1 - V);
+        constexpr int sh = LE - R + V;
+        constexpr bool last = LAST && (V == 0);
+        constexpr bool red = !last && (4 * B > HB);
+        const u64 q = P.q;
+        const u64 bq = (u64)B * q;
+#pragma unroll
+        for (int key = 0; key < (1 << sh); key++) {
+            Twiddle w;
+            if (last) { w.w = P.w1ninv; w.ws = P.w1ninv_s; }
+            else w = ld_tw(tw + ((root << sh) + key));
+#pragma unroll
+            for (int j = 0; j < st; j++) {
+                const int e = (key << (R - V)) | j;
+                const u64 X = x[e], Y = x[e + st];
+                u64 S = X + Y;
+                const u64 D = X + bq - Y;
+                if (last) S = shoup_mul_lazy(S, P.ninv, P.ninv_s, q);
+                else if (red) S = csub(S, bq);
+                x[e] = S;
+                x[e + st] = shoup_mul_lazy(D, w.w, w.ws, q);
+            }
+        }
+        inv_stages<LE, R, HB, LAST, (red ? B : 2 * B), V - 1>(x, tw, root, P);
+    }
+}
+
+// bring a value bounded by B*q into [0, q)
+template <int HB, int B>
+FHE_HD u64 normalize(u64 x, u64 q) {
+    if (HB >= 16 && B > 8) x = csub(x, 8 * q);
+    if (HB >= 8 && B > 4) x = csub(x, 4 * q);
+    if (B > 2) x = csub(x, 2 * q);
+    if (B > 1) x = csub(x, q);
+    return x;
+}
+
+// =====================================================================================================
+// pass B, forward: one CTA (NT = 2^(LB-4) threads) per tile of NB = 2^LB contiguous elements.
+// Split into phases separated by a block barrier; phase functions are what the emulator calls.
+//   g    : tile base in global memory (in place)
+//   s    : NB u64 of shared memory
+//   root : 2^K1 + tile index within the limb
+//   B0   : entry bound (1 + 2*K1 after pass A, 1 when K1 = 0)
+// =====================================================================================================
+template <int LB, int HB>
+struct TileFwd {
+    static constexpr int NB = 1 << LB;
+    static constexpr int NT = NB / 16;
+    static constexpr int R3 = LB - 8;
+    static_assert(LB >= 9 && LB <= 12, "tile pass supports 512..4096 elements");
+
+    template <int B0>
+    static FHE_HD void phase1(u32 tid, const u64* g, u64* s, const Twiddle* tw, u32 root, u64 q) {
+        u64 x[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = g[(e << (LB - 4)) | tid];
+        fwd_stages<4, 4, HB, B0>(x, tw, root, q);
+#pragma unroll
+        for (int e = 0; e < 16; e++) s[swz((e << (LB - 4)) | tid)] = x[e];
+    }
+    template <int B0>
+    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* tw, u32 root, u64 q) {
+        const u32 lo = tid & ((1u << (LB - 8)) - 1), hi = tid >> (LB - 8);
+        const u32 base = (hi << (LB - 4)) | lo;
+        u64 x[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = s[swz(base | (e << (LB - 8)))];
+        fwd_stages<4, 4, HB, fwd_bound_after(B0, 4, HB)>(x, tw, (root << 4) + hi, q);
+#pragma unroll
+        for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
+    }
+    template <int B0>
+    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* tw, u32 root, u64 q) {
+        u64 x[16];
+        const u32 row = tid << 4;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u32 a = row | ((k ^ (tid & 7)) << 1);
+            ld2(s + a, x[2 * k], x[2 * k + 1]);
+        }
+        constexpr int B3 = fwd_bound_after(B0, 8, HB);
+        constexpr int BE = fwd_bound_after(B3, R3, HB);
+        fwd_stages<4, R3, HB, B3>(x, tw, (root << (4 + R3)) + tid, q);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u32 a = row | ((k ^ (tid & 7)) << 1);
+            st2(s + a, normalize<HB, BE>(x[2 * k], q), normalize<HB, BE>(x[2 * k + 1], q));
+        }
+    }
+    // coalesced 16-byte copy-out of the swizzled tile
+    static FHE_HD void phase4(u32 tid, u64* g, const u64* s) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 c = tid + i * NT;                       // logical 16-byte chunk
+            const u32 p = ((c >> 3) << 3) | ((c & 7) ^ ((c >> 3) & 7));
+            u64 a, b; ld2(s + 2 * p, a, b); st2(g + 2 * c, a, b);
+        }
+    }
+};
+
+// pass B', inverse: mirror image.  phase1 = coalesced copy-in, phase2 = low strides (16 contiguous per thread),
+// phase3 = middle, phase4 = high strides + store.  LAST: K1 == 0, i.e. this tile pass ends the transform.
+template <int LB, int HB>
+struct TileInv {
+    static constexpr int NB = 1 << LB;
+    static constexpr int NT = NB / 16;
+    static constexpr int R3 = LB - 8;
+    static_assert(LB >= 9 && LB <= 12, "tile pass supports 512..4096 elements");
+
+    static FHE_HD void phase1(u32 tid, const u64* g, u64* s) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 c = tid + i * NT;
+            const u32 p = ((c >> 3) << 3) | ((c & 7) ^ ((c >> 3) & 7));
+            u64 a, b; ld2(g + 2 * c, a, b); st2(s + 2 * p, a, b);
+        }
+    }
+    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* tw, u32 root, const LimbParams& P) {
+        u64 x[16];
+        const u32 row = tid << 4;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u32 a = row | ((k ^ (tid & 7)) << 1);
+            ld2(s + a, x[2 * k], x[2 * k + 1]);
+        }
+        inv_stages<4, R3, HB, false, 1>(x, tw, (root << (4 + R3)) + tid, P);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u32 a = row | ((k ^ (tid & 7)) << 1);
+            st2(s + a, x[2 * k], x[2 * k + 1]);
+        }
+    }
+    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* tw, u32 root, const LimbParams& P) {
+        const u32 lo = tid & ((1u << (LB - 8)) - 1), hi = tid >> (LB - 8);
+        const u32 base = (hi << (LB - 4)) | lo;
+        u64 x[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = s[swz(base | (e << (LB - 8)))];
+        inv_stages<4, 4, HB, false, inv_bound_after(1, R3, HB)>(x, tw, (root << 4) + hi, P);
+#pragma unroll
+        for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
+    }
+    template <bool LAST>
+    static FHE_HD void phase4(u32 tid, u64* g, const u64* s, const Twiddle* tw, u32 root, const LimbParams& P) {
+        u64 x[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = s[swz((e << (LB - 4)) | tid)];
+        inv_stages<4, 4, HB, LAST, inv_bound_after(1, R3 + 4, HB)>(x, tw, root, P);
+        // LAST: fully reduce.  Otherwise leave the lazy bound for pass A' (it starts from out_bound()).
+#pragma unroll
+        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? csub(x[e], P.q) : x[e];
+    }
+    static FHE_HDC int out_bound() { return inv_bound_after(1, LB, HB); }
+};
+
+// =====================================================================================================
+// pass A (forward) / A' (inverse): 2^K1 rows x V adjacent columns per thread, registers only.
+//   g : limb base, col : first column of this thread, row stride = NB elements (V is 1 or 2)
+// =====================================================================================================
+template <int K1, int V, int LB, int HB>
+struct RowPass {
+    static constexpr int NA = 1 << K1;
+    static constexpr int NB = 1 << LB;
+
+    static FHE_HD void forward(u64* gout, const u64* gin, u32 col, const Twiddle* tw, u64 q) {
+        u64 x[V][NA];
+#pragma unroll
+        for (int r = 0; r < NA; r++) {
+            if (V == 2) ld2(gin + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
+            else x[0][r] = gin[(size_t)r * NB + col];
+        }
+#pragma unroll
+        for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, 1>(x[c], tw, 1u, q);
+#pragma unroll
+        for (int r = 0; r < NA; r++) {
+            if (V == 2) st2(gout + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
+            else gout[(size_t)r * NB + col] = x[0][r];
+        }
+    }
+    static FHE_HDC int fwd_out_bound() { return fwd_bound_after(1, K1, HB); }
+
+    template <int B0>
+    static FHE_HD void inverse(u64* g, u32 col, const Twiddle* tw, const LimbParams& P) {
+        u64 x[V][NA];
+#pragma unroll
+        for (int r = 0; r < NA; r++) {
+            if (V == 2) ld2(g + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
+            else x[0][r] = g[(size_t)r * NB + col];
+        }
+#pragma unroll
+        for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, true, B0>(x[c], tw, 1u, P);
+#pragma unroll
+        for (int r = 0; r < NA; r++) {
+            if (V == 2) st2(g + (size_t)r * NB + col, csub(x[0][r], P.q), csub(x[V - 1][r], P.q));
+            else g[(size_t)r * NB + col] = csub(x[0][r], P.q);
+        }
+    }
+};
+
+}  // namespace fhe_b200

@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's operator interface over the C ABI (harness; torch is plumbing).
+
+Mirrors, with the same method names and argument meaning (device buffers in, device buffers out, in-place
+transforms, asynchronous on a stream):
+    fhe::NTTEngine       /root/reference/include/ntt.cuh:72-103
+    fhe::RNS_NTTEngine   /root/reference/include/ntt.cuh:106-137
+    fhe::PolynomialOps   /root/reference/include/polynomial.cuh:21-59
+    fhe::RNSContext      /root/reference/include/rns.cuh:27-65
+    fhe::FHEContext      /root/reference/include/fhe.cuh:78-148   (BfvContext)
+Device arrays are torch int64 CUDA tensors used as containers for uint64 words, limb-major [batch][limbs][N].
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import check, load_library, u64p
+
+
+def _np_u64(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+def _ptr(t: torch.Tensor) -> int:
+    assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous(), "expected a contiguous int64 CUDA tensor"
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_device(a: np.ndarray, device=None) -> torch.Tensor:
+    """uint64 numpy array -> int64 CUDA tensor (same bits)."""
+    a = _np_u64(a)
+    return torch.from_numpy(a.view(np.int64)).to(device or "cuda", non_blocking=False)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def pinned_empty(shape) -> np.ndarray:
+    """page-locked uint64 host buffer (numpy view of a pinned torch tensor, kept alive by the view's base)."""
+    t = torch.empty(shape, dtype=torch.int64, pin_memory=True)
+    a = t.numpy().view(np.uint64)
+    return a
+
+
+def gaussian_cdt(sigma: float) -> np.ndarray:
+    buf = np.zeros(128, dtype=np.uint64)
+    ln = load_library().fhe_b200_gaussian_cdt(float(sigma), buf.ctypes.data_as(u64p), 128)
+    if ln < 0:
+        check(ln)
+    return buf[:ln].copy()
+
+
+class Plan:
+    """fhe_b200_plan: ring degree N, RNS moduli, device twiddle tables."""
+
+    def __init__(self, n: int, moduli, device: int = 0):
+        self.lib = load_library()
+        self.n = int(n)
+        self.moduli = [int(m) for m in moduli]
+        self.device = device
+        m = _np_u64(self.moduli)
+        h = C.c_void_p()
+        check(self.lib.fhe_b200_plan_create(self.n, m.ctypes.data_as(u64p), len(self.moduli), device, C.byref(h)))
+        self.h = h
+        self.torch_device = torch.device("cuda", device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fhe_b200_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- shape helpers: tensors are [batch, limb_count, N] (batch may be omitted)
+    def _dims(self, t: torch.Tensor, limb_count):
+        assert t.shape[-1] == self.n, f"last dimension must be N={self.n}"
+        total = t.numel() // self.n
+        lc = limb_count if limb_count is not None else (t.shape[-2] if t.dim() >= 2 else 1)
+        assert total % lc == 0
+        return total // lc, lc
+
+    def tables(self, limb: int):
+        out = [np.zeros(self.n, dtype=np.uint64) for _ in range(4)]
+        check(self.lib.fhe_b200_plan_tables(self.h, limb, *[o.ctypes.data_as(u64p) for o in out]))
+        return out
+
+    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None, limb_begin=0, limb_count=None):
+        out = x if out is None else out
+        b, lc = self._dims(x, limb_count)
+        check(self.lib.fhe_b200_ntt_forward(self.h, _ptr(out), _ptr(x), b, limb_begin, lc, _stream()))
+        return out
+
+    def inverse(self, x: torch.Tensor, out: torch.Tensor | None = None, limb_begin=0, limb_count=None):
+        out = x if out is None else out
+        b, lc = self._dims(x, limb_count)
+        check(self.lib.fhe_b200_ntt_inverse(self.h, _ptr(out), _ptr(x), b, limb_begin, lc, _stream()))
+        return out
+
+    def negacyclic_mul(self, a, b, out=None, limb_begin=0, limb_count=None):
+        out = torch.empty_like(a) if out is None else out
+        bt, lc = self._dims(a, limb_count)
+        check(self.lib.fhe_b200_negacyclic_mul(self.h, _ptr(out), _ptr(a), _ptr(b), bt, limb_begin, lc, _stream()))
+        return out
+
+    def bitrev_permute(self, x):
+        out = torch.empty_like(x)
+        check(self.lib.fhe_b200_bitrev_permute(self.h, _ptr(out), _ptr(x), x.numel() // self.n, _stream()))
+        return out
+
+    def _ew(self, fn, a, b, out, limb_begin, limb_count):
+        out = torch.empty_like(a) if out is None else out
+        bt, lc = self._dims(a, limb_count)
+        check(getattr(self.lib, fn)(self.h, _ptr(out), _ptr(a), _ptr(b), bt, limb_begin, lc, _stream()))
+        return out
+
+    def add(self, a, b, out=None, limb_begin=0, limb_count=None): return self._ew("fhe_b200_poly_add", a, b, out, limb_begin, limb_count)
+    def sub(self, a, b, out=None, limb_begin=0, limb_count=None): return self._ew("fhe_b200_poly_sub", a, b, out, limb_begin, limb_count)
+    def mul(self, a, b, out=None, limb_begin=0, limb_count=None): return self._ew("fhe_b200_poly_mul", a, b, out, limb_begin, limb_count)
+
+    def mac(self, acc, a, b, out=None, limb_begin=0, limb_count=None):
+        out = torch.empty_like(a) if out is None else out
+        bt, lc = self._dims(a, limb_count)
+        check(self.lib.fhe_b200_poly_mac(self.h, _ptr(out), _ptr(acc), _ptr(a), _ptr(b), bt, limb_begin, lc, _stream()))
+        return out
+
+    def _scalar(self, fn, a, scalars, out, limb_begin, limb_count):
+        out = torch.empty_like(a) if out is None else out
+        bt, lc = self._dims(a, limb_count)
+        s = _np_u64([int(v) % self.moduli[limb_begin + i] for i, v in enumerate(scalars)])
+        assert len(s) == lc
+        check(getattr(self.lib, fn)(self.h, _ptr(out), _ptr(a), s.ctypes.data_as(u64p), bt, limb_begin, lc, _stream()))
+        return out
+
+    def mul_scalar(self, a, scalars, out=None, limb_begin=0, limb_count=None):
+        return self._scalar("fhe_b200_poly_mul_scalar", a, scalars, out, limb_begin, limb_count)
+
+    def add_scalar(self, a, scalars, out=None, limb_begin=0, limb_count=None):
+        return self._scalar("fhe_b200_poly_add_scalar", a, scalars, out, limb_begin, limb_count)
+
+    def negate(self, a, out=None, limb_begin=0, limb_count=None):
+        out = torch.empty_like(a) if out is None else out
+        bt, lc = self._dims(a, limb_count)
+        check(self.lib.fhe_b200_poly_negate(self.h, _ptr(out), _ptr(a), bt, limb_begin, lc, _stream()))
+        return out
+
+    def modswitch_drop_last(self, x, limb_begin=0, limb_count=None):
+        bt, lc = self._dims(x, limb_count)
+        out = torch.empty(x.shape[:-2] + (lc - 1, self.n), dtype=torch.int64, device=x.device)
+        check(self.lib.fhe_b200_modswitch_drop_last(self.h, _ptr(out), _ptr(x), bt, limb_begin, lc, _stream()))
+        return out
+
+    def ntt_host(self, h: np.ndarray, direction: int, limb_begin=0, limb_count=None):
+        """host-buffer entry point (e2e path): h is uint64 [batch][limb_count][N], transformed in place."""
+        assert h.dtype == np.uint64 and h.flags.c_contiguous
+        lc = limb_count if limb_count is not None else h.shape[-2]
+        bt = h.size // (lc * self.n)
+        check(self.lib.fhe_b200_ntt_host(self.h, h.ctypes.data_as(C.c_void_p), bt, limb_begin, lc, direction))
+        return h
+
+
+# ---- fhe::uint256_t edge --------------------------------------------------------------------------------------
+def unpack_u256(d_u256: torch.Tensor) -> torch.Tensor:
+    """[count][4] int64 (uint256_t words) -> [count] int64 (limbs[0])."""
+    count = d_u256.numel() // 4
+    out = torch.empty(count, dtype=torch.int64, device=d_u256.device)
+    check(load_library().fhe_b200_unpack_u256(_ptr(out), _ptr(d_u256), count, _stream()))
+    return out
+
+
+def pack_u256(d: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(d.numel(), 4, dtype=torch.int64, device=d.device)
+    check(load_library().fhe_b200_pack_u256(_ptr(out), _ptr(d), d.numel(), _stream()))
+    return out
+
+
+class NTTEngine:
+    """fhe::NTTEngine(polynomial_degree, modulus): single-modulus transforms on device arrays of N uint64."""
+
+    def __init__(self, polynomial_degree: int, modulus: int, device: int = 0):
+        self.plan = Plan(polynomial_degree, [modulus], device)
+        self.n = polynomial_degree
+
+    def forward(self, d_data: torch.Tensor): return self.plan.forward(d_data.view(-1, 1, self.n)).view_as(d_data)
+    def inverse(self, d_data: torch.Tensor): return self.plan.inverse(d_data.view(-1, 1, self.n)).view_as(d_data)
+
+    def multiply(self, d_result, d_a, d_b):
+        self.plan.negacyclic_mul(d_a.view(-1, 1, self.n), d_b.view(-1, 1, self.n), out=d_result.view(-1, 1, self.n))
+        return d_result
+
+    def forward_batch(self, d_data, batch_size):
+        assert d_data.numel() == batch_size * self.n
+        return self.forward(d_data)
+
+    def inverse_batch(self, d_data, batch_size):
+        assert d_data.numel() == batch_size * self.n
+        return self.inverse(d_data)
+
+
+class RNS_NTTEngine:
+    """fhe::RNS_NTTEngine(polynomial_degree, rns_moduli, num_primes): limb-major d_rns_data[i*N + j]."""
+
+    def __init__(self, polynomial_degree: int, rns_moduli, device: int = 0):
+        self.plan = Plan(polynomial_degree, rns_moduli, device)
+        self.n = polynomial_degree
+        self.num_primes = len(self.plan.moduli)
+
+    def _v(self, t): return t.view(-1, self.num_primes, self.n)
+    def forward_rns(self, d_rns_data): self.plan.forward(self._v(d_rns_data)); return d_rns_data
+    def inverse_rns(self, d_rns_data): self.plan.inverse(self._v(d_rns_data)); return d_rns_data
+
+    def multiply_rns(self, d_result, d_a, d_b):
+        self.plan.negacyclic_mul(self._v(d_a), self._v(d_b), out=self._v(d_result))
+        return d_result
+
+    def to_rns(self, d_u256: torch.Tensor) -> torch.Tensor:
+        """d_u256: [N][4] words of 256-bit coefficients -> [num_primes][N] residues."""
+        count = d_u256.numel() // 4
+        out = torch.empty(self.num_primes, count, dtype=torch.int64, device=d_u256.device)
+        check(self.plan.lib.fhe_b200_to_rns_u256(self.plan.h, _ptr(out), _ptr(d_u256), count, 0, self.num_primes, _stream()))
+        return out
+
+
+class PolynomialOps:
+    """fhe::PolynomialOps over one plan (any number of limbs)."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+
+    def add(self, result, a, b): return self.plan.add(a, b, out=result)
+    def sub(self, result, a, b): return self.plan.sub(a, b, out=result)
+    def mul_ntt(self, result, a, b): return self.plan.negacyclic_mul(a, b, out=result)
+    mul = mul_ntt
+    mul_negacyclic = mul_ntt
+    def mul_scalar(self, result, a, scalar): return self.plan.mul_scalar(a, [scalar] * a.shape[-2], out=result)
+    def add_scalar(self, result, a, scalar): return self.plan.add_scalar(a, [scalar] * a.shape[-2], out=result)
+
+
+class LinComb:
+    """fhe_b200_lincomb: exact RNS base conversion / scale-and-round."""
+
+    def __init__(self, handle, S, T):
+        self.h, self.S, self.T = handle, S, T
+        self.lib = load_library()
+
+    @classmethod
+    def conv(cls, src, dst, device=0):
+        s, d = _np_u64(src), _np_u64(dst)
+        h = C.c_void_p()
+        check(load_library().fhe_b200_lincomb_create_conv(s.ctypes.data_as(u64p), len(s), d.ctypes.data_as(u64p), len(d),
+                                                          device, C.byref(h)))
+        return cls(h, len(s), len(d))
+
+    @classmethod
+    def scale(cls, qs, ps, t, targets, with_extra, device=0):
+        q, tg = _np_u64(qs), _np_u64(targets)
+        p = _np_u64(ps) if len(ps) else np.zeros(1, dtype=np.uint64)
+        h = C.c_void_p()
+        check(load_library().fhe_b200_lincomb_create_scale(q.ctypes.data_as(u64p), len(q), p.ctypes.data_as(u64p), len(ps),
+                                                           int(t), tg.ctypes.data_as(u64p), len(tg), int(with_extra),
+                                                           device, C.byref(h)))
+        return cls(h, len(q), len(tg))
+
+    def constants(self):
+        S, T = self.S, self.T
+        arr = dict(pre=np.zeros(S, np.uint64), th_hi=np.zeros(S, np.uint64), th_lo=np.zeros(S, np.uint64),
+                   M=np.zeros(S * T, np.uint64), c=np.zeros(T, np.uint64), lam=np.zeros(T, np.uint64))
+        check(self.lib.fhe_b200_lincomb_constants(self.h, *[a.ctypes.data_as(u64p) for a in arr.values()]))
+        arr["M"] = arr["M"].reshape(S, T)
+        return arr
+
+    def apply(self, x: torch.Tensor, extra: torch.Tensor | None = None) -> torch.Tensor:
+        n = x.shape[-1]
+        batch = x.numel() // (self.S * n)
+        out = torch.empty(x.shape[:-2] + (self.T, n), dtype=torch.int64, device=x.device)
+        check(self.lib.fhe_b200_lincomb_apply(self.h, _ptr(out), _ptr(x), _ptr(extra) if extra is not None else None,
+                                              n, batch, _stream()))
+        return out
+
+    def __del__(self):
+        try:
+            self.lib.fhe_b200_lincomb_destroy(self.h)
+        except Exception:
+            pass
+
+
+class RNSContext:
+    """fhe::RNSContext(primes): RNS arithmetic on limb-major residues [num_primes][count]."""
+
+    def __init__(self, primes, n: int, device: int = 0):
+        self.plan = Plan(n, primes, device)
+        self.primes = self.plan.moduli
+
+    def num_primes(self): return len(self.primes)
+    def add_rns(self, result, a, b): return self.plan.add(a, b, out=result)
+    def sub_rns(self, result, a, b): return self.plan.sub(a, b, out=result)
+    def mul_rns(self, result, a, b): return self.plan.mul(a, b, out=result)
+    def mod_switch_rns(self, x): return self.plan.modswitch_drop_last(x)
+
+    def base_extend(self, x, target_primes):
+        lc = LinComb.conv(self.primes, target_primes, self.plan.device)
+        return lc.apply(x)
+
+
+class BfvContext:
+    """fhe::FHEContext on RNS (BFV).  primes = Q (L) then auxiliary basis (R); P = first K auxiliary primes."""
+
+    def __init__(self, n, L, R, K, dnum, t, primes, sigma=3.2, hamming_weight=64, device=0):
+        self.lib = load_library()
+        self.n, self.L, self.R, self.K, self.dnum, self.t = n, L, R, K, dnum, t
+        p = _np_u64(primes)
+        assert len(p) == L + R
+        h = C.c_void_p()
+        check(self.lib.fhe_b200_bfv_create(n, L, R, K, dnum, int(t), p.ctypes.data_as(u64p), float(sigma),
+                                           int(hamming_weight), device, C.byref(h)))
+        self.h = h
+        self.dev = torch.device("cuda", device)
+
+    def _empty(self, *shape): return torch.empty(shape, dtype=torch.int64, device=self.dev)
+
+    def keygen(self, seed_sk, seed_pk):
+        sk = self._empty(self.L + self.R, self.n); pk = self._empty(2, self.L, self.n)
+        check(self.lib.fhe_b200_bfv_keygen(self.h, seed_sk, seed_pk, _ptr(sk), _ptr(pk), _stream()))
+        return sk, pk
+
+    def relinkey_gen(self, seed, sk):
+        rlk = self._empty(self.dnum, 2, self.L + self.K, self.n)
+        check(self.lib.fhe_b200_bfv_relinkeygen(self.h, seed, _ptr(sk), _ptr(rlk), _stream()))
+        return rlk
+
+    def encode(self, values) -> torch.Tensor:
+        pt = np.zeros(self.n, dtype=np.uint64)
+        v = np.asarray(values, dtype=np.uint64)[: self.n]
+        pt[: v.size] = v % np.uint64(self.t)
+        return to_device(pt, self.dev)
+
+    def decode(self, pt: torch.Tensor): return to_host(pt)
+
+    def encrypt(self, seed, pt, pk):
+        batch = pt.numel() // self.n
+        ct = self._empty(batch, 2, self.L, self.n)
+        check(self.lib.fhe_b200_bfv_encrypt(self.h, seed, _ptr(pt), _ptr(pk), _ptr(ct), batch, _stream()))
+        return ct
+
+    def decrypt(self, ct, sk):
+        batch = ct.numel() // (2 * self.L * self.n)
+        pt = self._empty(batch, self.n)
+        check(self.lib.fhe_b200_bfv_decrypt(self.h, _ptr(ct), _ptr(sk), _ptr(pt), batch, _stream()))
+        return pt
+
+    def add(self, a, b):
+        out = torch.empty_like(a)
+        check(self.lib.fhe_b200_bfv_add(self.h, _ptr(a), _ptr(b), _ptr(out), a.numel() // (2 * self.L * self.n), _stream()))
+        return out
+
+    def multiply(self, a, b, rlk, want_scaled=False, out=None):
+        batch = a.numel() // (2 * self.L * self.n)
+        out = torch.empty_like(a) if out is None else out
+        sc = self._empty(batch, 3, self.L, self.n) if want_scaled else None
+        check(self.lib.fhe_b200_bfv_multiply_relin(self.h, _ptr(a), _ptr(b), _ptr(rlk), _ptr(out),
+                                                   _ptr(sc) if want_scaled else None, batch, _stream()))
+        return (out, sc) if want_scaled else out
+
+    def multiply_host(self, h_a: np.ndarray, h_b: np.ndarray, rlk, h_out: np.ndarray):
+        batch = h_a.size // (2 * self.L * self.n)
+        check(self.lib.fhe_b200_bfv_multiply_relin_host(self.h, h_a.ctypes.data_as(C.c_void_p), h_b.ctypes.data_as(C.c_void_p),
+                                                        _ptr(rlk), h_out.ctypes.data_as(C.c_void_p), batch))
+        return h_out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fhe_b200_bfv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

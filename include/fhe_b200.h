@@ -1,0 +1,184 @@
+/*
+ * fhe_b200.h -- C ABI of the B200-native RNS-NTT polynomial-arithmetic engine (libfhe_b200.so).
+ *
+ * This is the drop-in boundary for the hot path under fhe::FHEContext multiply / relinearize / encrypt of
+ * codebasecomprehension987/gpu-homomorphic-encryption.  The reference has no FFI layer (it is a C++ static
+ * library, CMakeLists.txt:29-30); each entry point below names the reference interface it replaces.  The
+ * compat C++ headers in include/fhe/ re-implement the reference's fhe:: classes purely on top of this file.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FHE_B200_E* code on failure; fhe_b200_last_error() gives
+ *     the message for the calling thread.  Nothing throws, no C++ type crosses the boundary.
+ *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are host pointers.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is asynchronous on that stream.
+ *   - polynomial layout is limb-major uint64_t [batch][limb_count][N]; limb l of every polynomial is reduced
+ *     modulo plan.moduli[limb_begin + l]; values are canonical residues in [0, q) at every call boundary.
+ *   - NTT-domain order: forward leaves X[k] = sum_j a_j psi^(j(2k+1)) at position bitrev(k); inverse consumes
+ *     that order.  Pointwise operations are order-agnostic.  fhe_b200_bitrev_permute converts to natural order.
+ *   - a plan (and a BFV context) must not be used from two host threads at once (the reference documents the
+ *     same rule, docs/API_REFERENCE.md:600-606).
+ *   - there is no CPU fallback: every entry point needs a CUDA device of compute capability 10.0.
+ */
+#ifndef FHE_B200_H
+#define FHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FHE_B200_OK 0
+#define FHE_B200_EINVAL (-1)   /* bad argument (N not a power of two in [512, 131072], modulus not NTT friendly, ...) */
+#define FHE_B200_ECUDA (-2)    /* a CUDA runtime call failed */
+#define FHE_B200_ENOMEM (-3)
+#define FHE_B200_ESTATE (-4)   /* object used in the wrong state */
+
+typedef struct fhe_b200_plan fhe_b200_plan;
+typedef struct fhe_b200_lincomb fhe_b200_lincomb;
+typedef struct fhe_b200_bfv fhe_b200_bfv;
+
+const char* fhe_b200_last_error(void);
+int fhe_b200_version(void);
+/* number of kernels this library has launched in this process (all threads) */
+uint64_t fhe_b200_launch_count(void);
+/* per-kernel timing for the roofline report: while enabled, every NTT kernel launch is bracketed by CUDA events
+ * on its own stream.  kind: 0 = tile pass (forward), 1 = tile pass (inverse), 2 = row pass (forward), 3 = row pass
+ * (inverse).  profile_read synchronises the recorded events and returns launches, total milliseconds and the
+ * limb-transforms those launches covered. */
+int fhe_b200_profile_enable(int on);
+int fhe_b200_profile_read(int kind, uint64_t* launches, double* total_ms, uint64_t* limb_transforms);
+
+/* ---- plan: N, the RNS moduli and their device-resident twiddle tables ------------------------------------
+ * replaces NTTEngine::NTTEngine / precompute_twiddle_factors / find_primitive_root / mod_inverse
+ * (src/ntt.cu:7-22,77-119) and RNS_NTTEngine::RNS_NTTEngine (src/ntt.cu:122-141).
+ * Every modulus must be an odd prime < 2^61 with q = 1 (mod 2N). */
+int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32_t n_limbs, int device, fhe_b200_plan** out);
+int fhe_b200_plan_destroy(fhe_b200_plan* plan);
+uint32_t fhe_b200_plan_n(const fhe_b200_plan* plan);
+uint32_t fhe_b200_plan_limbs(const fhe_b200_plan* plan);
+int fhe_b200_plan_moduli(const fhe_b200_plan* plan, uint64_t* h_out);
+/* copies limb `limb`'s tables to the host: w[N] and shoup[N] for each direction (for parity tests) */
+int fhe_b200_plan_tables(const fhe_b200_plan* plan, uint32_t limb, uint64_t* h_fwd, uint64_t* h_fwd_shoup,
+                         uint64_t* h_inv, uint64_t* h_inv_shoup);
+
+/* ---- transforms -------------------------------------------------------------------------------------------
+ * replaces NTTEngine::forward / inverse / forward_batch / inverse_batch (src/ntt.cu:30-47, include/ntt.cuh:87-88),
+ * RNS_NTTEngine::forward_rns / inverse_rns (src/ntt.cu:158-171) and the kernels in kernels/ntt_kernels.cu.
+ * d_out may equal d_in (in place).  Layout [batch][limb_count][N]. */
+int fhe_b200_ntt_forward(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t batch,
+                         uint32_t limb_begin, uint32_t limb_count, void* stream);
+int fhe_b200_ntt_inverse(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t batch,
+                         uint32_t limb_begin, uint32_t limb_count, void* stream);
+/* out = a * b in Z_q[x]/(x^N+1) per limb, coefficient form in and out.
+ * replaces NTTEngine::multiply (src/ntt.cu:49-75), RNS_NTTEngine::multiply_rns (include/ntt.cuh:123-126),
+ * PolynomialOps::mul_ntt / mul_negacyclic (src/polynomial.cu:54-58, include/polynomial.cuh:36-39). */
+int fhe_b200_negacyclic_mul(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
+                            uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+/* out[bitrev(k)] = in[k] per limb (out != in) -- the job of bit_reverse_kernel (kernels/ntt_kernels.cu:140-161),
+ * only needed by callers that want natural-order NTT values. */
+int fhe_b200_bitrev_permute(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t n_polys,
+                            void* stream);
+/* host-buffer variant: copies h_data (pinned or pageable) to the device in pipelined chunks, transforms, copies
+ * back.  direction: 0 forward, 1 inverse, 2 forward then inverse.  Synchronous. */
+int fhe_b200_ntt_host(fhe_b200_plan* plan, uint64_t* h_data, uint32_t batch, uint32_t limb_begin,
+                      uint32_t limb_count, int direction);
+
+/* ---- element-wise ------------------------------------------------------------------------------------------
+ * replaces poly_add / poly_sub / poly_mul_scalar kernels (src/polynomial.cu:70-111), ntt_pointwise_mul_kernel
+ * (kernels/ntt_kernels.cu:124-137), rns_add / rns_sub / rns_mul kernels (src/rns.cu:143-180, include/rns.cuh:96-103). */
+int fhe_b200_poly_add(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
+                      uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+int fhe_b200_poly_sub(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
+                      uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+int fhe_b200_poly_mul(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
+                      uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+/* out = acc + a*b */
+int fhe_b200_poly_mac(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_acc, const uint64_t* d_a,
+                      const uint64_t* d_b, uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+/* out = a * scalar; h_scalars[limb_count] holds the scalar's residue for each limb */
+int fhe_b200_poly_mul_scalar(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* h_scalars,
+                             uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+int fhe_b200_poly_add_scalar(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* h_scalars,
+                             uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+int fhe_b200_poly_negate(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, uint32_t batch,
+                         uint32_t limb_begin, uint32_t limb_count, void* stream);
+
+/* ---- fhe::uint256_t edge conversion (include/bigint.cuh:9-24: four little-endian 64-bit words) ---------------
+ * the reference API passes 32-byte coefficients; the engine works on 8-byte residues.  unpack keeps limbs[0]
+ * (all hot-path values are < 2^61); pack zero-extends. */
+int fhe_b200_unpack_u256(uint64_t* d_out, const void* d_u256, size_t count, void* stream);
+int fhe_b200_pack_u256(void* d_u256, const uint64_t* d_in, size_t count, void* stream);
+/* RNSContext::to_rns (src/rns.cu:57-63): residues of `count` 256-bit values for limbs [limb_begin, +limb_count),
+ * written limb-major [limb_count][count]. */
+int fhe_b200_to_rns_u256(fhe_b200_plan* plan, uint64_t* d_out, const void* d_u256, size_t count,
+                         uint32_t limb_begin, uint32_t limb_count, void* stream);
+
+/* ---- RNS linear combination: exact base conversion and t/Q scale-and-round ----------------------------------
+ * replaces fast_base_conversion_kernel / RNSContext::base_extend (include/rns.cuh:47-49,116-125),
+ * rns_mod_switch_kernel / mod_switch_rns (include/rns.cuh:44-45,128-136), poly_mod_switch_kernel
+ * (include/polynomial.cuh:96-102) and from_rns_crt_kernel's role in decryption (src/rns.cu:117-141).
+ *   out_k = ( sum_i z_i M[i][k] + (I mod m_k) c_k + extra_k lam_k ) mod m_k ,
+ *   z_i = x_i pre_i mod s_i (conversion) or x_i (scaling),  I = round( sum_i z_i theta_i ) in 128-bit fixed point.
+ * in: [batch][S][N]   extra: [batch][T][N] or NULL   out: [batch][T][N]     (n_coeffs = N of the caller's ring) */
+int fhe_b200_lincomb_create_conv(const uint64_t* h_src, uint32_t S, const uint64_t* h_dst, uint32_t T, int device,
+                                 fhe_b200_lincomb** out);
+int fhe_b200_lincomb_create_scale(const uint64_t* h_q, uint32_t L, const uint64_t* h_p, uint32_t R, uint64_t t,
+                                  const uint64_t* h_targets, uint32_t T, int with_extra, int device,
+                                  fhe_b200_lincomb** out);
+int fhe_b200_lincomb_destroy(fhe_b200_lincomb* lc);
+int fhe_b200_lincomb_apply(fhe_b200_lincomb* lc, uint64_t* d_out, const uint64_t* d_in, const uint64_t* d_extra,
+                           uint32_t n_coeffs, uint32_t batch, void* stream);
+/* copies the precomputed constants to the host (for parity tests): pre[S], th_hi[S], th_lo[S], M[S*T], c[T], lam[T] */
+int fhe_b200_lincomb_constants(const fhe_b200_lincomb* lc, uint64_t* pre, uint64_t* th_hi, uint64_t* th_lo,
+                               uint64_t* M, uint64_t* c, uint64_t* lam);
+/* drop the last limb with rounding: out_i = round(x / q_last) mod q_i, in [batch][limbs][N] -> out [batch][limbs-1][N] */
+int fhe_b200_modswitch_drop_last(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t batch,
+                                 uint32_t limb_begin, uint32_t limb_count, void* stream);
+
+/* ---- BFV on RNS: the path under fhe::FHEContext ------------------------------------------------------------
+ * moduli = Q (L primes) followed by the auxiliary basis (R primes); the special modulus of hybrid key switching
+ * is the first K auxiliary primes; dnum digits of alpha = L/dnum limbs each.
+ * Device data formats (uint64_t):
+ *   secret key   [L+R][N]            NTT form          public key  [2][L][N]   NTT form  (pk0 = e - a s, pk1 = a)
+ *   relin key    [dnum][2][L+K][N]   NTT form          ciphertext  [2][L][N]   coefficient form
+ *   plaintext    [N]                 coefficients mod t
+ * Randomness is a counter-based generator keyed by the caller's 64-bit seed (specification in DESIGN.md), so
+ * results are reproducible and identical to the CPU oracle's. */
+int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t K, uint32_t dnum, uint64_t t,
+                        const uint64_t* h_moduli, float sigma, uint32_t hamming_weight, int device,
+                        fhe_b200_bfv** out);
+int fhe_b200_bfv_destroy(fhe_b200_bfv* ctx);
+/* FHEContext::keygen (src/fhe.cu:54-74) */
+int fhe_b200_bfv_keygen(fhe_b200_bfv* ctx, uint64_t seed_sk, uint64_t seed_pk, uint64_t* d_sk, uint64_t* d_pk,
+                        void* stream);
+/* FHEContext::relinkey_gen (src/fhe.cu:76-111) */
+int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* ctx, uint64_t seed, const uint64_t* d_sk, uint64_t* d_rlk, void* stream);
+/* FHEContext::encrypt (src/fhe.cu:138-169); batch plaintexts [batch][N] -> ciphertexts [batch][2][L][N]; ciphertext b uses seed + b */
+int fhe_b200_bfv_encrypt(fhe_b200_bfv* ctx, uint64_t seed, const uint64_t* d_pt, const uint64_t* d_pk,
+                         uint64_t* d_ct, uint32_t batch, void* stream);
+/* FHEContext::decrypt (src/fhe.cu:171-185) */
+int fhe_b200_bfv_decrypt(fhe_b200_bfv* ctx, const uint64_t* d_ct, const uint64_t* d_sk, uint64_t* d_pt,
+                         uint32_t batch, void* stream);
+/* FHEContext::add (src/fhe.cu:187-197) */
+int fhe_b200_bfv_add(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint32_t batch,
+                     void* stream);
+/* FHEContext::multiply + relinearize (src/fhe.cu:199-235).  d_scaled (optional, [batch][3][L][N]) receives the
+ * scaled tensor before relinearisation. */
+int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
+                                uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream);
+/* host-buffer variant of multiply_relin (copies in, computes, copies out; synchronous) */
+int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* ctx, const uint64_t* h_a, const uint64_t* h_b,
+                                     const uint64_t* d_rlk, uint64_t* h_out, uint32_t batch);
+/* scheme constants for the compat layer and tests */
+int fhe_b200_bfv_info(const fhe_b200_bfv* ctx, uint32_t* n, uint32_t* L, uint32_t* R, uint32_t* K, uint32_t* dnum,
+                      uint64_t* t);
+fhe_b200_plan* fhe_b200_bfv_plan(fhe_b200_bfv* ctx);
+/* the Gaussian CDT the samplers use (<= 128 entries); returns the length */
+int fhe_b200_gaussian_cdt(double sigma, uint64_t* h_cdt, uint32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

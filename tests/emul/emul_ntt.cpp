@@ -1,0 +1,88 @@
+// TEST INFRASTRUCTURE: runs the engine's kernel bodies (csrc/ntt_core.cuh) on the CPU, one emulated thread at a
+// time with phase boundaries where the kernels have block barriers, so that index maps, twiddle addressing and
+// lazy-reduction bounds can be validated against the oracle in the GPU-less container.  Not a product path:
+// nothing in the C-ABI library references this file.
+#include <vector>
+#include <cstring>
+#include "ntt_core.cuh"
+#include "tables.hpp"
+
+using namespace fhe_b200;
+
+template <int LB, int K1, int HB>
+static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
+    constexpr int NB = 1 << LB;
+    if constexpr (K1 > 0) {
+        constexpr int V = (K1 >= 5) ? 1 : 2;
+        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB>::forward(d, d, col, tw, P.q);
+    }
+    constexpr int B0 = fwd_bound_after(1, K1, HB);
+    std::vector<u64> s(NB);
+    using T = TileFwd<LB, HB>;
+    for (u32 b = 0; b < (1u << K1); b++) {
+        u64* g = d + (size_t)b * NB;
+        const u32 root = (1u << K1) + b;
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase1<B0>(t, g, s.data(), tw, root, P.q);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase2<B0>(t, s.data(), tw, root, P.q);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase3<B0>(t, s.data(), tw, root, P.q);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::phase4(t, g, s.data());
+    }
+}
+
+template <int LB, int K1, int HB>
+static void inv_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
+    constexpr int NB = 1 << LB;
+    std::vector<u64> s(NB);
+    using T = TileInv<LB, HB>;
+    for (u32 b = 0; b < (1u << K1); b++) {
+        u64* g = d + (size_t)b * NB;
+        const u32 root = (1u << K1) + b;
+        for (u32 t = 0; t < (u32)T::NT; t++) T::phase1(t, g, s.data());
+        for (u32 t = 0; t < (u32)T::NT; t++) T::phase2(t, s.data(), tw, root, P);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::phase3(t, s.data(), tw, root, P);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase4<K1 == 0>(t, g, s.data(), tw, root, P);
+    }
+    if constexpr (K1 > 0) {
+        constexpr int V = (K1 >= 5) ? 1 : 2;
+        constexpr int B0 = T::out_bound();
+        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB>::template inverse<B0>(d, col, tw, P);
+    }
+}
+
+template <int HB>
+static int run(u64* d, u32 logn, const Twiddle* tw, const LimbParams& P, int inverse) {
+#define CASE(LBv, K1v) if (inverse) inv_limb<LBv, K1v, HB>(d, tw, P); else fwd_limb<LBv, K1v, HB>(d, tw, P); return 0;
+    switch (logn) {
+        case 9: CASE(9, 0)
+        case 10: CASE(10, 0)
+        case 11: CASE(11, 0)
+        case 12: CASE(12, 0)
+        case 13: CASE(12, 1)
+        case 14: CASE(12, 2)
+        case 15: CASE(12, 3)
+        case 16: CASE(12, 4)
+        case 17: CASE(12, 5)
+    }
+#undef CASE
+    return -2;
+}
+
+extern "C" int emul_ntt(uint64_t* data, uint32_t n, uint64_t q, int inverse, int hb) {
+    std::vector<Twiddle> fwd(n), inv(n);
+    LimbParams P;
+    if (build_limb_tables(q, n, fwd.data(), inv.data(), &P)) return -1;
+    const u32 logn = host::ilog2(n);
+    const Twiddle* tw = inverse ? inv.data() : fwd.data();
+    if (hb == 16) return run<16>(data, logn, tw, P, inverse);
+    if (hb == 8) return run<8>(data, logn, tw, P, inverse);
+    return -3;
+}
+
+extern "C" uint64_t emul_mul_mod(uint64_t a, uint64_t b, uint64_t q) {
+    LimbParams P; P.q = q; host::frac128(1, q, P.mu_hi, P.mu_lo);
+    return mul_mod(a, b, P);
+}
+extern "C" uint64_t emul_barrett128(uint64_t hi, uint64_t lo, uint64_t q) {
+    u64 mh, ml; host::frac128(1, q, mh, ml);
+    return barrett128(hi, lo, q, mh, ml);
+}

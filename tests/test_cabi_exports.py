@@ -1,0 +1,37 @@
+"""The C-ABI library must load without a GPU and export every symbol include/fhe_b200.h declares."""
+import ctypes
+import os
+import re
+
+import fhe_b200
+
+
+def _declared():
+    src = open(fhe_b200.HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fhe_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(fhe_b200.LIB_PATH), "libfhe_b200.so not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(fhe_b200.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/fhe_b200.h but not exported: {missing}"
+
+
+def test_no_oracle_in_product():
+    """the product must not reference the oracle or any CPU fallback (tier rule 3)."""
+    pkg = os.path.dirname(fhe_b200.LIB_PATH)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "liboracle" not in txt and "orc_" not in txt, f
+
+
+def test_version_and_error_string_without_gpu():
+    lib = fhe_b200.load_library()
+    assert lib.fhe_b200_version() >= 100
+    assert lib.fhe_b200_last_error() is not None
