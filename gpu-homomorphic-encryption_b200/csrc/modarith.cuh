@@ -138,7 +138,7 @@ FHE_HD u64 mul_mod(u64 a, u64 b, const LimbParams& P) {
     return barrett128(hi, lo, P.q, P.mu_hi, P.mu_lo);
 }
 
-// ---- counter-based generator shared (by specification) with oracle/orc_math.h ----
+// ---- counter-based generator (specification in DESIGN.md; the CPU checker restates it independently) ----
 FHE_HD u64 mix64(u64 z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
