@@ -1,0 +1,77 @@
+"""Secondary metric (BASELINE.json): BFV HMult+relinearize ops/s at config 4 (N=2^16, L=24, aux 25, dnum=3, K=8).
+Imported by bench.py (--with-hmult) or run directly:  python bench_hmult.py [--batch B] [--steps K]"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
+    import numpy as np
+    import torch
+    import fhe_b200
+    from fhe_b200.engine import pinned_empty, to_device, to_host
+    from fhe_b200.params import bfv_preset
+
+    torch.cuda.set_device(local_rank)
+    p = bfv_preset(preset)
+    n, L, t = p["n"], p["L"], p["t"]
+    B = batch or 4
+    K = steps or max(3, min(getattr(args, "steps", 10), 10))
+    g = fhe_b200.BfvContext(n, L, p["R"], p["K"], p["dnum"], t, p["primes"], p["sigma"], p["hamming_weight"], device=local_rank)
+    sk, pk = g.keygen(1, 2)
+    rlk = g.relinkey_gen(3, sk)
+    rng = np.random.default_rng(5)
+    m1 = rng.integers(0, t, (B, n), dtype=np.uint64); m2 = rng.integers(0, t, (B, n), dtype=np.uint64)
+    ca = g.encrypt(10, to_device(m1), pk); cb = g.encrypt(100, to_device(m2), pk)
+    out = torch.empty_like(ca)
+    lib = fhe_b200.load_library()
+    for _ in range(3):
+        g.multiply(ca, cb, rlk, out=out)
+    torch.cuda.synchronize()
+    l0 = lib.fhe_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        g.multiply(ca, cb, rlk, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.fhe_b200_launch_count() - l0
+    # correctness of what was timed: decrypt one result
+    import oracle
+    dec = to_host(g.decrypt(out, sk))
+    ok = bool(np.array_equal(dec[0], oracle.negacyclic_mul_ntt(m1[0], m2[0], t)))
+    # end to end with host buffers
+    ha, hb = pinned_empty(tuple(ca.shape)), pinned_empty(tuple(cb.shape))
+    ha[...] = to_host(ca); hb[...] = to_host(cb)
+    ho = pinned_empty(tuple(ca.shape))
+    g.multiply_host(ha, hb, rlk, ho)
+    t0 = time.perf_counter()
+    e2e_steps = 3
+    for _ in range(e2e_steps):
+        g.multiply_host(ha, hb, rlk, ho)
+    e2e = time.perf_counter() - t0
+    ok2 = bool(np.array_equal(ho, to_host(out)))
+    ct_bytes = 2 * L * n * 8
+    return {"metric": "BFV HMult+relinearize ops/s", "value": B * K / (ms / 1e3), "unit": "ops/s", "batch": B, "steps": K,
+            "ms_per_op": ms / (B * K), "config": {"workload": f"config4: N={n}, L={L}, R={p['R']}, dnum={p['dnum']}, K={p['K']}, t={t}"},
+            "decrypts_to_product": ok, "gpu_launches": int(launches),
+            "e2e": {"value": B * e2e_steps / e2e, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
+                    "matches_device_path": ok2},
+            "limb_ntts_per_op": 4 * (L + p["R"]) + 3 * (L + p["R"]) + p["dnum"] * (L + p["K"]) + 2 * (L + p["K"])}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--preset", default="c4")
+    a = ap.parse_args()
+    print(json.dumps(run_hmult(a, 0, a.preset, a.batch, a.steps)))

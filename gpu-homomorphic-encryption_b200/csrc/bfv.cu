@@ -1,0 +1,544 @@
+// BFV on RNS: the path under fhe::FHEContext (keygen, relinkey_gen, encrypt, decrypt, add, multiply+relinearize).
+//
+// Scheme equations follow /root/reference/src/fhe.cu:54-235 and docs/ARCHITECTURE.md:260-326; the parts the
+// reference leaves out (honouring log_q through an RNS basis, the t/Q scaling of the tensor product, and
+// relinearisation -- `relinearize` there is components.resize(2)) are built as
+//   HPS-style RNS multiplication: exact extension Q -> Q u R, tensor in the NTT domain, round(t/Q .) computed in R,
+//   exact conversion back R -> Q,  then hybrid (dnum-digit) key switching with special modulus P = first K primes of R:
+//   ModUp (exact) -> NTT -> inner product with the key -> INTT -> ModDown (exact, fused with the final add).
+// All base conversions go through the lincomb kernel; every NTT through launch_ntt.
+//
+// Buffers (uint64):  sk [L+R][N] NTT | pk [2][L][N] NTT | rlk [dnum][2][L+K][N] NTT | ct [B][2][L][N] coeff | pt [B][N].
+#include "common.cuh"
+#include "lincomb.cuh"
+#include "samplers.cuh"
+#include "host_math.hpp"
+#include <cmath>
+#include <cstring>
+
+struct fhe_b200_bfv {
+    uint32_t n = 0, logn = 0, L = 0, R = 0, K = 0, dnum = 0, alpha = 0;
+    uint64_t t = 0;
+    int device = 0;
+    uint32_t hw = 0, thr = 1u << 31;
+    std::vector<uint64_t> primes;
+    fhe_b200_plan* plan = nullptr;                       // all L+R primes
+    fhe_b200_lincomb *q2r = nullptr, *scale = nullptr, *r2q = nullptr, *moddown = nullptr, *dec = nullptr;
+    std::vector<fhe_b200_lincomb*> modup;                // [dnum]
+    // device constants
+    uint64_t* d_consts = nullptr;                        // delta[L] | p_mod_q[L+K] (0 outside Q) | pinv_mod_q[L] | cdt[128]
+    const uint64_t *d_delta = nullptr, *d_pmodq = nullptr, *d_pinv = nullptr, *d_cdt = nullptr;
+    uint32_t cdt_len = 0;
+    std::vector<uint64_t> h_cdt;
+    uint32_t* d_idx = nullptr;                           // index maps for the lincomb views
+    const uint32_t *d_idx_p = nullptr;                   // [K]  L .. L+K-1
+    std::vector<const uint32_t*> d_idx_grp, d_idx_tgt;   // per digit: sources [alpha], targets [L+K-alpha]
+};
+
+namespace fhe_b200 {
+
+// ---- sampling kernels ----------------------------------------------------------------------------------------------
+// small polynomial (ternary or Gaussian), expanded to residues for limbs [limb_begin, +limb_count); polynomial b uses seed+b
+template <int MODE>   // 0 ternary, 1 gaussian
+__global__ void __launch_bounds__(256) sample_small_kernel(u64* __restrict__ out, const LimbParams* __restrict__ params,
+                                                           uint32_t logn, uint32_t limb_begin, uint32_t limb_count, uint32_t batch,
+                                                           u64 seed, u64 stream, u32 thr, const u64* __restrict__ cdt, u32 cdt_len) {
+    __shared__ u64 scdt[kMaxCdt];
+    if (MODE == 1) { for (u32 i = threadIdx.x; i < cdt_len; i += blockDim.x) scdt[i] = cdt[i]; __syncthreads(); }
+    const uint32_t n = 1u << logn;
+    const size_t total = (size_t)batch * n;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g & (n - 1));
+        const size_t b = g >> logn;
+        const u64 r = rng_at(rng_key(seed + b, stream), j);
+        const int v = MODE == 0 ? ternary_from(r, thr) : gauss_from(r, scdt, cdt_len);
+        for (uint32_t l = 0; l < limb_count; l++) out[(b * limb_count + l) * n + j] = small_to_residue(v, params[limb_begin + l].q);
+    }
+}
+// host-generated small polynomial (int8) -> residues
+__global__ void __launch_bounds__(256) expand_small_kernel(u64* __restrict__ out, const int8_t* __restrict__ s,
+                                                           const LimbParams* __restrict__ params, uint32_t n, uint32_t limb_begin, uint32_t limb_count) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int v = s[j];
+        for (uint32_t l = 0; l < limb_count; l++) out[(size_t)l * n + j] = small_to_residue(v, params[limb_begin + l].q);
+    }
+}
+// uniform residues: limb l uses stream stream_base + l
+__global__ void __launch_bounds__(256) sample_uniform_kernel(u64* __restrict__ out, const LimbParams* __restrict__ params, uint32_t logn,
+                                                             uint32_t limb_begin, uint32_t limb_count, u64 seed, u64 stream_base) {
+    const uint32_t n = 1u << logn;
+    const size_t total = (size_t)limb_count * n;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g & (n - 1));
+        const uint32_t l = (uint32_t)(g >> logn);
+        const LimbParams P = params[limb_begin + l];
+        const u64 key = rng_key(seed, stream_base + l);
+        out[g] = barrett128(rng_at(key, 2ull * j), rng_at(key, 2ull * j + 1), P.q, P.mu_hi, P.mu_lo);
+    }
+}
+
+// ---- key generation -------------------------------------------------------------------------------------------------
+// pk0 = e - a*s  (all NTT form), one polynomial of L limbs
+__global__ void __launch_bounds__(256) pk_finish_kernel(u64* __restrict__ pk0, const u64* __restrict__ a, const u64* __restrict__ s,
+                                                        const LimbParams* __restrict__ params, uint32_t logn, size_t total) {
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const LimbParams P = params[g >> logn];
+        pk0[g] = sub_mod(pk0[g], mul_mod(a[g], s[g], P), P.q);
+    }
+}
+// b = e - a*s + f*s^2, f = P mod q_i for the digit's own limbs, 0 elsewhere; W = L+K limbs
+__global__ void __launch_bounds__(256) rlk_finish_kernel(u64* __restrict__ b, const u64* __restrict__ a, const u64* __restrict__ s,
+                                                         const LimbParams* __restrict__ params, const u64* __restrict__ pmodq,
+                                                         uint32_t logn, uint32_t g_lo, uint32_t g_hi, size_t total) {
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(g >> logn);
+        const LimbParams P = params[i];
+        const u64 sv = s[g];
+        u64 v = sub_mod(b[g], mul_mod(a[g], sv, P), P.q);
+        if (i >= g_lo && i < g_hi) v = add_mod(v, mul_mod(pmodq[i], mul_mod(sv, sv, P), P), P.q);
+        b[g] = v;
+    }
+}
+
+// ---- encrypt ----------------------------------------------------------------------------------------------------------
+// ct[b][0][i] = pk0[i]*u[b][i], ct[b][1][i] = pk1[i]*u[b][i]   (NTT form)
+__global__ void __launch_bounds__(256) enc_mul_kernel(u64* __restrict__ ct, const u64* __restrict__ u, const u64* __restrict__ pk,
+                                                      const LimbParams* __restrict__ params, uint32_t logn, uint32_t L, size_t total) {
+    const size_t ln = (size_t)L << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = g / ln, r = g % ln;
+        const LimbParams P = params[r >> logn];
+        const u64 uv = u[g];
+        ct[(2 * b) * ln + r] = mul_mod(pk[r], uv, P);
+        ct[(2 * b + 1) * ln + r] = mul_mod(pk[ln + r], uv, P);
+    }
+}
+// c0 += e1 + delta*m ; c1 += e2   (coefficient form; e1, e2 regenerated from the counter generator)
+__global__ void __launch_bounds__(256) enc_finish_kernel(u64* __restrict__ ct, const u64* __restrict__ pt, const LimbParams* __restrict__ params,
+                                                         const u64* __restrict__ delta, const u64* __restrict__ cdt, u32 cdt_len,
+                                                         uint32_t logn, uint32_t L, uint32_t batch, u64 seed) {
+    __shared__ u64 scdt[kMaxCdt];
+    for (u32 i = threadIdx.x; i < cdt_len; i += blockDim.x) scdt[i] = cdt[i];
+    __syncthreads();
+    const uint32_t n = 1u << logn;
+    const size_t total = (size_t)batch * n;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g & (n - 1));
+        const size_t b = g >> logn;
+        const int e1 = gauss_from(rng_at(rng_key(seed + b, 1), j), scdt, cdt_len);
+        const int e2 = gauss_from(rng_at(rng_key(seed + b, 2), j), scdt, cdt_len);
+        const u64 m = pt[g];
+        for (uint32_t i = 0; i < L; i++) {
+            const LimbParams P = params[i];
+            const size_t o0 = ((2 * b) * L + i) * n + j, o1 = ((2 * b + 1) * L + i) * n + j;
+            const u64 dm = mul_mod(delta[i], barrett128(0, m, P.q, P.mu_hi, P.mu_lo), P);
+            ct[o0] = add_mod(add_mod(ct[o0], small_to_residue(e1, P.q), P.q), dm, P.q);
+            ct[o1] = add_mod(ct[o1], small_to_residue(e2, P.q), P.q);
+        }
+    }
+}
+
+// ---- decrypt ----------------------------------------------------------------------------------------------------------
+// x[b][i] = NTT(c1)[b][i] * s[i]
+__global__ void __launch_bounds__(256) dec_mul_kernel(u64* __restrict__ x, const u64* __restrict__ s, const LimbParams* __restrict__ params,
+                                                      uint32_t logn, uint32_t L, size_t total) {
+    const size_t ln = (size_t)L << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = g % ln;
+        x[g] = mul_mod(x[g], s[r], params[r >> logn]);
+    }
+}
+// x[b][i] += c0[b][i]   (ct is [B][2][L][N])
+__global__ void __launch_bounds__(256) dec_add_kernel(u64* __restrict__ x, const u64* __restrict__ ct, const LimbParams* __restrict__ params,
+                                                      uint32_t logn, uint32_t L, size_t total) {
+    const size_t ln = (size_t)L << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = g / ln, r = g % ln;
+        x[g] = add_mod(x[g], ct[(2 * b) * ln + r], params[r >> logn].q);
+    }
+}
+
+// ---- multiply ---------------------------------------------------------------------------------------------------------
+// ext: [4][B][A][N] (a0,a1,b0,b1; NTT form) -> d: [3][B][A][N]   d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1
+__global__ void __launch_bounds__(256) tensor_kernel(ulonglong2* __restrict__ d, const ulonglong2* __restrict__ ext,
+                                                     const LimbParams* __restrict__ params, uint32_t logn, uint32_t A, size_t per_comp /* B*A*N/2 */) {
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < per_comp; v += (size_t)gridDim.x * blockDim.x) {
+        const LimbParams P = params[((2 * v) >> logn) % A];
+        const ulonglong2 a0 = ext[v], a1 = ext[per_comp + v], b0 = ext[2 * per_comp + v], b1 = ext[3 * per_comp + v];
+        ulonglong2 r0, r1, r2;
+        u64 hi, lo;
+        r0.x = mul_mod(a0.x, b0.x, P); r0.y = mul_mod(a0.y, b0.y, P);
+        r2.x = mul_mod(a1.x, b1.x, P); r2.y = mul_mod(a1.y, b1.y, P);
+        hi = 0; lo = 0; mac128(hi, lo, a0.x, b1.x); mac128(hi, lo, a1.x, b0.x); r1.x = barrett128(hi, lo, P.q, P.mu_hi, P.mu_lo);
+        hi = 0; lo = 0; mac128(hi, lo, a0.y, b1.y); mac128(hi, lo, a1.y, b0.y); r1.y = barrett128(hi, lo, P.q, P.mu_hi, P.mu_lo);
+        d[v] = r0; d[per_comp + v] = r1; d[2 * per_comp + v] = r2;
+    }
+}
+// key-switch inner product: acc[c][b][i] = sum_dg dig[dg][b][i] * rlk[dg][c][i]    (W = L+K limbs, NTT form)
+__global__ void __launch_bounds__(256) ks_inner_kernel(ulonglong2* __restrict__ acc, const ulonglong2* __restrict__ dig,
+                                                       const ulonglong2* __restrict__ rlk, const LimbParams* __restrict__ params,
+                                                       uint32_t logn, uint32_t W, uint32_t dnum, uint32_t batch) {
+    const size_t wn = ((size_t)W << logn) / 2;              // vectors per polynomial
+    const size_t per = wn * batch;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < per; v += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = v % wn;
+        const LimbParams P = params[(2 * r) >> logn];
+        u64 h0x = 0, l0x = 0, h0y = 0, l0y = 0, h1x = 0, l1x = 0, h1y = 0, l1y = 0;
+        for (uint32_t dg = 0; dg < dnum; dg++) {
+            const ulonglong2 x = dig[dg * per + v];
+            const ulonglong2 kb = rlk[(size_t)(2 * dg) * wn + r], ka = rlk[(size_t)(2 * dg + 1) * wn + r];
+            mac128(h0x, l0x, x.x, kb.x); mac128(h0y, l0y, x.y, kb.y);
+            mac128(h1x, l1x, x.x, ka.x); mac128(h1y, l1y, x.y, ka.y);
+        }
+        ulonglong2 o0, o1;
+        o0.x = barrett128(h0x, l0x, P.q, P.mu_hi, P.mu_lo); o0.y = barrett128(h0y, l0y, P.q, P.mu_hi, P.mu_lo);
+        o1.x = barrett128(h1x, l1x, P.q, P.mu_hi, P.mu_lo); o1.y = barrett128(h1y, l1y, P.q, P.mu_hi, P.mu_lo);
+        acc[v] = o0; acc[per + v] = o1;
+    }
+}
+
+static inline uint32_t grid_for(const fhe_b200_bfv* c, size_t items) {
+    const size_t w = (items + 255) / 256, cap = (size_t)c->plan->sm_count * 16;
+    return (uint32_t)(w < cap ? (w ? w : 1) : cap);
+}
+
+// host twin of the hamming-weight ternary sampler
+static void host_ternary_hw(std::vector<int8_t>& s, uint32_t n, u64 seed, u64 stream, uint32_t hw) {
+    std::vector<uint32_t> perm(n);
+    for (uint32_t j = 0; j < n; j++) perm[j] = j;
+    s.assign(n, 0);
+    if (hw > n) hw = n;
+    const u64 k0 = rng_key(seed, stream), k1 = rng_key(seed, stream + 1);
+    for (uint32_t i = 0; i < hw; i++) {
+        const uint32_t j = i + (uint32_t)(rng_at(k0, i) % (n - i));
+        const uint32_t tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
+        s[perm[i]] = (rng_at(k1, i) & 1) ? -1 : 1;
+    }
+}
+
+static uint32_t host_gaussian_cdt(double sigma, uint64_t* cdt, uint32_t cap) {
+    uint32_t tail = (uint32_t)std::ceil(6.0 * sigma);
+    if (tail + 1 > cap) tail = cap - 1;
+    double norm = 1.0;
+    for (uint32_t x = 1; x <= tail; x++) norm += 2.0 * std::exp(-((double)x * (double)x) / (2.0 * sigma * sigma));
+    double cum = 1.0;
+    for (uint32_t k = 0; k <= tail; k++) {
+        if (k) cum += 2.0 * std::exp(-((double)k * (double)k) / (2.0 * sigma * sigma));
+        const double f = cum / norm;
+        cdt[k] = f >= 1.0 ? (1ull << 63) : (uint64_t)(f * 9223372036854775808.0);
+    }
+    cdt[tail] = 1ull << 63;
+    return tail + 1;
+}
+
+}  // namespace fhe_b200
+
+using namespace fhe_b200;
+
+extern "C" int fhe_b200_gaussian_cdt(double sigma, uint64_t* h_cdt, uint32_t cap) {
+    if (!h_cdt || cap < 2 || !(sigma > 0)) { set_error("gaussian_cdt: bad argument"); return FHE_B200_EINVAL; }
+    return (int)host_gaussian_cdt(sigma, h_cdt, cap < (uint32_t)kMaxCdt ? cap : (uint32_t)kMaxCdt);
+}
+
+extern "C" int fhe_b200_bfv_destroy(fhe_b200_bfv* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    fhe_b200_lincomb_destroy(c->q2r); fhe_b200_lincomb_destroy(c->scale); fhe_b200_lincomb_destroy(c->r2q);
+    fhe_b200_lincomb_destroy(c->moddown); fhe_b200_lincomb_destroy(c->dec);
+    for (auto* m : c->modup) fhe_b200_lincomb_destroy(m);
+    cudaFree(c->d_consts); cudaFree(c->d_idx);
+    fhe_b200_plan_destroy(c->plan);
+    delete c;
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t K, uint32_t dnum, uint64_t t,
+                                   const uint64_t* h_moduli, float sigma, uint32_t hamming_weight, int device, fhe_b200_bfv** out) {
+    FHE_REQUIRE(out && h_moduli, "bfv_create: null argument");
+    *out = nullptr;
+    FHE_REQUIRE(L >= 1 && dnum >= 1 && L % dnum == 0, "bfv_create: L=%u must be a multiple of dnum=%u", L, dnum);
+    FHE_REQUIRE(K >= 1 && K <= R, "bfv_create: need 1 <= K <= R (K=%u, R=%u)", K, R);
+    FHE_REQUIRE(K >= L / dnum, "bfv_create: special modulus needs K >= alpha = L/dnum limbs (K=%u, alpha=%u)", K, L / dnum);
+    FHE_REQUIRE(R >= L + 1, "bfv_create: auxiliary basis needs R >= L+1 limbs so that P_R > t*N*Q (R=%u, L=%u)", R, L);
+    FHE_REQUIRE(L + R <= 62, "bfv_create: at most 62 primes in total");
+    FHE_REQUIRE(t >= 2 && (t >> 32) == 0, "bfv_create: plaintext modulus must be in [2, 2^32)");
+    FHE_REQUIRE(sigma > 0 && sigma < 20, "bfv_create: sigma out of range");
+    for (uint32_t i = 0; i < L + R; i++)
+        for (uint32_t k = i + 1; k < L + R; k++) FHE_REQUIRE(h_moduli[i] != h_moduli[k], "bfv_create: moduli %u and %u are equal", i, k);
+    for (uint32_t i = 0; i < L; i++) FHE_REQUIRE(host::invmod(t % h_moduli[i], h_moduli[i]) != 0, "bfv_create: t is not coprime to q_%u", i);
+
+    auto* c = new fhe_b200_bfv();
+    c->n = n; c->logn = host::ilog2(n); c->L = L; c->R = R; c->K = K; c->dnum = dnum; c->alpha = L / dnum; c->t = t;
+    c->device = device; c->hw = hamming_weight;
+    c->primes.assign(h_moduli, h_moduli + L + R);
+    int rc = fhe_b200_plan_create(n, h_moduli, L + R, device, &c->plan);
+    if (rc) { delete c; return rc; }
+    const uint64_t* Q = h_moduli; const uint64_t* P = h_moduli + L;
+    const uint32_t W = L + K, alpha = c->alpha;
+#define BFV_TRY(e) do { rc = (e); if (rc) { fhe_b200_bfv_destroy(c); return rc; } } while (0)
+    BFV_TRY(lincomb_create(make_conv_consts(Q, L, P, R), device, &c->q2r));
+    BFV_TRY(lincomb_create(make_scale_consts(Q, L, P, R, t, P, R, true), device, &c->scale));
+    BFV_TRY(lincomb_create(make_conv_consts(P, R, Q, L), device, &c->r2q));
+    BFV_TRY(lincomb_create(make_conv_consts(P, K, Q, L), device, &c->moddown));
+    BFV_TRY(lincomb_create(make_scale_consts(Q, L, nullptr, 0, t, &c->t, 1, false), device, &c->dec));
+    // index maps: [K] special limbs | per digit: [alpha] sources, [W-alpha] targets
+    std::vector<uint32_t> idx;
+    for (uint32_t k = 0; k < K; k++) idx.push_back(L + k);
+    std::vector<size_t> off_grp(dnum), off_tgt(dnum);
+    for (uint32_t d = 0; d < dnum; d++) {
+        std::vector<uint64_t> tm;
+        off_grp[d] = idx.size();
+        for (uint32_t i = 0; i < alpha; i++) idx.push_back(d * alpha + i);
+        off_tgt[d] = idx.size();
+        for (uint32_t i = 0; i < W; i++) {
+            if (i >= d * alpha && i < (d + 1) * alpha) continue;
+            idx.push_back(i); tm.push_back(h_moduli[i]);
+        }
+        fhe_b200_lincomb* mu = nullptr;
+        BFV_TRY(lincomb_create(make_conv_consts(Q + d * alpha, alpha, tm.data(), (uint32_t)tm.size()), device, &mu));
+        c->modup.push_back(mu);
+    }
+    cudaError_t e = cudaMalloc(&c->d_idx, idx.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_idx, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    // constants
+    std::vector<uint64_t> cst(L + W + L + kMaxCdt, 0);
+    uint64_t q_mod_t = 1 % t;
+    for (uint32_t i = 0; i < L; i++) q_mod_t = host::mulmod(q_mod_t, Q[i] % t, t);
+    for (uint32_t i = 0; i < L; i++) {
+        const uint64_t qi = Q[i];
+        const uint64_t neg = (q_mod_t % qi) ? qi - (q_mod_t % qi) : 0;
+        cst[i] = host::mulmod(neg, host::invmod(t % qi, qi), qi);                  // floor(Q/t) mod q_i
+        uint64_t pm = 1;
+        for (uint32_t k = 0; k < K; k++) pm = host::mulmod(pm, P[k] % qi, qi);
+        cst[L + i] = pm;                                                           // P mod q_i (0 for the special limbs)
+        cst[L + W + i] = host::invmod(pm, qi);                                     // P^-1 mod q_i
+    }
+    c->h_cdt.resize(kMaxCdt);
+    c->cdt_len = host_gaussian_cdt((double)sigma, c->h_cdt.data(), kMaxCdt);
+    for (uint32_t k = 0; k < c->cdt_len; k++) cst[L + W + L + k] = c->h_cdt[k];
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_consts, cst.size() * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_consts, cst.data(), cst.size() * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("bfv_create: device allocation failed: %s", cudaGetErrorString(e)); fhe_b200_bfv_destroy(c); return FHE_B200_ECUDA; }
+    c->d_delta = c->d_consts; c->d_pmodq = c->d_consts + L; c->d_pinv = c->d_consts + L + W; c->d_cdt = c->d_consts + L + W + L;
+    c->d_idx_p = c->d_idx;
+    for (uint32_t d = 0; d < dnum; d++) { c->d_idx_grp.push_back(c->d_idx + off_grp[d]); c->d_idx_tgt.push_back(c->d_idx + off_tgt[d]); }
+#undef BFV_TRY
+    *out = c;
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_info(const fhe_b200_bfv* c, uint32_t* n, uint32_t* L, uint32_t* R, uint32_t* K, uint32_t* dnum, uint64_t* t) {
+    FHE_REQUIRE(c, "bfv_info: null context");
+    if (n) *n = c->n; if (L) *L = c->L; if (R) *R = c->R; if (K) *K = c->K; if (dnum) *dnum = c->dnum; if (t) *t = c->t;
+    return 0;
+}
+extern "C" fhe_b200_plan* fhe_b200_bfv_plan(fhe_b200_bfv* c) { return c ? c->plan : nullptr; }
+
+// ---- keys ---------------------------------------------------------------------------------------------------------------
+extern "C" int fhe_b200_bfv_keygen(fhe_b200_bfv* c, uint64_t seed_sk, uint64_t seed_pk, uint64_t* d_sk, uint64_t* d_pk, void* stream) {
+    FHE_REQUIRE(c && d_sk && d_pk, "bfv_keygen: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, L = c->L, A = c->L + c->R;
+    const LimbParams* prm = c->plan->d_params;
+    // secret: stream 0 (signs: stream 1 when a hamming weight is set)
+    if (c->hw) {
+        std::vector<int8_t> s;
+        host_ternary_hw(s, n, seed_sk, 0, c->hw);
+        int8_t* d_s = nullptr;
+        FHE_CUDA(cudaMallocAsync(&d_s, n, st));
+        FHE_CUDA(cudaMemcpyAsync(d_s, s.data(), n, cudaMemcpyHostToDevice, st));
+        FHE_CUDA(cudaStreamSynchronize(st));          // s is a stack-owned host buffer
+        expand_small_kernel<<<grid_for(c, n), 256, 0, st>>>(d_sk, d_s, prm, n, 0, A);
+        FHE_LAUNCH_CHECK();
+        FHE_CUDA(cudaFreeAsync(d_s, st));
+    } else {
+        sample_small_kernel<0><<<grid_for(c, n), 256, 0, st>>>(d_sk, prm, c->logn, 0, A, 1, seed_sk, 0, c->thr, c->d_cdt, c->cdt_len);
+        FHE_LAUNCH_CHECK();
+    }
+    FHE_TRY(launch_ntt(c->plan, d_sk, d_sk, 1, 0, A, false, st));
+    // public key: e on stream 2, a on streams 16+i
+    uint64_t* pk0 = d_pk; uint64_t* pk1 = d_pk + (size_t)L * n;
+    sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(pk0, prm, c->logn, 0, L, 1, seed_pk, 2, 0, c->d_cdt, c->cdt_len);
+    FHE_LAUNCH_CHECK();
+    FHE_TRY(launch_ntt(c->plan, pk0, pk0, 1, 0, L, false, st));
+    sample_uniform_kernel<<<grid_for(c, (size_t)L * n), 256, 0, st>>>(pk1, prm, c->logn, 0, L, seed_pk, 16);
+    FHE_LAUNCH_CHECK();
+    pk_finish_kernel<<<grid_for(c, (size_t)L * n), 256, 0, st>>>(pk0, pk1, d_sk, prm, c->logn, (size_t)L * n);
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* c, uint64_t seed, const uint64_t* d_sk, uint64_t* d_rlk, void* stream) {
+    FHE_REQUIRE(c && d_sk && d_rlk, "bfv_relinkeygen: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, W = c->L + c->K;
+    const LimbParams* prm = c->plan->d_params;
+    for (uint32_t d = 0; d < c->dnum; d++) {
+        uint64_t* b = d_rlk + (size_t)(2 * d) * W * n; uint64_t* a = b + (size_t)W * n;
+        const uint64_t base = 1024ull * (d + 1);
+        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, base + 512, 0, c->d_cdt, c->cdt_len);
+        FHE_LAUNCH_CHECK();
+        FHE_TRY(launch_ntt(c->plan, b, b, 1, 0, W, false, st));
+        sample_uniform_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base);
+        FHE_LAUNCH_CHECK();
+        rlk_finish_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(b, a, d_sk, prm, c->d_pmodq, c->logn, d * c->alpha, (d + 1) * c->alpha, (size_t)W * n);
+        FHE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// ---- encrypt / decrypt / add -----------------------------------------------------------------------------------------------
+extern "C" int fhe_b200_bfv_encrypt(fhe_b200_bfv* c, uint64_t seed, const uint64_t* d_pt, const uint64_t* d_pk, uint64_t* d_ct,
+                                    uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_pt && d_pk && d_ct, "bfv_encrypt: null argument");
+    if (!batch) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, L = c->L;
+    const LimbParams* prm = c->plan->d_params;
+    const size_t ln = (size_t)L * n;
+    uint64_t* u = nullptr;
+    FHE_CUDA(cudaMallocAsync(&u, batch * ln * sizeof(uint64_t), st));
+    sample_small_kernel<0><<<grid_for(c, (size_t)batch * n), 256, 0, st>>>(u, prm, c->logn, 0, L, batch, seed, 0, c->thr, c->d_cdt, c->cdt_len);
+    FHE_LAUNCH_CHECK();
+    int rc = launch_ntt(c->plan, u, u, batch, 0, L, false, st);
+    if (!rc) {
+        enc_mul_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(d_ct, u, d_pk, prm, c->logn, L, batch * ln);
+        count_launch();
+        rc = launch_ntt(c->plan, d_ct, d_ct, 2 * batch, 0, L, true, st);
+    }
+    if (!rc) {
+        enc_finish_kernel<<<grid_for(c, (size_t)batch * n), 256, 0, st>>>(d_ct, d_pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, batch, seed);
+        count_launch();
+    }
+    cudaFreeAsync(u, st);
+    if (rc) return rc;
+    FHE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_decrypt(fhe_b200_bfv* c, const uint64_t* d_ct, const uint64_t* d_sk, uint64_t* d_pt, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_ct && d_sk && d_pt, "bfv_decrypt: null argument");
+    if (!batch) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, L = c->L;
+    const LimbParams* prm = c->plan->d_params;
+    const size_t ln = (size_t)L * n;
+    uint64_t* x = nullptr;
+    FHE_CUDA(cudaMallocAsync(&x, batch * ln * sizeof(uint64_t), st));
+    // x = c1 (strided gather), then x = INTT(NTT(x) * s) + c0
+    cudaError_t e = cudaMemcpy2DAsync(x, ln * 8, d_ct + ln, 2 * ln * 8, ln * 8, batch, cudaMemcpyDeviceToDevice, st);
+    int rc = e == cudaSuccess ? 0 : FHE_B200_ECUDA;
+    if (rc) set_error("bfv_decrypt: gather failed: %s", cudaGetErrorString(e));
+    if (!rc) rc = launch_ntt(c->plan, x, x, batch, 0, L, false, st);
+    if (!rc) { dec_mul_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(x, d_sk, prm, c->logn, L, batch * ln); count_launch(); }
+    if (!rc) rc = launch_ntt(c->plan, x, x, batch, 0, L, true, st);
+    if (!rc) { dec_add_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(x, d_ct, prm, c->logn, L, batch * ln); count_launch(); }
+    if (!rc) { LcView v; v.in = x; v.out = d_pt; rc = lincomb_launch(c->dec, v, n, batch, st); }
+    cudaFreeAsync(x, st);
+    if (rc) return rc;
+    FHE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_add(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_a && d_b && d_out, "bfv_add: null argument");
+    return launch_elementwise(c->plan, EW_ADD, d_out, d_a, d_b, nullptr, 2 * batch, 0, c->L, (cudaStream_t)stream);
+}
+
+// ---- multiply + relinearize --------------------------------------------------------------------------------------------------
+extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
+                                           uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_a && d_b && d_rlk && d_out, "bfv_multiply_relin: null argument");
+    if (!batch) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, alpha = c->alpha, dnum = c->dnum, B = batch;
+    const LimbParams* prm = c->plan->d_params;
+    const size_t N = n, ln = (size_t)L * N, an = (size_t)A * N, wn = (size_t)W * N, rn = (size_t)R * N;
+    // workspace: ext [4][B][A][N] | d [3][B][A][N] | sR [3][B][R][N] | sc [3][B][L][N] | dig [dnum][B][W][N] | acc [2][B][W][N]
+    const size_t w_ext = 4 * B * an, w_d = 3 * B * an, w_sr = 3 * B * rn, w_sc = 3 * B * ln, w_dig = (size_t)dnum * B * wn, w_acc = 2 * B * wn;
+    uint64_t* ws = nullptr;
+    FHE_CUDA(cudaMallocAsync(&ws, (w_ext + w_d + w_sr + w_sc + w_dig + w_acc) * sizeof(uint64_t), st));
+    uint64_t* ext = ws; uint64_t* d = ext + w_ext; uint64_t* sR = d + w_d; uint64_t* sc = sR + w_sr; uint64_t* dig = sc + w_sc; uint64_t* acc = dig + w_dig;
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+#define STEP(expr) do { if (!rc) rc = (expr); } while (0)
+#define COPY2D(dst, dpitch, src, spitch, width, rows) do { if (!rc && e == cudaSuccess) e = cudaMemcpy2DAsync(dst, (dpitch) * 8, src, (spitch) * 8, (width) * 8, rows, cudaMemcpyDeviceToDevice, st); } while (0)
+    // 1. the four input polynomials into ext: Q limbs copied, R limbs by exact conversion Q -> R
+    for (int p = 0; p < 4; p++) {
+        const uint64_t* src = (p < 2 ? d_a : d_b) + (size_t)(p & 1) * ln;           // component p&1 of every ciphertext: stride 2*ln
+        uint64_t* dst = ext + (size_t)p * B * an;
+        COPY2D(dst, an, src, 2 * ln, ln, B);
+        LcView v; v.in = src; v.in_stride = 2 * ln; v.out = dst + ln; v.out_stride = an;
+        STEP(lincomb_launch(c->q2r, v, n, B, st));
+    }
+    // 2. NTT over Q u R, 3. tensor, 4. INTT
+    STEP(launch_ntt(c->plan, ext, ext, 4 * B, 0, A, false, st));
+    if (!rc) {
+        const size_t per = B * an / 2;
+        tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, A, per);
+        count_launch();
+    }
+    STEP(launch_ntt(c->plan, d, d, 3 * B, 0, A, true, st));
+    // 5. round(t/Q .) in basis R, 6. exact conversion R -> Q
+    if (!rc) { LcView v; v.in = d; v.in_stride = an; v.extra = d + ln; v.extra_stride = an; v.out = sR; v.out_stride = rn; rc = lincomb_launch(c->scale, v, n, 3 * B, st); }
+    if (!rc) { LcView v; v.in = sR; v.in_stride = rn; v.out = sc; v.out_stride = ln; rc = lincomb_launch(c->r2q, v, n, 3 * B, st); }
+    if (d_scaled && !rc) {
+        // caller layout [B][3][L][N]; ours is [3][B][L][N]
+        for (int p = 0; p < 3; p++) COPY2D(d_scaled + (size_t)p * ln, 3 * ln, sc + (size_t)p * B * ln, ln, ln, B);
+    }
+    // 7. relinearise d2 = sc[2]: ModUp each digit, NTT, inner product with the key, INTT, ModDown (+ add d0/d1)
+    const uint64_t* d2 = sc + 2 * B * ln;
+    for (uint32_t dg = 0; dg < dnum && !rc; dg++) {
+        uint64_t* D = dig + (size_t)dg * B * wn;
+        COPY2D(D + (size_t)dg * alpha * N, wn, d2 + (size_t)dg * alpha * N, ln, (size_t)alpha * N, B);
+        LcView v; v.in = d2; v.in_stride = ln; v.src_idx = c->d_idx_grp[dg]; v.out = D; v.out_stride = wn; v.dst_idx = c->d_idx_tgt[dg];
+        STEP(lincomb_launch(c->modup[dg], v, n, B, st));
+    }
+    STEP(launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st));
+    if (!rc) {
+        const size_t per = B * wn / 2;
+        ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_rlk, prm, c->logn, W, dnum, B);
+        count_launch();
+    }
+    STEP(launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st));
+    for (int p = 0; p < 2 && !rc; p++) {
+        const uint64_t* s = acc + (size_t)p * B * wn;
+        LcView v; v.in = s; v.in_stride = wn; v.src_idx = c->d_idx_p;
+        v.sub = s; v.sub_stride = wn; v.epi_scalar = c->d_pinv;
+        v.add = sc + (size_t)p * B * ln; v.add_stride = ln;
+        v.out = d_out + (size_t)p * ln; v.out_stride = 2 * ln;
+        STEP(lincomb_launch(c->moddown, v, n, B, st));
+    }
+#undef STEP
+#undef COPY2D
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) { set_error("bfv_multiply_relin: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
+    if (rc) return rc;
+    FHE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* c, const uint64_t* h_a, const uint64_t* h_b, const uint64_t* d_rlk,
+                                                uint64_t* h_out, uint32_t batch) {
+    FHE_REQUIRE(c && h_a && h_b && d_rlk && h_out, "bfv_multiply_relin_host: null argument");
+    if (!batch) return 0;
+    FHE_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = nullptr;          // legacy default stream: ordered after everything the caller queued
+    const size_t ct = 2 * (size_t)c->L * c->n * batch;
+    uint64_t* buf = nullptr;
+    FHE_CUDA(cudaMallocAsync(&buf, 3 * ct * sizeof(uint64_t), st));
+    cudaError_t e = cudaMemcpyAsync(buf, h_a, ct * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(buf + ct, h_b, ct * 8, cudaMemcpyHostToDevice, st);
+    int rc = e == cudaSuccess ? fhe_b200_bfv_multiply_relin(c, buf, buf + ct, d_rlk, buf + 2 * ct, nullptr, batch, st) : FHE_B200_ECUDA;
+    if (!rc) e = cudaMemcpyAsync(h_out, buf + 2 * ct, ct * 8, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(buf, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { set_error("bfv_multiply_relin_host: copy failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); return FHE_B200_ECUDA; }
+    return 0;
+}

@@ -1,0 +1,280 @@
+// RNS linear combination kernel: exact base conversion and t/Q scale-and-round in one primitive.
+//
+//   z_i   = use_pre ? x_i * pre_i mod s_i : x_i
+//   I     = ( sum_i ( z_i * Th_i + hi64(z_i * Tl_i) ) + 2^63 ) >> 64                     (192-bit accumulate)
+//   out_k = ( sum_i z_i * M[i][k] + (I mod m_k) * c_k + extra_k * lam_k ) mod m_k      (128-bit lazy accumulate,
+//                                                                                        one Barrett reduction)
+// Replaces fast_base_conversion_kernel / base_extend (/root/reference/include/rns.cuh:47-49,116-125),
+// rns_mod_switch_kernel (:128-136), poly_mod_switch_kernel (include/polynomial.cuh:96-102) and the CRT step of
+// decryption (from_rns_crt_kernel, src/rns.cu:117-141).  Integer only: the overflow count / rounding term is a
+// 128-bit fixed-point sum, so results are exact and identical on every platform.
+//
+// One thread per coefficient: the S source residues stay in registers (compile-time SP), the matrix row for the
+// current target is read from shared memory as a warp-uniform broadcast.  gridDim.y splits the targets when
+// batch*N alone cannot fill the 148 SMs.  IMAD-bound: 4 wide multiplies per (source, target) pair.
+#include "lincomb.cuh"
+#include "host_math.hpp"
+#include <cstring>
+
+namespace fhe_b200 {
+
+struct LcKernelArgs {
+    const u64 *src_mod, *pre, *pre_s, *th_hi, *th_lo;
+    const u64 *dst_mod, *mu_hi, *mu_lo, *c, *lam, *Mt;
+    LcView v;
+    uint32_t S, T, logn, k_per_block, use_pre, use_extra;
+    size_t total;        // batch * n
+};
+
+template <int SP>
+__global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const uint32_t k0 = blockIdx.y * a.k_per_block;
+    const uint32_t k1 = min(a.T, k0 + a.k_per_block);
+    // shared: matrix rows [k1-k0][SP], then per-source arrays (5 x SP)
+    u64* sMt = sm;
+    u64* sSrc = sm + (size_t)a.k_per_block * SP;      // src_mod, pre, pre_s, th_hi, th_lo
+    for (uint32_t t = threadIdx.x; t < (k1 - k0) * SP; t += blockDim.x) sMt[t] = a.Mt[(size_t)k0 * SP + t];
+    for (uint32_t t = threadIdx.x; t < (uint32_t)SP; t += blockDim.x) {
+        sSrc[t] = a.src_mod[t]; sSrc[SP + t] = a.pre[t]; sSrc[2 * SP + t] = a.pre_s[t];
+        sSrc[3 * SP + t] = a.th_hi[t]; sSrc[4 * SP + t] = a.th_lo[t];
+    }
+    __syncthreads();
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.total) return;
+    const uint32_t b = (uint32_t)(g >> a.logn);
+    const uint32_t j = (uint32_t)(g & ((1u << a.logn) - 1));
+    const size_t nn = (size_t)1 << a.logn;
+
+    u64 z[SP];
+    u64 f0 = 0, f1 = 0, f2 = 0;                       // 192-bit fixed-point accumulator
+    const u64* inb = a.v.in + (size_t)b * a.v.in_stride + j;
+#pragma unroll
+    for (int i = 0; i < SP; i++) {
+        u64 x = 0;
+        if (i < (int)a.S) {
+            x = inb[(size_t)a.v.src_idx[i] * nn];
+            if (a.use_pre) x = shoup_mul(x, sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
+        }
+        z[i] = x;
+        u64 ph, pl;
+        mul128(x, sSrc[3 * SP + i], ph, pl);
+        const u64 lo = mulhi64(x, sSrc[4 * SP + i]);
+        add192(f2, f1, f0, ph, pl);
+        add192(f2, f1, f0, 0, lo);
+    }
+    add192(f2, f1, f0, 0, 1ull << 63);
+    const u64 I_hi = f2, I_lo = f1;                   // I = (f2:f1), the rounded integer part
+
+    for (uint32_t k = k0; k < k1; k++) {
+        const u64 m = a.dst_mod[k], mh = a.mu_hi[k], ml = a.mu_lo[k];
+        const u64* row = sMt + (size_t)(k - k0) * SP;
+        u64 hi = 0, lo = 0;
+#pragma unroll
+        for (int i = 0; i < SP; i++) mac128(hi, lo, z[i], row[i]);
+        mac128(hi, lo, barrett128(I_hi, I_lo, m, mh, ml), a.c[k]);
+        if (a.use_extra) mac128(hi, lo, a.v.extra[(size_t)b * a.v.extra_stride + (size_t)a.v.extra_idx[k] * nn + j], a.lam[k]);
+        u64 r = barrett128(hi, lo, m, mh, ml);
+        if (a.v.sub) {
+            const size_t eo = (size_t)a.v.epi_idx[k] * nn + j;
+            const u64 d = sub_mod(a.v.sub[(size_t)b * a.v.sub_stride + eo], r, m);
+            u64 ph, pl;
+            mul128(d, a.v.epi_scalar[k], ph, pl);
+            r = barrett128(ph, pl, m, mh, ml);
+            if (a.v.add) r = add_mod(r, a.v.add[(size_t)b * a.v.add_stride + eo], m);
+        }
+        a.v.out[(size_t)b * a.v.out_stride + (size_t)a.v.dst_idx[k] * nn + j] = r;
+    }
+}
+
+static const int kSupportedSP[] = {1, 2, 3, 4, 5, 6, 7, 8, 12, 16, 20, 24, 25, 28, 32, 40, 48, 56, 62};
+
+static uint32_t pad_sources(uint32_t S) {
+    for (int sp : kSupportedSP) if ((uint32_t)sp >= S) return (uint32_t)sp;
+    return 0;
+}
+
+template <int SP>
+static int launch_sp(const LcKernelArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lincomb_kernel<SP><<<grid, 256, smem, st>>>(a);
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+
+int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_t batch, cudaStream_t st) {
+    FHE_REQUIRE(lc && view.in && view.out, "lincomb: null argument");
+    FHE_REQUIRE(n >= 2 && (n & (n - 1)) == 0, "lincomb: n_coeffs must be a power of two");
+    FHE_REQUIRE(!lc->use_extra || view.extra, "lincomb: this object needs the extra limbs (scale-and-round)");
+    if (!batch) return 0;
+    LcKernelArgs a;
+    a.src_mod = lc->src_mod; a.pre = lc->pre; a.pre_s = lc->pre_s; a.th_hi = lc->th_hi; a.th_lo = lc->th_lo;
+    a.dst_mod = lc->dst_mod; a.mu_hi = lc->mu_hi; a.mu_lo = lc->mu_lo; a.c = lc->c; a.lam = lc->lam; a.Mt = lc->Mt;
+    a.v = view;
+    if (!a.v.src_idx) a.v.src_idx = lc->id_src;
+    if (!a.v.dst_idx) a.v.dst_idx = lc->id_dst;
+    if (!a.v.extra_idx) a.v.extra_idx = lc->id_dst;
+    if (!a.v.epi_idx) a.v.epi_idx = lc->id_dst;
+    if (!a.v.in_stride) a.v.in_stride = (size_t)lc->S * n;
+    if (!a.v.out_stride) a.v.out_stride = (size_t)lc->T * n;
+    if (!a.v.extra_stride) a.v.extra_stride = (size_t)lc->T * n;
+    if (!a.v.sub_stride) a.v.sub_stride = (size_t)lc->T * n;
+    if (!a.v.add_stride) a.v.add_stride = (size_t)lc->T * n;
+    a.S = lc->S; a.T = lc->T; a.logn = host::ilog2(n);
+    a.use_pre = lc->use_pre; a.use_extra = lc->use_extra;
+    a.total = (size_t)batch * n;
+    const uint32_t cblocks = (uint32_t)((a.total + 255) / 256);
+    // split the targets across gridDim.y only when the coefficients alone leave SMs idle (each split recomputes z, I)
+    uint32_t splits = 1;
+    const uint32_t want = 2 * lc->sm_count;
+    if (cblocks < want) { splits = (want + cblocks - 1) / cblocks; const uint32_t maxs = (lc->T + 3) / 4; if (splits > maxs) splits = maxs; if (!splits) splits = 1; }
+    a.k_per_block = (lc->T + splits - 1) / splits;
+    splits = (lc->T + a.k_per_block - 1) / a.k_per_block;
+    const dim3 grid(cblocks, splits);
+    const size_t smem = ((size_t)a.k_per_block * lc->SP + 5 * lc->SP) * sizeof(u64);
+    FHE_REQUIRE(smem <= 200 * 1024, "lincomb: constant block too large for shared memory");
+    switch (lc->SP) {
+#define LC_CASE(N_) case N_: return launch_sp<N_>(a, grid, smem, st);
+        LC_CASE(1) LC_CASE(2) LC_CASE(3) LC_CASE(4) LC_CASE(5) LC_CASE(6) LC_CASE(7) LC_CASE(8) LC_CASE(12) LC_CASE(16)
+        LC_CASE(20) LC_CASE(24) LC_CASE(25) LC_CASE(28) LC_CASE(32) LC_CASE(40) LC_CASE(48) LC_CASE(56) LC_CASE(62)
+#undef LC_CASE
+    }
+    set_error("lincomb: unsupported source count %u", lc->S);
+    return FHE_B200_EINVAL;
+}
+
+int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
+    *out = nullptr;
+    FHE_REQUIRE(h.S >= 1 && h.T >= 1, "lincomb: empty basis");
+    const uint32_t SP = pad_sources(h.S);
+    FHE_REQUIRE(SP != 0, "lincomb: at most 62 source moduli are supported (got %u)", h.S);
+    for (uint32_t i = 0; i < h.S; i++) FHE_REQUIRE(h.src_mod[i] > 1 && (h.src_mod[i] >> 61) == 0, "lincomb: source modulus %u out of range", i);
+    for (uint32_t k = 0; k < h.T; k++) FHE_REQUIRE(h.dst_mod[k] > 1 && (h.dst_mod[k] >> 61) == 0, "lincomb: target modulus %u out of range", k);
+    FHE_CUDA(cudaSetDevice(device));
+    auto* lc = new fhe_b200_lincomb();
+    lc->device = device; lc->S = h.S; lc->T = h.T; lc->SP = SP; lc->use_pre = h.use_pre; lc->use_extra = h.use_extra; lc->h = h;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) lc->sm_count = prop.multiProcessorCount;
+    const uint32_t T = h.T, S = h.S;
+    // blob layout (u64 units): 5 x SP source arrays | 5 x T target arrays | Mt [T][SP] | id_src (u32 x SP) | id_dst (u32 x T)
+    const size_t n64 = 5 * (size_t)SP + 5 * (size_t)T + (size_t)T * SP + (SP + 1) / 2 + (T + 1) / 2 + 2;
+    std::vector<uint64_t> blob(n64, 0);
+    uint64_t* p = blob.data();
+    uint64_t* src_mod = p; p += SP; uint64_t* pre = p; p += SP; uint64_t* pre_s = p; p += SP;
+    uint64_t* th_hi = p; p += SP; uint64_t* th_lo = p; p += SP;
+    uint64_t* dst_mod = p; p += T; uint64_t* mu_hi = p; p += T; uint64_t* mu_lo = p; p += T; uint64_t* cc = p; p += T; uint64_t* lam = p; p += T;
+    uint64_t* Mt = p; p += (size_t)T * SP;
+    uint32_t* id_src = reinterpret_cast<uint32_t*>(p); p += (SP + 1) / 2;
+    uint32_t* id_dst = reinterpret_cast<uint32_t*>(p);
+    for (uint32_t i = 0; i < SP; i++) {
+        src_mod[i] = i < S ? h.src_mod[i] : 3;           // padding sources contribute z = 0
+        if (i < S) { pre[i] = h.pre[i]; pre_s[i] = host::shoup(h.pre[i] % h.src_mod[i], h.src_mod[i]); th_hi[i] = h.th_hi[i]; th_lo[i] = h.th_lo[i]; }
+        id_src[i] = i < S ? i : 0;
+    }
+    for (uint32_t k = 0; k < T; k++) {
+        dst_mod[k] = h.dst_mod[k];
+        host::frac128(1, h.dst_mod[k], mu_hi[k], mu_lo[k]);
+        cc[k] = h.c[k]; lam[k] = h.lam[k]; id_dst[k] = k;
+        for (uint32_t i = 0; i < S; i++) Mt[(size_t)k * SP + i] = h.M[(size_t)i * T + k];
+    }
+    cudaError_t e = cudaMalloc(&lc->d_blob, n64 * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemcpy(lc->d_blob, blob.data(), n64 * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("lincomb: device allocation failed: %s", cudaGetErrorString(e)); delete lc; return FHE_B200_ECUDA; }
+    const uint64_t* d = lc->d_blob;
+    lc->src_mod = d; d += SP; lc->pre = d; d += SP; lc->pre_s = d; d += SP; lc->th_hi = d; d += SP; lc->th_lo = d; d += SP;
+    lc->dst_mod = d; d += T; lc->mu_hi = d; d += T; lc->mu_lo = d; d += T; lc->c = d; d += T; lc->lam = d; d += T;
+    lc->Mt = d; d += (size_t)T * SP;
+    lc->id_src = reinterpret_cast<const uint32_t*>(d); d += (SP + 1) / 2;
+    lc->id_dst = reinterpret_cast<const uint32_t*>(d);
+    *out = lc;
+    return 0;
+}
+
+// ---- drop the last limb with rounding ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) modswitch_drop_last_kernel(u64* __restrict__ out, const u64* __restrict__ in,
+                                                                  const LimbParams* __restrict__ params, const u64* __restrict__ qlast_inv,
+                                                                  uint32_t logn, uint32_t limb_begin, uint32_t limb_count, size_t total) {
+    // total = batch * (limb_count-1) * n output elements
+    const uint32_t n = 1u << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g & (n - 1));
+        const size_t pl = g >> logn;
+        const uint32_t i = (uint32_t)(pl % (limb_count - 1));
+        const size_t b = pl / (limb_count - 1);
+        const LimbParams P = params[limb_begin + i];
+        const u64 ql = params[limb_begin + limb_count - 1].q;
+        const u64 r = in[(b * limb_count + (limb_count - 1)) * n + j];
+        // centred remainder of the dropped limb, reduced modulo q_i
+        u64 rr = barrett128(0, r, P.q, P.mu_hi, P.mu_lo);
+        if (r > (ql >> 1)) rr = sub_mod(rr, barrett128(0, ql, P.q, P.mu_hi, P.mu_lo), P.q);
+        const u64 d = sub_mod(in[(b * limb_count + i) * n + j], rr, P.q);
+        out[g] = mul_mod(d, qlast_inv[i], P);
+    }
+}
+
+}  // namespace fhe_b200
+
+using namespace fhe_b200;
+
+extern "C" int fhe_b200_lincomb_create_conv(const uint64_t* h_src, uint32_t S, const uint64_t* h_dst, uint32_t T, int device,
+                                            fhe_b200_lincomb** out) {
+    FHE_REQUIRE(h_src && h_dst && out && S && T, "lincomb_create_conv: null/empty argument");
+    return lincomb_create(make_conv_consts(h_src, S, h_dst, T), device, out);
+}
+extern "C" int fhe_b200_lincomb_create_scale(const uint64_t* h_q, uint32_t L, const uint64_t* h_p, uint32_t R, uint64_t t,
+                                             const uint64_t* h_targets, uint32_t T, int with_extra, int device,
+                                             fhe_b200_lincomb** out) {
+    FHE_REQUIRE(h_q && h_targets && out && L && T, "lincomb_create_scale: null/empty argument");
+    FHE_REQUIRE(!with_extra || (h_p && R == T), "lincomb_create_scale: with_extra needs targets == the P basis");
+    for (uint32_t i = 0; i < L; i++)
+        for (uint32_t k = 0; k < T; k++)
+            FHE_REQUIRE(h_targets[k] > 1 && host::invmod(h_q[i] % h_targets[k], h_targets[k]) != 0,
+                        "lincomb_create_scale: target %u is not coprime to q_%u", k, i);
+    return lincomb_create(make_scale_consts(h_q, L, h_p, R, t, h_targets, T, with_extra != 0), device, out);
+}
+extern "C" int fhe_b200_lincomb_destroy(fhe_b200_lincomb* lc) {
+    if (!lc) return 0;
+    cudaSetDevice(lc->device);
+    cudaFree(lc->d_blob);
+    delete lc;
+    return 0;
+}
+extern "C" int fhe_b200_lincomb_apply(fhe_b200_lincomb* lc, uint64_t* d_out, const uint64_t* d_in, const uint64_t* d_extra,
+                                      uint32_t n_coeffs, uint32_t batch, void* stream) {
+    FHE_REQUIRE(lc && d_out && d_in, "lincomb_apply: null argument");
+    LcView v; v.in = d_in; v.out = d_out; v.extra = d_extra;
+    return lincomb_launch(lc, v, n_coeffs, batch, (cudaStream_t)stream);
+}
+extern "C" int fhe_b200_lincomb_constants(const fhe_b200_lincomb* lc, uint64_t* pre, uint64_t* th_hi, uint64_t* th_lo,
+                                          uint64_t* M, uint64_t* c, uint64_t* lam) {
+    FHE_REQUIRE(lc, "lincomb_constants: null handle");
+    const auto& h = lc->h;
+    if (pre) memcpy(pre, h.pre.data(), h.S * 8);
+    if (th_hi) memcpy(th_hi, h.th_hi.data(), h.S * 8);
+    if (th_lo) memcpy(th_lo, h.th_lo.data(), h.S * 8);
+    if (M) memcpy(M, h.M.data(), (size_t)h.S * h.T * 8);
+    if (c) memcpy(c, h.c.data(), h.T * 8);
+    if (lam) memcpy(lam, h.lam.data(), h.T * 8);
+    return 0;
+}
+extern "C" int fhe_b200_modswitch_drop_last(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t batch,
+                                            uint32_t limb_begin, uint32_t limb_count, void* stream) {
+    FHE_REQUIRE(plan && d_out && d_in, "modswitch_drop_last: null argument");
+    FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
+    FHE_REQUIRE(limb_count >= 2 && limb_count <= 64, "modswitch_drop_last: needs 2..64 limbs");
+    const size_t total = (size_t)batch * (limb_count - 1) * plan->n;
+    if (!total) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t h_inv[64];
+    const uint64_t ql = plan->moduli[limb_begin + limb_count - 1];
+    for (uint32_t i = 0; i + 1 < limb_count; i++) { const uint64_t qi = plan->moduli[limb_begin + i]; h_inv[i] = host::invmod(ql % qi, qi); }
+    uint64_t* d_inv = nullptr;
+    FHE_CUDA(cudaMallocAsync(&d_inv, 64 * sizeof(uint64_t), st));
+    FHE_CUDA(cudaMemcpyAsync(d_inv, h_inv, (limb_count - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const size_t w = (total + 255) / 256;
+    const uint32_t grid = (uint32_t)(w < (size_t)plan->sm_count * 16 ? w : (size_t)plan->sm_count * 16);
+    modswitch_drop_last_kernel<<<grid, 256, 0, st>>>(d_out, d_in, plan->d_params, d_inv, plan->logn, limb_begin, limb_count, total);
+    FHE_LAUNCH_CHECK();
+    FHE_CUDA(cudaFreeAsync(d_inv, st));
+    return 0;
+}

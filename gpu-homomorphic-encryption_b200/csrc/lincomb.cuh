@@ -1,0 +1,38 @@
+// RNS linear combination (exact base conversion / scale-and-round): object and internal launcher.
+#pragma once
+#include "common.cuh"
+#include "rns_consts.hpp"
+
+struct fhe_b200_lincomb {
+    int device = 0;
+    uint32_t S = 0, T = 0, SP = 0;          // SP: S padded to a supported register-array size
+    bool use_pre = false, use_extra = false;
+    fhe_b200::LincombConsts h;              // host copy (constants getter, tests)
+    uint64_t* d_blob = nullptr;             // all device constants, one allocation
+    // device views into d_blob
+    const uint64_t *src_mod, *pre, *pre_s, *th_hi, *th_lo;     // [SP]
+    const uint64_t *dst_mod, *mu_hi, *mu_lo, *c, *lam;          // [T]
+    const uint64_t* Mt;                                         // [T][SP]
+    const uint32_t *id_src, *id_dst;                            // identity limb maps [SP], [T]
+    int sm_count = 148;
+};
+
+namespace fhe_b200 {
+
+// Where the limbs live.  Polynomial b of the input starts at in + b*in_stride; source limb i is limb src_idx[i] of
+// it; same for out/extra/sub/add with dst_idx.  Epilogue (ModDown): out = (sub - r) * epi_k [+ add]  (mod m_k).
+struct LcView {
+    const uint64_t* in = nullptr; size_t in_stride = 0; const uint32_t* src_idx = nullptr;      // device idx arrays
+    uint64_t* out = nullptr; size_t out_stride = 0; const uint32_t* dst_idx = nullptr;
+    const uint64_t* extra = nullptr; size_t extra_stride = 0;                                    // indexed by dst_idx_extra
+    const uint32_t* extra_idx = nullptr;
+    const uint64_t* sub = nullptr; size_t sub_stride = 0;                                        // epilogue operands, indexed by epi_idx
+    const uint64_t* add = nullptr; size_t add_stride = 0;
+    const uint32_t* epi_idx = nullptr;
+    const uint64_t* epi_scalar = nullptr;                                                        // [T] device
+};
+
+int lincomb_create(const LincombConsts& consts, int device, fhe_b200_lincomb** out);
+int lincomb_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
+
+}  // namespace fhe_b200

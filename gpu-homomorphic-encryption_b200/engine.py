@@ -98,12 +98,16 @@ class Plan:
     def forward(self, x: torch.Tensor, out: torch.Tensor | None = None, limb_begin=0, limb_count=None):
         out = x if out is None else out
         b, lc = self._dims(x, limb_count)
+        if x.numel() == 0:
+            return out
         check(self.lib.fhe_b200_ntt_forward(self.h, _ptr(out), _ptr(x), b, limb_begin, lc, _stream()))
         return out
 
     def inverse(self, x: torch.Tensor, out: torch.Tensor | None = None, limb_begin=0, limb_count=None):
         out = x if out is None else out
         b, lc = self._dims(x, limb_count)
+        if x.numel() == 0:
+            return out
         check(self.lib.fhe_b200_ntt_inverse(self.h, _ptr(out), _ptr(x), b, limb_begin, lc, _stream()))
         return out
 

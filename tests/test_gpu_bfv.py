@@ -1,0 +1,172 @@
+"""GPU parity tests for the RNS layer and the BFV path (run with -m gpu): CUDA through the C ABI vs the CPU oracle,
+bit-exact on every ciphertext word."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def fhe():
+    import fhe_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    fhe_b200.load_library()
+    return fhe_b200
+
+
+def _rand_limbs(rng, mods, n, batch):
+    return np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods]) for _ in range(batch)])
+
+
+@pytest.mark.parametrize("S,T", [(1, 3), (2, 3), (4, 5), (8, 24), (24, 25), (25, 24), (9, 4), (30, 7)])
+def test_base_conversion_vs_oracle(fhe, oracle, chain, S, T):
+    from fhe_b200.engine import to_device, to_host
+    src, dst = chain[:S], chain[S:S + T]
+    n, batch = 256, 3
+    rng = np.random.default_rng(100 + S)
+    x = _rand_limbs(rng, src, n, batch)
+    x[0, :, 0] = 0; x[0, :, 1] = [q - 1 for q in src]; x[0, :, 2] = 1
+    lc = fhe.LinComb.conv(src, dst)
+    olc = oracle.LinComb.conv(src, dst)
+    got = to_host(lc.apply(to_device(x)))
+    for b in range(batch):
+        assert np.array_equal(got[b], olc.apply(x[b])), b
+    cg, co = lc.constants(), olc.constants()
+    for k in co:
+        assert np.array_equal(cg[k], co[k]), k
+
+
+@pytest.mark.parametrize("L,R,t", [(1, 2, 65537), (2, 3, 65537), (4, 5, 786433), (24, 25, 65537), (3, 4, 1 << 20)])
+def test_scale_and_round_vs_oracle(fhe, oracle, chain, L, R, t):
+    from fhe_b200.engine import to_device, to_host
+    qs, ps = chain[:L], chain[L:L + R]
+    n, batch = 512, 2
+    rng = np.random.default_rng(200 + L)
+    dq = _rand_limbs(rng, qs, n, batch); dp = _rand_limbs(rng, ps, n, batch)
+    lc = fhe.LinComb.scale(qs, ps, t, ps, True)
+    olc = oracle.LinComb.scale(qs, ps, t, ps, True)
+    got = to_host(lc.apply(to_device(dq), to_device(dp)))
+    for b in range(batch):
+        assert np.array_equal(got[b], olc.apply(dq[b], extra=dp[b]))
+    # decryption scaling: targets = {t}
+    lcd = fhe.LinComb.scale(qs, [], t, [t], False)
+    old = oracle.LinComb.scale(qs, [], t, [t], False)
+    got = to_host(lcd.apply(to_device(dq)))
+    for b in range(batch):
+        assert np.array_equal(got[b], old.apply(dq[b]))
+
+
+def test_modswitch_drop_last_vs_oracle(fhe, oracle, chain):
+    from fhe_b200.engine import to_device, to_host
+    n, mods = 1024, chain[:4]
+    plan = fhe.Plan(n, mods)
+    rng = np.random.default_rng(300)
+    x = _rand_limbs(rng, mods, n, 2)
+    x[0, 3, :4] = [0, mods[3] // 2, mods[3] // 2 + 1, mods[3] - 1]
+    got = to_host(plan.modswitch_drop_last(to_device(x)))
+    for b in range(2):
+        assert np.array_equal(got[b], oracle.modswitch_drop_last(x[b], mods))
+
+
+def test_gaussian_cdt_matches_oracle(fhe, oracle):
+    for sigma in (3.2, 3.19, 1.0, 8.0):
+        assert np.array_equal(fhe.gaussian_cdt(sigma), oracle.gaussian_cdt(sigma))
+
+
+def _setup(fhe, oracle, preset, hw=None):
+    from fhe_b200.params import bfv_preset
+    p = bfv_preset(preset)
+    if hw is not None:
+        p["hamming_weight"] = hw
+    g = fhe.BfvContext(p["n"], p["L"], p["R"], p["K"], p["dnum"], p["t"], p["primes"], p["sigma"], p["hamming_weight"])
+    o = oracle.Bfv(p["n"], p["L"], p["R"], p["K"], p["dnum"], p["t"], p["primes"], sigma=p["sigma"], hw=p["hamming_weight"])
+    return p, g, o
+
+
+@pytest.mark.parametrize("preset,hw", [("small", 64), ("small", 0), ("c2", 64)])
+def test_bfv_keys_encrypt_decrypt_add_vs_oracle(fhe, oracle, preset, hw):
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, preset, hw)
+    n, t = p["n"], p["t"]
+    sk, pk = g.keygen(11, 12)
+    s_small, osk = o.secret_keygen(11)
+    opk = o.public_keygen(12, osk)
+    assert np.array_equal(to_host(sk), osk)
+    assert np.array_equal(to_host(pk), opk)
+    rlk = g.relinkey_gen(13, sk)
+    assert np.array_equal(to_host(rlk), o.relin_keygen(13, osk))
+    rng = np.random.default_rng(400)
+    m = rng.integers(0, t, (3, n), dtype=np.uint64)
+    m[0, :4] = [5, 10, 15, 20]; m[0, 4:] = 0            # tests/test_fhe.cu:201
+    m[1, :4] = [3, 6, 9, 12]; m[1, 4:] = 0              # tests/test_fhe.cu:202
+    ct = g.encrypt(500, to_device(m), pk)               # ciphertext b uses seed 500+b
+    h = to_host(ct)
+    for b in range(3):
+        assert np.array_equal(h[b], o.encrypt(500 + b, m[b], opk)), b
+    assert np.array_equal(to_host(g.decrypt(ct, sk)), m)
+    s = g.add(ct[0:1].contiguous(), ct[1:2].contiguous())
+    assert np.array_equal(to_host(s)[0], o.add(h[0], h[1]))
+    assert [int(v) for v in to_host(g.decrypt(s, sk))[0, :4]] == [8, 16, 24, 32]      # tests/test_fhe.cu:264
+    # reference example: encrypt -> decrypt identity on {42,100,255,1337} (examples/basic_encryption.cu:46,90-106)
+    pt = g.encode([42, 100, 255, 1337])
+    assert [int(v) for v in g.decode(g.decrypt(g.encrypt(7, pt, pk), sk))[0, :4]] == [42, 100, 255, 1337]
+
+
+@pytest.mark.parametrize("preset", ["small", "c2"])
+def test_bfv_multiply_relin_vs_oracle(fhe, oracle, preset):
+    """BASELINE.json config 2 (preset c2): every ciphertext word equals the oracle's; decrypts to the negacyclic product."""
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, preset)
+    n, t = p["n"], p["t"]
+    sk, pk = g.keygen(21, 22); rlk = g.relinkey_gen(23, sk)
+    _, osk = o.secret_keygen(21); orlk = o.relin_keygen(23, osk)
+    rng = np.random.default_rng(600)
+    m1 = rng.integers(0, t, (2, n), dtype=np.uint64); m2 = rng.integers(0, t, (2, n), dtype=np.uint64)
+    m1[0] = 0; m1[0, :4] = [5, 10, 15, 20]; m2[0] = 0; m2[0, :4] = [3, 6, 9, 12]
+    ca = g.encrypt(700, to_device(m1), pk); cb = g.encrypt(800, to_device(m2), pk)
+    out, sc = g.multiply(ca, cb, rlk, want_scaled=True)
+    ha, hb, ho, hs = to_host(ca), to_host(cb), to_host(out), to_host(sc)
+    for b in range(2):
+        eo, es = o.multiply_relin(ha[b], hb[b], orlk, want_scaled=True)
+        assert np.array_equal(hs[b], es), ("scaled tensor", b)
+        assert np.array_equal(ho[b], eo), ("relinearised", b)
+    dec = to_host(g.decrypt(out, sk))
+    assert [int(v) for v in dec[0, :8]] == [15, 60, 150, 300, 375, 360, 240, 0]
+    assert np.array_equal(dec[1], oracle.schoolbook_negacyclic(m1[1], m2[1], t))
+    # depth 2
+    out2 = g.multiply(out, ca, rlk)
+    exp = oracle.schoolbook_negacyclic(oracle.schoolbook_negacyclic(m1[1], m2[1], t), m1[1], t)
+    assert np.array_equal(to_host(g.decrypt(out2, sk))[1], exp)
+    # host-buffer entry point gives the same words
+    h_out = np.zeros_like(ha)
+    g.multiply_host(ha, hb, rlk, h_out)
+    assert np.array_equal(h_out, ho)
+
+
+@pytest.mark.slow
+def test_bfv_config4_properties(fhe, oracle):
+    """BASELINE.json config 4 at full size (N=2^16, L=24, R=25, dnum=3, K=8).  The oracle needs minutes here, so the
+    check is by properties: decrypt(HMult(enc m1, enc m2)) == m1*m2 mod (x^N+1, t) (host NTT product), add is
+    homomorphic, and two limbs of the key material are spot-checked against the oracle's samplers."""
+    from fhe_b200.engine import to_device, to_host
+    from fhe_b200.params import bfv_preset
+    p = bfv_preset("c4")
+    n, t = p["n"], p["t"]
+    g = fhe.BfvContext(n, p["L"], p["R"], p["K"], p["dnum"], t, p["primes"], p["sigma"], p["hamming_weight"])
+    sk, pk = g.keygen(31, 32); rlk = g.relinkey_gen(33, sk)
+    q0 = p["primes"][0]
+    assert np.array_equal(to_host(pk)[1, 0], oracle.sample_uniform(n, q0, 32, 16))
+    rng = np.random.default_rng(900)
+    m1 = rng.integers(0, t, n, dtype=np.uint64); m2 = rng.integers(0, t, n, dtype=np.uint64)
+    ca = g.encrypt(41, to_device(m1.reshape(1, n)), pk); cb = g.encrypt(42, to_device(m2.reshape(1, n)), pk)
+    assert np.array_equal(to_host(g.decrypt(ca, sk))[0], m1)
+    out = g.multiply(ca, cb, rlk)
+    # t = 65537 = 1 mod 2^17: the plaintext ring supports an NTT, use the oracle's NTT product as the expectation
+    assert np.array_equal(to_host(g.decrypt(out, sk))[0], oracle.negacyclic_mul_ntt(m1, m2, t))
+    out2 = g.multiply(out, cb, rlk)
+    assert np.array_equal(to_host(g.decrypt(out2, sk))[0], oracle.negacyclic_mul_ntt(oracle.negacyclic_mul_ntt(m1, m2, t), m2, t))
+    s = g.add(ca, cb)
+    assert np.array_equal(to_host(g.decrypt(s, sk))[0], (m1 + m2) % np.uint64(t))
