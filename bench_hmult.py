@@ -47,7 +47,10 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
     # correctness of what was timed: decrypt one result
     import oracle
     dec = to_host(g.decrypt(out, sk))
-    ok = bool(np.array_equal(dec[0], oracle.negacyclic_mul_ntt(m1[0], m2[0], t)))
+    q0 = p["primes"][0]                      # |coeff of the integer product| < N t^2 < q0/2: centred lift is exact
+    r = oracle.negacyclic_mul_ntt(m1[0], m2[0], q0)
+    signed = np.where(r > np.uint64(q0 // 2), r.astype(np.int64) - np.int64(q0), r.astype(np.int64))
+    ok = bool(np.array_equal(dec[0], np.mod(signed, np.int64(t)).astype(np.uint64)))
     # end to end with host buffers
     ha, hb = pinned_empty(tuple(ca.shape)), pinned_empty(tuple(cb.shape))
     ha[...] = to_host(ca); hb[...] = to_host(cb)

@@ -103,8 +103,21 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
             delete p; return FHE_B200_EINVAL;
         }
     }
+    p->tiles = 1u << (p->logn - (uint32_t)tile_lb(p->logn));
+    p->p3_entries = tile_p3_entries(p->logn);
+    const size_t n12 = (size_t)p->tiles * 256, n3 = (size_t)p->tiles * p->p3_entries;
+    std::vector<Twiddle> f12(n_limbs * n12), f3(n_limbs * n3), i12(n_limbs * n12), i3(n_limbs * n3);
+    for (uint32_t l = 0; l < n_limbs; l++) {
+        build_tile_tables(fwd.data() + (size_t)l * n, p->logn, f12.data() + l * n12, f3.data() + l * n3);
+        build_tile_tables(inv.data() + (size_t)l * n, p->logn, i12.data() + l * n12, i3.data() + l * n3);
+    }
     const size_t tb = (size_t)n_limbs * n * sizeof(Twiddle);
     cudaError_t e = cudaMalloc(&p->d_fwd, tb);
+    auto up = [&](Twiddle** dst, const std::vector<Twiddle>& src) {
+        if (e == cudaSuccess) e = cudaMalloc(dst, src.size() * sizeof(Twiddle));
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(Twiddle), cudaMemcpyHostToDevice);
+    };
+    up(&p->d_fwd_p12, f12); up(&p->d_fwd_p3, f3); up(&p->d_inv_p12, i12); up(&p->d_inv_p3, i3);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_inv, tb);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_params, n_limbs * sizeof(LimbParams));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_fwd, fwd.data(), tb, cudaMemcpyHostToDevice);
@@ -123,6 +136,7 @@ extern "C" int fhe_b200_plan_destroy(fhe_b200_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     cudaFree(p->d_fwd); cudaFree(p->d_inv); cudaFree(p->d_params);
+    cudaFree(p->d_fwd_p12); cudaFree(p->d_fwd_p3); cudaFree(p->d_inv_p12); cudaFree(p->d_inv_p3);
     for (int i = 0; i < 3; i++) { if (p->d_stage[i]) cudaFree(p->d_stage[i]); if (p->hs[i]) cudaStreamDestroy(p->hs[i]); }
     delete p;
     return 0;

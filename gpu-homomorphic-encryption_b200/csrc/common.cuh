@@ -48,6 +48,10 @@ struct fhe_b200_plan {
     std::vector<uint64_t> moduli;
     fhe_b200::Twiddle* d_fwd = nullptr;            // [limbs][n]
     fhe_b200::Twiddle* d_inv = nullptr;            // [limbs][n]
+    // per-tile staged blocks of the tile pass (one bulk copy each): [limbs][tiles][256] and [limbs][tiles][p3]
+    fhe_b200::Twiddle *d_fwd_p12 = nullptr, *d_fwd_p3 = nullptr, *d_inv_p12 = nullptr, *d_inv_p3 = nullptr;
+    size_t p3_entries = 0;                         // per tile
+    uint32_t tiles = 1;                            // tiles per limb = 2^K1
     fhe_b200::LimbParams* d_params = nullptr;      // [limbs]
     std::vector<fhe_b200::LimbParams> h_params;
     size_t chunk_bytes = 32u << 20;                // L2-resident working set between pass A and pass B

@@ -64,11 +64,48 @@ FHE_HDC int inv_bound_after(int B, int stages, int HB) {
     return B;
 }
 
+// ---- twiddle accessors: where stage v / group key of the current sub-transform finds its twiddle ------------------
+// global table, SEAL-style index (root << (SH0+v)) + key
+template <int SH0>
+struct TwGlobal {
+    const Twiddle* tw; u32 root;
+    FHE_HD Twiddle get(int v, int key) const { return ld_tw(tw + ((root << (SH0 + v)) + key)); }
+};
+FHE_HD Twiddle ld_tw_s(const Twiddle* p) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
+    Twiddle w; w.w = t.x; w.ws = t.y; return w;
+#else
+    return *p;
+#endif
+}
+// Per-tile staged tables (shared memory on the device).  Layout of one tile's block "p12" (256 entries):
+//   phase 1 (first 4 tile stages, uniform over the CTA):   [ (1<<v)-1 + key ]                       v<4, key<2^v   (15)
+//   phase 2 (next 4, depends on hi = tid >> (LB-8) < 16):  [ 15 + 16*((1<<v)-1) + (hi<<v) + key ]                 (240)
+// and of the block "p3" (last R3 = LB-8 stages, every thread its own twiddles), stored [stage][key][tid] so that
+// consecutive lanes read consecutive 16-byte entries:        [ NT*KB*((1<<v)-1) + key*NT + tid ],  KB = 2^(4-R3), key < KB*2^v
+struct TwP1 {
+    const Twiddle* s;
+    FHE_HD Twiddle get(int v, int key) const { return ld_tw_s(s + ((1 << v) - 1 + key)); }
+};
+struct TwP2 {
+    const Twiddle* s; u32 hi;
+    FHE_HD Twiddle get(int v, int key) const { return ld_tw_s(s + (15 + 16 * ((1 << v) - 1) + (hi << v) + key)); }
+};
+template <int NT, int R3>
+struct TwP3 {
+    const Twiddle* s; u32 tid;
+    FHE_HD Twiddle get(int v, int key) const { return ld_tw_s(s + (NT * (1 << (4 - R3)) * ((1 << v) - 1) + key * NT + tid)); }
+};
+// sizes (entries) of the staged blocks
+FHE_HDC int p12_entries() { return 256; }
+FHE_HDC int p3_entries(int LB) { return (1 << (LB - 4)) * (16 - (1 << (12 - LB))); }
+
 // ---- forward stages on a register array of E = 2^LE elements: R stages, active bits = low R bits of e ----
 // B (template) is the bound on entry in units of q; the bound on exit is fwd_bound_after(B, R, HB).
 // Compile-time recursion over the stage index V keeps every array index and every bound a constant.
-template <int LE, int R, int HB, int B, int V = 0>
-FHE_HD void fwd_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, u64 q) {
+template <int LE, int R, int HB, int B, class TW, int V = 0>
+FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, u64 q) {
     if constexpr (V < R) {
         constexpr int st = 1 << (R - 1 - V);
         constexpr int sh = LE - R + V;
@@ -77,7 +114,7 @@ FHE_HD void fwd_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, u64 q) {
         const u64 hq = (u64)(HB / 2) * q;
 #pragma unroll
         for (int key = 0; key < (1 << sh); key++) {
-            const Twiddle w = ld_tw(tw + ((root << sh) + key));
+            const Twiddle w = tw.get(V, key);
 #pragma unroll
             for (int j = 0; j < st; j++) {
                 const int e = (key << (R - V)) | j;
@@ -88,14 +125,14 @@ FHE_HD void fwd_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, u64 q) {
                 x[e + st] = X + twoq - T;
             }
         }
-        fwd_stages<LE, R, HB, (red ? HB / 2 : B) + 2, V + 1>(x, tw, root, q);
+        fwd_stages<LE, R, HB, (red ? HB / 2 : B) + 2, TW, V + 1>(x, tw, q);
     }
 }
 
 // ---- inverse stages (mirror order: V runs R-1 .. 0).  LAST: the final stage of the whole transform folds N^-1 in.
 // exit bound: inv_bound_after(B, R, HB), or 2 when LAST.
-template <int LE, int R, int HB, bool LAST, int B, int V = R - 1>
-FHE_HD void inv_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, const LimbParams& P) {
+template <int LE, int R, int HB, bool LAST, int B, class TW, int V = R - 1>
+FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
     if constexpr (V >= 0) {
         constexpr int st = 1 << (R - 1 - V);
         constexpr int sh = LE - R + V;
@@ -107,7 +144,7 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, const Lim
         for (int key = 0; key < (1 << sh); key++) {
             Twiddle w;
             if (last) { w.w = P.w1ninv; w.ws = P.w1ninv_s; }
-            else w = ld_tw(tw + ((root << sh) + key));
+            else w = tw.get(V, key);
 #pragma unroll
             for (int j = 0; j < st; j++) {
                 const int e = (key << (R - V)) | j;
@@ -120,7 +157,7 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const Twiddle* tw, u32 root, const Lim
                 x[e + st] = shoup_mul_lazy(D, w.w, w.ws, q);
             }
         }
-        inv_stages<LE, R, HB, LAST, (red ? B : 2 * B), V - 1>(x, tw, root, P);
+        inv_stages<LE, R, HB, LAST, (red ? B : 2 * B), TW, V - 1>(x, tw, P);
     }
 }
 
@@ -139,7 +176,7 @@ FHE_HD u64 normalize(u64 x, u64 q) {
 // Split into phases separated by a block barrier; phase functions are what the emulator calls.
 //   g    : tile base in global memory (in place)
 //   s    : NB u64 of shared memory
-//   root : 2^K1 + tile index within the limb
+//   s12/s3 : this tile's staged twiddle blocks (see TwP1/TwP2/TwP3), copied from the plan's per-tile tables
 //   B0   : entry bound (1 + 2*K1 after pass A, 1 when K1 = 0)
 // =====================================================================================================
 template <int LB, int HB>
@@ -149,28 +186,36 @@ struct TileFwd {
     static constexpr int R3 = LB - 8;
     static_assert(LB >= 9 && LB <= 12, "tile pass supports 512..4096 elements");
 
-    template <int B0>
-    static FHE_HD void phase1(u32 tid, const u64* g, u64* s, const Twiddle* tw, u32 root, u64 q) {
-        u64 x[16];
+    // phase 1 is split so that the kernel can issue the global loads before it waits for the staged twiddles
+    static FHE_HD void phase1_load(u32 tid, const u64* g, u64 (&x)[16]) {
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = g[(e << (LB - 4)) | tid];
-        fwd_stages<4, 4, HB, B0>(x, tw, root, q);
+    }
+    template <int B0>
+    static FHE_HD void phase1_compute(u32 tid, u64 (&x)[16], u64* s, const Twiddle* s12, u64 q) {
+        fwd_stages<4, 4, HB, B0>(x, TwP1{s12}, q);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz((e << (LB - 4)) | tid)] = x[e];
     }
     template <int B0>
-    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* tw, u32 root, u64 q) {
+    static FHE_HD void phase1(u32 tid, const u64* g, u64* s, const Twiddle* s12, u64 q) {
+        u64 x[16];
+        phase1_load(tid, g, x);
+        phase1_compute<B0>(tid, x, s, s12, q);
+    }
+    template <int B0>
+    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* s12, u64 q) {
         const u32 lo = tid & ((1u << (LB - 8)) - 1), hi = tid >> (LB - 8);
         const u32 base = (hi << (LB - 4)) | lo;
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz(base | (e << (LB - 8)))];
-        fwd_stages<4, 4, HB, fwd_bound_after(B0, 4, HB)>(x, tw, (root << 4) + hi, q);
+        fwd_stages<4, 4, HB, fwd_bound_after(B0, 4, HB)>(x, TwP2{s12, hi}, q);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
     }
     template <int B0>
-    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* tw, u32 root, u64 q) {
+    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* s3, u64 q) {
         u64 x[16];
         const u32 row = tid << 4;
 #pragma unroll
@@ -180,7 +225,7 @@ struct TileFwd {
         }
         constexpr int B3 = fwd_bound_after(B0, 8, HB);
         constexpr int BE = fwd_bound_after(B3, R3, HB);
-        fwd_stages<4, R3, HB, B3>(x, tw, (root << (4 + R3)) + tid, q);
+        fwd_stages<4, R3, HB, B3>(x, TwP3<NT, R3>{s3, tid}, q);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
@@ -215,7 +260,7 @@ struct TileInv {
             u64 a, b; ld2(g + 2 * c, a, b); st2(s + 2 * p, a, b);
         }
     }
-    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* tw, u32 root, const LimbParams& P) {
+    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* s3, const LimbParams& P) {
         u64 x[16];
         const u32 row = tid << 4;
 #pragma unroll
@@ -223,29 +268,29 @@ struct TileInv {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
             ld2(s + a, x[2 * k], x[2 * k + 1]);
         }
-        inv_stages<4, R3, HB, false, 1>(x, tw, (root << (4 + R3)) + tid, P);
+        inv_stages<4, R3, HB, false, 1>(x, TwP3<NT, R3>{s3, tid}, P);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
             st2(s + a, x[2 * k], x[2 * k + 1]);
         }
     }
-    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* tw, u32 root, const LimbParams& P) {
+    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* s12, const LimbParams& P) {
         const u32 lo = tid & ((1u << (LB - 8)) - 1), hi = tid >> (LB - 8);
         const u32 base = (hi << (LB - 4)) | lo;
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz(base | (e << (LB - 8)))];
-        inv_stages<4, 4, HB, false, inv_bound_after(1, R3, HB)>(x, tw, (root << 4) + hi, P);
+        inv_stages<4, 4, HB, false, inv_bound_after(1, R3, HB)>(x, TwP2{s12, hi}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
     }
     template <bool LAST>
-    static FHE_HD void phase4(u32 tid, u64* g, const u64* s, const Twiddle* tw, u32 root, const LimbParams& P) {
+    static FHE_HD void phase4(u32 tid, u64* g, const u64* s, const Twiddle* s12, const LimbParams& P) {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz((e << (LB - 4)) | tid)];
-        inv_stages<4, 4, HB, LAST, inv_bound_after(1, R3 + 4, HB)>(x, tw, root, P);
+        inv_stages<4, 4, HB, LAST, inv_bound_after(1, R3 + 4, HB)>(x, TwP1{s12}, P);
         // LAST: fully reduce.  Otherwise leave the lazy bound for pass A' (it starts from out_bound()).
 #pragma unroll
         for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? csub(x[e], P.q) : x[e];
@@ -270,7 +315,7 @@ struct RowPass {
             else x[0][r] = gin[(size_t)r * NB + col];
         }
 #pragma unroll
-        for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, 1>(x[c], tw, 1u, q);
+        for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, 1>(x[c], TwGlobal<0>{tw, 1u}, q);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
             if (V == 2) st2(gout + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
@@ -288,7 +333,7 @@ struct RowPass {
             else x[0][r] = g[(size_t)r * NB + col];
         }
 #pragma unroll
-        for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, true, B0>(x[c], tw, 1u, P);
+        for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, true, B0>(x[c], TwGlobal<0>{tw, 1u}, P);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
             if (V == 2) st2(g + (size_t)r * NB + col, csub(x[0][r], P.q), csub(x[V - 1][r], P.q));

@@ -1,80 +1,129 @@
 // __global__ wrappers and launchers of the batched negacyclic NTT (bodies in ntt_core.cuh).
 //
 // Work decomposition over a batch laid out [batch][limb_count][N]:
-//   tile pass : one CTA of 2^(LB-4) threads per (limb, tile, polynomial); CTAs that share (limb, tile) -- hence the
-//               same twiddles -- are adjacent in blockIdx so the twiddle lines are hot in L2 when their
-//               neighbours ask for them.
+//   tile pass : one CTA of 2^(LB-4) threads per (limb, tile, polynomial group).  The CTA stages the tile's twiddles in
+//               shared memory once (two cp.async.bulk copies completing on an mbarrier) and reuses them for every
+//               polynomial of its group; CTAs that share (limb, tile) are adjacent in blockIdx (L2 hits).
 //   row pass  : one thread per V adjacent columns of a (limb, polynomial); 256-thread CTAs.
 // For N > 4096 the two passes are issued chunk by chunk (plan->chunk_bytes of polynomials at a time) so that the
 // intermediate written by the first pass is still L2-resident (126 MB on B200) when the second pass reads it:
 // HBM then sees one read and one write per limb-transform.
 #include "common.cuh"
 #include "ntt_core.cuh"
+#include "tma.cuh"
 
 namespace fhe_b200 {
 
 struct NttArgs {
     uint64_t* out;
     const uint64_t* in;
-    const Twiddle* tw;           // [limbs][n] table of the direction in use
+    const Twiddle* tw;           // [limbs][n] table of the direction in use (row pass)
+    const Twiddle* p12;          // [limbs][tiles][256] staged blocks of the tile pass
+    const Twiddle* p3;           // [limbs][tiles][p3n]
     const LimbParams* params;    // [limbs]
     uint32_t n;                  // ring degree
     uint32_t limb_count;         // limbs per polynomial in the buffer
     uint32_t limb_begin;         // first plan limb the buffer's limb 0 maps to
     uint32_t l0, nl;             // chunk: buffer limbs [l0, l0+nl)
     uint32_t b0, nb;             // chunk: polynomials [b0, b0+nb)
+    uint32_t groups;             // tile pass: CTAs per (limb, tile); CTA g handles polynomials b0+g, b0+g+groups, ...
+    uint32_t tiles, p3n;
 };
 
-// (limb, tile/column-block, polynomial) from a linear CTA index with the polynomial fastest
-__device__ __forceinline__ void decode(const NttArgs& a, uint32_t i, uint32_t units, uint32_t& limb, uint32_t& unit,
-                                       uint32_t& poly) {
-    poly = a.b0 + i % a.nb;
-    const uint32_t r = i / a.nb;
+// (limb, tile/column-block, polynomial or group) from a linear CTA index, innermost fastest
+__device__ __forceinline__ void decode(uint32_t i, uint32_t inner, uint32_t units, uint32_t l0, uint32_t& limb, uint32_t& unit,
+                                       uint32_t& in_idx) {
+    in_idx = i % inner;
+    const uint32_t r = i / inner;
     unit = r % units;
-    limb = a.l0 + r / units;
+    limb = l0 + r / units;
 }
 
+template <int LB>
+struct TileSmem {
+    static constexpr int NB = 1 << LB;
+    static constexpr size_t data_bytes = (size_t)NB * 8;
+    static constexpr size_t p12_bytes = 256 * sizeof(Twiddle);
+    static constexpr size_t p3_bytes = (size_t)p3_entries(LB) * sizeof(Twiddle);
+    static constexpr size_t total = data_bytes + p12_bytes + p3_bytes + 16;
+};
+
+// One CTA = one (limb, tile): stages that tile's twiddles once with two bulk copies (TMA), then runs the tile pass for
+// every polynomial of its group out of shared memory.
 template <int LB, int K1, int HB>
-__global__ void __launch_bounds__(1 << (LB - 4)) ntt_tile_fwd_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const NttArgs a) {
     using T = TileFwd<LB, HB>;
-    __shared__ __align__(16) u64 s[T::NB];
-    uint32_t limb, tile, poly;
-    decode(a, blockIdx.x, 1u << K1, limb, tile, poly);
-    const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)tile * T::NB;
+    using SM = TileSmem<LB>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u64* s = reinterpret_cast<u64*>(smem_raw);
+    Twiddle* s12 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes);
+    Twiddle* s3 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes + SM::p12_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::data_bytes + SM::p12_bytes + SM::p3_bytes);
+    uint32_t limb, tile, grp;
+    decode(blockIdx.x, a.groups, 1u << K1, a.l0, limb, tile, grp);
     const uint32_t pl = a.limb_begin + limb;
-    const Twiddle* tw = a.tw + (size_t)pl * a.n;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)(SM::p12_bytes + SM::p3_bytes));
+        bulk_copy_g2s(s12, a.p12 + ((size_t)pl * a.tiles + tile) * 256, (uint32_t)SM::p12_bytes, bar);
+        bulk_copy_g2s(s3, a.p3 + ((size_t)pl * a.tiles + tile) * a.p3n, (uint32_t)SM::p3_bytes, bar);
+    }
     const u64 q = a.params[pl].q;
-    const uint32_t root = (1u << K1) + tile;
     constexpr int B0 = fwd_bound_after(1, K1, HB);
-    // K1 > 0: the row pass already moved the data to `out`
-    const u64* src = (K1 > 0 ? a.out : a.in) + off;
-    T::template phase1<B0>(threadIdx.x, src, s, tw, root, q);
-    __syncthreads();
-    T::template phase2<B0>(threadIdx.x, s, tw, root, q);
-    __syncthreads();
-    T::template phase3<B0>(threadIdx.x, s, tw, root, q);
-    __syncthreads();
-    T::phase4(threadIdx.x, a.out + off, s);
+    bool staged = false;
+    for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
+        const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)tile * T::NB;
+        const u64* src = (K1 > 0 ? a.out : a.in) + off;      // K1 > 0: the row pass already moved the data to `out`
+        u64 x[16];
+        T::phase1_load(tid, src, x);
+        if (!staged) { mbar_wait(bar, 0); staged = true; }
+        T::template phase1_compute<B0>(tid, x, s, s12, q);
+        __syncthreads();
+        T::template phase2<B0>(tid, s, s12, q);
+        __syncthreads();
+        T::template phase3<B0>(tid, s, s3, q);
+        __syncthreads();
+        T::phase4(tid, a.out + off, s);
+        __syncthreads();
+    }
 }
 
 template <int LB, int K1, int HB>
-__global__ void __launch_bounds__(1 << (LB - 4)) ntt_tile_inv_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_inv_kernel(const NttArgs a) {
     using T = TileInv<LB, HB>;
-    __shared__ __align__(16) u64 s[T::NB];
-    uint32_t limb, tile, poly;
-    decode(a, blockIdx.x, 1u << K1, limb, tile, poly);
-    const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)tile * T::NB;
+    using SM = TileSmem<LB>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u64* s = reinterpret_cast<u64*>(smem_raw);
+    Twiddle* s12 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes);
+    Twiddle* s3 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes + SM::p12_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::data_bytes + SM::p12_bytes + SM::p3_bytes);
+    uint32_t limb, tile, grp;
+    decode(blockIdx.x, a.groups, 1u << K1, a.l0, limb, tile, grp);
     const uint32_t pl = a.limb_begin + limb;
-    const Twiddle* tw = a.tw + (size_t)pl * a.n;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)(SM::p12_bytes + SM::p3_bytes));
+        bulk_copy_g2s(s12, a.p12 + ((size_t)pl * a.tiles + tile) * 256, (uint32_t)SM::p12_bytes, bar);
+        bulk_copy_g2s(s3, a.p3 + ((size_t)pl * a.tiles + tile) * a.p3n, (uint32_t)SM::p3_bytes, bar);
+    }
     const LimbParams P = a.params[pl];
-    const uint32_t root = (1u << K1) + tile;
-    T::phase1(threadIdx.x, a.in + off, s);
-    __syncthreads();
-    T::phase2(threadIdx.x, s, tw, root, P);
-    __syncthreads();
-    T::phase3(threadIdx.x, s, tw, root, P);
-    __syncthreads();
-    T::template phase4<K1 == 0>(threadIdx.x, a.out + off, s, tw, root, P);
+    bool staged = false;
+    for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
+        const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)tile * T::NB;
+        T::phase1(tid, a.in + off, s);
+        if (!staged) { mbar_wait(bar, 0); staged = true; }
+        __syncthreads();
+        T::phase2(tid, s, s3, P);
+        __syncthreads();
+        T::phase3(tid, s, s12, P);
+        __syncthreads();
+        T::template phase4<K1 == 0>(tid, a.out + off, s, s12, P);
+        __syncthreads();
+    }
 }
 
 constexpr int kRowThreads = 256;
@@ -83,7 +132,8 @@ template <int LB, int K1, int HB, int V>
 __global__ void __launch_bounds__(kRowThreads) ntt_row_fwd_kernel(const NttArgs a) {
     constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
     uint32_t limb, cb, poly;
-    decode(a, blockIdx.x, blocks_per_pl, limb, cb, poly);
+    decode(blockIdx.x, a.nb, blocks_per_pl, a.l0, limb, cb, poly);
+    poly += a.b0;
     const size_t off = ((size_t)poly * a.limb_count + limb) * a.n;
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t col = (cb * kRowThreads + threadIdx.x) * V;
@@ -94,7 +144,8 @@ template <int LB, int K1, int HB, int V>
 __global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs a) {
     constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
     uint32_t limb, cb, poly;
-    decode(a, blockIdx.x, blocks_per_pl, limb, cb, poly);
+    decode(blockIdx.x, a.nb, blocks_per_pl, a.l0, limb, cb, poly);
+    poly += a.b0;
     const size_t off = ((size_t)poly * a.limb_count + limb) * a.n;
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t col = (cb * kRowThreads + threadIdx.x) * V;
@@ -104,11 +155,26 @@ __global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs 
 }
 
 template <int LB, int K1, int HB>
-static int run_chunk(const NttArgs& a, bool inverse, cudaStream_t st) {
+static int run_chunk(NttArgs a, bool inverse, int sm_count, cudaStream_t st) {
     constexpr int V = (K1 >= 5) ? 1 : 2;
     const uint32_t pls = a.nl * a.nb;
-    const uint32_t tile_grid = pls << K1;
     const bool prof = profile_on();
+    // tile pass: one CTA per (limb, tile, group); a CTA reuses its staged twiddles for every polynomial of its group.
+    // Keep >= 8 CTAs per SM in the grid when the batch allows it, otherwise reuse as much as possible (8 polynomials/CTA).
+    const uint32_t lt = a.nl << K1;
+    uint32_t groups = (uint32_t)((8u * sm_count + lt - 1) / lt);
+    const uint32_t min_groups = (a.nb + 7) / 8;
+    if (groups < min_groups) groups = min_groups;
+    if (groups > a.nb) groups = a.nb;
+    a.groups = groups;
+    const uint32_t tile_grid = lt * groups;
+    constexpr size_t smem = TileSmem<LB>::total;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FHE_CUDA(cudaFuncSetAttribute(ntt_tile_fwd_kernel<LB, K1, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FHE_CUDA(cudaFuncSetAttribute(ntt_tile_inv_kernel<LB, K1, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     if (!inverse) {
         if constexpr (K1 > 0) {
             const uint32_t row_grid = pls * ((1u << LB) / (V * kRowThreads));
@@ -118,12 +184,12 @@ static int run_chunk(const NttArgs& a, bool inverse, cudaStream_t st) {
             FHE_LAUNCH_CHECK();
         }
         if (prof) profile_begin(0, pls, st);
-        ntt_tile_fwd_kernel<LB, K1, HB><<<tile_grid, 1 << (LB - 4), 0, st>>>(a);
+        ntt_tile_fwd_kernel<LB, K1, HB><<<tile_grid, 1 << (LB - 4), smem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
     } else {
         if (prof) profile_begin(1, pls, st);
-        ntt_tile_inv_kernel<LB, K1, HB><<<tile_grid, 1 << (LB - 4), 0, st>>>(a);
+        ntt_tile_inv_kernel<LB, K1, HB><<<tile_grid, 1 << (LB - 4), smem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
         if constexpr (K1 > 0) {
@@ -138,17 +204,17 @@ static int run_chunk(const NttArgs& a, bool inverse, cudaStream_t st) {
 }
 
 template <int HB>
-static int dispatch(uint32_t logn, const NttArgs& a, bool inverse, cudaStream_t st) {
+static int dispatch(uint32_t logn, const NttArgs& a, bool inverse, int sm_count, cudaStream_t st) {
     switch (logn) {
-        case 9: return run_chunk<9, 0, HB>(a, inverse, st);
-        case 10: return run_chunk<10, 0, HB>(a, inverse, st);
-        case 11: return run_chunk<11, 0, HB>(a, inverse, st);
-        case 12: return run_chunk<12, 0, HB>(a, inverse, st);
-        case 13: return run_chunk<12, 1, HB>(a, inverse, st);
-        case 14: return run_chunk<12, 2, HB>(a, inverse, st);
-        case 15: return run_chunk<12, 3, HB>(a, inverse, st);
-        case 16: return run_chunk<12, 4, HB>(a, inverse, st);
-        case 17: return run_chunk<12, 5, HB>(a, inverse, st);
+        case 9: return run_chunk<9, 0, HB>(a, inverse, sm_count, st);
+        case 10: return run_chunk<10, 0, HB>(a, inverse, sm_count, st);
+        case 11: return run_chunk<11, 0, HB>(a, inverse, sm_count, st);
+        case 12: return run_chunk<12, 0, HB>(a, inverse, sm_count, st);
+        case 13: return run_chunk<12, 1, HB>(a, inverse, sm_count, st);
+        case 14: return run_chunk<12, 2, HB>(a, inverse, sm_count, st);
+        case 15: return run_chunk<12, 3, HB>(a, inverse, sm_count, st);
+        case 16: return run_chunk<12, 4, HB>(a, inverse, sm_count, st);
+        case 17: return run_chunk<12, 5, HB>(a, inverse, sm_count, st);
     }
     set_error("unsupported ring degree 2^%u (supported: 2^9 .. 2^17)", logn);
     return FHE_B200_EINVAL;
@@ -161,6 +227,9 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
     NttArgs a;
     a.out = d_out; a.in = d_in;
     a.tw = inverse ? plan->d_inv : plan->d_fwd;
+    a.p12 = inverse ? plan->d_inv_p12 : plan->d_fwd_p12;
+    a.p3 = inverse ? plan->d_inv_p3 : plan->d_fwd_p3;
+    a.tiles = plan->tiles; a.p3n = (uint32_t)plan->p3_entries; a.groups = 1;
     a.params = plan->d_params;
     a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin;
     const size_t pl_bytes = (size_t)plan->n * sizeof(uint64_t);
@@ -177,7 +246,7 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
         for (uint32_t b0 = 0; b0 < batch; b0 += nb) {
             a.l0 = l0; a.nl = (l0 + nl <= limb_count) ? nl : limb_count - l0;
             a.b0 = b0; a.nb = (b0 + nb <= batch) ? nb : batch - b0;
-            const int rc = plan->hb == 16 ? dispatch<16>(plan->logn, a, inverse, st) : dispatch<8>(plan->logn, a, inverse, st);
+            const int rc = plan->hb == 16 ? dispatch<16>(plan->logn, a, inverse, plan->sm_count, st) : dispatch<8>(plan->logn, a, inverse, plan->sm_count, st);
             if (rc) return rc;
         }
     return 0;

@@ -27,6 +27,34 @@ int build_limb_tables(uint64_t q, uint32_t n, Twiddle* fwd, Twiddle* inv, LimbPa
     return 0;
 }
 
+size_t tile_p3_entries(uint32_t logn) {
+    const int LB = tile_lb(logn);
+    return (size_t)(1u << (LB - 4)) * (16 - (1u << (12 - LB)));
+}
+
+void build_tile_tables(const Twiddle* main, uint32_t logn, Twiddle* p12, Twiddle* p3) {
+    const int LB = tile_lb(logn), K1 = (int)logn - LB, R3 = LB - 8;
+    const uint32_t NT = 1u << (LB - 4), KB = 1u << (4 - R3);
+    const size_t p3n = tile_p3_entries(logn);
+    for (uint32_t b = 0; b < (1u << K1); b++) {
+        const uint32_t root = (1u << K1) + b;
+        Twiddle* a = p12 + (size_t)b * 256;
+        a[255].w = 0; a[255].ws = 0;
+        for (int v = 0; v < 4; v++)
+            for (uint32_t key = 0; key < (1u << v); key++) a[(1u << v) - 1 + key] = main[(root << v) + key];
+        for (int v = 0; v < 4; v++)
+            for (uint32_t hi = 0; hi < 16; hi++)
+                for (uint32_t key = 0; key < (1u << v); key++)
+                    a[15 + 16 * ((1u << v) - 1) + (hi << v) + key] = main[((((root << 4) + hi)) << v) + key];
+        Twiddle* c = p3 + (size_t)b * p3n;
+        for (int v = 0; v < R3; v++)
+            for (uint32_t key = 0; key < (KB << v); key++)
+                for (uint32_t tid = 0; tid < NT; tid++)
+                    c[(size_t)NT * KB * ((1u << v) - 1) + (size_t)key * NT + tid] =
+                        main[((((root << (4 + R3)) + tid)) << (4 - R3 + v)) + key];
+    }
+}
+
 int lazy_headroom(const uint64_t* moduli, uint32_t count) {
     int hb = 16;
     for (uint32_t i = 0; i < count; i++) if (moduli[i] >> 60) hb = 8;

@@ -9,6 +9,16 @@
 
 using namespace fhe_b200;
 
+struct TileTabs { std::vector<Twiddle> p12, p3; size_t p3n; };
+static TileTabs tile_tabs(const Twiddle* main, u32 logn) {
+    TileTabs t;
+    const u32 tiles = 1u << (logn - (u32)tile_lb(logn));
+    t.p3n = tile_p3_entries(logn);
+    t.p12.resize((size_t)tiles * 256); t.p3.resize((size_t)tiles * t.p3n);
+    build_tile_tables(main, logn, t.p12.data(), t.p3.data());
+    return t;
+}
+
 template <int LB, int K1, int HB>
 static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
     constexpr int NB = 1 << LB;
@@ -17,14 +27,17 @@ static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
         for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB>::forward(d, d, col, tw, P.q);
     }
     constexpr int B0 = fwd_bound_after(1, K1, HB);
+    const TileTabs tt = tile_tabs(tw, LB + K1);
     std::vector<u64> s(NB);
     using T = TileFwd<LB, HB>;
     for (u32 b = 0; b < (1u << K1); b++) {
         u64* g = d + (size_t)b * NB;
-        const u32 root = (1u << K1) + b;
-        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase1<B0>(t, g, s.data(), tw, root, P.q);
-        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase2<B0>(t, s.data(), tw, root, P.q);
-        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase3<B0>(t, s.data(), tw, root, P.q);
+        // what the kernel's two bulk copies stage into shared memory
+        std::vector<Twiddle> s12(tt.p12.begin() + (size_t)b * 256, tt.p12.begin() + (size_t)(b + 1) * 256);
+        std::vector<Twiddle> s3(tt.p3.begin() + (size_t)b * tt.p3n, tt.p3.begin() + (size_t)(b + 1) * tt.p3n);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase1<B0>(t, g, s.data(), s12.data(), P.q);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase2<B0>(t, s.data(), s12.data(), P.q);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase3<B0>(t, s.data(), s3.data(), P.q);
         for (u32 t = 0; t < (u32)T::NT; t++) T::phase4(t, g, s.data());
     }
 }
@@ -32,15 +45,17 @@ static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
 template <int LB, int K1, int HB>
 static void inv_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
     constexpr int NB = 1 << LB;
+    const TileTabs tt = tile_tabs(tw, LB + K1);
     std::vector<u64> s(NB);
     using T = TileInv<LB, HB>;
     for (u32 b = 0; b < (1u << K1); b++) {
         u64* g = d + (size_t)b * NB;
-        const u32 root = (1u << K1) + b;
+        std::vector<Twiddle> s12(tt.p12.begin() + (size_t)b * 256, tt.p12.begin() + (size_t)(b + 1) * 256);
+        std::vector<Twiddle> s3(tt.p3.begin() + (size_t)b * tt.p3n, tt.p3.begin() + (size_t)(b + 1) * tt.p3n);
         for (u32 t = 0; t < (u32)T::NT; t++) T::phase1(t, g, s.data());
-        for (u32 t = 0; t < (u32)T::NT; t++) T::phase2(t, s.data(), tw, root, P);
-        for (u32 t = 0; t < (u32)T::NT; t++) T::phase3(t, s.data(), tw, root, P);
-        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase4<K1 == 0>(t, g, s.data(), tw, root, P);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::phase2(t, s.data(), s3.data(), P);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::phase3(t, s.data(), s12.data(), P);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase4<K1 == 0>(t, g, s.data(), s12.data(), P);
     }
     if constexpr (K1 > 0) {
         constexpr int V = (K1 >= 5) ? 1 : 2;
