@@ -280,7 +280,7 @@ def run_ours(args, rank, local_rank, world):
                                    "(4096 limb-transforms per step per GPU)",
                        "N": N, "limbs": LIMBS, "polys_per_gpu": POLYS, "parallelism": f"batch-sharded x{world}",
                        "l2_policy": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
-                       "ntt_chunk_mb": int(os.environ.get("FHE_B200_NTT_CHUNK_MB", "32"))},
+                       "ntt_chunk_mb": int(os.environ.get("FHE_B200_NTT_CHUNK_MB", "1024"))},
             "roundtrip_bit_exact": ok and e2e_ok,
             "clocks": clocks,
             "gpu_launches": int(launches),

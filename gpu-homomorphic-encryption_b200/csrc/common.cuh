@@ -54,7 +54,7 @@ struct fhe_b200_plan {
     uint32_t tiles = 1;                            // tiles per limb = 2^K1
     fhe_b200::LimbParams* d_params = nullptr;      // [limbs]
     std::vector<fhe_b200::LimbParams> h_params;
-    size_t chunk_bytes = 32u << 20;                // L2-resident working set between pass A and pass B
+    size_t chunk_bytes = (size_t)1 << 30;          // polynomials per row-pass/tile-pass launch pair (FHE_B200_NTT_CHUNK_MB)
     int sm_count = 148;
     // host-buffer pipeline (lazy)
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};

@@ -117,6 +117,49 @@ FHE_HD u64 shoup_mul_lazy(u64 x, u64 w, u64 ws, u64 q) {
 }
 FHE_HD u64 shoup_mul(u64 x, u64 w, u64 ws, u64 q) { return csub(shoup_mul_lazy(x, w, ws, q), q); }
 
+// Shoup multiplication with a three-product quotient estimate: returns x*w mod q + {0,1,2,3} q, a value in [0, 4q),
+// for ANY 64-bit x.  nq = 2^64 - q.
+//   h' = x1*s1 + hi32(x1*s0) + hi32(x0*s1)  is the true hi64(x*ws) minus {0,1,2}  (x = x1:x0, ws = s1:s0), and the true
+//   quotient leaves a remainder in [0, 2q), so  x*w - h'*q  is in [0, 4q).
+// On the B200 integer pipe (measured, tools/microbench2.cu): IMAD.lo issues at 64 lanes/clk/SM, IMAD.WIDE and IMAD.HI at 32.
+// This form needs 3 WIDE + 2 HI + 4 lo = 28 pipe-cycles per warp against 32 for the exact quotient (4 WIDE + ...), and --
+// written as one asm block -- it keeps the carry adds on the ALU pipe instead of IMAD.X / IMAD.MOV on the FMA pipe.
+FHE_HD u64 shoup_mul_lazy4(u64 x, u64 w, u64 ws, u64 nq) {
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 y0, y1, s0, s1, w0, w1, n0, n1, a, b, h0, h1, t0, t1;\n\t"
+        ".reg .u64 h, t;\n\t"
+        "mov.b64 {y0, y1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {s0, s1}, %3;\n\t"
+        "mov.b64 {n0, n1}, %4;\n\t"
+        "mul.hi.u32 a, y1, s0;\n\t"
+        "mul.hi.u32 b, y0, s1;\n\t"
+        "mov.b64 h, {a, 0};\n\t"
+        "mad.wide.u32 h, y1, s1, h;\n\t"
+        "mov.b64 {h0, h1}, h;\n\t"
+        "add.cc.u32 h0, h0, b;\n\t"
+        "addc.u32 h1, h1, 0;\n\t"
+        "mul.wide.u32 t, y0, w0;\n\t"
+        "mov.b64 {t0, t1}, t;\n\t"
+        "mad.lo.u32 t1, y0, w1, t1;\n\t"
+        "mad.lo.u32 t1, y1, w0, t1;\n\t"
+        "mov.b64 t, {t0, t1};\n\t"
+        "mad.wide.u32 t, h0, n0, t;\n\t"
+        "mov.b64 {t0, t1}, t;\n\t"
+        "mad.lo.u32 t1, h0, n1, t1;\n\t"
+        "mad.lo.u32 t1, h1, n0, t1;\n\t"
+        "mov.b64 %0, {t0, t1};\n\t"
+        "}" : "=l"(r) : "l"(x), "l"(w), "l"(ws), "l"(nq));
+    return r;
+#else
+    const u64 x0 = (u32)x, x1 = x >> 32, s0 = (u32)ws, s1 = ws >> 32;
+    const u64 h = x1 * s1 + ((x1 * s0) >> 32) + ((x0 * s1) >> 32);
+    return x * w + h * nq;
+#endif
+}
+
 // (hi:lo) mod q for any 128-bit input; mu = floor(2^128/q), q < 2^63.
 // Quotient estimate from the three high partial products; it is low by at most 3, fixed by two conditional
 // subtractions (2q then q).  Needs 4q < 2^64.

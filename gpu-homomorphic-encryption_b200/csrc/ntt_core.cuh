@@ -15,14 +15,31 @@
 // psi-power table (Twiddle{w, floor(w 2^64 / q)}); a tile with index b starts from "root" 2^K1 + b and every
 // sub-transform a thread performs is addressed as (root << v) + key.
 //
-// Lazy arithmetic: values live in [0, B*q) with the bound B tracked at compile time (all loops are
-// unrolled).  HB = floor(2^64 / q_max) rounded down to a power of two is the head-room (16 for q < 2^60).
-//   forward (CT):  X' = X + T, Y' = X + 2q - T with T = Shoup(Y) in [0,2q): the bound grows by 2 per stage; a
-//                  conditional subtraction of (HB/2) q is inserted only when B + 2 would exceed HB.
-//   inverse (GS):  X' = X + Y, Y' = Shoup(X + Bq - Y): the sum bound doubles; one conditional subtraction
-//                  per butterfly once 2B would exceed HB/2 (i.e. Harvey's rule, but skipped while there is room).
+// Lazy arithmetic: values live in [0, B*q) with the bound B tracked at compile time (template recursion over the
+// stages).  HB = largest power of two with HB*q_max <= 2^64 is the head-room (16 for q < 2^60, 8 for q < 2^61).
+// The twiddle product T = shoup_mul_lazy4(.) lies in [0, 4q) for any 64-bit input.
+//   forward (CT):  X' = X + T, Y' = X + 4q - T: the bound grows by 4 per stage; X gets one conditional subtraction of
+//                  (HB/2) q only in the stages where B + 4 would exceed HB.
+//   inverse (GS):  S = X + Y, Y' = T(X + Bq - Y): the sum bound doubles; S gets one conditional subtraction of B q once
+//                  doubling again would overflow (steady state B = HB/2).
+// The conditional subtractions run on the ALU pipe, which has slack; the FMA pipe (IMAD) is the binding one.
 #pragma once
 #include "modarith.cuh"
+
+// host-only bound checking for the CPU emulation tests (compile the emulator with -DFHE_CHECK_BOUNDS)
+#if defined(FHE_CHECK_BOUNDS) && !defined(__CUDA_ARCH__)
+#include <cstdio>
+#include <cstdlib>
+#define FHE_BOUND(val, B, q)                                                                                      \
+    do {                                                                                                          \
+        if ((unsigned __int128)(val) >= (unsigned __int128)(B) * (q)) {                                           \
+            std::fprintf(stderr, "lazy bound violated: %s >= %d*q at %s:%d\n", #val, (int)(B), __FILE__, __LINE__); \
+            std::abort();                                                                                         \
+        }                                                                                                         \
+    } while (0)
+#else
+#define FHE_BOUND(val, B, q) do { } while (0)
+#endif
 
 namespace fhe_b200 {
 
@@ -55,12 +72,18 @@ FHE_HD void st2(u64* p, u64 a, u64 b) {
 #endif
 }
 
+// bounds in units of q; the twiddle product is lazy in [0, 4q) (shoup_mul_lazy4)
 FHE_HDC int fwd_bound_after(int B, int stages, int HB) {
-    for (int i = 0; i < stages; i++) { if (B + 2 > HB) B = HB / 2; B += 2; }
+    for (int i = 0; i < stages; i++) { if (B + 4 > HB) B = HB / 2; B += 4; }
     return B;
 }
+FHE_HDC int inv_bound_step(int B, int HB) {
+    int nb = 2 * B > 4 ? 2 * B : 4;
+    if (2 * nb > HB) nb = nb / 2 > 4 ? nb / 2 : 4;
+    return nb;
+}
 FHE_HDC int inv_bound_after(int B, int stages, int HB) {
-    for (int i = 0; i < stages; i++) { B = 2 * B; if (2 * B > HB) B = B / 2; }
+    for (int i = 0; i < stages; i++) B = inv_bound_step(B, HB);
     return B;
 }
 
@@ -109,8 +132,8 @@ FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, u64 q) {
     if constexpr (V < R) {
         constexpr int st = 1 << (R - 1 - V);
         constexpr int sh = LE - R + V;
-        constexpr bool red = (B + 2 > HB);
-        const u64 twoq = 2 * q;
+        constexpr bool red = (B + 4 > HB);
+        const u64 fourq = 4 * q, nq = 0 - q;
         const u64 hq = (u64)(HB / 2) * q;
 #pragma unroll
         for (int key = 0; key < (1 << sh); key++) {
@@ -119,26 +142,30 @@ FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, u64 q) {
             for (int j = 0; j < st; j++) {
                 const int e = (key << (R - V)) | j;
                 u64 X = x[e];
+                FHE_BOUND(X, B, q); FHE_BOUND(x[e + st], B, q);
                 if (red) X = csub(X, hq);
-                const u64 T = shoup_mul_lazy(x[e + st], w.w, w.ws, q);
+                const u64 T = shoup_mul_lazy4(x[e + st], w.w, w.ws, nq);
+                FHE_BOUND(T, 4, q); FHE_BOUND((unsigned __int128)X + T, (red ? HB / 2 : B) + 4, q);
                 x[e] = X + T;
-                x[e + st] = X + twoq - T;
+                x[e + st] = X + fourq - T;
             }
         }
-        fwd_stages<LE, R, HB, (red ? HB / 2 : B) + 2, TW, V + 1>(x, tw, q);
+        fwd_stages<LE, R, HB, (red ? HB / 2 : B) + 4, TW, V + 1>(x, tw, q);
     }
 }
 
 // ---- inverse stages (mirror order: V runs R-1 .. 0).  LAST: the final stage of the whole transform folds N^-1 in.
-// exit bound: inv_bound_after(B, R, HB), or 2 when LAST.
+// exit bound: inv_bound_after(B, R, HB), or 4 when LAST.
 template <int LE, int R, int HB, bool LAST, int B, class TW, int V = R - 1>
 FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
     if constexpr (V >= 0) {
         constexpr int st = 1 << (R - 1 - V);
         constexpr int sh = LE - R + V;
         constexpr bool last = LAST && (V == 0);
-        constexpr bool red = !last && (4 * B > HB);
-        const u64 q = P.q;
+        constexpr int SB = 2 * B > 4 ? 2 * B : 4;            // bound after this stage before any reduction
+        constexpr bool red = !last && (2 * SB > HB);           // reduce the sums so that the next stage cannot overflow
+        static_assert(2 * B <= HB, "inverse stage would overflow 64 bits");
+        const u64 q = P.q, nq = 0 - q;
         const u64 bq = (u64)B * q;
 #pragma unroll
         for (int key = 0; key < (1 << sh); key++) {
@@ -149,15 +176,16 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
             for (int j = 0; j < st; j++) {
                 const int e = (key << (R - V)) | j;
                 const u64 X = x[e], Y = x[e + st];
+                FHE_BOUND(X, B, q); FHE_BOUND(Y, B, q); FHE_BOUND((unsigned __int128)X + Y, HB, q);
                 u64 S = X + Y;
                 const u64 D = X + bq - Y;
-                if (last) S = shoup_mul_lazy(S, P.ninv, P.ninv_s, q);
+                if (last) S = shoup_mul_lazy4(S, P.ninv, P.ninv_s, nq);
                 else if (red) S = csub(S, bq);
                 x[e] = S;
-                x[e + st] = shoup_mul_lazy(D, w.w, w.ws, q);
+                x[e + st] = shoup_mul_lazy4(D, w.w, w.ws, nq);
             }
         }
-        inv_stages<LE, R, HB, LAST, (red ? B : 2 * B), TW, V - 1>(x, tw, P);
+        inv_stages<LE, R, HB, LAST, inv_bound_step(B, HB), TW, V - 1>(x, tw, P);
     }
 }
 
@@ -293,7 +321,7 @@ struct TileInv {
         inv_stages<4, 4, HB, LAST, inv_bound_after(1, R3 + 4, HB)>(x, TwP1{s12}, P);
         // LAST: fully reduce.  Otherwise leave the lazy bound for pass A' (it starts from out_bound()).
 #pragma unroll
-        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? csub(x[e], P.q) : x[e];
+        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize<HB, 4>(x[e], P.q) : x[e];
     }
     static FHE_HDC int out_bound() { return inv_bound_after(1, LB, HB); }
 };
@@ -336,8 +364,8 @@ struct RowPass {
         for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, true, B0>(x[c], TwGlobal<0>{tw, 1u}, P);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
-            if (V == 2) st2(g + (size_t)r * NB + col, csub(x[0][r], P.q), csub(x[V - 1][r], P.q));
-            else g[(size_t)r * NB + col] = csub(x[0][r], P.q);
+            if (V == 2) st2(g + (size_t)r * NB + col, normalize<HB, 4>(x[0][r], P.q), normalize<HB, 4>(x[V - 1][r], P.q));
+            else g[(size_t)r * NB + col] = normalize<HB, 4>(x[0][r], P.q);
         }
     }
 };

@@ -19,8 +19,9 @@ def emul():
     srcs = [os.path.join(EMUL, "emul_ntt.cpp"), os.path.join(CSRC, "tables.cpp"), os.path.join(CSRC, "ntt_core.cuh"),
             os.path.join(CSRC, "modarith.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + CSRC, srcs[0], srcs[1],
-                               "-o", so])
+        # -DFHE_CHECK_BOUNDS: every butterfly asserts its compile-time lazy bound (values < B*q, no 64-bit wrap)
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DFHE_CHECK_BOUNDS", "-I" + CSRC,
+                               srcs[0], srcs[1], "-o", so])
     lib = C.CDLL(so)
     lib.emul_ntt.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64, C.c_int, C.c_int]
     lib.emul_mul_mod.restype = C.c_uint64
