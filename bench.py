@@ -297,9 +297,18 @@ def run_ours(args, rank, local_rank, world):
                          "step_frac": value * UNIT_BYTES / 1e9 / world / peak,
                          "per_kernel_ms": {k: v[1] / psteps for k, v in kinds.items()}},
         }
+        # integer-pipe roofline (the binding one): 28 FMA-pipe cycles per warp-butterfly
+        # (3 IMAD.WIDE + 2 IMAD.HI at 4 cycles, 4 IMAD.lo at 2 cycles per warp instruction per SM sub-partition; measured by
+        # tools/microbench2.cu), 4 sub-partitions per SM, at the SM clock sampled during the timed region
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak_bfly = 148 * 4 * 32 * sm_mhz * 1e6 / 28.0
+        bfly = value / world * (N // 2) * LOGN
+        line["int_pipe"] = {"bound": "imad", "achieved_Gbutterflies_s": bfly / 1e9, "peak_Gbutterflies_s": peak_bfly / 1e9,
+                            "frac": bfly / peak_bfly, "pipe_cycles_per_warp_butterfly": 28, "sm_mhz": sm_mhz,
+                            "peak_limb_transforms_s": peak_bfly / ((N // 2) * LOGN)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
-        if args.with_hmult and world == 1:
+        if world == 1 and not args.no_hmult:
             try:
                 from bench_hmult import run_hmult
                 line["hmult"] = run_hmult(args, local_rank)
@@ -319,6 +328,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-hmult", action="store_true", default=False)
+    ap.add_argument("--no-hmult", action="store_true", default=False)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -64,6 +64,7 @@ def load_library() -> C.CDLL:
         "fhe_b200_unpack_u256": [_vp, _vp, C.c_size_t, _vp],
         "fhe_b200_pack_u256": [_vp, _vp, C.c_size_t, _vp],
         "fhe_b200_to_rns_u256": [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_uint32, _vp],
+        "fhe_b200_from_rns_u256": [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_lincomb_create_conv": [u64p, C.c_uint32, u64p, C.c_uint32, C.c_int, C.POINTER(_vp)],
         "fhe_b200_lincomb_create_scale": [u64p, C.c_uint32, u64p, C.c_uint32, C.c_uint64, u64p, C.c_uint32, C.c_int,
                                           C.c_int, C.POINTER(_vp)],

@@ -63,5 +63,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_compat_test(force: bool = False) -> str:
+    """tests/cpp/test_fhe_compat.bin: the reference's test program re-expressed against include/fhe/*.cuh."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp", "test_fhe_compat.cu")
+    out = os.path.join(root, "tests", "cpp", "test_fhe_compat.bin")
+    hdrs = [os.path.join(root, "include", "fhe", f) for f in os.listdir(os.path.join(root, "include", "fhe"))]
+    if force or _stale(out, [src, LIB] + hdrs):
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2", "-std=c++17", "-ccbin", HOSTCXX,
+               "-I" + os.path.join(root, "include"), src, "-o", out, "-L" + HERE, "-lfhe_b200",
+               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../gpu-homomorphic-encryption_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"compat test build failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_compat_test(force="--force" in sys.argv))

@@ -33,7 +33,21 @@ struct fhe_b200_bfv {
     uint32_t* d_idx = nullptr;                           // index maps for the lincomb views
     const uint32_t *d_idx_p = nullptr;                   // [K]  L .. L+K-1
     std::vector<const uint32_t*> d_idx_grp, d_idx_tgt;   // per digit: sources [alpha], targets [L+K-alpha]
+    // workspaces, grown on demand and kept (a context is single-threaded by contract, see fhe_b200.h)
+    uint64_t* d_ws = nullptr; size_t ws_words = 0;       // multiply / encrypt / decrypt scratch
+    uint64_t* d_io = nullptr; size_t io_words = 0;       // device staging of the host-buffer entry point
+    cudaStream_t io_stream = nullptr;
 };
+
+namespace fhe_b200 {
+static int ensure_words(uint64_t** buf, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    if (*buf) { FHE_CUDA(cudaDeviceSynchronize()); FHE_CUDA(cudaFree(*buf)); *buf = nullptr; *have = 0; }
+    FHE_CUDA(cudaMalloc(buf, need * sizeof(uint64_t)));
+    *have = need;
+    return 0;
+}
+}  // namespace fhe_b200
 
 namespace fhe_b200 {
 
@@ -247,6 +261,8 @@ extern "C" int fhe_b200_bfv_destroy(fhe_b200_bfv* c) {
     fhe_b200_lincomb_destroy(c->moddown); fhe_b200_lincomb_destroy(c->dec);
     for (auto* m : c->modup) fhe_b200_lincomb_destroy(m);
     cudaFree(c->d_consts); cudaFree(c->d_idx);
+    cudaFree(c->d_ws); cudaFree(c->d_io);
+    if (c->io_stream) cudaStreamDestroy(c->io_stream);
     fhe_b200_plan_destroy(c->plan);
     delete c;
     return 0;
@@ -399,8 +415,8 @@ extern "C" int fhe_b200_bfv_encrypt(fhe_b200_bfv* c, uint64_t seed, const uint64
     const uint32_t n = c->n, L = c->L;
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
-    uint64_t* u = nullptr;
-    FHE_CUDA(cudaMallocAsync(&u, batch * ln * sizeof(uint64_t), st));
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
+    uint64_t* u = c->d_ws;
     sample_small_kernel<0><<<grid_for(c, (size_t)batch * n), 256, 0, st>>>(u, prm, c->logn, 0, L, batch, seed, 0, c->thr, c->d_cdt, c->cdt_len);
     FHE_LAUNCH_CHECK();
     int rc = launch_ntt(c->plan, u, u, batch, 0, L, false, st);
@@ -413,7 +429,6 @@ extern "C" int fhe_b200_bfv_encrypt(fhe_b200_bfv* c, uint64_t seed, const uint64
         enc_finish_kernel<<<grid_for(c, (size_t)batch * n), 256, 0, st>>>(d_ct, d_pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, batch, seed);
         count_launch();
     }
-    cudaFreeAsync(u, st);
     if (rc) return rc;
     FHE_CUDA(cudaGetLastError());
     return 0;
@@ -427,8 +442,8 @@ extern "C" int fhe_b200_bfv_decrypt(fhe_b200_bfv* c, const uint64_t* d_ct, const
     const uint32_t n = c->n, L = c->L;
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
-    uint64_t* x = nullptr;
-    FHE_CUDA(cudaMallocAsync(&x, batch * ln * sizeof(uint64_t), st));
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
+    uint64_t* x = c->d_ws;
     // x = c1 (strided gather), then x = INTT(NTT(x) * s) + c0
     cudaError_t e = cudaMemcpy2DAsync(x, ln * 8, d_ct + ln, 2 * ln * 8, ln * 8, batch, cudaMemcpyDeviceToDevice, st);
     int rc = e == cudaSuccess ? 0 : FHE_B200_ECUDA;
@@ -438,7 +453,6 @@ extern "C" int fhe_b200_bfv_decrypt(fhe_b200_bfv* c, const uint64_t* d_ct, const
     if (!rc) rc = launch_ntt(c->plan, x, x, batch, 0, L, true, st);
     if (!rc) { dec_add_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(x, d_ct, prm, c->logn, L, batch * ln); count_launch(); }
     if (!rc) { LcView v; v.in = x; v.out = d_pt; rc = lincomb_launch(c->dec, v, n, batch, st); }
-    cudaFreeAsync(x, st);
     if (rc) return rc;
     FHE_CUDA(cudaGetLastError());
     return 0;
@@ -461,8 +475,8 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     const size_t N = n, ln = (size_t)L * N, an = (size_t)A * N, wn = (size_t)W * N, rn = (size_t)R * N;
     // workspace: ext [4][B][A][N] | d [3][B][A][N] | sR [3][B][R][N] | sc [3][B][L][N] | dig [dnum][B][W][N] | acc [2][B][W][N]
     const size_t w_ext = 4 * B * an, w_d = 3 * B * an, w_sr = 3 * B * rn, w_sc = 3 * B * ln, w_dig = (size_t)dnum * B * wn, w_acc = 2 * B * wn;
-    uint64_t* ws = nullptr;
-    FHE_CUDA(cudaMallocAsync(&ws, (w_ext + w_d + w_sr + w_sc + w_dig + w_acc) * sizeof(uint64_t), st));
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_ext + w_d + w_sr + w_sc + w_dig + w_acc));
+    uint64_t* ws = c->d_ws;
     uint64_t* ext = ws; uint64_t* d = ext + w_ext; uint64_t* sR = d + w_d; uint64_t* sc = sR + w_sr; uint64_t* dig = sc + w_sc; uint64_t* acc = dig + w_dig;
     int rc = 0;
     cudaError_t e = cudaSuccess;
@@ -516,7 +530,6 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     }
 #undef STEP
 #undef COPY2D
-    cudaFreeAsync(ws, st);
     if (e != cudaSuccess) { set_error("bfv_multiply_relin: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
     if (rc) return rc;
     FHE_CUDA(cudaGetLastError());
@@ -528,17 +541,15 @@ extern "C" int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* c, const uint64_t*
     FHE_REQUIRE(c && h_a && h_b && d_rlk && h_out, "bfv_multiply_relin_host: null argument");
     if (!batch) return 0;
     FHE_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = nullptr;          // legacy default stream: ordered after everything the caller queued
+    if (!c->io_stream) FHE_CUDA(cudaStreamCreateWithFlags(&c->io_stream, cudaStreamNonBlocking));
+    cudaStream_t st = c->io_stream;
     const size_t ct = 2 * (size_t)c->L * c->n * batch;
-    uint64_t* buf = nullptr;
-    FHE_CUDA(cudaMallocAsync(&buf, 3 * ct * sizeof(uint64_t), st));
-    cudaError_t e = cudaMemcpyAsync(buf, h_a, ct * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(buf + ct, h_b, ct * 8, cudaMemcpyHostToDevice, st);
-    int rc = e == cudaSuccess ? fhe_b200_bfv_multiply_relin(c, buf, buf + ct, d_rlk, buf + 2 * ct, nullptr, batch, st) : FHE_B200_ECUDA;
-    if (!rc) e = cudaMemcpyAsync(h_out, buf + 2 * ct, ct * 8, cudaMemcpyDeviceToHost, st);
-    cudaFreeAsync(buf, st);
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    if (rc) return rc;
-    if (e != cudaSuccess || e2 != cudaSuccess) { set_error("bfv_multiply_relin_host: copy failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); return FHE_B200_ECUDA; }
+    FHE_TRY(ensure_words(&c->d_io, &c->io_words, 3 * ct));
+    uint64_t* buf = c->d_io;
+    FHE_CUDA(cudaMemcpyAsync(buf, h_a, ct * 8, cudaMemcpyHostToDevice, st));
+    FHE_CUDA(cudaMemcpyAsync(buf + ct, h_b, ct * 8, cudaMemcpyHostToDevice, st));
+    FHE_TRY(fhe_b200_bfv_multiply_relin(c, buf, buf + ct, d_rlk, buf + 2 * ct, nullptr, batch, st));
+    FHE_CUDA(cudaMemcpyAsync(h_out, buf + 2 * ct, ct * 8, cudaMemcpyDeviceToHost, st));
+    FHE_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

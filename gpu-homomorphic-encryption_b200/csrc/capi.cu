@@ -87,6 +87,14 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
     FHE_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { set_error("plan_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return FHE_B200_ESTATE; }
     FHE_CUDA(cudaSetDevice(device));
+    {   // keep stream-ordered temporaries (cudaMallocAsync) cached instead of returning them to the OS at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
 
     fhe_b200_plan* p = new (std::nothrow) fhe_b200_plan();
     if (!p) { set_error("out of host memory"); return FHE_B200_ENOMEM; }

@@ -4,6 +4,7 @@
 // bit_reverse_kernel (kernels/ntt_kernels.cu:140-161) and the uint256_t edge (include/bigint.cuh:9-24).
 // One thread moves 16 bytes per operand per iteration (LDG.128/STG.128); grids are sized to a multiple of the SM count.
 #include "common.cuh"
+#include "host_math.hpp"
 
 namespace fhe_b200 {
 
@@ -110,6 +111,42 @@ __global__ void __launch_bounds__(256) to_rns_u256_kernel(u64* __restrict__ out,
     }
 }
 
+// Garner mixed-radix CRT into 256 bits: x = v0 + v1 q0 + v2 q0 q1 + v3 q0 q1 q2, v_i < q_i.
+struct GarnerConsts { u64 q[4]; u64 inv[4][4]; };     // inv[i][j] = (q_j)^-1 mod q_i for j < i
+__global__ void __launch_bounds__(256) from_rns_u256_kernel(ulonglong2* __restrict__ out, const u64* __restrict__ in,
+                                                            const LimbParams* __restrict__ params, uint32_t limb_begin,
+                                                            uint32_t k, size_t count, const GarnerConsts gc) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        u64 v[4] = {0, 0, 0, 0};
+        for (uint32_t a = 0; a < k; a++) {
+            const LimbParams P = params[limb_begin + a];
+            u64 t = in[(size_t)a * count + i];
+            // t = (...((x_a - v0) q0^-1 - v1) q1^-1 ...) mod q_a
+            for (uint32_t b = 0; b < a; b++) {
+                const u64 vb = barrett128(0, v[b], P.q, P.mu_hi, P.mu_lo);
+                t = mul_mod(sub_mod(t, vb, P.q), gc.inv[a][b], P);
+            }
+            v[a] = t;
+        }
+        // Horner: ((v3 q2 + v2) q1 + v1) q0 + v0 over four 64-bit words
+        u64 w[4] = {0, 0, 0, 0};
+        for (int a = (int)k - 1; a >= 0; a--) {
+            if (a < (int)k - 1) {           // w *= q[a]
+                u64 carry = 0;
+                for (int j = 0; j < 4; j++) {
+                    u64 hi, lo; mul128(w[j], gc.q[a], hi, lo);
+                    lo += carry; hi += (lo < carry);
+                    w[j] = lo; carry = hi;
+                }
+            }
+            u64 c = v[a];                    // w += v[a]
+            for (int j = 0; j < 4 && c; j++) { w[j] += c; c = (w[j] < c) ? 1 : 0; }
+        }
+        out[2 * i] = make_ulonglong2(w[0], w[1]);
+        out[2 * i + 1] = make_ulonglong2(w[2], w[3]);
+    }
+}
+
 static inline uint32_t flat_grid(size_t n) { const size_t w = (n + 255) / 256; return (uint32_t)(w < 148 * 16 ? (w ? w : 1) : 148 * 16); }
 
 }  // namespace fhe_b200
@@ -135,6 +172,28 @@ extern "C" int fhe_b200_pack_u256(void* d_u256, const uint64_t* d_in, size_t cou
     FHE_REQUIRE(d_in && d_u256, "pack_u256: null buffer");
     if (!count) return 0;
     pack_u256_kernel<<<flat_grid(count), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_u256, d_in, count);
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int fhe_b200_from_rns_u256(fhe_b200_plan* plan, void* d_u256, const uint64_t* d_in, size_t count, uint32_t limb_begin,
+                                      uint32_t limb_count, void* stream) {
+    FHE_REQUIRE(plan && d_u256 && d_in, "from_rns_u256: null argument");
+    FHE_TRY(check_range(plan, 1, limb_begin, limb_count));
+    FHE_REQUIRE(limb_count >= 1 && limb_count <= 4, "from_rns_u256: 1..4 limbs (Q must fit 256 bits)");
+    double bits = 0;
+    for (uint32_t a = 0; a < limb_count; a++) bits += (double)plan->h_params[limb_begin + a].qbits;
+    FHE_REQUIRE(bits <= 256, "from_rns_u256: the product of the moduli exceeds 256 bits");
+    if (!count) return 0;
+    GarnerConsts gc;
+    for (uint32_t a = 0; a < 4; a++) {
+        gc.q[a] = a < limb_count ? plan->moduli[limb_begin + a] : 1;
+        for (uint32_t b = 0; b < 4; b++) {
+            gc.inv[a][b] = 0;
+            if (a < limb_count && b < a) gc.inv[a][b] = host::invmod(plan->moduli[limb_begin + b] % gc.q[a], gc.q[a]);
+        }
+    }
+    from_rns_u256_kernel<<<flat_grid(count), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_u256, d_in, plan->d_params, limb_begin,
+                                                                            limb_count, count, gc);
     FHE_LAUNCH_CHECK();
     return 0;
 }

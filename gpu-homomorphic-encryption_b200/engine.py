@@ -235,6 +235,14 @@ class RNS_NTTEngine:
         return out
 
 
+    def from_rns(self, d_rns: torch.Tensor) -> torch.Tensor:
+        """[num_primes][N] residues -> [N][4] words of the CRT value in [0, Q)  (Q < 2^256)."""
+        count = d_rns.numel() // self.num_primes
+        out = torch.empty(count, 4, dtype=torch.int64, device=d_rns.device)
+        check(self.plan.lib.fhe_b200_from_rns_u256(self.plan.h, _ptr(out), _ptr(d_rns), count, 0, self.num_primes, _stream()))
+        return out
+
+
 class PolynomialOps:
     """fhe::PolynomialOps over one plan (any number of limbs)."""
 

@@ -1,0 +1,219 @@
+// Compat header: fhe::FHEContext and its PODs with the reference's names and signatures (include/fhe.cuh:15-166),
+// implemented on the BFV entry points of libfhe_b200.so.
+//
+// What changes behind the same API: log_q is honoured (L = ceil(log_q / 60) RNS limbs of
+// the deterministic 60-bit prime chain instead of the hard-coded q = 2^60), multiply() applies the t/q scaling, and
+// relinearize() performs hybrid key switching instead of dropping c2.  Polynomials of keys and ciphertexts are RNS
+// polynomials (Polynomial::rns, limb-major uint64_t [L][N]); plaintexts keep the reference's uint256_t coefficients.
+#pragma once
+#include <algorithm>
+#include <memory>
+#include <vector>
+#include "bigint.cuh"
+#include "ntt.cuh"
+#include "polynomial.cuh"
+#include "rns.cuh"
+
+namespace fhe {
+
+struct SecurityParams {
+    uint32_t lambda;          // security level (recorded; parameter validation is the caller's job, as in the reference)
+    uint32_t poly_degree;     // power of two in [512, 131072]
+    uint32_t log_q;           // bits of the ciphertext modulus -> ceil(log_q / 60) limbs
+    float sigma;              // Gaussian noise standard deviation
+    uint32_t hamming_weight;  // non-zero coefficients of the ternary secret (0: each coefficient non-zero with prob. 1/2)
+};
+
+struct SchemeParams {
+    SecurityParams security;
+    uint32_t n;
+    uint256_t q;              // Q when it fits 256 bits, else 0 (see rns_moduli)
+    uint256_t t;
+    uint256_t delta;          // floor(Q/t) when it fits 256 bits, else 0
+    RNSContext* rns_ctx = nullptr;
+    NTTEngine* ntt_engine = nullptr;      // single-limb engine over q_0 (kept for callers that reach for it)
+    PolynomialOps* poly_ops = nullptr;
+    uint32_t num_levels = 0;
+    std::vector<uint256_t> modulus_chain; // q_0 .. q_{L-1}
+    // engine view
+    uint32_t L = 0, R = 0, K = 0, dnum = 0;
+    std::vector<uint64_t> rns_moduli;     // Q limbs then auxiliary limbs
+};
+
+struct PublicKey { Polynomial* pk0 = nullptr; Polynomial* pk1 = nullptr; };
+struct SecretKey { Polynomial* sk = nullptr; };
+struct RelinKeys { std::vector<PublicKey*> rlk_keys; uint32_t decomp_bits = 0; };
+struct GaloisKeys { std::vector<PublicKey*> gal_keys; };
+struct Ciphertext {
+    std::vector<Polynomial*> components;
+    uint32_t level = 0;
+    float noise_budget = 0;
+    bool is_ntt_form = false;
+};
+struct Plaintext { Polynomial* poly = nullptr; bool is_ntt_form = false; };
+
+class FHEContext {
+public:
+    explicit FHEContext(const SecurityParams& sp) {
+        params_.security = sp;
+        params_.n = sp.poly_degree;
+        const uint32_t L = std::max<uint32_t>(1, (sp.log_q + 59) / 60);
+        // hybrid key switching: dnum digits of alpha limbs, special modulus of K = alpha auxiliary limbs
+        uint32_t dnum = L;
+        if (L >= 6 && L % 3 == 0) dnum = 3; else if (L >= 4 && L % 2 == 0) dnum = 2;
+        const uint32_t alpha = L / dnum, R = L + 1, K = alpha;
+        params_.L = L; params_.R = R; params_.K = K; params_.dnum = dnum;
+        // deterministic chain: k-th largest prime below 2^60 with p = 1 (mod 2^18)
+        for (uint64_t p = (1ull << 60) - (1ull << 18) + 1; params_.rns_moduli.size() < L + R; p -= (1ull << 18))
+            if (is_prime(uint256_t(p))) params_.rns_moduli.push_back(p);
+        for (uint32_t i = 0; i < L; i++) params_.modulus_chain.push_back(uint256_t(params_.rns_moduli[i]));
+        params_.num_levels = L;
+        params_.t = uint256_t(65537);
+        cudaGetDevice(&device_);
+        detail::check(fhe_b200_bfv_create(params_.n, L, R, K, dnum, 65537, params_.rns_moduli.data(), sp.sigma, sp.hamming_weight,
+                                          device_, &ctx_), "FHEContext");
+        if (L <= 4) {      // Q and delta as 256-bit numbers for callers that read params().q / params().delta
+            uint256_t Q(1);
+            for (uint32_t i = 0; i < L; i++) Q = mul_small(Q, params_.rns_moduli[i]);
+            params_.q = Q; params_.delta = div_small(Q, 65537);
+        }
+        std::vector<uint256_t> qs(params_.modulus_chain);
+        params_.rns_ctx = new RNSContext(qs);
+        params_.ntt_engine = new NTTEngine(params_.n, params_.modulus_chain[0]);
+        params_.poly_ops = new PolynomialOps(params_.n, params_.modulus_chain[0], params_.ntt_engine);
+        detail::check_cuda(cudaStreamCreate(&stream_), "cudaStreamCreate");
+        init_rng(12345);
+    }
+    ~FHEContext() {
+        delete params_.rns_ctx; delete params_.poly_ops; delete params_.ntt_engine;
+        fhe_b200_bfv_destroy(ctx_);
+        if (stream_) cudaStreamDestroy(stream_);
+    }
+    FHEContext(const FHEContext&) = delete;
+    FHEContext& operator=(const FHEContext&) = delete;
+
+    // ---- key generation (src/fhe.cu:54-111).  Ownership: the structs own what they receive; call release() helpers.
+    void keygen(PublicKey& pk, SecretKey& sk) {
+        const uint32_t n = params_.n, L = params_.L, A = params_.L + params_.R;
+        sk.sk = new Polynomial(n, A); sk.sk->is_ntt_form = true;
+        pk.pk0 = new Polynomial(n, 2 * L); pk.pk0->is_ntt_form = true;                 // owns [2][L][N]
+        pk.pk1 = new Polynomial(n, L, pk.pk0->rns + (size_t)L * n); pk.pk1->is_ntt_form = true;
+        detail::check(fhe_b200_bfv_keygen(ctx_, next_seed(), next_seed(), sk.sk->rns, pk.pk0->rns, stream_), "keygen");
+    }
+    // decomp_bits is accepted for source compatibility; the digits are RNS digits (dnum of them), not base-2^w digits
+    void relinkey_gen(RelinKeys& rlk, const SecretKey& sk, uint32_t decomp_bits = 16) {
+        const uint32_t n = params_.n, W = params_.L + params_.K, dnum = params_.dnum;
+        rlk.decomp_bits = decomp_bits;
+        Polynomial* all = new Polynomial(n, 2 * W * dnum); all->is_ntt_form = true;    // [dnum][2][W][N]
+        detail::check(fhe_b200_bfv_relinkeygen(ctx_, next_seed(), sk.sk->rns, all->rns, stream_), "relinkey_gen");
+        for (uint32_t d = 0; d < dnum; d++) {
+            PublicKey* k = new PublicKey();
+            k->pk0 = d == 0 ? all : new Polynomial(n, W, all->rns + (size_t)(2 * d) * W * n);
+            k->pk1 = new Polynomial(n, W, all->rns + (size_t)(2 * d + 1) * W * n);
+            rlk.rlk_keys.push_back(k);
+        }
+    }
+
+    // ---- encoding (src/fhe.cu:113-136): coefficient encoding, values[i] -> coefficient i
+    void encode(Plaintext& pt, const std::vector<uint64_t>& values) {
+        pt.poly = new Polynomial(params_.n, params_.t);
+        pt.is_ntt_form = false;
+        std::vector<uint256_t> h(params_.n);
+        for (size_t i = 0; i < std::min(values.size(), (size_t)params_.n); i++) h[i] = uint256_t(values[i] % 65537);
+        detail::check_cuda(cudaMemcpy(pt.poly->coeffs, h.data(), params_.n * sizeof(uint256_t), cudaMemcpyHostToDevice), "encode");
+    }
+    void decode(std::vector<uint64_t>& values, const Plaintext& pt) {
+        std::vector<uint256_t> h(params_.n);
+        detail::check_cuda(cudaStreamSynchronize(stream_), "decode");
+        detail::check_cuda(cudaMemcpy(h.data(), pt.poly->coeffs, params_.n * sizeof(uint256_t), cudaMemcpyDeviceToHost), "decode");
+        values.clear();
+        for (uint32_t i = 0; i < params_.n; i++) values.push_back(h[i].limbs[0]);
+    }
+
+    // ---- encryption (src/fhe.cu:138-185)
+    void encrypt(Ciphertext& ct, const Plaintext& pt, const PublicKey& pk) {
+        const uint32_t n = params_.n, L = params_.L;
+        new_ciphertext(ct);
+        scratch_.reserve(n);
+        detail::check(fhe_b200_unpack_u256(scratch_.p, pt.poly->coeffs, n, stream_), "encrypt");
+        detail::check(fhe_b200_bfv_encrypt(ctx_, next_seed(), scratch_.p, pk.pk0->rns, ct.components[0]->rns, 1, stream_), "encrypt");
+        ct.level = 0; ct.is_ntt_form = false;
+        ct.noise_budget = params_.security.sigma * 10;   // the reference's rough bookkeeping (src/fhe.cu:168)
+        (void)L;
+    }
+    void decrypt(Plaintext& pt, const Ciphertext& ct, const SecretKey& sk) {
+        const uint32_t n = params_.n;
+        pt.poly = new Polynomial(n, params_.t);
+        pt.is_ntt_form = false;
+        scratch_.reserve(n);
+        detail::check(fhe_b200_bfv_decrypt(ctx_, ct.components[0]->rns, sk.sk->rns, scratch_.p, 1, stream_), "decrypt");
+        detail::check(fhe_b200_pack_u256(pt.poly->coeffs, scratch_.p, n, stream_), "decrypt");
+    }
+
+    // ---- homomorphic operations (src/fhe.cu:187-235)
+    void add(Ciphertext& result, const Ciphertext& a, const Ciphertext& b) {
+        Ciphertext out; new_ciphertext(out);
+        detail::check(fhe_b200_bfv_add(ctx_, a.components[0]->rns, b.components[0]->rns, out.components[0]->rns, 1, stream_), "add");
+        out.noise_budget = std::min(a.noise_budget, b.noise_budget);
+        out.level = std::max(a.level, b.level);
+        replace(result, out);
+    }
+    void multiply(Ciphertext& result, const Ciphertext& a, const Ciphertext& b, const RelinKeys& rlk) {
+        Ciphertext out; new_ciphertext(out);
+        detail::check(fhe_b200_bfv_multiply_relin(ctx_, a.components[0]->rns, b.components[0]->rns, rlk.rlk_keys.at(0)->pk0->rns,
+                                                  out.components[0]->rns, nullptr, 1, stream_), "multiply");
+        out.noise_budget = a.noise_budget + b.noise_budget + 10;
+        out.level = std::max(a.level, b.level);
+        replace(result, out);
+    }
+    // multiply() already relinearises (the tensor product never leaves the engine); kept for source compatibility
+    void relinearize(Ciphertext& ct, const RelinKeys&) { if (ct.components.size() > 2) throw std::runtime_error("relinearize: 3-component input is produced only inside multiply()"); }
+
+    const SchemeParams& params() const { return params_; }
+    fhe_b200_bfv* engine() const { return ctx_; }
+    cudaStream_t stream() const { return stream_; }
+    void synchronize() { detail::check_cuda(cudaStreamSynchronize(stream_), "synchronize"); }
+
+    // frees what keygen / encrypt / ... allocated (the reference leaks these)
+    static void release(Ciphertext& ct) { for (size_t i = 0; i < ct.components.size(); i++) delete ct.components[i]; ct.components.clear(); }
+    static void release(PublicKey& pk) { delete pk.pk1; delete pk.pk0; pk.pk0 = pk.pk1 = nullptr; }
+    static void release(SecretKey& sk) { delete sk.sk; sk.sk = nullptr; }
+    static void release(Plaintext& pt) { delete pt.poly; pt.poly = nullptr; }
+    static void release(RelinKeys& rlk) {
+        for (size_t d = rlk.rlk_keys.size(); d-- > 0;) { delete rlk.rlk_keys[d]->pk1; delete rlk.rlk_keys[d]->pk0; delete rlk.rlk_keys[d]; }
+        rlk.rlk_keys.clear();
+    }
+
+private:
+    void new_ciphertext(Ciphertext& ct) {
+        const uint32_t n = params_.n, L = params_.L;
+        Polynomial* c0 = new Polynomial(n, 2 * L);                               // owns [2][L][N]
+        Polynomial* c1 = new Polynomial(n, L, c0->rns + (size_t)L * n);
+        ct.components.clear(); ct.components.push_back(c0); ct.components.push_back(c1);
+    }
+    void replace(Ciphertext& dst, Ciphertext& src) {
+        // dst may alias an operand: the engine call has been queued on stream_, release after it completes
+        if (!dst.components.empty()) { synchronize(); release(dst); }
+        dst = src; src.components.clear();
+    }
+    void init_rng(uint64_t seed) { seed_ = seed; }
+    uint64_t next_seed() { seed_ += 0x9E3779B97F4A7C15ull; return seed_; }
+    static uint256_t mul_small(const uint256_t& a, uint64_t m) {
+        uint256_t r; unsigned __int128 c = 0;
+        for (int i = 0; i < 4; i++) { c += (unsigned __int128)a.limbs[i] * m; r.limbs[i] = (uint64_t)c; c >>= 64; }
+        return r;
+    }
+    static uint256_t div_small(const uint256_t& a, uint64_t d) {
+        uint256_t r; unsigned __int128 rem = 0;
+        for (int i = 3; i >= 0; i--) { rem = (rem << 64) | a.limbs[i]; r.limbs[i] = (uint64_t)(rem / d); rem %= d; }
+        return r;
+    }
+    SchemeParams params_;
+    fhe_b200_bfv* ctx_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    int device_ = 0;
+    uint64_t seed_ = 0;
+    detail::DeviceBuf scratch_;
+};
+
+}  // namespace fhe

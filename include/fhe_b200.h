@@ -115,6 +115,12 @@ int fhe_b200_pack_u256(void* d_u256, const uint64_t* d_in, size_t count, void* s
 int fhe_b200_to_rns_u256(fhe_b200_plan* plan, uint64_t* d_out, const void* d_u256, size_t count,
                          uint32_t limb_begin, uint32_t limb_count, void* stream);
 
+/* RNSContext::from_rns / RNS_NTTEngine::from_rns (src/rns.cu:65-72, from_rns_crt_kernel :117-141 -- writes 0 in the
+ * reference): CRT reconstruction of `count` values from limb-major residues [limb_count][count] into 256-bit words,
+ * value in [0, Q).  Needs Q = prod q_i < 2^256 (at most four 60-bit limbs). */
+int fhe_b200_from_rns_u256(fhe_b200_plan* plan, void* d_u256, const uint64_t* d_in, size_t count, uint32_t limb_begin,
+                           uint32_t limb_count, void* stream);
+
 /* ---- RNS linear combination: exact base conversion and t/Q scale-and-round ----------------------------------
  * replaces fast_base_conversion_kernel / RNSContext::base_extend (include/rns.cuh:47-49,116-125),
  * rns_mod_switch_kernel / mod_switch_rns (include/rns.cuh:44-45,128-136), poly_mod_switch_kernel

@@ -1,0 +1,148 @@
+// Mirrors the reference's test program (/root/reference/tests/test_fhe.cu) against the compat headers -- same
+// parameters and call sequences, but every "expected" value is ASSERTED (the reference only prints them).
+// Built and run by tests/test_gpu_compat.py on the GPU box.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "fhe/fhe.cuh"
+
+using namespace fhe;
+
+#define REQUIRE(c) do { if (!(c)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); std::exit(1); } } while (0)
+#define CUDA_CHECK(x) REQUIRE((x) == cudaSuccess)
+
+// the reference declares these in no header and defines them in src/bigint.cu:171-198; tests launch them <<<1,1>>>
+__global__ void batch_mod_add_kernel(uint256_t* r, const uint256_t* a, const uint256_t* b, uint256_t m, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) r[i] = add_mod(a[i], b[i], m);
+}
+__global__ void batch_mod_sub_kernel(uint256_t* r, const uint256_t* a, const uint256_t* b, uint256_t m, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) r[i] = sub_mod(a[i], b[i], m);
+}
+
+static void test_bigint_arithmetic() {           // tests/test_fhe.cu:24-63
+    uint256_t a(12345), b(67890), m(100000), *d_a, *d_b, *d_r, h;
+    CUDA_CHECK(cudaMalloc(&d_a, sizeof(uint256_t))); CUDA_CHECK(cudaMalloc(&d_b, sizeof(uint256_t))); CUDA_CHECK(cudaMalloc(&d_r, sizeof(uint256_t)));
+    CUDA_CHECK(cudaMemcpy(d_a, &a, sizeof(a), cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(d_b, &b, sizeof(b), cudaMemcpyHostToDevice));
+    batch_mod_add_kernel<<<1, 1>>>(d_r, d_a, d_b, m, 1);
+    CUDA_CHECK(cudaMemcpy(&h, d_r, sizeof(h), cudaMemcpyDeviceToHost));
+    REQUIRE(h.limbs[0] == 80235);
+    batch_mod_sub_kernel<<<1, 1>>>(d_r, d_a, d_b, m, 1);
+    CUDA_CHECK(cudaMemcpy(&h, d_r, sizeof(h), cudaMemcpyDeviceToHost));
+    REQUIRE(h.limbs[0] == 44455);
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_r);
+    std::printf("bigint arithmetic ok\n");
+}
+
+static void test_ntt_transform() {               // tests/test_fhe.cu:65-124
+    const uint32_t n = 1024; uint256_t modulus(12289);
+    NTTEngine ntt(n, modulus);
+    std::vector<uint256_t> h(n), r(n);
+    for (uint32_t i = 0; i < n; i++) h[i] = uint256_t(i + 1);
+    uint256_t* d; CUDA_CHECK(cudaMalloc(&d, n * sizeof(uint256_t)));
+    CUDA_CHECK(cudaMemcpy(d, h.data(), n * sizeof(uint256_t), cudaMemcpyHostToDevice));
+    ntt.forward(d); CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(r.data(), d, n * sizeof(uint256_t), cudaMemcpyDeviceToHost));
+    bool changed = false; for (uint32_t i = 0; i < n; i++) changed |= r[i].limbs[0] != h[i].limbs[0];
+    REQUIRE(changed);
+    ntt.inverse(d); CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(r.data(), d, n * sizeof(uint256_t), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) REQUIRE(r[i].limbs[0] == h[i].limbs[0] && r[i].limbs[1] == 0);
+    cudaFree(d);
+    std::printf("ntt round trip ok\n");
+}
+
+static void test_polynomial_multiplication() {   // tests/test_fhe.cu:126-167 (+ the check it never makes)
+    const uint32_t n = 2048; const uint64_t q = 40961;
+    NTTEngine ntt(n, uint256_t(q));
+    std::vector<uint256_t> a(n), b(n), r(n);
+    std::srand(1);
+    for (uint32_t i = 0; i < n; i++) { a[i] = uint256_t(std::rand() % 100); b[i] = uint256_t(std::rand() % 100); }
+    uint256_t *d_a, *d_b, *d_r;
+    CUDA_CHECK(cudaMalloc(&d_a, n * sizeof(uint256_t))); CUDA_CHECK(cudaMalloc(&d_b, n * sizeof(uint256_t))); CUDA_CHECK(cudaMalloc(&d_r, n * sizeof(uint256_t)));
+    CUDA_CHECK(cudaMemcpy(d_a, a.data(), n * sizeof(uint256_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d_b, b.data(), n * sizeof(uint256_t), cudaMemcpyHostToDevice));
+    ntt.multiply(d_r, d_a, d_b); CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(r.data(), d_r, n * sizeof(uint256_t), cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < n; k++) {           // schoolbook negacyclic product
+        int64_t acc = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t j = (k + n - i) % n;
+            const int64_t v = (int64_t)(a[i].limbs[0] * b[j].limbs[0] % q);
+            acc += (i <= k) ? v : -v;
+        }
+        acc %= (int64_t)q; if (acc < 0) acc += q;
+        REQUIRE(r[k].limbs[0] == (uint64_t)acc);
+    }
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_r);
+    std::printf("polynomial multiplication ok\n");
+}
+
+static void test_rns_context() {
+    const uint32_t n = 1024;
+    std::vector<uint256_t> primes = generate_rns_primes(40, 3, n);
+    RNSContext rns(primes);
+    std::vector<uint256_t> x(n), back(n);
+    for (uint32_t i = 0; i < n; i++) x[i] = uint256_t(0x123456789abcdefull * (i + 1), i, 0, 0);   // < 2^75 < Q (120 bits)
+    uint256_t *d_x, *d_r, *d_s;
+    CUDA_CHECK(cudaMalloc(&d_x, n * sizeof(uint256_t))); CUDA_CHECK(cudaMalloc(&d_r, 3 * n * sizeof(uint256_t))); CUDA_CHECK(cudaMalloc(&d_s, 3 * n * sizeof(uint256_t)));
+    CUDA_CHECK(cudaMemcpy(d_x, x.data(), n * sizeof(uint256_t), cudaMemcpyHostToDevice));
+    rns.to_rns(d_r, d_x, n);
+    rns.add_rns(d_s, d_r, d_r, n);       // 2x
+    rns.sub_rns(d_s, d_s, d_r, n);       // x
+    rns.from_rns(d_x, d_s, n);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(back.data(), d_x, n * sizeof(uint256_t), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) REQUIRE(back[i].limbs[0] == x[i].limbs[0] && back[i].limbs[1] == x[i].limbs[1] && back[i].limbs[2] == 0);
+    cudaFree(d_x); cudaFree(d_r); cudaFree(d_s);
+    std::printf("rns context ok\n");
+}
+
+static void test_fhe_operations() {              // tests/test_fhe.cu:169-273
+    SecurityParams params;
+    params.lambda = 128; params.poly_degree = 4096; params.log_q = 120; params.sigma = 3.2f; params.hamming_weight = 64;
+    FHEContext ctx(params);
+    REQUIRE(ctx.params().L == 2);
+    PublicKey pk; SecretKey sk; RelinKeys rlk;
+    ctx.keygen(pk, sk);
+    ctx.relinkey_gen(rlk, sk, 16);
+    std::vector<uint64_t> v1 = {5, 10, 15, 20}, v2 = {3, 6, 9, 12};
+    Plaintext pt1, pt2; ctx.encode(pt1, v1); ctx.encode(pt2, v2);
+    Ciphertext ct1, ct2; ctx.encrypt(ct1, pt1, pk); ctx.encrypt(ct2, pt2, pk);
+    Ciphertext ct_add; ctx.add(ct_add, ct1, ct2);
+    Ciphertext ct_mul; ctx.multiply(ct_mul, ct1, ct2, rlk);
+    Plaintext pa, pm, p1; ctx.decrypt(pa, ct_add, sk); ctx.decrypt(pm, ct_mul, sk); ctx.decrypt(p1, ct1, sk);
+    std::vector<uint64_t> ra, rm, r1; ctx.decode(ra, pa); ctx.decode(rm, pm); ctx.decode(r1, p1);
+    const uint64_t exp_add[4] = {8, 16, 24, 32};                    // tests/test_fhe.cu:264
+    const uint64_t exp_mul[8] = {15, 60, 150, 300, 375, 360, 240, 0};  // coefficient encoding -> negacyclic product
+    for (int i = 0; i < 4; i++) { REQUIRE(ra[i] == exp_add[i]); REQUIRE(r1[i] == v1[i]); }
+    for (int i = 4; i < 4096; i++) { REQUIRE(ra[i] == 0); REQUIRE(r1[i] == 0); }
+    for (int i = 0; i < 8; i++) REQUIRE(rm[i] == exp_mul[i]);
+    for (int i = 8; i < 4096; i++) REQUIRE(rm[i] == 0);
+    // chained: (ct1 * ct2) * ct1, result written over an operand
+    ctx.multiply(ct_mul, ct_mul, ct1, rlk);
+    Plaintext pc; ctx.decrypt(pc, ct_mul, sk); std::vector<uint64_t> rc; ctx.decode(rc, pc);
+    const uint64_t exp_chain[4] = {75, 450, 1575, 4200};            // (15+60x+150x^2+300x^3+..)(5+10x+15x^2+20x^3) low coefficients
+    for (int i = 0; i < 4; i++) REQUIRE(rc[i] == exp_chain[i]);
+    FHEContext::release(ct1); FHEContext::release(ct2); FHEContext::release(ct_add); FHEContext::release(ct_mul);
+    FHEContext::release(pt1); FHEContext::release(pt2); FHEContext::release(pa); FHEContext::release(pm); FHEContext::release(p1); FHEContext::release(pc);
+    FHEContext::release(rlk); FHEContext::release(pk); FHEContext::release(sk);
+    std::printf("fhe operations ok\n");
+}
+
+static void test_errors() {
+    bool threw = false;
+    try { NTTEngine bad(4096, uint256_t(12289)); } catch (const std::runtime_error&) { threw = true; }   // 12289 != 1 mod 8192
+    REQUIRE(threw);
+    std::printf("error behaviour ok\n");
+}
+
+int main() {
+    test_bigint_arithmetic();
+    test_ntt_transform();
+    test_polynomial_multiplication();
+    test_rns_context();
+    test_fhe_operations();
+    test_errors();
+    std::printf("ALL COMPAT TESTS PASSED\n");
+    return 0;
+}

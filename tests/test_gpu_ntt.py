@@ -187,6 +187,12 @@ def test_u256_edge_and_bitrev(fhe, oracle, chain):
     for l, q in enumerate(chain[:3]):
         exp = [(int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192) % q for r in words[:32]]
         assert [int(x) for x in res[l, :32]] == exp
+    # CRT back: from_rns(to_rns(x)) == x mod Q
+    Q = chain[0] * chain[1] * chain[2]
+    back = to_host(eng.from_rns(to_device(res))).reshape(n, 4)
+    for r, b in list(zip(words, back))[:64]:
+        x = int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192
+        assert int(b[0]) | int(b[1]) << 64 | int(b[2]) << 128 | int(b[3]) << 192 == x % Q
     # natural-order NTT values = definitional transform
     q = 12289
     x = rng.integers(0, q, n, dtype=np.uint64)
