@@ -102,6 +102,8 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
     p->sm_count = prop.multiProcessorCount;
     p->moduli.assign(h_moduli, h_moduli + n_limbs);
     p->hb = lazy_headroom(h_moduli, n_limbs);
+    p->near60 = all_near60(h_moduli, n_limbs);
+    if (getenv("FHE_B200_NO_NEAR60")) p->near60 = false;
     if (const char* e = getenv("FHE_B200_NTT_CHUNK_MB")) { long mb = atol(e); if (mb > 0) p->chunk_bytes = (size_t)mb << 20; }
     p->h_params.resize(n_limbs);
     std::vector<Twiddle> fwd((size_t)n_limbs * n), inv((size_t)n_limbs * n);

@@ -45,6 +45,7 @@ struct fhe_b200_plan {
     uint32_t n = 0, logn = 0, limbs = 0;
     int device = 0;
     int hb = 16;                                   // lazy head-room (16: all q < 2^60, 8: all q < 2^61)
+    bool near60 = false;                           // every q in [2^60 - 2^55, 2^60): cheap range reduction (near60_reduce)
     std::vector<uint64_t> moduli;
     fhe_b200::Twiddle* d_fwd = nullptr;            // [limbs][n]
     fhe_b200::Twiddle* d_inv = nullptr;            // [limbs][n]

@@ -175,6 +175,29 @@ FHE_HD u64 barrett128(u64 hi, u64 lo, u64 q, u64 mu_hi, u64 mu_lo) {
     return csub(r, q);
 }
 
+// Range reduction for moduli just below 2^60 (2^60 - q <= 2^55, true for the whole 60-bit prime chain):
+// x < 16q  ->  x - (x >> 60) * q  in [0, 2q).   (k = x >> 60 <= x/q, and the remainder is x mod 2^60 + k (2^60 - q) < 2q.)
+// Three instructions (SHF, IMAD.WIDE, IMAD) instead of the six of a 64-bit compare-and-subtract.  nq = 2^64 - q.
+FHE_HD u64 near60_reduce(u64 x, u64 nq) {
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 x0, x1, k, n0, n1;\n\t"
+        ".reg .u64 t;\n\t"
+        "mov.b64 {x0, x1}, %1;\n\t"
+        "mov.b64 {n0, n1}, %2;\n\t"
+        "shr.u32 k, x1, 28;\n\t"
+        "mad.wide.u32 t, k, n0, %1;\n\t"
+        "mov.b64 {x0, x1}, t;\n\t"
+        "mad.lo.u32 x1, k, n1, x1;\n\t"
+        "mov.b64 %0, {x0, x1};\n\t"
+        "}" : "=l"(r) : "l"(x), "l"(nq));
+    return r;
+#else
+    return x + (x >> 60) * nq;
+#endif
+}
+
 FHE_HD u64 mul_mod(u64 a, u64 b, const LimbParams& P) {
     u64 hi, lo;
     mul128(a, b, hi, lo);

@@ -72,18 +72,20 @@ FHE_HD void st2(u64* p, u64 a, u64 b) {
 #endif
 }
 
-// bounds in units of q; the twiddle product is lazy in [0, 4q) (shoup_mul_lazy4)
-FHE_HDC int fwd_bound_after(int B, int stages, int HB) {
-    for (int i = 0; i < stages; i++) { if (B + 4 > HB) B = HB / 2; B += 4; }
+// bounds in units of q; the twiddle product is lazy in [0, 4q) (shoup_mul_lazy4).
+// NEAR: every modulus q satisfies 2^60 - 2^55 <= q < 2^60, so near60_reduce brings anything below 16q under 2q.
+FHE_HDC int red_to(int HB, bool NEAR) { return NEAR ? 2 : HB / 2; }
+FHE_HDC int fwd_bound_after(int B, int stages, int HB, bool NEAR) {
+    for (int i = 0; i < stages; i++) { if (B + 4 > HB) B = red_to(HB, NEAR); B += 4; }
     return B;
 }
-FHE_HDC int inv_bound_step(int B, int HB) {
+FHE_HDC int inv_bound_step(int B, int HB, bool NEAR) {
     int nb = 2 * B > 4 ? 2 * B : 4;
-    if (2 * nb > HB) nb = nb / 2 > 4 ? nb / 2 : 4;
+    if (2 * nb > HB) { const int r = NEAR ? 2 : nb / 2; nb = r > 4 ? r : 4; }
     return nb;
 }
-FHE_HDC int inv_bound_after(int B, int stages, int HB) {
-    for (int i = 0; i < stages; i++) B = inv_bound_step(B, HB);
+FHE_HDC int inv_bound_after(int B, int stages, int HB, bool NEAR) {
+    for (int i = 0; i < stages; i++) B = inv_bound_step(B, HB, NEAR);
     return B;
 }
 
@@ -127,7 +129,7 @@ FHE_HDC int p3_entries(int LB) { return (1 << (LB - 4)) * (16 - (1 << (12 - LB))
 // ---- forward stages on a register array of E = 2^LE elements: R stages, active bits = low R bits of e ----
 // B (template) is the bound on entry in units of q; the bound on exit is fwd_bound_after(B, R, HB).
 // Compile-time recursion over the stage index V keeps every array index and every bound a constant.
-template <int LE, int R, int HB, int B, class TW, int V = 0>
+template <int LE, int R, int HB, bool NEAR, int B, class TW, int V = 0>
 FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, u64 q) {
     if constexpr (V < R) {
         constexpr int st = 1 << (R - 1 - V);
@@ -143,20 +145,20 @@ FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, u64 q) {
                 const int e = (key << (R - V)) | j;
                 u64 X = x[e];
                 FHE_BOUND(X, B, q); FHE_BOUND(x[e + st], B, q);
-                if (red) X = csub(X, hq);
+                if (red) X = NEAR ? near60_reduce(X, nq) : csub(X, hq);
                 const u64 T = shoup_mul_lazy4(x[e + st], w.w, w.ws, nq);
-                FHE_BOUND(T, 4, q); FHE_BOUND((unsigned __int128)X + T, (red ? HB / 2 : B) + 4, q);
+                FHE_BOUND(T, 4, q); FHE_BOUND((unsigned __int128)X + T, (red ? red_to(HB, NEAR) : B) + 4, q);
                 x[e] = X + T;
                 x[e + st] = X + fourq - T;
             }
         }
-        fwd_stages<LE, R, HB, (red ? HB / 2 : B) + 4, TW, V + 1>(x, tw, q);
+        fwd_stages<LE, R, HB, NEAR, (red ? red_to(HB, NEAR) : B) + 4, TW, V + 1>(x, tw, q);
     }
 }
 
 // ---- inverse stages (mirror order: V runs R-1 .. 0).  LAST: the final stage of the whole transform folds N^-1 in.
 // exit bound: inv_bound_after(B, R, HB), or 4 when LAST.
-template <int LE, int R, int HB, bool LAST, int B, class TW, int V = R - 1>
+template <int LE, int R, int HB, bool NEAR, bool LAST, int B, class TW, int V = R - 1>
 FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
     if constexpr (V >= 0) {
         constexpr int st = 1 << (R - 1 - V);
@@ -180,18 +182,19 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
                 u64 S = X + Y;
                 const u64 D = X + bq - Y;
                 if (last) S = shoup_mul_lazy4(S, P.ninv, P.ninv_s, nq);
-                else if (red) S = csub(S, bq);
+                else if (red) S = NEAR ? near60_reduce(S, nq) : csub(S, bq);
                 x[e] = S;
                 x[e + st] = shoup_mul_lazy4(D, w.w, w.ws, nq);
             }
         }
-        inv_stages<LE, R, HB, LAST, inv_bound_step(B, HB), TW, V - 1>(x, tw, P);
+        inv_stages<LE, R, HB, NEAR, LAST, inv_bound_step(B, HB, NEAR), TW, V - 1>(x, tw, P);
     }
 }
 
 // bring a value bounded by B*q into [0, q)
-template <int HB, int B>
+template <int HB, bool NEAR, int B>
 FHE_HD u64 normalize(u64 x, u64 q) {
+    if (NEAR && B > 2) return csub(near60_reduce(x, 0 - q), q);
     if (HB >= 16 && B > 8) x = csub(x, 8 * q);
     if (HB >= 8 && B > 4) x = csub(x, 4 * q);
     if (B > 2) x = csub(x, 2 * q);
@@ -207,7 +210,7 @@ FHE_HD u64 normalize(u64 x, u64 q) {
 //   s12/s3 : this tile's staged twiddle blocks (see TwP1/TwP2/TwP3), copied from the plan's per-tile tables
 //   B0   : entry bound (1 + 2*K1 after pass A, 1 when K1 = 0)
 // =====================================================================================================
-template <int LB, int HB>
+template <int LB, int HB, bool NEAR>
 struct TileFwd {
     static constexpr int NB = 1 << LB;
     static constexpr int NT = NB / 16;
@@ -221,7 +224,7 @@ struct TileFwd {
     }
     template <int B0>
     static FHE_HD void phase1_compute(u32 tid, u64 (&x)[16], u64* s, const Twiddle* s12, u64 q) {
-        fwd_stages<4, 4, HB, B0>(x, TwP1{s12}, q);
+        fwd_stages<4, 4, HB, NEAR, B0>(x, TwP1{s12}, q);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz((e << (LB - 4)) | tid)] = x[e];
     }
@@ -238,7 +241,7 @@ struct TileFwd {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz(base | (e << (LB - 8)))];
-        fwd_stages<4, 4, HB, fwd_bound_after(B0, 4, HB)>(x, TwP2{s12, hi}, q);
+        fwd_stages<4, 4, HB, NEAR, fwd_bound_after(B0, 4, HB, NEAR)>(x, TwP2{s12, hi}, q);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
     }
@@ -251,13 +254,13 @@ struct TileFwd {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
             ld2(s + a, x[2 * k], x[2 * k + 1]);
         }
-        constexpr int B3 = fwd_bound_after(B0, 8, HB);
-        constexpr int BE = fwd_bound_after(B3, R3, HB);
-        fwd_stages<4, R3, HB, B3>(x, TwP3<NT, R3>{s3, tid}, q);
+        constexpr int B3 = fwd_bound_after(B0, 8, HB, NEAR);
+        constexpr int BE = fwd_bound_after(B3, R3, HB, NEAR);
+        fwd_stages<4, R3, HB, NEAR, B3>(x, TwP3<NT, R3>{s3, tid}, q);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
-            st2(s + a, normalize<HB, BE>(x[2 * k], q), normalize<HB, BE>(x[2 * k + 1], q));
+            st2(s + a, normalize<HB, NEAR, BE>(x[2 * k], q), normalize<HB, NEAR, BE>(x[2 * k + 1], q));
         }
     }
     // coalesced 16-byte copy-out of the swizzled tile
@@ -273,7 +276,7 @@ struct TileFwd {
 
 // pass B', inverse: mirror image.  phase1 = coalesced copy-in, phase2 = low strides (16 contiguous per thread),
 // phase3 = middle, phase4 = high strides + store.  LAST: K1 == 0, i.e. this tile pass ends the transform.
-template <int LB, int HB>
+template <int LB, int HB, bool NEAR>
 struct TileInv {
     static constexpr int NB = 1 << LB;
     static constexpr int NT = NB / 16;
@@ -296,7 +299,7 @@ struct TileInv {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
             ld2(s + a, x[2 * k], x[2 * k + 1]);
         }
-        inv_stages<4, R3, HB, false, 1>(x, TwP3<NT, R3>{s3, tid}, P);
+        inv_stages<4, R3, HB, NEAR, false, 1>(x, TwP3<NT, R3>{s3, tid}, P);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
@@ -309,7 +312,7 @@ struct TileInv {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz(base | (e << (LB - 8)))];
-        inv_stages<4, 4, HB, false, inv_bound_after(1, R3, HB)>(x, TwP2{s12, hi}, P);
+        inv_stages<4, 4, HB, NEAR, false, inv_bound_after(1, R3, HB, NEAR)>(x, TwP2{s12, hi}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
     }
@@ -318,19 +321,19 @@ struct TileInv {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz((e << (LB - 4)) | tid)];
-        inv_stages<4, 4, HB, LAST, inv_bound_after(1, R3 + 4, HB)>(x, TwP1{s12}, P);
+        inv_stages<4, 4, HB, NEAR, LAST, inv_bound_after(1, R3 + 4, HB, NEAR)>(x, TwP1{s12}, P);
         // LAST: fully reduce.  Otherwise leave the lazy bound for pass A' (it starts from out_bound()).
 #pragma unroll
-        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize<HB, 4>(x[e], P.q) : x[e];
+        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize<HB, NEAR, 4>(x[e], P.q) : x[e];
     }
-    static FHE_HDC int out_bound() { return inv_bound_after(1, LB, HB); }
+    static FHE_HDC int out_bound() { return inv_bound_after(1, LB, HB, NEAR); }
 };
 
 // =====================================================================================================
 // pass A (forward) / A' (inverse): 2^K1 rows x V adjacent columns per thread, registers only.
 //   g : limb base, col : first column of this thread, row stride = NB elements (V is 1 or 2)
 // =====================================================================================================
-template <int K1, int V, int LB, int HB>
+template <int K1, int V, int LB, int HB, bool NEAR>
 struct RowPass {
     static constexpr int NA = 1 << K1;
     static constexpr int NB = 1 << LB;
@@ -343,14 +346,14 @@ struct RowPass {
             else x[0][r] = gin[(size_t)r * NB + col];
         }
 #pragma unroll
-        for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, 1>(x[c], TwGlobal<0>{tw, 1u}, q);
+        for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, NEAR, 1>(x[c], TwGlobal<0>{tw, 1u}, q);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
             if (V == 2) st2(gout + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
             else gout[(size_t)r * NB + col] = x[0][r];
         }
     }
-    static FHE_HDC int fwd_out_bound() { return fwd_bound_after(1, K1, HB); }
+    static FHE_HDC int fwd_out_bound() { return fwd_bound_after(1, K1, HB, NEAR); }
 
     template <int B0>
     static FHE_HD void inverse(u64* g, u32 col, const Twiddle* tw, const LimbParams& P) {
@@ -361,11 +364,11 @@ struct RowPass {
             else x[0][r] = g[(size_t)r * NB + col];
         }
 #pragma unroll
-        for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, true, B0>(x[c], TwGlobal<0>{tw, 1u}, P);
+        for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, NEAR, true, B0>(x[c], TwGlobal<0>{tw, 1u}, P);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
-            if (V == 2) st2(g + (size_t)r * NB + col, normalize<HB, 4>(x[0][r], P.q), normalize<HB, 4>(x[V - 1][r], P.q));
-            else g[(size_t)r * NB + col] = normalize<HB, 4>(x[0][r], P.q);
+            if (V == 2) st2(g + (size_t)r * NB + col, normalize<HB, NEAR, 4>(x[0][r], P.q), normalize<HB, NEAR, 4>(x[V - 1][r], P.q));
+            else g[(size_t)r * NB + col] = normalize<HB, NEAR, 4>(x[0][r], P.q);
         }
     }
 };

@@ -50,9 +50,9 @@ struct TileSmem {
 
 // One CTA = one (limb, tile): stages that tile's twiddles once with two bulk copies (TMA), then runs the tile pass for
 // every polynomial of its group out of shared memory.
-template <int LB, int K1, int HB>
+template <int LB, int K1, int HB, bool NEAR>
 __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const NttArgs a) {
-    using T = TileFwd<LB, HB>;
+    using T = TileFwd<LB, HB, NEAR>;
     using SM = TileSmem<LB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* s = reinterpret_cast<u64*>(smem_raw);
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const Nt
         bulk_copy_g2s(s3, a.p3 + ((size_t)pl * a.tiles + tile) * a.p3n, (uint32_t)SM::p3_bytes, bar);
     }
     const u64 q = a.params[pl].q;
-    constexpr int B0 = fwd_bound_after(1, K1, HB);
+    constexpr int B0 = fwd_bound_after(1, K1, HB, NEAR);
     bool staged = false;
     for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
         const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)tile * T::NB;
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const Nt
     }
 }
 
-template <int LB, int K1, int HB>
+template <int LB, int K1, int HB, bool NEAR>
 __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_inv_kernel(const NttArgs a) {
-    using T = TileInv<LB, HB>;
+    using T = TileInv<LB, HB, NEAR>;
     using SM = TileSmem<LB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* s = reinterpret_cast<u64*>(smem_raw);
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_inv_kernel(const Nt
 
 constexpr int kRowThreads = 256;
 
-template <int LB, int K1, int HB, int V>
+template <int LB, int K1, int HB, bool NEAR, int V>
 __global__ void __launch_bounds__(kRowThreads) ntt_row_fwd_kernel(const NttArgs a) {
     constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
     uint32_t limb, cb, poly;
@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(kRowThreads) ntt_row_fwd_kernel(const NttArgs 
     const size_t off = ((size_t)poly * a.limb_count + limb) * a.n;
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t col = (cb * kRowThreads + threadIdx.x) * V;
-    RowPass<K1, V, LB, HB>::forward(a.out + off, a.in + off, col, a.tw + (size_t)pl * a.n, a.params[pl].q);
+    RowPass<K1, V, LB, HB, NEAR>::forward(a.out + off, a.in + off, col, a.tw + (size_t)pl * a.n, a.params[pl].q);
 }
 
-template <int LB, int K1, int HB, int V>
+template <int LB, int K1, int HB, bool NEAR, int V>
 __global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs a) {
     constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
     uint32_t limb, cb, poly;
@@ -149,12 +149,12 @@ __global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs 
     const size_t off = ((size_t)poly * a.limb_count + limb) * a.n;
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t col = (cb * kRowThreads + threadIdx.x) * V;
-    constexpr int B0 = TileInv<LB, HB>::out_bound();
+    constexpr int B0 = TileInv<LB, HB, NEAR>::out_bound();
     // in place on `out`: the tile pass wrote there
-    RowPass<K1, V, LB, HB>::template inverse<B0>(a.out + off, col, a.tw + (size_t)pl * a.n, a.params[pl]);
+    RowPass<K1, V, LB, HB, NEAR>::template inverse<B0>(a.out + off, col, a.tw + (size_t)pl * a.n, a.params[pl]);
 }
 
-template <int LB, int K1, int HB>
+template <int LB, int K1, int HB, bool NEAR>
 static int run_chunk(NttArgs a, bool inverse, int sm_count, cudaStream_t st) {
     constexpr int V = (K1 >= 5) ? 1 : 2;
     const uint32_t pls = a.nl * a.nb;
@@ -171,31 +171,31 @@ static int run_chunk(NttArgs a, bool inverse, int sm_count, cudaStream_t st) {
     constexpr size_t smem = TileSmem<LB>::total;
     static bool attr_set = false;
     if (!attr_set) {
-        FHE_CUDA(cudaFuncSetAttribute(ntt_tile_fwd_kernel<LB, K1, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FHE_CUDA(cudaFuncSetAttribute(ntt_tile_inv_kernel<LB, K1, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FHE_CUDA(cudaFuncSetAttribute(ntt_tile_fwd_kernel<LB, K1, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FHE_CUDA(cudaFuncSetAttribute(ntt_tile_inv_kernel<LB, K1, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     if (!inverse) {
         if constexpr (K1 > 0) {
             const uint32_t row_grid = pls * ((1u << LB) / (V * kRowThreads));
             if (prof) profile_begin(2, pls, st);
-            ntt_row_fwd_kernel<LB, K1, HB, V><<<row_grid, kRowThreads, 0, st>>>(a);
+            ntt_row_fwd_kernel<LB, K1, HB, NEAR, V><<<row_grid, kRowThreads, 0, st>>>(a);
             if (prof) profile_end(st);
             FHE_LAUNCH_CHECK();
         }
         if (prof) profile_begin(0, pls, st);
-        ntt_tile_fwd_kernel<LB, K1, HB><<<tile_grid, 1 << (LB - 4), smem, st>>>(a);
+        ntt_tile_fwd_kernel<LB, K1, HB, NEAR><<<tile_grid, 1 << (LB - 4), smem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
     } else {
         if (prof) profile_begin(1, pls, st);
-        ntt_tile_inv_kernel<LB, K1, HB><<<tile_grid, 1 << (LB - 4), smem, st>>>(a);
+        ntt_tile_inv_kernel<LB, K1, HB, NEAR><<<tile_grid, 1 << (LB - 4), smem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
         if constexpr (K1 > 0) {
             const uint32_t row_grid = pls * ((1u << LB) / (V * kRowThreads));
             if (prof) profile_begin(3, pls, st);
-            ntt_row_inv_kernel<LB, K1, HB, V><<<row_grid, kRowThreads, 0, st>>>(a);
+            ntt_row_inv_kernel<LB, K1, HB, NEAR, V><<<row_grid, kRowThreads, 0, st>>>(a);
             if (prof) profile_end(st);
             FHE_LAUNCH_CHECK();
         }
@@ -203,18 +203,18 @@ static int run_chunk(NttArgs a, bool inverse, int sm_count, cudaStream_t st) {
     return 0;
 }
 
-template <int HB>
+template <int HB, bool NEAR>
 static int dispatch(uint32_t logn, const NttArgs& a, bool inverse, int sm_count, cudaStream_t st) {
     switch (logn) {
-        case 9: return run_chunk<9, 0, HB>(a, inverse, sm_count, st);
-        case 10: return run_chunk<10, 0, HB>(a, inverse, sm_count, st);
-        case 11: return run_chunk<11, 0, HB>(a, inverse, sm_count, st);
-        case 12: return run_chunk<12, 0, HB>(a, inverse, sm_count, st);
-        case 13: return run_chunk<12, 1, HB>(a, inverse, sm_count, st);
-        case 14: return run_chunk<12, 2, HB>(a, inverse, sm_count, st);
-        case 15: return run_chunk<12, 3, HB>(a, inverse, sm_count, st);
-        case 16: return run_chunk<12, 4, HB>(a, inverse, sm_count, st);
-        case 17: return run_chunk<12, 5, HB>(a, inverse, sm_count, st);
+        case 9: return run_chunk<9, 0, HB, NEAR>(a, inverse, sm_count, st);
+        case 10: return run_chunk<10, 0, HB, NEAR>(a, inverse, sm_count, st);
+        case 11: return run_chunk<11, 0, HB, NEAR>(a, inverse, sm_count, st);
+        case 12: return run_chunk<12, 0, HB, NEAR>(a, inverse, sm_count, st);
+        case 13: return run_chunk<12, 1, HB, NEAR>(a, inverse, sm_count, st);
+        case 14: return run_chunk<12, 2, HB, NEAR>(a, inverse, sm_count, st);
+        case 15: return run_chunk<12, 3, HB, NEAR>(a, inverse, sm_count, st);
+        case 16: return run_chunk<12, 4, HB, NEAR>(a, inverse, sm_count, st);
+        case 17: return run_chunk<12, 5, HB, NEAR>(a, inverse, sm_count, st);
     }
     set_error("unsupported ring degree 2^%u (supported: 2^9 .. 2^17)", logn);
     return FHE_B200_EINVAL;
@@ -246,7 +246,9 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
         for (uint32_t b0 = 0; b0 < batch; b0 += nb) {
             a.l0 = l0; a.nl = (l0 + nl <= limb_count) ? nl : limb_count - l0;
             a.b0 = b0; a.nb = (b0 + nb <= batch) ? nb : batch - b0;
-            const int rc = plan->hb == 16 ? dispatch<16>(plan->logn, a, inverse, plan->sm_count, st) : dispatch<8>(plan->logn, a, inverse, plan->sm_count, st);
+            const int rc = plan->near60 ? dispatch<16, true>(plan->logn, a, inverse, plan->sm_count, st)
+                         : plan->hb == 16 ? dispatch<16, false>(plan->logn, a, inverse, plan->sm_count, st)
+                                          : dispatch<8, false>(plan->logn, a, inverse, plan->sm_count, st);
             if (rc) return rc;
         }
     return 0;

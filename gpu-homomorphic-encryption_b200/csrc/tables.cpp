@@ -61,4 +61,10 @@ int lazy_headroom(const uint64_t* moduli, uint32_t count) {
     return hb;
 }
 
+bool all_near60(const uint64_t* moduli, uint32_t count) {
+    for (uint32_t i = 0; i < count; i++)
+        if ((moduli[i] >> 60) != 0 || moduli[i] < (1ull << 60) - (1ull << 55)) return false;
+    return true;
+}
+
 }  // namespace fhe_b200

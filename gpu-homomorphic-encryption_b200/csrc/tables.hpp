@@ -18,5 +18,7 @@ void build_tile_tables(const Twiddle* main, uint32_t logn, Twiddle* p12, Twiddle
 size_t tile_p3_entries(uint32_t logn);
 // head-room of the lazy butterflies for a set of moduli: 16 if all < 2^60, else 8 (all < 2^61)
 int lazy_headroom(const uint64_t* moduli, uint32_t count);
+// true when every modulus lies in [2^60 - 2^55, 2^60) (the whole deterministic 60-bit prime chain does)
+bool all_near60(const uint64_t* moduli, uint32_t count);
 
 }  // namespace fhe_b200

@@ -19,17 +19,17 @@ static TileTabs tile_tabs(const Twiddle* main, u32 logn) {
     return t;
 }
 
-template <int LB, int K1, int HB>
+template <int LB, int K1, int HB, bool NEAR>
 static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
     constexpr int NB = 1 << LB;
     if constexpr (K1 > 0) {
         constexpr int V = (K1 >= 5) ? 1 : 2;
-        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB>::forward(d, d, col, tw, P.q);
+        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB, NEAR>::forward(d, d, col, tw, P.q);
     }
-    constexpr int B0 = fwd_bound_after(1, K1, HB);
+    constexpr int B0 = fwd_bound_after(1, K1, HB, NEAR);
     const TileTabs tt = tile_tabs(tw, LB + K1);
     std::vector<u64> s(NB);
-    using T = TileFwd<LB, HB>;
+    using T = TileFwd<LB, HB, NEAR>;
     for (u32 b = 0; b < (1u << K1); b++) {
         u64* g = d + (size_t)b * NB;
         // what the kernel's two bulk copies stage into shared memory
@@ -42,12 +42,12 @@ static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
     }
 }
 
-template <int LB, int K1, int HB>
+template <int LB, int K1, int HB, bool NEAR>
 static void inv_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
     constexpr int NB = 1 << LB;
     const TileTabs tt = tile_tabs(tw, LB + K1);
     std::vector<u64> s(NB);
-    using T = TileInv<LB, HB>;
+    using T = TileInv<LB, HB, NEAR>;
     for (u32 b = 0; b < (1u << K1); b++) {
         u64* g = d + (size_t)b * NB;
         std::vector<Twiddle> s12(tt.p12.begin() + (size_t)b * 256, tt.p12.begin() + (size_t)(b + 1) * 256);
@@ -60,13 +60,13 @@ static void inv_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
     if constexpr (K1 > 0) {
         constexpr int V = (K1 >= 5) ? 1 : 2;
         constexpr int B0 = T::out_bound();
-        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB>::template inverse<B0>(d, col, tw, P);
+        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB, NEAR>::template inverse<B0>(d, col, tw, P);
     }
 }
 
-template <int HB>
+template <int HB, bool NEAR>
 static int run(u64* d, u32 logn, const Twiddle* tw, const LimbParams& P, int inverse) {
-#define CASE(LBv, K1v) if (inverse) inv_limb<LBv, K1v, HB>(d, tw, P); else fwd_limb<LBv, K1v, HB>(d, tw, P); return 0;
+#define CASE(LBv, K1v) if (inverse) inv_limb<LBv, K1v, HB, NEAR>(d, tw, P); else fwd_limb<LBv, K1v, HB, NEAR>(d, tw, P); return 0;
     switch (logn) {
         case 9: CASE(9, 0)
         case 10: CASE(10, 0)
@@ -88,8 +88,9 @@ extern "C" int emul_ntt(uint64_t* data, uint32_t n, uint64_t q, int inverse, int
     if (build_limb_tables(q, n, fwd.data(), inv.data(), &P)) return -1;
     const u32 logn = host::ilog2(n);
     const Twiddle* tw = inverse ? inv.data() : fwd.data();
-    if (hb == 16) return run<16>(data, logn, tw, P, inverse);
-    if (hb == 8) return run<8>(data, logn, tw, P, inverse);
+    if (hb == 16 && all_near60(&q, 1)) return run<16, true>(data, logn, tw, P, inverse);     // what the plan would pick
+    if (hb == 16) return run<16, false>(data, logn, tw, P, inverse);
+    if (hb == 8) return run<8, false>(data, logn, tw, P, inverse);
     return -3;
 }
 

@@ -49,6 +49,21 @@ def test_kernel_bodies_match_oracle(emul, oracle, chain, logn):
             assert np.array_equal(_run(emul, ref, q, 1, hb), a)
 
 
+def test_near60_boundary_prime(emul, oracle):
+    """near60_reduce must hold its [0, 2q) promise for the smallest admissible modulus (2^60 - q just under 2^55)."""
+    q = (1 << 60) - (1 << 55) + 1
+    while not (oracle.is_prime(q) and q % (1 << 18) == 1):
+        q += 1 << 18
+    assert (1 << 60) - (1 << 55) <= q < (1 << 60)
+    for logn in (12, 16):
+        n = 1 << logn
+        rng = np.random.default_rng(5)
+        for a in (rng.integers(0, q, n, dtype=np.uint64), np.full(n, q - 1, dtype=np.uint64)):
+            ref = oracle.ntt_forward(a, q)
+            assert np.array_equal(_run(emul, a, q, 0, 16), ref)
+            assert np.array_equal(_run(emul, ref, q, 1, 16), a)
+
+
 def test_reference_test_primes(emul, oracle):
     # the reference's own NTT test moduli: (1024, 12289) tests/test_fhe.cu:68-70, (2048, 40961) :129-131
     for n, q in [(1024, 12289), (2048, 40961)]:
