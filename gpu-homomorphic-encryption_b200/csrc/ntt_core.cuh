@@ -316,15 +316,24 @@ struct TileInv {
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
     }
-    template <bool LAST>
-    static FHE_HD void phase4(u32 tid, u64* g, const u64* s, const Twiddle* s12, const LimbParams& P) {
-        u64 x[16];
+    // phase 4 is split so that the kernel can release the tile buffer (for the next tile's asynchronous copy-in)
+    // as soon as every thread holds its inputs
+    static FHE_HD void phase4_load(u32 tid, const u64* s, u64 (&x)[16]) {
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz((e << (LB - 4)) | tid)];
+    }
+    template <bool LAST>
+    static FHE_HD void phase4_compute(u32 tid, u64 (&x)[16], u64* g, const Twiddle* s12, const LimbParams& P) {
         inv_stages<4, 4, HB, NEAR, LAST, inv_bound_after(1, R3 + 4, HB, NEAR)>(x, TwP1{s12}, P);
         // LAST: fully reduce.  Otherwise leave the lazy bound for pass A' (it starts from out_bound()).
 #pragma unroll
         for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize<HB, NEAR, 4>(x[e], P.q) : x[e];
+    }
+    template <bool LAST>
+    static FHE_HD void phase4(u32 tid, u64* g, const u64* s, const Twiddle* s12, const LimbParams& P) {
+        u64 x[16];
+        phase4_load(tid, s, x);
+        phase4_compute<LAST>(tid, x, g, s12, P);
     }
     static FHE_HDC int out_bound() { return inv_bound_after(1, LB, HB, NEAR); }
 };

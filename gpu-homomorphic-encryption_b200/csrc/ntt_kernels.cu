@@ -39,6 +39,24 @@ __device__ __forceinline__ void decode(uint32_t i, uint32_t inner, uint32_t unit
     limb = l0 + r / units;
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS) of one tile into the swizzled layout
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+template <int LB>
+__device__ __forceinline__ void tile_copy_in_async(uint32_t tid, const u64* g, u64* s) {
+    constexpr int NT = 1 << (LB - 4);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t c = tid + i * NT;                            // logical 16-byte chunk
+        const uint32_t p = ((c >> 3) << 3) | ((c & 7) ^ ((c >> 3) & 7));
+        cp_async_16(s + 2 * p, g + 2 * c);
+    }
+}
+
 template <int LB>
 struct TileSmem {
     static constexpr int NB = 1 << LB;
@@ -72,19 +90,25 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const Nt
     }
     const u64 q = a.params[pl].q;
     constexpr int B0 = fwd_bound_after(1, K1, HB, NEAR);
-    bool staged = false;
-    for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
-        const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)tile * T::NB;
-        const u64* src = (K1 > 0 ? a.out : a.in) + off;      // K1 > 0: the row pass already moved the data to `out`
-        u64 x[16];
-        T::phase1_load(tid, src, x);
-        if (!staged) { mbar_wait(bar, 0); staged = true; }
+    const u64* base_in = (K1 > 0 ? a.out : a.in);             // K1 > 0: the row pass already moved the data to `out`
+    const size_t limb_off = (size_t)limb * a.n + (size_t)tile * T::NB;
+    const size_t poly_stride = (size_t)a.limb_count * a.n;
+    uint32_t poly = a.b0 + grp;
+    const uint32_t poly_end = a.b0 + a.nb;
+    u64 x[16];
+    if (poly < poly_end) T::phase1_load(tid, base_in + poly * poly_stride + limb_off, x);
+    mbar_wait(bar, 0);                                        // staged twiddles have landed
+    for (; poly < poly_end; poly += a.groups) {
+        const size_t off = poly * poly_stride + limb_off;
         T::template phase1_compute<B0>(tid, x, s, s12, q);
         __syncthreads();
         T::template phase2<B0>(tid, s, s12, q);
         __syncthreads();
         T::template phase3<B0>(tid, s, s3, q);
         __syncthreads();
+        // software pipeline: the next polynomial's global loads fly while this one is copied out
+        const uint32_t next = poly + a.groups;
+        if (next < poly_end) T::phase1_load(tid, base_in + next * poly_stride + limb_off, x);
         T::phase4(tid, a.out + off, s);
         __syncthreads();
     }
@@ -111,18 +135,26 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_inv_kernel(const Nt
         bulk_copy_g2s(s3, a.p3 + ((size_t)pl * a.tiles + tile) * a.p3n, (uint32_t)SM::p3_bytes, bar);
     }
     const LimbParams P = a.params[pl];
-    bool staged = false;
-    for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
-        const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)tile * T::NB;
-        T::phase1(tid, a.in + off, s);
-        if (!staged) { mbar_wait(bar, 0); staged = true; }
+    const size_t limb_off = (size_t)limb * a.n + (size_t)tile * T::NB;
+    const size_t poly_stride = (size_t)a.limb_count * a.n;
+    uint32_t poly = a.b0 + grp;
+    const uint32_t poly_end = a.b0 + a.nb;
+    if (poly < poly_end) tile_copy_in_async<LB>(tid, a.in + poly * poly_stride + limb_off, s);
+    mbar_wait(bar, 0);
+    for (; poly < poly_end; poly += a.groups) {
+        const size_t off = poly * poly_stride + limb_off;
+        cp_async_wait_all();
         __syncthreads();
         T::phase2(tid, s, s3, P);
         __syncthreads();
         T::phase3(tid, s, s12, P);
         __syncthreads();
-        T::template phase4<K1 == 0>(tid, a.out + off, s, s12, P);
-        __syncthreads();
+        u64 x[16];
+        T::phase4_load(tid, s, x);
+        __syncthreads();                                       // every thread has its inputs: the tile buffer is free
+        const uint32_t next = poly + a.groups;
+        if (next < poly_end) tile_copy_in_async<LB>(tid, a.in + next * poly_stride + limb_off, s);   // overlaps the last 4 stages
+        T::template phase4_compute<K1 == 0>(tid, x, a.out + off, s12, P);
     }
 }
 
