@@ -80,6 +80,8 @@ def load_library() -> C.CDLL:
         "fhe_b200_bfv_decrypt": [_vp, _vp, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_bfv_add": [_vp, _vp, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_bfv_multiply_relin": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp],
+        "fhe_b200_bfv_tensor": [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
+        "fhe_b200_bfv_ks_inner": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_multiply_relin_host": [_vp, _vp, _vp, _vp, _vp, C.c_uint32],
         "fhe_b200_bfv_info": [_vp] + [C.POINTER(C.c_uint32)] * 5 + [u64p],
         "fhe_b200_bfv_plan": [_vp],

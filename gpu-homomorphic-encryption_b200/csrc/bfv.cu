@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(256) dec_add_kernel(u64* __restrict__ x, const
 // ---- multiply ---------------------------------------------------------------------------------------------------------
 // ext: [4][B][A][N] (a0,a1,b0,b1; NTT form) -> d: [3][B][A][N]   d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1
 __global__ void __launch_bounds__(256) tensor_kernel(ulonglong2* __restrict__ d, const ulonglong2* __restrict__ ext,
-                                                     const LimbParams* __restrict__ params, uint32_t logn, uint32_t A, size_t per_comp /* B*A*N/2 */) {
+                                                     const LimbParams* __restrict__ params, uint32_t logn, uint32_t limb_begin, uint32_t A,
+                                                     size_t per_comp /* B*A*N/2 */) {
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < per_comp; v += (size_t)gridDim.x * blockDim.x) {
-        const LimbParams P = params[((2 * v) >> logn) % A];
+        const LimbParams P = params[limb_begin + ((2 * v) >> logn) % A];
         const ulonglong2 a0 = ext[v], a1 = ext[per_comp + v], b0 = ext[2 * per_comp + v], b1 = ext[3 * per_comp + v];
         ulonglong2 r0, r1, r2;
         u64 hi, lo;
@@ -191,12 +192,12 @@ __global__ void __launch_bounds__(256) tensor_kernel(ulonglong2* __restrict__ d,
 // key-switch inner product: acc[c][b][i] = sum_dg dig[dg][b][i] * rlk[dg][c][i]    (W = L+K limbs, NTT form)
 __global__ void __launch_bounds__(256) ks_inner_kernel(ulonglong2* __restrict__ acc, const ulonglong2* __restrict__ dig,
                                                        const ulonglong2* __restrict__ rlk, const LimbParams* __restrict__ params,
-                                                       uint32_t logn, uint32_t W, uint32_t dnum, uint32_t batch) {
+                                                       uint32_t logn, uint32_t limb_begin, uint32_t W, uint32_t dnum, uint32_t batch) {
     const size_t wn = ((size_t)W << logn) / 2;              // vectors per polynomial
     const size_t per = wn * batch;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < per; v += (size_t)gridDim.x * blockDim.x) {
         const size_t r = v % wn;
-        const LimbParams P = params[(2 * r) >> logn];
+        const LimbParams P = params[limb_begin + ((2 * r) >> logn)];
         u64 h0x = 0, l0x = 0, h0y = 0, l0y = 0, h1x = 0, l1x = 0, h1y = 0, l1y = 0;
         for (uint32_t dg = 0; dg < dnum; dg++) {
             const ulonglong2 x = dig[dg * per + v];
@@ -494,7 +495,7 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     STEP(launch_ntt(c->plan, ext, ext, 4 * B, 0, A, false, st));
     if (!rc) {
         const size_t per = B * an / 2;
-        tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, A, per);
+        tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per);
         count_launch();
     }
     STEP(launch_ntt(c->plan, d, d, 3 * B, 0, A, true, st));
@@ -516,7 +517,7 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     STEP(launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st));
     if (!rc) {
         const size_t per = B * wn / 2;
-        ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_rlk, prm, c->logn, W, dnum, B);
+        ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_rlk, prm, c->logn, 0, W, dnum, B);
         count_launch();
     }
     STEP(launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st));
@@ -551,5 +552,30 @@ extern "C" int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* c, const uint64_t*
     FHE_TRY(fhe_b200_bfv_multiply_relin(c, buf, buf + ct, d_rlk, buf + 2 * ct, nullptr, batch, st));
     FHE_CUDA(cudaMemcpyAsync(h_out, buf + 2 * ct, ct * 8, cudaMemcpyDeviceToHost, st));
     FHE_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_tensor(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_ext, uint32_t batch, uint32_t limb_begin,
+                                   uint32_t limb_count, void* stream) {
+    FHE_REQUIRE(plan && d_out && d_ext, "bfv_tensor: null argument");
+    FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
+    const size_t per = (size_t)batch * limb_count * plan->n / 2;
+    if (!per) return 0;
+    const size_t w = (per + 255) / 256, cap = (size_t)plan->sm_count * 16;
+    tensor_kernel<<<(uint32_t)(w < cap ? w : cap), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_out, (const ulonglong2*)d_ext, plan->d_params,
+                                                                                 plan->logn, limb_begin, limb_count, per);
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int fhe_b200_bfv_ks_inner(fhe_b200_plan* plan, uint64_t* d_acc, const uint64_t* d_dig, const uint64_t* d_key, uint32_t dnum,
+                                     uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream) {
+    FHE_REQUIRE(plan && d_acc && d_dig && d_key && dnum >= 1, "bfv_ks_inner: bad argument");
+    FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
+    const size_t per = (size_t)batch * limb_count * plan->n / 2;
+    if (!per) return 0;
+    const size_t w = (per + 255) / 256, cap = (size_t)plan->sm_count * 16;
+    ks_inner_kernel<<<(uint32_t)(w < cap ? w : cap), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_acc, (const ulonglong2*)d_dig, (const ulonglong2*)d_key,
+                                                                                   plan->d_params, plan->logn, limb_begin, limb_count, dnum, batch);
+    FHE_LAUNCH_CHECK();
     return 0;
 }

@@ -225,7 +225,13 @@ extern "C" int fhe_b200_lincomb_create_scale(const uint64_t* h_q, uint32_t L, co
                                              const uint64_t* h_targets, uint32_t T, int with_extra, int device,
                                              fhe_b200_lincomb** out) {
     FHE_REQUIRE(h_q && h_targets && out && L && T, "lincomb_create_scale: null/empty argument");
-    FHE_REQUIRE(!with_extra || (h_p && R == T), "lincomb_create_scale: with_extra needs targets == the P basis");
+    FHE_REQUIRE(!with_extra || (h_p && R >= T), "lincomb_create_scale: with_extra needs the targets to be P-basis moduli");
+    if (with_extra)
+        for (uint32_t k = 0; k < T; k++) {
+            bool found = false;
+            for (uint32_t r = 0; r < R; r++) found |= (h_p[r] == h_targets[k]);
+            FHE_REQUIRE(found, "lincomb_create_scale: target %u is not a modulus of the P basis", k);
+        }
     for (uint32_t i = 0; i < L; i++)
         for (uint32_t k = 0; k < T; k++)
             FHE_REQUIRE(h_targets[k] > 1 && host::invmod(h_q[i] % h_targets[k], h_targets[k]) != 0,

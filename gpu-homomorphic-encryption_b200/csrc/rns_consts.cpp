@@ -60,8 +60,11 @@ LincombConsts make_scale_consts(const uint64_t* qs, uint32_t L, const uint64_t* 
         const u64 m = targets[k];
         c.c[k] = 1 % m;
         if (with_extra) {
-            const u64 over = mulmod(basis_product_mod(qs, L, -1, m), basis_product_mod(ps, R, (int)k, m), m);
-            c.lam[k] = mulmod(mulmod(t % m, invmod(over, m), m), basis_product_mod(ps, R, (int)k, m), m);
+            int j = -1;                                   // position of this target inside the P basis
+            for (uint32_t r = 0; r < R; r++) if (ps[r] == m) j = (int)r;
+            if (j < 0) { c.S = 0; return c; }             // caller reports the error
+            const u64 over = mulmod(basis_product_mod(qs, L, -1, m), basis_product_mod(ps, R, j, m), m);
+            c.lam[k] = mulmod(mulmod(t % m, invmod(over, m), m), basis_product_mod(ps, R, j, m), m);
         }
     }
     return c;

@@ -132,7 +132,7 @@ int fhe_b200_lincomb_create_conv(const uint64_t* h_src, uint32_t S, const uint64
                                  fhe_b200_lincomb** out);
 int fhe_b200_lincomb_create_scale(const uint64_t* h_q, uint32_t L, const uint64_t* h_p, uint32_t R, uint64_t t,
                                   const uint64_t* h_targets, uint32_t T, int with_extra, int device,
-                                  fhe_b200_lincomb** out);
+                                  fhe_b200_lincomb** out);   /* with_extra: every target must be one of h_p (any subset, any order) */
 int fhe_b200_lincomb_destroy(fhe_b200_lincomb* lc);
 int fhe_b200_lincomb_apply(fhe_b200_lincomb* lc, uint64_t* d_out, const uint64_t* d_in, const uint64_t* d_extra,
                            uint32_t n_coeffs, uint32_t batch, void* stream);
@@ -174,6 +174,14 @@ int fhe_b200_bfv_add(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b
  * scaled tensor before relinearisation. */
 int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
                                 uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream);
+/* Building blocks of multiply_relin on a limb range, for limb-sharded execution (one rank owns limbs
+ * [limb_begin, limb_begin+limb_count) of every polynomial; NTT form in, NTT form out).
+ *   tensor  : ext [4][batch][limb_count][N] = (a0,a1,b0,b1)  ->  out [3][batch][limb_count][N] = (a0 b0, a0 b1 + a1 b0, a1 b1)
+ *   ks_inner: acc[c][b][i] = sum_d dig[d][b][i] * key[d][c][i],  dig [dnum][batch][limb_count][N], key [dnum][2][limb_count][N] */
+int fhe_b200_bfv_tensor(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_ext, uint32_t batch, uint32_t limb_begin,
+                        uint32_t limb_count, void* stream);
+int fhe_b200_bfv_ks_inner(fhe_b200_plan* plan, uint64_t* d_acc, const uint64_t* d_dig, const uint64_t* d_key, uint32_t dnum,
+                          uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
 /* host-buffer variant of multiply_relin (copies in, computes, copies out; synchronous) */
 int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* ctx, const uint64_t* h_a, const uint64_t* h_b,
                                      const uint64_t* d_rlk, uint64_t* h_out, uint32_t batch);

@@ -113,9 +113,11 @@ orc_lincomb *orc_lc_make_scale(const u64 *qs, u32 L, const u64 *ps, u32 R, u64 t
         u64 m = targets[k];
         lc->c[k] = 1 % m;
         if (with_extra) {
-            /* lambda_k = t * ((Q*P)/p_k)^-1 * (P/p_k) mod p_k ; targets == ps */
-            u64 qp_over = orc_mulmod(prod_mod(qs, L, -1, m), prod_mod(ps, R, (int)k, m), m);
-            lc->lam[k] = orc_mulmod(orc_mulmod(t % m, inv_general(qp_over, m), m), prod_mod(ps, R, (int)k, m), m);
+            /* lambda_k = t * ((Q*P)/p_j)^-1 * (P/p_j) mod p_j, j = position of the target inside ps (targets subset of ps) */
+            int j = -1;
+            for (u32 r = 0; r < R; r++) if (ps[r] == m) j = (int)r;
+            u64 qp_over = orc_mulmod(prod_mod(qs, L, -1, m), prod_mod(ps, R, j, m), m);
+            lc->lam[k] = orc_mulmod(orc_mulmod(t % m, inv_general(qp_over, m), m), prod_mod(ps, R, j, m), m);
         }
     }
     return lc;

@@ -178,3 +178,33 @@ def test_bfv_config4_properties(fhe, oracle):
     assert np.array_equal(to_host(g.decrypt(out2, sk))[0], _exact_product_mod_t(oracle, m12, m2, t, q0))
     s = g.add(ca, cb)
     assert np.array_equal(to_host(g.decrypt(s, sk))[0], (m1 + m2) % np.uint64(t))
+
+
+def test_limb_sharded_building_blocks_single_rank(fhe, oracle):
+    """parallel.LimbShardedBfv with the GPU backend at world=1 must reproduce fhe_b200_bfv_multiply_relin bit for bit
+    (exercises fhe_b200_bfv_tensor / _ks_inner and the subset-target scale constants on the device)."""
+    from fhe_b200.engine import to_device, to_host
+    import fhe_b200.parallel as par
+    p, g, o = _setup(fhe, oracle, "small")
+    n, t = p["n"], p["t"]
+    sk, pk = g.keygen(51, 52); rlk = g.relinkey_gen(53, sk)
+    rng = np.random.default_rng(54)
+    ca = g.encrypt(55, to_device(rng.integers(0, t, (1, n), dtype=np.uint64)), pk)
+    cb = g.encrypt(56, to_device(rng.integers(0, t, (1, n), dtype=np.uint64)), pk)
+    expect = to_host(g.multiply(ca, cb, rlk))[0]
+    be = par.GpuBackend(n, p["primes"], 0)
+    sb = par.LimbShardedBfv(n, p["L"], p["R"], p["K"], p["dnum"], t, p["primes"], be, rank=0, world=1)
+    kq, kp = sb.shard_relin_key(rlk)
+    out = sb.multiply_relin(ca[0].contiguous(), cb[0].contiguous(), kq, kp)
+    assert np.array_equal(to_host(out), expect)
+    # emulate a 2-rank split on one GPU: each "rank" computes its limbs from the same gathered inputs
+    for world in (2, 3):
+        for r in range(world):
+            sh = par.LimbShard(p["L"], p["R"], p["K"], r, world)
+            lc = fhe.LinComb.scale(p["primes"][:p["L"]], p["primes"][p["L"]:], t, p["primes"][p["L"] + sh.rb:p["L"] + sh.rb + sh.rc], True)
+            oc = oracle.LinComb.scale(p["primes"][:p["L"]], p["primes"][p["L"]:], t, p["primes"][p["L"] + sh.rb:p["L"] + sh.rb + sh.rc], True)
+            if sh.rc == 0:
+                continue
+            dq = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in p["primes"][:p["L"]]])
+            dp = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in p["primes"][p["L"] + sh.rb:p["L"] + sh.rb + sh.rc]])
+            assert np.array_equal(to_host(lc.apply(to_device(dq[None]), to_device(dp[None])))[0], oc.apply(dq, extra=dp))
