@@ -107,7 +107,8 @@ def run_reference(args, rank, world):
     oracle.build()
     chain = oracle.prime_chain(LIMBS)
     eng = oracle.RnsNtt(N, chain)
-    threads = oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     sample_polys = max(1, min(POLYS, threads // 8 if threads >= 16 else 1))
     rng = np.random.default_rng(0x5EED0003)
     data = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in chain]) for _ in range(sample_polys)])
@@ -115,8 +116,8 @@ def run_reference(args, rank, world):
     units = 2 * LIMBS * sample_polys
 
     def step():
-        eng.run_inplace(flat, sample_polys, False)
-        eng.run_inplace(flat, sample_polys, True)
+        eng.run_inplace(flat, sample_polys, False, threads)
+        eng.run_inplace(flat, sample_polys, True, threads)
 
     for _ in range(max(1, min(args.warmup, 2))):
         step()
@@ -147,15 +148,15 @@ def cpu_baseline_sample():
     oracle.build()
     chain = oracle.prime_chain(LIMBS)
     eng = oracle.RnsNtt(N, chain)
-    threads = oracle.max_threads()
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rng = np.random.default_rng(0x5EED0003)
     polys = 1
     data = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in chain]) for _ in range(polys)])
     flat = data.reshape(-1)
-    eng.run_inplace(flat, polys, False); eng.run_inplace(flat, polys, True)          # warm
+    eng.run_inplace(flat, polys, False, threads); eng.run_inplace(flat, polys, True, threads)          # warm
     t0 = time.perf_counter(); reps = 0
     while True:
-        eng.run_inplace(flat, polys, False); eng.run_inplace(flat, polys, True)
+        eng.run_inplace(flat, polys, False, threads); eng.run_inplace(flat, polys, True, threads)
         reps += 1
         dt = time.perf_counter() - t0
         if dt > 8.0 or reps >= 200:
@@ -177,6 +178,8 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (NCCL prints its version banner there)
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)

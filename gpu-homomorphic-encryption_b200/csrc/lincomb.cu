@@ -23,10 +23,19 @@ struct LcKernelArgs {
     const u64 *dst_mod, *mu_hi, *mu_lo, *c, *lam, *Mt;
     LcView v;
     uint32_t S, T, logn, k_per_block, use_pre, use_extra;
+    const u64* Mt30;     // [T][SP] matrix entries re-split at bit 30: (m & (2^30-1)) | ((m >> 30) << 32)
     size_t total;        // batch * n
 };
 
-template <int SP>
+// 128-bit accumulator += (64-bit v) << sh, sh < 64
+__device__ __forceinline__ void add_shifted(u64& hi, u64& lo, u64 v, int sh) {
+    add128(hi, lo, sh ? (v >> (64 - sh)) : 0, v << sh);
+}
+
+// SPLIT30 (every modulus < 2^60): operands are split at bit 30, so each of the four partial products is below 2^60 and
+// sixteen of them fit a 64-bit accumulator.  One (source, target) pair then costs exactly four IMAD.WIDE with the add
+// folded into the instruction -- no carry chain, no 64-bit mul.hi emulation (which recomputes the whole product).
+template <int SP, bool SPLIT30>
 __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const uint32_t k0 = blockIdx.y * a.k_per_block;
@@ -34,7 +43,8 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
     // shared: matrix rows [k1-k0][SP], then per-source arrays (5 x SP)
     u64* sMt = sm;
     u64* sSrc = sm + (size_t)a.k_per_block * SP;      // src_mod, pre, pre_s, th_hi, th_lo
-    for (uint32_t t = threadIdx.x; t < (k1 - k0) * SP; t += blockDim.x) sMt[t] = a.Mt[(size_t)k0 * SP + t];
+    const u64* gMt = SPLIT30 ? a.Mt30 : a.Mt;
+    for (uint32_t t = threadIdx.x; t < (k1 - k0) * SP; t += blockDim.x) sMt[t] = gMt[(size_t)k0 * SP + t];
     for (uint32_t t = threadIdx.x; t < (uint32_t)SP; t += blockDim.x) {
         sSrc[t] = a.src_mod[t]; sSrc[SP + t] = a.pre[t]; sSrc[2 * SP + t] = a.pre_s[t];
         sSrc[3 * SP + t] = a.th_hi[t]; sSrc[4 * SP + t] = a.th_lo[t];
@@ -56,12 +66,13 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
             x = inb[(size_t)a.v.src_idx[i] * nn];
             if (a.use_pre) x = shoup_mul(x, sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
         }
-        z[i] = x;
         u64 ph, pl;
         mul128(x, sSrc[3 * SP + i], ph, pl);
         const u64 lo = mulhi64(x, sSrc[4 * SP + i]);
         add192(f2, f1, f0, ph, pl);
         add192(f2, f1, f0, 0, lo);
+        // SPLIT30: keep the two 30-bit halves side by side in one 64-bit register
+        z[i] = SPLIT30 ? ((x & 0x3fffffffull) | ((x >> 30) << 32)) : x;
     }
     add192(f2, f1, f0, 0, 1ull << 63);
     const u64 I_hi = f2, I_lo = f1;                   // I = (f2:f1), the rounded integer part
@@ -70,9 +81,27 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
         const u64 m = a.dst_mod[k], mh = a.mu_hi[k], ml = a.mu_lo[k];
         const u64* row = sMt + (size_t)(k - k0) * SP;
         u64 hi = 0, lo = 0;
+        if (SPLIT30) {
+            u64 u0 = 0, u1 = 0, u2 = 0, u3 = 0;
 #pragma unroll
-        for (int i = 0; i < SP; i++) mac128(hi, lo, z[i], row[i]);
-        mac128(hi, lo, barrett128(I_hi, I_lo, m, mh, ml), a.c[k]);
+            for (int i = 0; i < SP; i++) {
+                const u64 mw = row[i];
+                const u32 z0 = (u32)z[i], z1 = (u32)(z[i] >> 32), m0 = (u32)mw, m1 = (u32)(mw >> 32);
+                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u0) : "r"(z0), "r"(m0));
+                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u1) : "r"(z0), "r"(m1));
+                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u2) : "r"(z1), "r"(m0));
+                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u3) : "r"(z1), "r"(m1));
+                if ((i & 15) == 15 || i == SP - 1) {           // sixteen terms below 2^60 each: flush before overflow
+                    add128(hi, lo, 0, u0); add_shifted(hi, lo, u1, 30); add_shifted(hi, lo, u2, 30); add_shifted(hi, lo, u3, 60);
+                    u0 = u1 = u2 = u3 = 0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SP; i++) mac128(hi, lo, z[i], row[i]);
+        }
+        const u64 Ik = (I_hi == 0 && I_lo < m) ? I_lo : barrett128(I_hi, I_lo, m, mh, ml);
+        mac128(hi, lo, Ik, a.c[k]);
         if (a.use_extra) mac128(hi, lo, a.v.extra[(size_t)b * a.v.extra_stride + (size_t)a.v.extra_idx[k] * nn + j], a.lam[k]);
         u64 r = barrett128(hi, lo, m, mh, ml);
         if (a.v.sub) {
@@ -95,9 +124,14 @@ static uint32_t pad_sources(uint32_t S) {
 }
 
 template <int SP>
-static int launch_sp(const LcKernelArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-    if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lincomb_kernel<SP><<<grid, 256, smem, st>>>(a);
+static int launch_sp(const LcKernelArgs& a, dim3 grid, size_t smem, bool split30, cudaStream_t st) {
+    if (split30) {
+        if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lincomb_kernel<SP, true><<<grid, 256, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lincomb_kernel<SP, false><<<grid, 256, smem, st>>>(a);
+    }
     FHE_LAUNCH_CHECK();
     return 0;
 }
@@ -109,7 +143,7 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     if (!batch) return 0;
     LcKernelArgs a;
     a.src_mod = lc->src_mod; a.pre = lc->pre; a.pre_s = lc->pre_s; a.th_hi = lc->th_hi; a.th_lo = lc->th_lo;
-    a.dst_mod = lc->dst_mod; a.mu_hi = lc->mu_hi; a.mu_lo = lc->mu_lo; a.c = lc->c; a.lam = lc->lam; a.Mt = lc->Mt;
+    a.dst_mod = lc->dst_mod; a.mu_hi = lc->mu_hi; a.mu_lo = lc->mu_lo; a.c = lc->c; a.lam = lc->lam; a.Mt = lc->Mt; a.Mt30 = lc->Mt30;
     a.v = view;
     if (!a.v.src_idx) a.v.src_idx = lc->id_src;
     if (!a.v.dst_idx) a.v.dst_idx = lc->id_dst;
@@ -134,7 +168,7 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     const size_t smem = ((size_t)a.k_per_block * lc->SP + 5 * lc->SP) * sizeof(u64);
     FHE_REQUIRE(smem <= 200 * 1024, "lincomb: constant block too large for shared memory");
     switch (lc->SP) {
-#define LC_CASE(N_) case N_: return launch_sp<N_>(a, grid, smem, st);
+#define LC_CASE(N_) case N_: return launch_sp<N_>(a, grid, smem, lc->split30, st);
         LC_CASE(1) LC_CASE(2) LC_CASE(3) LC_CASE(4) LC_CASE(5) LC_CASE(6) LC_CASE(7) LC_CASE(8) LC_CASE(12) LC_CASE(16)
         LC_CASE(20) LC_CASE(24) LC_CASE(25) LC_CASE(28) LC_CASE(32) LC_CASE(40) LC_CASE(48) LC_CASE(56) LC_CASE(62)
 #undef LC_CASE
@@ -150,20 +184,24 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
     FHE_REQUIRE(SP != 0, "lincomb: at most 62 source moduli are supported (got %u)", h.S);
     for (uint32_t i = 0; i < h.S; i++) FHE_REQUIRE(h.src_mod[i] > 1 && (h.src_mod[i] >> 61) == 0, "lincomb: source modulus %u out of range", i);
     for (uint32_t k = 0; k < h.T; k++) FHE_REQUIRE(h.dst_mod[k] > 1 && (h.dst_mod[k] >> 61) == 0, "lincomb: target modulus %u out of range", k);
+    bool split30 = getenv("FHE_B200_NO_SPLIT30") == nullptr;
+    for (uint32_t i = 0; i < h.S; i++) split30 = split30 && (h.src_mod[i] >> 60) == 0;
+    for (uint32_t k = 0; k < h.T; k++) split30 = split30 && (h.dst_mod[k] >> 60) == 0;
     FHE_CUDA(cudaSetDevice(device));
     auto* lc = new fhe_b200_lincomb();
-    lc->device = device; lc->S = h.S; lc->T = h.T; lc->SP = SP; lc->use_pre = h.use_pre; lc->use_extra = h.use_extra; lc->h = h;
+    lc->device = device; lc->S = h.S; lc->T = h.T; lc->SP = SP; lc->use_pre = h.use_pre; lc->use_extra = h.use_extra; lc->h = h; lc->split30 = split30;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) lc->sm_count = prop.multiProcessorCount;
     const uint32_t T = h.T, S = h.S;
     // blob layout (u64 units): 5 x SP source arrays | 5 x T target arrays | Mt [T][SP] | id_src (u32 x SP) | id_dst (u32 x T)
-    const size_t n64 = 5 * (size_t)SP + 5 * (size_t)T + (size_t)T * SP + (SP + 1) / 2 + (T + 1) / 2 + 2;
+    const size_t n64 = 5 * (size_t)SP + 5 * (size_t)T + 2 * (size_t)T * SP + (SP + 1) / 2 + (T + 1) / 2 + 2;
     std::vector<uint64_t> blob(n64, 0);
     uint64_t* p = blob.data();
     uint64_t* src_mod = p; p += SP; uint64_t* pre = p; p += SP; uint64_t* pre_s = p; p += SP;
     uint64_t* th_hi = p; p += SP; uint64_t* th_lo = p; p += SP;
     uint64_t* dst_mod = p; p += T; uint64_t* mu_hi = p; p += T; uint64_t* mu_lo = p; p += T; uint64_t* cc = p; p += T; uint64_t* lam = p; p += T;
     uint64_t* Mt = p; p += (size_t)T * SP;
+    uint64_t* Mt30 = p; p += (size_t)T * SP;
     uint32_t* id_src = reinterpret_cast<uint32_t*>(p); p += (SP + 1) / 2;
     uint32_t* id_dst = reinterpret_cast<uint32_t*>(p);
     for (uint32_t i = 0; i < SP; i++) {
@@ -175,7 +213,11 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
         dst_mod[k] = h.dst_mod[k];
         host::frac128(1, h.dst_mod[k], mu_hi[k], mu_lo[k]);
         cc[k] = h.c[k]; lam[k] = h.lam[k]; id_dst[k] = k;
-        for (uint32_t i = 0; i < S; i++) Mt[(size_t)k * SP + i] = h.M[(size_t)i * T + k];
+        for (uint32_t i = 0; i < S; i++) {
+            const uint64_t mv = h.M[(size_t)i * T + k];
+            Mt[(size_t)k * SP + i] = mv;
+            Mt30[(size_t)k * SP + i] = (mv & 0x3fffffffull) | ((mv >> 30) << 32);
+        }
     }
     cudaError_t e = cudaMalloc(&lc->d_blob, n64 * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemcpy(lc->d_blob, blob.data(), n64 * sizeof(uint64_t), cudaMemcpyHostToDevice);
@@ -184,6 +226,7 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
     lc->src_mod = d; d += SP; lc->pre = d; d += SP; lc->pre_s = d; d += SP; lc->th_hi = d; d += SP; lc->th_lo = d; d += SP;
     lc->dst_mod = d; d += T; lc->mu_hi = d; d += T; lc->mu_lo = d; d += T; lc->c = d; d += T; lc->lam = d; d += T;
     lc->Mt = d; d += (size_t)T * SP;
+    lc->Mt30 = d; d += (size_t)T * SP;
     lc->id_src = reinterpret_cast<const uint32_t*>(d); d += (SP + 1) / 2;
     lc->id_dst = reinterpret_cast<const uint32_t*>(d);
     *out = lc;

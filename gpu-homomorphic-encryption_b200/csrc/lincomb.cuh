@@ -13,6 +13,8 @@ struct fhe_b200_lincomb {
     const uint64_t *src_mod, *pre, *pre_s, *th_hi, *th_lo;     // [SP]
     const uint64_t *dst_mod, *mu_hi, *mu_lo, *c, *lam;          // [T]
     const uint64_t* Mt;                                         // [T][SP]
+    const uint64_t* Mt30;                                       // [T][SP], entries re-split at bit 30 (SPLIT30 path)
+    bool split30 = false;                                       // every modulus below 2^60
     const uint32_t *id_src, *id_dst;                            // identity limb maps [SP], [T]
     int sm_count = 148;
 };
