@@ -35,8 +35,9 @@ struct fhe_b200_bfv {
     std::vector<const uint32_t*> d_idx_grp, d_idx_tgt;   // per digit: sources [alpha], targets [L+K-alpha]
     // workspaces, grown on demand and kept (a context is single-threaded by contract, see fhe_b200.h)
     uint64_t* d_ws = nullptr; size_t ws_words = 0;       // multiply / encrypt / decrypt scratch
-    uint64_t* d_io = nullptr; size_t io_words = 0;       // device staging of the host-buffer entry point
-    cudaStream_t io_stream = nullptr;
+    uint64_t* d_io[2] = {nullptr, nullptr}; size_t io_words[2] = {0, 0};   // device staging of the host-buffer entry point
+    cudaStream_t io_stream[2] = {nullptr, nullptr};
+    cudaEvent_t io_done[2] = {nullptr, nullptr};
 };
 
 namespace fhe_b200 {
@@ -152,6 +153,47 @@ __global__ void __launch_bounds__(256) enc_finish_kernel(u64* __restrict__ ct, c
     }
 }
 
+// ---- plaintext operands ------------------------------------------------------------------------------------------------
+// out[b][0][i] = ct[b][0][i] +- delta_i * m[b],  out[b][1][i] = ct[b][1][i]
+__global__ void __launch_bounds__(256) add_plain_kernel(u64* __restrict__ out, const u64* __restrict__ ct, const u64* __restrict__ pt,
+                                                        const LimbParams* __restrict__ params, const u64* __restrict__ delta,
+                                                        uint32_t logn, uint32_t L, size_t total /* B*2*L*N */, int subtract) {
+    const uint32_t n = 1u << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g & (n - 1));
+        const size_t pl = g >> logn;                  // (b*2 + comp)*L + i
+        const uint32_t i = (uint32_t)(pl % L);
+        const size_t bc = pl / L;
+        u64 v = ct[g];
+        if ((bc & 1) == 0) {
+            const LimbParams P = params[i];
+            const u64 dm = mul_mod(delta[i], barrett128(0, pt[(bc >> 1) * n + j], P.q, P.mu_hi, P.mu_lo), P);
+            v = subtract ? sub_mod(v, dm, P.q) : add_mod(v, dm, P.q);
+        }
+        out[g] = v;
+    }
+}
+// lifted plaintext: out[b][i][j] = pt[b][j] mod q_i
+__global__ void __launch_bounds__(256) lift_plain_kernel(u64* __restrict__ out, const u64* __restrict__ pt, const LimbParams* __restrict__ params,
+                                                         uint32_t logn, uint32_t L, size_t total /* B*L*N */) {
+    const uint32_t n = 1u << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g & (n - 1));
+        const size_t pl = g >> logn;
+        const LimbParams P = params[pl % L];
+        out[g] = barrett128(0, pt[(pl / L) * n + j], P.q, P.mu_hi, P.mu_lo);
+    }
+}
+// ct[b][c][i] *= m[b][i]  (NTT form)
+__global__ void __launch_bounds__(256) mul_plain_kernel(u64* __restrict__ ct, const u64* __restrict__ m, const LimbParams* __restrict__ params,
+                                                        uint32_t logn, uint32_t L, size_t total /* B*2*L*N */) {
+    const size_t ln = (size_t)L << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = g / (2 * ln), r = g % ln;
+        ct[g] = mul_mod(ct[g], m[b * ln + r], params[r >> logn]);
+    }
+}
+
 // ---- decrypt ----------------------------------------------------------------------------------------------------------
 // x[b][i] = NTT(c1)[b][i] * s[i]
 __global__ void __launch_bounds__(256) dec_mul_kernel(u64* __restrict__ x, const u64* __restrict__ s, const LimbParams* __restrict__ params,
@@ -262,8 +304,12 @@ extern "C" int fhe_b200_bfv_destroy(fhe_b200_bfv* c) {
     fhe_b200_lincomb_destroy(c->moddown); fhe_b200_lincomb_destroy(c->dec);
     for (auto* m : c->modup) fhe_b200_lincomb_destroy(m);
     cudaFree(c->d_consts); cudaFree(c->d_idx);
-    cudaFree(c->d_ws); cudaFree(c->d_io);
-    if (c->io_stream) cudaStreamDestroy(c->io_stream);
+    cudaFree(c->d_ws);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_io[i]);
+        if (c->io_stream[i]) cudaStreamDestroy(c->io_stream[i]);
+        if (c->io_done[i]) cudaEventDestroy(c->io_done[i]);
+    }
     fhe_b200_plan_destroy(c->plan);
     delete c;
     return 0;
@@ -464,6 +510,37 @@ extern "C" int fhe_b200_bfv_add(fhe_b200_bfv* c, const uint64_t* d_a, const uint
     return launch_elementwise(c->plan, EW_ADD, d_out, d_a, d_b, nullptr, 2 * batch, 0, c->L, (cudaStream_t)stream);
 }
 
+extern "C" int fhe_b200_bfv_sub(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_a && d_b && d_out, "bfv_sub: null argument");
+    return launch_elementwise(c->plan, EW_SUB, d_out, d_a, d_b, nullptr, 2 * batch, 0, c->L, (cudaStream_t)stream);
+}
+extern "C" int fhe_b200_bfv_add_plain(fhe_b200_bfv* c, const uint64_t* d_ct, const uint64_t* d_pt, uint64_t* d_out, uint32_t batch,
+                                      int subtract, void* stream) {
+    FHE_REQUIRE(c && d_ct && d_pt && d_out, "bfv_add_plain: null argument");
+    if (!batch) return 0;
+    const size_t total = (size_t)batch * 2 * c->L * c->n;
+    add_plain_kernel<<<grid_for(c, total), 256, 0, (cudaStream_t)stream>>>(d_out, d_ct, d_pt, c->plan->d_params, c->d_delta, c->logn, c->L, total, subtract);
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* c, const uint64_t* d_ct, const uint64_t* d_pt, uint64_t* d_out, uint32_t batch,
+                                           void* stream) {
+    FHE_REQUIRE(c && d_ct && d_pt && d_out, "bfv_multiply_plain: null argument");
+    if (!batch) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const size_t ln = (size_t)c->L * c->n;
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
+    uint64_t* m = c->d_ws;
+    lift_plain_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(m, d_pt, c->plan->d_params, c->logn, c->L, batch * ln);
+    FHE_LAUNCH_CHECK();
+    FHE_TRY(launch_ntt(c->plan, m, m, batch, 0, c->L, false, st));
+    FHE_TRY(launch_ntt(c->plan, d_out, d_ct, 2 * batch, 0, c->L, false, st));
+    mul_plain_kernel<<<grid_for(c, 2 * batch * ln), 256, 0, st>>>(d_out, m, c->plan->d_params, c->logn, c->L, 2 * batch * ln);
+    FHE_LAUNCH_CHECK();
+    return launch_ntt(c->plan, d_out, d_out, 2 * batch, 0, c->L, true, st);
+}
+
 // ---- multiply + relinearize --------------------------------------------------------------------------------------------------
 extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
                                            uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream) {
@@ -537,21 +614,38 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     return 0;
 }
 
+// Host-buffer entry point.  The ciphertext pairs are processed one at a time on two alternating streams, each with its
+// own device staging buffers: the upload of pair i+1 and the download of pair i-1 overlap the multiply of pair i (PCIe is
+// full duplex).  The multiplies themselves are serialised through an event because they share the context workspace.
 extern "C" int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* c, const uint64_t* h_a, const uint64_t* h_b, const uint64_t* d_rlk,
                                                 uint64_t* h_out, uint32_t batch) {
     FHE_REQUIRE(c && h_a && h_b && d_rlk && h_out, "bfv_multiply_relin_host: null argument");
     if (!batch) return 0;
     FHE_CUDA(cudaSetDevice(c->device));
-    if (!c->io_stream) FHE_CUDA(cudaStreamCreateWithFlags(&c->io_stream, cudaStreamNonBlocking));
-    cudaStream_t st = c->io_stream;
-    const size_t ct = 2 * (size_t)c->L * c->n * batch;
-    FHE_TRY(ensure_words(&c->d_io, &c->io_words, 3 * ct));
-    uint64_t* buf = c->d_io;
-    FHE_CUDA(cudaMemcpyAsync(buf, h_a, ct * 8, cudaMemcpyHostToDevice, st));
-    FHE_CUDA(cudaMemcpyAsync(buf + ct, h_b, ct * 8, cudaMemcpyHostToDevice, st));
-    FHE_TRY(fhe_b200_bfv_multiply_relin(c, buf, buf + ct, d_rlk, buf + 2 * ct, nullptr, batch, st));
-    FHE_CUDA(cudaMemcpyAsync(h_out, buf + 2 * ct, ct * 8, cudaMemcpyDeviceToHost, st));
-    FHE_CUDA(cudaStreamSynchronize(st));
+    const size_t ct = 2 * (size_t)c->L * c->n;            // words per ciphertext
+    for (int i = 0; i < 2; i++) {
+        if (!c->io_stream[i]) FHE_CUDA(cudaStreamCreateWithFlags(&c->io_stream[i], cudaStreamNonBlocking));
+        if (!c->io_done[i]) FHE_CUDA(cudaEventCreateWithFlags(&c->io_done[i], cudaEventDisableTiming));
+        FHE_TRY(ensure_words(&c->d_io[i], &c->io_words[i], 3 * ct));
+    }
+    // size the shared workspace up front so that no (synchronising) reallocation happens inside the pipeline
+    {
+        const size_t an = (size_t)(c->L + c->R) * c->n, wn = (size_t)(c->L + c->K) * c->n, rn = (size_t)c->R * c->n, ln = (size_t)c->L * c->n;
+        FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, 7 * an + 3 * rn + 3 * ln + ((size_t)c->dnum + 2) * wn));
+    }
+    for (uint32_t i = 0; i < batch; i++) {
+        const int s = (int)(i & 1);
+        cudaStream_t st = c->io_stream[s];
+        uint64_t* buf = c->d_io[s];
+        FHE_CUDA(cudaMemcpyAsync(buf, h_a + i * ct, ct * 8, cudaMemcpyHostToDevice, st));
+        FHE_CUDA(cudaMemcpyAsync(buf + ct, h_b + i * ct, ct * 8, cudaMemcpyHostToDevice, st));
+        if (i > 0) FHE_CUDA(cudaStreamWaitEvent(st, c->io_done[s ^ 1], 0));      // previous multiply owns the workspace
+        FHE_TRY(fhe_b200_bfv_multiply_relin(c, buf, buf + ct, d_rlk, buf + 2 * ct, nullptr, 1, st));
+        FHE_CUDA(cudaEventRecord(c->io_done[s], st));
+        FHE_CUDA(cudaMemcpyAsync(h_out + i * ct, buf + 2 * ct, ct * 8, cudaMemcpyDeviceToHost, st));
+    }
+    FHE_CUDA(cudaStreamSynchronize(c->io_stream[0]));
+    FHE_CUDA(cudaStreamSynchronize(c->io_stream[1]));
     return 0;
 }
 

@@ -375,6 +375,41 @@ class BfvContext:
         check(self.lib.fhe_b200_bfv_add(self.h, _ptr(a), _ptr(b), _ptr(out), a.numel() // (2 * self.L * self.n), _stream()))
         return out
 
+    def sub(self, a, b):
+        out = torch.empty_like(a)
+        check(self.lib.fhe_b200_bfv_sub(self.h, _ptr(a), _ptr(b), _ptr(out), a.numel() // (2 * self.L * self.n), _stream()))
+        return out
+
+    def add_plain(self, ct, pt, subtract=False):
+        out = torch.empty_like(ct)
+        check(self.lib.fhe_b200_bfv_add_plain(self.h, _ptr(ct), _ptr(pt), _ptr(out), ct.numel() // (2 * self.L * self.n),
+                                              int(subtract), _stream()))
+        return out
+
+    def multiply_plain(self, ct, pt):
+        out = torch.empty_like(ct)
+        check(self.lib.fhe_b200_bfv_multiply_plain(self.h, _ptr(ct), _ptr(pt), _ptr(out), ct.numel() // (2 * self.L * self.n),
+                                                   _stream()))
+        return out
+
+    # SIMD slot encoding (fhe::BatchEncoder, include/fhe.cuh:151-166): slot i is the value of the plaintext polynomial at
+    # the evaluation point the engine's NTT puts at position i; needs t = 1 (mod 2N)
+    def _slot_plan(self):
+        if getattr(self, "_tplan", None) is None:
+            self._tplan = Plan(self.n, [self.t], self.dev.index or 0)
+        return self._tplan
+
+    def batch_encode(self, values) -> torch.Tensor:
+        v = np.zeros(self.n, dtype=np.uint64)
+        a = np.asarray(values, dtype=np.uint64)[: self.n]
+        v[: a.size] = a % np.uint64(self.t)
+        d = to_device(v.reshape(1, 1, self.n), self.dev)
+        return self._slot_plan().inverse(d).view(self.n)
+
+    def batch_decode(self, pt: torch.Tensor) -> np.ndarray:
+        d = pt.clone().view(-1, 1, self.n)
+        return to_host(self._slot_plan().forward(d)).reshape(-1, self.n)
+
     def multiply(self, a, b, rlk, want_scaled=False, out=None):
         batch = a.numel() // (2 * self.L * self.n)
         out = torch.empty_like(a) if out is None else out

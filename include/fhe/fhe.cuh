@@ -166,6 +166,17 @@ public:
         out.level = std::max(a.level, b.level);
         replace(result, out);
     }
+    // declared-only in the reference (include/fhe.cuh:98-104): sub, add_plain, sub_plain, multiply_plain
+    void sub(Ciphertext& result, const Ciphertext& a, const Ciphertext& b) {
+        Ciphertext out; new_ciphertext(out);
+        detail::check(fhe_b200_bfv_sub(ctx_, a.components[0]->rns, b.components[0]->rns, out.components[0]->rns, 1, stream_), "sub");
+        out.noise_budget = std::min(a.noise_budget, b.noise_budget); out.level = std::max(a.level, b.level);
+        replace(result, out);
+    }
+    void add_plain(Ciphertext& result, const Ciphertext& ct, const Plaintext& pt) { plain_op(result, ct, pt, 0); }
+    void sub_plain(Ciphertext& result, const Ciphertext& ct, const Plaintext& pt) { plain_op(result, ct, pt, 1); }
+    void multiply_plain(Ciphertext& result, const Ciphertext& ct, const Plaintext& pt) { plain_op(result, ct, pt, 2); }
+
     // multiply() already relinearises (the tensor product never leaves the engine); kept for source compatibility
     void relinearize(Ciphertext& ct, const RelinKeys&) { if (ct.components.size() > 2) throw std::runtime_error("relinearize: 3-component input is produced only inside multiply()"); }
 
@@ -185,6 +196,16 @@ public:
     }
 
 private:
+    void plain_op(Ciphertext& result, const Ciphertext& ct, const Plaintext& pt, int op) {
+        Ciphertext out; new_ciphertext(out);
+        scratch_.reserve(params_.n);
+        detail::check(fhe_b200_unpack_u256(scratch_.p, pt.poly->coeffs, params_.n, stream_), "plain operand");
+        detail::check(op == 2 ? fhe_b200_bfv_multiply_plain(ctx_, ct.components[0]->rns, scratch_.p, out.components[0]->rns, 1, stream_)
+                              : fhe_b200_bfv_add_plain(ctx_, ct.components[0]->rns, scratch_.p, out.components[0]->rns, 1, op, stream_),
+                      "plain operand");
+        out.noise_budget = ct.noise_budget; out.level = ct.level;
+        replace(result, out);
+    }
     void new_ciphertext(Ciphertext& ct) {
         const uint32_t n = params_.n, L = params_.L;
         Polynomial* c0 = new Polynomial(n, 2 * L);                               // owns [2][L][N]
@@ -214,6 +235,46 @@ private:
     int device_ = 0;
     uint64_t seed_ = 0;
     detail::DeviceBuf scratch_;
+};
+
+// SIMD slot encoding (reference: include/fhe.cuh:151-166; src/fhe.cu:267-279 is a stub that forwards to coefficient
+// encoding, which is why the reference's printed slot-wise expectations never come out).  Slot i is the value of the
+// plaintext polynomial at the evaluation point the engine's negacyclic NTT modulo t leaves at position i, so ciphertext
+// add / multiply act slot-wise.  Needs t = 1 (mod 2N): t = 65537 supports N <= 32768.
+class BatchEncoder {
+public:
+    explicit BatchEncoder(const FHEContext& context) : context_(context), slot_count_(context.params().n / 2),
+                                                        ntt_(context.params().n, context.params().t) {}
+    // up to n values are accepted (slot_count() keeps the reference's n/2)
+    void encode(Plaintext& pt, const std::vector<uint64_t>& values) {
+        const uint32_t n = context_.params().n;
+        std::vector<uint64_t> h(n, 0);
+        for (size_t i = 0; i < std::min(values.size(), (size_t)n); i++) h[i] = values[i] % 65537;
+        buf_.reserve(n);
+        detail::check_cuda(cudaMemcpyAsync(buf_.p, h.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ntt_.stream()), "encode");
+        ntt_.inverse_u64(buf_.p);
+        pt.poly = new Polynomial(n, context_.params().t);
+        pt.is_ntt_form = false;
+        detail::check(fhe_b200_pack_u256(pt.poly->coeffs, buf_.p, n, ntt_.stream()), "encode");
+        detail::check_cuda(cudaStreamSynchronize(ntt_.stream()), "encode");
+    }
+    void decode(std::vector<uint64_t>& values, const Plaintext& pt) {
+        const uint32_t n = context_.params().n;
+        buf_.reserve(n);
+        detail::check_cuda(cudaStreamSynchronize(context_.stream()), "decode");
+        detail::check(fhe_b200_unpack_u256(buf_.p, pt.poly->coeffs, n, ntt_.stream()), "decode");
+        ntt_.forward_u64(buf_.p);
+        values.assign(n, 0);
+        detail::check_cuda(cudaMemcpyAsync(values.data(), buf_.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ntt_.stream()), "decode");
+        detail::check_cuda(cudaStreamSynchronize(ntt_.stream()), "decode");
+    }
+    uint32_t slot_count() const { return slot_count_; }
+
+private:
+    const FHEContext& context_;
+    uint32_t slot_count_;
+    NTTEngine ntt_;
+    detail::DeviceBuf buf_;
 };
 
 }  // namespace fhe

@@ -170,6 +170,15 @@ int fhe_b200_bfv_decrypt(fhe_b200_bfv* ctx, const uint64_t* d_ct, const uint64_t
 /* FHEContext::add (src/fhe.cu:187-197) */
 int fhe_b200_bfv_add(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint32_t batch,
                      void* stream);
+/* FHEContext::sub, add_plain, sub_plain, multiply_plain (declared include/fhe.cuh:98-104, undefined in the reference).
+ * Plaintexts are [batch][N] coefficients mod t.  add/sub_plain: c0 +- Delta*m.  multiply_plain: (c0*m, c1*m) in R_Q with m
+ * lifted from [0,t). */
+int fhe_b200_bfv_sub(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint32_t batch,
+                     void* stream);
+int fhe_b200_bfv_add_plain(fhe_b200_bfv* ctx, const uint64_t* d_ct, const uint64_t* d_pt, uint64_t* d_out, uint32_t batch,
+                           int subtract, void* stream);
+int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* ctx, const uint64_t* d_ct, const uint64_t* d_pt, uint64_t* d_out,
+                                uint32_t batch, void* stream);
 /* FHEContext::multiply + relinearize (src/fhe.cu:199-235).  d_scaled (optional, [batch][3][L][N]) receives the
  * scaled tensor before relinearisation. */
 int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,

@@ -359,6 +359,32 @@ class Bfv:
         lib().orc_bfv_add(C.c_void_p(self.h), _p(_u64(a).reshape(-1)), _p(_u64(b).reshape(-1)), _p(out.reshape(-1)))
         return out
 
+    def sub(self, a, b):
+        out = np.zeros((2, self.L, self.n), np.uint64)
+        lib().orc_bfv_sub(C.c_void_p(self.h), _p(_u64(a).reshape(-1)), _p(_u64(b).reshape(-1)), _p(out.reshape(-1)))
+        return out
+
+    def add_plain(self, ct, pt, subtract=False):
+        out = np.zeros((2, self.L, self.n), np.uint64)
+        lib().orc_bfv_add_plain(C.c_void_p(self.h), _p(_u64(ct).reshape(-1)), _p(_u64(pt)), _p(out.reshape(-1)), int(subtract))
+        return out
+
+    def multiply_plain(self, ct, pt):
+        out = np.zeros((2, self.L, self.n), np.uint64)
+        lib().orc_bfv_multiply_plain(C.c_void_p(self.h), _p(_u64(ct).reshape(-1)), _p(_u64(pt)), _p(out.reshape(-1)))
+        return out
+
+    # SIMD slot encoding (fhe::BatchEncoder): slot i = value of the plaintext polynomial at the evaluation point the
+    # negacyclic NTT modulo t leaves at position i (bit-reversed order); needs t = 1 (mod 2N)
+    def batch_encode(self, values):
+        v = np.zeros(self.n, np.uint64)
+        a = np.asarray(values, dtype=np.uint64)[: self.n]
+        v[: a.size] = a % np.uint64(self.t)
+        return ntt_inverse(v, self.t)
+
+    def batch_decode(self, pt):
+        return ntt_forward(pt, self.t)
+
     def multiply_relin(self, a, b, rlk, want_scaled=False):
         out = np.zeros((2, self.L, self.n), np.uint64)
         sc = np.zeros((3, self.L, self.n), np.uint64) if want_scaled else None

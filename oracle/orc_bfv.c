@@ -336,3 +336,39 @@ void orc_bfv_multiply_relin(const orc_bfv *c, const u64 *cta, const u64 *ctb, co
     }
     free(ext); free(d); free(sc); free(tmpR); free(acc); free(dig); free(conv);
 }
+
+/* ---------- plaintext operands and subtraction (declared only in the reference: include/fhe.cuh:98-104) -------------- */
+void orc_bfv_sub(const orc_bfv *c, const u64 *a, const u64 *b, u64 *out) {
+    u32 n = c->n, L = c->L;
+    for (u32 p = 0; p < 2 * L; p++) { u64 q = c->primes[p % L];
+        for (u32 j = 0; j < n; j++) out[(size_t)p * n + j] = orc_submod(a[(size_t)p * n + j], b[(size_t)p * n + j], q); }
+}
+/* c0 +- Delta*m, c1 unchanged */
+void orc_bfv_add_plain(const orc_bfv *c, const u64 *ct, const u64 *pt, u64 *out, int subtract) {
+    u32 n = c->n, L = c->L;
+    memcpy(out, ct, 2 * (size_t)L * n * sizeof(u64));
+    for (u32 i = 0; i < L; i++) { u64 q = c->primes[i];
+        for (u32 j = 0; j < n; j++) {
+            u64 dm = orc_mulmod(c->delta[i], pt[j] % q, q);
+            u64 *o = out + (size_t)i * n + j;
+            *o = subtract ? orc_submod(*o, dm, q) : orc_addmod(*o, dm, q);
+        } }
+}
+/* (c0*m, c1*m) in R_Q, m lifted from [0,t) */
+void orc_bfv_multiply_plain(const orc_bfv *c, const u64 *ct, const u64 *pt, u64 *out) {
+    u32 n = c->n, L = c->L;
+    u64 *m = (u64 *)malloc(n * sizeof(u64));
+    for (u32 i = 0; i < L; i++) {
+        u64 q = c->primes[i];
+        for (u32 j = 0; j < n; j++) m[j] = pt[j] % q;
+        fwd_limb(c, m, i);
+        for (int p = 0; p < 2; p++) {
+            u64 *o = out + ((size_t)p * L + i) * n;
+            memcpy(o, ct + ((size_t)p * L + i) * n, n * sizeof(u64));
+            fwd_limb(c, o, i);
+            for (u32 j = 0; j < n; j++) o[j] = orc_mulmod(o[j], m[j], q);
+            inv_limb(c, o, i);
+        }
+    }
+    free(m);
+}

@@ -123,6 +123,21 @@ static void test_fhe_operations() {              // tests/test_fhe.cu:169-273
     Plaintext pc; ctx.decrypt(pc, ct_mul, sk); std::vector<uint64_t> rc; ctx.decode(rc, pc);
     const uint64_t exp_chain[4] = {75, 450, 1575, 4200};            // (15+60x+150x^2+300x^3+..)(5+10x+15x^2+20x^3) low coefficients
     for (int i = 0; i < 4; i++) REQUIRE(rc[i] == exp_chain[i]);
+    // SIMD slot encoding: the reference's printed expectations (tests/test_fhe.cu:270; examples/homomorphic_operations.cu:148,242)
+    {
+        BatchEncoder enc(ctx);
+        REQUIRE(enc.slot_count() == 2048);
+        Plaintext b1, b2, two; enc.encode(b1, v1); enc.encode(b2, v2); enc.encode(two, std::vector<uint64_t>(4096, 2));
+        Ciphertext e1, e2, prod, sum, diff, scaled; ctx.encrypt(e1, b1, pk); ctx.encrypt(e2, b2, pk);
+        ctx.multiply(prod, e1, e2, rlk); ctx.add_plain(sum, e1, b2); ctx.sub(diff, e1, e2); ctx.multiply_plain(scaled, e1, two);
+        Plaintext pp, ps, pd, pq; ctx.decrypt(pp, prod, sk); ctx.decrypt(ps, sum, sk); ctx.decrypt(pd, diff, sk); ctx.decrypt(pq, scaled, sk);
+        std::vector<uint64_t> rp, rs, rd, rq; enc.decode(rp, pp); enc.decode(rs, ps); enc.decode(rd, pd); enc.decode(rq, pq);
+        const uint64_t exp_slot[4] = {15, 60, 135, 240};
+        for (int i = 0; i < 4; i++) { REQUIRE(rp[i] == exp_slot[i]); REQUIRE(rs[i] == v1[i] + v2[i]); REQUIRE(rd[i] == v1[i] - v2[i]); REQUIRE(rq[i] == 2 * v1[i]); }
+        for (int i = 4; i < 4096; i++) REQUIRE(rp[i] == 0);
+        FHEContext::release(e1); FHEContext::release(e2); FHEContext::release(prod); FHEContext::release(sum); FHEContext::release(diff); FHEContext::release(scaled);
+        FHEContext::release(b1); FHEContext::release(b2); FHEContext::release(two); FHEContext::release(pp); FHEContext::release(ps); FHEContext::release(pd); FHEContext::release(pq);
+    }
     FHEContext::release(ct1); FHEContext::release(ct2); FHEContext::release(ct_add); FHEContext::release(ct_mul);
     FHEContext::release(pt1); FHEContext::release(pt2); FHEContext::release(pa); FHEContext::release(pm); FHEContext::release(p1); FHEContext::release(pc);
     FHEContext::release(rlk); FHEContext::release(pk); FHEContext::release(sk);

@@ -208,3 +208,26 @@ def test_limb_sharded_building_blocks_single_rank(fhe, oracle):
             dq = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in p["primes"][:p["L"]]])
             dp = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in p["primes"][p["L"] + sh.rb:p["L"] + sh.rb + sh.rc]])
             assert np.array_equal(to_host(lc.apply(to_device(dq[None]), to_device(dp[None])))[0], oc.apply(dq, extra=dp))
+
+
+def test_plain_ops_and_batch_encoding_vs_oracle(fhe, oracle):
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, "small")
+    n, t = p["n"], p["t"]
+    sk, pk = g.keygen(61, 62); rlk = g.relinkey_gen(63, sk)
+    _, osk = o.secret_keygen(61); opk = o.public_keygen(62, osk)
+    rng = np.random.default_rng(64)
+    m1 = rng.integers(0, t, (1, n), dtype=np.uint64); m2 = rng.integers(0, t, (1, n), dtype=np.uint64)
+    c1 = g.encrypt(65, to_device(m1), pk); c2 = g.encrypt(66, to_device(m2), pk)
+    h1, h2 = to_host(c1)[0], to_host(c2)[0]
+    assert np.array_equal(to_host(g.sub(c1, c2))[0], o.sub(h1, h2))
+    assert np.array_equal(to_host(g.add_plain(c1, to_device(m2)))[0], o.add_plain(h1, m2[0]))
+    assert np.array_equal(to_host(g.add_plain(c1, to_device(m2), subtract=True))[0], o.add_plain(h1, m2[0], subtract=True))
+    mp = g.multiply_plain(c1, to_device(m2))
+    assert np.array_equal(to_host(mp)[0], o.multiply_plain(h1, m2[0]))
+    assert np.array_equal(to_host(g.decrypt(mp, sk))[0], oracle.schoolbook_negacyclic(m1[0], m2[0], t))
+    # slot encoding: the reference's printed slot-wise expectations (tests/test_fhe.cu:270)
+    pa, pb = g.batch_encode([5, 10, 15, 20]), g.batch_encode([3, 6, 9, 12])
+    assert np.array_equal(to_host(pa), o.batch_encode([5, 10, 15, 20]))
+    prod = g.multiply(g.encrypt(67, pa.view(1, n), pk), g.encrypt(68, pb.view(1, n), pk), rlk)
+    assert [int(v) for v in g.batch_decode(g.decrypt(prod, sk))[0, :4]] == [15, 60, 135, 240]

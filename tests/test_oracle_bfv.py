@@ -212,3 +212,28 @@ def test_bfv_reference_style_products(oracle, chain):
     # depth 2
     c2 = ctx.multiply_relin(c, ctx.encrypt(6, ctx.encode([2]), pk), rlk)
     assert [int(v) for v in ctx.decrypt(c2, sk)[:7]] == [30, 120, 300, 600, 750, 720, 480]
+
+
+def test_bfv_plain_ops_and_batch_encoding(oracle, chain):
+    """'next' rows: sub / add_plain / sub_plain / multiply_plain and SIMD slot encoding.  With slot encoding
+    the reference's printed expectations become true: {5,10,15,20} x {3,6,9,12} -> 15 60 135 240 (tests/test_fhe.cu:270),
+    {3,4,5,6} x {2,5,10,3} -> 6 20 50 18 and x pt{2} -> 20 40 60 80 (examples/homomorphic_operations.cu:148,242)."""
+    n, L, R, K, dnum, t = 64, 2, 3, 1, 2, 65537
+    ctx = oracle.Bfv(n, L, R, K, dnum, t, chain[:L + R], hw=16)
+    _, sk = ctx.secret_keygen(1); pk = ctx.public_keygen(2, sk); rlk = ctx.relin_keygen(3, sk)
+    rng = np.random.default_rng(70)
+    m1 = rng.integers(0, t, n, dtype=np.uint64); m2 = rng.integers(0, t, n, dtype=np.uint64)
+    c1 = ctx.encrypt(4, m1, pk); c2 = ctx.encrypt(5, m2, pk)
+    tt = np.uint64(t)
+    assert np.array_equal(ctx.decrypt(ctx.sub(c1, c2), sk), (m1 + tt - m2) % tt)
+    assert np.array_equal(ctx.decrypt(ctx.add_plain(c1, m2), sk), (m1 + m2) % tt)
+    assert np.array_equal(ctx.decrypt(ctx.add_plain(c1, m2, subtract=True), sk), (m1 + tt - m2) % tt)
+    assert np.array_equal(ctx.decrypt(ctx.multiply_plain(c1, m2), sk), oracle.schoolbook_negacyclic(m1, m2, t))
+    # slot encoding
+    e = lambda v: ctx.encrypt(6 + sum(v), ctx.batch_encode(v), pk)
+    d = lambda c: [int(x) for x in ctx.batch_decode(ctx.decrypt(c, sk))[:4]]
+    assert d(e([5, 10, 15, 20])) == [5, 10, 15, 20]
+    assert d(ctx.multiply_relin(e([5, 10, 15, 20]), e([3, 6, 9, 12]), rlk)) == [15, 60, 135, 240]
+    assert d(ctx.multiply_relin(e([3, 4, 5, 6]), e([2, 5, 10, 3]), rlk)) == [6, 20, 50, 18]
+    assert d(ctx.add(e([10, 20, 30, 40]), e([5, 15, 25, 35]))) == [15, 35, 55, 75]
+    assert d(ctx.multiply_plain(e([10, 20, 30, 40]), ctx.batch_encode([2] * n))) == [20, 40, 60, 80]

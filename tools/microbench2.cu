@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 constexpr int ITERS = 2048;
 constexpr int ILP = 8;
@@ -105,11 +106,12 @@ template <class F> static float time_ms(F f) {
     return best;
 }
 
-int main() {
+int main(int argc, char** argv) {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     const int sms = p.multiProcessorCount;
     void* buf; cudaMalloc(&buf, 1 << 20);
-    const int blocks = sms * 8, threads = 256;
+    const int bps = argc > 1 ? atoi(argv[1]) : 8;     // resident 256-thread blocks per SM (occupancy sweep)
+    const int blocks = sms * bps, threads = 256;
     const double ghz = p.clockRate / 1e6;
     auto report = [&](const char* name, float ms, double ops_per_iter) {
         const double ops = (double)blocks * threads * ITERS * ILP * ops_per_iter;
