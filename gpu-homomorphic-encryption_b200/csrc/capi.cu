@@ -104,6 +104,7 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
     p->hb = lazy_headroom(h_moduli, n_limbs);
     p->near60 = all_near60(h_moduli, n_limbs);
     if (getenv("FHE_B200_NO_NEAR60")) p->near60 = false;
+    if (const char* e = getenv("FHE_B200_NTT_FUSED")) p->fused = atoi(e) != 0;
     if (const char* e = getenv("FHE_B200_NTT_CHUNK_MB")) { long mb = atol(e); if (mb > 0) p->chunk_bytes = (size_t)mb << 20; }
     p->h_params.resize(n_limbs);
     std::vector<Twiddle> fwd((size_t)n_limbs * n), inv((size_t)n_limbs * n);
@@ -145,6 +146,7 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
 extern "C" int fhe_b200_plan_destroy(fhe_b200_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
+    release_fused_scratch(p);
     cudaFree(p->d_fwd); cudaFree(p->d_inv); cudaFree(p->d_params);
     cudaFree(p->d_fwd_p12); cudaFree(p->d_fwd_p3); cudaFree(p->d_inv_p12); cudaFree(p->d_inv_p3);
     for (int i = 0; i < 3; i++) { if (p->d_stage[i]) cudaFree(p->d_stage[i]); if (p->hs[i]) cudaStreamDestroy(p->hs[i]); }

@@ -45,6 +45,7 @@ struct fhe_b200_plan {
     uint32_t n = 0, logn = 0, limbs = 0;
     int device = 0;
     int hb = 16;                                   // lazy head-room (16: all q < 2^60, 8: all q < 2^61)
+    bool fused = true;                             // N > 4096: single persistent row+tile kernel (FHE_B200_NTT_FUSED=0: two passes)
     bool near60 = false;                           // every q in [2^60 - 2^55, 2^60): cheap range reduction (near60_reduce)
     std::vector<uint64_t> moduli;
     fhe_b200::Twiddle* d_fwd = nullptr;            // [limbs][n]
@@ -71,4 +72,5 @@ enum EwOp { EW_ADD = 0, EW_SUB, EW_MUL, EW_MAC, EW_MUL_SCALAR, EW_ADD_SCALAR, EW
 int launch_elementwise(fhe_b200_plan* plan, EwOp op, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
                        const uint64_t* d_c, uint32_t batch, uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
 int check_range(const fhe_b200_plan* plan, uint32_t batch, uint32_t limb_begin, uint32_t limb_count);
+void release_fused_scratch(const fhe_b200_plan* plan);
 }  // namespace fhe_b200

@@ -72,6 +72,24 @@ FHE_HD void st2(u64* p, u64 a, u64 b) {
 #endif
 }
 
+// Global loads of polynomial data go to L2 only (ld.global.cg): the data is streamed (no L1 reuse), and in the fused
+// row+tile kernel another SM may have rewritten a line that this SM's L1 still holds from the row pass.
+FHE_HD u64 ldg1(const u64* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+FHE_HD void ldg2(const u64* p, u64& a, u64& b) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(p));
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+
 // bounds in units of q; the twiddle product is lazy in [0, 4q) (shoup_mul_lazy4).
 // NEAR: every modulus q satisfies 2^60 - 2^55 <= q < 2^60, so near60_reduce brings anything below 16q under 2q.
 FHE_HDC int red_to(int HB, bool NEAR) { return NEAR ? 2 : HB / 2; }
@@ -220,7 +238,7 @@ struct TileFwd {
     // phase 1 is split so that the kernel can issue the global loads before it waits for the staged twiddles
     static FHE_HD void phase1_load(u32 tid, const u64* g, u64 (&x)[16]) {
 #pragma unroll
-        for (int e = 0; e < 16; e++) x[e] = g[(e << (LB - 4)) | tid];
+        for (int e = 0; e < 16; e++) x[e] = ldg1(g + ((e << (LB - 4)) | tid));
     }
     template <int B0>
     static FHE_HD void phase1_compute(u32 tid, u64 (&x)[16], u64* s, const Twiddle* s12, u64 q) {
@@ -288,7 +306,7 @@ struct TileInv {
         for (int i = 0; i < 8; i++) {
             const u32 c = tid + i * NT;
             const u32 p = ((c >> 3) << 3) | ((c & 7) ^ ((c >> 3) & 7));
-            u64 a, b; ld2(g + 2 * c, a, b); st2(s + 2 * p, a, b);
+            u64 a, b; ldg2(g + 2 * c, a, b); st2(s + 2 * p, a, b);
         }
     }
     static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* s3, const LimbParams& P) {
@@ -351,8 +369,8 @@ struct RowPass {
         u64 x[V][NA];
 #pragma unroll
         for (int r = 0; r < NA; r++) {
-            if (V == 2) ld2(gin + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
-            else x[0][r] = gin[(size_t)r * NB + col];
+            if (V == 2) ldg2(gin + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
+            else x[0][r] = ldg1(gin + (size_t)r * NB + col);
         }
 #pragma unroll
         for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, NEAR, 1>(x[c], TwGlobal<0>{tw, 1u}, q);
@@ -369,8 +387,8 @@ struct RowPass {
         u64 x[V][NA];
 #pragma unroll
         for (int r = 0; r < NA; r++) {
-            if (V == 2) ld2(g + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
-            else x[0][r] = g[(size_t)r * NB + col];
+            if (V == 2) ldg2(g + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
+            else x[0][r] = ldg1(g + (size_t)r * NB + col);
         }
 #pragma unroll
         for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, NEAR, true, B0>(x[c], TwGlobal<0>{tw, 1u}, P);

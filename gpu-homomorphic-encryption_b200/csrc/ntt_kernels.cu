@@ -1,16 +1,24 @@
 // __global__ wrappers and launchers of the batched negacyclic NTT (bodies in ntt_core.cuh).
 //
-// Work decomposition over a batch laid out [batch][limb_count][N]:
-//   tile pass : one CTA of 2^(LB-4) threads per (limb, tile, polynomial group).  The CTA stages the tile's twiddles in
-//               shared memory once (two cp.async.bulk copies completing on an mbarrier) and reuses them for every
-//               polynomial of its group; CTAs that share (limb, tile) are adjacent in blockIdx (L2 hits).
-//   row pass  : one thread per V adjacent columns of a (limb, polynomial); 256-thread CTAs.
-// For N > 4096 the two passes are issued chunk by chunk (plan->chunk_bytes of polynomials at a time) so that the
-// intermediate written by the first pass is still L2-resident (126 MB on B200) when the second pass reads it:
-// HBM then sees one read and one write per limb-transform.
+// Work items over a batch laid out [batch][limb_count][N]:
+//   tile item : (limb, tile, polynomial group).  A CTA of 2^(LB-4) threads stages that tile's twiddles in shared memory once
+//               (two cp.async.bulk copies completing on an mbarrier) and runs the tile pass for every polynomial of the group,
+//               prefetching the next polynomial's tile while it finishes the current one.
+//   row item  : (limb, polynomial, column block): V adjacent columns x 2^K1 rows per thread, registers only.
+//
+// N <= 4096: tile items only (one kernel).  N > 4096, two strategies:
+//   fused (default) : ONE persistent kernel.  CTAs draw items from an ordered list through an atomic ticket; row items of a
+//                     group are listed a couple of groups ahead of the tile items that consume them, and a per-(limb, group)
+//                     counter in global memory tells a tile item when its rows are done.  The intermediate is therefore still
+//                     L2-resident when it is read back (HBM sees each limb once in, once out), and the HBM-bound row work
+//                     overlaps the IMAD-bound tile work of other CTAs on the same SM.  Waiting items only ever wait for
+//                     lower tickets, which are held by running CTAs that never wait themselves: no deadlock.
+//   two-pass        : row kernel then tile kernel per chunk (FHE_B200_NTT_FUSED=0).
 #include "common.cuh"
 #include "ntt_core.cuh"
 #include "tma.cuh"
+#include <map>
+#include <mutex>
 
 namespace fhe_b200 {
 
@@ -26,8 +34,14 @@ struct NttArgs {
     uint32_t limb_begin;         // first plan limb the buffer's limb 0 maps to
     uint32_t l0, nl;             // chunk: buffer limbs [l0, l0+nl)
     uint32_t b0, nb;             // chunk: polynomials [b0, b0+nb)
-    uint32_t groups;             // tile pass: CTAs per (limb, tile); CTA g handles polynomials b0+g, b0+g+groups, ...
+    uint32_t groups;             // two-pass tile kernel: CTAs per (limb, tile); CTA g handles polynomials b0+g, b0+g+groups, ...
     uint32_t tiles, p3n;
+    // fused kernel
+    const uint32_t* work;        // item list
+    uint32_t n_items;
+    uint32_t pg;                 // polynomials per group
+    uint32_t n_groups;           // groups per limb
+    uint32_t* sync;              // [0] ticket, [1] error flag, [2 + limb * n_groups + group] completion counters
 };
 
 // (limb, tile/column-block, polynomial or group) from a linear CTA index, innermost fastest
@@ -39,7 +53,7 @@ __device__ __forceinline__ void decode(uint32_t i, uint32_t inner, uint32_t unit
     limb = l0 + r / units;
 }
 
-// 16-byte asynchronous global -> shared copies (LDGSTS) of one tile into the swizzled layout
+// 16-byte asynchronous global -> shared copies (LDGSTS, L2 only) of one tile into the swizzled layout
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -63,42 +77,47 @@ struct TileSmem {
     static constexpr size_t data_bytes = (size_t)NB * 8;
     static constexpr size_t p12_bytes = 256 * sizeof(Twiddle);
     static constexpr size_t p3_bytes = (size_t)p3_entries(LB) * sizeof(Twiddle);
-    static constexpr size_t total = data_bytes + p12_bytes + p3_bytes + 16;
+    static constexpr size_t total = data_bytes + p12_bytes + p3_bytes + 32;
+    __device__ static u64* data(unsigned char* raw) { return reinterpret_cast<u64*>(raw); }
+    __device__ static Twiddle* p12(unsigned char* raw) { return reinterpret_cast<Twiddle*>(raw + data_bytes); }
+    __device__ static Twiddle* p3(unsigned char* raw) { return reinterpret_cast<Twiddle*>(raw + data_bytes + p12_bytes); }
+    __device__ static uint64_t* bar(unsigned char* raw) { return reinterpret_cast<uint64_t*>(raw + data_bytes + p12_bytes + p3_bytes); }
+    __device__ static uint32_t* scratch(unsigned char* raw) { return reinterpret_cast<uint32_t*>(raw + data_bytes + p12_bytes + p3_bytes + 16); }
 };
 
-// One CTA = one (limb, tile): stages that tile's twiddles once with two bulk copies (TMA), then runs the tile pass for
-// every polynomial of its group out of shared memory.
+template <int LB>
+__device__ __forceinline__ void stage_twiddles(const NttArgs& a, unsigned char* raw, uint32_t pl, uint32_t tile) {
+    using SM = TileSmem<LB>;
+    if (threadIdx.x == 0) {
+        uint64_t* bar = SM::bar(raw);
+        mbar_arrive_expect_tx(bar, (uint32_t)(SM::p12_bytes + SM::p3_bytes));
+        bulk_copy_g2s(SM::p12(raw), a.p12 + ((size_t)pl * a.tiles + tile) * 256, (uint32_t)SM::p12_bytes, bar);
+        bulk_copy_g2s(SM::p3(raw), a.p3 + ((size_t)pl * a.tiles + tile) * a.p3n, (uint32_t)SM::p3_bytes, bar);
+    }
+}
+
+// ---- tile item, forward: polynomials poly, poly+step, ... < poly_end of (limb, tile).  The mbarrier must be initialised;
+// `parity` is the barrier phase this item completes (the caller flips it afterwards).
 template <int LB, int K1, int HB, bool NEAR>
-__global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const NttArgs a) {
+__device__ __forceinline__ void tile_fwd_item(const NttArgs& a, unsigned char* raw, uint32_t limb, uint32_t tile, uint32_t poly,
+                                              uint32_t poly_end, uint32_t step, uint32_t parity) {
     using T = TileFwd<LB, HB, NEAR>;
     using SM = TileSmem<LB>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    u64* s = reinterpret_cast<u64*>(smem_raw);
-    Twiddle* s12 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes);
-    Twiddle* s3 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes + SM::p12_bytes);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::data_bytes + SM::p12_bytes + SM::p3_bytes);
-    uint32_t limb, tile, grp;
-    decode(blockIdx.x, a.groups, 1u << K1, a.l0, limb, tile, grp);
+    u64* s = SM::data(raw);
+    const Twiddle* s12 = SM::p12(raw);
+    const Twiddle* s3 = SM::p3(raw);
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar, (uint32_t)(SM::p12_bytes + SM::p3_bytes));
-        bulk_copy_g2s(s12, a.p12 + ((size_t)pl * a.tiles + tile) * 256, (uint32_t)SM::p12_bytes, bar);
-        bulk_copy_g2s(s3, a.p3 + ((size_t)pl * a.tiles + tile) * a.p3n, (uint32_t)SM::p3_bytes, bar);
-    }
+    stage_twiddles<LB>(a, raw, pl, tile);
     const u64 q = a.params[pl].q;
     constexpr int B0 = fwd_bound_after(1, K1, HB, NEAR);
     const u64* base_in = (K1 > 0 ? a.out : a.in);             // K1 > 0: the row pass already moved the data to `out`
     const size_t limb_off = (size_t)limb * a.n + (size_t)tile * T::NB;
     const size_t poly_stride = (size_t)a.limb_count * a.n;
-    uint32_t poly = a.b0 + grp;
-    const uint32_t poly_end = a.b0 + a.nb;
     u64 x[16];
     if (poly < poly_end) T::phase1_load(tid, base_in + poly * poly_stride + limb_off, x);
-    mbar_wait(bar, 0);                                        // staged twiddles have landed
-    for (; poly < poly_end; poly += a.groups) {
+    mbar_wait(SM::bar(raw), parity);                          // staged twiddles have landed
+    for (; poly < poly_end; poly += step) {
         const size_t off = poly * poly_stride + limb_off;
         T::template phase1_compute<B0>(tid, x, s, s12, q);
         __syncthreads();
@@ -107,7 +126,7 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const Nt
         T::template phase3<B0>(tid, s, s3, q);
         __syncthreads();
         // software pipeline: the next polynomial's global loads fly while this one is copied out
-        const uint32_t next = poly + a.groups;
+        const uint32_t next = poly + step;
         if (next < poly_end) T::phase1_load(tid, base_in + next * poly_stride + limb_off, x);
         T::phase4(tid, a.out + off, s);
         __syncthreads();
@@ -115,33 +134,22 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const Nt
 }
 
 template <int LB, int K1, int HB, bool NEAR>
-__global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_inv_kernel(const NttArgs a) {
+__device__ __forceinline__ void tile_inv_item(const NttArgs& a, unsigned char* raw, uint32_t limb, uint32_t tile, uint32_t poly,
+                                              uint32_t poly_end, uint32_t step, uint32_t parity) {
     using T = TileInv<LB, HB, NEAR>;
     using SM = TileSmem<LB>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    u64* s = reinterpret_cast<u64*>(smem_raw);
-    Twiddle* s12 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes);
-    Twiddle* s3 = reinterpret_cast<Twiddle*>(smem_raw + SM::data_bytes + SM::p12_bytes);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::data_bytes + SM::p12_bytes + SM::p3_bytes);
-    uint32_t limb, tile, grp;
-    decode(blockIdx.x, a.groups, 1u << K1, a.l0, limb, tile, grp);
+    u64* s = SM::data(raw);
+    const Twiddle* s12 = SM::p12(raw);
+    const Twiddle* s3 = SM::p3(raw);
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar, (uint32_t)(SM::p12_bytes + SM::p3_bytes));
-        bulk_copy_g2s(s12, a.p12 + ((size_t)pl * a.tiles + tile) * 256, (uint32_t)SM::p12_bytes, bar);
-        bulk_copy_g2s(s3, a.p3 + ((size_t)pl * a.tiles + tile) * a.p3n, (uint32_t)SM::p3_bytes, bar);
-    }
+    stage_twiddles<LB>(a, raw, pl, tile);
     const LimbParams P = a.params[pl];
     const size_t limb_off = (size_t)limb * a.n + (size_t)tile * T::NB;
     const size_t poly_stride = (size_t)a.limb_count * a.n;
-    uint32_t poly = a.b0 + grp;
-    const uint32_t poly_end = a.b0 + a.nb;
     if (poly < poly_end) tile_copy_in_async<LB>(tid, a.in + poly * poly_stride + limb_off, s);
-    mbar_wait(bar, 0);
-    for (; poly < poly_end; poly += a.groups) {
+    mbar_wait(SM::bar(raw), parity);
+    for (; poly < poly_end; poly += step) {
         const size_t off = poly * poly_stride + limb_off;
         cp_async_wait_all();
         __syncthreads();
@@ -152,32 +160,24 @@ __global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_inv_kernel(const Nt
         u64 x[16];
         T::phase4_load(tid, s, x);
         __syncthreads();                                       // every thread has its inputs: the tile buffer is free
-        const uint32_t next = poly + a.groups;
+        const uint32_t next = poly + step;
         if (next < poly_end) tile_copy_in_async<LB>(tid, a.in + next * poly_stride + limb_off, s);   // overlaps the last 4 stages
         T::template phase4_compute<K1 == 0>(tid, x, a.out + off, s12, P);
     }
+    __syncthreads();                                           // twiddle blocks may be restaged after this
 }
 
 constexpr int kRowThreads = 256;
 
 template <int LB, int K1, int HB, bool NEAR, int V>
-__global__ void __launch_bounds__(kRowThreads) ntt_row_fwd_kernel(const NttArgs a) {
-    constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
-    uint32_t limb, cb, poly;
-    decode(blockIdx.x, a.nb, blocks_per_pl, a.l0, limb, cb, poly);
-    poly += a.b0;
+__device__ __forceinline__ void row_fwd_item(const NttArgs& a, uint32_t limb, uint32_t poly, uint32_t cb) {
     const size_t off = ((size_t)poly * a.limb_count + limb) * a.n;
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t col = (cb * kRowThreads + threadIdx.x) * V;
     RowPass<K1, V, LB, HB, NEAR>::forward(a.out + off, a.in + off, col, a.tw + (size_t)pl * a.n, a.params[pl].q);
 }
-
 template <int LB, int K1, int HB, bool NEAR, int V>
-__global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs a) {
-    constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
-    uint32_t limb, cb, poly;
-    decode(blockIdx.x, a.nb, blocks_per_pl, a.l0, limb, cb, poly);
-    poly += a.b0;
+__device__ __forceinline__ void row_inv_item(const NttArgs& a, uint32_t limb, uint32_t poly, uint32_t cb) {
     const size_t off = ((size_t)poly * a.limb_count + limb) * a.n;
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t col = (cb * kRowThreads + threadIdx.x) * V;
@@ -186,9 +186,198 @@ __global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs 
     RowPass<K1, V, LB, HB, NEAR>::template inverse<B0>(a.out + off, col, a.tw + (size_t)pl * a.n, a.params[pl]);
 }
 
+// ================================================ two-pass kernels =====================================================
 template <int LB, int K1, int HB, bool NEAR>
-static int run_chunk(NttArgs a, bool inverse, int sm_count, cudaStream_t st) {
+__global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_fwd_kernel(const NttArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t limb, tile, grp;
+    decode(blockIdx.x, a.groups, 1u << K1, a.l0, limb, tile, grp);
+    if (threadIdx.x == 0) { mbar_init(TileSmem<LB>::bar(smem_raw), 1); mbar_fence_init(); }
+    __syncthreads();
+    tile_fwd_item<LB, K1, HB, NEAR>(a, smem_raw, limb, tile, a.b0 + grp, a.b0 + a.nb, a.groups, 0);
+}
+template <int LB, int K1, int HB, bool NEAR>
+__global__ void __launch_bounds__(1 << (LB - 4), 2) ntt_tile_inv_kernel(const NttArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t limb, tile, grp;
+    decode(blockIdx.x, a.groups, 1u << K1, a.l0, limb, tile, grp);
+    if (threadIdx.x == 0) { mbar_init(TileSmem<LB>::bar(smem_raw), 1); mbar_fence_init(); }
+    __syncthreads();
+    tile_inv_item<LB, K1, HB, NEAR>(a, smem_raw, limb, tile, a.b0 + grp, a.b0 + a.nb, a.groups, 0);
+}
+template <int LB, int K1, int HB, bool NEAR, int V>
+__global__ void __launch_bounds__(kRowThreads) ntt_row_fwd_kernel(const NttArgs a) {
+    constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
+    uint32_t limb, cb, poly;
+    decode(blockIdx.x, a.nb, blocks_per_pl, a.l0, limb, cb, poly);
+    row_fwd_item<LB, K1, HB, NEAR, V>(a, limb, a.b0 + poly, cb);
+}
+template <int LB, int K1, int HB, bool NEAR, int V>
+__global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs a) {
+    constexpr uint32_t blocks_per_pl = (1u << LB) / (V * kRowThreads);
+    uint32_t limb, cb, poly;
+    decode(blockIdx.x, a.nb, blocks_per_pl, a.l0, limb, cb, poly);
+    row_inv_item<LB, K1, HB, NEAR, V>(a, limb, a.b0 + poly, cb);
+}
+
+// ================================================ fused persistent kernel ==============================================
+// item code: bit 31 = consumer (waits for its group's counter), bit 30 = tile item (else row item),
+//            bits 29..22 limb (buffer-relative), bits 21..11 group, bits 10..0 unit (tile index, or poly-in-group * RB + column block)
+constexpr uint32_t kItemConsumer = 1u << 31, kItemTile = 1u << 30;
+__host__ __device__ inline uint32_t item_code(bool consumer, bool tile, uint32_t limb, uint32_t group, uint32_t unit) {
+    return (consumer ? kItemConsumer : 0) | (tile ? kItemTile : 0) | (limb << 22) | (group << 11) | unit;
+}
+
+template <int LB, int K1, int HB, bool NEAR, bool INVERSE>
+__global__ void __launch_bounds__(kRowThreads, 2) ntt_fused_kernel(const NttArgs a) {
+    static_assert((1 << (LB - 4)) == kRowThreads, "fused kernel needs 256-thread tile CTAs (LB = 12)");
     constexpr int V = (K1 >= 5) ? 1 : 2;
+    constexpr uint32_t RB = (1u << LB) / (V * kRowThreads);       // row items per (limb, polynomial)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using SM = TileSmem<LB>;
+    uint32_t* s_scr = SM::scratch(smem_raw);
+    if (threadIdx.x == 0) { mbar_init(SM::bar(smem_raw), 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t parity = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_scr[0] = atomicAdd(&a.sync[0], 1u);
+        __syncthreads();
+        const uint32_t ticket = s_scr[0];
+        if (ticket >= a.n_items) break;
+        const uint32_t code = a.work[ticket];
+        const uint32_t limb = a.l0 + ((code >> 22) & 0xffu), grp = (code >> 11) & 0x7ffu, unit = code & 0x7ffu;
+        const bool is_tile = (code & kItemTile) != 0;
+        uint32_t* counter = &a.sync[2 + ((code >> 22) & 0xffu) * a.n_groups + grp];
+        const uint32_t p0 = a.b0 + grp * a.pg;
+        const uint32_t p1 = min(a.b0 + a.nb, p0 + a.pg);
+        if (code & kItemConsumer) {
+            // wait until every producer item of this (limb, group) has published its stores
+            const uint32_t need = INVERSE ? (1u << K1) : (p1 - p0) * RB;
+            if (threadIdx.x == 0) {
+                uint32_t spins = 0, seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+                    if (seen >= need) break;
+                    __nanosleep(64);
+                } while (++spins < (1u << 26));
+                if (seen < need) atomicExch(&a.sync[1], 1u);          // give up loudly instead of hanging the GPU
+            }
+            __syncthreads();
+        }
+        if (is_tile) {
+            if (!INVERSE) tile_fwd_item<LB, K1, HB, NEAR>(a, smem_raw, limb, unit, p0, p1, 1, parity);
+            else tile_inv_item<LB, K1, HB, NEAR>(a, smem_raw, limb, unit, p0, p1, 1, parity);
+            parity ^= 1;
+        } else {
+            const uint32_t poly = p0 + unit / RB, cb = unit % RB;
+            if (!INVERSE) row_fwd_item<LB, K1, HB, NEAR, V>(a, limb, poly, cb);
+            else row_inv_item<LB, K1, HB, NEAR, V>(a, limb, poly, cb);
+        }
+        if (!(code & kItemConsumer)) {
+            // producer: make this CTA's stores visible GPU-wide, then count the item as done
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side of the fused kernel: item list and synchronisation words, cached per (stream, shape) -----------------
+struct FusedScratch {
+    uint32_t* d_work = nullptr; size_t work_cap = 0;
+    uint32_t* d_sync = nullptr; size_t sync_cap = 0;
+    uint64_t key = 0;            // shape the cached item list was built for
+    uint32_t n_items = 0;
+};
+static std::mutex g_fused_mu;
+static std::map<std::pair<const void*, const void*>, FusedScratch> g_fused;    // (plan, stream) -> scratch
+
+static constexpr uint32_t kPolysPerGroup = 8;
+static constexpr uint32_t kLeadGroups = 2;       // row items run this many groups ahead of the tile items that consume them
+
+static void build_items(std::vector<uint32_t>& w, uint32_t nl, uint32_t nb, uint32_t tiles, uint32_t RB, bool inverse) {
+    const uint32_t pg = kPolysPerGroup, G = (nb + pg - 1) / pg;
+    auto polys = [&](uint32_t g) { return (g + 1) * pg <= nb ? pg : nb - g * pg; };
+    for (uint32_t l = 0; l < nl; l++) {
+        // producers of group g are listed kLeadGroups groups before its consumers
+        auto emit = [&](uint32_t g, bool consumer) {
+            const bool tile = inverse ? !consumer : consumer;
+            const uint32_t cnt = tile ? tiles : polys(g) * RB;
+            for (uint32_t u = 0; u < cnt; u++) w.push_back(item_code(consumer, tile, l, g, u));
+        };
+        for (uint32_t g = 0; g < G + kLeadGroups; g++) {
+            if (g < G) emit(g, false);
+            if (g >= kLeadGroups) emit(g - kLeadGroups, true);
+        }
+    }
+}
+
+template <int LB, int K1, int HB, bool NEAR>
+static int run_fused(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t st) {
+    constexpr int V = (K1 >= 5) ? 1 : 2;
+    constexpr uint32_t RB = (1u << LB) / (V * kRowThreads);
+    const uint32_t G = (a.nb + kPolysPerGroup - 1) / kPolysPerGroup;
+    FHE_REQUIRE(a.nl <= 256 && G <= 2048, "fused NTT: at most 256 limbs and 16384 polynomials per launch");
+    FusedScratch* fs;
+    {
+        std::lock_guard<std::mutex> lk(g_fused_mu);
+        fs = &g_fused[std::make_pair((const void*)plan, (const void*)st)];
+    }
+    const uint64_t key = ((uint64_t)a.nl << 40) | ((uint64_t)a.nb << 8) | (inverse ? 1u : 0u) | 2u;
+    const size_t sync_words = 2 + (size_t)a.nl * G;
+    if (fs->sync_cap < sync_words) {
+        if (fs->d_sync) FHE_CUDA(cudaFree(fs->d_sync));
+        FHE_CUDA(cudaMalloc(&fs->d_sync, sync_words * sizeof(uint32_t)));
+        fs->sync_cap = sync_words;
+    }
+    if (fs->key != key) {
+        std::vector<uint32_t> w;
+        build_items(w, a.nl, a.nb, 1u << K1, RB, inverse);
+        if (fs->work_cap < w.size()) {
+            if (fs->d_work) FHE_CUDA(cudaFree(fs->d_work));
+            FHE_CUDA(cudaMalloc(&fs->d_work, w.size() * sizeof(uint32_t)));
+            fs->work_cap = w.size();
+        }
+        FHE_CUDA(cudaMemcpyAsync(fs->d_work, w.data(), w.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        FHE_CUDA(cudaStreamSynchronize(st));          // w is a stack-owned host vector
+        fs->key = key; fs->n_items = (uint32_t)w.size();
+    }
+    FHE_CUDA(cudaMemsetAsync(fs->d_sync, 0, sync_words * sizeof(uint32_t), st));
+    a.work = fs->d_work; a.n_items = fs->n_items; a.pg = kPolysPerGroup; a.n_groups = G; a.sync = fs->d_sync;
+    constexpr size_t smem = TileSmem<LB>::total;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FHE_CUDA(cudaFuncSetAttribute(ntt_fused_kernel<LB, K1, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FHE_CUDA(cudaFuncSetAttribute(ntt_fused_kernel<LB, K1, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const uint32_t grid = (uint32_t)std::min<size_t>((size_t)2 * plan->sm_count, fs->n_items);
+    const bool prof = profile_on();
+    if (prof) profile_begin(inverse ? 1 : 0, (uint64_t)a.nl * a.nb, st);
+    if (!inverse) ntt_fused_kernel<LB, K1, HB, NEAR, false><<<grid, kRowThreads, smem, st>>>(a);
+    else ntt_fused_kernel<LB, K1, HB, NEAR, true><<<grid, kRowThreads, smem, st>>>(a);
+    if (prof) profile_end(st);
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+
+void release_fused_scratch(const fhe_b200_plan* plan) {
+    std::lock_guard<std::mutex> lk(g_fused_mu);
+    for (auto it = g_fused.begin(); it != g_fused.end();) {
+        if (it->first.first == (const void*)plan) { cudaFree(it->second.d_work); cudaFree(it->second.d_sync); it = g_fused.erase(it); }
+        else ++it;
+    }
+}
+
+// ================================================ launch logic =========================================================
+template <int LB, int K1, int HB, bool NEAR>
+static int run_chunk(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t st) {
+    constexpr int V = (K1 >= 5) ? 1 : 2;
+    const int sm_count = plan->sm_count;
+    if constexpr (K1 > 0 && LB == 12) {
+        if (plan->fused) return run_fused<LB, K1, HB, NEAR>(plan, a, inverse, st);
+    }
     const uint32_t pls = a.nl * a.nb;
     const bool prof = profile_on();
     // tile pass: one CTA per (limb, tile, group); a CTA reuses its staged twiddles for every polynomial of its group.
@@ -236,19 +425,19 @@ static int run_chunk(NttArgs a, bool inverse, int sm_count, cudaStream_t st) {
 }
 
 template <int HB, bool NEAR>
-static int dispatch(uint32_t logn, const NttArgs& a, bool inverse, int sm_count, cudaStream_t st) {
-    switch (logn) {
-        case 9: return run_chunk<9, 0, HB, NEAR>(a, inverse, sm_count, st);
-        case 10: return run_chunk<10, 0, HB, NEAR>(a, inverse, sm_count, st);
-        case 11: return run_chunk<11, 0, HB, NEAR>(a, inverse, sm_count, st);
-        case 12: return run_chunk<12, 0, HB, NEAR>(a, inverse, sm_count, st);
-        case 13: return run_chunk<12, 1, HB, NEAR>(a, inverse, sm_count, st);
-        case 14: return run_chunk<12, 2, HB, NEAR>(a, inverse, sm_count, st);
-        case 15: return run_chunk<12, 3, HB, NEAR>(a, inverse, sm_count, st);
-        case 16: return run_chunk<12, 4, HB, NEAR>(a, inverse, sm_count, st);
-        case 17: return run_chunk<12, 5, HB, NEAR>(a, inverse, sm_count, st);
+static int dispatch(fhe_b200_plan* plan, const NttArgs& a, bool inverse, cudaStream_t st) {
+    switch (plan->logn) {
+        case 9: return run_chunk<9, 0, HB, NEAR>(plan, a, inverse, st);
+        case 10: return run_chunk<10, 0, HB, NEAR>(plan, a, inverse, st);
+        case 11: return run_chunk<11, 0, HB, NEAR>(plan, a, inverse, st);
+        case 12: return run_chunk<12, 0, HB, NEAR>(plan, a, inverse, st);
+        case 13: return run_chunk<12, 1, HB, NEAR>(plan, a, inverse, st);
+        case 14: return run_chunk<12, 2, HB, NEAR>(plan, a, inverse, st);
+        case 15: return run_chunk<12, 3, HB, NEAR>(plan, a, inverse, st);
+        case 16: return run_chunk<12, 4, HB, NEAR>(plan, a, inverse, st);
+        case 17: return run_chunk<12, 5, HB, NEAR>(plan, a, inverse, st);
     }
-    set_error("unsupported ring degree 2^%u (supported: 2^9 .. 2^17)", logn);
+    set_error("unsupported ring degree 2^%u (supported: 2^9 .. 2^17)", plan->logn);
     return FHE_B200_EINVAL;
 }
 
@@ -262,25 +451,26 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
     a.p12 = inverse ? plan->d_inv_p12 : plan->d_fwd_p12;
     a.p3 = inverse ? plan->d_inv_p3 : plan->d_fwd_p3;
     a.tiles = plan->tiles; a.p3n = (uint32_t)plan->p3_entries; a.groups = 1;
+    a.work = nullptr; a.n_items = 0; a.pg = 0; a.n_groups = 0; a.sync = nullptr;
     a.params = plan->d_params;
     a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin;
     const size_t pl_bytes = (size_t)plan->n * sizeof(uint64_t);
     uint32_t nb = batch, nl = limb_count;
     if (plan->logn > 12) {
-        // chunk so that (polynomials x limbs) of one chunk stay L2 resident between the two passes;
-        // prefer "one limb, many polynomials" (twiddle reuse), widen to several limbs when the batch is small
+        // chunking: one limb across many polynomials first (twiddle reuse), several limbs when the batch is small
         const size_t per_chunk = plan->chunk_bytes / pl_bytes ? plan->chunk_bytes / pl_bytes : 1;
         nb = (uint32_t)(batch < per_chunk ? batch : per_chunk);
         const size_t lim = per_chunk / nb ? per_chunk / nb : 1;
         nl = (uint32_t)(limb_count < lim ? limb_count : lim);
+        if (nl > 256) nl = 256;
     }
     for (uint32_t l0 = 0; l0 < limb_count; l0 += nl)
         for (uint32_t b0 = 0; b0 < batch; b0 += nb) {
             a.l0 = l0; a.nl = (l0 + nl <= limb_count) ? nl : limb_count - l0;
             a.b0 = b0; a.nb = (b0 + nb <= batch) ? nb : batch - b0;
-            const int rc = plan->near60 ? dispatch<16, true>(plan->logn, a, inverse, plan->sm_count, st)
-                         : plan->hb == 16 ? dispatch<16, false>(plan->logn, a, inverse, plan->sm_count, st)
-                                          : dispatch<8, false>(plan->logn, a, inverse, plan->sm_count, st);
+            const int rc = plan->near60 ? dispatch<16, true>(plan, a, inverse, st)
+                         : plan->hb == 16 ? dispatch<16, false>(plan, a, inverse, st)
+                                          : dispatch<8, false>(plan, a, inverse, st);
             if (rc) return rc;
         }
     return 0;

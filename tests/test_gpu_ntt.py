@@ -42,6 +42,42 @@ def test_forward_inverse_vs_oracle(fhe, oracle, chain, logn, limbs, batch):
     assert np.array_equal(to_host(d), y)          # input untouched
 
 
+@pytest.mark.parametrize("env", [{"FHE_B200_NTT_FUSED": "0"}, {"FHE_B200_NO_NEAR60": "1"}, {"FHE_B200_NTT_FUSED": "0", "FHE_B200_NTT_CHUNK_MB": "1"}])
+def test_alternative_code_paths(fhe, oracle, chain, env, monkeypatch):
+    """the two-pass (row kernel + tile kernel) strategy, chunked launches and the generic (non near-2^60) reduction are
+    selected per plan from the environment; they must give the same bits as the default fused / near-2^60 path."""
+    from fhe_b200.engine import to_device, to_host
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n, mods = 1 << 14, chain[:3]
+    rng = np.random.default_rng(77)
+    x = _rand(rng, mods, n, 11)                       # 11 polynomials: a ragged last group of the fused scheduler's 8
+    plan = fhe.Plan(n, mods)
+    d = to_device(x); plan.forward(d); y = to_host(d)
+    for b in (0, 7, 10):
+        for l, q in enumerate(mods):
+            assert np.array_equal(y[b, l], oracle.ntt_forward(x[b, l], q))
+    plan.inverse(d)
+    assert np.array_equal(to_host(d), x)
+
+
+def test_fused_scheduler_ragged_groups_and_many_limbs(fhe, oracle, chain):
+    from fhe_b200.engine import to_device, to_host
+    n, mods = 1 << 13, chain[:7]
+    rng = np.random.default_rng(78)
+    for batch in (1, 3, 8, 9, 17):
+        x = _rand(rng, mods, n, batch)
+        plan = fhe.Plan(n, mods)
+        d = to_device(x); out = torch.empty_like(d)
+        plan.forward(d, out=out)
+        y = to_host(out)
+        for b in {0, batch - 1}:
+            for l, q in enumerate(mods):
+                assert np.array_equal(y[b, l], oracle.ntt_forward(x[b, l], q)), (batch, b, l)
+        plan.inverse(out)
+        assert np.array_equal(to_host(out), x)
+
+
 def test_tables_match_oracle(fhe, oracle, chain):
     n = 2048
     plan = fhe.Plan(n, chain[:2])
