@@ -7,13 +7,15 @@
 //   row item  : (limb, polynomial, column block): V adjacent columns x 2^K1 rows per thread, registers only.
 //
 // N <= 4096: tile items only (one kernel).  N > 4096, two strategies:
-//   fused (default) : ONE persistent kernel.  CTAs draw items from an ordered list through an atomic ticket; row items of a
+//   two-pass (default): row kernel then tile kernel (per chunk of plan->chunk_bytes).  Both passes are bound by the IMAD pipe
+//                     at the same per-stage rate (measured), so hiding the row pass's HBM traffic buys nothing today.
+//   fused (FHE_B200_NTT_FUSED=1): ONE persistent kernel.  CTAs draw items from an ordered list through an atomic ticket; row items of a
 //                     group are listed a couple of groups ahead of the tile items that consume them, and a per-(limb, group)
 //                     counter in global memory tells a tile item when its rows are done.  The intermediate is therefore still
 //                     L2-resident when it is read back (HBM sees each limb once in, once out), and the HBM-bound row work
 //                     overlaps the IMAD-bound tile work of other CTAs on the same SM.  Waiting items only ever wait for
 //                     lower tickets, which are held by running CTAs that never wait themselves: no deadlock.
-//   two-pass        : row kernel then tile kernel per chunk (FHE_B200_NTT_FUSED=0).
+//                     Measured 5% slower than two-pass at config 3; kept because it touches HBM once per limb.
 #include "common.cuh"
 #include "ntt_core.cuh"
 #include "tma.cuh"
@@ -293,22 +295,41 @@ struct FusedScratch {
 static std::mutex g_fused_mu;
 static std::map<std::pair<const void*, const void*>, FusedScratch> g_fused;    // (plan, stream) -> scratch
 
-static constexpr uint32_t kPolysPerGroup = 8;
-static constexpr uint32_t kLeadGroups = 2;       // row items run this many groups ahead of the tile items that consume them
+// Scheduling parameters (tunable from the environment for experiments):
+//   pg   polynomials per group (a tile item runs them back to back on one staged twiddle block)
+//   lbk  limbs per block: one "step" = the producers of one group for every limb of the block (lbk * pg * N * 8 bytes)
+//   lead steps between a group's producers and its consumers.  (lead + 1) steps must stay L2 resident.
+struct FusedSched { uint32_t pg = 4, lbk = 8, lead = 2; };
+static FusedSched fused_sched() {
+    static FusedSched s = [] {
+        FusedSched v;
+        if (const char* e = getenv("FHE_B200_FUSED_PG")) v.pg = (uint32_t)atoi(e);
+        if (const char* e = getenv("FHE_B200_FUSED_LBK")) v.lbk = (uint32_t)atoi(e);
+        if (const char* e = getenv("FHE_B200_FUSED_LEAD")) v.lead = (uint32_t)atoi(e);
+        if (v.pg < 1) v.pg = 1; if (v.pg > 16) v.pg = 16; if (v.lbk < 1) v.lbk = 1; if (v.lead < 1) v.lead = 1;
+        return v;
+    }();
+    return s;
+}
 
-static void build_items(std::vector<uint32_t>& w, uint32_t nl, uint32_t nb, uint32_t tiles, uint32_t RB, bool inverse) {
-    const uint32_t pg = kPolysPerGroup, G = (nb + pg - 1) / pg;
+// Ticket order: limb blocks one after another; inside a block, step g lists the producers of group g for every limb of the
+// block, then the consumers of group g - lead for every limb.  A consumer's producers are therefore at least
+// lead * (items per step) tickets behind it and have normally finished by the time a CTA draws the consumer.
+static void build_items(std::vector<uint32_t>& w, uint32_t nl, uint32_t nb, uint32_t tiles, uint32_t RB, bool inverse, const FusedSched& sc) {
+    const uint32_t pg = sc.pg, G = (nb + pg - 1) / pg;
     auto polys = [&](uint32_t g) { return (g + 1) * pg <= nb ? pg : nb - g * pg; };
-    for (uint32_t l = 0; l < nl; l++) {
-        // producers of group g are listed kLeadGroups groups before its consumers
+    for (uint32_t lb0 = 0; lb0 < nl; lb0 += sc.lbk) {
+        const uint32_t lb1 = lb0 + sc.lbk < nl ? lb0 + sc.lbk : nl;
         auto emit = [&](uint32_t g, bool consumer) {
             const bool tile = inverse ? !consumer : consumer;
-            const uint32_t cnt = tile ? tiles : polys(g) * RB;
-            for (uint32_t u = 0; u < cnt; u++) w.push_back(item_code(consumer, tile, l, g, u));
+            for (uint32_t l = lb0; l < lb1; l++) {
+                const uint32_t cnt = tile ? tiles : polys(g) * RB;
+                for (uint32_t u = 0; u < cnt; u++) w.push_back(item_code(consumer, tile, l, g, u));
+            }
         };
-        for (uint32_t g = 0; g < G + kLeadGroups; g++) {
+        for (uint32_t g = 0; g < G + sc.lead; g++) {
             if (g < G) emit(g, false);
-            if (g >= kLeadGroups) emit(g - kLeadGroups, true);
+            if (g >= sc.lead) emit(g - sc.lead, true);
         }
     }
 }
@@ -317,7 +338,8 @@ template <int LB, int K1, int HB, bool NEAR>
 static int run_fused(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t st) {
     constexpr int V = (K1 >= 5) ? 1 : 2;
     constexpr uint32_t RB = (1u << LB) / (V * kRowThreads);
-    const uint32_t G = (a.nb + kPolysPerGroup - 1) / kPolysPerGroup;
+    const FusedSched sc = fused_sched();
+    const uint32_t G = (a.nb + sc.pg - 1) / sc.pg;
     FHE_REQUIRE(a.nl <= 256 && G <= 2048, "fused NTT: at most 256 limbs and 16384 polynomials per launch");
     FusedScratch* fs;
     {
@@ -333,7 +355,7 @@ static int run_fused(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t 
     }
     if (fs->key != key) {
         std::vector<uint32_t> w;
-        build_items(w, a.nl, a.nb, 1u << K1, RB, inverse);
+        build_items(w, a.nl, a.nb, 1u << K1, RB, inverse, sc);
         if (fs->work_cap < w.size()) {
             if (fs->d_work) FHE_CUDA(cudaFree(fs->d_work));
             FHE_CUDA(cudaMalloc(&fs->d_work, w.size() * sizeof(uint32_t)));
@@ -344,7 +366,7 @@ static int run_fused(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t 
         fs->key = key; fs->n_items = (uint32_t)w.size();
     }
     FHE_CUDA(cudaMemsetAsync(fs->d_sync, 0, sync_words * sizeof(uint32_t), st));
-    a.work = fs->d_work; a.n_items = fs->n_items; a.pg = kPolysPerGroup; a.n_groups = G; a.sync = fs->d_sync;
+    a.work = fs->d_work; a.n_items = fs->n_items; a.pg = sc.pg; a.n_groups = G; a.sync = fs->d_sync;
     constexpr size_t smem = TileSmem<LB>::total;
     static bool attr_set = false;
     if (!attr_set) {

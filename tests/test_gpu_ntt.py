@@ -42,7 +42,8 @@ def test_forward_inverse_vs_oracle(fhe, oracle, chain, logn, limbs, batch):
     assert np.array_equal(to_host(d), y)          # input untouched
 
 
-@pytest.mark.parametrize("env", [{"FHE_B200_NTT_FUSED": "0"}, {"FHE_B200_NO_NEAR60": "1"}, {"FHE_B200_NTT_FUSED": "0", "FHE_B200_NTT_CHUNK_MB": "1"}])
+@pytest.mark.parametrize("env", [{"FHE_B200_NTT_FUSED": "1"}, {"FHE_B200_NO_NEAR60": "1"}, {"FHE_B200_NTT_CHUNK_MB": "1"},
+                                 {"FHE_B200_NTT_FUSED": "1", "FHE_B200_FUSED_PG": "3", "FHE_B200_FUSED_LBK": "2", "FHE_B200_FUSED_LEAD": "1"}])
 def test_alternative_code_paths(fhe, oracle, chain, env, monkeypatch):
     """the two-pass (row kernel + tile kernel) strategy, chunked launches and the generic (non near-2^60) reduction are
     selected per plan from the environment; they must give the same bits as the default fused / near-2^60 path."""
@@ -61,8 +62,9 @@ def test_alternative_code_paths(fhe, oracle, chain, env, monkeypatch):
     assert np.array_equal(to_host(d), x)
 
 
-def test_fused_scheduler_ragged_groups_and_many_limbs(fhe, oracle, chain):
+def test_fused_scheduler_ragged_groups_and_many_limbs(fhe, oracle, chain, monkeypatch):
     from fhe_b200.engine import to_device, to_host
+    monkeypatch.setenv("FHE_B200_NTT_FUSED", "1")
     n, mods = 1 << 13, chain[:7]
     rng = np.random.default_rng(78)
     for batch in (1, 3, 8, 9, 17):
