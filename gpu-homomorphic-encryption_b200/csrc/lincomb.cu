@@ -22,7 +22,7 @@ struct LcKernelArgs {
     const u64 *src_mod, *pre, *pre_s, *th_hi, *th_lo;
     const u64 *dst_mod, *mu_hi, *mu_lo, *c, *lam, *Mt;
     LcView v;
-    uint32_t S, T, logn, k_per_block, use_pre, use_extra;
+    uint32_t S, T, logn, k_per_block, use_pre, use_extra, c_is_one;
     const u64* Mt30;     // [T][SP] matrix entries re-split at bit 30: (m & (2^30-1)) | ((m >> 30) << 32)
     size_t total;        // batch * n
 };
@@ -31,38 +31,46 @@ struct LcKernelArgs {
 __device__ __forceinline__ void add_shifted(u64& hi, u64& lo, u64 v, int sh) {
     add128(hi, lo, sh ? (v >> (64 - sh)) : 0, v << sh);
 }
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 
+// One coefficient is handled by TPC adjacent lanes (TPC = 1 or 2): each lane owns SPT of the sources for the prologue and
+// the multiply-accumulates, partial sums are exchanged with one shuffle step per target pair, and each lane finishes
+// (Barrett, epilogue, store) one target of the pair.  Nothing is computed twice, and at batch 1 the grid has twice the threads.
+//
 // SPLIT30 (every modulus < 2^60): operands are split at bit 30, so each of the four partial products is below 2^60 and
 // sixteen of them fit a 64-bit accumulator.  One (source, target) pair then costs exactly four IMAD.WIDE with the add
 // folded into the instruction -- no carry chain, no 64-bit mul.hi emulation (which recomputes the whole product).
-template <int SP, bool SPLIT30>
+template <int SPT, int TPC, bool SPLIT30>
 __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
     extern __shared__ __align__(16) u64 sm[];
-    const uint32_t k0 = blockIdx.y * a.k_per_block;
-    const uint32_t k1 = min(a.T, k0 + a.k_per_block);
-    // shared: matrix rows [k1-k0][SP], then per-source arrays (5 x SP)
+    constexpr int SP = SPT * TPC;                     // padded source count
+    // shared: matrix rows [T][SP], then per-source arrays (5 x SP)
     u64* sMt = sm;
-    u64* sSrc = sm + (size_t)a.k_per_block * SP;      // src_mod, pre, pre_s, th_hi, th_lo
+    u64* sSrc = sm + (size_t)a.T * SP;                // src_mod, pre, pre_s, th_hi, th_lo
     const u64* gMt = SPLIT30 ? a.Mt30 : a.Mt;
-    for (uint32_t t = threadIdx.x; t < (k1 - k0) * SP; t += blockDim.x) sMt[t] = gMt[(size_t)k0 * SP + t];
+    for (uint32_t t = threadIdx.x; t < a.T * SP; t += blockDim.x) sMt[t] = gMt[t];
     for (uint32_t t = threadIdx.x; t < (uint32_t)SP; t += blockDim.x) {
         sSrc[t] = a.src_mod[t]; sSrc[SP + t] = a.pre[t]; sSrc[2 * SP + t] = a.pre_s[t];
         sSrc[3 * SP + t] = a.th_hi[t]; sSrc[4 * SP + t] = a.th_lo[t];
     }
     __syncthreads();
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.total) return;
+    const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g = gt / TPC;                        // coefficient (over batch * n); a.total is a multiple of 32 / TPC
+    const uint32_t sub = (uint32_t)(gt % TPC);
+    if (g >= a.total) return;                         // whole warps only (total * TPC is a multiple of 32)
     const uint32_t b = (uint32_t)(g >> a.logn);
     const uint32_t j = (uint32_t)(g & ((1u << a.logn) - 1));
     const size_t nn = (size_t)1 << a.logn;
+    const uint32_t s0 = sub * SPT;                    // first source of this lane
 
-    u64 z[SP];
-    u64 f0 = 0, f1 = 0, f2 = 0;                       // 192-bit fixed-point accumulator
+    u64 z[SPT];
+    u64 f0 = 0, f1 = 0, f2 = 0;                       // 192-bit fixed-point accumulator (this lane's sources)
     const u64* inb = a.v.in + (size_t)b * a.v.in_stride + j;
 #pragma unroll
-    for (int i = 0; i < SP; i++) {
+    for (int ii = 0; ii < SPT; ii++) {
+        const uint32_t i = s0 + ii;
         u64 x = 0;
-        if (i < (int)a.S) {
+        if (i < a.S) {
             x = inb[(size_t)a.v.src_idx[i] * nn];
             if (a.use_pre) x = shoup_mul(x, sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
         }
@@ -72,78 +80,112 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
         add192(f2, f1, f0, ph, pl);
         add192(f2, f1, f0, 0, lo);
         // SPLIT30: keep the two 30-bit halves side by side in one 64-bit register
-        z[i] = SPLIT30 ? ((x & 0x3fffffffull) | ((x >> 30) << 32)) : x;
+        z[ii] = SPLIT30 ? ((x & 0x3fffffffull) | ((x >> 30) << 32)) : x;
+    }
+    if (TPC == 2) {                                   // combine the two lanes' fixed-point sums
+        const u64 o0 = shfl_xor_u64(f0, 1), o1 = shfl_xor_u64(f1, 1), o2 = shfl_xor_u64(f2, 1);
+        add192(f2, f1, f0, o1, o0); f2 += o2;
     }
     add192(f2, f1, f0, 0, 1ull << 63);
     const u64 I_hi = f2, I_lo = f1;                   // I = (f2:f1), the rounded integer part
 
-    for (uint32_t k = k0; k < k1; k++) {
-        const u64 m = a.dst_mod[k], mh = a.mu_hi[k], ml = a.mu_lo[k];
-        const u64* row = sMt + (size_t)(k - k0) * SP;
-        u64 hi = 0, lo = 0;
-        if (SPLIT30) {
-            u64 u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+    for (uint32_t kb = 0; kb < a.T; kb += TPC) {
+        u64 hi[TPC], lo[TPC];
 #pragma unroll
-            for (int i = 0; i < SP; i++) {
-                const u64 mw = row[i];
-                const u32 z0 = (u32)z[i], z1 = (u32)(z[i] >> 32), m0 = (u32)mw, m1 = (u32)(mw >> 32);
-                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u0) : "r"(z0), "r"(m0));
-                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u1) : "r"(z0), "r"(m1));
-                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u2) : "r"(z1), "r"(m0));
-                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u3) : "r"(z1), "r"(m1));
-                if ((i & 15) == 15 || i == SP - 1) {           // sixteen terms below 2^60 each: flush before overflow
-                    add128(hi, lo, 0, u0); add_shifted(hi, lo, u1, 30); add_shifted(hi, lo, u2, 30); add_shifted(hi, lo, u3, 60);
-                    u0 = u1 = u2 = u3 = 0;
+        for (int t = 0; t < TPC; t++) {
+            hi[t] = 0; lo[t] = 0;
+            const uint32_t k = min(kb + t, a.T - 1);  // a ragged last pair recomputes the last target (never stored twice)
+            const u64* row = sMt + (size_t)k * SP + s0;
+            if (SPLIT30) {
+                u64 u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+#pragma unroll
+                for (int ii = 0; ii < SPT; ii++) {
+                    const u64 mw = row[ii];
+                    const u32 z0 = (u32)z[ii], z1 = (u32)(z[ii] >> 32), m0 = (u32)mw, m1 = (u32)(mw >> 32);
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u0) : "r"(z0), "r"(m0));
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u1) : "r"(z0), "r"(m1));
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u2) : "r"(z1), "r"(m0));
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u3) : "r"(z1), "r"(m1));
+                    if ((ii & 15) == 15 || ii == SPT - 1) {    // sixteen terms below 2^60 each: flush before overflow
+                        add128(hi[t], lo[t], 0, u0); add_shifted(hi[t], lo[t], u1, 30); add_shifted(hi[t], lo[t], u2, 30);
+                        add_shifted(hi[t], lo[t], u3, 60);
+                        u0 = u1 = u2 = u3 = 0;
+                    }
                 }
-            }
-        } else {
+            } else {
 #pragma unroll
-            for (int i = 0; i < SP; i++) mac128(hi, lo, z[i], row[i]);
+                for (int ii = 0; ii < SPT; ii++) mac128(hi[t], lo[t], z[ii], row[ii]);
+            }
         }
-        const u64 Ik = (I_hi == 0 && I_lo < m) ? I_lo : barrett128(I_hi, I_lo, m, mh, ml);
-        mac128(hi, lo, Ik, a.c[k]);
-        if (a.use_extra) mac128(hi, lo, a.v.extra[(size_t)b * a.v.extra_stride + (size_t)a.v.extra_idx[k] * nn + j], a.lam[k]);
-        u64 r = barrett128(hi, lo, m, mh, ml);
-        if (a.v.sub) {
-            const size_t eo = (size_t)a.v.epi_idx[k] * nn + j;
-            const u64 d = sub_mod(a.v.sub[(size_t)b * a.v.sub_stride + eo], r, m);
-            u64 ph, pl;
-            mul128(d, a.v.epi_scalar[k], ph, pl);
-            r = barrett128(ph, pl, m, mh, ml);
-            if (a.v.add) r = add_mod(r, a.v.add[(size_t)b * a.v.add_stride + eo], m);
+        u64 ah = hi[0], al = lo[0];
+        if (TPC == 2) {
+            // lane `sub` finishes target kb + sub: it keeps its own partial of that target and receives the partner's
+            const u64 sh = sub ? hi[0] : hi[1], sl = sub ? lo[0] : lo[1];
+            const u64 rh = shfl_xor_u64(sh, 1), rl = shfl_xor_u64(sl, 1);
+            ah = sub ? hi[1] : hi[0]; al = sub ? lo[1] : lo[0];
+            add128(ah, al, rh, rl);
         }
-        a.v.out[(size_t)b * a.v.out_stride + (size_t)a.v.dst_idx[k] * nn + j] = r;
+        const uint32_t k = kb + sub;
+        if (k < a.T) {
+            const u64 m = a.dst_mod[k], mh = a.mu_hi[k], ml = a.mu_lo[k];
+            // rounded integer term: c_k = 1 for scale-and-round (add I itself), c_k = -Q for conversions (I = overflow count < S)
+            if (a.c_is_one) add128(ah, al, I_hi, I_lo); else mac128(ah, al, I_lo, a.c[k]);
+            if (a.use_extra) mac128(ah, al, a.v.extra[(size_t)b * a.v.extra_stride + (size_t)a.v.extra_idx[k] * nn + j], a.lam[k]);
+            u64 r = barrett128(ah, al, m, mh, ml);
+            if (a.v.sub) {
+                const size_t eo = (size_t)a.v.epi_idx[k] * nn + j;
+                const u64 d = sub_mod(a.v.sub[(size_t)b * a.v.sub_stride + eo], r, m);
+                u64 ph, pl;
+                mul128(d, a.v.epi_scalar[k], ph, pl);
+                r = barrett128(ph, pl, m, mh, ml);
+                if (a.v.add) r = add_mod(r, a.v.add[(size_t)b * a.v.add_stride + eo], m);
+            }
+            a.v.out[(size_t)b * a.v.out_stride + (size_t)a.v.dst_idx[k] * nn + j] = r;
+        }
     }
 }
 
-static const int kSupportedSP[] = {1, 2, 3, 4, 5, 6, 7, 8, 12, 16, 20, 24, 25, 28, 32, 40, 48, 56, 62};
+// sources per thread the kernel is instantiated for (the source count is padded up to SPT * TPC)
+static const int kSupportedSPT[] = {1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 16, 20, 24, 25, 28, 32, 40, 48, 56, 62};
 
-static uint32_t pad_sources(uint32_t S) {
-    for (int sp : kSupportedSP) if ((uint32_t)sp >= S) return (uint32_t)sp;
+static uint32_t pad_spt(uint32_t need) {
+    for (int sp : kSupportedSPT) if ((uint32_t)sp >= need) return (uint32_t)sp;
     return 0;
 }
 
-template <int SP>
-static int launch_sp(const LcKernelArgs& a, dim3 grid, size_t smem, bool split30, cudaStream_t st) {
+template <int SPT, int TPC>
+static int launch_spt(const LcKernelArgs& a, dim3 grid, size_t smem, bool split30, cudaStream_t st) {
     if (split30) {
-        if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lincomb_kernel<SP, true><<<grid, 256, smem, st>>>(a);
+        if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SPT, TPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lincomb_kernel<SPT, TPC, true><<<grid, 256, smem, st>>>(a);
     } else {
-        if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lincomb_kernel<SP, false><<<grid, 256, smem, st>>>(a);
+        if (smem > 48 * 1024) FHE_CUDA(cudaFuncSetAttribute(lincomb_kernel<SPT, TPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lincomb_kernel<SPT, TPC, false><<<grid, 256, smem, st>>>(a);
     }
     FHE_LAUNCH_CHECK();
     return 0;
 }
 
+template <int TPC>
+static int launch_tpc(uint32_t spt, const LcKernelArgs& a, dim3 grid, size_t smem, bool split30, cudaStream_t st) {
+    switch (spt) {
+#define LC_CASE(N_) case N_: return launch_spt<N_, TPC>(a, grid, smem, split30, st);
+        LC_CASE(1) LC_CASE(2) LC_CASE(3) LC_CASE(4) LC_CASE(5) LC_CASE(6) LC_CASE(7) LC_CASE(8) LC_CASE(12) LC_CASE(13) LC_CASE(16)
+        LC_CASE(20) LC_CASE(24) LC_CASE(25) LC_CASE(28) LC_CASE(32) LC_CASE(40) LC_CASE(48) LC_CASE(56) LC_CASE(62)
+#undef LC_CASE
+    }
+    set_error("lincomb: unsupported sources-per-thread %u", spt);
+    return FHE_B200_EINVAL;
+}
+
 int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_t batch, cudaStream_t st) {
     FHE_REQUIRE(lc && view.in && view.out, "lincomb: null argument");
-    FHE_REQUIRE(n >= 2 && (n & (n - 1)) == 0, "lincomb: n_coeffs must be a power of two");
+    FHE_REQUIRE(n >= 32 && (n & (n - 1)) == 0, "lincomb: n_coeffs must be a power of two >= 32");
     FHE_REQUIRE(!lc->use_extra || view.extra, "lincomb: this object needs the extra limbs (scale-and-round)");
     if (!batch) return 0;
     LcKernelArgs a;
     a.src_mod = lc->src_mod; a.pre = lc->pre; a.pre_s = lc->pre_s; a.th_hi = lc->th_hi; a.th_lo = lc->th_lo;
-    a.dst_mod = lc->dst_mod; a.mu_hi = lc->mu_hi; a.mu_lo = lc->mu_lo; a.c = lc->c; a.lam = lc->lam; a.Mt = lc->Mt; a.Mt30 = lc->Mt30;
+    a.dst_mod = lc->dst_mod; a.mu_hi = lc->mu_hi; a.mu_lo = lc->mu_lo; a.c = lc->c; a.lam = lc->lam;
     a.v = view;
     if (!a.v.src_idx) a.v.src_idx = lc->id_src;
     if (!a.v.dst_idx) a.v.dst_idx = lc->id_dst;
@@ -155,33 +197,32 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     if (!a.v.sub_stride) a.v.sub_stride = (size_t)lc->T * n;
     if (!a.v.add_stride) a.v.add_stride = (size_t)lc->T * n;
     a.S = lc->S; a.T = lc->T; a.logn = host::ilog2(n);
-    a.use_pre = lc->use_pre; a.use_extra = lc->use_extra;
+    a.use_pre = lc->use_pre; a.use_extra = lc->use_extra; a.c_is_one = lc->use_pre ? 0 : 1;
+    a.k_per_block = lc->T;
     a.total = (size_t)batch * n;
-    const uint32_t cblocks = (uint32_t)((a.total + 255) / 256);
-    // split the targets across gridDim.y only when the coefficients alone leave SMs idle (each split recomputes z, I)
-    uint32_t splits = 1;
-    const uint32_t want = 2 * lc->sm_count;
-    if (cblocks < want) { splits = (want + cblocks - 1) / cblocks; const uint32_t maxs = (lc->T + 3) / 4; if (splits > maxs) splits = maxs; if (!splits) splits = 1; }
-    a.k_per_block = (lc->T + splits - 1) / splits;
-    splits = (lc->T + a.k_per_block - 1) / a.k_per_block;
-    const dim3 grid(cblocks, splits);
-    const size_t smem = ((size_t)a.k_per_block * lc->SP + 5 * lc->SP) * sizeof(u64);
+    // two lanes per coefficient when the coefficients alone cannot fill the SMs (or when asked to)
+    int tpc = (a.total < (size_t)lc->sm_count * 2048 && lc->S >= 2) ? 2 : 1;
+    if (lc->force_tpc) tpc = lc->force_tpc;
+    if (lc->S < 2) tpc = 1;
+    const bool use2 = tpc == 2;
+    a.Mt = use2 ? lc->Mt2 : lc->Mt; a.Mt30 = use2 ? lc->Mt30_2 : lc->Mt30;
+    // the per-source device arrays are padded to SP1 (one lane) and SP2 = 2 * SPT2 (two lanes): pick the matching set
+    if (use2) { a.src_mod = lc->src_mod2; a.pre = lc->pre2; a.pre_s = lc->pre_s2; a.th_hi = lc->th_hi2; a.th_lo = lc->th_lo2; }
+    const uint32_t spt = use2 ? lc->SPT2 : lc->SP;
+    const uint32_t sp = use2 ? 2 * lc->SPT2 : lc->SP;
+    const size_t threads = a.total * (use2 ? 2 : 1);
+    const dim3 grid((uint32_t)((threads + 255) / 256), 1);
+    const size_t smem = ((size_t)lc->T * sp + 5 * sp) * sizeof(u64);
     FHE_REQUIRE(smem <= 200 * 1024, "lincomb: constant block too large for shared memory");
-    switch (lc->SP) {
-#define LC_CASE(N_) case N_: return launch_sp<N_>(a, grid, smem, lc->split30, st);
-        LC_CASE(1) LC_CASE(2) LC_CASE(3) LC_CASE(4) LC_CASE(5) LC_CASE(6) LC_CASE(7) LC_CASE(8) LC_CASE(12) LC_CASE(16)
-        LC_CASE(20) LC_CASE(24) LC_CASE(25) LC_CASE(28) LC_CASE(32) LC_CASE(40) LC_CASE(48) LC_CASE(56) LC_CASE(62)
-#undef LC_CASE
-    }
-    set_error("lincomb: unsupported source count %u", lc->S);
-    return FHE_B200_EINVAL;
+    return use2 ? launch_tpc<2>(spt, a, grid, smem, lc->split30, st) : launch_tpc<1>(spt, a, grid, smem, lc->split30, st);
 }
 
 int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
     *out = nullptr;
     FHE_REQUIRE(h.S >= 1 && h.T >= 1, "lincomb: empty basis");
-    const uint32_t SP = pad_sources(h.S);
+    const uint32_t SP = pad_spt(h.S);
     FHE_REQUIRE(SP != 0, "lincomb: at most 62 source moduli are supported (got %u)", h.S);
+    const uint32_t SPT2 = pad_spt((h.S + 1) / 2), SP2 = 2 * SPT2;
     for (uint32_t i = 0; i < h.S; i++) FHE_REQUIRE(h.src_mod[i] > 1 && (h.src_mod[i] >> 61) == 0, "lincomb: source modulus %u out of range", i);
     for (uint32_t k = 0; k < h.T; k++) FHE_REQUIRE(h.dst_mod[k] > 1 && (h.dst_mod[k] >> 61) == 0, "lincomb: target modulus %u out of range", k);
     bool split30 = getenv("FHE_B200_NO_SPLIT30") == nullptr;
@@ -189,46 +230,63 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
     for (uint32_t k = 0; k < h.T; k++) split30 = split30 && (h.dst_mod[k] >> 60) == 0;
     FHE_CUDA(cudaSetDevice(device));
     auto* lc = new fhe_b200_lincomb();
-    lc->device = device; lc->S = h.S; lc->T = h.T; lc->SP = SP; lc->use_pre = h.use_pre; lc->use_extra = h.use_extra; lc->h = h; lc->split30 = split30;
+    lc->device = device; lc->S = h.S; lc->T = h.T; lc->SP = SP; lc->SPT2 = SPT2;
+    lc->use_pre = h.use_pre; lc->use_extra = h.use_extra; lc->h = h; lc->split30 = split30;
+    if (const char* e = getenv("FHE_B200_LINCOMB_TPC")) lc->force_tpc = atoi(e) == 2 ? 2 : (atoi(e) == 1 ? 1 : 0);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) lc->sm_count = prop.multiProcessorCount;
     const uint32_t T = h.T, S = h.S;
-    // blob layout (u64 units): 5 x SP source arrays | 5 x T target arrays | Mt [T][SP] | id_src (u32 x SP) | id_dst (u32 x T)
-    const size_t n64 = 5 * (size_t)SP + 5 * (size_t)T + 2 * (size_t)T * SP + (SP + 1) / 2 + (T + 1) / 2 + 2;
+    const uint32_t SPmax = SP > SP2 ? SP : SP2;
+    // blob (u64 words): for each padding P in {SP, SP2}: 5 x P source arrays, Mt [T][P], Mt30 [T][P];
+    //                   5 x T target arrays; identity maps (u32): [SPmax], [T]
+    const size_t per_set = [&](uint32_t P) { return 5 * (size_t)P + 2 * (size_t)T * P; }(0);
+    (void)per_set;
+    const size_t n64 = 5 * (size_t)(SP + SP2) + 2 * (size_t)T * (SP + SP2) + 5 * (size_t)T + (SPmax + 1) / 2 + (T + 1) / 2 + 2;
     std::vector<uint64_t> blob(n64, 0);
-    uint64_t* p = blob.data();
-    uint64_t* src_mod = p; p += SP; uint64_t* pre = p; p += SP; uint64_t* pre_s = p; p += SP;
-    uint64_t* th_hi = p; p += SP; uint64_t* th_lo = p; p += SP;
-    uint64_t* dst_mod = p; p += T; uint64_t* mu_hi = p; p += T; uint64_t* mu_lo = p; p += T; uint64_t* cc = p; p += T; uint64_t* lam = p; p += T;
-    uint64_t* Mt = p; p += (size_t)T * SP;
-    uint64_t* Mt30 = p; p += (size_t)T * SP;
-    uint32_t* id_src = reinterpret_cast<uint32_t*>(p); p += (SP + 1) / 2;
-    uint32_t* id_dst = reinterpret_cast<uint32_t*>(p);
-    for (uint32_t i = 0; i < SP; i++) {
-        src_mod[i] = i < S ? h.src_mod[i] : 3;           // padding sources contribute z = 0
-        if (i < S) { pre[i] = h.pre[i]; pre_s[i] = host::shoup(h.pre[i] % h.src_mod[i], h.src_mod[i]); th_hi[i] = h.th_hi[i]; th_lo[i] = h.th_lo[i]; }
-        id_src[i] = i < S ? i : 0;
-    }
-    for (uint32_t k = 0; k < T; k++) {
-        dst_mod[k] = h.dst_mod[k];
-        host::frac128(1, h.dst_mod[k], mu_hi[k], mu_lo[k]);
-        cc[k] = h.c[k]; lam[k] = h.lam[k]; id_dst[k] = k;
-        for (uint32_t i = 0; i < S; i++) {
-            const uint64_t mv = h.M[(size_t)i * T + k];
-            Mt[(size_t)k * SP + i] = mv;
-            Mt30[(size_t)k * SP + i] = (mv & 0x3fffffffull) | ((mv >> 30) << 32);
+    size_t off = 0;
+    struct SetOff { size_t src_mod, pre, pre_s, th_hi, th_lo, Mt, Mt30; } so[2];
+    const uint32_t pads[2] = {SP, SP2};
+    for (int v = 0; v < 2; v++) {
+        const uint32_t P = pads[v];
+        so[v].src_mod = off; off += P; so[v].pre = off; off += P; so[v].pre_s = off; off += P; so[v].th_hi = off; off += P; so[v].th_lo = off; off += P;
+        so[v].Mt = off; off += (size_t)T * P; so[v].Mt30 = off; off += (size_t)T * P;
+        for (uint32_t i = 0; i < P; i++) {
+            blob[so[v].src_mod + i] = i < S ? h.src_mod[i] : 3;           // padding sources contribute z = 0
+            if (i < S) {
+                blob[so[v].pre + i] = h.pre[i]; blob[so[v].pre_s + i] = host::shoup(h.pre[i] % h.src_mod[i], h.src_mod[i]);
+                blob[so[v].th_hi + i] = h.th_hi[i]; blob[so[v].th_lo + i] = h.th_lo[i];
+            }
         }
+        for (uint32_t k = 0; k < T; k++)
+            for (uint32_t i = 0; i < S; i++) {
+                const uint64_t mv = h.M[(size_t)i * T + k];
+                blob[so[v].Mt + (size_t)k * P + i] = mv;
+                blob[so[v].Mt30 + (size_t)k * P + i] = (mv & 0x3fffffffull) | ((mv >> 30) << 32);
+            }
     }
+    const size_t o_dst = off; off += T; const size_t o_muh = off; off += T; const size_t o_mul = off; off += T;
+    const size_t o_c = off; off += T; const size_t o_lam = off; off += T;
+    const size_t o_ids = off; off += (SPmax + 1) / 2; const size_t o_idd = off; off += (T + 1) / 2;
+    for (uint32_t k = 0; k < T; k++) {
+        blob[o_dst + k] = h.dst_mod[k];
+        host::frac128(1, h.dst_mod[k], blob[o_muh + k], blob[o_mul + k]);
+        blob[o_c + k] = h.c[k]; blob[o_lam + k] = h.lam[k];
+    }
+    uint32_t* id_src = reinterpret_cast<uint32_t*>(blob.data() + o_ids);
+    uint32_t* id_dst = reinterpret_cast<uint32_t*>(blob.data() + o_idd);
+    for (uint32_t i = 0; i < SPmax; i++) id_src[i] = i < S ? i : 0;
+    for (uint32_t k = 0; k < T; k++) id_dst[k] = k;
     cudaError_t e = cudaMalloc(&lc->d_blob, n64 * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemcpy(lc->d_blob, blob.data(), n64 * sizeof(uint64_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("lincomb: device allocation failed: %s", cudaGetErrorString(e)); delete lc; return FHE_B200_ECUDA; }
     const uint64_t* d = lc->d_blob;
-    lc->src_mod = d; d += SP; lc->pre = d; d += SP; lc->pre_s = d; d += SP; lc->th_hi = d; d += SP; lc->th_lo = d; d += SP;
-    lc->dst_mod = d; d += T; lc->mu_hi = d; d += T; lc->mu_lo = d; d += T; lc->c = d; d += T; lc->lam = d; d += T;
-    lc->Mt = d; d += (size_t)T * SP;
-    lc->Mt30 = d; d += (size_t)T * SP;
-    lc->id_src = reinterpret_cast<const uint32_t*>(d); d += (SP + 1) / 2;
-    lc->id_dst = reinterpret_cast<const uint32_t*>(d);
+    lc->src_mod = d + so[0].src_mod; lc->pre = d + so[0].pre; lc->pre_s = d + so[0].pre_s; lc->th_hi = d + so[0].th_hi; lc->th_lo = d + so[0].th_lo;
+    lc->Mt = d + so[0].Mt; lc->Mt30 = d + so[0].Mt30;
+    lc->src_mod2 = d + so[1].src_mod; lc->pre2 = d + so[1].pre; lc->pre_s2 = d + so[1].pre_s; lc->th_hi2 = d + so[1].th_hi; lc->th_lo2 = d + so[1].th_lo;
+    lc->Mt2 = d + so[1].Mt; lc->Mt30_2 = d + so[1].Mt30;
+    lc->dst_mod = d + o_dst; lc->mu_hi = d + o_muh; lc->mu_lo = d + o_mul; lc->c = d + o_c; lc->lam = d + o_lam;
+    lc->id_src = reinterpret_cast<const uint32_t*>(d + o_ids);
+    lc->id_dst = reinterpret_cast<const uint32_t*>(d + o_idd);
     *out = lc;
     return 0;
 }

@@ -15,6 +15,10 @@ struct fhe_b200_lincomb {
     const uint64_t* Mt;                                         // [T][SP]
     const uint64_t* Mt30;                                       // [T][SP], entries re-split at bit 30 (SPLIT30 path)
     bool split30 = false;                                       // every modulus below 2^60
+    // second copy of the source-side constants padded for the two-lanes-per-coefficient kernel (SP2 = 2 * SPT2)
+    uint32_t SPT2 = 0;
+    const uint64_t *src_mod2, *pre2, *pre_s2, *th_hi2, *th_lo2, *Mt2, *Mt30_2;
+    int force_tpc = 0;                                          // FHE_B200_LINCOMB_TPC = 1 | 2
     const uint32_t *id_src, *id_dst;                            // identity limb maps [SP], [T]
     int sm_count = 148;
 };
