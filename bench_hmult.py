@@ -44,6 +44,21 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = lib.fhe_b200_launch_count() - l0
+    # per-kernel-class breakdown of one more pass (CUDA events around every launch)
+    import ctypes as C
+    lib.fhe_b200_profile_enable(1)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    g.multiply(ca, cb, rlk, out=out)
+    e3.record()
+    torch.cuda.synchronize()
+    breakdown = {}
+    for kind, name in enumerate(("ntt_tile_fwd", "ntt_tile_inv", "ntt_row_fwd", "ntt_row_inv", "lincomb", "tensor", "ks_inner")):
+        n_l, t_ms, u = C.c_uint64(), C.c_double(), C.c_uint64()
+        lib.fhe_b200_profile_read(kind, C.byref(n_l), C.byref(t_ms), C.byref(u))
+        breakdown[name] = {"launches": n_l.value, "ms": round(t_ms.value, 4)}
+    breakdown["whole_call_ms"] = round(e2.elapsed_time(e3), 4)
+    lib.fhe_b200_profile_enable(0)
     # correctness of what was timed: decrypt one result
     import oracle
     dec = to_host(g.decrypt(out, sk))
@@ -65,7 +80,7 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
     ct_bytes = 2 * L * n * 8
     return {"metric": "BFV HMult+relinearize ops/s", "value": B * K / (ms / 1e3), "unit": "ops/s", "batch": B, "steps": K,
             "ms_per_op": ms / (B * K), "config": {"workload": f"config4: N={n}, L={L}, R={p['R']}, dnum={p['dnum']}, K={p['K']}, t={t}"},
-            "decrypts_to_product": ok, "gpu_launches": int(launches),
+            "decrypts_to_product": ok, "gpu_launches": int(launches), "kernel_ms_per_call": breakdown,
             "e2e": {"value": B * e2e_steps / e2e, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
                     "matches_device_path": ok2},
             "limb_ntts_per_op": 4 * (L + p["R"]) + 3 * (L + p["R"]) + p["dnum"] * (L + p["K"]) + 2 * (L + p["K"])}

@@ -572,7 +572,9 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     STEP(launch_ntt(c->plan, ext, ext, 4 * B, 0, A, false, st));
     if (!rc) {
         const size_t per = B * an / 2;
+        if (profile_on()) profile_begin(5, B, st);
         tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per);
+        if (profile_on()) profile_end(st);
         count_launch();
     }
     STEP(launch_ntt(c->plan, d, d, 3 * B, 0, A, true, st));
@@ -594,7 +596,9 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     STEP(launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st));
     if (!rc) {
         const size_t per = B * wn / 2;
+        if (profile_on()) profile_begin(6, B, st);
         ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_rlk, prm, c->logn, 0, W, dnum, B);
+        if (profile_on()) profile_end(st);
         count_launch();
     }
     STEP(launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st));

@@ -214,7 +214,11 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     const dim3 grid((uint32_t)((threads + 255) / 256), 1);
     const size_t smem = ((size_t)lc->T * sp + 5 * sp) * sizeof(u64);
     FHE_REQUIRE(smem <= 200 * 1024, "lincomb: constant block too large for shared memory");
-    return use2 ? launch_tpc<2>(spt, a, grid, smem, lc->split30, st) : launch_tpc<1>(spt, a, grid, smem, lc->split30, st);
+    const bool prof = profile_on();
+    if (prof) profile_begin(4, (uint64_t)batch * lc->S * lc->T, st);          // kind 4: lincomb, units = source-target pairs x batch
+    const int rc = use2 ? launch_tpc<2>(spt, a, grid, smem, lc->split30, st) : launch_tpc<1>(spt, a, grid, smem, lc->split30, st);
+    if (prof) profile_end(st);
+    return rc;
 }
 
 int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {

@@ -45,7 +45,7 @@ int fhe_b200_version(void);
 uint64_t fhe_b200_launch_count(void);
 /* per-kernel timing for the roofline report: while enabled, every NTT kernel launch is bracketed by CUDA events
  * on its own stream.  kind: 0 = tile pass (forward), 1 = tile pass (inverse), 2 = row pass (forward), 3 = row pass
- * (inverse).  profile_read synchronises the recorded events and returns launches, total milliseconds and the
+ * (inverse), 4 = RNS linear combination, 5 = BFV tensor product, 6 = key-switch inner product.  profile_read synchronises the recorded events and returns launches, total milliseconds and the
  * limb-transforms those launches covered. */
 int fhe_b200_profile_enable(int on);
 int fhe_b200_profile_read(int kind, uint64_t* launches, double* total_ms, uint64_t* limb_transforms);
