@@ -1,6 +1,7 @@
 // extern "C" entry points: plan lifetime, transforms, element-wise wrappers, host-buffer pipeline.
 #include "common.cuh"
 #include "tables.hpp"
+#include "ntt_bal.cuh"
 #include <cstring>
 #include <string>
 #include <atomic>
@@ -105,6 +106,8 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
     p->near60 = all_near60(h_moduli, n_limbs);
     if (getenv("FHE_B200_NO_NEAR60")) p->near60 = false;
     if (const char* e = getenv("FHE_B200_NTT_FUSED")) p->fused = atoi(e) != 0;
+    p->bal = bal_supported((int)p->logn);
+    if (const char* e = getenv("FHE_B200_NTT_BAL")) p->bal = p->bal && atoi(e) != 0;
     if (const char* e = getenv("FHE_B200_NTT_CHUNK_MB")) { long mb = atol(e); if (mb > 0) p->chunk_bytes = (size_t)mb << 20; }
     p->h_params.resize(n_limbs);
     std::vector<Twiddle> fwd((size_t)n_limbs * n), inv((size_t)n_limbs * n);
@@ -129,6 +132,14 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
         if (e == cudaSuccess) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(Twiddle), cudaMemcpyHostToDevice);
     };
     up(&p->d_fwd_p12, f12); up(&p->d_fwd_p3, f3); up(&p->d_inv_p12, i12); up(&p->d_inv_p3, i3);
+    if (p->bal) {
+        std::vector<Twiddle> fb((size_t)n_limbs * n), ib((size_t)n_limbs * n);
+        for (uint32_t l = 0; l < n_limbs; l++) {
+            build_bal_tables(fwd.data() + (size_t)l * n, p->logn, fb.data() + (size_t)l * n);
+            build_bal_tables(inv.data() + (size_t)l * n, p->logn, ib.data() + (size_t)l * n);
+        }
+        up(&p->d_fwd_bal, fb); up(&p->d_inv_bal, ib);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&p->d_inv, tb);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_params, n_limbs * sizeof(LimbParams));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_fwd, fwd.data(), tb, cudaMemcpyHostToDevice);
@@ -148,6 +159,7 @@ extern "C" int fhe_b200_plan_destroy(fhe_b200_plan* p) {
     cudaSetDevice(p->device);
     release_fused_scratch(p);
     cudaFree(p->d_fwd); cudaFree(p->d_inv); cudaFree(p->d_params);
+    cudaFree(p->d_fwd_bal); cudaFree(p->d_inv_bal);
     cudaFree(p->d_fwd_p12); cudaFree(p->d_fwd_p3); cudaFree(p->d_inv_p12); cudaFree(p->d_inv_p3);
     for (int i = 0; i < 3; i++) { if (p->d_stage[i]) cudaFree(p->d_stage[i]); if (p->hs[i]) cudaStreamDestroy(p->hs[i]); }
     delete p;

@@ -52,6 +52,9 @@ struct fhe_b200_plan {
     fhe_b200::Twiddle* d_inv = nullptr;            // [limbs][n]
     // per-tile staged blocks of the tile pass (one bulk copy each): [limbs][tiles][256] and [limbs][tiles][p3]
     fhe_b200::Twiddle *d_fwd_p12 = nullptr, *d_fwd_p3 = nullptr, *d_inv_p12 = nullptr, *d_inv_p3 = nullptr;
+    // balanced two-pass NTT (ntt_bal.cuh), 2^13 <= N <= 2^16: per tile-pair staged blocks [limbs][n/512][512]; default path there
+    bool bal = false;                              // FHE_B200_NTT_BAL=0 falls back to the row+tile passes
+    fhe_b200::Twiddle *d_fwd_bal = nullptr, *d_inv_bal = nullptr;
     size_t p3_entries = 0;                         // per tile
     uint32_t tiles = 1;                            // tiles per limb = 2^K1
     fhe_b200::LimbParams* d_params = nullptr;      // [limbs]
@@ -71,6 +74,8 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
 enum EwOp { EW_ADD = 0, EW_SUB, EW_MUL, EW_MAC, EW_MUL_SCALAR, EW_ADD_SCALAR, EW_NEG };
 int launch_elementwise(fhe_b200_plan* plan, EwOp op, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
                        const uint64_t* d_c, uint32_t batch, uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
+int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
+                   uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st);
 int check_range(const fhe_b200_plan* plan, uint32_t batch, uint32_t limb_begin, uint32_t limb_count);
 void release_fused_scratch(const fhe_b200_plan* plan);
 }  // namespace fhe_b200

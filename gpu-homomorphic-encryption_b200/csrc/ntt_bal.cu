@@ -1,0 +1,189 @@
+// __global__ wrappers and launcher of the balanced two-pass NTT (bodies and layouts: ntt_bal.cuh), 2^13 <= N <= 2^16.
+//
+//   bal_a_kernel : pass A / A'.  CTA = 256 threads = one limb, a run of M items (item = one polynomial's block of C columns,
+//                  4096 elements).  The limb's first 2^KA twiddles are staged once; the exchange buffer is double-buffered so
+//                  that each item costs a single block barrier.  68 KiB of shared memory, 3 CTAs per SM.
+//   bal_b_kernel : pass B / B'.  Every WARP owns one pair of adjacent tiles of one limb; its 8 KiB twiddle block arrives by one
+//                  bulk copy (cp.async.bulk on the warp's own mbarrier) and serves every polynomial of the warp's group.  Only
+//                  __syncwarp() between phases.  8 warps per CTA (96 KiB), 2 CTAs per SM.
+// Forward: A reads `in`, writes `out`; B runs in place on `out`.  Inverse: B' reads `in`, writes `out`; A' in place on `out`.
+#include "common.cuh"
+#include "ntt_bal.cuh"
+#include "tma.cuh"
+
+namespace fhe_b200 {
+
+struct BalArgs {
+    uint64_t* out;
+    const uint64_t* in;
+    const Twiddle* tw;           // [limbs][n] table of the direction in use (pass A reads its first 2^KA entries)
+    const Twiddle* blocks;       // [limbs][n/512][512] staged blocks of pass B
+    const LimbParams* params;    // [limbs]
+    uint32_t n, limb_count, limb_begin;
+    uint32_t l0, nl, b0, nb;     // chunk: buffer limbs [l0, l0+nl), polynomials [b0, b0+nb)
+    uint32_t m_items, ctas_per_limb;   // pass A: items per CTA, CTAs per limb
+    uint32_t groups;             // pass B: warps per (limb, tile pair); warp g handles polynomials b0+g, b0+g+groups, ...
+};
+
+constexpr size_t kBalASmem = 2 * 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
+constexpr int kBalBWarps = 8;
+constexpr size_t kBalBSmem = kBalBWarps * (512 * sizeof(u64) + 512 * sizeof(Twiddle)) + kBalBWarps * 16;
+
+template <int KA, int HB, bool NEAR, bool INV>
+__global__ void __launch_bounds__(256, 3) bal_a_kernel(const BalArgs a) {
+    using A = BalA<KA, HB, NEAR>;
+    extern __shared__ __align__(128) unsigned char raw[];
+    u64* sbuf = reinterpret_cast<u64*>(raw);
+    Twiddle* stw = reinterpret_cast<Twiddle*>(raw + 2 * 4096 * sizeof(u64));
+    const uint32_t tid = threadIdx.x;
+    const uint32_t limb = a.l0 + blockIdx.x / a.ctas_per_limb, chunk = blockIdx.x % a.ctas_per_limb;
+    const uint32_t pl = a.limb_begin + limb;
+    if (tid < (1u << KA)) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(a.tw + (size_t)pl * a.n + tid));
+        *reinterpret_cast<ulonglong2*>(stw + tid) = v;
+    }
+    const LimbParams P = a.params[pl];
+    const uint32_t items = a.nb * A::CB;
+    uint32_t it = chunk * a.m_items;
+    const uint32_t end = min(items, it + a.m_items);
+    constexpr int BIN = BalB<HB, NEAR>::inv_out_bound();
+    __syncthreads();
+    for (uint32_t k = 0; it < end; it++, k ^= 1u) {
+        const uint32_t poly = a.b0 + it / A::CB, cb = it % A::CB;
+        const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)cb * A::C;
+        u64* s = sbuf + k * 4096;
+        if (!INV) {
+            A::fwd_round1(tid, a.in + off, s, stw, P.q);
+            __syncthreads();
+            A::fwd_round2(tid, a.out + off, s, stw, P.q);
+        } else {
+            A::template inv_round2<BIN>(tid, a.out + off, s, stw, P);
+            __syncthreads();
+            A::template inv_round1<BIN>(tid, a.out + off, s, stw, P);
+        }
+    }
+}
+
+template <int KA, int HB, bool NEAR, bool INV>
+__global__ void __launch_bounds__(32 * kBalBWarps, 2) bal_b_kernel(const BalArgs a) {
+    using B = BalB<HB, NEAR>;
+    extern __shared__ __align__(128) unsigned char raw[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u64* s = reinterpret_cast<u64*>(raw) + warp * 512;
+    Twiddle* sb = reinterpret_cast<Twiddle*>(raw + kBalBWarps * 512 * sizeof(u64)) + warp * 512;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(raw + kBalBWarps * (512 * sizeof(u64) + 512 * sizeof(Twiddle)) + warp * 16);
+    constexpr uint32_t pairs = 1u << (KA - 1);
+    const uint32_t w = blockIdx.x * kBalBWarps + warp;
+    const uint32_t pair = w % pairs, r = w / pairs, grp = r % a.groups, limb = a.l0 + r / a.groups;
+    const uint32_t pl = a.limb_begin + limb;
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    if (lane == 0) {
+        mbar_arrive_expect_tx(bar, 512 * sizeof(Twiddle));
+        bulk_copy_g2s(sb, a.blocks + ((size_t)pl * pairs + pair) * 512, 512 * sizeof(Twiddle), bar);
+    }
+    const LimbParams P = a.params[pl];
+    const size_t limb_off = (size_t)limb * a.n + (size_t)pair * 512;
+    const size_t poly_stride = (size_t)a.limb_count * a.n;
+    constexpr int B0 = BalA<KA, HB, NEAR>::fwd_out_bound();
+    mbar_wait(bar, 0);
+    for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
+        const size_t off = poly * poly_stride + limb_off;
+        if (!INV) {
+            B::template fwd_phase1<B0>(lane, a.out + off, s, sb, P.q);
+            __syncwarp();
+            B::template fwd_phase2<B0>(lane, s, sb, P.q);
+            __syncwarp();
+            B::fwd_phase3(lane, a.out + off, s);
+        } else {
+            B::inv_phase1(lane, a.in + off, s);
+            __syncwarp();
+            B::inv_phase2(lane, s, sb, P);
+            __syncwarp();
+            B::inv_phase3(lane, a.out + off, s, sb, P);
+        }
+        __syncwarp();
+    }
+}
+
+#ifndef FHE_BAL_EXPERIMENT          // (build/exp: a scratch TU instantiates single kernels for SASS inspection)
+template <int KA, int HB, bool NEAR>
+static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st) {
+    using A = BalA<KA, HB, NEAR>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FHE_CUDA(cudaFuncSetAttribute(bal_a_kernel<KA, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
+        FHE_CUDA(cudaFuncSetAttribute(bal_a_kernel<KA, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
+        FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
+        FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
+        attr_set = true;
+    }
+    const uint32_t sms = (uint32_t)plan->sm_count;
+    const uint64_t pls = (uint64_t)a.nl * a.nb;
+    // pass A: items per CTA so that the grid keeps >= ~12 CTAs per SM when the batch allows it (at most 8 items per CTA)
+    const uint32_t items_per_limb = a.nb * A::CB;
+    uint32_t m = (uint32_t)(((uint64_t)a.nl * items_per_limb) / (12u * sms));
+    m = m < 1 ? 1 : (m > 8 ? 8 : m);
+    a.m_items = m;
+    a.ctas_per_limb = (items_per_limb + m - 1) / m;
+    const uint32_t grid_a = a.nl * a.ctas_per_limb;
+    // pass B: one warp per (limb, tile pair, group); >= ~8 CTAs per SM when the batch allows it
+    constexpr uint32_t pairs = 1u << (KA - 1);
+    const uint32_t lp = a.nl * pairs;
+    uint32_t groups = (8u * sms * kBalBWarps + lp - 1) / lp;
+    groups = groups < 1 ? 1 : (groups > a.nb ? a.nb : groups);
+    a.groups = groups;
+    const uint32_t grid_b = lp * groups / kBalBWarps;
+    const bool prof = profile_on();
+    if (!inverse) {
+        if (prof) profile_begin(2, pls, st);
+        bal_a_kernel<KA, HB, NEAR, false><<<grid_a, 256, kBalASmem, st>>>(a);
+        if (prof) profile_end(st);
+        FHE_LAUNCH_CHECK();
+        if (prof) profile_begin(0, pls, st);
+        bal_b_kernel<KA, HB, NEAR, false><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
+        if (prof) profile_end(st);
+        FHE_LAUNCH_CHECK();
+    } else {
+        if (prof) profile_begin(1, pls, st);
+        bal_b_kernel<KA, HB, NEAR, true><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
+        if (prof) profile_end(st);
+        FHE_LAUNCH_CHECK();
+        if (prof) profile_begin(3, pls, st);
+        bal_a_kernel<KA, HB, NEAR, true><<<grid_a, 256, kBalASmem, st>>>(a);
+        if (prof) profile_end(st);
+        FHE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+template <int HB, bool NEAR>
+static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cudaStream_t st) {
+    switch (plan->logn) {
+        case 13: return run_bal_chunk<5, HB, NEAR>(plan, a, inverse, st);
+        case 14: return run_bal_chunk<6, HB, NEAR>(plan, a, inverse, st);
+        case 15: return run_bal_chunk<7, HB, NEAR>(plan, a, inverse, st);
+        case 16: return run_bal_chunk<8, HB, NEAR>(plan, a, inverse, st);
+    }
+    set_error("balanced NTT: unsupported ring degree 2^%u", plan->logn);
+    return FHE_B200_EINVAL;
+}
+
+// chunk = buffer limbs [l0, l0+nl) x polynomials [b0, b0+nb) of a [batch][limb_count][n] buffer
+int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
+                   uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st) {
+    BalArgs a;
+    a.out = d_out; a.in = d_in;
+    a.tw = inverse ? plan->d_inv : plan->d_fwd;
+    a.blocks = inverse ? plan->d_inv_bal : plan->d_fwd_bal;
+    a.params = plan->d_params;
+    a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin;
+    a.l0 = l0; a.nl = nl; a.b0 = b0; a.nb = nb;
+    a.m_items = 1; a.ctas_per_limb = 1; a.groups = 1;
+    return plan->near60 ? dispatch_bal<16, true>(plan, a, inverse, st)
+         : plan->hb == 16 ? dispatch_bal<16, false>(plan, a, inverse, st)
+                          : dispatch_bal<8, false>(plan, a, inverse, st);
+}
+#endif
+
+}  // namespace fhe_b200

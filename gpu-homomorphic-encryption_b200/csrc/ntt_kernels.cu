@@ -490,6 +490,11 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
         for (uint32_t b0 = 0; b0 < batch; b0 += nb) {
             a.l0 = l0; a.nl = (l0 + nl <= limb_count) ? nl : limb_count - l0;
             a.b0 = b0; a.nb = (b0 + nb <= batch) ? nb : batch - b0;
+            if (plan->bal) {
+                const int rc = launch_ntt_bal(plan, d_out, d_in, limb_begin, limb_count, a.l0, a.nl, a.b0, a.nb, inverse, st);
+                if (rc) return rc;
+                continue;
+            }
             const int rc = plan->near60 ? dispatch<16, true>(plan, a, inverse, st)
                          : plan->hb == 16 ? dispatch<16, false>(plan, a, inverse, st)
                                           : dispatch<8, false>(plan, a, inverse, st);

@@ -55,6 +55,23 @@ void build_tile_tables(const Twiddle* main, uint32_t logn, Twiddle* p12, Twiddle
     }
 }
 
+void build_bal_tables(const Twiddle* main, uint32_t logn, Twiddle* out) {
+    const uint32_t ka = logn - 8, pairs = 1u << (ka - 1);
+    for (uint32_t p = 0; p < pairs; p++) {
+        Twiddle* a = out + (size_t)p * 512;
+        for (uint32_t t = 0; t < 2; t++) {
+            const uint32_t root = (1u << ka) + 2 * p + t;
+            a[t * 16 + 15].w = 0; a[t * 16 + 15].ws = 0;
+            for (int v = 0; v < 4; v++)
+                for (uint32_t key = 0; key < (1u << v); key++) a[t * 16 + (1u << v) - 1 + key] = main[(root << v) + key];
+            for (int v = 0; v < 4; v++)
+                for (uint32_t key = 0; key < (1u << v); key++)
+                    for (uint32_t e = 0; e < 16; e++)
+                        a[32 + 32 * ((1u << v) - 1) + key * 32 + t * 16 + e] = main[(((root << 4) + e) << v) + key];
+        }
+    }
+}
+
 int lazy_headroom(const uint64_t* moduli, uint32_t count) {
     int hb = 16;
     for (uint32_t i = 0; i < count; i++) if (moduli[i] >> 60) hb = 8;

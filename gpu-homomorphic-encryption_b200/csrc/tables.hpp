@@ -16,6 +16,9 @@ inline int tile_lb(uint32_t logn) { return logn < 12 ? (int)logn : 12; }
 //   p12: [2^K1 tiles][256]     p3: [2^K1 tiles][p3_entries(LB)]
 void build_tile_tables(const Twiddle* main, uint32_t logn, Twiddle* p12, Twiddle* p3);
 size_t tile_p3_entries(uint32_t logn);
+// Balanced two-pass NTT (ntt_bal.cuh), 2^13 <= N <= 2^16: one 512-entry block per pair of adjacent 256-element tiles
+// (layout: ntt_bal.cuh, TwB1/TwB2).  out: [N/512 pairs][512]
+void build_bal_tables(const Twiddle* main, uint32_t logn, Twiddle* out);
 // head-room of the lazy butterflies for a set of moduli: 16 if all < 2^60, else 8 (all < 2^61)
 int lazy_headroom(const uint64_t* moduli, uint32_t count);
 // true when every modulus lies in [2^60 - 2^55, 2^60) (the whole deterministic 60-bit prime chain does)

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstring>
 #include "ntt_core.cuh"
+#include "ntt_bal.cuh"
 #include "tables.hpp"
 
 using namespace fhe_b200;
@@ -91,6 +92,68 @@ extern "C" int emul_ntt(uint64_t* data, uint32_t n, uint64_t q, int inverse, int
     if (hb == 16 && all_near60(&q, 1)) return run<16, true>(data, logn, tw, P, inverse);     // what the plan would pick
     if (hb == 16) return run<16, false>(data, logn, tw, P, inverse);
     if (hb == 8) return run<8, false>(data, logn, tw, P, inverse);
+    return -3;
+}
+
+// ---- balanced two-pass bodies (ntt_bal.cuh): pass A per item with a barrier between the rounds, pass B per warp ----
+template <int KA, int HB, bool NEAR>
+static void bal_limb(u64* d, const Twiddle* tw, const LimbParams& P, int inverse) {
+    using A = BalA<KA, HB, NEAR>;
+    using B = BalB<HB, NEAR>;
+    const u32 logn = KA + 8, pairs = 1u << (KA - 1);
+    std::vector<Twiddle> blocks((size_t)pairs * 512);
+    build_bal_tables(tw, logn, blocks.data());
+    std::vector<u64> s(4096), sw(512);
+    std::vector<Twiddle> stw(tw, tw + (1u << KA));          // what the CTA stages
+    if (!inverse) {
+        for (u32 cb = 0; cb < (u32)A::CB; cb++) {
+            u64* g = d + (size_t)cb * A::C;
+            for (u32 t = 0; t < 256; t++) A::fwd_round1(t, g, s.data(), stw.data(), P.q);
+            for (u32 t = 0; t < 256; t++) A::fwd_round2(t, g, s.data(), stw.data(), P.q);
+        }
+        constexpr int B0 = A::fwd_out_bound();
+        for (u32 p = 0; p < pairs; p++) {
+            u64* g = d + (size_t)p * 512;
+            const Twiddle* sb = blocks.data() + (size_t)p * 512;
+            for (u32 l = 0; l < 32; l++) B::template fwd_phase1<B0>(l, g, sw.data(), sb, P.q);
+            for (u32 l = 0; l < 32; l++) B::template fwd_phase2<B0>(l, sw.data(), sb, P.q);
+            for (u32 l = 0; l < 32; l++) B::fwd_phase3(l, g, sw.data());
+        }
+    } else {
+        for (u32 p = 0; p < pairs; p++) {
+            u64* g = d + (size_t)p * 512;
+            const Twiddle* sb = blocks.data() + (size_t)p * 512;
+            for (u32 l = 0; l < 32; l++) B::inv_phase1(l, g, sw.data());
+            for (u32 l = 0; l < 32; l++) B::inv_phase2(l, sw.data(), sb, P);
+            for (u32 l = 0; l < 32; l++) B::inv_phase3(l, g, sw.data(), sb, P);
+        }
+        constexpr int BIN = B::inv_out_bound();
+        for (u32 cb = 0; cb < (u32)A::CB; cb++) {
+            u64* g = d + (size_t)cb * A::C;
+            for (u32 t = 0; t < 256; t++) A::template inv_round2<BIN>(t, g, s.data(), stw.data(), P);
+            for (u32 t = 0; t < 256; t++) A::template inv_round1<BIN>(t, g, s.data(), stw.data(), P);
+        }
+    }
+}
+template <int HB, bool NEAR>
+static int run_bal(u64* d, u32 logn, const Twiddle* tw, const LimbParams& P, int inverse) {
+    switch (logn) {
+        case 13: bal_limb<5, HB, NEAR>(d, tw, P, inverse); return 0;
+        case 14: bal_limb<6, HB, NEAR>(d, tw, P, inverse); return 0;
+        case 15: bal_limb<7, HB, NEAR>(d, tw, P, inverse); return 0;
+        case 16: bal_limb<8, HB, NEAR>(d, tw, P, inverse); return 0;
+    }
+    return -2;
+}
+extern "C" int emul_ntt_bal(uint64_t* data, uint32_t n, uint64_t q, int inverse, int hb) {
+    std::vector<Twiddle> fwd(n), inv(n);
+    LimbParams P;
+    if (build_limb_tables(q, n, fwd.data(), inv.data(), &P)) return -1;
+    const u32 logn = host::ilog2(n);
+    const Twiddle* tw = inverse ? inv.data() : fwd.data();
+    if (hb == 16 && all_near60(&q, 1)) return run_bal<16, true>(data, logn, tw, P, inverse);
+    if (hb == 16) return run_bal<16, false>(data, logn, tw, P, inverse);
+    if (hb == 8) return run_bal<8, false>(data, logn, tw, P, inverse);
     return -3;
 }
 

@@ -17,13 +17,14 @@ EMUL = os.path.join(ROOT, "tests", "emul")
 def emul():
     so = os.path.join(EMUL, "libemul.so")
     srcs = [os.path.join(EMUL, "emul_ntt.cpp"), os.path.join(CSRC, "tables.cpp"), os.path.join(CSRC, "ntt_core.cuh"),
-            os.path.join(CSRC, "modarith.cuh")]
+            os.path.join(CSRC, "modarith.cuh"), os.path.join(CSRC, "ntt_bal.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         # -DFHE_CHECK_BOUNDS: every butterfly asserts its compile-time lazy bound (values < B*q, no 64-bit wrap)
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DFHE_CHECK_BOUNDS", "-I" + CSRC,
                                srcs[0], srcs[1], "-o", so])
     lib = C.CDLL(so)
     lib.emul_ntt.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64, C.c_int, C.c_int]
+    lib.emul_ntt_bal.argtypes = lib.emul_ntt.argtypes
     lib.emul_mul_mod.restype = C.c_uint64
     lib.emul_mul_mod.argtypes = [C.c_uint64] * 3
     lib.emul_barrett128.restype = C.c_uint64
@@ -31,9 +32,10 @@ def emul():
     return lib
 
 
-def _run(lib, a, q, inverse, hb):
+def _run(lib, a, q, inverse, hb, bal=False):
     x = a.copy()
-    assert lib.emul_ntt(x.ctypes.data_as(C.POINTER(C.c_uint64)), x.size, q, inverse, hb) == 0
+    fn = lib.emul_ntt_bal if bal else lib.emul_ntt
+    assert fn(x.ctypes.data_as(C.POINTER(C.c_uint64)), x.size, q, inverse, hb) == 0
     return x
 
 
@@ -49,6 +51,20 @@ def test_kernel_bodies_match_oracle(emul, oracle, chain, logn):
             assert np.array_equal(_run(emul, ref, q, 1, hb), a)
 
 
+@pytest.mark.parametrize("logn", [13, 14, 15, 16])
+def test_balanced_bodies_match_oracle(emul, oracle, chain, logn):
+    """ntt_bal.cuh: pass A (column pass, CTA exchange) + pass B (tile pairs, warp exchange), both directions."""
+    n = 1 << logn
+    p61 = oracle.prime_chain(1, bits=61)[0]
+    small = next(p for p in range(2 * n + 1, 1 << 30, 2 * n) if oracle.is_prime(p))       # far from 2^60: the generic csub path
+    rng = np.random.default_rng(100 + logn)
+    for q, hb in [(chain[0], 16), (chain[7], 8), (p61, 8), (small, 16)]:
+        for a in (rng.integers(0, q, n, dtype=np.uint64), np.full(n, q - 1, dtype=np.uint64)):
+            ref = oracle.ntt_forward(a, q)
+            assert np.array_equal(_run(emul, a, q, 0, hb, bal=True), ref)
+            assert np.array_equal(_run(emul, ref, q, 1, hb, bal=True), a)
+
+
 def test_near60_boundary_prime(emul, oracle):
     """near60_reduce must hold its [0, 2q) promise for the smallest admissible modulus (2^60 - q just under 2^55)."""
     q = (1 << 60) - (1 << 55) + 1
@@ -62,6 +78,9 @@ def test_near60_boundary_prime(emul, oracle):
             ref = oracle.ntt_forward(a, q)
             assert np.array_equal(_run(emul, a, q, 0, 16), ref)
             assert np.array_equal(_run(emul, ref, q, 1, 16), a)
+            if logn == 16:
+                assert np.array_equal(_run(emul, a, q, 0, 16, bal=True), ref)
+                assert np.array_equal(_run(emul, ref, q, 1, 16, bal=True), a)
 
 
 def test_reference_test_primes(emul, oracle):

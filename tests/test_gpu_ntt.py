@@ -42,11 +42,14 @@ def test_forward_inverse_vs_oracle(fhe, oracle, chain, logn, limbs, batch):
     assert np.array_equal(to_host(d), y)          # input untouched
 
 
-@pytest.mark.parametrize("env", [{"FHE_B200_NTT_FUSED": "1"}, {"FHE_B200_NO_NEAR60": "1"}, {"FHE_B200_NTT_CHUNK_MB": "1"},
-                                 {"FHE_B200_NTT_FUSED": "1", "FHE_B200_FUSED_PG": "3", "FHE_B200_FUSED_LBK": "2", "FHE_B200_FUSED_LEAD": "1"}])
+@pytest.mark.parametrize("env", [{"FHE_B200_NTT_BAL": "0"}, {"FHE_B200_NTT_BAL": "0", "FHE_B200_NTT_FUSED": "1"}, {"FHE_B200_NO_NEAR60": "1"},
+                                 {"FHE_B200_NTT_BAL": "0", "FHE_B200_NO_NEAR60": "1"}, {"FHE_B200_NTT_CHUNK_MB": "1"},
+                                 {"FHE_B200_NTT_BAL": "0", "FHE_B200_NTT_CHUNK_MB": "1"},
+                                 {"FHE_B200_NTT_BAL": "0", "FHE_B200_NTT_FUSED": "1", "FHE_B200_FUSED_PG": "3", "FHE_B200_FUSED_LBK": "2", "FHE_B200_FUSED_LEAD": "1"}])
 def test_alternative_code_paths(fhe, oracle, chain, env, monkeypatch):
-    """the two-pass (row kernel + tile kernel) strategy, chunked launches and the generic (non near-2^60) reduction are
-    selected per plan from the environment; they must give the same bits as the default fused / near-2^60 path."""
+    """the row+tile two-pass strategy (FHE_B200_NTT_BAL=0), its fused persistent variant, chunked launches and the generic
+    (non near-2^60) reduction are selected per plan from the environment; they must give the same bits as the default
+    balanced / near-2^60 path."""
     from fhe_b200.engine import to_device, to_host
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -62,9 +65,44 @@ def test_alternative_code_paths(fhe, oracle, chain, env, monkeypatch):
     assert np.array_equal(to_host(d), x)
 
 
+@pytest.mark.parametrize("logn", [13, 14, 15, 16])
+def test_balanced_passes_ragged_batches_and_limb_ranges(fhe, oracle, chain, logn):
+    """ntt_bal: item runs of pass A and polynomial groups of pass B with batches that do not divide evenly, 61-bit and
+    far-from-2^60 moduli (generic reduction), limb sub-ranges, in place and out of place."""
+    from fhe_b200.engine import to_device, to_host
+    n = 1 << logn
+    rng = np.random.default_rng(900 + logn)
+    p61 = oracle.prime_chain(2, bits=61)
+    small = [p for p in range(2 * n + 1, 1 << 24, 2 * n) if oracle.is_prime(p)][:2]
+    for mods, batches in ((chain[:5], (1, 3, 7, 20)), (p61, (2,)), (small + chain[:1], (5,))):
+        plan = fhe.Plan(n, mods)
+        for batch in batches:
+            x = _rand(rng, mods, n, batch)
+            d = to_device(x); out = torch.empty_like(d)
+            plan.forward(d, out=out)
+            y = to_host(out)
+            for b in {0, batch - 1}:
+                for l, q in enumerate(mods):
+                    assert np.array_equal(y[b, l], oracle.ntt_forward(x[b, l], q)), (batch, b, l)
+            plan.inverse(out)                         # in place
+            assert np.array_equal(to_host(out), x)
+    # limb sub-range: buffer limbs map to plan limbs [2, 4)
+    mods = chain[:5]
+    plan = fhe.Plan(n, mods)
+    x = _rand(rng, mods[2:4], n, 3)
+    d = to_device(x)
+    plan.forward(d, limb_begin=2)
+    y = to_host(d)
+    for l, q in enumerate(mods[2:4]):
+        assert np.array_equal(y[1, l], oracle.ntt_forward(x[1, l], q))
+    plan.inverse(d, limb_begin=2)
+    assert np.array_equal(to_host(d), x)
+
+
 def test_fused_scheduler_ragged_groups_and_many_limbs(fhe, oracle, chain, monkeypatch):
     from fhe_b200.engine import to_device, to_host
     monkeypatch.setenv("FHE_B200_NTT_FUSED", "1")
+    monkeypatch.setenv("FHE_B200_NTT_BAL", "0")
     n, mods = 1 << 13, chain[:7]
     rng = np.random.default_rng(78)
     for batch in (1, 3, 8, 9, 17):
