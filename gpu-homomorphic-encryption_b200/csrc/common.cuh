@@ -46,7 +46,7 @@ struct fhe_b200_plan {
     int device = 0;
     int hb = 16;                                   // lazy head-room (16: all q < 2^60, 8: all q < 2^61)
     bool fused = false;                            // N > 4096: single persistent row+tile kernel (FHE_B200_NTT_FUSED=1); default two passes
-    bool near60 = false;                           // every q in [2^60 - 2^55, 2^60): cheap range reduction (near60_reduce)
+    bool near60 = false;                           // every q in (2^60 - 2^32, 2^60): cheap range reduction (near60_reduce)
     std::vector<uint64_t> moduli;
     fhe_b200::Twiddle* d_fwd = nullptr;            // [limbs][n]
     fhe_b200::Twiddle* d_inv = nullptr;            // [limbs][n]

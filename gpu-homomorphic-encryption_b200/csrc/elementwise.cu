@@ -181,7 +181,7 @@ extern "C" int fhe_b200_from_rns_u256(fhe_b200_plan* plan, void* d_u256, const u
     FHE_TRY(check_range(plan, 1, limb_begin, limb_count));
     FHE_REQUIRE(limb_count >= 1 && limb_count <= 4, "from_rns_u256: 1..4 limbs (Q must fit 256 bits)");
     double bits = 0;
-    for (uint32_t a = 0; a < limb_count; a++) bits += (double)plan->h_params[limb_begin + a].qbits;
+    for (uint32_t a = 0; a < limb_count; a++) { double b = 0; for (uint64_t t = plan->h_params[limb_begin + a].q; t; t >>= 1) b++; bits += b; }
     FHE_REQUIRE(bits <= 256, "from_rns_u256: the product of the moduli exceeds 256 bits");
     if (!count) return 0;
     GarnerConsts gc;

@@ -41,7 +41,8 @@ struct alignas(64) LimbParams {
     u64 ninv_s;   // Shoup companion of ninv
     u64 w1ninv;   // inv_tab[1] * N^-1 mod q (last inverse stage, bottom output)
     u64 w1ninv_s; // its Shoup companion
-    u64 qbits;    // bit length of q
+    u64 tq;       // kTQ * q: the offset of the lazy butterfly's difference (from memory, so that the compiler cannot
+                  // rematerialise it as a multiply on the binding pipe)
 };
 
 FHE_HD u64 mulhi64(u64 a, u64 b) {
@@ -103,6 +104,20 @@ FHE_HD void add192(u64& a2, u64& a1, u64& a0, u64 b1, u64 b0) {
 #endif
 }
 
+// A zero the compiler cannot see through (device: a __constant__ word, an immediate operand of IADD3).  ptxas implements a
+// two-input 64-bit addition on whichever pipe its model finds idle, and picks the FMA pipe (IMAD.X) -- the one that binds the
+// butterflies.  A third addend keeps the addition an IADD3/IADD3.X pair on the ALU pipe: add3z(a, b) = a + b + 0.
+#if defined(__CUDACC__)
+static __constant__ u64 kOpaqueZero;          // zero-initialised, never written
+#endif
+FHE_HD u64 add3z(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    return a + b + kOpaqueZero;
+#else
+    return a + b;
+#endif
+}
+
 // x - m if x >= m else x
 FHE_HD u64 csub(u64 x, u64 m) { return x >= m ? x - m : x; }
 
@@ -117,37 +132,40 @@ FHE_HD u64 shoup_mul_lazy(u64 x, u64 w, u64 ws, u64 q) {
 }
 FHE_HD u64 shoup_mul(u64 x, u64 w, u64 ws, u64 q) { return csub(shoup_mul_lazy(x, w, ws, q), q); }
 
-// Shoup multiplication with a three-product quotient estimate: returns x*w mod q + {0,1,2,3} q, a value in [0, 4q),
-// for ANY 64-bit x.  nq = 2^64 - q.
-//   h' = x1*s1 + hi32(x1*s0) + hi32(x0*s1)  is the true hi64(x*ws) minus {0,1,2}  (x = x1:x0, ws = s1:s0), and the true
-//   quotient leaves a remainder in [0, 2q), so  x*w - h'*q  is in [0, 4q).
+// Shoup multiplication with a three-product quotient estimate: returns x*w mod q + {0,1,2} q, a value in [0, 3q), for ANY
+// 64-bit x.  nq = 2^64 - q.
+//   h' = x1*s1 + floor((x1*s0 + x0*s1) / 2^32)   (x = x1:x0, ws = s1:s0; the 65-bit cross sum keeps its carry)
+// is the true hi64(x*ws) minus {0,1} (only hi32(x0*s0) is dropped), and the true quotient leaves a remainder in [0, 2q), so
+// x*w - h'*q is in [0, 3q).  kTQ below is that bound in units of q; every lazy butterfly bound is derived from it.
 // On the B200 integer pipe (measured, tools/microbench2.cu): IMAD.lo issues at 64 lanes/clk/SM, IMAD.WIDE and IMAD.HI at 32.
-// This form needs 3 WIDE + 2 HI + 4 lo = 28 pipe-cycles per warp against 32 for the exact quotient (4 WIDE + ...), and --
-// written as one asm block -- it keeps the carry adds on the ALU pipe instead of IMAD.X / IMAD.MOV on the FMA pipe.
-FHE_HD u64 shoup_mul_lazy4(u64 x, u64 w, u64 ws, u64 nq) {
+// Written so that every 64-bit temporary is a natural register pair produced by IMAD.WIDE: 5 WIDE + 4 lo = 28 pipe-cycles per
+// warp and NOTHING else on the FMA pipe (the earlier form, hi32 products added through a {a,0} pair, cost one register zeroing
+// and one move per butterfly there: 30.4 cycles, ncu sm__pipe_fmaheavy_cycles_active).  Carry adds stay on the ALU pipe.
+constexpr int kTQ = 3;
+FHE_HD u64 shoup_mul_lazy3(u64 x, u64 w, u64 ws, u64 nq) {
 #if defined(__CUDA_ARCH__)
     u64 r;
     asm("{\n\t"
-        ".reg .u32 y0, y1, s0, s1, w0, w1, n0, n1, a, b, h0, h1, t0, t1;\n\t"
-        ".reg .u64 h, t;\n\t"
+        ".reg .u32 y0, y1, s0, s1, w0, w1, n0, n1, c, h0, h1, t0, t1, u0, u1;\n\t"
+        ".reg .u64 h, t, U, V;\n\t"
         "mov.b64 {y0, y1}, %1;\n\t"
         "mov.b64 {w0, w1}, %2;\n\t"
         "mov.b64 {s0, s1}, %3;\n\t"
         "mov.b64 {n0, n1}, %4;\n\t"
-        "mul.hi.u32 a, y1, s0;\n\t"
-        "mul.hi.u32 b, y0, s1;\n\t"
-        "mov.b64 h, {a, 0};\n\t"
-        "mad.wide.u32 h, y1, s1, h;\n\t"
+        "mul.wide.u32 U, y1, s0;\n\t"
+        "mul.wide.u32 V, y0, s1;\n\t"
+        "mul.wide.u32 h, y1, s1;\n\t"
         "mov.b64 {h0, h1}, h;\n\t"
-        "add.cc.u32 h0, h0, b;\n\t"
+        "add.cc.u64 U, U, V;\n\t"
+        "addc.u32 h1, h1, 0;\n\t"
+        "mov.b64 {u0, u1}, U;\n\t"
+        "add.cc.u32 h0, h0, u1;\n\t"
         "addc.u32 h1, h1, 0;\n\t"
         "mul.wide.u32 t, y0, w0;\n\t"
+        "mad.wide.u32 t, h0, n0, t;\n\t"
         "mov.b64 {t0, t1}, t;\n\t"
         "mad.lo.u32 t1, y0, w1, t1;\n\t"
         "mad.lo.u32 t1, y1, w0, t1;\n\t"
-        "mov.b64 t, {t0, t1};\n\t"
-        "mad.wide.u32 t, h0, n0, t;\n\t"
-        "mov.b64 {t0, t1}, t;\n\t"
         "mad.lo.u32 t1, h0, n1, t1;\n\t"
         "mad.lo.u32 t1, h1, n0, t1;\n\t"
         "mov.b64 %0, {t0, t1};\n\t"
@@ -155,7 +173,8 @@ FHE_HD u64 shoup_mul_lazy4(u64 x, u64 w, u64 ws, u64 nq) {
     return r;
 #else
     const u64 x0 = (u32)x, x1 = x >> 32, s0 = (u32)ws, s1 = ws >> 32;
-    const u64 h = x1 * s1 + ((x1 * s0) >> 32) + ((x0 * s1) >> 32);
+    const unsigned __int128 cross = (unsigned __int128)(x1 * s0) + (x0 * s1);
+    const u64 h = x1 * s1 + (u64)(cross >> 32);
     return x * w + h * nq;
 #endif
 }
@@ -175,26 +194,26 @@ FHE_HD u64 barrett128(u64 hi, u64 lo, u64 q, u64 mu_hi, u64 mu_lo) {
     return csub(r, q);
 }
 
-// Range reduction for moduli just below 2^60 (2^60 - q <= 2^55, true for the whole 60-bit prime chain):
-// x < 16q  ->  x - (x >> 60) * q  in [0, 2q).   (k = x >> 60 <= x/q, and the remainder is x mod 2^60 + k (2^60 - q) < 2q.)
-// Three instructions (SHF, IMAD.WIDE, IMAD) instead of the six of a 64-bit compare-and-subtract.  nq = 2^64 - q.
+// Range reduction for moduli just below 2^60 (delta = 2^60 - q < 2^32, true for the whole 60-bit prime chain):
+// x < 16q  ->  (x mod 2^60) + (x >> 60) * delta  =  x - (x >> 60) * q  in [0, 2q).
+// Three instructions (SHF, LOP3, IMAD.WIDE: 4 cycles of the FMA pipe) instead of the six of a 64-bit compare-and-subtract.
+// nq = 2^64 - q, whose low word is delta.
 FHE_HD u64 near60_reduce(u64 x, u64 nq) {
 #if defined(__CUDA_ARCH__)
     u64 r;
     asm("{\n\t"
         ".reg .u32 x0, x1, k, n0, n1;\n\t"
-        ".reg .u64 t;\n\t"
+        ".reg .u64 m;\n\t"
         "mov.b64 {x0, x1}, %1;\n\t"
         "mov.b64 {n0, n1}, %2;\n\t"
         "shr.u32 k, x1, 28;\n\t"
-        "mad.wide.u32 t, k, n0, %1;\n\t"
-        "mov.b64 {x0, x1}, t;\n\t"
-        "mad.lo.u32 x1, k, n1, x1;\n\t"
-        "mov.b64 %0, {x0, x1};\n\t"
+        "and.b32 x1, x1, 0x0fffffff;\n\t"
+        "mov.b64 m, {x0, x1};\n\t"
+        "mad.wide.u32 %0, k, n0, m;\n\t"
         "}" : "=l"(r) : "l"(x), "l"(nq));
     return r;
 #else
-    return x + (x >> 60) * nq;
+    return (x & 0x0fffffffffffffffULL) + (x >> 60) * (u64)(u32)nq;
 #endif
 }
 

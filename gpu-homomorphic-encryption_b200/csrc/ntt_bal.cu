@@ -48,14 +48,15 @@ __global__ void __launch_bounds__(256, 3) bal_a_kernel(const BalArgs a) {
     const uint32_t end = min(items, it + a.m_items);
     constexpr int BIN = BalB<HB, NEAR>::inv_out_bound();
     __syncthreads();
+#pragma unroll 1
     for (uint32_t k = 0; it < end; it++, k ^= 1u) {
         const uint32_t poly = a.b0 + it / A::CB, cb = it % A::CB;
         const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)cb * A::C;
         u64* s = sbuf + k * 4096;
         if (!INV) {
-            A::fwd_round1(tid, a.in + off, s, stw, P.q);
+            A::fwd_round1(tid, a.in + off, s, stw, P);
             __syncthreads();
-            A::fwd_round2(tid, a.out + off, s, stw, P.q);
+            A::fwd_round2(tid, a.out + off, s, stw, P);
         } else {
             A::template inv_round2<BIN>(tid, a.out + off, s, stw, P);
             __syncthreads();
@@ -87,12 +88,13 @@ __global__ void __launch_bounds__(32 * kBalBWarps, 2) bal_b_kernel(const BalArgs
     const size_t poly_stride = (size_t)a.limb_count * a.n;
     constexpr int B0 = BalA<KA, HB, NEAR>::fwd_out_bound();
     mbar_wait(bar, 0);
+#pragma unroll 1
     for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
         const size_t off = poly * poly_stride + limb_off;
         if (!INV) {
-            B::template fwd_phase1<B0>(lane, a.out + off, s, sb, P.q);
+            B::template fwd_phase1<B0>(lane, a.out + off, s, sb, P);
             __syncwarp();
-            B::template fwd_phase2<B0>(lane, s, sb, P.q);
+            B::template fwd_phase2<B0>(lane, s, sb, P);
             __syncwarp();
             B::fwd_phase3(lane, a.out + off, s);
         } else {

@@ -66,20 +66,20 @@ struct BalA {
     // round-2 thread (e1, ct), e1 = (cc << R1) | rh, holds rows rh*16 + rl
     static FHE_HD size_t at2(u32 tid, int rl) { const u32 e1 = tid >> 4; return (size_t)(((e1 & RM) << 4) | (u32)rl) * 256 + ((e1 >> R1) << 4) + (tid & 15); }
 
-    static FHE_HD void fwd_round1(u32 tid, const u64* g, u64* s, const Twiddle* stw, u64 q) {
+    static FHE_HD void fwd_round1(u32 tid, const u64* g, u64* s, const Twiddle* stw, const LimbParams& P) {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = ldg1(g + at1(tid, e));
-        fwd_stages<4, R1, HB, NEAR, 1>(x, TwA1{stw}, q);
+        fwd_stages<4, R1, HB, NEAR, 1>(x, TwA1{stw}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[(e << 8) | tid] = x[e];
     }
-    static FHE_HD void fwd_round2(u32 tid, u64* g, const u64* s, const Twiddle* stw, u64 q) {
+    static FHE_HD void fwd_round2(u32 tid, u64* g, const u64* s, const Twiddle* stw, const LimbParams& P) {
         u64 x[16];
         const u32 e1 = tid >> 4, ct = tid & 15;
 #pragma unroll
         for (int rl = 0; rl < 16; rl++) x[rl] = s[(e1 << 8) | (rl << 4) | ct];
-        fwd_stages<4, 4, HB, NEAR, fwd_bound_after(1, R1, HB, NEAR)>(x, TwA2{stw, (1u << R1) + (e1 & RM)}, q);
+        fwd_stages<4, 4, HB, NEAR, fwd_bound_after(1, R1, HB, NEAR)>(x, TwA2{stw, (1u << R1) + (e1 & RM)}, P);
 #pragma unroll
         for (int rl = 0; rl < 16; rl++) g[at2(tid, rl)] = x[rl];
     }
@@ -102,7 +102,7 @@ struct BalA {
         for (int e = 0; e < 16; e++) x[e] = s[(e << 8) | tid];
         inv_stages<4, R1, HB, NEAR, true, inv_bound_after(BIN, 4, HB, NEAR)>(x, TwA1{stw}, P);
 #pragma unroll
-        for (int e = 0; e < 16; e++) g[at1(tid, e)] = normalize<HB, NEAR, 4>(x[e], P.q);
+        for (int e = 0; e < 16; e++) g[at1(tid, e)] = normalize<HB, NEAR, kTQ>(x[e], P.q);
     }
 };
 
@@ -117,24 +117,25 @@ struct BalB {
 
     // ---- forward: B0 = bound left by pass A
     template <int B0>
-    static FHE_HD void fwd_phase1(u32 lane, const u64* g, u64* s, const Twiddle* sb, u64 q) {
+    static FHE_HD void fwd_phase1(u32 lane, const u64* g, u64* s, const Twiddle* sb, const LimbParams& P) {
         const u32 t = lane >> 4, j = lane & 15;
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = ldg1(g + ((t << 8) | (e << 4) | j));
-        fwd_stages<4, 4, HB, NEAR, B0>(x, TwB1{sb + t * 16}, q);
+        fwd_stages<4, 4, HB, NEAR, B0>(x, TwB1{sb + t * 16}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz((t << 8) | (e << 4) | j)] = x[e];
     }
     template <int B0>
-    static FHE_HD void fwd_phase2(u32 lane, u64* s, const Twiddle* sb, u64 q) {
+    static FHE_HD void fwd_phase2(u32 lane, u64* s, const Twiddle* sb, const LimbParams& P) {
         u64 x[16];
+        const u64 q = P.q;
         const u32 row = lane << 4;
 #pragma unroll
         for (int k = 0; k < 8; k++) ld2(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
         constexpr int B1 = fwd_bound_after(B0, 4, HB, NEAR);
         constexpr int BE = fwd_bound_after(B1, 4, HB, NEAR);
-        fwd_stages<4, 4, HB, NEAR, B1>(x, TwB2{sb, lane}, q);
+        fwd_stages<4, 4, HB, NEAR, B1>(x, TwB2{sb, lane}, P);
 #pragma unroll
         for (int k = 0; k < 8; k++)
             st2(s + (row | ((k ^ (lane & 7)) << 1)), normalize<HB, NEAR, BE>(x[2 * k], q), normalize<HB, NEAR, BE>(x[2 * k + 1], q));

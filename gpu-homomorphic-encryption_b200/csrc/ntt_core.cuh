@@ -17,9 +17,9 @@
 //
 // Lazy arithmetic: values live in [0, B*q) with the bound B tracked at compile time (template recursion over the
 // stages).  HB = largest power of two with HB*q_max <= 2^64 is the head-room (16 for q < 2^60, 8 for q < 2^61).
-// The twiddle product T = shoup_mul_lazy4(.) lies in [0, 4q) for any 64-bit input.
-//   forward (CT):  X' = X + T, Y' = X + 4q - T: the bound grows by 4 per stage; X gets one conditional subtraction of
-//                  (HB/2) q only in the stages where B + 4 would exceed HB.
+// The twiddle product T = shoup_mul_lazy3(.) lies in [0, kTQ q) = [0, 3q) for any 64-bit input.
+//   forward (CT):  X' = X + T, Y' = X + 3q - T: the bound grows by 3 per stage; X gets one range reduction only in the
+//                  stages where B + 3 would exceed HB.
 //   inverse (GS):  S = X + Y, Y' = T(X + Bq - Y): the sum bound doubles; S gets one conditional subtraction of B q once
 //                  doubling again would overflow (steady state B = HB/2).
 // The conditional subtractions run on the ALU pipe, which has slack; the FMA pipe (IMAD) is the binding one.
@@ -90,16 +90,16 @@ FHE_HD void ldg2(const u64* p, u64& a, u64& b) {
 #endif
 }
 
-// bounds in units of q; the twiddle product is lazy in [0, 4q) (shoup_mul_lazy4).
-// NEAR: every modulus q satisfies 2^60 - 2^55 <= q < 2^60, so near60_reduce brings anything below 16q under 2q.
+// bounds in units of q; the twiddle product is lazy in [0, kTQ q) (shoup_mul_lazy3).
+// NEAR: every modulus q satisfies 2^60 - 2^32 < q < 2^60, so near60_reduce brings anything below 16q under 2q.
 FHE_HDC int red_to(int HB, bool NEAR) { return NEAR ? 2 : HB / 2; }
 FHE_HDC int fwd_bound_after(int B, int stages, int HB, bool NEAR) {
-    for (int i = 0; i < stages; i++) { if (B + 4 > HB) B = red_to(HB, NEAR); B += 4; }
+    for (int i = 0; i < stages; i++) { if (B + kTQ > HB) B = red_to(HB, NEAR); B += kTQ; }
     return B;
 }
 FHE_HDC int inv_bound_step(int B, int HB, bool NEAR) {
-    int nb = 2 * B > 4 ? 2 * B : 4;
-    if (2 * nb > HB) { const int r = NEAR ? 2 : nb / 2; nb = r > 4 ? r : 4; }
+    int nb = 2 * B > kTQ ? 2 * B : kTQ;
+    if (2 * nb > HB) { const int r = NEAR ? 2 : nb / 2; nb = r > kTQ ? r : kTQ; }
     return nb;
 }
 FHE_HDC int inv_bound_after(int B, int stages, int HB, bool NEAR) {
@@ -148,12 +148,12 @@ FHE_HDC int p3_entries(int LB) { return (1 << (LB - 4)) * (16 - (1 << (12 - LB))
 // B (template) is the bound on entry in units of q; the bound on exit is fwd_bound_after(B, R, HB).
 // Compile-time recursion over the stage index V keeps every array index and every bound a constant.
 template <int LE, int R, int HB, bool NEAR, int B, class TW, int V = 0>
-FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, u64 q) {
+FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
     if constexpr (V < R) {
         constexpr int st = 1 << (R - 1 - V);
         constexpr int sh = LE - R + V;
-        constexpr bool red = (B + 4 > HB);
-        const u64 fourq = 4 * q, nq = 0 - q;
+        constexpr bool red = (B + kTQ > HB);
+        const u64 q = P.q, tq = P.tq, nq = 0 - q;
         const u64 hq = (u64)(HB / 2) * q;
 #pragma unroll
         for (int key = 0; key < (1 << sh); key++) {
@@ -164,29 +164,29 @@ FHE_HD void fwd_stages(u64 (&x)[1 << LE], const TW& tw, u64 q) {
                 u64 X = x[e];
                 FHE_BOUND(X, B, q); FHE_BOUND(x[e + st], B, q);
                 if (red) X = NEAR ? near60_reduce(X, nq) : csub(X, hq);
-                const u64 T = shoup_mul_lazy4(x[e + st], w.w, w.ws, nq);
-                FHE_BOUND(T, 4, q); FHE_BOUND((unsigned __int128)X + T, (red ? red_to(HB, NEAR) : B) + 4, q);
-                x[e] = X + T;
-                x[e + st] = X + fourq - T;
+                const u64 T = shoup_mul_lazy3(x[e + st], w.w, w.ws, nq);
+                FHE_BOUND(T, kTQ, q); FHE_BOUND((unsigned __int128)X + T, (red ? red_to(HB, NEAR) : B) + kTQ, q);
+                x[e] = add3z(X, T);
+                x[e + st] = X + tq - T;
             }
         }
-        fwd_stages<LE, R, HB, NEAR, (red ? red_to(HB, NEAR) : B) + 4, TW, V + 1>(x, tw, q);
+        fwd_stages<LE, R, HB, NEAR, (red ? red_to(HB, NEAR) : B) + kTQ, TW, V + 1>(x, tw, P);
     }
 }
 
 // ---- inverse stages (mirror order: V runs R-1 .. 0).  LAST: the final stage of the whole transform folds N^-1 in.
-// exit bound: inv_bound_after(B, R, HB), or 4 when LAST.
+// exit bound: inv_bound_after(B, R, HB), or kTQ when LAST.
 template <int LE, int R, int HB, bool NEAR, bool LAST, int B, class TW, int V = R - 1>
 FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
     if constexpr (V >= 0) {
         constexpr int st = 1 << (R - 1 - V);
         constexpr int sh = LE - R + V;
         constexpr bool last = LAST && (V == 0);
-        constexpr int SB = 2 * B > 4 ? 2 * B : 4;            // bound after this stage before any reduction
+        constexpr int SB = 2 * B > kTQ ? 2 * B : kTQ;          // bound after this stage before any reduction
         constexpr bool red = !last && (2 * SB > HB);           // reduce the sums so that the next stage cannot overflow
         static_assert(2 * B <= HB, "inverse stage would overflow 64 bits");
         const u64 q = P.q, nq = 0 - q;
-        const u64 bq = (u64)B * q;
+        const u64 bq = (B % kTQ == 0) ? (u64)(B / kTQ) * P.tq : (u64)B * q;      // multiples of 3q from the loaded 3q (no multiply by 3 in the loop)
 #pragma unroll
         for (int key = 0; key < (1 << sh); key++) {
             Twiddle w;
@@ -197,12 +197,12 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
                 const int e = (key << (R - V)) | j;
                 const u64 X = x[e], Y = x[e + st];
                 FHE_BOUND(X, B, q); FHE_BOUND(Y, B, q); FHE_BOUND((unsigned __int128)X + Y, HB, q);
-                u64 S = X + Y;
+                u64 S = add3z(X, Y);
                 const u64 D = X + bq - Y;
-                if (last) S = shoup_mul_lazy4(S, P.ninv, P.ninv_s, nq);
+                if (last) S = shoup_mul_lazy3(S, P.ninv, P.ninv_s, nq);
                 else if (red) S = NEAR ? near60_reduce(S, nq) : csub(S, bq);
                 x[e] = S;
-                x[e + st] = shoup_mul_lazy4(D, w.w, w.ws, nq);
+                x[e + st] = shoup_mul_lazy3(D, w.w, w.ws, nq);
             }
         }
         inv_stages<LE, R, HB, NEAR, LAST, inv_bound_step(B, HB, NEAR), TW, V - 1>(x, tw, P);
@@ -241,31 +241,32 @@ struct TileFwd {
         for (int e = 0; e < 16; e++) x[e] = ldg1(g + ((e << (LB - 4)) | tid));
     }
     template <int B0>
-    static FHE_HD void phase1_compute(u32 tid, u64 (&x)[16], u64* s, const Twiddle* s12, u64 q) {
-        fwd_stages<4, 4, HB, NEAR, B0>(x, TwP1{s12}, q);
+    static FHE_HD void phase1_compute(u32 tid, u64 (&x)[16], u64* s, const Twiddle* s12, const LimbParams& P) {
+        fwd_stages<4, 4, HB, NEAR, B0>(x, TwP1{s12}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz((e << (LB - 4)) | tid)] = x[e];
     }
     template <int B0>
-    static FHE_HD void phase1(u32 tid, const u64* g, u64* s, const Twiddle* s12, u64 q) {
+    static FHE_HD void phase1(u32 tid, const u64* g, u64* s, const Twiddle* s12, const LimbParams& P) {
         u64 x[16];
         phase1_load(tid, g, x);
-        phase1_compute<B0>(tid, x, s, s12, q);
+        phase1_compute<B0>(tid, x, s, s12, P);
     }
     template <int B0>
-    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* s12, u64 q) {
+    static FHE_HD void phase2(u32 tid, u64* s, const Twiddle* s12, const LimbParams& P) {
         const u32 lo = tid & ((1u << (LB - 8)) - 1), hi = tid >> (LB - 8);
         const u32 base = (hi << (LB - 4)) | lo;
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz(base | (e << (LB - 8)))];
-        fwd_stages<4, 4, HB, NEAR, fwd_bound_after(B0, 4, HB, NEAR)>(x, TwP2{s12, hi}, q);
+        fwd_stages<4, 4, HB, NEAR, fwd_bound_after(B0, 4, HB, NEAR)>(x, TwP2{s12, hi}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz(base | (e << (LB - 8)))] = x[e];
     }
     template <int B0>
-    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* s3, u64 q) {
+    static FHE_HD void phase3(u32 tid, u64* s, const Twiddle* s3, const LimbParams& P) {
         u64 x[16];
+        const u64 q = P.q;
         const u32 row = tid << 4;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -274,7 +275,7 @@ struct TileFwd {
         }
         constexpr int B3 = fwd_bound_after(B0, 8, HB, NEAR);
         constexpr int BE = fwd_bound_after(B3, R3, HB, NEAR);
-        fwd_stages<4, R3, HB, NEAR, B3>(x, TwP3<NT, R3>{s3, tid}, q);
+        fwd_stages<4, R3, HB, NEAR, B3>(x, TwP3<NT, R3>{s3, tid}, P);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const u32 a = row | ((k ^ (tid & 7)) << 1);
@@ -345,7 +346,7 @@ struct TileInv {
         inv_stages<4, 4, HB, NEAR, LAST, inv_bound_after(1, R3 + 4, HB, NEAR)>(x, TwP1{s12}, P);
         // LAST: fully reduce.  Otherwise leave the lazy bound for pass A' (it starts from out_bound()).
 #pragma unroll
-        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize<HB, NEAR, 4>(x[e], P.q) : x[e];
+        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize<HB, NEAR, kTQ>(x[e], P.q) : x[e];
     }
     template <bool LAST>
     static FHE_HD void phase4(u32 tid, u64* g, const u64* s, const Twiddle* s12, const LimbParams& P) {
@@ -365,7 +366,7 @@ struct RowPass {
     static constexpr int NA = 1 << K1;
     static constexpr int NB = 1 << LB;
 
-    static FHE_HD void forward(u64* gout, const u64* gin, u32 col, const Twiddle* tw, u64 q) {
+    static FHE_HD void forward(u64* gout, const u64* gin, u32 col, const Twiddle* tw, const LimbParams& P) {
         u64 x[V][NA];
 #pragma unroll
         for (int r = 0; r < NA; r++) {
@@ -373,7 +374,7 @@ struct RowPass {
             else x[0][r] = ldg1(gin + (size_t)r * NB + col);
         }
 #pragma unroll
-        for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, NEAR, 1>(x[c], TwGlobal<0>{tw, 1u}, q);
+        for (int c = 0; c < V; c++) fwd_stages<K1, K1, HB, NEAR, 1>(x[c], TwGlobal<0>{tw, 1u}, P);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
             if (V == 2) st2(gout + (size_t)r * NB + col, x[0][r], x[V - 1][r]);
@@ -394,8 +395,8 @@ struct RowPass {
         for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, NEAR, true, B0>(x[c], TwGlobal<0>{tw, 1u}, P);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
-            if (V == 2) st2(g + (size_t)r * NB + col, normalize<HB, NEAR, 4>(x[0][r], P.q), normalize<HB, NEAR, 4>(x[V - 1][r], P.q));
-            else g[(size_t)r * NB + col] = normalize<HB, NEAR, 4>(x[0][r], P.q);
+            if (V == 2) st2(g + (size_t)r * NB + col, normalize<HB, NEAR, kTQ>(x[0][r], P.q), normalize<HB, NEAR, kTQ>(x[V - 1][r], P.q));
+            else g[(size_t)r * NB + col] = normalize<HB, NEAR, kTQ>(x[0][r], P.q);
         }
     }
 };

@@ -111,7 +111,7 @@ __device__ __forceinline__ void tile_fwd_item(const NttArgs& a, unsigned char* r
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t tid = threadIdx.x;
     stage_twiddles<LB>(a, raw, pl, tile);
-    const u64 q = a.params[pl].q;
+    const LimbParams P = a.params[pl];
     constexpr int B0 = fwd_bound_after(1, K1, HB, NEAR);
     const u64* base_in = (K1 > 0 ? a.out : a.in);             // K1 > 0: the row pass already moved the data to `out`
     const size_t limb_off = (size_t)limb * a.n + (size_t)tile * T::NB;
@@ -121,11 +121,11 @@ __device__ __forceinline__ void tile_fwd_item(const NttArgs& a, unsigned char* r
     mbar_wait(SM::bar(raw), parity);                          // staged twiddles have landed
     for (; poly < poly_end; poly += step) {
         const size_t off = poly * poly_stride + limb_off;
-        T::template phase1_compute<B0>(tid, x, s, s12, q);
+        T::template phase1_compute<B0>(tid, x, s, s12, P);
         __syncthreads();
-        T::template phase2<B0>(tid, s, s12, q);
+        T::template phase2<B0>(tid, s, s12, P);
         __syncthreads();
-        T::template phase3<B0>(tid, s, s3, q);
+        T::template phase3<B0>(tid, s, s3, P);
         __syncthreads();
         // software pipeline: the next polynomial's global loads fly while this one is copied out
         const uint32_t next = poly + step;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void row_fwd_item(const NttArgs& a, uint32_t limb, ui
     const size_t off = ((size_t)poly * a.limb_count + limb) * a.n;
     const uint32_t pl = a.limb_begin + limb;
     const uint32_t col = (cb * kRowThreads + threadIdx.x) * V;
-    RowPass<K1, V, LB, HB, NEAR>::forward(a.out + off, a.in + off, col, a.tw + (size_t)pl * a.n, a.params[pl].q);
+    RowPass<K1, V, LB, HB, NEAR>::forward(a.out + off, a.in + off, col, a.tw + (size_t)pl * a.n, a.params[pl]);
 }
 template <int LB, int K1, int HB, bool NEAR, int V>
 __device__ __forceinline__ void row_inv_item(const NttArgs& a, uint32_t limb, uint32_t poly, uint32_t cb) {

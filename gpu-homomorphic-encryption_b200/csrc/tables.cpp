@@ -22,8 +22,7 @@ int build_limb_tables(uint64_t q, uint32_t n, Twiddle* fwd, Twiddle* inv, LimbPa
     P->ninv_s = shoup(P->ninv, q);
     P->w1ninv = mulmod(inv[1].w, P->ninv, q);
     P->w1ninv_s = shoup(P->w1ninv, q);
-    u64 bits = 0; for (u64 t = q; t; t >>= 1) bits++;
-    P->qbits = bits;
+    P->tq = (u64)kTQ * q;
     return 0;
 }
 
@@ -80,7 +79,7 @@ int lazy_headroom(const uint64_t* moduli, uint32_t count) {
 
 bool all_near60(const uint64_t* moduli, uint32_t count) {
     for (uint32_t i = 0; i < count; i++)
-        if ((moduli[i] >> 60) != 0 || moduli[i] < (1ull << 60) - (1ull << 55)) return false;
+        if ((moduli[i] >> 60) != 0 || moduli[i] <= (1ull << 60) - (1ull << 32)) return false;
     return true;
 }
 

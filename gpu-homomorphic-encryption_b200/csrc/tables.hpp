@@ -21,7 +21,7 @@ size_t tile_p3_entries(uint32_t logn);
 void build_bal_tables(const Twiddle* main, uint32_t logn, Twiddle* out);
 // head-room of the lazy butterflies for a set of moduli: 16 if all < 2^60, else 8 (all < 2^61)
 int lazy_headroom(const uint64_t* moduli, uint32_t count);
-// true when every modulus lies in [2^60 - 2^55, 2^60) (the whole deterministic 60-bit prime chain does)
+// true when every modulus lies in (2^60 - 2^32, 2^60) (the whole deterministic 60-bit prime chain does)
 bool all_near60(const uint64_t* moduli, uint32_t count);
 
 }  // namespace fhe_b200

@@ -25,7 +25,7 @@ static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
     constexpr int NB = 1 << LB;
     if constexpr (K1 > 0) {
         constexpr int V = (K1 >= 5) ? 1 : 2;
-        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB, NEAR>::forward(d, d, col, tw, P.q);
+        for (u32 col = 0; col < (u32)NB; col += V) RowPass<K1, V, LB, HB, NEAR>::forward(d, d, col, tw, P);
     }
     constexpr int B0 = fwd_bound_after(1, K1, HB, NEAR);
     const TileTabs tt = tile_tabs(tw, LB + K1);
@@ -36,9 +36,9 @@ static void fwd_limb(u64* d, const Twiddle* tw, const LimbParams& P) {
         // what the kernel's two bulk copies stage into shared memory
         std::vector<Twiddle> s12(tt.p12.begin() + (size_t)b * 256, tt.p12.begin() + (size_t)(b + 1) * 256);
         std::vector<Twiddle> s3(tt.p3.begin() + (size_t)b * tt.p3n, tt.p3.begin() + (size_t)(b + 1) * tt.p3n);
-        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase1<B0>(t, g, s.data(), s12.data(), P.q);
-        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase2<B0>(t, s.data(), s12.data(), P.q);
-        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase3<B0>(t, s.data(), s3.data(), P.q);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase1<B0>(t, g, s.data(), s12.data(), P);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase2<B0>(t, s.data(), s12.data(), P);
+        for (u32 t = 0; t < (u32)T::NT; t++) T::template phase3<B0>(t, s.data(), s3.data(), P);
         for (u32 t = 0; t < (u32)T::NT; t++) T::phase4(t, g, s.data());
     }
 }
@@ -108,15 +108,15 @@ static void bal_limb(u64* d, const Twiddle* tw, const LimbParams& P, int inverse
     if (!inverse) {
         for (u32 cb = 0; cb < (u32)A::CB; cb++) {
             u64* g = d + (size_t)cb * A::C;
-            for (u32 t = 0; t < 256; t++) A::fwd_round1(t, g, s.data(), stw.data(), P.q);
-            for (u32 t = 0; t < 256; t++) A::fwd_round2(t, g, s.data(), stw.data(), P.q);
+            for (u32 t = 0; t < 256; t++) A::fwd_round1(t, g, s.data(), stw.data(), P);
+            for (u32 t = 0; t < 256; t++) A::fwd_round2(t, g, s.data(), stw.data(), P);
         }
         constexpr int B0 = A::fwd_out_bound();
         for (u32 p = 0; p < pairs; p++) {
             u64* g = d + (size_t)p * 512;
             const Twiddle* sb = blocks.data() + (size_t)p * 512;
-            for (u32 l = 0; l < 32; l++) B::template fwd_phase1<B0>(l, g, sw.data(), sb, P.q);
-            for (u32 l = 0; l < 32; l++) B::template fwd_phase2<B0>(l, sw.data(), sb, P.q);
+            for (u32 l = 0; l < 32; l++) B::template fwd_phase1<B0>(l, g, sw.data(), sb, P);
+            for (u32 l = 0; l < 32; l++) B::template fwd_phase2<B0>(l, sw.data(), sb, P);
             for (u32 l = 0; l < 32; l++) B::fwd_phase3(l, g, sw.data());
         }
     } else {

@@ -66,11 +66,12 @@ def test_balanced_bodies_match_oracle(emul, oracle, chain, logn):
 
 
 def test_near60_boundary_prime(emul, oracle):
-    """near60_reduce must hold its [0, 2q) promise for the smallest admissible modulus (2^60 - q just under 2^55)."""
-    q = (1 << 60) - (1 << 55) + 1
+    """near60_reduce must hold its [0, 2q) promise for the smallest admissible modulus (2^60 - q just under 2^32), and the
+    first prime below that window must take the generic path."""
+    q = (1 << 60) - (1 << 32) + 1
     while not (oracle.is_prime(q) and q % (1 << 18) == 1):
         q += 1 << 18
-    assert (1 << 60) - (1 << 55) <= q < (1 << 60)
+    assert (1 << 60) - (1 << 32) < q < (1 << 60)
     for logn in (12, 16):
         n = 1 << logn
         rng = np.random.default_rng(5)
@@ -81,6 +82,16 @@ def test_near60_boundary_prime(emul, oracle):
             if logn == 16:
                 assert np.array_equal(_run(emul, a, q, 0, 16, bal=True), ref)
                 assert np.array_equal(_run(emul, ref, q, 1, 16, bal=True), a)
+    # just outside the window (2^60 - 2^32 - something): the emulator, like the plan, must select the generic reduction
+    q2 = (1 << 60) - (1 << 32) - (1 << 18) + 1
+    while not (oracle.is_prime(q2) and q2 % (1 << 18) == 1):
+        q2 -= 1 << 18
+    n = 1 << 13
+    a = np.full(n, q2 - 1, dtype=np.uint64)
+    ref = oracle.ntt_forward(a, q2)
+    for bal in (False, True):
+        assert np.array_equal(_run(emul, a, q2, 0, 16, bal=bal), ref)
+        assert np.array_equal(_run(emul, ref, q2, 1, 16, bal=bal), a)
 
 
 def test_reference_test_primes(emul, oracle):
