@@ -88,11 +88,15 @@ __global__ void __launch_bounds__(32 * kBalBWarps, 2) bal_b_kernel(const BalArgs
     const size_t poly_stride = (size_t)a.limb_count * a.n;
     constexpr int B0 = BalA<KA, HB, NEAR>::fwd_out_bound();
     mbar_wait(bar, 0);
+    // (issuing a polynomial's global loads early -- before the wait, or before the previous copy-out -- was measured slower:
+    //  0.701 ms against 0.646 ms per forward pass at config 3; the 16 live values cost more than the latency they hide)
 #pragma unroll 1
     for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
         const size_t off = poly * poly_stride + limb_off;
         if (!INV) {
-            B::template fwd_phase1<B0>(lane, a.out + off, s, sb, P);
+            u64 x[16];
+            B::fwd_load(lane, a.out + off, x);
+            B::template fwd_phase1<B0>(lane, x, s, sb, P);
             __syncwarp();
             B::template fwd_phase2<B0>(lane, s, sb, P);
             __syncwarp();
@@ -122,17 +126,22 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
     }
     const uint32_t sms = (uint32_t)plan->sm_count;
     const uint64_t pls = (uint64_t)a.nl * a.nb;
-    // pass A: items per CTA so that the grid keeps >= ~12 CTAs per SM when the batch allows it (at most 8 items per CTA)
+    // pass A: one item per CTA (measured at config 3: 1 item 0.590 ms, 2 items 0.653 ms, 8 items 0.684 ms per forward pass --
+    // the hardware CTA scheduler overlaps the load, compute and store phases of neighbouring items better than a loop does)
     const uint32_t items_per_limb = a.nb * A::CB;
-    uint32_t m = (uint32_t)(((uint64_t)a.nl * items_per_limb) / (12u * sms));
-    m = m < 1 ? 1 : (m > 8 ? 8 : m);
+    uint32_t m = 1;
+    static const int env_m = getenv("FHE_B200_BAL_M") ? atoi(getenv("FHE_B200_BAL_M")) : 0;          // experiments
+    if (env_m > 0) m = (uint32_t)env_m;
     a.m_items = m;
     a.ctas_per_limb = (items_per_limb + m - 1) / m;
     const uint32_t grid_a = a.nl * a.ctas_per_limb;
-    // pass B: one warp per (limb, tile pair, group); >= ~8 CTAs per SM when the batch allows it
+    // pass B: one warp per (limb, tile pair, group).  Few groups = many polynomials per staged twiddle block (measured at
+    // config 3: 2 groups 0.646 ms, 3 groups 0.669 ms, 8 groups 0.657 ms, 1 group 0.740 ms (under two waves)): aim at three waves
     constexpr uint32_t pairs = 1u << (KA - 1);
     const uint32_t lp = a.nl * pairs;
-    uint32_t groups = (8u * sms * kBalBWarps + lp - 1) / lp;
+    uint32_t groups = (3u * 2u * sms * kBalBWarps + lp - 1) / lp;
+    static const int env_g = getenv("FHE_B200_BAL_GROUPS") ? atoi(getenv("FHE_B200_BAL_GROUPS")) : 0;
+    if (env_g > 0) groups = (uint32_t)env_g;
     groups = groups < 1 ? 1 : (groups > a.nb ? a.nb : groups);
     a.groups = groups;
     const uint32_t grid_b = lp * groups / kBalBWarps;

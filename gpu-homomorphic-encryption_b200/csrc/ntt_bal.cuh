@@ -116,12 +116,16 @@ struct BalB {
     static FHE_HD u32 chunk_pos(u32 c) { return ((c >> 3) << 3) | ((c & 7) ^ ((c >> 3) & 7)); }
 
     // ---- forward: B0 = bound left by pass A
-    template <int B0>
-    static FHE_HD void fwd_phase1(u32 lane, const u64* g, u64* s, const Twiddle* sb, const LimbParams& P) {
+    // phase 1 is split so that the kernel can issue the global loads early (before the staged twiddles have landed, and for
+    // the next polynomial while the current one is copied out)
+    static FHE_HD void fwd_load(u32 lane, const u64* g, u64 (&x)[16]) {
         const u32 t = lane >> 4, j = lane & 15;
-        u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = ldg1(g + ((t << 8) | (e << 4) | j));
+    }
+    template <int B0>
+    static FHE_HD void fwd_phase1(u32 lane, u64 (&x)[16], u64* s, const Twiddle* sb, const LimbParams& P) {
+        const u32 t = lane >> 4, j = lane & 15;
         fwd_stages<4, 4, HB, NEAR, B0>(x, TwB1{sb + t * 16}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz((t << 8) | (e << 4) | j)] = x[e];

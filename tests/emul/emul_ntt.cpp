@@ -115,7 +115,7 @@ static void bal_limb(u64* d, const Twiddle* tw, const LimbParams& P, int inverse
         for (u32 p = 0; p < pairs; p++) {
             u64* g = d + (size_t)p * 512;
             const Twiddle* sb = blocks.data() + (size_t)p * 512;
-            for (u32 l = 0; l < 32; l++) B::template fwd_phase1<B0>(l, g, sw.data(), sb, P);
+            for (u32 l = 0; l < 32; l++) { u64 x[16]; B::fwd_load(l, g, x); B::template fwd_phase1<B0>(l, x, sw.data(), sb, P); }
             for (u32 l = 0; l < 32; l++) B::template fwd_phase2<B0>(l, sw.data(), sb, P);
             for (u32 l = 0; l < 32; l++) B::fwd_phase3(l, g, sw.data());
         }
