@@ -262,17 +262,22 @@ def run_ours(args, rank, local_rank, world):
         peak, peak_src = measured_peaks()
         value = world * UNITS_PER_STEP * args.steps / (ms_max / 1e3)
         e2e_val = world * UNITS_PER_STEP * e2e_steps / (e2e_ms_max / 1e3)
-        # dominant kernel = the tile pass (12 of the 16 stages)
-        tl = kinds["tile_fwd"][0] + kinds["tile_inv"][0]
-        tms = kinds["tile_fwd"][1] + kinds["tile_inv"][1]
-        tu = kinds["tile_fwd"][2] + kinds["tile_inv"][2]
+        # N = 2^16 runs as two balanced passes per direction (8 stages each; ntt_bal.cu): every launch reads and writes each limb
+        # once, i.e. moves the algorithmic 1 MiB per limb-transform it covers.  The dominant kernel is the slowest of the four.
+        names = {"tile_fwd": "bal_b_kernel<8,16,near,fwd> (tile-pair pass)", "tile_inv": "bal_b_kernel<8,16,near,inv> (tile-pair pass)",
+                 "row_fwd": "bal_a_kernel<8,16,near,fwd> (column pass)", "row_inv": "bal_a_kernel<8,16,near,inv> (column pass)"}
+        if os.environ.get("FHE_B200_NTT_BAL", "1") == "0":
+            names = {"tile_fwd": "ntt_tile_fwd_kernel<12,4,16>", "tile_inv": "ntt_tile_inv_kernel<12,4,16>",
+                     "row_fwd": "ntt_row_fwd_kernel<12,4,16>", "row_inv": "ntt_row_inv_kernel<12,4,16>"}
+        dom = max(kinds, key=lambda k: kinds[k][1])
+        tl, tms, tu = kinds[dom]
         all_ms = sum(v[1] for v in kinds.values())
         achieved = (tu * UNIT_BYTES / 1e9) / (tms / 1e3) if tms > 0 else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("tile_pass_dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch", {}).get(dom)
             except Exception:
                 traffic = None
         line = {
@@ -292,7 +297,7 @@ def run_ours(args, rank, local_rank, world):
                     "api": "fhe_b200_ntt_host (pinned host buffer, 3-stream chunk pipeline)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "ntt_tile_{fwd,inv}_kernel<12,4,16>", "peak_source": peak_src,
+                         "kernel": names[dom], "peak_source": peak_src,
                          "launches_profiled": tl, "avg_launch_ms": (tms / tl) if tl else None,
                          "units_per_launch": (tu / tl) if tl else None, "bytes_per_unit": UNIT_BYTES,
                          "kernel_share_of_step": (tms / all_ms) if all_ms else None,
@@ -301,7 +306,7 @@ def run_ours(args, rank, local_rank, world):
                          "per_kernel_ms": {k: v[1] / psteps for k, v in kinds.items()}},
         }
         # integer-pipe roofline (the binding one): 28 FMA-pipe cycles per warp-butterfly
-        # (3 IMAD.WIDE + 2 IMAD.HI at 4 cycles, 4 IMAD.lo at 2 cycles per warp instruction per SM sub-partition; measured by
+        # (5 IMAD.WIDE at 4 cycles, 4 IMAD.lo at 2 cycles per warp instruction per SM sub-partition; measured by
         # tools/microbench2.cu), 4 sub-partitions per SM, at the SM clock sampled during the timed region
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         peak_bfly = 148 * 4 * 32 * sm_mhz * 1e6 / 28.0
