@@ -200,6 +200,13 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     a.use_pre = lc->use_pre; a.use_extra = lc->use_extra; a.c_is_one = lc->use_pre ? 0 : 1;
     a.k_per_block = lc->T;
     a.total = (size_t)batch * n;
+    if (lc->use_mma) {
+        const bool prof = profile_on();
+        if (prof) profile_begin(4, (uint64_t)batch * lc->S * lc->T, st);
+        const int rc = lincomb_mma_launch(lc, a.v, n, batch, st);
+        if (prof) profile_end(st);
+        return rc;
+    }
     // two lanes per coefficient when the coefficients alone cannot fill the SMs (or when asked to)
     int tpc = (a.total < (size_t)lc->sm_count * 2048 && lc->S >= 2) ? 2 : 1;
     if (lc->force_tpc) tpc = lc->force_tpc;
@@ -291,6 +298,16 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
     lc->dst_mod = d + o_dst; lc->mu_hi = d + o_muh; lc->mu_lo = d + o_mul; lc->c = d + o_c; lc->lam = d + o_lam;
     lc->id_src = reinterpret_cast<const uint32_t*>(d + o_ids);
     lc->id_dst = reinterpret_cast<const uint32_t*>(d + o_idd);
+    lc->mma_kt = lincomb_mma_pad_kt(S);
+    lc->use_mma = lc->mma_kt != 0 && (size_t)S * T >= 64;
+    if (const char* ev = getenv("FHE_B200_LINCOMB_MMA")) lc->use_mma = lc->mma_kt != 0 && atoi(ev) != 0;
+    if (lc->use_mma) {
+        std::vector<uint2> bf;
+        lincomb_mma_build_bfrag(h, lc->mma_kt, bf);
+        e = cudaMalloc(&lc->d_bfrag, bf.size() * sizeof(uint2));
+        if (e == cudaSuccess) e = cudaMemcpy(lc->d_bfrag, bf.data(), bf.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error("lincomb: device allocation failed: %s", cudaGetErrorString(e)); cudaFree(lc->d_blob); delete lc; return FHE_B200_ECUDA; }
+    }
     *out = lc;
     return 0;
 }
@@ -347,6 +364,7 @@ extern "C" int fhe_b200_lincomb_destroy(fhe_b200_lincomb* lc) {
     if (!lc) return 0;
     cudaSetDevice(lc->device);
     cudaFree(lc->d_blob);
+    cudaFree(lc->d_bfrag);
     delete lc;
     return 0;
 }

@@ -21,6 +21,10 @@ struct fhe_b200_lincomb {
     int force_tpc = 0;                                          // FHE_B200_LINCOMB_TPC = 1 | 2
     const uint32_t *id_src, *id_dst;                            // identity limb maps [SP], [T]
     int sm_count = 148;
+    // tensor-core path (lincomb_mma.cu): B fragments of the Toeplitz byte matrix, [ceil(T/4)][mma_kt][8][32] uint2
+    uint2* d_bfrag = nullptr;
+    uint32_t mma_kt = 0;
+    bool use_mma = false;                                       // default when S*T >= 64; FHE_B200_LINCOMB_MMA = 0 | 1 overrides
 };
 
 namespace fhe_b200 {
@@ -40,5 +44,9 @@ struct LcView {
 
 int lincomb_create(const LincombConsts& consts, int device, fhe_b200_lincomb** out);
 int lincomb_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
+// tensor-core path; v must have every default (index maps, strides) filled in
+int lincomb_mma_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
+uint32_t lincomb_mma_pad_kt(uint32_t S);
+void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<uint2>& out);
 
 }  // namespace fhe_b200

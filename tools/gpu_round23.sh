@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_bfv.py tests/test_gpu_compat.py -m gpu -q -x > gpurun_out/pytest_gpu23.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu23.log
+for mma in 1 0; do for b in 1 4 8; do FHE_B200_LINCOMB_MMA=$mma timeout 300 python bench_hmult.py --batch $b --steps 5 2>gpurun_out/hmult23_m${mma}_b$b.err > gpurun_out/hmult23_m${mma}_b$b.json; python -c "
+import json;d=json.load(open('gpurun_out/hmult23_m${mma}_b$b.json'));print('mma=$mma hmult b$b',round(d['value'],1),round(d['ms_per_op'],3),d['decrypts_to_product'],'e2e',round(d['e2e']['value'],1),{k:v['ms'] for k,v in d['kernel_ms_per_call'].items() if isinstance(v,dict)})"; done; done
