@@ -38,7 +38,7 @@ struct alignas(64) LimbParams {
     u64 mu_hi;    // floor(2^128 / q) high word
     u64 mu_lo;    // floor(2^128 / q) low word
     u64 ninv;     // N^-1 mod q
-    u64 ninv_s;   // Shoup companion of ninv
+    u64 nm;       // ((q - 1) >> logN) | (logN << 56): N^-1 = -(q-1)/N (mod q), see scale_ninv
     u64 w1ninv;   // inv_tab[1] * N^-1 mod q (last inverse stage, bottom output)
     u64 w1ninv_s; // its Shoup companion
     u64 tq;       // kTQ * q: the offset of the lazy butterfly's difference (from memory, so that the compiler cannot
@@ -215,6 +215,17 @@ FHE_HD u64 near60_reduce(u64 x, u64 nq) {
 #else
     return (x & 0x0fffffffffffffffULL) + (x >> 60) * (u64)(u32)nq;
 #endif
+}
+
+// s * N^-1 mod q (lazy, in (0, 2q)) for any s < 2^64 with s / N < q, N = 2^lg:  m = (q-1)/N is an integer because q = 1 mod 2N,
+// and m * N = -1 (mod q), so N^-1 = -m and  s * N^-1 = (s >> lg) - (s mod N) * m.  (s mod N) * m < q.  One IMAD.WIDE + one IMAD
+// instead of the nine of a Shoup multiply: the last inverse stage scales N/2 sums with it.
+FHE_HD u64 scale_ninv(u64 s, u64 nm, u64 q) {
+    const u32 lg = (u32)(nm >> 56);
+    const u64 m = nm & 0x00ffffffffffffffULL;
+    const u32 lo = (u32)s & ((1u << lg) - 1);                       // lg <= 17
+    const u64 prod = (u64)lo * (u32)m + ((u64)(lo * (u32)(m >> 32)) << 32);      // lo * m < q: the high product fits 32 bits
+    return (s >> lg) + q - prod;
 }
 
 FHE_HD u64 mul_mod(u64 a, u64 b, const LimbParams& P) {

@@ -1,8 +1,8 @@
 // __global__ wrappers and launcher of the balanced two-pass NTT (bodies and layouts: ntt_bal.cuh), 2^13 <= N <= 2^16.
 //
 //   bal_a_kernel : pass A / A'.  CTA = 256 threads = one limb, a run of M items (item = one polynomial's block of C columns,
-//                  4096 elements).  The limb's first 2^KA twiddles are staged once; the exchange buffer is double-buffered so
-//                  that each item costs a single block barrier.  68 KiB of shared memory, 3 CTAs per SM.
+//                  4096 elements; M = 1 by default).  The limb's first 2^KA twiddles are staged once.  36 KiB of shared memory,
+//                  64 registers: 4 CTAs per SM.
 //   bal_b_kernel : pass B / B'.  Every WARP owns one pair of adjacent tiles of one limb; its 8 KiB twiddle block arrives by one
 //                  bulk copy (cp.async.bulk on the warp's own mbarrier) and serves every polynomial of the warp's group.  Only
 //                  __syncwarp() between phases.  8 warps per CTA (96 KiB), 2 CTAs per SM.
@@ -25,16 +25,16 @@ struct BalArgs {
     uint32_t groups;             // pass B: warps per (limb, tile pair); warp g handles polynomials b0+g, b0+g+groups, ...
 };
 
-constexpr size_t kBalASmem = 2 * 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
-constexpr int kBalBWarps = 8;
-constexpr size_t kBalBSmem = kBalBWarps * (512 * sizeof(u64) + 512 * sizeof(Twiddle)) + kBalBWarps * 16;
+constexpr size_t kBalASmem = 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
+constexpr int kBalBPairs = 4, kBalBGroups = 2, kBalBWarps = kBalBPairs * kBalBGroups, kBalBMinBlocks = 2;
+constexpr size_t kBalBSmem = kBalBWarps * 512 * sizeof(u64) + kBalBPairs * (512 * sizeof(Twiddle) + 16);
 
 template <int KA, int HB, bool NEAR, bool INV>
-__global__ void __launch_bounds__(256, 3) bal_a_kernel(const BalArgs a) {
+__global__ void __launch_bounds__(256, 4) bal_a_kernel(const BalArgs a) {
     using A = BalA<KA, HB, NEAR>;
     extern __shared__ __align__(128) unsigned char raw[];
     u64* sbuf = reinterpret_cast<u64*>(raw);
-    Twiddle* stw = reinterpret_cast<Twiddle*>(raw + 2 * 4096 * sizeof(u64));
+    Twiddle* stw = reinterpret_cast<Twiddle*>(raw + 4096 * sizeof(u64));
     const uint32_t tid = threadIdx.x;
     const uint32_t limb = a.l0 + blockIdx.x / a.ctas_per_limb, chunk = blockIdx.x % a.ctas_per_limb;
     const uint32_t pl = a.limb_begin + limb;
@@ -49,40 +49,47 @@ __global__ void __launch_bounds__(256, 3) bal_a_kernel(const BalArgs a) {
     constexpr int BIN = BalB<HB, NEAR>::inv_out_bound();
     __syncthreads();
 #pragma unroll 1
-    for (uint32_t k = 0; it < end; it++, k ^= 1u) {
+    for (; it < end; it++) {
         const uint32_t poly = a.b0 + it / A::CB, cb = it % A::CB;
         const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)cb * A::C;
-        u64* s = sbuf + k * 4096;
         if (!INV) {
-            A::fwd_round1(tid, a.in + off, s, stw, P);
+            A::fwd_round1(tid, a.in + off, sbuf, stw, P);
             __syncthreads();
-            A::fwd_round2(tid, a.out + off, s, stw, P);
+            A::fwd_round2(tid, a.out + off, sbuf, stw, P);
         } else {
-            A::template inv_round2<BIN>(tid, a.out + off, s, stw, P);
+            A::template inv_round2<BIN>(tid, a.out + off, sbuf, stw, P);
             __syncthreads();
-            A::template inv_round1<BIN>(tid, a.out + off, s, stw, P);
+            A::template inv_round1<BIN>(tid, a.out + off, sbuf, stw, P);
         }
+        if (it + 1 < end) __syncthreads();              // (one item per CTA is the default: no second barrier then)
     }
 }
 
+// CTA = kBalBWarps warps = kBalBPairs tile pairs x kBalBGroups polynomial groups: the warps of one pair share its staged
+// twiddle block (8 KiB), so a CTA needs 4 x 8 KiB of twiddles + 8 x 4 KiB of exchange buffers = 64 KiB and three CTAs (24 warps)
+// fit an SM.
 template <int KA, int HB, bool NEAR, bool INV>
-__global__ void __launch_bounds__(32 * kBalBWarps, 2) bal_b_kernel(const BalArgs a) {
+__global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(const BalArgs a) {
     using B = BalB<HB, NEAR>;
     extern __shared__ __align__(128) unsigned char raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pl_local = warp % kBalBPairs, gl = warp / kBalBPairs;       // pair and group inside the CTA
     u64* s = reinterpret_cast<u64*>(raw) + warp * 512;
-    Twiddle* sb = reinterpret_cast<Twiddle*>(raw + kBalBWarps * 512 * sizeof(u64)) + warp * 512;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(raw + kBalBWarps * (512 * sizeof(u64) + 512 * sizeof(Twiddle)) + warp * 16);
-    constexpr uint32_t pairs = 1u << (KA - 1);
-    const uint32_t w = blockIdx.x * kBalBWarps + warp;
-    const uint32_t pair = w % pairs, r = w / pairs, grp = r % a.groups, limb = a.l0 + r / a.groups;
+    Twiddle* sb = reinterpret_cast<Twiddle*>(raw + kBalBWarps * 512 * sizeof(u64)) + pl_local * 512;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(raw + kBalBWarps * 512 * sizeof(u64) + kBalBPairs * 512 * sizeof(Twiddle)) + pl_local * 2;
+    constexpr uint32_t pairs = 1u << (KA - 1), pair_blocks = pairs / kBalBPairs;
+    const uint32_t gblocks = (a.groups + kBalBGroups - 1) / kBalBGroups;
+    const uint32_t pb = blockIdx.x % pair_blocks, r = blockIdx.x / pair_blocks, gb = r % gblocks, limb = a.l0 + r / gblocks;
+    const uint32_t pair = pb * kBalBPairs + pl_local, grp = gb * kBalBGroups + gl;
     const uint32_t pl = a.limb_begin + limb;
-    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    __syncwarp();
-    if (lane == 0) {
+    if (threadIdx.x < kBalBPairs) mbar_init(reinterpret_cast<uint64_t*>(raw + kBalBWarps * 512 * sizeof(u64) + kBalBPairs * 512 * sizeof(Twiddle)) + threadIdx.x * 2, 1);
+    if (threadIdx.x == 0) mbar_fence_init();
+    __syncthreads();
+    if (gl == 0 && lane == 0) {
         mbar_arrive_expect_tx(bar, 512 * sizeof(Twiddle));
         bulk_copy_g2s(sb, a.blocks + ((size_t)pl * pairs + pair) * 512, 512 * sizeof(Twiddle), bar);
     }
+    if (grp >= a.groups) return;                       // odd group count: the second half of the last group block has no work
     const LimbParams P = a.params[pl];
     const size_t limb_off = (size_t)limb * a.n + (size_t)pair * 512;
     const size_t poly_stride = (size_t)a.limb_count * a.n;
@@ -135,16 +142,18 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
     a.m_items = m;
     a.ctas_per_limb = (items_per_limb + m - 1) / m;
     const uint32_t grid_a = a.nl * a.ctas_per_limb;
-    // pass B: one warp per (limb, tile pair, group).  Few groups = many polynomials per staged twiddle block (measured at
-    // config 3: 2 groups 0.646 ms, 3 groups 0.669 ms, 8 groups 0.657 ms, 1 group 0.740 ms (under two waves)): aim at three waves
+    // pass B: one warp per (limb, tile pair, group); a CTA covers kBalBPairs pairs x kBalBGroups groups.  Few groups = many
+    // polynomials per staged twiddle block (measured at config 3: 2 groups 0.646 ms, 3 groups 0.669 ms, 8 groups 0.657 ms,
+    // 1 group 0.740 ms (under two waves)): aim at three waves of resident warps
     constexpr uint32_t pairs = 1u << (KA - 1);
     const uint32_t lp = a.nl * pairs;
-    uint32_t groups = (3u * 2u * sms * kBalBWarps + lp - 1) / lp;
+    uint32_t groups = (4u * kBalBMinBlocks * sms * kBalBWarps + lp - 1) / lp;
     static const int env_g = getenv("FHE_B200_BAL_GROUPS") ? atoi(getenv("FHE_B200_BAL_GROUPS")) : 0;
     if (env_g > 0) groups = (uint32_t)env_g;
+    groups = (groups + kBalBGroups - 1) / kBalBGroups * kBalBGroups;       // whole CTAs (a CTA spans kBalBGroups groups)
     groups = groups < 1 ? 1 : (groups > a.nb ? a.nb : groups);
     a.groups = groups;
-    const uint32_t grid_b = lp * groups / kBalBWarps;
+    const uint32_t grid_b = a.nl * (pairs / kBalBPairs) * ((groups + kBalBGroups - 1) / kBalBGroups);
     const bool prof = profile_on();
     if (!inverse) {
         if (prof) profile_begin(2, pls, st);

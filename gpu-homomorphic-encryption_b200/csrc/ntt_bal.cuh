@@ -62,14 +62,14 @@ struct BalA {
     static FHE_HDC int fwd_out_bound() { return fwd_bound_after(1, KA, HB, NEAR); }
 
     // round-1 thread (rl, ct) holds element e = (cc << R1) | rh: row rh*16 + rl, column cc*16 + ct
+    struct Off1 { static FHE_HDC long at(int e) { return (long)((e & (int)RM) << 4) * 256 + ((e >> R1) << 4); } };       // at1(tid, e) - at1(tid, 0)
     static FHE_HD size_t at1(u32 tid, int e) { return (size_t)(((e & RM) << 4) | (tid >> 4)) * 256 + (((u32)e >> R1) << 4) + (tid & 15); }
     // round-2 thread (e1, ct), e1 = (cc << R1) | rh, holds rows rh*16 + rl
     static FHE_HD size_t at2(u32 tid, int rl) { const u32 e1 = tid >> 4; return (size_t)(((e1 & RM) << 4) | (u32)rl) * 256 + ((e1 >> R1) << 4) + (tid & 15); }
 
     static FHE_HD void fwd_round1(u32 tid, const u64* g, u64* s, const Twiddle* stw, const LimbParams& P) {
         u64 x[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) x[e] = ldg1(g + at1(tid, e));
+        ldg16o<Off1>(g + (size_t)(tid >> 4) * 256 + (tid & 15), x);
         fwd_stages<4, R1, HB, NEAR, 1>(x, TwA1{stw}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) s[(e << 8) | tid] = x[e];
@@ -89,8 +89,7 @@ struct BalA {
     static FHE_HD void inv_round2(u32 tid, const u64* g, u64* s, const Twiddle* stw, const LimbParams& P) {
         u64 x[16];
         const u32 e1 = tid >> 4, ct = tid & 15;
-#pragma unroll
-        for (int rl = 0; rl < 16; rl++) x[rl] = ldg1(g + at2(tid, rl));
+        ldg16<256>(g + at2(tid, 0), x);
         inv_stages<4, 4, HB, NEAR, false, BIN>(x, TwA2{stw, (1u << R1) + (e1 & RM)}, P);
 #pragma unroll
         for (int rl = 0; rl < 16; rl++) s[(e1 << 8) | (rl << 4) | ct] = x[rl];
@@ -120,8 +119,7 @@ struct BalB {
     // the next polynomial while the current one is copied out)
     static FHE_HD void fwd_load(u32 lane, const u64* g, u64 (&x)[16]) {
         const u32 t = lane >> 4, j = lane & 15;
-#pragma unroll
-        for (int e = 0; e < 16; e++) x[e] = ldg1(g + ((t << 8) | (e << 4) | j));
+        ldg16<16>(g + ((t << 8) | j), x);
     }
     template <int B0>
     static FHE_HD void fwd_phase1(u32 lane, u64 (&x)[16], u64* s, const Twiddle* sb, const LimbParams& P) {

@@ -90,6 +90,33 @@ FHE_HD void ldg2(const u64* p, u64& a, u64& b) {
 #endif
 }
 
+// Sixteen L2-only loads base[OFF::at(e)], e = 0..15 (compile-time element offsets), as ONE asm statement: the compiler may not sink some of them below the
+// first butterflies (it did, to save registers: four of the sixteen loads of the tile pass were issued 200 instructions late and
+// `long_scoreboard` became the top stall, 0.78 ms against 0.65 ms per pass at config 3).
+struct Stride16 { template <int STRIDE> struct Of { static FHE_HDC long at(int e) { return (long)e * STRIDE; } }; };
+template <class OFF>
+FHE_HD void ldg16o(const u64* base, u64 (&x)[16]) {
+#if defined(__CUDA_ARCH__)
+    asm volatile(
+        "ld.global.cg.u64 %0, [%16+%17];\n\t"  "ld.global.cg.u64 %1, [%16+%18];\n\t"  "ld.global.cg.u64 %2, [%16+%19];\n\t"
+        "ld.global.cg.u64 %3, [%16+%20];\n\t"  "ld.global.cg.u64 %4, [%16+%21];\n\t"  "ld.global.cg.u64 %5, [%16+%22];\n\t"
+        "ld.global.cg.u64 %6, [%16+%23];\n\t"  "ld.global.cg.u64 %7, [%16+%24];\n\t"  "ld.global.cg.u64 %8, [%16+%25];\n\t"
+        "ld.global.cg.u64 %9, [%16+%26];\n\t"  "ld.global.cg.u64 %10, [%16+%27];\n\t" "ld.global.cg.u64 %11, [%16+%28];\n\t"
+        "ld.global.cg.u64 %12, [%16+%29];\n\t" "ld.global.cg.u64 %13, [%16+%30];\n\t" "ld.global.cg.u64 %14, [%16+%31];\n\t"
+        "ld.global.cg.u64 %15, [%16+%32];"
+        : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]), "=l"(x[4]), "=l"(x[5]), "=l"(x[6]), "=l"(x[7]), "=l"(x[8]), "=l"(x[9]),
+          "=l"(x[10]), "=l"(x[11]), "=l"(x[12]), "=l"(x[13]), "=l"(x[14]), "=l"(x[15])
+        : "l"(base), "n"(OFF::at(0) * 8), "n"(OFF::at(1) * 8), "n"(OFF::at(2) * 8), "n"(OFF::at(3) * 8), "n"(OFF::at(4) * 8),
+          "n"(OFF::at(5) * 8), "n"(OFF::at(6) * 8), "n"(OFF::at(7) * 8), "n"(OFF::at(8) * 8), "n"(OFF::at(9) * 8), "n"(OFF::at(10) * 8),
+          "n"(OFF::at(11) * 8), "n"(OFF::at(12) * 8), "n"(OFF::at(13) * 8), "n"(OFF::at(14) * 8), "n"(OFF::at(15) * 8)
+        : "memory");
+#else
+    for (int e = 0; e < 16; e++) x[e] = base[OFF::at(e)];
+#endif
+}
+template <int STRIDE>
+FHE_HD void ldg16(const u64* base, u64 (&x)[16]) { ldg16o<Stride16::Of<STRIDE>>(base, x); }
+
 // bounds in units of q; the twiddle product is lazy in [0, kTQ q) (shoup_mul_lazy3).
 // NEAR: every modulus q satisfies 2^60 - 2^32 < q < 2^60, so near60_reduce brings anything below 16q under 2q.
 FHE_HDC int red_to(int HB, bool NEAR) { return NEAR ? 2 : HB / 2; }
@@ -199,7 +226,7 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
                 FHE_BOUND(X, B, q); FHE_BOUND(Y, B, q); FHE_BOUND((unsigned __int128)X + Y, HB, q);
                 u64 S = add3z(X, Y);
                 const u64 D = X + bq - Y;
-                if (last) S = shoup_mul_lazy3(S, P.ninv, P.ninv_s, nq);
+                if (last) S = scale_ninv(S, P.nm, q);
                 else if (red) S = NEAR ? near60_reduce(S, nq) : csub(S, bq);
                 x[e] = S;
                 x[e + st] = shoup_mul_lazy3(D, w.w, w.ws, nq);

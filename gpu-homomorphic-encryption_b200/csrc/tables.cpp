@@ -19,7 +19,7 @@ int build_limb_tables(uint64_t q, uint32_t n, Twiddle* fwd, Twiddle* inv, LimbPa
     P->q = q;
     frac128(1, q, P->mu_hi, P->mu_lo);
     P->ninv = invmod(n % q, q);
-    P->ninv_s = shoup(P->ninv, q);
+    P->nm = ((q - 1) >> lg) | ((u64)lg << 56);
     P->w1ninv = mulmod(inv[1].w, P->ninv, q);
     P->w1ninv_s = shoup(P->w1ninv, q);
     P->tq = (u64)kTQ * q;
