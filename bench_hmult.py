@@ -12,7 +12,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
+def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None):
+    """dist: an initialised torch.distributed module for the batch-sharded multi-GPU run (every rank multiplies its own `batch`
+    ciphertext pairs with replicated keys -- no data-path collective; the timed region is bracketed by barriers, the time is the
+    max over ranks and `value` the whole-job aggregate)."""
     import numpy as np
     import torch
     import fhe_b200
@@ -35,6 +38,9 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
     for _ in range(3):
         g.multiply(ca, cb, rlk, out=out)
     torch.cuda.synchronize()
+    world = dist.get_world_size() if dist is not None else 1
+    if dist is not None:
+        dist.barrier(); torch.cuda.synchronize()
     l0 = lib.fhe_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -43,6 +49,10 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    if dist is not None:
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax[0])
     launches = lib.fhe_b200_launch_count() - l0
     # per-kernel-class breakdown of one more pass (CUDA events around every launch)
     import ctypes as C
@@ -78,7 +88,8 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None):
     e2e = time.perf_counter() - t0
     ok2 = bool(np.array_equal(ho, to_host(out)))
     ct_bytes = 2 * L * n * 8
-    return {"metric": "BFV HMult+relinearize ops/s", "value": B * K / (ms / 1e3), "unit": "ops/s", "batch": B, "steps": K,
+    return {"metric": "BFV HMult+relinearize ops/s", "value": world * B * K / (ms / 1e3), "unit": "ops/s", "n_gpus": world,
+            "batch_per_gpu": B, "batch": B, "steps": K, "scaling": "weak", "parallelism": f"batch-sharded x{world}",
             "ms_per_op": ms / (B * K), "config": {"workload": f"config4: N={n}, L={L}, R={p['R']}, dnum={p['dnum']}, K={p['K']}, t={t}"},
             "decrypts_to_product": ok, "gpu_launches": int(launches), "kernel_ms_per_call": breakdown,
             "e2e": {"value": B * e2e_steps / e2e, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
@@ -92,4 +103,18 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--preset", default="c4")
     a = ap.parse_args()
-    print(json.dumps(run_hmult(a, 0, a.preset, a.batch, a.steps)))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:        # torchrun: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 bench_hmult.py
+        import torch
+        import torch.distributed as dist
+        lr = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(lr)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        res = run_hmult(a, lr, a.preset, a.batch, a.steps, dist=dist)
+        if dist.get_rank() == 0:
+            print(json.dumps(res), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        print(json.dumps(run_hmult(a, 0, a.preset, a.batch, a.steps)))

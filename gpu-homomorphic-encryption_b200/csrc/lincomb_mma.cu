@@ -123,14 +123,29 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
         int acc[8][4];
 #pragma unroll
         for (int t = 0; t < 8; t++) { acc[t][0] = 0; acc[t][1] = 0; acc[t][2] = 0; acc[t][3] = 0; }
+        // epilogue operands of this lane's target (extra limb, ModDown minuend and addend): issued now, consumed after the mma block
+        const uint32_t k = 4 * G + q;
+        const bool live = k < a.T;
+        u64 ex[2] = {0, 0}, su[2] = {0, 0}, ad[2] = {0, 0};
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const uint32_t j = j0 + 8 * r;
+                if (a.use_extra) ex[r] = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + k] + j];
+                if (a.v.sub) {
+                    const size_t eo = sIdx[2 * a.T + k] + j;
+                    su[r] = a.v.sub[(size_t)b * a.v.sub_stride + eo];
+                    if (a.v.add) ad[r] = a.v.add[(size_t)b * a.v.add_stride + eo];
+                }
+            }
+        }
         const uint2* bf = sB + (size_t)G * KT * 8 * 32 + lane;
 #pragma unroll
         for (int kt = 0; kt < KT; kt++) {
 #pragma unroll
             for (int t = 0; t < 8; t++) mma_u8(acc[t], A[kt], bf[(kt * 8 + t) * 32]);
         }
-        const uint32_t k = 4 * G + q;
-        if (k >= a.T) continue;
+        if (!live) continue;
         const u64 m = sDst[k], mh = sDst[a.T + k], ml = sDst[2 * a.T + k];
 #pragma unroll
         for (int r = 0; r < 2; r++) {
@@ -146,15 +161,14 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
             u64 ah = (u64)(V >> 64), al = (u64)V;
             const uint32_t j = j0 + 8 * r;
             if (a.c_is_one) add128(ah, al, I_hi[r], I_lo[r]); else mac128(ah, al, I_lo[r], sDst[3 * a.T + k]);
-            if (a.use_extra) mac128(ah, al, a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + k] + j], sDst[4 * a.T + k]);
+            if (a.use_extra) mac128(ah, al, ex[r], sDst[4 * a.T + k]);
             u64 res = barrett128(ah, al, m, mh, ml);
             if (a.v.sub) {
-                const size_t eo = sIdx[2 * a.T + k] + j;
-                const u64 d = sub_mod(a.v.sub[(size_t)b * a.v.sub_stride + eo], res, m);
+                const u64 d = sub_mod(su[r], res, m);
                 u64 ph, pl;
                 mul128(d, sDst[5 * a.T + k], ph, pl);
                 res = barrett128(ph, pl, m, mh, ml);
-                if (a.v.add) res = add_mod(res, a.v.add[(size_t)b * a.v.add_stride + eo], m);
+                if (a.v.add) res = add_mod(res, ad[r], m);
             }
             a.v.out[(size_t)b * a.v.out_stride + sIdx[k] + j] = res;
         }
