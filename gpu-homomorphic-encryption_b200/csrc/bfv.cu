@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(256) pk_finish_kernel(u64* __restrict__ pk0, c
     }
 }
 // b = e - a*s + f*s^2, f = P mod q_i for the digit's own limbs, 0 elsewhere; W = L+K limbs
+// (s_from: the key being switched FROM in NTT form -- s(x^g) for a Galois key; nullptr = s^2, the relinearisation key)
 __global__ void __launch_bounds__(256) rlk_finish_kernel(u64* __restrict__ b, const u64* __restrict__ a, const u64* __restrict__ s,
+                                                         const u64* __restrict__ s_from,
                                                          const LimbParams* __restrict__ params, const u64* __restrict__ pmodq,
                                                          uint32_t logn, uint32_t g_lo, uint32_t g_hi, size_t total) {
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
@@ -110,8 +112,24 @@ __global__ void __launch_bounds__(256) rlk_finish_kernel(u64* __restrict__ b, co
         const LimbParams P = params[i];
         const u64 sv = s[g];
         u64 v = sub_mod(b[g], mul_mod(a[g], sv, P), P.q);
-        if (i >= g_lo && i < g_hi) v = add_mod(v, mul_mod(pmodq[i], mul_mod(sv, sv, P), P), P.q);
+        if (i >= g_lo && i < g_hi) v = add_mod(v, mul_mod(pmodq[i], s_from ? s_from[g] : mul_mod(sv, sv, P), P), P.q);
         b[g] = v;
+    }
+}
+
+// out(x) = in(x^g) per limb (g odd, ginv = g^-1 mod 2N): output coefficient j comes from i' = j*ginv mod 2N, negated when i' >= N.
+// Buffers [polys][limb_count][N], limb l of the buffer = plan limb limb_begin + l.  Gather form: coalesced stores.
+__global__ void __launch_bounds__(256) galois_kernel(u64* __restrict__ out, const u64* __restrict__ in,
+                                                     const LimbParams* __restrict__ params, uint32_t logn, uint32_t limb_begin,
+                                                     uint32_t limb_count, uint32_t ginv, size_t total) {
+    const uint32_t n = 1u << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g & (n - 1));
+        const size_t pl = g >> logn;
+        const u64 q = params[limb_begin + (uint32_t)(pl % limb_count)].q;
+        const uint32_t ip = (uint32_t)(((u64)j * ginv) & (2 * (u64)n - 1));
+        const u64 v = in[(pl << logn) + (ip & (n - 1))];
+        out[g] = ip < n ? v : neg_mod(v, q);
     }
 }
 
@@ -446,7 +464,7 @@ extern "C" int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* c, uint64_t seed, const ui
         FHE_TRY(launch_ntt(c->plan, b, b, 1, 0, W, false, st));
         sample_uniform_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base);
         FHE_LAUNCH_CHECK();
-        rlk_finish_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(b, a, d_sk, prm, c->d_pmodq, c->logn, d * c->alpha, (d + 1) * c->alpha, (size_t)W * n);
+        rlk_finish_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(b, a, d_sk, nullptr, prm, c->d_pmodq, c->logn, d * c->alpha, (d + 1) * c->alpha, (size_t)W * n);
         FHE_LAUNCH_CHECK();
     }
     return 0;
@@ -541,6 +559,47 @@ extern "C" int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* c, const uint64_t* d_ct
     return launch_ntt(c->plan, d_out, d_out, 2 * batch, 0, c->L, true, st);
 }
 
+// ---- hybrid key switching ----------------------------------------------------------------------------------------------------
+//   out[b][p] = add_p[b] + ModDown( sum_digits NTT(ModUp(x[b] digit)) * key[digit][p] ),  p = 0, 1   (add_p may be nullptr)
+// x: [B] polynomials of L limbs (coefficient form, stride x_stride words), key: [dnum][2][L+K][N] NTT form, out: [B][2][L][N].
+// dig [dnum][B][L+K][N] and acc [2][B][L+K][N] are workspace.  Replaces FHEContext::relinearize / key_switch
+// (/root/reference/src/fhe.cu:226-235, include/fhe.cuh:134-135; a stub there, intent docs/ARCHITECTURE.md:319-326).
+static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const uint64_t* d_key, const uint64_t* add0, size_t add0_stride,
+                      const uint64_t* add1, size_t add1_stride, uint64_t* d_out, uint32_t B, uint64_t* dig, uint64_t* acc, cudaStream_t st) {
+    const uint32_t n = c->n, L = c->L, K = c->K, W = L + K, alpha = c->alpha, dnum = c->dnum;
+    const LimbParams* prm = c->plan->d_params;
+    const size_t N = n, ln = (size_t)L * N, wn = (size_t)W * N;
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    for (uint32_t dg = 0; dg < dnum && !rc; dg++) {
+        uint64_t* D = dig + (size_t)dg * B * wn;
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(D + (size_t)dg * alpha * N, wn * 8, x + (size_t)dg * alpha * N, x_stride * 8, (size_t)alpha * N * 8, B,
+                                  cudaMemcpyDeviceToDevice, st);
+        LcView v; v.in = x; v.in_stride = x_stride; v.src_idx = c->d_idx_grp[dg]; v.out = D; v.out_stride = wn; v.dst_idx = c->d_idx_tgt[dg];
+        rc = lincomb_launch(c->modup[dg], v, n, B, st);
+    }
+    if (e != cudaSuccess) { set_error("key_switch: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
+    if (!rc) rc = launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st);
+    if (!rc) {
+        const size_t per = B * wn / 2;
+        if (profile_on()) profile_begin(6, B, st);
+        ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn, 0, W, dnum, B);
+        if (profile_on()) profile_end(st);
+        count_launch();
+    }
+    if (!rc) rc = launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st);
+    for (int p = 0; p < 2 && !rc; p++) {
+        const uint64_t* s = acc + (size_t)p * B * wn;
+        LcView v; v.in = s; v.in_stride = wn; v.src_idx = c->d_idx_p;
+        v.sub = s; v.sub_stride = wn; v.epi_scalar = c->d_pinv;
+        v.add = p ? add1 : add0; v.add_stride = p ? add1_stride : add0_stride;
+        v.out = d_out + (size_t)p * ln; v.out_stride = 2 * ln;
+        rc = lincomb_launch(c->moddown, v, n, B, st);
+    }
+    return rc;
+}
+
 // ---- multiply + relinearize --------------------------------------------------------------------------------------------------
 extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
                                            uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream) {
@@ -585,37 +644,79 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
         // caller layout [B][3][L][N]; ours is [3][B][L][N]
         for (int p = 0; p < 3; p++) COPY2D(d_scaled + (size_t)p * ln, 3 * ln, sc + (size_t)p * B * ln, ln, ln, B);
     }
-    // 7. relinearise d2 = sc[2]: ModUp each digit, NTT, inner product with the key, INTT, ModDown (+ add d0/d1)
-    const uint64_t* d2 = sc + 2 * B * ln;
-    for (uint32_t dg = 0; dg < dnum && !rc; dg++) {
-        uint64_t* D = dig + (size_t)dg * B * wn;
-        COPY2D(D + (size_t)dg * alpha * N, wn, d2 + (size_t)dg * alpha * N, ln, (size_t)alpha * N, B);
-        LcView v; v.in = d2; v.in_stride = ln; v.src_idx = c->d_idx_grp[dg]; v.out = D; v.out_stride = wn; v.dst_idx = c->d_idx_tgt[dg];
-        STEP(lincomb_launch(c->modup[dg], v, n, B, st));
-    }
-    STEP(launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st));
-    if (!rc) {
-        const size_t per = B * wn / 2;
-        if (profile_on()) profile_begin(6, B, st);
-        ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_rlk, prm, c->logn, 0, W, dnum, B);
-        if (profile_on()) profile_end(st);
-        count_launch();
-    }
-    STEP(launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st));
-    for (int p = 0; p < 2 && !rc; p++) {
-        const uint64_t* s = acc + (size_t)p * B * wn;
-        LcView v; v.in = s; v.in_stride = wn; v.src_idx = c->d_idx_p;
-        v.sub = s; v.sub_stride = wn; v.epi_scalar = c->d_pinv;
-        v.add = sc + (size_t)p * B * ln; v.add_stride = ln;
-        v.out = d_out + (size_t)p * ln; v.out_stride = 2 * ln;
-        STEP(lincomb_launch(c->moddown, v, n, B, st));
-    }
+    // 7. relinearise d2 = sc[2]: hybrid key switching, added onto (d0, d1)
+    if (e != cudaSuccess) { set_error("bfv_multiply_relin: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
+    STEP(key_switch(c, sc + 2 * B * ln, ln, d_rlk, sc, ln, sc + B * ln, ln, d_out, B, dig, acc, st));
 #undef STEP
 #undef COPY2D
     if (e != cudaSuccess) { set_error("bfv_multiply_relin: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
     if (rc) return rc;
     FHE_CUDA(cudaGetLastError());
     return 0;
+}
+
+// ---- Galois keys, automorphisms / rotations, modulus chain (declared only in the reference: include/fhe.cuh:59-61,86,109-116) ---
+static uint32_t inv_mod_2n(uint32_t g, uint32_t two_n) {          // g odd, two_n a power of two: Newton iteration
+    uint32_t x = g;                                                // correct to 3 bits
+    for (int i = 0; i < 5; i++) x *= 2u - g * x;
+    return x & (two_n - 1);
+}
+
+extern "C" int fhe_b200_bfv_galoiskeygen(fhe_b200_bfv* c, uint64_t seed, uint32_t galois_elt, const uint64_t* d_sk, uint64_t* d_gk, void* stream) {
+    FHE_REQUIRE(c && d_sk && d_gk, "bfv_galoiskeygen: null argument");
+    FHE_REQUIRE((galois_elt & 1u) && galois_elt < 2 * c->n, "bfv_galoiskeygen: the Galois element must be odd and below 2N");
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, W = c->L + c->K;
+    const LimbParams* prm = c->plan->d_params;
+    const size_t wn = (size_t)W * n;
+    // s(x^g) in NTT form over the L+K key limbs: INTT(s) -> automorphism -> NTT
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, 2 * wn));
+    uint64_t* tmp = c->d_ws; uint64_t* sg = tmp + wn;
+    FHE_TRY(launch_ntt(c->plan, tmp, d_sk, 1, 0, W, true, st));
+    galois_kernel<<<grid_for(c, wn), 256, 0, st>>>(sg, tmp, prm, c->logn, 0, W, inv_mod_2n(galois_elt, 2 * n), wn);
+    FHE_LAUNCH_CHECK();
+    FHE_TRY(launch_ntt(c->plan, sg, sg, 1, 0, W, false, st));
+    for (uint32_t d = 0; d < c->dnum; d++) {
+        uint64_t* b = d_gk + (size_t)(2 * d) * wn; uint64_t* a = b + wn;
+        const uint64_t base = 1024ull * (d + 1);
+        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, base + 512, 0, c->d_cdt, c->cdt_len);
+        FHE_LAUNCH_CHECK();
+        FHE_TRY(launch_ntt(c->plan, b, b, 1, 0, W, false, st));
+        sample_uniform_kernel<<<grid_for(c, wn), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base);
+        FHE_LAUNCH_CHECK();
+        rlk_finish_kernel<<<grid_for(c, wn), 256, 0, st>>>(b, a, d_sk, sg, prm, c->d_pmodq, c->logn, d * c->alpha, (d + 1) * c->alpha, wn);
+        FHE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_apply_galois(fhe_b200_bfv* c, const uint64_t* d_ct, uint32_t galois_elt, const uint64_t* d_gk, uint64_t* d_out,
+                                         uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_ct && d_gk && d_out, "bfv_apply_galois: null argument");
+    FHE_REQUIRE((galois_elt & 1u) && galois_elt < 2 * c->n, "bfv_apply_galois: the Galois element must be odd and below 2N");
+    if (!batch) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, L = c->L, W = L + c->K, B = batch;
+    const size_t ln = (size_t)L * n, wn = (size_t)W * n;
+    // workspace: rot [B][2][L][N] | dig [dnum][B][W][N] | acc [2][B][W][N]
+    const size_t w_rot = 2 * B * ln, w_dig = (size_t)c->dnum * B * wn, w_acc = 2 * B * wn;
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_rot + w_dig + w_acc));
+    uint64_t* rot = c->d_ws; uint64_t* dig = rot + w_rot; uint64_t* acc = dig + w_dig;
+    galois_kernel<<<grid_for(c, w_rot), 256, 0, st>>>(rot, d_ct, c->plan->d_params, c->logn, 0, L, inv_mod_2n(galois_elt, 2 * n), w_rot);
+    FHE_LAUNCH_CHECK();
+    // (c0(x^g), 0) + KeySwitch(c1(x^g))
+    FHE_TRY(key_switch(c, rot + ln, 2 * ln, d_gk, rot, 2 * ln, nullptr, 0, d_out, B, dig, acc, st));
+    FHE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_mod_switch_to_next(fhe_b200_bfv* c, const uint64_t* d_ct, uint64_t* d_out, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_ct && d_out, "bfv_mod_switch_to_next: null argument");
+    FHE_REQUIRE(c->L >= 2, "bfv_mod_switch_to_next: the ciphertext modulus has a single limb");
+    // both components of every ciphertext: [2 batch][L][N] -> [2 batch][L-1][N]
+    return fhe_b200_modswitch_drop_last(c->plan, d_out, d_ct, 2 * batch, 0, c->L, stream);
 }
 
 // Host-buffer entry point.  The ciphertext pairs are processed one at a time on two alternating streams, each with its

@@ -392,6 +392,27 @@ class BfvContext:
                                                    _stream()))
         return out
 
+    # Galois automorphisms / rotations and the modulus chain (include/fhe.cuh:59-61,86,109-116)
+    def galoiskey_gen(self, seed, galois_elt, sk):
+        gk = self._empty(self.dnum, 2, self.L + self.K, self.n)
+        check(self.lib.fhe_b200_bfv_galoiskeygen(self.h, C.c_uint64(seed), C.c_uint32(galois_elt), _ptr(sk), _ptr(gk), _stream()))
+        return gk
+
+    def apply_galois(self, ct, galois_elt, gk):
+        out = torch.empty_like(ct)
+        check(self.lib.fhe_b200_bfv_apply_galois(self.h, _ptr(ct), C.c_uint32(galois_elt), _ptr(gk), _ptr(out),
+                                                 ct.numel() // (2 * self.L * self.n), _stream()))
+        return out
+
+    def rotate_rows(self, ct, steps, gk): return self.apply_galois(ct, pow(3, steps % (self.n // 2), 2 * self.n), gk)
+    def rotate_columns(self, ct, gk): return self.apply_galois(ct, 2 * self.n - 1, gk)
+
+    def mod_switch_to_next(self, ct):
+        b = ct.numel() // (2 * self.L * self.n)
+        out = self._empty(b, 2, self.L - 1, self.n)
+        check(self.lib.fhe_b200_bfv_mod_switch_to_next(self.h, _ptr(ct), _ptr(out), b, _stream()))
+        return out
+
     # SIMD slot encoding (fhe::BatchEncoder, include/fhe.cuh:151-166): slot i is the value of the plaintext polynomial at
     # the evaluation point the engine's NTT puts at position i; needs t = 1 (mod 2N)
     def _slot_plan(self):

@@ -43,7 +43,7 @@ struct SchemeParams {
 struct PublicKey { Polynomial* pk0 = nullptr; Polynomial* pk1 = nullptr; };
 struct SecretKey { Polynomial* sk = nullptr; };
 struct RelinKeys { std::vector<PublicKey*> rlk_keys; uint32_t decomp_bits = 0; };
-struct GaloisKeys { std::vector<PublicKey*> gal_keys; };
+struct GaloisKeys { std::vector<PublicKey*> gal_keys; std::vector<uint32_t> elts; };   // elts[i]: the Galois element of gal_keys[i]
 struct Ciphertext {
     std::vector<Polynomial*> components;
     uint32_t level = 0;
@@ -112,6 +112,50 @@ public:
             k->pk1 = new Polynomial(n, W, all->rns + (size_t)(2 * d + 1) * W * n);
             rlk.rlk_keys.push_back(k);
         }
+    }
+
+    // Galois keys for the power-of-two row rotations (elements 3^(2^k) mod 2N) and the column swap (2N - 1): declared only in
+    // the reference (include/fhe.cuh:59-61,86).  Each key has the relinearisation-key layout [dnum][2][L+K][N].
+    void galoiskey_gen(GaloisKeys& gal_keys, const SecretKey& sk) {
+        const uint32_t n = params_.n, W = params_.L + params_.K, dnum = params_.dnum;
+        std::vector<uint32_t> elts;
+        uint64_t e = 3;
+        for (uint32_t k = 1; k < n / 2; k <<= 1) { elts.push_back((uint32_t)e); e = e * e % (2ull * n); }
+        elts.push_back(2 * n - 1);
+        for (uint32_t g : elts) {
+            PublicKey* k = new PublicKey();
+            k->pk0 = new Polynomial(n, 2 * W * dnum); k->pk0->is_ntt_form = true;          // owns [dnum][2][W][N]
+            k->pk1 = new Polynomial(n, W, k->pk0->rns + (size_t)W * n); k->pk1->is_ntt_form = true;
+            detail::check(fhe_b200_bfv_galoiskeygen(ctx_, next_seed(), g, sk.sk->rns, k->pk0->rns, stream_), "galoiskey_gen");
+            gal_keys.gal_keys.push_back(k); gal_keys.elts.push_back(g);
+        }
+    }
+    // slot rotation by `steps` inside each row of the 2 x N/2 batching matrix = automorphism x -> x^(3^steps); composed from the
+    // power-of-two keys (include/fhe.cuh:113-114, declared only)
+    void rotate_rows(Ciphertext& result, const Ciphertext& ct, int steps, const GaloisKeys& gal_keys) {
+        const uint32_t half = params_.n / 2;
+        uint32_t s = (uint32_t)(((steps % (int)half) + (int)half) % (int)half);
+        Ciphertext cur; new_ciphertext(cur);
+        detail::check_cuda(cudaMemcpyAsync(cur.components[0]->rns, ct.components[0]->rns, (size_t)2 * params_.L * params_.n * sizeof(uint64_t),
+                                           cudaMemcpyDeviceToDevice, stream_), "rotate_rows");
+        for (uint32_t k = 0; (1u << k) < half; k++) {
+            if (!((s >> k) & 1u)) continue;
+            Ciphertext nxt; new_ciphertext(nxt);
+            detail::check(fhe_b200_bfv_apply_galois(ctx_, cur.components[0]->rns, gal_keys.elts.at(k), gal_keys.gal_keys.at(k)->pk0->rns,
+                                                    nxt.components[0]->rns, 1, stream_), "rotate_rows");
+            detail::check_cuda(cudaStreamSynchronize(stream_), "rotate_rows");
+            release(cur); cur = nxt;
+        }
+        cur.noise_budget = ct.noise_budget; cur.level = ct.level;
+        replace(result, cur);
+    }
+    // swaps the two rows of the batching matrix: x -> x^(2N-1) (include/fhe.cuh:115-116, declared only)
+    void rotate_columns(Ciphertext& result, const Ciphertext& ct, const GaloisKeys& gal_keys) {
+        Ciphertext out; new_ciphertext(out);
+        detail::check(fhe_b200_bfv_apply_galois(ctx_, ct.components[0]->rns, gal_keys.elts.back(), gal_keys.gal_keys.back()->pk0->rns,
+                                                out.components[0]->rns, 1, stream_), "rotate_columns");
+        out.noise_budget = ct.noise_budget; out.level = ct.level;
+        replace(result, out);
     }
 
     // ---- encoding (src/fhe.cu:113-136): coefficient encoding, values[i] -> coefficient i
@@ -190,6 +234,10 @@ public:
     static void release(PublicKey& pk) { delete pk.pk1; delete pk.pk0; pk.pk0 = pk.pk1 = nullptr; }
     static void release(SecretKey& sk) { delete sk.sk; sk.sk = nullptr; }
     static void release(Plaintext& pt) { delete pt.poly; pt.poly = nullptr; }
+    static void release(GaloisKeys& gk) {
+        for (size_t i = gk.gal_keys.size(); i-- > 0;) { delete gk.gal_keys[i]->pk1; delete gk.gal_keys[i]->pk0; delete gk.gal_keys[i]; }
+        gk.gal_keys.clear(); gk.elts.clear();
+    }
     static void release(RelinKeys& rlk) {
         for (size_t d = rlk.rlk_keys.size(); d-- > 0;) { delete rlk.rlk_keys[d]->pk1; delete rlk.rlk_keys[d]->pk0; delete rlk.rlk_keys[d]; }
         rlk.rlk_keys.clear();

@@ -191,6 +191,18 @@ int fhe_b200_bfv_tensor(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_
                         uint32_t limb_count, void* stream);
 int fhe_b200_bfv_ks_inner(fhe_b200_plan* plan, uint64_t* d_acc, const uint64_t* d_dig, const uint64_t* d_key, uint32_t dnum,
                           uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream);
+/* Galois keys and automorphisms: FHEContext::galoiskey_gen / rotate_rows / rotate_columns (include/fhe.cuh:59-61,86,113-116;
+ * declared only in the reference).  galois_elt g is odd and < 2N; the key has the relinearisation-key layout
+ * [dnum][2][L+K][N] (NTT form) and switches s(x^g) back to s.  apply_galois: ct(x) -> ct(x^g) re-encrypted under s,
+ * ciphertexts [batch][2][L][N] coefficient form.  rotate_rows(steps) = apply_galois(3^steps mod 2N), rotate_columns =
+ * apply_galois(2N - 1) (compat layer). */
+int fhe_b200_bfv_galoiskeygen(fhe_b200_bfv* ctx, uint64_t seed, uint32_t galois_elt, const uint64_t* d_sk, uint64_t* d_gk,
+                              void* stream);
+int fhe_b200_bfv_apply_galois(fhe_b200_bfv* ctx, const uint64_t* d_ct, uint32_t galois_elt, const uint64_t* d_gk,
+                              uint64_t* d_out, uint32_t batch, void* stream);
+/* FHEContext::mod_switch_to_next (include/fhe.cuh:109; declared only): both components lose the last limb of Q with rounding,
+ * [batch][2][L][N] -> [batch][2][L-1][N]; the result decrypts under a context built on the first L-1 limbs. */
+int fhe_b200_bfv_mod_switch_to_next(fhe_b200_bfv* ctx, const uint64_t* d_ct, uint64_t* d_out, uint32_t batch, void* stream);
 /* host-buffer variant of multiply_relin (copies in, computes, copies out; synchronous) */
 int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* ctx, const uint64_t* h_a, const uint64_t* h_b,
                                      const uint64_t* d_rlk, uint64_t* h_out, uint32_t batch);

@@ -220,6 +220,13 @@ def to_rns(values, moduli) -> np.ndarray:
     return out
 
 
+def apply_galois_poly(a, g, q) -> np.ndarray:
+    """a(x) -> a(x^g) in Z_q[x]/(x^n+1), g odd."""
+    a = _u64(a); out = np.zeros_like(a)
+    lib().orc_apply_galois_poly(_p(a), _p(out), C.c_uint32(a.size), C.c_uint32(g), C.c_uint64(q))
+    return out
+
+
 def modswitch_drop_last(x, moduli) -> np.ndarray:
     x = _u64(x); moduli = _u64(moduli)
     limbs = len(moduli); n = x.size // limbs
@@ -384,6 +391,23 @@ class Bfv:
 
     def batch_decode(self, pt):
         return ntt_forward(pt, self.t)
+
+    # Galois automorphisms / rotations and the modulus chain (declared only in the reference: include/fhe.cuh:59-61,86,109-116)
+    def galois_keygen(self, seed, g, sk):
+        gk = np.zeros((self.dnum, 2, self.L + self.K, self.n), np.uint64)
+        lib().orc_bfv_galois_keygen(C.c_void_p(self.h), C.c_uint64(seed), C.c_uint32(g), _p(sk.reshape(-1)), _p(self.cdt),
+                                    len(self.cdt), _p(gk.reshape(-1)))
+        return gk
+
+    def apply_galois(self, ct, g, gk):
+        out = np.zeros((2, self.L, self.n), np.uint64)
+        lib().orc_bfv_apply_galois(C.c_void_p(self.h), _p(_u64(ct).reshape(-1)), C.c_uint32(g), _p(gk.reshape(-1)), _p(out.reshape(-1)))
+        return out
+
+    def mod_switch_to_next(self, ct):
+        out = np.zeros((2, self.L - 1, self.n), np.uint64)
+        lib().orc_bfv_mod_switch_to_next(C.c_void_p(self.h), _p(_u64(ct).reshape(-1)), _p(out.reshape(-1)))
+        return out
 
     def multiply_relin(self, a, b, rlk, want_scaled=False):
         out = np.zeros((2, self.L, self.n), np.uint64)

@@ -267,12 +267,52 @@ void orc_bfv_add(const orc_bfv *c, const u64 *a, const u64 *b, u64 *out) {
         for (u32 j = 0; j < n; j++) out[(size_t)p * n + j] = orc_addmod(a[(size_t)p * n + j], b[(size_t)p * n + j], q); }
 }
 
+/* Hybrid key switching (docs/ARCHITECTURE.md:319-326; the reference's relinearize, src/fhe.cu:226-235, is a stub):
+ *   out_p = add_p + ModDown( sum_digits ModUp(x digit) * key[digit][p] ),  p = 0, 1;  add_p may be NULL.
+ * x, add_p: [L][n] coefficient form; key: [dnum][2][L+K][n] NTT form; out: [2][L][n] coefficient form. */
+static void key_switch(const orc_bfv *c, const u64 *x, const u64 *key, const u64 *add0, const u64 *add1, u64 *out) {
+    u32 n = c->n, L = c->L, K = c->K, W = L + K, alpha = c->alpha;
+    u64 *acc = (u64 *)calloc(2 * (size_t)W * n, sizeof(u64));
+    u64 *dig = (u64 *)malloc((size_t)W * n * sizeof(u64));
+    u64 *conv = (u64 *)malloc((size_t)W * n * sizeof(u64));
+    for (u32 dg = 0; dg < c->dnum; dg++) {
+        orc_lc_apply(c->modup[dg], conv, x + (size_t)dg * alpha * n, NULL, n);    /* ModUp */
+        u32 nt = W - alpha;
+        for (u32 k = 0; k < nt; k++) memcpy(dig + (size_t)c->modup_targets[dg][k] * n, conv + (size_t)k * n, n * sizeof(u64));
+        for (u32 i = dg * alpha; i < (dg + 1) * alpha; i++) memcpy(dig + (size_t)i * n, x + (size_t)i * n, n * sizeof(u64));
+        for (u32 i = 0; i < W; i++) {
+            u64 q = c->primes[i]; u64 *v = dig + (size_t)i * n;
+            fwd_limb(c, v, i);
+            const u64 *kb = key + ((size_t)(dg * 2 + 0) * W + i) * n, *ka = key + ((size_t)(dg * 2 + 1) * W + i) * n;
+            u64 *s0 = acc + (size_t)i * n, *s1 = acc + (size_t)(W + i) * n;
+            for (u32 j = 0; j < n; j++) {
+                s0[j] = orc_addmod(s0[j], orc_mulmod(v[j], kb[j], q), q);
+                s1[j] = orc_addmod(s1[j], orc_mulmod(v[j], ka[j], q), q);
+            }
+        }
+    }
+    for (int p = 0; p < 2; p++) {
+        u64 *s = acc + (size_t)p * W * n;
+        const u64 *add = p ? add1 : add0;
+        for (u32 i = 0; i < W; i++) inv_limb(c, s + (size_t)i * n, i);
+        orc_lc_apply(c->moddown, conv, s + (size_t)L * n, NULL, n);                /* [s]_P -> Q (centred) */
+        for (u32 i = 0; i < L; i++) {
+            u64 q = c->primes[i];
+            for (u32 j = 0; j < n; j++) {
+                u64 v = orc_mulmod(orc_submod(s[(size_t)i * n + j], conv[(size_t)i * n + j], q), c->pinv_mod_q[i], q);
+                out[((size_t)p * L + i) * n + j] = add ? orc_addmod(add[(size_t)i * n + j], v, q) : v;
+            }
+        }
+    }
+    free(acc); free(dig); free(conv);
+}
+
 /* ---------- multiply + relinearize --------------------------------------- */
 /* stage outputs are optional (NULL to skip) so tests can pin each step:
  *   d_scaled: [3][L][n]  round(t/Q * tensor) in basis Q, coefficient form (before relinearisation)
  *   out     : [2][L][n]  relinearised ciphertext, coefficient form */
 void orc_bfv_multiply_relin(const orc_bfv *c, const u64 *cta, const u64 *ctb, const u64 *rlk, u64 *out, u64 *d_scaled) {
-    u32 n = c->n, L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, alpha = c->alpha;
+    u32 n = c->n, L = c->L, R = c->R, A = L + R;
     size_t pn = (size_t)A * n;
     u64 *ext = (u64 *)malloc(4 * pn * sizeof(u64));       /* a0,a1,b0,b1 over Q u R */
     u64 *d = (u64 *)malloc(3 * pn * sizeof(u64));         /* tensor over Q u R */
@@ -301,40 +341,9 @@ void orc_bfv_multiply_relin(const orc_bfv *c, const u64 *cta, const u64 *ctb, co
         orc_lc_apply(c->r2q, sc + (size_t)p * L * n, tmpR, NULL, n);               /* 6. exact R -> Q      */
     }
     if (d_scaled) memcpy(d_scaled, sc, 3 * (size_t)L * n * sizeof(u64));
-    /* 7. relinearise d2: hybrid key switching */
-    const u64 *d2 = sc + 2 * (size_t)L * n;
-    u64 *acc = (u64 *)calloc(2 * (size_t)W * n, sizeof(u64));
-    u64 *dig = (u64 *)malloc((size_t)W * n * sizeof(u64));
-    u64 *conv = (u64 *)malloc((size_t)W * n * sizeof(u64));
-    for (u32 dg = 0; dg < c->dnum; dg++) {
-        orc_lc_apply(c->modup[dg], conv, d2 + (size_t)dg * alpha * n, NULL, n);    /* ModUp */
-        u32 nt = W - alpha;
-        for (u32 k = 0; k < nt; k++) memcpy(dig + (size_t)c->modup_targets[dg][k] * n, conv + (size_t)k * n, n * sizeof(u64));
-        for (u32 i = dg * alpha; i < (dg + 1) * alpha; i++) memcpy(dig + (size_t)i * n, d2 + (size_t)i * n, n * sizeof(u64));
-        for (u32 i = 0; i < W; i++) {
-            u64 q = c->primes[i]; u64 *x = dig + (size_t)i * n;
-            fwd_limb(c, x, i);
-            const u64 *kb = rlk + ((size_t)(dg * 2 + 0) * W + i) * n, *ka = rlk + ((size_t)(dg * 2 + 1) * W + i) * n;
-            u64 *s0 = acc + (size_t)i * n, *s1 = acc + (size_t)(W + i) * n;
-            for (u32 j = 0; j < n; j++) {
-                s0[j] = orc_addmod(s0[j], orc_mulmod(x[j], kb[j], q), q);
-                s1[j] = orc_addmod(s1[j], orc_mulmod(x[j], ka[j], q), q);
-            }
-        }
-    }
-    for (int p = 0; p < 2; p++) {
-        u64 *s = acc + (size_t)p * W * n;
-        for (u32 i = 0; i < W; i++) inv_limb(c, s + (size_t)i * n, i);
-        orc_lc_apply(c->moddown, conv, s + (size_t)L * n, NULL, n);                /* [s]_P -> Q (centred) */
-        for (u32 i = 0; i < L; i++) {
-            u64 q = c->primes[i];
-            for (u32 j = 0; j < n; j++) {
-                u64 v = orc_mulmod(orc_submod(s[(size_t)i * n + j], conv[(size_t)i * n + j], q), c->pinv_mod_q[i], q);
-                out[((size_t)p * L + i) * n + j] = orc_addmod(sc[((size_t)p * L + i) * n + j], v, q);
-            }
-        }
-    }
-    free(ext); free(d); free(sc); free(tmpR); free(acc); free(dig); free(conv);
+    /* 7. relinearise d2: hybrid key switching, added onto (d0, d1) */
+    key_switch(c, sc + 2 * (size_t)L * n, rlk, sc, sc + (size_t)L * n, out);
+    free(ext); free(d); free(sc); free(tmpR);
 }
 
 /* ---------- plaintext operands and subtraction (declared only in the reference: include/fhe.cuh:98-104) -------------- */
@@ -371,4 +380,59 @@ void orc_bfv_multiply_plain(const orc_bfv *c, const u64 *ct, const u64 *pt, u64 
         }
     }
     free(m);
+}
+
+/* ---------- Galois automorphisms and rotations (declared only in the reference: include/fhe.cuh:59-61,86,113-116) -------- */
+/* out(x) = in(x^g) in Z_q[x]/(x^n+1), g odd: coefficient i moves to i*g mod 2n, negated when that index is >= n */
+void orc_apply_galois_poly(const u64 *in, u64 *out, u32 n, u32 g, u64 q) {
+    for (u32 i = 0; i < n; i++) {
+        u32 t = (u32)(((u64)i * g) & (2 * (u64)n - 1));
+        if (t < n) out[t] = in[i]; else out[t - n] = in[i] ? q - in[i] : 0;
+    }
+}
+/* gk: [dnum][2][L+K][n] NTT form;  b_d = -a_d s + e_d + P*B_d*s(x^g): switches a ciphertext component under s(x^g) back to s.
+ * Streams as for the relinearisation key (so seeds must differ between keys). */
+void orc_bfv_galois_keygen(const orc_bfv *c, u64 seed, u32 g, const u64 *sk_ntt, const u64 *cdt, u32 cdt_len, u64 *gk) {
+    u32 n = c->n, L = c->L, K = c->K, W = L + K;
+    int64_t *e = (int64_t *)malloc(n * sizeof(int64_t));
+    u64 *sg = (u64 *)malloc((size_t)W * n * sizeof(u64)), *tmp = (u64 *)malloc(n * sizeof(u64));
+    for (u32 i = 0; i < W; i++) {                                  /* s(x^g) per limb, NTT form */
+        memcpy(tmp, sk_ntt + (size_t)i * n, n * sizeof(u64));
+        inv_limb(c, tmp, i);
+        orc_apply_galois_poly(tmp, sg + (size_t)i * n, n, g, c->primes[i]);
+        fwd_limb(c, sg + (size_t)i * n, i);
+    }
+    for (u32 d = 0; d < c->dnum; d++) {
+        orc_sample_gaussian(e, n, seed, ST_RLK_BASE * (d + 1) + ST_RLK_E, cdt, cdt_len);
+        for (u32 i = 0; i < W; i++) {
+            u64 q = c->primes[i];
+            u64 *b = gk + ((size_t)(d * 2 + 0) * W + i) * n, *a = gk + ((size_t)(d * 2 + 1) * W + i) * n;
+            const u64 *s = sk_ntt + (size_t)i * n, *t = sg + (size_t)i * n;
+            orc_sample_uniform(a, n, q, seed, ST_RLK_BASE * (d + 1) + i);
+            small_to_limb(b, e, n, q); fwd_limb(c, b, i);
+            int in_group = (i < L) && (i / c->alpha == d);
+            u64 f = in_group ? c->p_mod_q[i] : 0;
+            for (u32 j = 0; j < n; j++) {
+                u64 v = orc_submod(b[j], orc_mulmod(a[j], s[j], q), q);
+                if (f) v = orc_addmod(v, orc_mulmod(f, t[j], q), q);
+                b[j] = v;
+            }
+        }
+    }
+    free(e); free(sg); free(tmp);
+}
+/* ct(x) -> ct(x^g) re-encrypted under s: (c0(x^g), 0) + KeySwitch(c1(x^g)).  ct, out: [2][L][n] coefficient form */
+void orc_bfv_apply_galois(const orc_bfv *c, const u64 *ct, u32 g, const u64 *gk, u64 *out) {
+    u32 n = c->n, L = c->L;
+    u64 *r = (u64 *)malloc(2 * (size_t)L * n * sizeof(u64));
+    for (u32 p = 0; p < 2 * L; p++) orc_apply_galois_poly(ct + (size_t)p * n, r + (size_t)p * n, n, g, c->primes[p % L]);
+    key_switch(c, r + (size_t)L * n, gk, r, NULL, out);
+    free(r);
+}
+/* mod_switch_to_next (include/fhe.cuh:109): both components lose the last limb of Q with rounding; the result is a ciphertext
+ * of the same plaintext for the context built on the first L-1 limbs.  ct: [2][L][n] -> out: [2][L-1][n] */
+void orc_modswitch_drop_last(u64 *out, const u64 *in, u32 n, const u64 *moduli, u32 limbs);
+void orc_bfv_mod_switch_to_next(const orc_bfv *c, const u64 *ct, u64 *out) {
+    u32 n = c->n, L = c->L;
+    for (int p = 0; p < 2; p++) orc_modswitch_drop_last(out + (size_t)p * (L - 1) * n, ct + (size_t)p * L * n, n, c->primes, L);
 }

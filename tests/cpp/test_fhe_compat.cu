@@ -138,6 +138,32 @@ static void test_fhe_operations() {              // tests/test_fhe.cu:169-273
         FHEContext::release(e1); FHEContext::release(e2); FHEContext::release(prod); FHEContext::release(sum); FHEContext::release(diff); FHEContext::release(scaled);
         FHEContext::release(b1); FHEContext::release(b2); FHEContext::release(two); FHEContext::release(pp); FHEContext::release(ps); FHEContext::release(pd); FHEContext::release(pq);
     }
+    // rotations (include/fhe.cuh:113-116, declared only in the reference): the slot at NTT position k holds the evaluation at
+    // psi^(2 bitrev(k) + 1); x -> x^g sends the value of position k' to position k with exponent(k') = exponent(k) * g mod 2N
+    {
+        BatchEncoder enc(ctx);
+        GaloisKeys gk; ctx.galoiskey_gen(gk, sk);
+        REQUIRE(gk.gal_keys.size() == 12);                          // 3^(2^k), k = 0..10, and 2N - 1
+        const uint32_t n = 4096, lg = 12;
+        std::vector<uint64_t> vals(n); for (uint32_t i = 0; i < n; i++) vals[i] = (i * 7 + 3) % 65537;
+        Plaintext bp; enc.encode(bp, vals);
+        Ciphertext e, r1, r5, r6, cc, c2; ctx.encrypt(e, bp, pk);
+        ctx.rotate_rows(r1, e, 1, gk); ctx.rotate_rows(r5, e, 5, gk); ctx.rotate_rows(r6, r5, 1, gk);
+        ctx.rotate_columns(cc, e, gk); ctx.rotate_columns(c2, cc, gk);
+        auto slots = [&](Ciphertext& c) { Plaintext p; ctx.decrypt(p, c, sk); std::vector<uint64_t> v; enc.decode(v, p); FHEContext::release(p); return v; };
+        auto brev = [&](uint32_t k) { uint32_t r = 0; for (uint32_t b = 0; b < lg; b++) r |= ((k >> b) & 1u) << (lg - 1 - b); return r; };
+        std::vector<uint32_t> pos_of_exp(2 * n, 0);
+        for (uint32_t k = 0; k < n; k++) pos_of_exp[2 * brev(k) + 1] = k;
+        auto expect = [&](uint64_t g) { std::vector<uint64_t> v(n); for (uint32_t k = 0; k < n; k++) v[k] = vals[pos_of_exp[(uint32_t)(((2ull * brev(k) + 1) * g) % (2 * n))]]; return v; };
+        uint64_t g5 = 1; for (int i = 0; i < 5; i++) g5 = g5 * 3 % (2 * n);
+        REQUIRE(slots(r1) == expect(3));
+        REQUIRE(slots(r5) == expect(g5));
+        REQUIRE(slots(r6) == expect(g5 * 3 % (2 * n)));             // rotations compose
+        REQUIRE(slots(cc) == expect(2 * n - 1));
+        REQUIRE(slots(c2) == vals);                                 // the column swap is an involution
+        FHEContext::release(e); FHEContext::release(r1); FHEContext::release(r5); FHEContext::release(r6); FHEContext::release(cc); FHEContext::release(c2);
+        FHEContext::release(bp); FHEContext::release(gk);
+    }
     FHEContext::release(ct1); FHEContext::release(ct2); FHEContext::release(ct_add); FHEContext::release(ct_mul);
     FHEContext::release(pt1); FHEContext::release(pt2); FHEContext::release(pa); FHEContext::release(pm); FHEContext::release(p1); FHEContext::release(pc);
     FHEContext::release(rlk); FHEContext::release(pk); FHEContext::release(sk);

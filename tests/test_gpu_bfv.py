@@ -240,3 +240,62 @@ def test_plain_ops_and_batch_encoding_vs_oracle(fhe, oracle):
     assert np.array_equal(to_host(pa), o.batch_encode([5, 10, 15, 20]))
     prod = g.multiply(g.encrypt(67, pa.view(1, n), pk), g.encrypt(68, pb.view(1, n), pk), rlk)
     assert [int(v) for v in g.batch_decode(g.decrypt(prod, sk))[0, :4]] == [15, 60, 135, 240]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["small", "c2"])
+def test_galois_and_mod_switch_vs_oracle(fhe, oracle, preset):
+    """'next' rows: Galois keys, automorphisms (rotate_rows / rotate_columns) and mod_switch_to_next, bit for bit
+    against the oracle (keys, rotated ciphertexts, switched ciphertexts) and by definition after decryption."""
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, preset)
+    n, t, L = p["n"], p["t"], p["L"]
+    sk, pk = g.keygen(71, 72)
+    _, osk = o.secret_keygen(71)
+    rng = np.random.default_rng(73)
+    m = rng.integers(0, t, (2, n), dtype=np.uint64)
+    ct = g.encrypt(74, to_device(m), pk)
+    h = to_host(ct)
+    for elt in (3, 2 * n - 1, pow(3, 7, 2 * n)):
+        gk = g.galoiskey_gen(80 + elt, elt, sk)
+        ogk = o.galois_keygen(80 + elt, elt, osk)
+        assert np.array_equal(to_host(gk), ogk), elt
+        rot = g.apply_galois(ct, elt, gk)
+        hr = to_host(rot)
+        for b in range(2):
+            assert np.array_equal(hr[b], o.apply_galois(h[b], elt, ogk)), (elt, b)
+            assert np.array_equal(to_host(g.decrypt(rot, sk))[b], oracle.apply_galois_poly(m[b], elt, t)), (elt, b)
+    # helpers: rotate_rows(steps) = x -> x^(3^steps), rotate_columns = x -> x^(2N-1)
+    gk1 = g.galoiskey_gen(90, 3, sk)
+    assert torch.equal(g.rotate_rows(ct, 1, gk1), g.apply_galois(ct, 3, gk1))
+    # modulus chain
+    low = to_host(g.mod_switch_to_next(ct))
+    assert low.shape == (2, 2, L - 1, n)
+    for b in range(2):
+        assert np.array_equal(low[b], o.mod_switch_to_next(h[b])), b
+    if L - 1 >= 1:
+        primes = list(p["primes"][:L - 1]) + list(p["primes"][L:])
+        lo = oracle.Bfv(n, L - 1, p["R"], p["K"], 1, t, primes, sigma=p["sigma"], hw=p["hamming_weight"])
+        _, lsk = lo.secret_keygen(71)
+        for b in range(2):
+            assert np.array_equal(lo.decrypt(low[b], lsk), m[b]), b
+
+
+@pytest.mark.gpu
+def test_galois_config4_properties(fhe, oracle):
+    """config 4 size: decrypt(apply_galois(enc m, g)) = m(x^g) for a row rotation and the column swap; rotations compose."""
+    from fhe_b200.engine import to_device, to_host
+    from fhe_b200.params import bfv_preset
+    p = bfv_preset("c4"); n, t = p["n"], p["t"]
+    g = fhe.BfvContext(n, p["L"], p["R"], p["K"], p["dnum"], t, p["primes"], p["sigma"], p["hamming_weight"])
+    sk, pk = g.keygen(1, 2)
+    rng = np.random.default_rng(9)
+    m = rng.integers(0, t, (1, n), dtype=np.uint64)
+    ct = g.encrypt(3, to_device(m), pk)
+    g3 = g.galoiskey_gen(4, 3, sk); gc = g.galoiskey_gen(5, 2 * n - 1, sk)
+    r = g.rotate_rows(ct, 1, g3)
+    assert np.array_equal(to_host(g.decrypt(r, sk))[0], oracle.apply_galois_poly(m[0], 3, t))
+    rr = g.rotate_rows(r, 1, g3)
+    assert np.array_equal(to_host(g.decrypt(rr, sk))[0], oracle.apply_galois_poly(m[0], 9, t))
+    c = g.rotate_columns(g.rotate_columns(ct, gc), gc)
+    assert np.array_equal(to_host(g.decrypt(c, sk))[0], m[0])

@@ -237,3 +237,66 @@ def test_bfv_plain_ops_and_batch_encoding(oracle, chain):
     assert d(ctx.multiply_relin(e([3, 4, 5, 6]), e([2, 5, 10, 3]), rlk)) == [6, 20, 50, 18]
     assert d(ctx.add(e([10, 20, 30, 40]), e([5, 15, 25, 35]))) == [15, 35, 55, 75]
     assert d(ctx.multiply_plain(e([10, 20, 30, 40]), ctx.batch_encode([2] * n))) == [20, 40, 60, 80]
+
+
+def _galois_ref(a, g, q):
+    """a(x) -> a(x^g) mod (x^n + 1, q), written out from the definition."""
+    n = len(a); out = [0] * n
+    for i, v in enumerate(a):
+        e = (i * g) % (2 * n)
+        if e < n: out[e] = (out[e] + int(v)) % q
+        else: out[e - n] = (out[e - n] - int(v)) % q
+    return out
+
+
+def test_galois_keys_rotation_and_mod_switch(oracle, chain, small_bfv):
+    """'next' rows: Galois keys + automorphisms (rotate_rows / rotate_columns, include/fhe.cuh:86,113-116)
+    and mod_switch_to_next (include/fhe.cuh:109).  Pinned by definition: the automorphism against x -> x^g written out, the key
+    as an RLWE sample of P*B_d*s(x^g), decrypt(apply_galois(enc m)) = m(x^g), the slot permutation k -> k' with
+    (2 bitrev(k') + 1) = (2 bitrev(k) + 1) g mod 2N under batch encoding, and decryption under the (L-1)-limb context."""
+    ctx, s, sk, pk, rlk = small_bfv
+    n, L, K, t = ctx.n, ctx.L, ctx.K, ctx.t
+    qs = chain[:L]; Q = prod(qs)
+    sl = [int(v) for v in s]
+    rng = np.random.default_rng(71)
+    a = rng.integers(0, qs[0], n, dtype=np.uint64)
+    for g in (3, 9, 2 * n - 1, 5, 27):
+        assert [int(v) for v in oracle.apply_galois_poly(a, g, qs[0])] == _galois_ref(a, g, qs[0])
+    W = chain[:L + K]; QP = prod(W); P = prod(chain[L:L + K])
+    m = rng.integers(0, t, n, dtype=np.uint64)
+    ct = ctx.encrypt(301, m, pk)
+    lg = n.bit_length() - 1
+    brev = lambda k: int(format(k, f"0{lg}b")[::-1], 2)
+    for g in (3, 2 * n - 1, 3 ** 5 % (2 * n)):
+        gk = ctx.galois_keygen(400 + g, g, sk)
+        # gk_d: b + a*s - P*B_d*s(x^g) = e_d (small) mod QP
+        sg = [centred(v, Q * P) for v in _galois_ref([v % QP for v in sl], g, QP)]
+        for d in range(ctx.dnum):
+            grp = qs[d * ctx.alpha:(d + 1) * ctx.alpha]
+            Qd = prod(grp); Qh = Q // Qd
+            B = Qh * pow(Qh, -1, Qd)
+            b = poly_from_rns([oracle.ntt_inverse(gk[d, 0, i], W[i]) for i in range(L + K)], W)
+            aa = poly_from_rns([oracle.ntt_inverse(gk[d, 1, i], W[i]) for i in range(L + K)], W)
+            e = [centred(bb + x - P * B * ss, QP) for bb, x, ss in zip(b, negacyclic_mul(aa, sl, n), sg)]
+            assert max(abs(v) for v in e) <= 20
+        rot = ctx.apply_galois(ct, g, gk)
+        assert [int(v) for v in ctx.decrypt(rot, sk)] == _galois_ref(m, g, t)
+        # the rotated ciphertext is a fresh-looking encryption under s: c0 + c1 s = Delta m(x^g) + small
+        c0 = poly_from_rns(rot[0], qs); c1 = poly_from_rns(rot[1], qs)
+        x = [centred(u + v, Q) for u, v in zip(c0, negacyclic_mul(c1, sl, n))]
+        noise = [centred(xx - (Q // t) * mm, Q) for xx, mm in zip(x, _galois_ref(m, g, t))]
+        assert max(abs(v) for v in noise) < 2**40
+        # slots (t = 65537 = 1 mod 2N): decode(m(x^g))[k] = decode(m)[k'] with exponent(k') = exponent(k) * g
+        slots = ctx.batch_decode(m); rslots = ctx.batch_decode(ctx.decrypt(rot, sk))
+        inv = {2 * brev(k) + 1: k for k in range(n)}
+        for k in range(n):
+            assert rslots[k] == slots[inv[((2 * brev(k) + 1) * g) % (2 * n)]]
+    # modulus chain: drop q_{L-1} with rounding; same plaintext under the context on the first L-1 limbs (same secret seed)
+    low = oracle.Bfv(n, L - 1, ctx.R, K, 1, t, list(chain[:L - 1]) + list(chain[L:L + ctx.R]), sigma=3.2, hw=8)
+    s2, sk2 = low.secret_keygen(101)
+    assert np.array_equal(s2, s)
+    ct2 = ctx.mod_switch_to_next(ct)
+    assert ct2.shape == (2, L - 1, n)
+    assert np.array_equal(low.decrypt(ct2, sk2), m)
+    for p in range(2):
+        assert np.array_equal(ct2[p], oracle.modswitch_drop_last(ct[p], qs))
