@@ -23,6 +23,12 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
     from fhe_b200.params import bfv_preset
 
     torch.cuda.set_device(local_rank)
+    if dist is not None:
+        try:
+            from bench import bind_to_gpu_numa_node
+            bind_to_gpu_numa_node(local_rank)
+        except Exception:
+            pass
     p = bfv_preset(preset)
     n, L, t = p["n"], p["L"], p["t"]
     B = batch or 4

@@ -37,6 +37,23 @@ __device__ __forceinline__ void mma_u8(int (&d)[4], const u32 (&a)[4], const uin
 
 __device__ __forceinline__ u64 shfl_x64(u64 v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
+// sum_c p[c] * 2^(8c), c = 0..14, every p[c] < 2^31, as a 128-bit value (the caller guarantees it fits).  Grouped by c mod 4 the
+// partial sums are the 32-bit digits of four 128-bit numbers E_r; E_r << 8r is four funnel shifts, and the three additions are
+// plain carry chains -- all on 32-bit registers (written with 64-bit integers the compiler pairs the accumulator registers up
+// and spends ~30 moves per value doing so).
+__device__ __forceinline__ void assemble128(const u32 (&p)[16], u64& hi, u64& lo) {
+    u32 v0 = p[0], v1 = p[4], v2 = p[8], v3 = p[12];
+#pragma unroll
+    for (int r = 1; r < 4; r++) {
+        const u32 d0 = p[r], d1 = p[r + 4], d2 = p[r + 8], d3 = (r + 12 < 15) ? p[r + 12] : 0u;
+        const u32 w0 = d0 << (8 * r), w1 = __funnelshift_l(d0, d1, 8 * r), w2 = __funnelshift_l(d1, d2, 8 * r),
+                  w3 = __funnelshift_l(d2, d3, 8 * r);
+        asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, %3, %7;"
+            : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3) : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+    }
+    lo = ((u64)v1 << 32) | v0; hi = ((u64)v3 << 32) | v2;
+}
+
 // Persistent CTAs: the whole B-fragment table (NG * KT * 2 KiB) is staged in shared memory once per CTA, then the CTA's warps
 // walk the coefficient tiles with a grid stride.  (Reading the fragments through L1 instead left the tensor pipe 29% busy with
 // long_scoreboard the top stall: ncu, profiles/r01_lincomb_mma_ncu_summary.md.)
@@ -149,16 +166,12 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
         const u64 m = sDst[k], mh = sDst[a.T + k], ml = sDst[2 * a.T + k];
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            // partial sum of weight 2^(8c) is acc[c / 2][2 r + (c & 1)], c = 0..14; group by c mod 4 into four 128-bit numbers
-            // whose 32-bit digits are the partial sums themselves (each < 2^31), then add them shifted by 0, 8, 16, 24 bits
-            auto P = [&](int c) -> u32 { return (u32)acc[c >> 1][2 * r + (c & 1)]; };
-            auto E = [&](int c0) -> unsigned __int128 {
-                const u64 lo = (u64)P(c0) | ((u64)P(c0 + 4) << 32);
-                const u64 hi = (u64)P(c0 + 8) | (c0 + 12 < 15 ? (u64)P(c0 + 12) << 32 : 0);
-                return ((unsigned __int128)hi << 64) | lo;
-            };
-            const unsigned __int128 V = E(0) + (E(1) << 8) + (E(2) << 16) + (E(3) << 24);
-            u64 ah = (u64)(V >> 64), al = (u64)V;
+            // partial sum of weight 2^(8c) is acc[c / 2][2 r + (c & 1)], c = 0..14
+            u32 pc[16];
+#pragma unroll
+            for (int cc = 0; cc < 16; cc++) pc[cc] = (u32)acc[cc >> 1][2 * r + (cc & 1)];
+            u64 ah, al;
+            assemble128(pc, ah, al);
             const uint32_t j = j0 + 8 * r;
             if (a.c_is_one) add128(ah, al, I_hi[r], I_lo[r]); else mac128(ah, al, I_lo[r], sDst[3 * a.T + k]);
             if (a.use_extra) mac128(ah, al, ex[r], sDst[4 * a.T + k]);
