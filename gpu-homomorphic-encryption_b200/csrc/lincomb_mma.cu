@@ -23,7 +23,7 @@ namespace fhe_b200 {
 struct LcMmaArgs {
     const u64 *src_mod, *pre, *pre_s, *th_hi, *th_lo;      // [>= S]
     const u64 *dst_mod, *mu_hi, *mu_lo, *c, *lam;          // [T]
-    const uint2* bfrag;                                    // [NG][KT][8][32]
+    const uint2* bfrag;                                    // [NG][KT][4][32][2]: n-tiles (2j, 2j+1) of a lane adjacent
     LcView v;
     uint32_t S, T, NG, logn, use_pre, use_extra, c_is_one;
     size_t tiles;                                          // batch * n / 16
@@ -156,11 +156,15 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
                 }
             }
         }
-        const uint2* bf = sB + (size_t)G * KT * 8 * 32 + lane;
+        const uint4* bf = reinterpret_cast<const uint4*>(sB) + (size_t)G * KT * 4 * 32 + lane;       // two n-tiles per 16-byte load
 #pragma unroll
         for (int kt = 0; kt < KT; kt++) {
 #pragma unroll
-            for (int t = 0; t < 8; t++) mma_u8(acc[t], A[kt], bf[(kt * 8 + t) * 32]);
+            for (int t2 = 0; t2 < 4; t2++) {
+                const uint4 bb = bf[(kt * 4 + t2) * 32];
+                mma_u8(acc[2 * t2], A[kt], make_uint2(bb.x, bb.y));
+                mma_u8(acc[2 * t2 + 1], A[kt], make_uint2(bb.z, bb.w));
+            }
         }
         if (!live) continue;
         const u64 m = sDst[k], mh = sDst[a.T + k], ml = sDst[2 * a.T + k];
@@ -198,7 +202,7 @@ uint32_t lincomb_mma_pad_kt(uint32_t S) {
     return 0;
 }
 
-// host: B fragments [NG][KT][8 n-tiles][32 lanes] of the Toeplitz byte matrix (see the header comment)
+// host: B fragments [NG][KT][4 n-tile pairs][32 lanes][2] of the Toeplitz byte matrix (see the header comment)
 void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<uint2>& out) {
     const uint32_t NG = (h.T + 3) / 4;
     out.assign((size_t)NG * KT * 8 * 32, make_uint2(0, 0));
@@ -219,7 +223,7 @@ void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<ui
                         b0 |= mbyte(i, k, c - by) << (8 * by);                // rows (i, a = by)
                         b1 |= mbyte(i, k, c - 4 - by) << (8 * by);            // rows (i, a = 4 + by)
                     }
-                    out[(((size_t)G * KT + kt) * 8 + t) * 32 + lane] = make_uint2(b0, b1);
+                    out[((((size_t)G * KT + kt) * 4 + t / 2) * 32 + lane) * 2 + (t & 1)] = make_uint2(b0, b1);   // n-tiles 2j, 2j+1 adjacent
                 }
 }
 
