@@ -75,6 +75,18 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
         breakdown[name] = {"launches": n_l.value, "ms": round(t_ms.value, 4)}
     breakdown["whole_call_ms"] = round(e2.elapsed_time(e3), 4)
     lib.fhe_b200_profile_enable(0)
+    # the other two operations of the path: public-key encryption and decryption of the same batch (device-resident, CUDA events)
+    def timed(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    d_m1 = to_device(m1)
+    enc_ms = timed(lambda: g.encrypt(10, d_m1, pk))
+    dec_ms = timed(lambda: g.decrypt(out, sk))
     # correctness of what was timed: decrypt one result
     import oracle
     dec = to_host(g.decrypt(out, sk))
@@ -100,7 +112,9 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
             "decrypts_to_product": ok, "gpu_launches": int(launches), "kernel_ms_per_call": breakdown,
             "e2e": {"value": B * e2e_steps / e2e, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
                     "matches_device_path": ok2},
-            "limb_ntts_per_op": 4 * (L + p["R"]) + 3 * (L + p["R"]) + p["dnum"] * (L + p["K"]) + 2 * (L + p["K"])}
+            "limb_ntts_per_op": 4 * (L + p["R"]) + 3 * (L + p["R"]) + p["dnum"] * (L + p["K"]) + 2 * (L + p["K"]),
+            "encrypt": {"value": B / (enc_ms / 1e3), "unit": "ops/s", "ms_per_op": enc_ms / B, "limb_ntts_per_op": 3 * L},
+            "decrypt": {"value": B / (dec_ms / 1e3), "unit": "ops/s", "ms_per_op": dec_ms / B, "limb_ntts_per_op": 2 * L}}
 
 
 if __name__ == "__main__":

@@ -622,10 +622,11 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     // 1. the four input polynomials into ext: Q limbs copied, R limbs by exact conversion Q -> R
     for (int p = 0; p < 4; p++) {
         const uint64_t* src = (p < 2 ? d_a : d_b) + (size_t)(p & 1) * ln;           // component p&1 of every ciphertext: stride 2*ln
-        uint64_t* dst = ext + (size_t)p * B * an;
-        COPY2D(dst, an, src, 2 * ln, ln, B);
-        LcView v; v.in = src; v.in_stride = 2 * ln; v.out = dst + ln; v.out_stride = an;
-        STEP(lincomb_launch(c->q2r, v, n, B, st));
+        COPY2D(ext + (size_t)p * B * an, an, src, 2 * ln, ln, B);
+    }
+    if (e == cudaSuccess) {                                                           // one launch for all 4B polynomials
+        LcView v; v.in = ext; v.in_stride = an; v.out = ext + ln; v.out_stride = an;
+        STEP(lincomb_launch(c->q2r, v, n, 4 * B, st));
     }
     // 2. NTT over Q u R, 3. tensor, 4. INTT
     STEP(launch_ntt(c->plan, ext, ext, 4 * B, 0, A, false, st));
