@@ -226,6 +226,13 @@ extern "C" int fhe_b200_negacyclic_mul(fhe_b200_plan* plan, uint64_t* d_out, con
     const size_t bytes = (size_t)batch * limb_count * plan->n * sizeof(uint64_t);
     if (!bytes) return 0;
     FHE_CUDA(cudaSetDevice(plan->device));
+    // N <= 4096: one fused kernel (both forward transforms, the pointwise product and the inverse in shared memory) while the
+    // grid is small enough that its single CTA per SM does not cost throughput; FHE_B200_MUL_FUSED = 0 | 1 overrides
+    if (plan->logn <= 12) {
+        static const int env = getenv("FHE_B200_MUL_FUSED") ? atoi(getenv("FHE_B200_MUL_FUSED")) : -1;
+        const bool fused = env >= 0 ? env != 0 : (size_t)batch * limb_count <= (size_t)4 * plan->sm_count;
+        if (fused) return launch_negacyclic_mul_fused(plan, d_out, d_a, d_b, batch, limb_begin, limb_count, st);
+    }
     uint64_t* tmp = nullptr;                       // NTT(b); NTT(a) goes straight into d_out
     FHE_CUDA(cudaMallocAsync(&tmp, bytes, st));
     int rc = launch_ntt(plan, tmp, d_b, batch, limb_begin, limb_count, false, st);

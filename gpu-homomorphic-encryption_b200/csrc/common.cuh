@@ -76,6 +76,8 @@ int launch_elementwise(fhe_b200_plan* plan, EwOp op, uint64_t* d_out, const uint
                        const uint64_t* d_c, uint32_t batch, uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
 int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
                    uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st);
+int launch_negacyclic_mul_fused(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, uint32_t batch,
+                                uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
 int check_range(const fhe_b200_plan* plan, uint32_t batch, uint32_t limb_begin, uint32_t limb_count);
 void release_fused_scratch(const fhe_b200_plan* plan);
 }  // namespace fhe_b200

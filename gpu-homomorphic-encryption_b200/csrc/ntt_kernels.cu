@@ -392,6 +392,106 @@ void release_fused_scratch(const fhe_b200_plan* plan) {
     }
 }
 
+// ================================================ fused negacyclic product (N <= 4096) ===================================
+// out = INTT(NTT(a) . NTT(b)) of one limb-polynomial per CTA, everything in shared memory: replaces the five launches (and the
+// two device allocations) of NTTEngine::multiply, /root/reference/src/ntt.cu:49-75, for the sizes where a transform is a single
+// tile (BASELINE.json config 1).  The forward tile pass leaves the normalised transform in shared memory in exactly the
+// swizzled layout the inverse tile pass starts from, so the two transforms and the pointwise product chain without a copy.
+struct MulArgs {
+    uint64_t* out; const uint64_t *a, *b;
+    const Twiddle *f12, *f3, *i12, *i3;          // staged blocks of both directions, [limbs][1 tile][...]
+    const LimbParams* params;
+    uint32_t n, limb_count, limb_begin, p3n;
+};
+template <int LB>
+struct MulSmem {
+    static constexpr size_t data = (size_t)(1 << LB) * 8, p12 = 256 * sizeof(Twiddle), p3 = (size_t)p3_entries(LB) * sizeof(Twiddle);
+    static constexpr size_t total = 2 * data + 2 * (p12 + p3) + 16;
+};
+template <int LB, int HB, bool NEAR>
+__global__ void __launch_bounds__(1 << (LB - 4), 1) negacyclic_mul_kernel(const MulArgs a) {
+    using F = TileFwd<LB, HB, NEAR>;
+    using I = TileInv<LB, HB, NEAR>;
+    using SM = MulSmem<LB>;
+    extern __shared__ __align__(128) unsigned char raw[];
+    u64* sa = reinterpret_cast<u64*>(raw);
+    u64* sb = reinterpret_cast<u64*>(raw + SM::data);
+    Twiddle* f12 = reinterpret_cast<Twiddle*>(raw + 2 * SM::data);
+    Twiddle* f3 = reinterpret_cast<Twiddle*>(raw + 2 * SM::data + SM::p12);
+    Twiddle* i12 = reinterpret_cast<Twiddle*>(raw + 2 * SM::data + SM::p12 + SM::p3);
+    Twiddle* i3 = reinterpret_cast<Twiddle*>(raw + 2 * SM::data + 2 * SM::p12 + SM::p3);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(raw + 2 * SM::data + 2 * (SM::p12 + SM::p3));
+    const uint32_t tid = threadIdx.x;
+    const uint32_t limb = blockIdx.x % a.limb_count, pl = a.limb_begin + limb;
+    const size_t off = (size_t)blockIdx.x * a.n;                       // [batch][limb_count][n], CTA = (poly, limb)
+    if (tid == 0) {
+        mbar_init(bar, 1); mbar_fence_init();
+        mbar_arrive_expect_tx(bar, (uint32_t)(2 * (SM::p12 + SM::p3)));
+        bulk_copy_g2s(f12, a.f12 + (size_t)pl * 256, (uint32_t)SM::p12, bar);
+        bulk_copy_g2s(f3, a.f3 + (size_t)pl * a.p3n, (uint32_t)SM::p3, bar);
+        bulk_copy_g2s(i12, a.i12 + (size_t)pl * 256, (uint32_t)SM::p12, bar);
+        bulk_copy_g2s(i3, a.i3 + (size_t)pl * a.p3n, (uint32_t)SM::p3, bar);
+    }
+    const LimbParams P = a.params[pl];
+    u64 xa[16], xb[16];
+    F::phase1_load(tid, a.a + off, xa);
+    F::phase1_load(tid, a.b + off, xb);
+    __syncthreads();                                                   // barrier initialised before anyone waits on it
+    mbar_wait(bar, 0);
+    F::template phase1_compute<1>(tid, xa, sa, f12, P);
+    F::template phase1_compute<1>(tid, xb, sb, f12, P);
+    __syncthreads();
+    F::template phase2<1>(tid, sa, f12, P); F::template phase2<1>(tid, sb, f12, P);
+    __syncthreads();
+    F::template phase3<1>(tid, sa, f3, P); F::template phase3<1>(tid, sb, f3, P);
+    __syncthreads();
+    constexpr int NT = 1 << (LB - 4);
+#pragma unroll
+    for (int i = 0; i < 16; i++) { const uint32_t j = tid + i * NT; sa[j] = mul_mod(sa[j], sb[j], P); }     // same layout in both buffers
+    __syncthreads();
+    I::phase2(tid, sa, i3, P);
+    __syncthreads();
+    I::phase3(tid, sa, i12, P);
+    __syncthreads();
+    I::template phase4<true>(tid, a.out + off, sa, i12, P);
+}
+
+template <int LB, int HB, bool NEAR>
+static int run_mul(fhe_b200_plan* plan, const MulArgs& a, uint32_t ctas, cudaStream_t st) {
+    constexpr size_t smem = MulSmem<LB>::total;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FHE_CUDA(cudaFuncSetAttribute(negacyclic_mul_kernel<LB, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    negacyclic_mul_kernel<LB, HB, NEAR><<<ctas, 1 << (LB - 4), smem, st>>>(a);
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+template <int HB, bool NEAR>
+static int dispatch_mul(fhe_b200_plan* plan, const MulArgs& a, uint32_t ctas, cudaStream_t st) {
+    switch (plan->logn) {
+        case 9: return run_mul<9, HB, NEAR>(plan, a, ctas, st);
+        case 10: return run_mul<10, HB, NEAR>(plan, a, ctas, st);
+        case 11: return run_mul<11, HB, NEAR>(plan, a, ctas, st);
+        case 12: return run_mul<12, HB, NEAR>(plan, a, ctas, st);
+    }
+    set_error("fused negacyclic product: N = 2^%u is not a single tile", plan->logn);
+    return FHE_B200_EINVAL;
+}
+// out may alias a or b (every CTA reads its whole inputs before it writes)
+int launch_negacyclic_mul_fused(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, uint32_t batch,
+                                uint32_t limb_begin, uint32_t limb_count, cudaStream_t st) {
+    MulArgs a;
+    a.out = d_out; a.a = d_a; a.b = d_b;
+    a.f12 = plan->d_fwd_p12; a.f3 = plan->d_fwd_p3; a.i12 = plan->d_inv_p12; a.i3 = plan->d_inv_p3;
+    a.params = plan->d_params; a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin; a.p3n = (uint32_t)plan->p3_entries;
+    const uint32_t ctas = batch * limb_count;
+    return plan->near60 ? dispatch_mul<16, true>(plan, a, ctas, st)
+         : plan->hb == 16 ? dispatch_mul<16, false>(plan, a, ctas, st)
+                          : dispatch_mul<8, false>(plan, a, ctas, st);
+}
+
 // ================================================ launch logic =========================================================
 template <int LB, int K1, int HB, bool NEAR>
 static int run_chunk(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t st) {

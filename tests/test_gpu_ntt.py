@@ -183,6 +183,32 @@ def test_config1_negacyclic_product_vs_schoolbook(fhe, oracle, chain):
     assert np.array_equal(to_host(da), oracle.schoolbook_negacyclic(a, b, q))
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("logn", [9, 10, 11, 12])
+def test_negacyclic_mul_fused_and_unfused(fhe, oracle, chain, logn, fused, monkeypatch):
+    """fhe_b200_negacyclic_mul at N <= 4096: the single fused kernel (two forward tile passes, pointwise product and inverse in
+    shared memory) and the four-launch path give the schoolbook product bit for bit; 60- and 61-bit moduli, several limbs and
+    polynomials, worst-case inputs, in place on either operand."""
+    from fhe_b200.engine import to_device, to_host
+    monkeypatch.setenv("FHE_B200_MUL_FUSED", fused)
+    n = 1 << logn
+    rng = np.random.default_rng(40 + logn)
+    for mods in (chain[:3], oracle.prime_chain(2, bits=61)):
+        plan = fhe.Plan(n, mods)
+        a = _rand(rng, mods, n, 2); b = _rand(rng, mods, n, 2)
+        a[0, :, :] = np.array(mods, dtype=np.uint64)[:, None] - np.uint64(1); b[0, 0, :] = np.uint64(mods[0] - 1)
+        want = np.stack([np.stack([oracle.negacyclic_mul_ntt(a[i, l], b[i, l], q) for l, q in enumerate(mods)]) for i in range(2)])
+        assert np.array_equal(want[1, 0], oracle.schoolbook_negacyclic(a[1, 0], b[1, 0], mods[0]))
+        da, db = to_device(a), to_device(b)
+        out = plan.negacyclic_mul(da, db)
+        assert np.array_equal(to_host(out), want)
+        plan.negacyclic_mul(da, db, out=da)               # in place on the first operand
+        assert np.array_equal(to_host(da), want)
+        da = to_device(a)
+        plan.negacyclic_mul(da, db, out=db)               # ... and on the second
+        assert np.array_equal(to_host(db), want)
+
+
 @pytest.mark.parametrize("vec", ["zero", "qm1", "delta0", "deltaN", "iota"])
 def test_edge_vectors(fhe, oracle, chain, vec):
     from fhe_b200.engine import to_device, to_host
