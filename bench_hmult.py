@@ -12,6 +12,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def _floor(n, L, R, K, dnum, ms_per_op, sms=148, mhz=1965.0):
+    logn = n.bit_length() - 1
+    ntts = 4 * (L + R) + 3 * (L + R) + dnum * (L + K) + 2 * (L + K)
+    alpha = L // dnum
+    macs = 4 * L * R + 3 * L * R + 3 * R * L + dnum * alpha * (L + K - alpha) + 2 * K * L          # per coefficient
+    lanes_per_s = sms * 4 * 32 * mhz * 1e6
+    ntt_ms = ntts * (n // 2) * logn * 28.0 / lanes_per_s * 1e3
+    conv_ms = macs * n * 16.0 / lanes_per_s * 1e3
+    return {"limb_ntts": ntts, "ntt_ms": ntt_ms, "conversion_macs_per_coefficient": macs, "conversion_ms_if_imad": conv_ms,
+            "floor_ms": ntt_ms + conv_ms, "frac": (ntt_ms + conv_ms) / ms_per_op}
+
+
 def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None):
     """dist: an initialised torch.distributed module for the batch-sharded multi-GPU run (every rank multiplies its own `batch`
     ciphertext pairs with replicated keys -- no data-path collective; the timed region is bracketed by barriers, the time is the
@@ -113,6 +125,9 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
             "e2e": {"value": B * e2e_steps / e2e, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
                     "matches_device_path": ok2},
             "limb_ntts_per_op": 4 * (L + p["R"]) + 3 * (L + p["R"]) + p["dnum"] * (L + p["K"]) + 2 * (L + p["K"]),
+            # integer-pipe floor of one multiply: limb-NTTs at 28 FMA-pipe cycles per warp-butterfly plus the
+            # conversions at four IMAD.WIDE per (source, target) pair -- the second term is what the tensor-core kernel removes
+            "int_pipe_floor": _floor(n, L, p["R"], p["K"], p["dnum"], ms / (B * K)),
             "encrypt": {"value": B / (enc_ms / 1e3), "unit": "ops/s", "ms_per_op": enc_ms / B, "limb_ntts_per_op": 3 * L},
             "decrypt": {"value": B / (dec_ms / 1e3), "unit": "ops/s", "ms_per_op": dec_ms / B, "limb_ntts_per_op": 2 * L}}
 

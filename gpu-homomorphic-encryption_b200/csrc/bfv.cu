@@ -573,10 +573,9 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
     cudaError_t e = cudaSuccess;
     for (uint32_t dg = 0; dg < dnum && !rc; dg++) {
         uint64_t* D = dig + (size_t)dg * B * wn;
-        if (e == cudaSuccess)
-            e = cudaMemcpy2DAsync(D + (size_t)dg * alpha * N, wn * 8, x + (size_t)dg * alpha * N, x_stride * 8, (size_t)alpha * N * 8, B,
-                                  cudaMemcpyDeviceToDevice, st);
+        // the digit's own limbs are written through by the conversion kernel (copy_idx = src_idx)
         LcView v; v.in = x; v.in_stride = x_stride; v.src_idx = c->d_idx_grp[dg]; v.out = D; v.out_stride = wn; v.dst_idx = c->d_idx_tgt[dg];
+        v.copy_out = D; v.copy_stride = wn;
         rc = lincomb_launch(c->modup[dg], v, n, B, st);
     }
     if (e != cudaSuccess) { set_error("key_switch: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
@@ -620,13 +619,12 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
 #define STEP(expr) do { if (!rc) rc = (expr); } while (0)
 #define COPY2D(dst, dpitch, src, spitch, width, rows) do { if (!rc && e == cudaSuccess) e = cudaMemcpy2DAsync(dst, (dpitch) * 8, src, (spitch) * 8, (width) * 8, rows, cudaMemcpyDeviceToDevice, st); } while (0)
     // 1. the four input polynomials into ext: Q limbs copied, R limbs by exact conversion Q -> R
+    //    (the conversion kernel also writes the Q limbs through: no separate copy)
     for (int p = 0; p < 4; p++) {
         const uint64_t* src = (p < 2 ? d_a : d_b) + (size_t)(p & 1) * ln;           // component p&1 of every ciphertext: stride 2*ln
-        COPY2D(ext + (size_t)p * B * an, an, src, 2 * ln, ln, B);
-    }
-    if (e == cudaSuccess) {                                                           // one launch for all 4B polynomials
-        LcView v; v.in = ext; v.in_stride = an; v.out = ext + ln; v.out_stride = an;
-        STEP(lincomb_launch(c->q2r, v, n, 4 * B, st));
+        uint64_t* dst = ext + (size_t)p * B * an;
+        LcView v; v.in = src; v.in_stride = 2 * ln; v.out = dst + ln; v.out_stride = an; v.copy_out = dst; v.copy_stride = an;
+        STEP(lincomb_launch(c->q2r, v, n, B, st));
     }
     // 2. NTT over Q u R, 3. tensor, 4. INTT
     STEP(launch_ntt(c->plan, ext, ext, 4 * B, 0, A, false, st));

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
         u64 x = 0;
         if (i < a.S) {
             x = inb[(size_t)a.v.src_idx[i] * nn];
+            if (a.v.copy_out) a.v.copy_out[(size_t)b * a.v.copy_stride + (size_t)a.v.copy_idx[i] * nn + j] = x;
             if (a.use_pre) x = shoup_mul(x, sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
         }
         u64 ph, pl;
@@ -191,6 +192,8 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     if (!a.v.dst_idx) a.v.dst_idx = lc->id_dst;
     if (!a.v.extra_idx) a.v.extra_idx = lc->id_dst;
     if (!a.v.epi_idx) a.v.epi_idx = lc->id_dst;
+    if (!a.v.copy_idx) a.v.copy_idx = a.v.src_idx;
+    if (!a.v.copy_stride) a.v.copy_stride = a.v.out_stride ? a.v.out_stride : (size_t)lc->T * n;
     if (!a.v.in_stride) a.v.in_stride = (size_t)lc->S * n;
     if (!a.v.out_stride) a.v.out_stride = (size_t)lc->T * n;
     if (!a.v.extra_stride) a.v.extra_stride = (size_t)lc->T * n;

@@ -40,6 +40,9 @@ struct LcView {
     const uint64_t* add = nullptr; size_t add_stride = 0;
     const uint32_t* epi_idx = nullptr;
     const uint64_t* epi_scalar = nullptr;                                                        // [T] device
+    // pass-through: the raw source limbs are also written to copy_out (limb copy_idx[i] of polynomial b at copy_out + b*copy_stride);
+    // saves the separate device-to-device copy when the sources are part of the output polynomial (Q limbs next to the R limbs)
+    uint64_t* copy_out = nullptr; size_t copy_stride = 0; const uint32_t* copy_idx = nullptr;
 };
 
 int lincomb_create(const LincombConsts& consts, int device, fhe_b200_lincomb** out);

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
     constexpr int SP = 4 * KT;
     u64* sSrc = reinterpret_cast<u64*>(lc_smem + (size_t)a.NG * KT * 8 * 32 * sizeof(uint2));
     u64* sOff = sSrc + 5 * SP;                          // element offset of source limb i inside a polynomial
-    u64* sDst = sOff + SP;                              // [6][T]: modulus, mu_hi, mu_lo, c, lam, epilogue scalar
+    u64* sCpy = sOff + SP;                              // element offset of source limb i in the pass-through output
+    u64* sDst = sCpy + SP;                              // [6][T]: modulus, mu_hi, mu_lo, c, lam, epilogue scalar
     u64* sIdx = sDst + 6 * (size_t)a.T;                 // [3][T]: element offsets of the target limb in out / extra / epilogue operands
     const size_t nn = (size_t)1 << a.logn;
     for (uint32_t i = threadIdx.x; i < (uint32_t)SP; i += blockDim.x) {
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
         sSrc[i] = in ? a.src_mod[i] : 3; sSrc[SP + i] = in ? a.pre[i] : 0; sSrc[2 * SP + i] = in ? a.pre_s[i] : 0;
         sSrc[3 * SP + i] = in ? a.th_hi[i] : 0; sSrc[4 * SP + i] = in ? a.th_lo[i] : 0;
         sOff[i] = in ? (u64)a.v.src_idx[i] * nn : 0;
+        sCpy[i] = (in && a.v.copy_out) ? (u64)a.v.copy_idx[i] * nn : 0;
     }
     for (uint32_t k = threadIdx.x; k < a.T; k += blockDim.x) {
         sDst[k] = a.dst_mod[k]; sDst[a.T + k] = a.mu_hi[k]; sDst[2 * a.T + k] = a.mu_lo[k]; sDst[3 * a.T + k] = a.c[k];
@@ -108,6 +110,10 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
     for (int kt = 0; kt < KT; kt++) {
         const uint32_t i = 4 * kt + q;
         if (i >= a.S) { x[kt][0] = 0; x[kt][1] = 0; }
+        else if (a.v.copy_out) {
+            u64* o = a.v.copy_out + (size_t)b * a.v.copy_stride + sCpy[i] + j0;
+            o[0] = x[kt][0]; o[8] = x[kt][1];
+        }
         if (a.use_pre) {
             const u64 pr = sSrc[SP + i], prs = sSrc[2 * SP + i], sm = sSrc[i];
             x[kt][0] = shoup_mul(x[kt][0], pr, prs, sm); x[kt][1] = shoup_mul(x[kt][1], pr, prs, sm);
@@ -229,7 +235,7 @@ void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<ui
 
 template <int KT>
 static int launch_kt(const LcMmaArgs& a, int sm_count, cudaStream_t st) {
-    const size_t smem = (size_t)a.NG * KT * 8 * 32 * sizeof(uint2) + (size_t)(6 * 4 * KT + 9 * a.T) * sizeof(u64);
+    const size_t smem = (size_t)a.NG * KT * 8 * 32 * sizeof(uint2) + (size_t)(7 * 4 * KT + 9 * a.T) * sizeof(u64);
     FHE_REQUIRE(smem <= 220 * 1024, "lincomb (tensor-core path): fragment table of %zu bytes does not fit shared memory", smem);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
