@@ -1,6 +1,7 @@
 #!/bin/bash
-# profiles for the judged state: launch lists of bench.py and of one HMult, full captures of the NTT passes and of the two lincomb kernels.
-# (.ncu-rep files are exported to csv and deleted: gpurun_out/ is only copied back below 64 MiB)
+# profiles for the judged state (run under gpurun): launch lists of bench.py and of one HMult, full ncu captures of the NTT passes
+# and of the two base-conversion kernels; exported to csv (the .ncu-rep files stay on the box: gpurun_out/ is copied back below 64 MiB).
+# Summaries: tools/ncu_summary.py, tools/launch_summary.py, tools/lincomb_profile_summary.py -> profiles/r01_*.md
 mkdir -p gpurun_out
 python bench.py --steps 2 --warmup 3 --no-hmult --no-cpu-baseline > gpurun_out/b28.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r01b_bench.csv python bench.py --steps 2 --warmup 3 --no-hmult --no-cpu-baseline > gpurun_out/ncu_b28.log 2>&1
