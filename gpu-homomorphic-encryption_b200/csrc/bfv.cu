@@ -35,9 +35,9 @@ struct fhe_b200_bfv {
     std::vector<const uint32_t*> d_idx_grp, d_idx_tgt;   // per digit: sources [alpha], targets [L+K-alpha]
     // workspaces, grown on demand and kept (a context is single-threaded by contract, see fhe_b200.h)
     uint64_t* d_ws = nullptr; size_t ws_words = 0;       // multiply / encrypt / decrypt scratch
-    uint64_t* d_io[2] = {nullptr, nullptr}; size_t io_words[2] = {0, 0};   // device staging of the host-buffer entry point
-    cudaStream_t io_stream[2] = {nullptr, nullptr};
-    cudaEvent_t io_done[2] = {nullptr, nullptr};
+    uint64_t* d_io[3] = {nullptr, nullptr, nullptr}; size_t io_words[3] = {0, 0, 0};   // device staging of the host-buffer entry point
+    cudaStream_t io_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t io_done[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace fhe_b200 {
@@ -323,7 +323,7 @@ extern "C" int fhe_b200_bfv_destroy(fhe_b200_bfv* c) {
     for (auto* m : c->modup) fhe_b200_lincomb_destroy(m);
     cudaFree(c->d_consts); cudaFree(c->d_idx);
     cudaFree(c->d_ws);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         cudaFree(c->d_io[i]);
         if (c->io_stream[i]) cudaStreamDestroy(c->io_stream[i]);
         if (c->io_done[i]) cudaEventDestroy(c->io_done[i]);
@@ -718,38 +718,42 @@ extern "C" int fhe_b200_bfv_mod_switch_to_next(fhe_b200_bfv* c, const uint64_t* 
     return fhe_b200_modswitch_drop_last(c->plan, d_out, d_ct, 2 * batch, 0, c->L, stream);
 }
 
-// Host-buffer entry point.  The ciphertext pairs are processed one at a time on two alternating streams, each with its
-// own device staging buffers: the upload of pair i+1 and the download of pair i-1 overlap the multiply of pair i (PCIe is
-// full duplex).  The multiplies themselves are serialised through an event because they share the context workspace.
+// Host-buffer entry point.  Chunks of ciphertext pairs rotate over three streams, each with its own device staging buffers:
+// the upload of chunk k+1 and the download of chunk k-1 overlap the multiply of chunk k (PCIe is full duplex; with two
+// streams the upload of chunk k+2 queued behind the download of chunk k).  The multiplies themselves are serialised through an event because they share the context workspace.
 extern "C" int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* c, const uint64_t* h_a, const uint64_t* h_b, const uint64_t* d_rlk,
                                                 uint64_t* h_out, uint32_t batch) {
     FHE_REQUIRE(c && h_a && h_b && d_rlk && h_out, "bfv_multiply_relin_host: null argument");
     if (!batch) return 0;
     FHE_CUDA(cudaSetDevice(c->device));
     const size_t ct = 2 * (size_t)c->L * c->n;            // words per ciphertext
-    for (int i = 0; i < 2; i++) {
+    // chunk = G ciphertext pairs (about 64 MiB of input, at least one pair); three staging sets on three streams
+    uint32_t G = (uint32_t)(((size_t)64 << 20) / (2 * ct * 8));
+    G = G < 1 ? 1 : (G > batch ? batch : G);
+    for (int i = 0; i < 3; i++) {
         if (!c->io_stream[i]) FHE_CUDA(cudaStreamCreateWithFlags(&c->io_stream[i], cudaStreamNonBlocking));
         if (!c->io_done[i]) FHE_CUDA(cudaEventCreateWithFlags(&c->io_done[i], cudaEventDisableTiming));
-        FHE_TRY(ensure_words(&c->d_io[i], &c->io_words[i], 3 * ct));
+        FHE_TRY(ensure_words(&c->d_io[i], &c->io_words[i], 3 * ct * G));
     }
     // size the shared workspace up front so that no (synchronising) reallocation happens inside the pipeline
     {
         const size_t an = (size_t)(c->L + c->R) * c->n, wn = (size_t)(c->L + c->K) * c->n, rn = (size_t)c->R * c->n, ln = (size_t)c->L * c->n;
-        FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, 7 * an + 3 * rn + 3 * ln + ((size_t)c->dnum + 2) * wn));
+        FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, (size_t)G * (7 * an + 3 * rn + 3 * ln + ((size_t)c->dnum + 2) * wn)));
     }
-    for (uint32_t i = 0; i < batch; i++) {
-        const int s = (int)(i & 1);
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < batch; i += G, k++) {
+        const uint32_t g = i + G <= batch ? G : batch - i;
+        const int s = (int)(k % 3), prev = (int)((k + 2) % 3);
         cudaStream_t st = c->io_stream[s];
         uint64_t* buf = c->d_io[s];
-        FHE_CUDA(cudaMemcpyAsync(buf, h_a + i * ct, ct * 8, cudaMemcpyHostToDevice, st));
-        FHE_CUDA(cudaMemcpyAsync(buf + ct, h_b + i * ct, ct * 8, cudaMemcpyHostToDevice, st));
-        if (i > 0) FHE_CUDA(cudaStreamWaitEvent(st, c->io_done[s ^ 1], 0));      // previous multiply owns the workspace
-        FHE_TRY(fhe_b200_bfv_multiply_relin(c, buf, buf + ct, d_rlk, buf + 2 * ct, nullptr, 1, st));
+        FHE_CUDA(cudaMemcpyAsync(buf, h_a + i * ct, g * ct * 8, cudaMemcpyHostToDevice, st));
+        FHE_CUDA(cudaMemcpyAsync(buf + G * ct, h_b + i * ct, g * ct * 8, cudaMemcpyHostToDevice, st));
+        if (k > 0) FHE_CUDA(cudaStreamWaitEvent(st, c->io_done[prev], 0));      // the previous multiply owns the workspace
+        FHE_TRY(fhe_b200_bfv_multiply_relin(c, buf, buf + G * ct, d_rlk, buf + 2 * G * ct, nullptr, g, st));
         FHE_CUDA(cudaEventRecord(c->io_done[s], st));
-        FHE_CUDA(cudaMemcpyAsync(h_out + i * ct, buf + 2 * ct, ct * 8, cudaMemcpyDeviceToHost, st));
+        FHE_CUDA(cudaMemcpyAsync(h_out + i * ct, buf + 2 * G * ct, g * ct * 8, cudaMemcpyDeviceToHost, st));
     }
-    FHE_CUDA(cudaStreamSynchronize(c->io_stream[0]));
-    FHE_CUDA(cudaStreamSynchronize(c->io_stream[1]));
+    for (int i = 0; i < 3; i++) FHE_CUDA(cudaStreamSynchronize(c->io_stream[i]));
     return 0;
 }
 
