@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(256, 4) bal_a_kernel(const BalArgs a) {
 }
 
 // CTA = kBalBWarps warps = kBalBPairs tile pairs x kBalBGroups polynomial groups: the warps of one pair share its staged
-// twiddle block (8 KiB), so a CTA needs 4 x 8 KiB of twiddles + 8 x 4 KiB of exchange buffers = 64 KiB and three CTAs (24 warps)
-// fit an SM.
+// twiddle block (8 KiB): 4 x 8 KiB of twiddles + 8 x 4 KiB of exchange buffers = 64 KiB per CTA.  Two CTAs (16 warps, 128 registers) per
+// SM is the measured optimum at config 3: 0.645 / 0.611 ms per forward / inverse pass, against 0.666 / 0.618 with three CTAs at 80
+// registers, 0.655 / 0.599 with five 128-thread CTAs at 96, 0.717 / 0.657 with four CTAs at 64 (spills).
 template <int KA, int HB, bool NEAR, bool INV>
 __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(const BalArgs a) {
     using B = BalB<HB, NEAR>;
