@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
     }
 }
 
-#ifndef FHE_BAL_EXPERIMENT          // (build/exp: a scratch TU instantiates single kernels for SASS inspection)
+#ifndef FHE_BAL_EXPERIMENT          // (tools/sass/balexp.cu instantiates single kernels for SASS accounting)
 template <int KA, int HB, bool NEAR>
 static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st) {
     using A = BalA<KA, HB, NEAR>;
