@@ -195,7 +195,8 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    bind_to_gpu_numa_node(local_rank)
+    if world > 1:            # (single-GPU runs keep every host core: the CPU baseline of the same line uses them)
+        bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
