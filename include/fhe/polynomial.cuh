@@ -1,6 +1,8 @@
 // Compat header: fhe::Polynomial / fhe::PolynomialOps (reference: include/polynomial.cuh:10-59, src/polynomial.cu).
 #pragma once
 #include "ntt.cuh"
+#include <cmath>
+#include <vector>
 
 namespace fhe {
 
@@ -48,6 +50,39 @@ public:
     void mul_negacyclic(Polynomial& result, const Polynomial& a, const Polynomial& b) { mul_ntt(result, a, b); }
     void mul_scalar(Polynomial& result, const Polynomial& a, const uint256_t& scalar) { scalar_op(result, a, scalar, true); }
     void add_scalar(Polynomial& result, const Polynomial& a, const uint256_t& scalar) { scalar_op(result, a, scalar, false); }
+    // result = round(q'/q * a) mod q', coefficients of a taken in [0, q)  (declared only in the reference: include/polynomial.cuh:42,
+    // poly_mod_switch_kernel :96-102; "in decrypt q' = t").  Exact (integer fixed point); q' < 2^61 coprime to q.
+    void mod_switch(Polynomial& result, const Polynomial& a, const uint256_t& new_modulus) {
+        const uint32_t n = ntt_engine_->degree();
+        const uint64_t q = modulus_.limbs[0], qn = new_modulus.limbs[0];
+        if (new_modulus.limbs[1] | new_modulus.limbs[2] | new_modulus.limbs[3]) throw std::runtime_error("mod_switch: new modulus must be below 2^61");
+        if (!ms_ || ms_to_ != qn) {
+            if (ms_) fhe_b200_lincomb_destroy(ms_);
+            ms_ = nullptr;
+            int dev = 0; detail::check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+            detail::check(fhe_b200_lincomb_create_scale(&q, 1, nullptr, 0, qn, &qn, 1, 0, dev, &ms_), "mod_switch");
+            ms_to_ = qn;
+        }
+        ua_.reserve(n); ub_.reserve(n);
+        cudaStream_t st = ntt_engine_->stream();
+        detail::check(fhe_b200_unpack_u256(ua_.p, a.coeffs, n, st), "unpack");
+        detail::check(fhe_b200_lincomb_apply(ms_, ub_.p, ua_.p, nullptr, n, 1, st), "mod_switch");
+        detail::check(fhe_b200_pack_u256(result.coeffs, ub_.p, n, st), "pack");
+        result.modulus = new_modulus;
+    }
+    // log2 of the largest centred coefficient magnitude (the reference declares `double estimate_noise(const Polynomial&)`,
+    // include/polynomial.cuh:45, without defining or using it); host-side convenience, synchronises the stream
+    double estimate_noise(const Polynomial& poly) {
+        const uint32_t n = ntt_engine_->degree();
+        std::vector<uint256_t> h(n);
+        detail::check_cuda(cudaStreamSynchronize(ntt_engine_->stream()), "estimate_noise");
+        detail::check_cuda(cudaMemcpy(h.data(), poly.coeffs, (size_t)n * sizeof(uint256_t), cudaMemcpyDeviceToHost), "estimate_noise");
+        const uint64_t q = modulus_.limbs[0];
+        uint64_t worst = 0;
+        for (uint32_t i = 0; i < n; i++) { const uint64_t v = h[i].limbs[0] % q; const uint64_t c = v > q / 2 ? q - v : v; if (c > worst) worst = c; }
+        return worst ? std::log2((double)worst) : 0.0;
+    }
+    ~PolynomialOps() { if (ms_) fhe_b200_lincomb_destroy(ms_); }
 
 private:
     void binary(Polynomial& r, const Polynomial& a, const Polynomial& b, int op) {
@@ -78,6 +113,8 @@ private:
     uint256_t modulus_;
     NTTEngine* ntt_engine_;
     detail::DeviceBuf ua_, ub_;
+    fhe_b200_lincomb* ms_ = nullptr;      // cached mod_switch constants for the last target modulus
+    uint64_t ms_to_ = 0;
 };
 
 }  // namespace fhe

@@ -77,6 +77,30 @@ static void test_polynomial_multiplication() {   // tests/test_fhe.cu:126-167 (+
     std::printf("polynomial multiplication ok\n");
 }
 
+static void test_polynomial_mod_switch() {        // include/polynomial.cuh:42,45 (declared only in the reference)
+    const uint32_t n = 2048; const uint64_t q = 40961, t = 257;     // q = 1 mod 2n; t coprime to q
+    NTTEngine ntt(n, uint256_t(q));
+    PolynomialOps ops(n, uint256_t(q), &ntt);
+    Polynomial a(n, uint256_t(q)), r(n, uint256_t(t));
+    std::vector<uint256_t> h(n);
+    for (uint32_t i = 0; i < n; i++) h[i] = uint256_t(((uint64_t)i * 7919u + 13u) % q);
+    h[0] = uint256_t(0); h[1] = uint256_t(q - 1); h[2] = uint256_t(q / 2); h[3] = uint256_t(q / 2 + 1);
+    CUDA_CHECK(cudaMemcpy(a.coeffs, h.data(), n * sizeof(uint256_t), cudaMemcpyHostToDevice));
+    ops.mod_switch(r, a, uint256_t(t));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<uint256_t> o(n);
+    CUDA_CHECK(cudaMemcpy(o.data(), r.coeffs, n * sizeof(uint256_t), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t v = h[i].limbs[0];
+        const uint64_t want = ((2 * v * t + q) / (2 * q)) % t;       // round(t/q * v) mod t, exact in integers (q odd: no ties)
+        REQUIRE(o[i].limbs[0] == want);
+    }
+    REQUIRE(r.modulus.limbs[0] == t);
+    const double nb = ops.estimate_noise(a);                          // largest centred magnitude is q/2 (coefficients 2 and 3)
+    REQUIRE(nb > 14.3 && nb < 14.33);                                 // log2(20480) = 14.32
+    std::printf("polynomial mod_switch / estimate_noise ok\n");
+}
+
 static void test_rns_context() {
     const uint32_t n = 1024;
     std::vector<uint256_t> primes = generate_rns_primes(40, 3, n);
@@ -181,6 +205,7 @@ int main() {
     test_bigint_arithmetic();
     test_ntt_transform();
     test_polynomial_multiplication();
+    test_polynomial_mod_switch();
     test_rns_context();
     test_fhe_operations();
     test_errors();
