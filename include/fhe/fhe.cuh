@@ -7,7 +7,10 @@
 // polynomials (Polynomial::rns, limb-major uint64_t [L][N]); plaintexts keep the reference's uint256_t coefficients.
 #pragma once
 #include <algorithm>
+#include <cstdio>
+#include <map>
 #include <memory>
+#include <string>
 #include <vector>
 #include "bigint.cuh"
 #include "ntt.cuh"
@@ -323,6 +326,80 @@ private:
     uint32_t slot_count_;
     NTTEngine ntt_;
     detail::DeviceBuf buf_;
+};
+
+// Performance monitoring (include/fhe.cuh:169-198; declared only in the reference).  start_timer / stop_timer bracket work on a
+// stream with CUDA events (the context's stream when one is given, else the legacy default stream); get_stats synchronises the
+// recorded events and fills the reference's PerfStats fields for the operation names "encrypt", "decrypt", "add", "multiply",
+// "relinearize", "mod_switch", "bootstrap"; any other name is timed and listed by print_stats.
+struct PerfStats {
+    double encrypt_time_ms = 0, decrypt_time_ms = 0, add_time_ms = 0, mul_time_ms = 0, relin_time_ms = 0, mod_switch_time_ms = 0,
+           bootstrap_time_ms = 0;
+    uint64_t num_encryptions = 0, num_multiplications = 0, num_bootstraps = 0;
+};
+
+class PerformanceMonitor {
+public:
+    explicit PerformanceMonitor(cudaStream_t stream = nullptr) : stream_(stream) {}
+    ~PerformanceMonitor() { reset(); }
+    PerformanceMonitor(const PerformanceMonitor&) = delete;
+    PerformanceMonitor& operator=(const PerformanceMonitor&) = delete;
+    void start_timer(const std::string& operation) {
+        cudaEvent_t e; detail::check_cuda(cudaEventCreate(&e), "start_timer");
+        detail::check_cuda(cudaEventRecord(e, stream_), "start_timer");
+        if (start_events_.count(operation)) cudaEventDestroy(start_events_[operation]);
+        start_events_[operation] = e;
+    }
+    void stop_timer(const std::string& operation) {
+        auto it = start_events_.find(operation);
+        if (it == start_events_.end()) throw std::runtime_error("stop_timer: no running timer for '" + operation + "'");
+        cudaEvent_t e; detail::check_cuda(cudaEventCreate(&e), "stop_timer");
+        detail::check_cuda(cudaEventRecord(e, stream_), "stop_timer");
+        intervals_.push_back({operation, it->second, e});
+        start_events_.erase(it);
+        record_operation(operation);
+    }
+    void record_operation(const std::string& op_name) { counts_[op_name]++; }
+    PerfStats get_stats() const {
+        PerfStats s;
+        for (const auto& kv : totals()) {
+            const std::string& k = kv.first; const double ms = kv.second;
+            if (k == "encrypt") s.encrypt_time_ms = ms; else if (k == "decrypt") s.decrypt_time_ms = ms; else if (k == "add") s.add_time_ms = ms;
+            else if (k == "multiply" || k == "mul") s.mul_time_ms += ms; else if (k == "relinearize" || k == "relin") s.relin_time_ms += ms;
+            else if (k == "mod_switch") s.mod_switch_time_ms = ms; else if (k == "bootstrap") s.bootstrap_time_ms = ms;
+        }
+        auto cnt = [&](const char* k) { auto it = counts_.find(k); return it == counts_.end() ? (uint64_t)0 : it->second; };
+        s.num_encryptions = cnt("encrypt"); s.num_multiplications = cnt("multiply") + cnt("mul"); s.num_bootstraps = cnt("bootstrap");
+        return s;
+    }
+    void print_stats() const {
+        for (const auto& kv : totals()) {
+            auto it = counts_.find(kv.first);
+            std::printf("%-16s %10.3f ms  (%llu)\n", kv.first.c_str(), kv.second, (unsigned long long)(it == counts_.end() ? 0 : it->second));
+        }
+    }
+    void reset() {
+        for (auto& kv : start_events_) cudaEventDestroy(kv.second);
+        for (auto& iv : intervals_) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
+        start_events_.clear(); intervals_.clear(); counts_.clear();
+    }
+
+private:
+    struct Interval { std::string op; cudaEvent_t a, b; };
+    std::map<std::string, double> totals() const {
+        std::map<std::string, double> t;
+        for (const auto& iv : intervals_) {
+            float ms = 0;
+            detail::check_cuda(cudaEventSynchronize(iv.b), "PerformanceMonitor");
+            detail::check_cuda(cudaEventElapsedTime(&ms, iv.a, iv.b), "PerformanceMonitor");
+            t[iv.op] += ms;
+        }
+        return t;
+    }
+    cudaStream_t stream_;
+    std::map<std::string, cudaEvent_t> start_events_;
+    std::vector<Interval> intervals_;
+    std::map<std::string, uint64_t> counts_;
 };
 
 }  // namespace fhe

@@ -162,6 +162,22 @@ static void test_fhe_operations() {              // tests/test_fhe.cu:169-273
         FHEContext::release(e1); FHEContext::release(e2); FHEContext::release(prod); FHEContext::release(sum); FHEContext::release(diff); FHEContext::release(scaled);
         FHEContext::release(b1); FHEContext::release(b2); FHEContext::release(two); FHEContext::release(pp); FHEContext::release(ps); FHEContext::release(pd); FHEContext::release(pq);
     }
+    // PerformanceMonitor (include/fhe.cuh:169-198, declared only in the reference): CUDA-event timing on the context's stream
+    {
+        PerformanceMonitor mon(ctx.stream());
+        Ciphertext tmp;
+        for (int i = 0; i < 3; i++) { mon.start_timer("multiply"); ctx.multiply(tmp, ct1, ct2, rlk); mon.stop_timer("multiply"); }
+        mon.start_timer("encrypt"); Ciphertext e3; ctx.encrypt(e3, pt1, pk); mon.stop_timer("encrypt");
+        const PerfStats st = mon.get_stats();
+        REQUIRE(st.num_multiplications == 3 && st.num_encryptions == 1);
+        REQUIRE(st.mul_time_ms > 0.0 && st.mul_time_ms < 1000.0 && st.encrypt_time_ms > 0.0);
+        bool threw = false;
+        try { mon.stop_timer("never started"); } catch (const std::runtime_error&) { threw = true; }
+        REQUIRE(threw);
+        mon.reset();
+        REQUIRE(mon.get_stats().num_multiplications == 0);
+        FHEContext::release(tmp); FHEContext::release(e3);
+    }
     // rotations (include/fhe.cuh:113-116, declared only in the reference): the slot at NTT position k holds the evaluation at
     // psi^(2 bitrev(k) + 1); x -> x^g sends the value of position k' to position k with exponent(k') = exponent(k) * g mod 2N
     {
