@@ -92,7 +92,12 @@ def load_library() -> C.CDLL:
         "fhe_b200_bfv_info": [_vp] + [C.POINTER(C.c_uint32)] * 5 + [u64p],
         "fhe_b200_bfv_plan": [_vp],
         "fhe_b200_gaussian_cdt": [C.c_double, u64p, C.c_uint32],
+        "fhe_b200_wire_pack": [C.c_uint32] * 4 + [C.c_int, C.c_uint32, u64p, u64p, _vp],
+        "fhe_b200_wire_unpack": [_vp, C.c_size_t, u64p] + [C.POINTER(C.c_uint32)] * 4 + [C.POINTER(C.c_int),
+                                 C.POINTER(C.c_uint32), u64p],
     }
+    lib.fhe_b200_wire_size.argtypes = [C.c_uint32] * 3
+    lib.fhe_b200_wire_size.restype = C.c_size_t
     for name, argtypes in sig.items():
         fn = getattr(lib, name, None)
         if fn is None:
@@ -113,7 +118,7 @@ def check(rc: int) -> None:
 
 
 from .engine import (BfvContext, LinComb, NTTEngine, Plan, PolynomialOps, RNSContext, RNS_NTTEngine,  # noqa: E402
-                     gaussian_cdt, pinned_empty)
+                     gaussian_cdt, pinned_empty, wire_pack, wire_unpack, WIRE_KINDS)
 
 __all__ = ["load_library", "check", "FheB200Error", "Plan", "NTTEngine", "RNS_NTTEngine", "PolynomialOps",
-           "RNSContext", "LinComb", "BfvContext", "gaussian_cdt", "pinned_empty", "LIB_PATH", "HEADER_PATH"]
+           "RNSContext", "LinComb", "BfvContext", "gaussian_cdt", "pinned_empty", "wire_pack", "wire_unpack", "WIRE_KINDS", "LIB_PATH", "HEADER_PATH"]

@@ -57,6 +57,43 @@ def gaussian_cdt(sigma: float) -> np.ndarray:
     return buf[:ln].copy()
 
 
+WIRE_KINDS = {"ciphertext": 1, "public_key": 2, "secret_key": 3, "switch_key": 4, "plaintext": 5}
+
+
+def wire_pack(kind: str, words, moduli, ntt_form: bool = False, galois_elt: int = 0) -> bytes:
+    """Serialise uint64 words [polys][limbs][n] (host array, or a device tensor which is copied back first) with the 64-byte
+    header csrc/wire.cpp documents.  The reference has no serialisation."""
+    if isinstance(words, torch.Tensor):
+        words = to_host(words)
+    w = _np_u64(words)
+    m = _np_u64(moduli)
+    n, limbs = w.shape[-1], len(m)
+    assert w.ndim >= 2 and w.shape[-2] == limbs, "words must be [..., limbs, n]"
+    polys = w.size // (n * limbs)
+    lib = load_library()
+    out = np.empty(lib.fhe_b200_wire_size(n, limbs, polys), dtype=np.uint8)
+    check(lib.fhe_b200_wire_pack(WIRE_KINDS[kind], n, limbs, polys, int(bool(ntt_form)), int(galois_elt),
+                                 m.ctypes.data_as(u64p), w.ctypes.data_as(u64p), out.ctypes.data))
+    return out.tobytes()
+
+
+def wire_unpack(blob: bytes, moduli=None):
+    """-> (header dict, uint64 array [polys][limbs][n]); raises FheB200Error on a bad magic / length / checksum / modulus chain."""
+    lib = load_library()
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    m = _np_u64(moduli) if moduli is not None else None
+    mp = m.ctypes.data_as(u64p) if m is not None else None
+    f = [C.c_uint32() for _ in range(4)]
+    nf, ge = C.c_int(), C.c_uint32()
+    refs = [C.byref(x) for x in f] + [C.byref(nf), C.byref(ge)]
+    check(lib.fhe_b200_wire_unpack(buf.ctypes.data, len(blob), mp, *refs, None))
+    kind, n, limbs, polys = (x.value for x in f)
+    out = np.empty((polys, limbs, n), dtype=np.uint64)
+    check(lib.fhe_b200_wire_unpack(buf.ctypes.data, len(blob), mp, *refs, out.ctypes.data_as(u64p)))
+    names = {v: k for k, v in WIRE_KINDS.items()}
+    return {"kind": names[kind], "n": n, "limbs": limbs, "polys": polys, "ntt_form": bool(nf.value), "galois_elt": ge.value}, out
+
+
 class Plan:
     """fhe_b200_plan: ring degree N, RNS moduli, device twiddle tables."""
 

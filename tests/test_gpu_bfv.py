@@ -299,3 +299,36 @@ def test_galois_config4_properties(fhe, oracle):
     assert np.array_equal(to_host(g.decrypt(rr, sk))[0], oracle.apply_galois_poly(m[0], 9, t))
     c = g.rotate_columns(g.rotate_columns(ct, gc), gc)
     assert np.array_equal(to_host(g.decrypt(c, sk))[0], m[0])
+
+
+@pytest.mark.gpu
+def test_wire_format_moves_keys_and_ciphertexts_between_contexts(fhe, oracle):
+    """keys and ciphertexts serialised by one context and loaded by a second one (a second process in production) give the
+    same HMult words and the same plaintext; an object of another modulus chain is refused."""
+    from fhe_b200.engine import to_device, to_host
+    p, g, _ = _setup(fhe, oracle, "small")
+    n, t, L, K = p["n"], p["t"], p["L"], p["K"]
+    primes = list(p["primes"])
+    q_chain, qp_chain, full = primes[:L], primes[:L + K], primes
+    sk, pk = g.keygen(31, 32); rlk = g.relinkey_gen(33, sk)
+    rng = np.random.default_rng(910)
+    m1 = rng.integers(0, t, (2, n), dtype=np.uint64); m2 = rng.integers(0, t, (2, n), dtype=np.uint64)
+    ca = g.encrypt(40, to_device(m1), pk); cb = g.encrypt(50, to_device(m2), pk)
+    want = to_host(g.multiply(ca, cb, rlk))
+    blobs = {"sk": fhe.wire_pack("secret_key", sk, full, ntt_form=True),
+             "rlk": fhe.wire_pack("switch_key", rlk, qp_chain, ntt_form=True),
+             "ca": fhe.wire_pack("ciphertext", ca, q_chain), "cb": fhe.wire_pack("ciphertext", cb, q_chain)}
+    g2 = fhe.BfvContext(n, L, p["R"], K, p["dnum"], t, p["primes"], p["sigma"], p["hamming_weight"])
+    hdr, w = fhe.wire_unpack(blobs["rlk"], qp_chain)
+    assert hdr["kind"] == "switch_key" and hdr["polys"] == 2 * p["dnum"] and hdr["limbs"] == L + K
+    rlk2 = to_device(w.reshape(tuple(rlk.shape)))
+    sk2 = to_device(fhe.wire_unpack(blobs["sk"], full)[1].reshape(tuple(sk.shape)))
+    ca2 = to_device(fhe.wire_unpack(blobs["ca"], q_chain)[1].reshape(tuple(ca.shape)))
+    cb2 = to_device(fhe.wire_unpack(blobs["cb"], q_chain)[1].reshape(tuple(cb.shape)))
+    out2 = g2.multiply(ca2, cb2, rlk2)
+    assert np.array_equal(to_host(out2), want)
+    dec = to_host(g2.decrypt(out2, sk2))
+    for b in range(2):
+        assert np.array_equal(dec[b], oracle.schoolbook_negacyclic(m1[b], m2[b], t))
+    with pytest.raises(fhe.FheB200Error):
+        fhe.wire_unpack(blobs["ca"], primes[1:L + 1])
