@@ -242,12 +242,19 @@ static int launch_kt(const LcMmaArgs& a, int sm_count, cudaStream_t st) {
         FHE_CUDA(cudaFuncSetAttribute(lincomb_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    // as many resident warps as the table allows: two 256-thread CTAs per SM, or one of 512 threads when the table needs
-    // more than half of the shared memory
+    // as many resident warps as the table and the registers allow: 256-thread CTAs (two per SM at 128 registers, three for the
+    // k-tile counts that compile to 80), or one CTA of 512 threads when the table needs more than half of the shared memory
     const bool one = smem > 100 * 1024;
     const uint32_t threads = one ? 512 : 256;
     const size_t want = (a.tiles * 32 + threads - 1) / threads;
-    const size_t cap = (size_t)sm_count * (one ? 1 : 2);
+    int per_sm = 1;                                      // resident 256-thread CTAs per SM (3 for the small tables of ModUp / ModDown)
+    if (!one) {
+        FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lincomb_mma_kernel<KT>, 256, smem));
+        if (per_sm < 1) per_sm = 1;
+        static const char* ev = getenv("FHE_B200_LINCOMB_CTAS");             // experiments: cap the resident CTAs per SM
+        if (ev && atoi(ev) > 0 && atoi(ev) < per_sm) per_sm = atoi(ev);
+    }
+    const size_t cap = (size_t)sm_count * (one ? 1 : per_sm);
     lincomb_mma_kernel<KT><<<(unsigned)(want < cap ? want : cap), threads, smem, st>>>(a);
     FHE_LAUNCH_CHECK();
     return 0;
