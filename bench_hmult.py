@@ -99,6 +99,13 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
     d_m1 = to_device(m1)
     enc_ms = timed(lambda: g.encrypt(10, d_m1, pk))
     dec_ms = timed(lambda: g.decrypt(out, sk))
+    # the same call with one operand twice (squaring path: two polynomials extended and transformed instead of four), and the
+    # two halves on their own (three-component product; relinearisation of it)
+    sq_ms = timed(lambda: g.multiply(ca, ca, rlk))
+    ct3 = g.multiply_no_relin(ca, cb)
+    mul3_ms = timed(lambda: g.multiply_no_relin(ca, cb, out=ct3))
+    out2 = torch.empty_like(ca)
+    relin_ms = timed(lambda: g.relinearize(ct3, rlk, out=out2))
     # correctness of what was timed: decrypt one result
     import oracle
     dec = to_host(g.decrypt(out, sk))
@@ -129,7 +136,10 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
             # conversions at four IMAD.WIDE per (source, target) pair -- the second term is what the tensor-core kernel removes
             "int_pipe_floor": _floor(n, L, p["R"], p["K"], p["dnum"], ms / (B * K)),
             "encrypt": {"value": B / (enc_ms / 1e3), "unit": "ops/s", "ms_per_op": enc_ms / B, "limb_ntts_per_op": 3 * L},
-            "decrypt": {"value": B / (dec_ms / 1e3), "unit": "ops/s", "ms_per_op": dec_ms / B, "limb_ntts_per_op": 2 * L}}
+            "decrypt": {"value": B / (dec_ms / 1e3), "unit": "ops/s", "ms_per_op": dec_ms / B, "limb_ntts_per_op": 2 * L},
+            "square": {"value": B / (sq_ms / 1e3), "unit": "ops/s", "ms_per_op": sq_ms / B},
+            "multiply_no_relin": {"value": B / (mul3_ms / 1e3), "unit": "ops/s", "ms_per_op": mul3_ms / B},
+            "relinearize": {"value": B / (relin_ms / 1e3), "unit": "ops/s", "ms_per_op": relin_ms / B}}
 
 
 if __name__ == "__main__":

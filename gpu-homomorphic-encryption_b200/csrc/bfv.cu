@@ -236,10 +236,10 @@ __global__ void __launch_bounds__(256) dec_add_kernel(u64* __restrict__ x, const
 // ext: [4][B][A][N] (a0,a1,b0,b1; NTT form) -> d: [3][B][A][N]   d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1
 __global__ void __launch_bounds__(256) tensor_kernel(ulonglong2* __restrict__ d, const ulonglong2* __restrict__ ext,
                                                      const LimbParams* __restrict__ params, uint32_t logn, uint32_t limb_begin, uint32_t A,
-                                                     size_t per_comp /* B*A*N/2 */) {
+                                                     size_t per_comp /* B*A*N/2 */, size_t b_off /* 2 per_comp; 0 when squaring */) {
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < per_comp; v += (size_t)gridDim.x * blockDim.x) {
         const LimbParams P = params[limb_begin + ((2 * v) >> logn) % A];
-        const ulonglong2 a0 = ext[v], a1 = ext[per_comp + v], b0 = ext[2 * per_comp + v], b1 = ext[3 * per_comp + v];
+        const ulonglong2 a0 = ext[v], a1 = ext[per_comp + v], b0 = ext[b_off + v], b1 = ext[b_off + per_comp + v];
         ulonglong2 r0, r1, r2;
         u64 hi, lo;
         r0.x = mul_mod(a0.x, b0.x, P); r0.y = mul_mod(a0.y, b0.y, P);
@@ -599,16 +599,18 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
     return rc;
 }
 
-// ---- multiply + relinearize --------------------------------------------------------------------------------------------------
-extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
-                                           uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream) {
-    FHE_REQUIRE(c && d_a && d_b && d_rlk && d_out, "bfv_multiply_relin: null argument");
-    if (!batch) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
+// ---- multiply, relinearize ---------------------------------------------------------------------------------------------------
+// Replaces FHEContext::multiply / relinearize (/root/reference/src/fhe.cu:198-235): tensor over Q u R, exact round(t/Q .), then --
+// when d_rlk is given -- hybrid key switching of the third component.  d_scaled (optional) receives the 3-component ciphertext
+// [B][3][L][N]; d_out (with d_rlk) the relinearised one [B][2][L][N].  d_a == d_b takes the squaring path: two polynomials are
+// extended and transformed instead of four (the tensor kernel reads the same planes for both operands; results are identical).
+static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk, uint64_t* d_out,
+                         uint64_t* d_scaled, uint32_t batch, cudaStream_t st) {
     FHE_CUDA(cudaSetDevice(c->device));
-    const uint32_t n = c->n, L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, alpha = c->alpha, dnum = c->dnum, B = batch;
+    const uint32_t n = c->n, L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, dnum = c->dnum, B = batch;
     const LimbParams* prm = c->plan->d_params;
     const size_t N = n, ln = (size_t)L * N, an = (size_t)A * N, wn = (size_t)W * N, rn = (size_t)R * N;
+    const bool square = d_a == d_b;
     // workspace: ext [4][B][A][N] | d [3][B][A][N] | sR [3][B][R][N] | sc [3][B][L][N] | dig [dnum][B][W][N] | acc [2][B][W][N]
     const size_t w_ext = 4 * B * an, w_d = 3 * B * an, w_sr = 3 * B * rn, w_sc = 3 * B * ln, w_dig = (size_t)dnum * B * wn, w_acc = 2 * B * wn;
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_ext + w_d + w_sr + w_sc + w_dig + w_acc));
@@ -618,20 +620,21 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
     cudaError_t e = cudaSuccess;
 #define STEP(expr) do { if (!rc) rc = (expr); } while (0)
 #define COPY2D(dst, dpitch, src, spitch, width, rows) do { if (!rc && e == cudaSuccess) e = cudaMemcpy2DAsync(dst, (dpitch) * 8, src, (spitch) * 8, (width) * 8, rows, cudaMemcpyDeviceToDevice, st); } while (0)
-    // 1. the four input polynomials into ext: Q limbs copied, R limbs by exact conversion Q -> R
+    // 1. the input polynomials into ext: Q limbs copied, R limbs by exact conversion Q -> R
     //    (the conversion kernel also writes the Q limbs through: no separate copy)
-    for (int p = 0; p < 4; p++) {
+    const int planes = square ? 2 : 4;
+    for (int p = 0; p < planes; p++) {
         const uint64_t* src = (p < 2 ? d_a : d_b) + (size_t)(p & 1) * ln;           // component p&1 of every ciphertext: stride 2*ln
         uint64_t* dst = ext + (size_t)p * B * an;
         LcView v; v.in = src; v.in_stride = 2 * ln; v.out = dst + ln; v.out_stride = an; v.copy_out = dst; v.copy_stride = an;
         STEP(lincomb_launch(c->q2r, v, n, B, st));
     }
     // 2. NTT over Q u R, 3. tensor, 4. INTT
-    STEP(launch_ntt(c->plan, ext, ext, 4 * B, 0, A, false, st));
+    STEP(launch_ntt(c->plan, ext, ext, planes * B, 0, A, false, st));
     if (!rc) {
         const size_t per = B * an / 2;
         if (profile_on()) profile_begin(5, B, st);
-        tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per);
+        tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per, square ? 0 : 2 * per);
         if (profile_on()) profile_end(st);
         count_launch();
     }
@@ -643,13 +646,40 @@ extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a,
         // caller layout [B][3][L][N]; ours is [3][B][L][N]
         for (int p = 0; p < 3; p++) COPY2D(d_scaled + (size_t)p * ln, 3 * ln, sc + (size_t)p * B * ln, ln, ln, B);
     }
+    if (e != cudaSuccess) { set_error("bfv_multiply: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
     // 7. relinearise d2 = sc[2]: hybrid key switching, added onto (d0, d1)
-    if (e != cudaSuccess) { set_error("bfv_multiply_relin: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
-    STEP(key_switch(c, sc + 2 * B * ln, ln, d_rlk, sc, ln, sc + B * ln, ln, d_out, B, dig, acc, st));
+    if (d_rlk) STEP(key_switch(c, sc + 2 * B * ln, ln, d_rlk, sc, ln, sc + B * ln, ln, d_out, B, dig, acc, st));
 #undef STEP
 #undef COPY2D
-    if (e != cudaSuccess) { set_error("bfv_multiply_relin: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
     if (rc) return rc;
+    FHE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
+                                           uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_a && d_b && d_rlk && d_out, "bfv_multiply_relin: null argument");
+    if (!batch) return 0;
+    return multiply_core(c, d_a, d_b, d_rlk, d_out, d_scaled, batch, (cudaStream_t)stream);
+}
+
+extern "C" int fhe_b200_bfv_multiply(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out3, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_a && d_b && d_out3, "bfv_multiply: null argument");
+    if (!batch) return 0;
+    return multiply_core(c, d_a, d_b, nullptr, nullptr, d_out3, batch, (cudaStream_t)stream);
+}
+
+extern "C" int fhe_b200_bfv_relinearize(fhe_b200_bfv* c, const uint64_t* d_ct3, const uint64_t* d_rlk, uint64_t* d_out, uint32_t batch, void* stream) {
+    FHE_REQUIRE(c && d_ct3 && d_rlk && d_out, "bfv_relinearize: null argument");
+    FHE_REQUIRE(d_ct3 != d_out, "bfv_relinearize: the output must not alias the input");
+    if (!batch) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const size_t ln = (size_t)c->L * c->n, wn = (size_t)(c->L + c->K) * c->n;
+    const size_t w_dig = (size_t)c->dnum * batch * wn, w_acc = 2 * (size_t)batch * wn;
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_dig + w_acc));
+    uint64_t* dig = c->d_ws; uint64_t* acc = dig + w_dig;
+    FHE_TRY(key_switch(c, d_ct3 + 2 * ln, 3 * ln, d_rlk, d_ct3, 3 * ln, d_ct3 + ln, 3 * ln, d_out, batch, dig, acc, st));
     FHE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -765,7 +795,7 @@ extern "C" int fhe_b200_bfv_tensor(fhe_b200_plan* plan, uint64_t* d_out, const u
     if (!per) return 0;
     const size_t w = (per + 255) / 256, cap = (size_t)plan->sm_count * 16;
     tensor_kernel<<<(uint32_t)(w < cap ? w : cap), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_out, (const ulonglong2*)d_ext, plan->d_params,
-                                                                                 plan->logn, limb_begin, limb_count, per);
+                                                                                 plan->logn, limb_begin, limb_count, per, 2 * per);
     FHE_LAUNCH_CHECK();
     return 0;
 }

@@ -476,6 +476,28 @@ class BfvContext:
                                                    _ptr(sc) if want_scaled else None, batch, _stream()))
         return (out, sc) if want_scaled else out
 
+    def multiply_no_relin(self, a, b, out=None):
+        """3-component product [B][3][L][N] (FHEContext::multiply before its relinearize call, src/fhe.cu:198-219); a is b (the same
+        tensor) takes the squaring path."""
+        batch = a.numel() // (2 * self.L * self.n)
+        out = out if out is not None else self._empty(batch, 3, self.L, self.n)
+        check(self.lib.fhe_b200_bfv_multiply(self.h, _ptr(a), _ptr(b), _ptr(out), batch, _stream()))
+        return out
+
+    def relinearize(self, ct3, rlk, out=None):
+        """[B][3][L][N] -> [B][2][L][N] by hybrid key switching of the third component (FHEContext::relinearize, src/fhe.cu:226-235)."""
+        batch = ct3.numel() // (3 * self.L * self.n)
+        out = out if out is not None else self._empty(batch, 2, self.L, self.n)
+        check(self.lib.fhe_b200_bfv_relinearize(self.h, _ptr(ct3), _ptr(rlk), _ptr(out), batch, _stream()))
+        return out
+
+    def add3(self, a3, b3):
+        """sum of two 3-component ciphertexts (lazy relinearisation: relinearize the sum once)."""
+        out = torch.empty_like(a3)
+        batch = a3.numel() // (self.L * self.n)
+        check(self.lib.fhe_b200_poly_add(self.lib.fhe_b200_bfv_plan(self.h), _ptr(out), _ptr(a3), _ptr(b3), batch, 0, self.L, _stream()))
+        return out
+
     def multiply_host(self, h_a: np.ndarray, h_b: np.ndarray, rlk, h_out: np.ndarray):
         batch = h_a.size // (2 * self.L * self.n)
         check(self.lib.fhe_b200_bfv_multiply_relin_host(self.h, h_a.ctypes.data_as(C.c_void_p), h_b.ctypes.data_as(C.c_void_p),

@@ -199,8 +199,12 @@ public:
 
     // ---- homomorphic operations (src/fhe.cu:187-235)
     void add(Ciphertext& result, const Ciphertext& a, const Ciphertext& b) {
-        Ciphertext out; new_ciphertext(out);
-        detail::check(fhe_b200_bfv_add(ctx_, a.components[0]->rns, b.components[0]->rns, out.components[0]->rns, 1, stream_), "add");
+        if (a.components.size() != b.components.size()) throw std::runtime_error("add: operands differ in their number of components");
+        const uint32_t comps = (uint32_t)a.components.size();
+        Ciphertext out; new_ciphertext(out, comps);
+        if (comps == 2) detail::check(fhe_b200_bfv_add(ctx_, a.components[0]->rns, b.components[0]->rns, out.components[0]->rns, 1, stream_), "add");
+        else detail::check(fhe_b200_poly_add(fhe_b200_bfv_plan(ctx_), out.components[0]->rns, a.components[0]->rns, b.components[0]->rns,
+                                             comps, 0, params_.L, stream_), "add");
         out.noise_budget = std::min(a.noise_budget, b.noise_budget);
         out.level = std::max(a.level, b.level);
         replace(result, out);
@@ -224,8 +228,24 @@ public:
     void sub_plain(Ciphertext& result, const Ciphertext& ct, const Plaintext& pt) { plain_op(result, ct, pt, 1); }
     void multiply_plain(Ciphertext& result, const Ciphertext& ct, const Plaintext& pt) { plain_op(result, ct, pt, 2); }
 
-    // multiply() already relinearises (the tensor product never leaves the engine); kept for source compatibility
-    void relinearize(Ciphertext& ct, const RelinKeys&) { if (ct.components.size() > 2) throw std::runtime_error("relinearize: 3-component input is produced only inside multiply()"); }
+    // The two halves of the reference's multiply on their own (src/fhe.cu:198-219 builds three components, :226-235 reduces them):
+    // multiply without keys returns a 3-component ciphertext; add() accepts two of those; relinearize() brings one back to two
+    // components by hybrid key switching.  Lets a sum of products be relinearised once.  &a == &b (or the same buffers) squares.
+    void multiply(Ciphertext& result, const Ciphertext& a, const Ciphertext& b) {
+        if (a.components.size() != 2 || b.components.size() != 2) throw std::runtime_error("multiply: operands must have two components");
+        Ciphertext out; new_ciphertext(out, 3);
+        detail::check(fhe_b200_bfv_multiply(ctx_, a.components[0]->rns, b.components[0]->rns, out.components[0]->rns, 1, stream_), "multiply");
+        out.noise_budget = a.noise_budget + b.noise_budget + 10;
+        out.level = std::max(a.level, b.level);
+        replace(result, out);
+    }
+    void relinearize(Ciphertext& ct, const RelinKeys& rlk) {
+        if (ct.components.size() <= 2) return;                                      // src/fhe.cu:227
+        Ciphertext out; new_ciphertext(out);
+        detail::check(fhe_b200_bfv_relinearize(ctx_, ct.components[0]->rns, rlk.rlk_keys.at(0)->pk0->rns, out.components[0]->rns, 1, stream_), "relinearize");
+        out.noise_budget = ct.noise_budget; out.level = ct.level;
+        replace(ct, out);
+    }
 
     const SchemeParams& params() const { return params_; }
     fhe_b200_bfv* engine() const { return ctx_; }
@@ -257,11 +277,11 @@ private:
         out.noise_budget = ct.noise_budget; out.level = ct.level;
         replace(result, out);
     }
-    void new_ciphertext(Ciphertext& ct) {
+    void new_ciphertext(Ciphertext& ct, uint32_t comps = 2) {
         const uint32_t n = params_.n, L = params_.L;
-        Polynomial* c0 = new Polynomial(n, 2 * L);                               // owns [2][L][N]
-        Polynomial* c1 = new Polynomial(n, L, c0->rns + (size_t)L * n);
-        ct.components.clear(); ct.components.push_back(c0); ct.components.push_back(c1);
+        Polynomial* c0 = new Polynomial(n, comps * L);                           // owns [comps][L][N]
+        ct.components.clear(); ct.components.push_back(c0);
+        for (uint32_t k = 1; k < comps; k++) ct.components.push_back(new Polynomial(n, L, c0->rns + (size_t)k * L * n));
     }
     void replace(Ciphertext& dst, Ciphertext& src) {
         // dst may alias an operand: the engine call has been queued on stream_, release after it completes

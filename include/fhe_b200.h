@@ -183,6 +183,15 @@ int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* ctx, const uint64_t* d_ct, const u
  * scaled tensor before relinearisation. */
 int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
                                 uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream);
+/* The two halves on their own, as the reference's API has them (multiply builds three components, src/fhe.cu:198-219;
+ * relinearize reduces them to two, :226-235 -- a stub there): d_out3 and d_ct3 are [batch][3][L][N] coefficient form.  Sums of
+ * 3-component ciphertexts (fhe_b200_poly_add over 3*batch polynomials) can be relinearised once.  d_a == d_b (same pointer) takes
+ * a squaring path in both multiply entry points (two polynomials extended and transformed instead of four; same words).
+ * relinearize: d_out [batch][2][L][N] must not alias d_ct3. */
+int fhe_b200_bfv_multiply(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out3, uint32_t batch,
+                          void* stream);
+int fhe_b200_bfv_relinearize(fhe_b200_bfv* ctx, const uint64_t* d_ct3, const uint64_t* d_rlk, uint64_t* d_out, uint32_t batch,
+                             void* stream);
 /* Building blocks of multiply_relin on a limb range, for limb-sharded execution (one rank owns limbs
  * [limb_begin, limb_begin+limb_count) of every polynomial; NTT form in, NTT form out).
  *   tensor  : ext [4][batch][limb_count][N] = (a0,a1,b0,b1)  ->  out [3][batch][limb_count][N] = (a0 b0, a0 b1 + a1 b0, a1 b1)

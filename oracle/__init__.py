@@ -409,6 +409,17 @@ class Bfv:
         lib().orc_bfv_mod_switch_to_next(C.c_void_p(self.h), _p(_u64(ct).reshape(-1)), _p(out.reshape(-1)))
         return out
 
+    def multiply(self, a, b):
+        """3-component product [3][L][n] (no relinearisation)."""
+        out = np.zeros((3, self.L, self.n), np.uint64)
+        lib().orc_bfv_multiply(C.c_void_p(self.h), _p(_u64(a).reshape(-1)), _p(_u64(b).reshape(-1)), _p(out.reshape(-1)))
+        return out
+
+    def relinearize(self, ct3, rlk):
+        out = np.zeros((2, self.L, self.n), np.uint64)
+        lib().orc_bfv_relinearize(C.c_void_p(self.h), _p(_u64(ct3).reshape(-1)), _p(rlk.reshape(-1)), _p(out.reshape(-1)))
+        return out
+
     def multiply_relin(self, a, b, rlk, want_scaled=False):
         out = np.zeros((2, self.L, self.n), np.uint64)
         sc = np.zeros((3, self.L, self.n), np.uint64) if want_scaled else None

@@ -307,11 +307,11 @@ static void key_switch(const orc_bfv *c, const u64 *x, const u64 *key, const u64
     free(acc); free(dig); free(conv);
 }
 
-/* ---------- multiply + relinearize --------------------------------------- */
-/* stage outputs are optional (NULL to skip) so tests can pin each step:
- *   d_scaled: [3][L][n]  round(t/Q * tensor) in basis Q, coefficient form (before relinearisation)
- *   out     : [2][L][n]  relinearised ciphertext, coefficient form */
-void orc_bfv_multiply_relin(const orc_bfv *c, const u64 *cta, const u64 *ctb, const u64 *rlk, u64 *out, u64 *d_scaled) {
+/* ---------- multiply, relinearize ----------------------------------------- */
+/* The reference's multiply builds the three tensor components and then calls relinearize (src/fhe.cu:198-224; its
+ * relinearize, :226-235, is a stub and its tensor is never scaled by t/Q).  Here:
+ *   sc  : [3][L][n]  round(t/Q * tensor) in basis Q, coefficient form -- the 3-component ciphertext */
+static void tensor_scale(const orc_bfv *c, const u64 *cta, const u64 *ctb, u64 *sc) {
     u32 n = c->n, L = c->L, R = c->R, A = L + R;
     size_t pn = (size_t)A * n;
     u64 *ext = (u64 *)malloc(4 * pn * sizeof(u64));       /* a0,a1,b0,b1 over Q u R */
@@ -334,16 +334,33 @@ void orc_bfv_multiply_relin(const orc_bfv *c, const u64 *cta, const u64 *ctb, co
         }
         inv_limb(c, d0, i); inv_limb(c, d1, i); inv_limb(c, d2, i);       /* 4. INTT         */
     }
-    u64 *sc = (u64 *)malloc(3 * (size_t)L * n * sizeof(u64));
     u64 *tmpR = (u64 *)malloc((size_t)R * n * sizeof(u64));
     for (int p = 0; p < 3; p++) {
         orc_lc_apply(c->scale, tmpR, d + p * pn, d + p * pn + (size_t)L * n, n);   /* 5. round(t/Q .) in R */
         orc_lc_apply(c->r2q, sc + (size_t)p * L * n, tmpR, NULL, n);               /* 6. exact R -> Q      */
     }
-    if (d_scaled) memcpy(d_scaled, sc, 3 * (size_t)L * n * sizeof(u64));
-    /* 7. relinearise d2: hybrid key switching, added onto (d0, d1) */
-    key_switch(c, sc + 2 * (size_t)L * n, rlk, sc, sc + (size_t)L * n, out);
-    free(ext); free(d); free(sc); free(tmpR);
+    free(ext); free(d); free(tmpR);
+}
+
+/* multiply without relinearisation: out3 = [3][L][n] */
+void orc_bfv_multiply(const orc_bfv *c, const u64 *cta, const u64 *ctb, u64 *out3) { tensor_scale(c, cta, ctb, out3); }
+
+/* relinearize a 3-component ciphertext [3][L][n] -> [2][L][n]: hybrid key switching of c2, added onto (c0, c1) */
+void orc_bfv_relinearize(const orc_bfv *c, const u64 *ct3, const u64 *rlk, u64 *out) {
+    size_t ln = (size_t)c->L * c->n;
+    key_switch(c, ct3 + 2 * ln, rlk, ct3, ct3 + ln, out);
+}
+
+/* fused form; stage outputs are optional (NULL to skip) so tests can pin each step:
+ *   d_scaled: [3][L][n]  the 3-component ciphertext before relinearisation
+ *   out     : [2][L][n]  relinearised ciphertext, coefficient form */
+void orc_bfv_multiply_relin(const orc_bfv *c, const u64 *cta, const u64 *ctb, const u64 *rlk, u64 *out, u64 *d_scaled) {
+    size_t ln = (size_t)c->L * c->n;
+    u64 *sc = (u64 *)malloc(3 * ln * sizeof(u64));
+    tensor_scale(c, cta, ctb, sc);
+    if (d_scaled) memcpy(d_scaled, sc, 3 * ln * sizeof(u64));
+    orc_bfv_relinearize(c, sc, rlk, out);
+    free(sc);
 }
 
 /* ---------- plaintext operands and subtraction (declared only in the reference: include/fhe.cuh:98-104) -------------- */

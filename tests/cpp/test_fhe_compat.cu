@@ -162,6 +162,26 @@ static void test_fhe_operations() {              // tests/test_fhe.cu:169-273
         FHEContext::release(e1); FHEContext::release(e2); FHEContext::release(prod); FHEContext::release(sum); FHEContext::release(diff); FHEContext::release(scaled);
         FHEContext::release(b1); FHEContext::release(b2); FHEContext::release(two); FHEContext::release(pp); FHEContext::release(ps); FHEContext::release(pd); FHEContext::release(pq);
     }
+    // multiply and relinearize as separate calls (src/fhe.cu:198-235): a sum of two 3-component products relinearised once,
+    // and the square of a ciphertext (same operand twice)
+    {
+        Ciphertext p12, p11, sum3, sq;
+        ctx.multiply(p12, ct1, ct2); ctx.multiply(p11, ct1, ct1);
+        REQUIRE(p12.components.size() == 3 && p11.components.size() == 3);
+        ctx.add(sum3, p12, p11);
+        REQUIRE(sum3.components.size() == 3);
+        ctx.relinearize(sum3, rlk);
+        REQUIRE(sum3.components.size() == 2);
+        ctx.relinearize(sum3, rlk);                                  // two components: a no-op, as in the reference
+        ctx.multiply(sq, ct1, ct1, rlk);
+        Plaintext ps3, psq; ctx.decrypt(ps3, sum3, sk); ctx.decrypt(psq, sq, sk);
+        std::vector<uint64_t> r3, rq; ctx.decode(r3, ps3); ctx.decode(rq, psq);
+        const uint64_t exp_sq[8] = {25, 100, 250, 500, 625, 600, 400, 0};       // (5 + 10x + 15x^2 + 20x^3)^2
+        for (int i = 0; i < 8; i++) { REQUIRE(rq[i] == exp_sq[i]); REQUIRE(r3[i] == exp_mul[i] + exp_sq[i]); }
+        for (int i = 8; i < 4096; i++) { REQUIRE(rq[i] == 0); REQUIRE(r3[i] == 0); }
+        FHEContext::release(p12); FHEContext::release(p11); FHEContext::release(sum3); FHEContext::release(sq);
+        FHEContext::release(ps3); FHEContext::release(psq);
+    }
     // PerformanceMonitor (include/fhe.cuh:169-198, declared only in the reference): CUDA-event timing on the context's stream
     {
         PerformanceMonitor mon(ctx.stream());

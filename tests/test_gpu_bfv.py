@@ -332,3 +332,49 @@ def test_wire_format_moves_keys_and_ciphertexts_between_contexts(fhe, oracle):
         assert np.array_equal(dec[b], oracle.schoolbook_negacyclic(m1[b], m2[b], t))
     with pytest.raises(fhe.FheB200Error):
         fhe.wire_unpack(blobs["ca"], primes[1:L + 1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["small", "c2"])
+def test_multiply_and_relinearize_separately_vs_oracle(fhe, oracle, preset):
+    """FHEContext::multiply (three components) and ::relinearize as separate calls (src/fhe.cu:198-235): each equals the oracle word
+    for word, their composition equals the fused entry point, a sum of products is relinearised once, and the squaring path
+    (same operand pointer) gives the words of the general path."""
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, preset)
+    n, t, L = p["n"], p["t"], p["L"]
+    sk, pk = g.keygen(61, 62); rlk = g.relinkey_gen(63, sk)
+    _, osk = o.secret_keygen(61); orlk = o.relin_keygen(63, osk)
+    rng = np.random.default_rng(1200)
+    m = rng.integers(0, t, (4, n), dtype=np.uint64)
+    ct = g.encrypt(900, to_device(m), pk)
+    a, b = ct[0:2].contiguous(), ct[2:4].contiguous()
+    ha, hb = to_host(a), to_host(b)
+    prod3 = g.multiply_no_relin(a, b)
+    assert tuple(prod3.shape) == (2, 3, L, n)
+    h3 = to_host(prod3)
+    for i in range(2):
+        assert np.array_equal(h3[i], o.multiply(ha[i], hb[i])), i
+    rel = g.relinearize(prod3, rlk)
+    fused = g.multiply(a, b, rlk)
+    assert np.array_equal(to_host(rel), to_host(fused))
+    for i in range(2):
+        assert np.array_equal(to_host(rel)[i], o.relinearize(h3[i], orlk)), i
+    # lazy relinearisation: a0*b0 + a1*b1 with one key switch
+    s3 = g.add3(prod3[0:1].contiguous(), prod3[1:2].contiguous())
+    mods = np.array(p["primes"][:L], dtype=np.uint64)[None, :, None]
+    exp3 = (h3[0] + h3[1]) % mods
+    assert np.array_equal(to_host(s3)[0], exp3)
+    lazy = g.relinearize(s3, rlk)
+    assert np.array_equal(to_host(lazy)[0], o.relinearize(exp3, orlk))
+    want = (oracle.schoolbook_negacyclic(m[0], m[2], t) + oracle.schoolbook_negacyclic(m[1], m[3], t)) % np.uint64(t)
+    assert np.array_equal(to_host(g.decrypt(lazy, sk))[0], want)
+    # squaring: the same tensor as both operands vs a copy of it
+    sq = g.multiply(a, a, rlk)
+    gen = g.multiply(a, a.clone(), rlk)
+    assert np.array_equal(to_host(sq), to_host(gen))
+    assert np.array_equal(to_host(sq)[0], o.multiply_relin(ha[0], ha[0], orlk))
+    assert np.array_equal(to_host(g.multiply_no_relin(a, a)), to_host(g.multiply_no_relin(a, a.clone())))
+    assert np.array_equal(to_host(g.decrypt(sq, sk))[1], oracle.schoolbook_negacyclic(m[1], m[1], t))
+    with pytest.raises(fhe.FheB200Error):
+        g.relinearize(prod3, rlk, out=prod3.view(-1)[: 2 * 2 * L * n].view(2, 2, L, n))

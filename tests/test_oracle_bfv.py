@@ -300,3 +300,24 @@ def test_galois_keys_rotation_and_mod_switch(oracle, chain, small_bfv):
     assert np.array_equal(low.decrypt(ct2, sk2), m)
     for p in range(2):
         assert np.array_equal(ct2[p], oracle.modswitch_drop_last(ct[p], qs))
+
+
+def test_multiply_then_relinearize_is_the_fused_multiply(oracle):
+    """orc_bfv_multiply (3 components) + orc_bfv_relinearize == orc_bfv_multiply_relin; the 3-component ciphertext decrypts with
+    (1, s, s^2) to the product, and a sum of two products relinearised once decrypts to the sum of the products."""
+    from fhe_b200.params import bfv_preset
+    p = bfv_preset("small")
+    o = oracle.Bfv(p["n"], p["L"], p["R"], p["K"], p["dnum"], p["t"], p["primes"], sigma=p["sigma"], hw=p["hamming_weight"])
+    n, t, L = p["n"], p["t"], p["L"]
+    _, sk = o.secret_keygen(5); pk = o.public_keygen(6, sk); rlk = o.relin_keygen(7, sk)
+    rng = np.random.default_rng(77)
+    m = rng.integers(0, t, (4, n), dtype=np.uint64)
+    ct = [o.encrypt(100 + i, m[i], pk) for i in range(4)]
+    p01, p23 = o.multiply(ct[0], ct[1]), o.multiply(ct[2], ct[3])
+    fused, scaled = o.multiply_relin(ct[0], ct[1], rlk, want_scaled=True)
+    assert np.array_equal(p01, scaled)
+    assert np.array_equal(o.relinearize(p01, rlk), fused)
+    mods = np.array(p["primes"][:L], dtype=np.uint64)[None, :, None]
+    lazy = o.relinearize((p01 + p23) % mods, rlk)
+    want = (oracle.schoolbook_negacyclic(m[0], m[1], t) + oracle.schoolbook_negacyclic(m[2], m[3], t)) % np.uint64(t)
+    assert np.array_equal(o.decrypt(lazy, sk), want)
