@@ -106,6 +106,10 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
     mul3_ms = timed(lambda: g.multiply_no_relin(ca, cb, out=ct3))
     out2 = torch.empty_like(ca)
     relin_ms = timed(lambda: g.relinearize(ct3, rlk, out=out2))
+    # invariant noise budget (bits) of one fresh ciphertext, of a product and of a depth-2 product: evidence that the parameter
+    # set leaves room (host-side diagnostic, not timed)
+    depth2 = g.multiply(out[0:1].contiguous(), ca[0:1].contiguous(), rlk)
+    nb = g.noise_budget(torch.cat([ca[0:1], out[0:1], depth2]).contiguous(), sk)
     # correctness of what was timed: decrypt one result
     import oracle
     dec = to_host(g.decrypt(out, sk))
@@ -137,6 +141,7 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
             "int_pipe_floor": _floor(n, L, p["R"], p["K"], p["dnum"], ms / (B * K)),
             "encrypt": {"value": B / (enc_ms / 1e3), "unit": "ops/s", "ms_per_op": enc_ms / B, "limb_ntts_per_op": 3 * L},
             "decrypt": {"value": B / (dec_ms / 1e3), "unit": "ops/s", "ms_per_op": dec_ms / B, "limb_ntts_per_op": 2 * L},
+            "noise_budget_bits": {"fresh": round(float(nb[0]), 2), "after_multiply": round(float(nb[1]), 2), "after_depth_2": round(float(nb[2]), 2)},
             "square": {"value": B / (sq_ms / 1e3), "unit": "ops/s", "ms_per_op": sq_ms / B},
             "multiply_no_relin": {"value": B / (mul3_ms / 1e3), "unit": "ops/s", "ms_per_op": mul3_ms / B},
             "relinearize": {"value": B / (relin_ms / 1e3), "unit": "ops/s", "ms_per_op": relin_ms / B}}

@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
         "fhe_b200_bfv_add": [_vp, _vp, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_bfv_multiply_relin": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_bfv_multiply": [_vp, _vp, _vp, _vp, C.c_uint32, _vp],
+        "fhe_b200_bfv_noise_budget": [_vp, _vp, _vp, C.c_uint32, C.POINTER(C.c_double), _vp],
         "fhe_b200_bfv_relinearize": [_vp, _vp, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_bfv_sub": [_vp, _vp, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_bfv_add_plain": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_int, _vp],

@@ -523,6 +523,74 @@ extern "C" int fhe_b200_bfv_decrypt(fhe_b200_bfv* c, const uint64_t* d_ct, const
     return 0;
 }
 
+// ---- invariant noise budget (FHEContext::estimate_noise_budget, /root/reference/include/fhe.cuh:142, declared only) ------------
+// budget = log2(Q) - log2( || [t (c0 + c1 s)]_Q ||_inf ) - 1 bits (the definition SEAL uses).  The device computes
+// w_i = t (c0 + c1 s) mod q_i per limb with the decryption kernels; the host turns every coefficient into mixed-radix digits
+// (Garner: d_0 + d_1 q_0 + d_2 q_0 q_1 + ...), which order like the integers themselves: (Q-1)/2 has the digits (q_i-1)/2 and
+// Q-1-w the digits q_i-1-d_i, so centring and the magnitude need no multi-precision arithmetic.  A diagnostic: O(N L^2) host work.
+extern "C" int fhe_b200_bfv_noise_budget(fhe_b200_bfv* c, const uint64_t* d_ct, const uint64_t* d_sk, uint32_t batch, double* h_bits,
+                                         void* stream) {
+    FHE_REQUIRE(c && d_ct && d_sk && h_bits, "bfv_noise_budget: null argument");
+    if (!batch) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = c->n, L = c->L;
+    const LimbParams* prm = c->plan->d_params;
+    const size_t ln = (size_t)L * n;
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
+    uint64_t* x = c->d_ws;
+    cudaError_t e = cudaMemcpy2DAsync(x, ln * 8, d_ct + ln, 2 * ln * 8, ln * 8, batch, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_error("bfv_noise_budget: gather failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
+    FHE_TRY(launch_ntt(c->plan, x, x, batch, 0, L, false, st));
+    dec_mul_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(x, d_sk, prm, c->logn, L, batch * ln); count_launch();
+    FHE_TRY(launch_ntt(c->plan, x, x, batch, 0, L, true, st));
+    dec_add_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(x, d_ct, prm, c->logn, L, batch * ln); count_launch();
+    std::vector<uint64_t> tq(L);
+    for (uint32_t i = 0; i < L; i++) tq[i] = c->t % c->primes[i];
+    FHE_TRY(fhe_b200_poly_mul_scalar(c->plan, x, x, tq.data(), batch, 0, L, stream));
+    std::vector<uint64_t> w(batch * ln);
+    FHE_CUDA(cudaMemcpyAsync(w.data(), x, batch * ln * 8, cudaMemcpyDeviceToHost, st));
+    FHE_CUDA(cudaStreamSynchronize(st));
+    // Garner constants: inv[j][i] = q_j^-1 mod q_i (j < i);  log2 of the partial products
+    std::vector<uint64_t> inv((size_t)L * L, 0);
+    std::vector<double> lg(L + 1, 0.0);
+    for (uint32_t i = 0; i < L; i++) {
+        lg[i + 1] = lg[i] + std::log2((double)c->primes[i]);
+        for (uint32_t j = 0; j < i; j++) inv[(size_t)j * L + i] = host::invmod(c->primes[j] % c->primes[i], c->primes[i]);
+    }
+    std::vector<uint64_t> dgt(L);
+    for (uint32_t b = 0; b < batch; b++) {
+        double worst = -1.0;                                   // log2 of the largest centred magnitude (-1: all zero)
+        for (uint32_t k = 0; k < n; k++) {
+            for (uint32_t i = 0; i < L; i++) {
+                const uint64_t qi = c->primes[i];
+                uint64_t u = w[((size_t)b * L + i) * n + k];
+                for (uint32_t j = 0; j < i; j++) u = host::mulmod(host::submod(u, dgt[j] % qi, qi), inv[(size_t)j * L + i], qi);
+                dgt[i] = u;
+            }
+            // w > (Q-1)/2 ?  compare digits from the top with (q_i-1)/2
+            bool neg = false;
+            for (int i = (int)L - 1; i >= 0; i--) {
+                const uint64_t h = (c->primes[i] - 1) / 2;
+                if (dgt[i] != h) { neg = dgt[i] > h; break; }
+            }
+            if (neg) {                                         // Q - w = (Q-1-w) + 1
+                for (uint32_t i = 0; i < L; i++) dgt[i] = c->primes[i] - 1 - dgt[i];
+                for (uint32_t i = 0; i < L; i++) { if (++dgt[i] < c->primes[i]) break; dgt[i] = 0; }
+            }
+            int top = (int)L - 1;
+            while (top >= 0 && dgt[top] == 0) top--;
+            if (top < 0) continue;
+            const double lead = (double)dgt[top] + (top > 0 ? (double)dgt[top - 1] / (double)c->primes[top - 1] : 0.0);
+            const double m = std::log2(lead) + lg[top];
+            if (m > worst) worst = m;
+        }
+        const double bits = worst < 0 ? lg[L] - 1.0 : lg[L] - worst - 1.0;
+        h_bits[b] = bits > 0 ? bits : 0.0;
+    }
+    return 0;
+}
+
 extern "C" int fhe_b200_bfv_add(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint32_t batch, void* stream) {
     FHE_REQUIRE(c && d_a && d_b && d_out, "bfv_add: null argument");
     return launch_elementwise(c->plan, EW_ADD, d_out, d_a, d_b, nullptr, 2 * batch, 0, c->L, (cudaStream_t)stream);

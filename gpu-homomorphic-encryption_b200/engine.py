@@ -476,6 +476,13 @@ class BfvContext:
                                                    _ptr(sc) if want_scaled else None, batch, _stream()))
         return (out, sc) if want_scaled else out
 
+    def noise_budget(self, ct, sk) -> np.ndarray:
+        """invariant noise budget in bits per ciphertext (FHEContext::estimate_noise_budget, include/fhe.cuh:142); synchronises."""
+        batch = ct.numel() // (2 * self.L * self.n)
+        bits = np.zeros(batch, dtype=np.float64)
+        check(self.lib.fhe_b200_bfv_noise_budget(self.h, _ptr(ct), _ptr(sk), batch, bits.ctypes.data_as(C.POINTER(C.c_double)), _stream()))
+        return bits
+
     def multiply_no_relin(self, a, b, out=None):
         """3-component product [B][3][L][N] (FHEContext::multiply before its relinearize call, src/fhe.cu:198-219); a is b (the same
         tensor) takes the squaring path."""

@@ -247,6 +247,14 @@ public:
         replace(ct, out);
     }
 
+    // invariant noise budget in bits (include/fhe.cuh:142, declared only in the reference)
+    float estimate_noise_budget(const Ciphertext& ct, const SecretKey& sk) {
+        if (ct.components.size() != 2) throw std::runtime_error("estimate_noise_budget: relinearize the ciphertext first");
+        double bits = 0;
+        detail::check(fhe_b200_bfv_noise_budget(ctx_, ct.components[0]->rns, sk.sk->rns, 1, &bits, stream_), "estimate_noise_budget");
+        return (float)bits;
+    }
+
     const SchemeParams& params() const { return params_; }
     fhe_b200_bfv* engine() const { return ctx_; }
     cudaStream_t stream() const { return stream_; }

@@ -183,6 +183,12 @@ int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* ctx, const uint64_t* d_ct, const u
  * scaled tensor before relinearisation. */
 int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
                                 uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream);
+/* FHEContext::estimate_noise_budget (include/fhe.cuh:142, declared only): invariant noise budget in bits,
+ * log2(Q) - log2(||[t (c0 + c1 s)]_Q||_inf) - 1, one value per ciphertext into the HOST array h_bits[batch].  The device
+ * computes t (c0 + c1 s) per limb; the host centres every coefficient through mixed-radix digits.  Synchronises the stream;
+ * a diagnostic (O(N L^2) host work), not a hot-path call. */
+int fhe_b200_bfv_noise_budget(fhe_b200_bfv* ctx, const uint64_t* d_ct, const uint64_t* d_sk, uint32_t batch, double* h_bits,
+                              void* stream);
 /* The two halves on their own, as the reference's API has them (multiply builds three components, src/fhe.cu:198-219;
  * relinearize reduces them to two, :226-235 -- a stub there): d_out3 and d_ct3 are [batch][3][L][N] coefficient form.  Sums of
  * 3-component ciphertexts (fhe_b200_poly_add over 3*batch polynomials) can be relinearised once.  d_a == d_b (same pointer) takes

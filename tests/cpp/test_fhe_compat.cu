@@ -162,6 +162,16 @@ static void test_fhe_operations() {              // tests/test_fhe.cu:169-273
         FHEContext::release(e1); FHEContext::release(e2); FHEContext::release(prod); FHEContext::release(sum); FHEContext::release(diff); FHEContext::release(scaled);
         FHEContext::release(b1); FHEContext::release(b2); FHEContext::release(two); FHEContext::release(pp); FHEContext::release(ps); FHEContext::release(pd); FHEContext::release(pq);
     }
+    // noise budget (include/fhe.cuh:142): log2 Q = 120 bits; a fresh ciphertext keeps most of it, a product less, a chain less still
+    {
+        const float fresh = ctx.estimate_noise_budget(ct1, sk);
+        Ciphertext once; ctx.multiply(once, ct1, ct2, rlk);
+        const float after1 = ctx.estimate_noise_budget(once, sk), after2 = ctx.estimate_noise_budget(ct_mul, sk);
+        REQUIRE(fresh > 70.0f && fresh < 119.0f);
+        REQUIRE(after1 > 20.0f && after1 < fresh - 10.0f);
+        REQUIRE(after2 > 0.0f && after2 < after1);
+        FHEContext::release(once);
+    }
     // multiply and relinearize as separate calls (src/fhe.cu:198-235): a sum of two 3-component products relinearised once,
     // and the square of a ciphertext (same operand twice)
     {

@@ -378,3 +378,44 @@ def test_multiply_and_relinearize_separately_vs_oracle(fhe, oracle, preset):
     assert np.array_equal(to_host(g.decrypt(sq, sk))[1], oracle.schoolbook_negacyclic(m[1], m[1], t))
     with pytest.raises(fhe.FheB200Error):
         g.relinearize(prod3, rlk, out=prod3.view(-1)[: 2 * 2 * L * n].view(2, 2, L, n))
+
+
+@pytest.mark.gpu
+def test_noise_budget_matches_exact_big_integer_value(fhe, oracle):
+    """fhe_b200_bfv_noise_budget against the definition evaluated with Python big integers: per limb t (c0 + c1 s) mod q_i from
+    the oracle, CRT, centred, infinity norm.  Floating point only in the final log2: tolerance 1e-6 bits."""
+    import math
+    from math import prod
+    from bigint_ref import crt
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, "small")
+    n, t, L = p["n"], p["t"], p["L"]
+    qs = [int(q) for q in p["primes"][:L]]
+    Q = prod(qs)
+    sk, pk = g.keygen(71, 72); rlk = g.relinkey_gen(73, sk)
+    s_small, _ = o.secret_keygen(71)
+    rng = np.random.default_rng(1300)
+    m = rng.integers(0, t, (2, n), dtype=np.uint64)
+    ct = g.encrypt(950, to_device(m), pk)
+    prod_ct = g.multiply(ct[0:1].contiguous(), ct[1:2].contiguous(), rlk)
+    zero = torch.zeros_like(ct[0:1])                                   # (0, 0): the noise is exactly zero
+    cts = torch.cat([ct, prod_ct, zero]).contiguous()
+    got = g.noise_budget(cts, sk)
+
+    def exact(h):
+        worst = 0
+        res = []
+        for i, q in enumerate(qs):
+            s_q = np.array([int(v) % q for v in s_small], dtype=np.uint64)
+            v = (oracle.negacyclic_mul_ntt(h[1, i], s_q, q).astype(object) + h[0, i].astype(object)) % q
+            res.append([(int(x) * t) % q for x in v])
+        for k in range(n):
+            w = crt([res[i][k] for i in range(L)], qs)
+            worst = max(worst, min(w, Q - w))
+        return math.log2(Q) - math.log2(worst) - 1 if worst else math.log2(Q) - 1
+
+    h = to_host(cts)
+    want = [exact(h[i]) for i in range(4)]
+    assert np.allclose(got, want, rtol=0, atol=1e-6), (got, want)
+    assert want[2] < min(want[0], want[1]) - 10 and want[2] > 0          # a product costs budget but leaves some
+    assert got[3] == pytest.approx(math.log2(Q) - 1, abs=1e-9)
