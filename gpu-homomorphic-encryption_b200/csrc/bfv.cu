@@ -317,7 +317,7 @@ extern "C" int fhe_b200_gaussian_cdt(double sigma, uint64_t* h_cdt, uint32_t cap
 
 extern "C" int fhe_b200_bfv_destroy(fhe_b200_bfv* c) {
     if (!c) return 0;
-    cudaSetDevice(c->device);
+    DeviceGuard dev_guard(c->device);
     fhe_b200_lincomb_destroy(c->q2r); fhe_b200_lincomb_destroy(c->scale); fhe_b200_lincomb_destroy(c->r2q);
     fhe_b200_lincomb_destroy(c->moddown); fhe_b200_lincomb_destroy(c->dec);
     for (auto* m : c->modup) fhe_b200_lincomb_destroy(m);
@@ -348,6 +348,7 @@ extern "C" int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t 
         for (uint32_t k = i + 1; k < L + R; k++) FHE_REQUIRE(h_moduli[i] != h_moduli[k], "bfv_create: moduli %u and %u are equal", i, k);
     for (uint32_t i = 0; i < L; i++) FHE_REQUIRE(host::invmod(t % h_moduli[i], h_moduli[i]) != 0, "bfv_create: t is not coprime to q_%u", i);
 
+    DeviceGuard dev_guard(device);                 // the allocations below belong to the context's device
     auto* c = new fhe_b200_bfv();
     c->n = n; c->logn = host::ilog2(n); c->L = L; c->R = R; c->K = K; c->dnum = dnum; c->alpha = L / dnum; c->t = t;
     c->device = device; c->hw = hamming_weight;
@@ -419,7 +420,7 @@ extern "C" fhe_b200_plan* fhe_b200_bfv_plan(fhe_b200_bfv* c) { return c ? c->pla
 extern "C" int fhe_b200_bfv_keygen(fhe_b200_bfv* c, uint64_t seed_sk, uint64_t seed_pk, uint64_t* d_sk, uint64_t* d_pk, void* stream) {
     FHE_REQUIRE(c && d_sk && d_pk, "bfv_keygen: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L, A = c->L + c->R;
     const LimbParams* prm = c->plan->d_params;
     // secret: stream 0 (signs: stream 1 when a hamming weight is set)
@@ -453,7 +454,7 @@ extern "C" int fhe_b200_bfv_keygen(fhe_b200_bfv* c, uint64_t seed_sk, uint64_t s
 extern "C" int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* c, uint64_t seed, const uint64_t* d_sk, uint64_t* d_rlk, void* stream) {
     FHE_REQUIRE(c && d_sk && d_rlk, "bfv_relinkeygen: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, W = c->L + c->K;
     const LimbParams* prm = c->plan->d_params;
     for (uint32_t d = 0; d < c->dnum; d++) {
@@ -476,7 +477,7 @@ extern "C" int fhe_b200_bfv_encrypt(fhe_b200_bfv* c, uint64_t seed, const uint64
     FHE_REQUIRE(c && d_pt && d_pk && d_ct, "bfv_encrypt: null argument");
     if (!batch) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L;
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
@@ -503,7 +504,7 @@ extern "C" int fhe_b200_bfv_decrypt(fhe_b200_bfv* c, const uint64_t* d_ct, const
     FHE_REQUIRE(c && d_ct && d_sk && d_pt, "bfv_decrypt: null argument");
     if (!batch) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L;
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
@@ -533,7 +534,7 @@ extern "C" int fhe_b200_bfv_noise_budget(fhe_b200_bfv* c, const uint64_t* d_ct, 
     FHE_REQUIRE(c && d_ct && d_sk && h_bits, "bfv_noise_budget: null argument");
     if (!batch) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L;
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
@@ -604,6 +605,7 @@ extern "C" int fhe_b200_bfv_add_plain(fhe_b200_bfv* c, const uint64_t* d_ct, con
                                       int subtract, void* stream) {
     FHE_REQUIRE(c && d_ct && d_pt && d_out, "bfv_add_plain: null argument");
     if (!batch) return 0;
+    DeviceGuard dev_guard(c->device);
     const size_t total = (size_t)batch * 2 * c->L * c->n;
     add_plain_kernel<<<grid_for(c, total), 256, 0, (cudaStream_t)stream>>>(d_out, d_ct, d_pt, c->plan->d_params, c->d_delta, c->logn, c->L, total, subtract);
     FHE_LAUNCH_CHECK();
@@ -614,7 +616,7 @@ extern "C" int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* c, const uint64_t* d_ct
     FHE_REQUIRE(c && d_ct && d_pt && d_out, "bfv_multiply_plain: null argument");
     if (!batch) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const size_t ln = (size_t)c->L * c->n;
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
     uint64_t* m = c->d_ws;
@@ -674,7 +676,7 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
 // extended and transformed instead of four (the tensor kernel reads the same planes for both operands; results are identical).
 static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk, uint64_t* d_out,
                          uint64_t* d_scaled, uint32_t batch, cudaStream_t st) {
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, dnum = c->dnum, B = batch;
     const LimbParams* prm = c->plan->d_params;
     const size_t N = n, ln = (size_t)L * N, an = (size_t)A * N, wn = (size_t)W * N, rn = (size_t)R * N;
@@ -742,7 +744,7 @@ extern "C" int fhe_b200_bfv_relinearize(fhe_b200_bfv* c, const uint64_t* d_ct3, 
     FHE_REQUIRE(d_ct3 != d_out, "bfv_relinearize: the output must not alias the input");
     if (!batch) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const size_t ln = (size_t)c->L * c->n, wn = (size_t)(c->L + c->K) * c->n;
     const size_t w_dig = (size_t)c->dnum * batch * wn, w_acc = 2 * (size_t)batch * wn;
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_dig + w_acc));
@@ -763,7 +765,7 @@ extern "C" int fhe_b200_bfv_galoiskeygen(fhe_b200_bfv* c, uint64_t seed, uint32_
     FHE_REQUIRE(c && d_sk && d_gk, "bfv_galoiskeygen: null argument");
     FHE_REQUIRE((galois_elt & 1u) && galois_elt < 2 * c->n, "bfv_galoiskeygen: the Galois element must be odd and below 2N");
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, W = c->L + c->K;
     const LimbParams* prm = c->plan->d_params;
     const size_t wn = (size_t)W * n;
@@ -794,7 +796,7 @@ extern "C" int fhe_b200_bfv_apply_galois(fhe_b200_bfv* c, const uint64_t* d_ct, 
     FHE_REQUIRE((galois_elt & 1u) && galois_elt < 2 * c->n, "bfv_apply_galois: the Galois element must be odd and below 2N");
     if (!batch) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L, W = L + c->K, B = batch;
     const size_t ln = (size_t)L * n, wn = (size_t)W * n;
     // workspace: rot [B][2][L][N] | dig [dnum][B][W][N] | acc [2][B][W][N]
@@ -823,7 +825,7 @@ extern "C" int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* c, const uint64_t*
                                                 uint64_t* h_out, uint32_t batch) {
     FHE_REQUIRE(c && h_a && h_b && d_rlk && h_out, "bfv_multiply_relin_host: null argument");
     if (!batch) return 0;
-    FHE_CUDA(cudaSetDevice(c->device));
+    DeviceGuard dev_guard(c->device);
     const size_t ct = 2 * (size_t)c->L * c->n;            // words per ciphertext
     // chunk = G ciphertext pairs (about 64 MiB of input, at least one pair); three staging sets on three streams
     uint32_t G = (uint32_t)(((size_t)64 << 20) / (2 * ct * 8));
@@ -861,6 +863,7 @@ extern "C" int fhe_b200_bfv_tensor(fhe_b200_plan* plan, uint64_t* d_out, const u
     FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
     const size_t per = (size_t)batch * limb_count * plan->n / 2;
     if (!per) return 0;
+    DeviceGuard dev_guard(plan->device);
     const size_t w = (per + 255) / 256, cap = (size_t)plan->sm_count * 16;
     tensor_kernel<<<(uint32_t)(w < cap ? w : cap), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_out, (const ulonglong2*)d_ext, plan->d_params,
                                                                                  plan->logn, limb_begin, limb_count, per, 2 * per);
@@ -873,6 +876,7 @@ extern "C" int fhe_b200_bfv_ks_inner(fhe_b200_plan* plan, uint64_t* d_acc, const
     FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
     const size_t per = (size_t)batch * limb_count * plan->n / 2;
     if (!per) return 0;
+    DeviceGuard dev_guard(plan->device);
     const size_t w = (per + 255) / 256, cap = (size_t)plan->sm_count * 16;
     ks_inner_kernel<<<(uint32_t)(w < cap ? w : cap), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_acc, (const ulonglong2*)d_dig, (const ulonglong2*)d_key,
                                                                                    plan->d_params, plan->logn, limb_begin, limb_count, dnum, batch);

@@ -87,7 +87,7 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
     cudaDeviceProp prop;
     FHE_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { set_error("plan_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return FHE_B200_ESTATE; }
-    FHE_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
     {   // keep stream-ordered temporaries (cudaMallocAsync) cached instead of returning them to the OS at every sync
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -156,7 +156,7 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
 
 extern "C" int fhe_b200_plan_destroy(fhe_b200_plan* p) {
     if (!p) return 0;
-    cudaSetDevice(p->device);
+    DeviceGuard dev_guard(p->device);
     release_fused_scratch(p);
     cudaFree(p->d_fwd); cudaFree(p->d_inv); cudaFree(p->d_params);
     cudaFree(p->d_fwd_bal); cudaFree(p->d_inv_bal);
@@ -225,7 +225,7 @@ extern "C" int fhe_b200_negacyclic_mul(fhe_b200_plan* plan, uint64_t* d_out, con
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bytes = (size_t)batch * limb_count * plan->n * sizeof(uint64_t);
     if (!bytes) return 0;
-    FHE_CUDA(cudaSetDevice(plan->device));
+    DeviceGuard dev_guard(plan->device);
     // N <= 4096: one fused kernel (both forward transforms, the pointwise product and the inverse in shared memory) while the
     // grid is small enough that its single CTA per SM does not cost throughput; FHE_B200_MUL_FUSED = 0 | 1 overrides
     if (plan->logn <= 12) {
@@ -252,7 +252,7 @@ extern "C" int fhe_b200_ntt_host(fhe_b200_plan* plan, uint64_t* h_data, uint32_t
     FHE_REQUIRE(direction >= 0 && direction <= 2, "ntt_host: direction must be 0, 1 or 2");
     FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
     if (!batch || !limb_count) return 0;
-    FHE_CUDA(cudaSetDevice(plan->device));
+    DeviceGuard dev_guard(plan->device);
     const size_t poly_bytes = (size_t)limb_count * plan->n * sizeof(uint64_t);
     size_t polys_per_chunk = (64u << 20) / poly_bytes; if (!polys_per_chunk) polys_per_chunk = 1;
     const size_t need = polys_per_chunk * poly_bytes;

@@ -10,6 +10,26 @@
 
 namespace fhe_b200 {
 
+// Function attributes (dynamic shared memory limits) are per device: a process may hold plans on several GPUs, so "set once" is
+// tracked per device ordinal.
+// Every entry point runs on the device its plan / context / conversion object was created for, whatever the caller's current
+// device is, and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1; bool changed = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) changed = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool need(int device) { const unsigned long long bit = 1ull << (device & 63); if (mask & bit) return false; mask |= bit; return true; }
+};
+
+
 void set_error(const char* fmt, ...);
 
 #define FHE_CUDA(call)                                                                              \

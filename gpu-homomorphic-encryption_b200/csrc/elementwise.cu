@@ -46,6 +46,7 @@ int launch_elementwise(fhe_b200_plan* plan, EwOp op, uint64_t* d_out, const uint
     FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
     const size_t nvec = (size_t)batch * limb_count * plan->n / 2;
     if (nvec == 0) return 0;
+    DeviceGuard dev_guard(plan->device);
     const uint32_t grid = ew_grid(plan, nvec);
     ScalarPack sc;
     if (op == EW_MUL_SCALAR || op == EW_ADD_SCALAR) {
@@ -157,6 +158,7 @@ extern "C" int fhe_b200_bitrev_permute(fhe_b200_plan* plan, uint64_t* d_out, con
     FHE_REQUIRE(plan && d_out && d_in && d_out != d_in, "bitrev_permute: null or aliased buffers");
     const size_t total = (size_t)n_polys * plan->n;
     if (!total) return 0;
+    DeviceGuard dev_guard(plan->device);
     bitrev_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(d_out, d_in, plan->logn, total);
     FHE_LAUNCH_CHECK();
     return 0;
@@ -184,6 +186,7 @@ extern "C" int fhe_b200_from_rns_u256(fhe_b200_plan* plan, void* d_u256, const u
     for (uint32_t a = 0; a < limb_count; a++) { double b = 0; for (uint64_t t = plan->h_params[limb_begin + a].q; t; t >>= 1) b++; bits += b; }
     FHE_REQUIRE(bits <= 256, "from_rns_u256: the product of the moduli exceeds 256 bits");
     if (!count) return 0;
+    DeviceGuard dev_guard(plan->device);
     GarnerConsts gc;
     for (uint32_t a = 0; a < 4; a++) {
         gc.q[a] = a < limb_count ? plan->moduli[limb_begin + a] : 1;
@@ -202,6 +205,7 @@ extern "C" int fhe_b200_to_rns_u256(fhe_b200_plan* plan, uint64_t* d_out, const 
     FHE_REQUIRE(plan && d_out && d_u256, "to_rns_u256: null argument");
     FHE_TRY(check_range(plan, 1, limb_begin, limb_count));
     if (!count) return 0;
+    DeviceGuard dev_guard(plan->device);
     to_rns_u256_kernel<<<flat_grid(count), 256, 0, (cudaStream_t)stream>>>(d_out, (const ulonglong2*)d_u256, plan->d_params,
                                                                           limb_begin, limb_count, count);
     FHE_LAUNCH_CHECK();

@@ -184,6 +184,7 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     FHE_REQUIRE(n >= 32 && (n & (n - 1)) == 0, "lincomb: n_coeffs must be a power of two >= 32");
     FHE_REQUIRE(!lc->use_extra || view.extra, "lincomb: this object needs the extra limbs (scale-and-round)");
     if (!batch) return 0;
+    DeviceGuard dev_guard(lc->device);
     LcKernelArgs a;
     a.src_mod = lc->src_mod; a.pre = lc->pre; a.pre_s = lc->pre_s; a.th_hi = lc->th_hi; a.th_lo = lc->th_lo;
     a.dst_mod = lc->dst_mod; a.mu_hi = lc->mu_hi; a.mu_lo = lc->mu_lo; a.c = lc->c; a.lam = lc->lam;
@@ -242,7 +243,7 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
     bool split30 = getenv("FHE_B200_NO_SPLIT30") == nullptr;
     for (uint32_t i = 0; i < h.S; i++) split30 = split30 && (h.src_mod[i] >> 60) == 0;
     for (uint32_t k = 0; k < h.T; k++) split30 = split30 && (h.dst_mod[k] >> 60) == 0;
-    FHE_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
     auto* lc = new fhe_b200_lincomb();
     lc->device = device; lc->S = h.S; lc->T = h.T; lc->SP = SP; lc->SPT2 = SPT2;
     lc->use_pre = h.use_pre; lc->use_extra = h.use_extra; lc->h = h; lc->split30 = split30;
@@ -365,7 +366,7 @@ extern "C" int fhe_b200_lincomb_create_scale(const uint64_t* h_q, uint32_t L, co
 }
 extern "C" int fhe_b200_lincomb_destroy(fhe_b200_lincomb* lc) {
     if (!lc) return 0;
-    cudaSetDevice(lc->device);
+    DeviceGuard dev_guard(lc->device);
     cudaFree(lc->d_blob);
     cudaFree(lc->d_bfrag);
     delete lc;
@@ -396,6 +397,7 @@ extern "C" int fhe_b200_modswitch_drop_last(fhe_b200_plan* plan, uint64_t* d_out
     FHE_REQUIRE(limb_count >= 2 && limb_count <= 64, "modswitch_drop_last: needs 2..64 limbs");
     const size_t total = (size_t)batch * (limb_count - 1) * plan->n;
     if (!total) return 0;
+    DeviceGuard dev_guard(plan->device);
     cudaStream_t st = (cudaStream_t)stream;
     uint64_t h_inv[64];
     const uint64_t ql = plan->moduli[limb_begin + limb_count - 1];

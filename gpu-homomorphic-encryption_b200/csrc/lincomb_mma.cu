@@ -234,13 +234,13 @@ void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<ui
 }
 
 template <int KT>
-static int launch_kt(const LcMmaArgs& a, int sm_count, cudaStream_t st) {
+static int launch_kt(const LcMmaArgs& a, int sm_count, int device, cudaStream_t st) {
     const size_t smem = (size_t)a.NG * KT * 8 * 32 * sizeof(uint2) + (size_t)(7 * 4 * KT + 9 * a.T) * sizeof(u64);
     FHE_REQUIRE(smem <= 220 * 1024, "lincomb (tensor-core path): fragment table of %zu bytes does not fit shared memory", smem);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    static size_t attr_smem[64] = {0};                   // per device ordinal: function attributes are per device
+    if (smem > attr_smem[device & 63]) {
         FHE_CUDA(cudaFuncSetAttribute(lincomb_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+        attr_smem[device & 63] = smem;
     }
     // as many resident warps as the table and the registers allow: 256-thread CTAs (two per SM at 128 registers, three for the
     // k-tile counts that compile to 80), or one CTA of 512 threads when the table needs more than half of the shared memory
@@ -270,7 +270,7 @@ int lincomb_mma_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uin
     a.use_pre = lc->use_pre; a.use_extra = lc->use_extra; a.c_is_one = lc->use_pre ? 0 : 1;
     a.tiles = (size_t)batch * n / 16;
     switch (lc->mma_kt) {
-#define KT_CASE(N_) case N_: return launch_kt<N_>(a, lc->sm_count, st);
+#define KT_CASE(N_) case N_: return launch_kt<N_>(a, lc->sm_count, lc->device, st);
         KT_CASE(1) KT_CASE(2) KT_CASE(3) KT_CASE(4) KT_CASE(5) KT_CASE(6) KT_CASE(7) KT_CASE(8) KT_CASE(10) KT_CASE(13) KT_CASE(16)
 #undef KT_CASE
     }

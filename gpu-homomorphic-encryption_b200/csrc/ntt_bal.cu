@@ -124,13 +124,12 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
 template <int KA, int HB, bool NEAR>
 static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st) {
     using A = BalA<KA, HB, NEAR>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need(plan->device)) {
         FHE_CUDA(cudaFuncSetAttribute(bal_a_kernel<KA, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_a_kernel<KA, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
-        attr_set = true;
     }
     const uint32_t sms = (uint32_t)plan->sm_count;
     const uint64_t pls = (uint64_t)a.nl * a.nb;

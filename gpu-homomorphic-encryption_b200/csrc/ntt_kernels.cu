@@ -368,11 +368,10 @@ static int run_fused(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t 
     FHE_CUDA(cudaMemsetAsync(fs->d_sync, 0, sync_words * sizeof(uint32_t), st));
     a.work = fs->d_work; a.n_items = fs->n_items; a.pg = sc.pg; a.n_groups = G; a.sync = fs->d_sync;
     constexpr size_t smem = TileSmem<LB>::total;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need(plan->device)) {
         FHE_CUDA(cudaFuncSetAttribute(ntt_fused_kernel<LB, K1, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FHE_CUDA(cudaFuncSetAttribute(ntt_fused_kernel<LB, K1, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     const uint32_t grid = (uint32_t)std::min<size_t>((size_t)2 * plan->sm_count, fs->n_items);
     const bool prof = profile_on();
@@ -459,10 +458,9 @@ __global__ void __launch_bounds__(1 << (LB - 4), 1) negacyclic_mul_kernel(const 
 template <int LB, int HB, bool NEAR>
 static int run_mul(fhe_b200_plan* plan, const MulArgs& a, uint32_t ctas, cudaStream_t st) {
     constexpr size_t smem = MulSmem<LB>::total;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need(plan->device)) {
         FHE_CUDA(cudaFuncSetAttribute(negacyclic_mul_kernel<LB, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     negacyclic_mul_kernel<LB, HB, NEAR><<<ctas, 1 << (LB - 4), smem, st>>>(a);
     FHE_LAUNCH_CHECK();
@@ -512,11 +510,10 @@ static int run_chunk(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t 
     a.groups = groups;
     const uint32_t tile_grid = lt * groups;
     constexpr size_t smem = TileSmem<LB>::total;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need(plan->device)) {
         FHE_CUDA(cudaFuncSetAttribute(ntt_tile_fwd_kernel<LB, K1, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FHE_CUDA(cudaFuncSetAttribute(ntt_tile_inv_kernel<LB, K1, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     if (!inverse) {
         if constexpr (K1 > 0) {
@@ -567,6 +564,7 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
                uint32_t limb_count, bool inverse, cudaStream_t st) {
     FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
     if (batch == 0 || limb_count == 0) return 0;
+    DeviceGuard dev_guard(plan->device);
     NttArgs a;
     a.out = d_out; a.in = d_in;
     a.tw = inverse ? plan->d_inv : plan->d_fwd;

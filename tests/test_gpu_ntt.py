@@ -345,3 +345,46 @@ def test_config3_full_size_properties(fhe, oracle, chain):
     assert torch.equal(s, plan.add(x[0:1].contiguous(), x[1:2].contiguous()))
     plan.inverse(x)
     assert torch.equal(x, ref)
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process(fhe, oracle):
+    """plans, conversions and BFV contexts on two GPUs of one process (the C ABI takes a device ordinal): function attributes
+    such as the dynamic shared-memory limit are per device.  Skipped on a single-GPU box."""
+    import torch
+    from fhe_b200.engine import to_device, to_host
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    chain = oracle.prime_chain(49)
+    rng = np.random.default_rng(4242)
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            for n in (1 << 12, 1 << 13, 1 << 16):
+                plan = fhe.Plan(n, chain[:2], device=dev)
+                x = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in chain[:2]])[None]
+                dx = to_device(x, f"cuda:{dev}")
+                plan.forward(dx)
+                torch.cuda.synchronize()
+                assert np.array_equal(to_host(dx)[0, 1], oracle.ntt_forward(x[0, 1], chain[1])), (dev, n)
+                plan.inverse(dx)
+                torch.cuda.synchronize()
+                assert np.array_equal(to_host(dx), x), (dev, n)
+            src, dst = chain[:24], chain[24:]
+            z = np.stack([rng.integers(0, m, 256, dtype=np.uint64) for m in src])[None]
+            got = to_host(fhe.LinComb.conv(src, dst, device=dev).apply(to_device(z, f"cuda:{dev}")))[0]
+            assert np.array_equal(got, oracle.LinComb.conv(src, dst).apply(z[0])), dev
+    # a BFV context on the second device while the current device is the first: the entry points switch to the object's
+    # device and restore the caller's
+    from fhe_b200.params import bfv_preset
+    p = bfv_preset("small")
+    torch.cuda.set_device(0)
+    g = fhe.BfvContext(p["n"], p["L"], p["R"], p["K"], p["dnum"], p["t"], p["primes"], p["sigma"], p["hamming_weight"], device=1)
+    assert torch.cuda.current_device() == 0
+    with torch.cuda.device(1):
+        sk, pk = g.keygen(1, 2); rlk = g.relinkey_gen(3, sk)
+        m = rng.integers(0, p["t"], (2, p["n"]), dtype=np.uint64)
+        ct = g.encrypt(5, to_device(m, "cuda:1"), pk)
+        out = g.multiply(ct[0:1].contiguous(), ct[1:2].contiguous(), rlk)
+        dec = to_host(g.decrypt(out, sk))[0]
+    assert np.array_equal(dec, oracle.schoolbook_negacyclic(m[0], m[1], p["t"]))
+    assert torch.cuda.current_device() == 0
