@@ -33,6 +33,46 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+_REF_ROOT = "/root/reference"
+_REF_LIB = os.path.join(_HERE, "_ref", "libref_kernels.so")
+
+
+def build_ref() -> str | None:
+    """Compile the REFERENCE's own complete device functions (add_mod / sub_mod / mul_mod_montgomery through its batch kernels,
+    src/bigint.cu:171-215) from the sources where they lie into oracle/_ref/ (git-ignored).  Only where /root/reference exists
+    (the build container); the GPU box uses the prebuilt file that travels with the snapshot."""
+    if os.path.isdir(_REF_ROOT):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "_ref"], stdout=subprocess.DEVNULL)
+    return _REF_LIB if os.path.exists(_REF_LIB) else None
+
+
+_ref_lib = None
+
+
+def ref_kernels():
+    """ctypes handle on oracle/_ref/libref_kernels.so (needs a GPU to call), or None when it was never built."""
+    global _ref_lib
+    if _ref_lib is None and os.path.exists(_REF_LIB):
+        L = C.CDLL(_REF_LIB)
+        for f in ("ref_batch_mod_add", "ref_batch_mod_sub", "ref_batch_mod_mul_montgomery"):
+            getattr(L, f).restype = C.c_int
+            getattr(L, f).argtypes = [u64p, u64p, C.c_uint64, u64p, C.c_uint32, u64p]
+        _ref_lib = L
+    return _ref_lib
+
+
+def ref_batch(op: str, a, b, q: int):
+    """run the reference's batch_mod_{add,sub,mul}_kernel on cuda:0 -> (uint64 results, True if every result fitted 64 bits)"""
+    L = ref_kernels()
+    a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.zeros_like(a); hi = np.zeros(1, dtype=np.uint64)
+    fn = {"add": L.ref_batch_mod_add, "sub": L.ref_batch_mod_sub, "mul_montgomery": L.ref_batch_mod_mul_montgomery}[op]
+    rc = fn(a.ctypes.data_as(u64p), b.ctypes.data_as(u64p), C.c_uint64(q), out.ctypes.data_as(u64p), a.size, hi.ctypes.data_as(u64p))
+    if rc:
+        raise RuntimeError(f"reference kernel failed (rc={rc})")
+    return out, int(hi[0]) == 0
+
+
 _lib = None
 
 

@@ -35,3 +35,16 @@ def test_version_and_error_string_without_gpu():
     lib = fhe_b200.load_library()
     assert lib.fhe_b200_version() >= 100
     assert lib.fhe_b200_last_error() is not None
+
+
+def test_reference_kernel_harness_builds_where_the_reference_is_present():
+    """oracle/_ref/libref_kernels.so: the reference's own add/sub/Montgomery kernels compiled from /root/reference (this container
+    only; the GPU box gets the prebuilt file).  Loading it and resolving its symbols needs no GPU."""
+    import oracle
+    path = oracle.build_ref()
+    if not os.path.isdir("/root/reference"):
+        return                                                   # on the GPU box: nothing to build, the prebuilt file is used
+    assert path and os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for name in ("ref_batch_mod_add", "ref_batch_mod_sub", "ref_batch_mod_mul_montgomery"):
+        assert hasattr(lib, name), name
