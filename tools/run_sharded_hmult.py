@@ -22,6 +22,7 @@ from fhe_b200.params import bfv_preset
 ap = argparse.ArgumentParser()
 ap.add_argument("--preset", default="c4")
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--profile", action="store_true", help="rank 0 prints the kernels of three multiplies by CUDA time (torch.profiler)")
 a = ap.parse_args()
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lr = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
@@ -54,6 +55,22 @@ e1.record(); torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=torch.device("cuda", lr))
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if a.profile:
+    import time
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        sb.multiply_relin(al, bl, kq, kp)
+    t_issue = (time.perf_counter() - t0) / 3
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            sb.multiply_relin(al, bl, kq, kp)
+        torch.cuda.synchronize()
+    if rank == 0:
+        print(f"host time to issue one multiply: {t_issue * 1e3:.3f} ms", flush=True)
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=60), flush=True)
 # single-GPU time of the same op on rank 0 for the scaling ratio
 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s0.record()
