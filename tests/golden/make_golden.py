@@ -49,6 +49,11 @@ def cases():
     out["bfv_c2/gk3"] = {"output": digest(gk)}
     out["bfv_c2/encrypt"] = {"input": digest(m1), "output": digest(c1)}
     out["bfv_c2/multiply_relin"] = {"output": digest(o.multiply_relin(c1, c2, rlk))}
+    prod3 = o.multiply(c1, c2)
+    out["bfv_c2/multiply_3_components"] = {"output": digest(prod3)}
+    mods = np.array(params["primes"][:params["L"]], dtype=np.uint64)[None, :, None]
+    out["bfv_c2/relinearize_sum_of_products"] = {"output": digest(o.relinearize((prod3 + o.multiply(c1, c1)) % mods, rlk))}
+    out["bfv_c2/square"] = {"output": digest(o.multiply_relin(c1, c1, rlk))}
     out["bfv_c2/rotate3"] = {"output": digest(o.apply_galois(c1, 3, gk))}
     out["bfv_c2/mod_switch_to_next"] = {"output": digest(o.mod_switch_to_next(c1))}
     return out

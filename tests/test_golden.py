@@ -67,5 +67,10 @@ def test_cuda_path_matches_golden_digests(oracle):
     assert _digest(to_host(gk)) == GOLD["bfv_c2/gk3"]["output"]
     assert _digest(to_host(c1)[0]) == GOLD["bfv_c2/encrypt"]["output"]
     assert _digest(to_host(g.multiply(c1, c2, rlk))[0]) == GOLD["bfv_c2/multiply_relin"]["output"]
+    prod3 = g.multiply_no_relin(c1, c2)
+    assert _digest(to_host(prod3)[0]) == GOLD["bfv_c2/multiply_3_components"]["output"]
+    lazy = g.relinearize(g.add3(prod3, g.multiply_no_relin(c1, c1)), rlk)
+    assert _digest(to_host(lazy)[0]) == GOLD["bfv_c2/relinearize_sum_of_products"]["output"]
+    assert _digest(to_host(g.multiply(c1, c1, rlk))[0]) == GOLD["bfv_c2/square"]["output"]
     assert _digest(to_host(g.apply_galois(c1, 3, gk))[0]) == GOLD["bfv_c2/rotate3"]["output"]
     assert _digest(to_host(g.mod_switch_to_next(c1))[0]) == GOLD["bfv_c2/mod_switch_to_next"]["output"]
