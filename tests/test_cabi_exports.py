@@ -48,3 +48,15 @@ def test_reference_kernel_harness_builds_where_the_reference_is_present():
     lib = ctypes.CDLL(path)
     for name in ("ref_batch_mod_add", "ref_batch_mod_sub", "ref_batch_mod_mul_montgomery"):
         assert hasattr(lib, name), name
+
+
+def test_header_is_plain_c():
+    """include/fhe_b200.h is the FFI surface: it must compile as C99 (what cgo / JNI / ctypes-style binders parse) and as C++."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "hdr.c")
+        open(src, "w").write('#include "include/fhe_b200.h"\nint main(void) { return fhe_b200_version == 0; }\n')
+        subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", root, src])
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", root, "-x", "c++", src])
