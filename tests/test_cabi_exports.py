@@ -57,6 +57,6 @@ def test_header_is_plain_c():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "hdr.c")
-        open(src, "w").write('#include "include/fhe_b200.h"\nint main(void) { return fhe_b200_version == 0; }\n')
+        open(src, "w").write('#include "include/fhe_b200.h"\nint main(void) { return 0; }\n')
         subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", root, src])
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", root, "-x", "c++", src])
