@@ -38,6 +38,9 @@ struct fhe_b200_bfv {
     uint64_t* d_io[3] = {nullptr, nullptr, nullptr}; size_t io_words[3] = {0, 0, 0};   // device staging of the host-buffer entry point
     cudaStream_t io_stream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t io_done[3] = {nullptr, nullptr, nullptr};
+    // multiply: the batch is split in two halves on two internal streams (the conversions of one half overlap the transforms of the other)
+    cudaStream_t mul_stream[2] = {nullptr, nullptr};
+    cudaEvent_t mul_fork = nullptr, mul_join[2] = {nullptr, nullptr};
 };
 
 namespace fhe_b200 {
@@ -328,6 +331,11 @@ extern "C" int fhe_b200_bfv_destroy(fhe_b200_bfv* c) {
         if (c->io_stream[i]) cudaStreamDestroy(c->io_stream[i]);
         if (c->io_done[i]) cudaEventDestroy(c->io_done[i]);
     }
+    for (int i = 0; i < 2; i++) {
+        if (c->mul_stream[i]) cudaStreamDestroy(c->mul_stream[i]);
+        if (c->mul_join[i]) cudaEventDestroy(c->mul_join[i]);
+    }
+    if (c->mul_fork) cudaEventDestroy(c->mul_fork);
     fhe_b200_plan_destroy(c->plan);
     delete c;
     return 0;
@@ -674,17 +682,19 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
 // when d_rlk is given -- hybrid key switching of the third component.  d_scaled (optional) receives the 3-component ciphertext
 // [B][3][L][N]; d_out (with d_rlk) the relinearised one [B][2][L][N].  d_a == d_b takes the squaring path: two polynomials are
 // extended and transformed instead of four (the tensor kernel reads the same planes for both operands; results are identical).
-static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk, uint64_t* d_out,
-                         uint64_t* d_scaled, uint32_t batch, cudaStream_t st) {
-    DeviceGuard dev_guard(c->device);
+static size_t multiply_ws_words(const fhe_b200_bfv* c, uint32_t B) {
+    const size_t N = c->n, an = (size_t)(c->L + c->R) * N, wn = (size_t)(c->L + c->K) * N, rn = (size_t)c->R * N, ln = (size_t)c->L * N;
+    return (size_t)B * (7 * an + 3 * rn + 3 * ln + ((size_t)c->dnum + 2) * wn);
+}
+
+static int multiply_half(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk, uint64_t* d_out,
+                         uint64_t* d_scaled, uint32_t batch, uint64_t* ws, cudaStream_t st) {
     const uint32_t n = c->n, L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, dnum = c->dnum, B = batch;
     const LimbParams* prm = c->plan->d_params;
     const size_t N = n, ln = (size_t)L * N, an = (size_t)A * N, wn = (size_t)W * N, rn = (size_t)R * N;
     const bool square = d_a == d_b;
     // workspace: ext [4][B][A][N] | d [3][B][A][N] | sR [3][B][R][N] | sc [3][B][L][N] | dig [dnum][B][W][N] | acc [2][B][W][N]
     const size_t w_ext = 4 * B * an, w_d = 3 * B * an, w_sr = 3 * B * rn, w_sc = 3 * B * ln, w_dig = (size_t)dnum * B * wn, w_acc = 2 * B * wn;
-    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_ext + w_d + w_sr + w_sc + w_dig + w_acc));
-    uint64_t* ws = c->d_ws;
     uint64_t* ext = ws; uint64_t* d = ext + w_ext; uint64_t* sR = d + w_d; uint64_t* sc = sR + w_sr; uint64_t* dig = sc + w_sc; uint64_t* acc = dig + w_dig;
     int rc = 0;
     cudaError_t e = cudaSuccess;
@@ -724,6 +734,37 @@ static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d
     if (rc) return rc;
     FHE_CUDA(cudaGetLastError());
     return 0;
+}
+
+// The batch runs as two halves on two internal streams, forked from and joined to the caller's stream: while one half is in a
+// base conversion (tensor pipe, 35% of the IMAD pipe) the other is in its transforms (75% of the IMAD pipe), and the hardware
+// interleaves their CTAs -- +4..7% at config 4 (tools/exp_two_streams.py).  The halves split the same workspace (its size is linear
+// in the batch).  FHE_B200_HMULT_STREAMS=1 keeps everything on the caller's stream.
+static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk, uint64_t* d_out,
+                         uint64_t* d_scaled, uint32_t batch, cudaStream_t st) {
+    DeviceGuard dev_guard(c->device);
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, multiply_ws_words(c, batch)));
+    static const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;
+    if (batch < 2 || env_streams < 2) return multiply_half(c, d_a, d_b, d_rlk, d_out, d_scaled, batch, c->d_ws, st);
+    for (int i = 0; i < 2; i++) {
+        if (!c->mul_stream[i]) FHE_CUDA(cudaStreamCreateWithFlags(&c->mul_stream[i], cudaStreamNonBlocking));
+        if (!c->mul_join[i]) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_join[i], cudaEventDisableTiming));
+    }
+    if (!c->mul_fork) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_fork, cudaEventDisableTiming));
+    const size_t ct = 2 * (size_t)c->L * c->n, ct3 = 3 * (size_t)c->L * c->n;
+    const uint32_t b0 = (batch + 1) / 2, cnt[2] = {b0, batch - b0}, first[2] = {0, b0};
+    FHE_CUDA(cudaEventRecord(c->mul_fork, st));
+    int rc = 0;
+    for (int i = 0; i < 2 && !rc; i++) {
+        cudaStream_t s = c->mul_stream[i];
+        FHE_CUDA(cudaStreamWaitEvent(s, c->mul_fork, 0));
+        const size_t o = (size_t)first[i];
+        rc = multiply_half(c, d_a + o * ct, d_b + o * ct, d_rlk, d_out ? d_out + o * ct : nullptr, d_scaled ? d_scaled + o * ct3 : nullptr,
+                           cnt[i], c->d_ws + (i ? multiply_ws_words(c, b0) : 0), s);
+        FHE_CUDA(cudaEventRecord(c->mul_join[i], s));
+    }
+    for (int i = 0; i < 2; i++) FHE_CUDA(cudaStreamWaitEvent(st, c->mul_join[i], 0));      // joined even after an error: nothing is left running unordered
+    return rc;
 }
 
 extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,

@@ -180,7 +180,8 @@ int fhe_b200_bfv_add_plain(fhe_b200_bfv* ctx, const uint64_t* d_ct, const uint64
 int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* ctx, const uint64_t* d_ct, const uint64_t* d_pt, uint64_t* d_out,
                                 uint32_t batch, void* stream);
 /* FHEContext::multiply + relinearize (src/fhe.cu:199-235).  d_scaled (optional, [batch][3][L][N]) receives the
- * scaled tensor before relinearisation. */
+ * scaled tensor before relinearisation.  For batch >= 2 the work is forked from `stream` onto two internal streams (one half of the
+ * batch each) and joined back before the call's work is complete on `stream`; FHE_B200_HMULT_STREAMS=1 disables the split. */
 int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
                                 uint64_t* d_out, uint64_t* d_scaled, uint32_t batch, void* stream);
 /* FHEContext::estimate_noise_budget (include/fhe.cuh:142, declared only): invariant noise budget in bits,
