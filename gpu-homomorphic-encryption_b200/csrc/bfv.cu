@@ -480,56 +480,81 @@ extern "C" int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* c, uint64_t seed, const ui
 }
 
 // ---- encrypt / decrypt / add -----------------------------------------------------------------------------------------------
+// ---- batch split over two internal streams ------------------------------------------------------------------------------------
+// f(first, count, stream) is queued for each half of the batch on its own internal stream, forked from and joined to the caller's
+// stream.  Kernels of different character then overlap: the base conversions (tensor pipe) or HBM-bound element-wise passes of one
+// half with the IMAD-bound transforms of the other.  FHE_B200_HMULT_STREAMS=1 keeps everything on the caller's stream.
+template <class F>
+static int fork_join_halves(fhe_b200_bfv* c, uint32_t batch, cudaStream_t st, F&& f) {
+    static const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;
+    if (batch < 2 || env_streams < 2) return f(0u, batch, st);
+    for (int i = 0; i < 2; i++) {
+        if (!c->mul_stream[i]) FHE_CUDA(cudaStreamCreateWithFlags(&c->mul_stream[i], cudaStreamNonBlocking));
+        if (!c->mul_join[i]) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_join[i], cudaEventDisableTiming));
+    }
+    if (!c->mul_fork) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_fork, cudaEventDisableTiming));
+    const uint32_t b0 = (batch + 1) / 2, cnt[2] = {b0, batch - b0}, first[2] = {0, b0};
+    FHE_CUDA(cudaEventRecord(c->mul_fork, st));
+    int rc = 0;
+    for (int i = 0; i < 2 && !rc; i++) {
+        FHE_CUDA(cudaStreamWaitEvent(c->mul_stream[i], c->mul_fork, 0));
+        rc = f(first[i], cnt[i], c->mul_stream[i]);
+        FHE_CUDA(cudaEventRecord(c->mul_join[i], c->mul_stream[i]));
+    }
+    for (int i = 0; i < 2; i++) if (c->mul_join[i]) cudaStreamWaitEvent(st, c->mul_join[i], 0);      // joined even after an error
+    return rc;
+}
+
 extern "C" int fhe_b200_bfv_encrypt(fhe_b200_bfv* c, uint64_t seed, const uint64_t* d_pt, const uint64_t* d_pk, uint64_t* d_ct,
                                     uint32_t batch, void* stream) {
     FHE_REQUIRE(c && d_pt && d_pk && d_ct, "bfv_encrypt: null argument");
     if (!batch) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L;
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
-    uint64_t* u = c->d_ws;
-    sample_small_kernel<0><<<grid_for(c, (size_t)batch * n), 256, 0, st>>>(u, prm, c->logn, 0, L, batch, seed, 0, c->thr, c->d_cdt, c->cdt_len);
-    FHE_LAUNCH_CHECK();
-    int rc = launch_ntt(c->plan, u, u, batch, 0, L, false, st);
-    if (!rc) {
-        enc_mul_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(d_ct, u, d_pk, prm, c->logn, L, batch * ln);
+    // ciphertext b uses seed + b: a half that starts at polynomial `first` is seeded with seed + first
+    return fork_join_halves(c, batch, (cudaStream_t)stream, [&](uint32_t first, uint32_t cnt, cudaStream_t st) -> int {
+        uint64_t* u = c->d_ws + (size_t)first * ln;
+        uint64_t* ct = d_ct + (size_t)first * 2 * ln;
+        const uint64_t* pt = d_pt + (size_t)first * n;
+        const uint64_t sd = seed + first;
+        sample_small_kernel<0><<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(u, prm, c->logn, 0, L, cnt, sd, 0, c->thr, c->d_cdt, c->cdt_len);
+        FHE_LAUNCH_CHECK();
+        FHE_TRY(launch_ntt(c->plan, u, u, cnt, 0, L, false, st));
+        enc_mul_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(ct, u, d_pk, prm, c->logn, L, cnt * ln);
         count_launch();
-        rc = launch_ntt(c->plan, d_ct, d_ct, 2 * batch, 0, L, true, st);
-    }
-    if (!rc) {
-        enc_finish_kernel<<<grid_for(c, (size_t)batch * n), 256, 0, st>>>(d_ct, d_pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, batch, seed);
-        count_launch();
-    }
-    if (rc) return rc;
-    FHE_CUDA(cudaGetLastError());
-    return 0;
+        FHE_TRY(launch_ntt(c->plan, ct, ct, 2 * cnt, 0, L, true, st));
+        enc_finish_kernel<<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(ct, pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, cnt, sd);
+        FHE_LAUNCH_CHECK();
+        return 0;
+    });
 }
 
 extern "C" int fhe_b200_bfv_decrypt(fhe_b200_bfv* c, const uint64_t* d_ct, const uint64_t* d_sk, uint64_t* d_pt, uint32_t batch, void* stream) {
     FHE_REQUIRE(c && d_ct && d_sk && d_pt, "bfv_decrypt: null argument");
     if (!batch) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard dev_guard(c->device);
     const uint32_t n = c->n, L = c->L;
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
-    uint64_t* x = c->d_ws;
-    // x = c1 (strided gather), then x = INTT(NTT(x) * s) + c0
-    cudaError_t e = cudaMemcpy2DAsync(x, ln * 8, d_ct + ln, 2 * ln * 8, ln * 8, batch, cudaMemcpyDeviceToDevice, st);
-    int rc = e == cudaSuccess ? 0 : FHE_B200_ECUDA;
-    if (rc) set_error("bfv_decrypt: gather failed: %s", cudaGetErrorString(e));
-    if (!rc) rc = launch_ntt(c->plan, x, x, batch, 0, L, false, st);
-    if (!rc) { dec_mul_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(x, d_sk, prm, c->logn, L, batch * ln); count_launch(); }
-    if (!rc) rc = launch_ntt(c->plan, x, x, batch, 0, L, true, st);
-    if (!rc) { dec_add_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(x, d_ct, prm, c->logn, L, batch * ln); count_launch(); }
-    if (!rc) { LcView v; v.in = x; v.out = d_pt; rc = lincomb_launch(c->dec, v, n, batch, st); }
-    if (rc) return rc;
-    FHE_CUDA(cudaGetLastError());
-    return 0;
+    return fork_join_halves(c, batch, (cudaStream_t)stream, [&](uint32_t first, uint32_t cnt, cudaStream_t st) -> int {
+        uint64_t* x = c->d_ws + (size_t)first * ln;
+        const uint64_t* ct = d_ct + (size_t)first * 2 * ln;
+        // x = c1 (strided gather), then x = INTT(NTT(x) * s) + c0
+        cudaError_t e = cudaMemcpy2DAsync(x, ln * 8, ct + ln, 2 * ln * 8, ln * 8, cnt, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) { set_error("bfv_decrypt: gather failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
+        FHE_TRY(launch_ntt(c->plan, x, x, cnt, 0, L, false, st));
+        dec_mul_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(x, d_sk, prm, c->logn, L, cnt * ln); count_launch();
+        FHE_TRY(launch_ntt(c->plan, x, x, cnt, 0, L, true, st));
+        dec_add_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(x, ct, prm, c->logn, L, cnt * ln); count_launch();
+        LcView v; v.in = x; v.out = d_pt + (size_t)first * n;
+        FHE_TRY(lincomb_launch(c->dec, v, n, cnt, st));
+        FHE_CUDA(cudaGetLastError());
+        return 0;
+    });
 }
 
 // ---- invariant noise budget (FHEContext::estimate_noise_budget, /root/reference/include/fhe.cuh:142, declared only) ------------
@@ -736,35 +761,19 @@ static int multiply_half(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d
     return 0;
 }
 
-// The batch runs as two halves on two internal streams, forked from and joined to the caller's stream: while one half is in a
-// base conversion (tensor pipe, 35% of the IMAD pipe) the other is in its transforms (75% of the IMAD pipe), and the hardware
-// interleaves their CTAs -- +4..7% at config 4 (tools/exp_two_streams.py).  The halves split the same workspace (its size is linear
-// in the batch).  FHE_B200_HMULT_STREAMS=1 keeps everything on the caller's stream.
+// The batch runs as two halves on two internal streams (fork_join_halves): while one half is in a base conversion (tensor pipe,
+// 35% of the IMAD pipe) the other is in its transforms (75% of the IMAD pipe), and the hardware interleaves their CTAs -- +4..10% at
+// config 4 (tools/gpu_ab_streams.sh).  The halves split the same workspace (its size is linear in the batch).
 static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk, uint64_t* d_out,
                          uint64_t* d_scaled, uint32_t batch, cudaStream_t st) {
     DeviceGuard dev_guard(c->device);
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, multiply_ws_words(c, batch)));
-    static const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;
-    if (batch < 2 || env_streams < 2) return multiply_half(c, d_a, d_b, d_rlk, d_out, d_scaled, batch, c->d_ws, st);
-    for (int i = 0; i < 2; i++) {
-        if (!c->mul_stream[i]) FHE_CUDA(cudaStreamCreateWithFlags(&c->mul_stream[i], cudaStreamNonBlocking));
-        if (!c->mul_join[i]) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_join[i], cudaEventDisableTiming));
-    }
-    if (!c->mul_fork) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_fork, cudaEventDisableTiming));
     const size_t ct = 2 * (size_t)c->L * c->n, ct3 = 3 * (size_t)c->L * c->n;
-    const uint32_t b0 = (batch + 1) / 2, cnt[2] = {b0, batch - b0}, first[2] = {0, b0};
-    FHE_CUDA(cudaEventRecord(c->mul_fork, st));
-    int rc = 0;
-    for (int i = 0; i < 2 && !rc; i++) {
-        cudaStream_t s = c->mul_stream[i];
-        FHE_CUDA(cudaStreamWaitEvent(s, c->mul_fork, 0));
-        const size_t o = (size_t)first[i];
-        rc = multiply_half(c, d_a + o * ct, d_b + o * ct, d_rlk, d_out ? d_out + o * ct : nullptr, d_scaled ? d_scaled + o * ct3 : nullptr,
-                           cnt[i], c->d_ws + (i ? multiply_ws_words(c, b0) : 0), s);
-        FHE_CUDA(cudaEventRecord(c->mul_join[i], s));
-    }
-    for (int i = 0; i < 2; i++) FHE_CUDA(cudaStreamWaitEvent(st, c->mul_join[i], 0));      // joined even after an error: nothing is left running unordered
-    return rc;
+    return fork_join_halves(c, batch, st, [&](uint32_t first, uint32_t cnt, cudaStream_t s) -> int {
+        const size_t o = first;
+        return multiply_half(c, d_a + o * ct, d_b + o * ct, d_rlk, d_out ? d_out + o * ct : nullptr, d_scaled ? d_scaled + o * ct3 : nullptr,
+                             cnt, c->d_ws + multiply_ws_words(c, first), s);
+    });
 }
 
 extern "C" int fhe_b200_bfv_multiply_relin(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk,
