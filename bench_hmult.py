@@ -106,6 +106,9 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
     mul3_ms = timed(lambda: g.multiply_no_relin(ca, cb, out=ct3))
     out2 = torch.empty_like(ca)
     relin_ms = timed(lambda: g.relinearize(ct3, rlk, out=out2))
+    gk = g.galoiskey_gen(31, 3, sk)                      # rotate_rows by one step: automorphism + the same hybrid key switch
+    rot_ms = timed(lambda: g.apply_galois(ca, 3, gk))
+    del gk
     # invariant noise budget (bits) of one fresh ciphertext, of a product and of a depth-2 product: evidence that the parameter
     # set leaves room (host-side diagnostic, not timed)
     depth2 = g.multiply(out[0:1].contiguous(), ca[0:1].contiguous(), rlk)
@@ -144,7 +147,8 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
             "noise_budget_bits": {"fresh": round(float(nb[0]), 2), "after_multiply": round(float(nb[1]), 2), "after_depth_2": round(float(nb[2]), 2)},
             "square": {"value": B / (sq_ms / 1e3), "unit": "ops/s", "ms_per_op": sq_ms / B},
             "multiply_no_relin": {"value": B / (mul3_ms / 1e3), "unit": "ops/s", "ms_per_op": mul3_ms / B},
-            "relinearize": {"value": B / (relin_ms / 1e3), "unit": "ops/s", "ms_per_op": relin_ms / B}}
+            "relinearize": {"value": B / (relin_ms / 1e3), "unit": "ops/s", "ms_per_op": relin_ms / B},
+            "rotate": {"value": B / (rot_ms / 1e3), "unit": "ops/s", "ms_per_op": rot_ms / B}}
 
 
 if __name__ == "__main__":

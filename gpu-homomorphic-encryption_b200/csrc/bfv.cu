@@ -648,18 +648,20 @@ extern "C" int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* c, const uint64_t* d_ct
                                            void* stream) {
     FHE_REQUIRE(c && d_ct && d_pt && d_out, "bfv_multiply_plain: null argument");
     if (!batch) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard dev_guard(c->device);
     const size_t ln = (size_t)c->L * c->n;
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
-    uint64_t* m = c->d_ws;
-    lift_plain_kernel<<<grid_for(c, batch * ln), 256, 0, st>>>(m, d_pt, c->plan->d_params, c->logn, c->L, batch * ln);
-    FHE_LAUNCH_CHECK();
-    FHE_TRY(launch_ntt(c->plan, m, m, batch, 0, c->L, false, st));
-    FHE_TRY(launch_ntt(c->plan, d_out, d_ct, 2 * batch, 0, c->L, false, st));
-    mul_plain_kernel<<<grid_for(c, 2 * batch * ln), 256, 0, st>>>(d_out, m, c->plan->d_params, c->logn, c->L, 2 * batch * ln);
-    FHE_LAUNCH_CHECK();
-    return launch_ntt(c->plan, d_out, d_out, 2 * batch, 0, c->L, true, st);
+    return fork_join_halves(c, batch, (cudaStream_t)stream, [&](uint32_t first, uint32_t cnt, cudaStream_t st) -> int {
+        uint64_t* m = c->d_ws + (size_t)first * ln;
+        uint64_t* out = d_out + (size_t)first * 2 * ln;
+        lift_plain_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(m, d_pt + (size_t)first * c->n, c->plan->d_params, c->logn, c->L, cnt * ln);
+        FHE_LAUNCH_CHECK();
+        FHE_TRY(launch_ntt(c->plan, m, m, cnt, 0, c->L, false, st));
+        FHE_TRY(launch_ntt(c->plan, out, d_ct + (size_t)first * 2 * ln, 2 * cnt, 0, c->L, false, st));
+        mul_plain_kernel<<<grid_for(c, 2 * cnt * ln), 256, 0, st>>>(out, m, c->plan->d_params, c->logn, c->L, 2 * cnt * ln);
+        FHE_LAUNCH_CHECK();
+        return launch_ntt(c->plan, out, out, 2 * cnt, 0, c->L, true, st);
+    });
 }
 
 // ---- hybrid key switching ----------------------------------------------------------------------------------------------------
@@ -793,15 +795,16 @@ extern "C" int fhe_b200_bfv_relinearize(fhe_b200_bfv* c, const uint64_t* d_ct3, 
     FHE_REQUIRE(c && d_ct3 && d_rlk && d_out, "bfv_relinearize: null argument");
     FHE_REQUIRE(d_ct3 != d_out, "bfv_relinearize: the output must not alias the input");
     if (!batch) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard dev_guard(c->device);
-    const size_t ln = (size_t)c->L * c->n, wn = (size_t)(c->L + c->K) * c->n;
-    const size_t w_dig = (size_t)c->dnum * batch * wn, w_acc = 2 * (size_t)batch * wn;
-    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_dig + w_acc));
-    uint64_t* dig = c->d_ws; uint64_t* acc = dig + w_dig;
-    FHE_TRY(key_switch(c, d_ct3 + 2 * ln, 3 * ln, d_rlk, d_ct3, 3 * ln, d_ct3 + ln, 3 * ln, d_out, batch, dig, acc, st));
-    FHE_CUDA(cudaGetLastError());
-    return 0;
+    const size_t ln = (size_t)c->L * c->n, wn = (size_t)(c->L + c->K) * c->n, per = ((size_t)c->dnum + 2) * wn;      // workspace words per ciphertext
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * per));
+    return fork_join_halves(c, batch, (cudaStream_t)stream, [&](uint32_t first, uint32_t cnt, cudaStream_t st) -> int {
+        uint64_t* dig = c->d_ws + (size_t)first * per; uint64_t* acc = dig + (size_t)c->dnum * cnt * wn;
+        const uint64_t* in = d_ct3 + (size_t)first * 3 * ln;
+        FHE_TRY(key_switch(c, in + 2 * ln, 3 * ln, d_rlk, in, 3 * ln, in + ln, 3 * ln, d_out + (size_t)first * 2 * ln, cnt, dig, acc, st));
+        FHE_CUDA(cudaGetLastError());
+        return 0;
+    });
 }
 
 // ---- Galois keys, automorphisms / rotations, modulus chain (declared only in the reference: include/fhe.cuh:59-61,86,109-116) ---
@@ -845,20 +848,23 @@ extern "C" int fhe_b200_bfv_apply_galois(fhe_b200_bfv* c, const uint64_t* d_ct, 
     FHE_REQUIRE(c && d_ct && d_gk && d_out, "bfv_apply_galois: null argument");
     FHE_REQUIRE((galois_elt & 1u) && galois_elt < 2 * c->n, "bfv_apply_galois: the Galois element must be odd and below 2N");
     if (!batch) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard dev_guard(c->device);
-    const uint32_t n = c->n, L = c->L, W = L + c->K, B = batch;
+    const uint32_t n = c->n, L = c->L, W = L + c->K;
     const size_t ln = (size_t)L * n, wn = (size_t)W * n;
-    // workspace: rot [B][2][L][N] | dig [dnum][B][W][N] | acc [2][B][W][N]
-    const size_t w_rot = 2 * B * ln, w_dig = (size_t)c->dnum * B * wn, w_acc = 2 * B * wn;
-    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, w_rot + w_dig + w_acc));
-    uint64_t* rot = c->d_ws; uint64_t* dig = rot + w_rot; uint64_t* acc = dig + w_dig;
-    galois_kernel<<<grid_for(c, w_rot), 256, 0, st>>>(rot, d_ct, c->plan->d_params, c->logn, 0, L, inv_mod_2n(galois_elt, 2 * n), w_rot);
-    FHE_LAUNCH_CHECK();
-    // (c0(x^g), 0) + KeySwitch(c1(x^g))
-    FHE_TRY(key_switch(c, rot + ln, 2 * ln, d_gk, rot, 2 * ln, nullptr, 0, d_out, B, dig, acc, st));
-    FHE_CUDA(cudaGetLastError());
-    return 0;
+    // workspace per ciphertext: rot [2][L][N] | dig [dnum][W][N] | acc [2][W][N]
+    const size_t per = 2 * ln + ((size_t)c->dnum + 2) * wn;
+    FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * per));
+    const uint32_t ginv = inv_mod_2n(galois_elt, 2 * n);
+    return fork_join_halves(c, batch, (cudaStream_t)stream, [&](uint32_t first, uint32_t cnt, cudaStream_t st) -> int {
+        const size_t w_rot = 2 * (size_t)cnt * ln, w_dig = (size_t)c->dnum * cnt * wn;
+        uint64_t* rot = c->d_ws + (size_t)first * per; uint64_t* dig = rot + w_rot; uint64_t* acc = dig + w_dig;
+        galois_kernel<<<grid_for(c, w_rot), 256, 0, st>>>(rot, d_ct + (size_t)first * 2 * ln, c->plan->d_params, c->logn, 0, L, ginv, w_rot);
+        FHE_LAUNCH_CHECK();
+        // (c0(x^g), 0) + KeySwitch(c1(x^g))
+        FHE_TRY(key_switch(c, rot + ln, 2 * ln, d_gk, rot, 2 * ln, nullptr, 0, d_out + (size_t)first * 2 * ln, cnt, dig, acc, st));
+        FHE_CUDA(cudaGetLastError());
+        return 0;
+    });
 }
 
 extern "C" int fhe_b200_bfv_mod_switch_to_next(fhe_b200_bfv* c, const uint64_t* d_ct, uint64_t* d_out, uint32_t batch, void* stream) {

@@ -234,6 +234,10 @@ def test_plain_ops_and_batch_encoding_vs_oracle(fhe, oracle):
     assert np.array_equal(to_host(g.add_plain(c1, to_device(m2), subtract=True))[0], o.add_plain(h1, m2[0], subtract=True))
     mp = g.multiply_plain(c1, to_device(m2))
     assert np.array_equal(to_host(mp)[0], o.multiply_plain(h1, m2[0]))
+    c3 = torch.cat([c1, c2, c1]); m3 = np.concatenate([m2, m1, m1])                       # batch 3: halves of 2 and 1
+    mp3 = to_host(g.multiply_plain(c3, to_device(m3)))
+    for b, (hh, mm) in enumerate(((h1, m2[0]), (h2, m1[0]), (h1, m1[0]))):
+        assert np.array_equal(mp3[b], o.multiply_plain(hh, mm)), b
     assert np.array_equal(to_host(g.decrypt(mp, sk))[0], oracle.schoolbook_negacyclic(m1[0], m2[0], t))
     # slot encoding: the reference's printed slot-wise expectations (tests/test_fhe.cu:270)
     pa, pb = g.batch_encode([5, 10, 15, 20]), g.batch_encode([3, 6, 9, 12])

@@ -1,8 +1,8 @@
 #!/bin/bash
-# A/B on one box: resident CTAs per SM of the tensor-core base conversion (2 = before, unset = occupancy API)
+# A/B on one box: resident CTAs per SM of the tensor-core base conversion (FHE_B200_LINCOMB_CTAS=1|2 caps them; 0 = occupancy API)
 mkdir -p gpurun_out
-for rep in 1 2; do for c in 2 0; do
-  FHE_B200_LINCOMB_CTAS=$c timeout 300 python bench_hmult.py --batch 8 --steps 5 2>/dev/null > gpurun_out/ab_$c.json
+for b in 8 16; do for c in 0 2 1; do
+  FHE_B200_LINCOMB_CTAS=$c timeout 300 python bench_hmult.py --batch $b --steps 5 2>/dev/null > gpurun_out/ab_$c.json
   python -c "
-import json;d=json.load(open('gpurun_out/ab_$c.json'));print('ctas=$c',round(d['value'],1),round(d['ms_per_op'],4),{k:v['ms'] for k,v in d['kernel_ms_per_call'].items() if isinstance(v,dict)})"
+import json;d=json.load(open('gpurun_out/ab_$c.json'));print('batch $b ctas=$c',round(d['value'],1),round(d['ms_per_op'],4))"
 done; done
