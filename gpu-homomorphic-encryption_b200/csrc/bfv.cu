@@ -41,6 +41,7 @@ struct fhe_b200_bfv {
     // multiply: the batch is split in two halves on two internal streams (the conversions of one half overlap the transforms of the other)
     cudaStream_t mul_stream[2] = {nullptr, nullptr};
     cudaEvent_t mul_fork = nullptr, mul_join[2] = {nullptr, nullptr};
+    cudaEvent_t mul_ev[3] = {nullptr, nullptr, nullptr};            // single-ciphertext multiply: branch synchronisation
 };
 
 namespace fhe_b200 {
@@ -336,6 +337,7 @@ extern "C" int fhe_b200_bfv_destroy(fhe_b200_bfv* c) {
         if (c->mul_join[i]) cudaEventDestroy(c->mul_join[i]);
     }
     if (c->mul_fork) cudaEventDestroy(c->mul_fork);
+    for (int i = 0; i < 3; i++) if (c->mul_ev[i]) cudaEventDestroy(c->mul_ev[i]);
     fhe_b200_plan_destroy(c->plan);
     delete c;
     return 0;
@@ -670,7 +672,8 @@ extern "C" int fhe_b200_bfv_multiply_plain(fhe_b200_bfv* c, const uint64_t* d_ct
 // dig [dnum][B][L+K][N] and acc [2][B][L+K][N] are workspace.  Replaces FHEContext::relinearize / key_switch
 // (/root/reference/src/fhe.cu:226-235, include/fhe.cuh:134-135; a stub there, intent docs/ARCHITECTURE.md:319-326).
 static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const uint64_t* d_key, const uint64_t* add0, size_t add0_stride,
-                      const uint64_t* add1, size_t add1_stride, uint64_t* d_out, uint32_t B, uint64_t* dig, uint64_t* acc, cudaStream_t st) {
+                      const uint64_t* add1, size_t add1_stride, uint64_t* d_out, uint32_t B, uint64_t* dig, uint64_t* acc, cudaStream_t st,
+                      cudaEvent_t addends_ready = nullptr /* waited for before ModDown reads add0 / add1 */) {
     const uint32_t n = c->n, L = c->L, K = c->K, W = L + K, alpha = c->alpha, dnum = c->dnum;
     const LimbParams* prm = c->plan->d_params;
     const size_t N = n, ln = (size_t)L * N, wn = (size_t)W * N;
@@ -693,6 +696,7 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
         count_launch();
     }
     if (!rc) rc = launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st);
+    if (addends_ready && cudaStreamWaitEvent(st, addends_ready, 0) != cudaSuccess && !rc) { set_error("key_switch: stream wait failed"); rc = FHE_B200_ECUDA; }
     for (int p = 0; p < 2 && !rc; p++) {
         const uint64_t* s = acc + (size_t)p * B * wn;
         LcView v; v.in = s; v.in_stride = wn; v.src_idx = c->d_idx_p;
@@ -763,6 +767,72 @@ static int multiply_half(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d
     return 0;
 }
 
+// One ciphertext pair (batch 1): the multiply itself has two independent branches, run on the caller's stream and on one
+// internal stream --
+//   inputs : (a0, a1) extended and transformed on the caller's stream, (b0, b1) on the other, joined before the tensor product;
+//   outputs: (d0, d1) inverse-transformed, scaled and converted on the caller's stream while d2 goes through the same steps and
+//            the key switch up to its ModDown on the other; ModDown adds (d0, d1) and waits for them.
+// so that a conversion of one branch overlaps the transforms of the other also when there is no second ciphertext to pair with.
+static int multiply_one_split(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_rlk, uint64_t* d_out,
+                              uint64_t* d_scaled, uint64_t* ws, cudaStream_t st) {
+    const uint32_t n = c->n, L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, dnum = c->dnum;
+    const LimbParams* prm = c->plan->d_params;
+    const size_t N = n, ln = (size_t)L * N, an = (size_t)A * N, wn = (size_t)W * N, rn = (size_t)R * N;
+    const bool square = d_a == d_b;
+    if (!c->mul_stream[1]) FHE_CUDA(cudaStreamCreateWithFlags(&c->mul_stream[1], cudaStreamNonBlocking));
+    if (!c->mul_fork) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_fork, cudaEventDisableTiming));
+    if (!c->mul_join[1]) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_join[1], cudaEventDisableTiming));
+    for (int i = 0; i < 3; i++) if (!c->mul_ev[i]) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_ev[i], cudaEventDisableTiming));
+    cudaStream_t sx = c->mul_stream[1];
+    uint64_t* ext = ws; uint64_t* d = ext + 4 * an; uint64_t* sR = d + 3 * an; uint64_t* sc = sR + 3 * rn; uint64_t* dig = sc + 3 * ln;
+    uint64_t* acc = dig + (size_t)dnum * wn;
+    int rc = 0;
+    auto extend = [&](int p0, cudaStream_t s) -> int {                 // planes p0, p0 + 1: exact Q -> R (Q limbs written through), forward NTT
+        for (int p = p0; p < p0 + 2; p++) {
+            const uint64_t* src = (p < 2 ? d_a : d_b) + (size_t)(p & 1) * ln;
+            uint64_t* dst = ext + (size_t)p * an;
+            LcView v; v.in = src; v.in_stride = 2 * ln; v.out = dst + ln; v.out_stride = an; v.copy_out = dst; v.copy_stride = an;
+            FHE_TRY(lincomb_launch(c->q2r, v, n, 1, s));
+        }
+        return launch_ntt(c->plan, ext + (size_t)p0 * an, ext + (size_t)p0 * an, 2, 0, A, false, s);
+    };
+    auto descale = [&](uint32_t p0, uint32_t cnt, cudaStream_t s) -> int {      // planes [p0, p0 + cnt) of the tensor: INTT, round(t/Q .), R -> Q
+        uint64_t* dp = d + (size_t)p0 * an;
+        FHE_TRY(launch_ntt(c->plan, dp, dp, cnt, 0, A, true, s));
+        { LcView v; v.in = dp; v.in_stride = an; v.extra = dp + ln; v.extra_stride = an; v.out = sR + (size_t)p0 * rn; v.out_stride = rn;
+          FHE_TRY(lincomb_launch(c->scale, v, n, cnt, s)); }
+        { LcView v; v.in = sR + (size_t)p0 * rn; v.in_stride = rn; v.out = sc + (size_t)p0 * ln; v.out_stride = ln;
+          FHE_TRY(lincomb_launch(c->r2q, v, n, cnt, s)); }
+        if (d_scaled) FHE_CUDA(cudaMemcpyAsync(d_scaled + (size_t)p0 * ln, sc + (size_t)p0 * ln, (size_t)cnt * ln * 8, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    };
+    FHE_CUDA(cudaEventRecord(c->mul_fork, st));
+    FHE_CUDA(cudaStreamWaitEvent(sx, c->mul_fork, 0));
+    // inputs
+    if (!square) { rc = extend(2, sx); cudaEventRecord(c->mul_ev[0], sx); }
+    if (!rc) rc = extend(0, st);
+    if (!square) cudaStreamWaitEvent(st, c->mul_ev[0], 0);
+    if (!rc) {
+        const size_t per = an / 2;
+        if (profile_on()) profile_begin(5, 1, st);
+        tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per, square ? 0 : 2 * per);
+        if (profile_on()) profile_end(st);
+        count_launch();
+    }
+    // outputs
+    cudaEventRecord(c->mul_ev[1], st);
+    cudaStreamWaitEvent(sx, c->mul_ev[1], 0);
+    if (!rc) rc = descale(2, 1, sx);
+    if (!rc) rc = descale(0, 2, st);
+    cudaEventRecord(c->mul_ev[2], st);                                   // (d0, d1) are in sc
+    if (!rc && d_rlk) rc = key_switch(c, sc + 2 * ln, ln, d_rlk, sc, ln, sc + ln, ln, d_out, 1, dig, acc, sx, c->mul_ev[2]);
+    cudaEventRecord(c->mul_join[1], sx);
+    cudaStreamWaitEvent(st, c->mul_join[1], 0);                          // joined even after an error
+    if (rc) return rc;
+    FHE_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // The batch runs as two halves on two internal streams (fork_join_halves): while one half is in a base conversion (tensor pipe,
 // 35% of the IMAD pipe) the other is in its transforms (75% of the IMAD pipe), and the hardware interleaves their CTAs -- +4..10% at
 // config 4 (tools/gpu_ab_streams.sh).  The halves split the same workspace (its size is linear in the batch).
@@ -771,6 +841,8 @@ static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d
     DeviceGuard dev_guard(c->device);
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, multiply_ws_words(c, batch)));
     const size_t ct = 2 * (size_t)c->L * c->n, ct3 = 3 * (size_t)c->L * c->n;
+    static const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;
+    if (batch == 1 && env_streams >= 2) return multiply_one_split(c, d_a, d_b, d_rlk, d_out, d_scaled, c->d_ws, st);
     return fork_join_halves(c, batch, st, [&](uint32_t first, uint32_t cnt, cudaStream_t s) -> int {
         const size_t o = first;
         return multiply_half(c, d_a + o * ct, d_b + o * ct, d_rlk, d_out ? d_out + o * ct : nullptr, d_scaled ? d_scaled + o * ct3 : nullptr,
