@@ -41,3 +41,36 @@ extern "C" int ref_batch_mod_add(const uint64_t* a, const uint64_t* b, uint64_t 
 extern "C" int ref_batch_mod_sub(const uint64_t* a, const uint64_t* b, uint64_t q, uint64_t* out, uint32_t n, uint64_t* hi) { return run(1, a, b, q, out, n, hi); }
 // reference Montgomery product: a * b * 2^-256 mod q (the reference never converts into the Montgomery domain)
 extern "C" int ref_batch_mod_mul_montgomery(const uint64_t* a, const uint64_t* b, uint64_t q, uint64_t* out, uint32_t n, uint64_t* hi) { return run(2, a, b, q, out, n, hi); }
+
+// Timing of the same kernels on device-resident operands (CUDA events, `reps` launches after one warm-up): the "reference CUDA
+// build on the same box" data point of SURVEY 8d for what can legally launch.  Operands are pseudo-random 60-bit values below q.
+extern "C" int ref_time_batch_kernel(int op, uint64_t q, uint32_t count, int reps, float* ms_per_launch) {
+    using fhe::uint256_t;
+    std::vector<uint256_t> a(count), b(count);
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    for (uint32_t i = 0; i < count; i++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17; a[i] = uint256_t(x % q);
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17; b[i] = uint256_t(x % q);
+    }
+    uint256_t *d_a = nullptr, *d_b = nullptr, *d_r = nullptr;
+    const size_t bytes = (size_t)count * sizeof(uint256_t);
+    if (cudaMalloc(&d_a, bytes) != cudaSuccess || cudaMalloc(&d_b, bytes) != cudaSuccess || cudaMalloc(&d_r, bytes) != cudaSuccess) return -1;
+    cudaMemcpy(d_a, a.data(), bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_b, b.data(), bytes, cudaMemcpyHostToDevice);
+    const uint256_t mod(q), inv = fhe::compute_montgomery_inverse(mod);
+    const uint32_t threads = 256, blocks = (count + threads - 1) / threads;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int r = -1; r < reps; r++) {
+        if (r == 0) cudaEventRecord(e0);
+        if (op == 0) fhe::batch_mod_add_kernel<<<blocks, threads>>>(d_r, d_a, d_b, mod, count);
+        else if (op == 1) fhe::batch_mod_sub_kernel<<<blocks, threads>>>(d_r, d_a, d_b, mod, count);
+        else fhe::batch_mod_mul_kernel<<<blocks, threads>>>(d_r, d_a, d_b, mod, inv, count);
+    }
+    cudaEventRecord(e1);
+    const cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_a); cudaFree(d_b); cudaFree(d_r);
+    if (e != cudaSuccess) return -2;
+    *ms_per_launch = ms / reps;
+    return 0;
+}
