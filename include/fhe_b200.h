@@ -10,7 +10,11 @@
  *   - every function returns 0 on success, a negative FHE_B200_E* code on failure; fhe_b200_last_error() gives
  *     the message for the calling thread.  Nothing throws, no C++ type crosses the boundary.
  *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are host pointers.
- *   - `stream` is a cudaStream_t passed as void*; all device work is asynchronous on that stream.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is asynchronous and ordered on that stream.  BFV calls on
+ *     two or more ciphertexts (and a single multiply) fork part of their work onto streams owned by the context and join it
+ *     back before the call's work completes on `stream`, so callers need no extra synchronisation (FHE_B200_HMULT_STREAMS=1
+ *     keeps everything on `stream`).  A BFV context owns one workspace: its calls must be stream-ordered, not concurrent.
+ *   - objects run on the device they were created for; a call switches to it and restores the caller's current device.
  *   - polynomial layout is limb-major uint64_t [batch][limb_count][N]; limb l of every polynomial is reduced
  *     modulo plan.moduli[limb_begin + l]; values are canonical residues in [0, q) at every call boundary.
  *   - NTT-domain order: forward leaves X[k] = sum_j a_j psi^(j(2k+1)) at position bitrev(k); inverse consumes
