@@ -29,6 +29,11 @@ uint64_t fnv1a(const void* p, size_t n, uint64_t h = 0xcbf29ce484222325ull) {
     for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ull; }
     return h;
 }
+// sanity limits of the header fields (the engine's own: N <= 2^17, at most 4096 limbs): they also keep n * limbs * polys far from
+// overflowing 64 bits, so a forged header cannot make the length check pass with a wrapped product
+bool dims_ok(uint32_t n, uint32_t limbs, uint32_t polys) {
+    return n >= 1 && n <= (1u << 17) && limbs >= 1 && limbs <= 4096 && polys >= 1 && polys <= (1u << 24);
+}
 void put32(uint8_t* p, uint32_t v) { for (int i = 0; i < 4; i++) p[i] = (uint8_t)(v >> (8 * i)); }
 void put64(uint8_t* p, uint64_t v) { for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (8 * i)); }
 uint32_t get32(const uint8_t* p) { uint32_t v = 0; for (int i = 0; i < 4; i++) v |= (uint32_t)p[i] << (8 * i); return v; }
@@ -39,7 +44,7 @@ extern "C" size_t fhe_b200_wire_size(uint32_t n, uint32_t limbs, uint32_t polys)
 
 extern "C" int fhe_b200_wire_pack(uint32_t kind, uint32_t n, uint32_t limbs, uint32_t polys, int ntt_form, uint32_t galois_elt,
                                   const uint64_t* h_moduli, const uint64_t* h_words, uint8_t* h_out) {
-    if (!h_moduli || !h_words || !h_out || kind < 1 || kind > 5 || !n || !limbs || !polys) {
+    if (!h_moduli || !h_words || !h_out || kind < 1 || kind > 5 || !dims_ok(n, limbs, polys)) {
         set_error("wire_pack: bad argument"); return FHE_B200_EINVAL;
     }
     const uint64_t words = (uint64_t)n * limbs * polys;
@@ -63,7 +68,7 @@ extern "C" int fhe_b200_wire_unpack(const uint8_t* h_in, size_t len, const uint6
     if (get32(h_in + 8) != 1) { set_error("wire_unpack: unsupported version %u", get32(h_in + 8)); return FHE_B200_EINVAL; }
     const uint32_t k = get32(h_in + 12), nn = get32(h_in + 16), ll = get32(h_in + 20), pp = get32(h_in + 24);
     const uint64_t words = get64(h_in + 48);
-    if (k < 1 || k > 5 || !nn || !ll || !pp || words != (uint64_t)nn * ll * pp) { set_error("wire_unpack: inconsistent header"); return FHE_B200_EINVAL; }
+    if (k < 1 || k > 5 || !dims_ok(nn, ll, pp) || words != (uint64_t)nn * ll * pp) { set_error("wire_unpack: inconsistent header"); return FHE_B200_EINVAL; }
     if (len != 64 + words * 8) { set_error("wire_unpack: %zu bytes given, header says %llu", len, (unsigned long long)(64 + words * 8)); return FHE_B200_EINVAL; }
     if (h_moduli) {
         uint8_t mb[8]; uint64_t mh = 0xcbf29ce484222325ull;

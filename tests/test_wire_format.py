@@ -39,7 +39,7 @@ def test_ciphertext_batch_shape():
     assert np.array_equal(got.reshape(3, 2, 3, 64), w.reshape(3, 2, 3, 64))
 
 
-@pytest.mark.parametrize("damage", ["magic", "version", "short", "long", "payload", "header", "chain"])
+@pytest.mark.parametrize("damage", ["magic", "version", "short", "long", "payload", "header", "chain", "wrap"])
 def test_rejects_damaged_objects(damage):
     chain, w = _sample()
     blob = bytearray(fhe_b200.wire_pack("public_key", w, chain))
@@ -56,6 +56,9 @@ def test_rejects_damaged_objects(damage):
         blob[64 + 100] ^= 0x40
     elif damage == "header":
         struct.pack_into("<I", blob, 20, 4)            # limbs no longer matches payload_words
+    elif damage == "wrap":                             # n * limbs * polys wraps to the stored word count modulo 2^64
+        struct.pack_into("<3I", blob, 16, 1 << 31, 1 << 31, 4 * 64 * 3 * 4)
+        struct.pack_into("<Q", blob, 48, ((1 << 31) * (1 << 31) * (4 * 64 * 3 * 4)) % (1 << 64))
     elif damage == "chain":
         use_chain = oracle.prime_chain(4)[1:]
     with pytest.raises(fhe_b200.FheB200Error):
