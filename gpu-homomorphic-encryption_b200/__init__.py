@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
         "fhe_b200_bfv_galoiskeygen": [_vp, C.c_uint64, C.c_uint32, _vp, _vp, _vp],
         "fhe_b200_bfv_apply_galois": [_vp, _vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_bfv_mod_switch_to_next": [_vp, _vp, _vp, C.c_uint32, _vp],
+        "fhe_b200_bfv_mod_switch_to_level": [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_tensor": [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_ks_inner": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_multiply_relin_host": [_vp, _vp, _vp, _vp, _vp, C.c_uint32],

@@ -946,6 +946,27 @@ extern "C" int fhe_b200_bfv_mod_switch_to_next(fhe_b200_bfv* c, const uint64_t* 
     return fhe_b200_modswitch_drop_last(c->plan, d_out, d_ct, 2 * batch, 0, c->L, stream);
 }
 
+// mod_switch_to_level (/root/reference/include/fhe.cuh:110, declared only): the last `drop` limbs of Q go one at a time, each step
+// rounding (x - [x]_{q_last}) / q_last exactly like mod_switch_to_next; the result [batch][2][L-drop][N] belongs to the context built
+// on the first L - drop limbs.  Intermediate levels ping-pong through the context workspace.
+extern "C" int fhe_b200_bfv_mod_switch_to_level(fhe_b200_bfv* c, const uint64_t* d_ct, uint64_t* d_out, uint32_t batch, uint32_t drop,
+                                                void* stream) {
+    FHE_REQUIRE(c && d_ct && d_out, "bfv_mod_switch_to_level: null argument");
+    FHE_REQUIRE(drop < c->L, "bfv_mod_switch_to_level: cannot drop %u of %u limbs", drop, c->L);
+    if (!batch) return 0;
+    DeviceGuard dev_guard(c->device);
+    const size_t pn = (size_t)2 * batch * c->n;                       // words per limb over all components
+    if (drop == 0) { FHE_CUDA(cudaMemcpyAsync(d_out, d_ct, pn * c->L * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0; }
+    if (drop > 1) FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, 2 * pn * (c->L - 1)));
+    const uint64_t* cur = d_ct;
+    for (uint32_t k = 0; k < drop; k++) {
+        uint64_t* dst = (k + 1 == drop) ? d_out : c->d_ws + (size_t)(k & 1) * pn * (c->L - 1);
+        FHE_TRY(fhe_b200_modswitch_drop_last(c->plan, dst, cur, 2 * batch, 0, c->L - k, stream));
+        cur = dst;
+    }
+    return 0;
+}
+
 // Host-buffer entry point.  Chunks of ciphertext pairs rotate over three streams, each with its own device staging buffers:
 // the upload of chunk k+1 and the download of chunk k-1 overlap the multiply of chunk k (PCIe is full duplex; with two
 // streams the upload of chunk k+2 queued behind the download of chunk k).  The multiplies themselves are serialised through an event because they share the context workspace.

@@ -450,6 +450,13 @@ class BfvContext:
         check(self.lib.fhe_b200_bfv_mod_switch_to_next(self.h, _ptr(ct), _ptr(out), b, _stream()))
         return out
 
+    def mod_switch_to_level(self, ct, drop):
+        """drop the last `drop` limbs of Q (FHEContext::mod_switch_to_level, include/fhe.cuh:110); result [B][2][L-drop][N]"""
+        b = ct.numel() // (2 * self.L * self.n)
+        out = self._empty(b, 2, self.L - drop, self.n)
+        check(self.lib.fhe_b200_bfv_mod_switch_to_level(self.h, _ptr(ct), _ptr(out), b, drop, _stream()))
+        return out
+
     # SIMD slot encoding (fhe::BatchEncoder, include/fhe.cuh:151-166): slot i is the value of the plaintext polynomial at
     # the evaluation point the engine's NTT puts at position i; needs t = 1 (mod 2N)
     def _slot_plan(self):

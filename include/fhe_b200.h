@@ -223,6 +223,10 @@ int fhe_b200_bfv_apply_galois(fhe_b200_bfv* ctx, const uint64_t* d_ct, uint32_t 
 /* FHEContext::mod_switch_to_next (include/fhe.cuh:109; declared only): both components lose the last limb of Q with rounding,
  * [batch][2][L][N] -> [batch][2][L-1][N]; the result decrypts under a context built on the first L-1 limbs. */
 int fhe_b200_bfv_mod_switch_to_next(fhe_b200_bfv* ctx, const uint64_t* d_ct, uint64_t* d_out, uint32_t batch, void* stream);
+/* FHEContext::mod_switch_to_level (include/fhe.cuh:110, declared only): `drop` limbs are removed one at a time (each step as
+ * mod_switch_to_next); d_out is [batch][2][L-drop][N] and belongs to the context on the first L-drop limbs.  drop = 0 copies. */
+int fhe_b200_bfv_mod_switch_to_level(fhe_b200_bfv* ctx, const uint64_t* d_ct, uint64_t* d_out, uint32_t batch, uint32_t drop,
+                                     void* stream);
 /* host-buffer variant of multiply_relin (copies in, computes, copies out; synchronous) */
 int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* ctx, const uint64_t* h_a, const uint64_t* h_b,
                                      const uint64_t* d_rlk, uint64_t* h_out, uint32_t batch);

@@ -449,6 +449,11 @@ class Bfv:
         lib().orc_bfv_mod_switch_to_next(C.c_void_p(self.h), _p(_u64(ct).reshape(-1)), _p(out.reshape(-1)))
         return out
 
+    def mod_switch_to_level(self, ct, drop):
+        out = np.zeros((2, self.L - drop, self.n), np.uint64)
+        lib().orc_bfv_mod_switch_to_level(C.c_void_p(self.h), _p(_u64(ct).reshape(-1)), C.c_uint32(drop), _p(out.reshape(-1)))
+        return out
+
     def multiply(self, a, b):
         """3-component product [3][L][n] (no relinearisation)."""
         out = np.zeros((3, self.L, self.n), np.uint64)

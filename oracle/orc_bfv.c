@@ -449,6 +449,19 @@ void orc_bfv_apply_galois(const orc_bfv *c, const u64 *ct, u32 g, const u64 *gk,
 /* mod_switch_to_next (include/fhe.cuh:109): both components lose the last limb of Q with rounding; the result is a ciphertext
  * of the same plaintext for the context built on the first L-1 limbs.  ct: [2][L][n] -> out: [2][L-1][n] */
 void orc_modswitch_drop_last(u64 *out, const u64 *in, u32 n, const u64 *moduli, u32 limbs);
+/* mod_switch_to_level (include/fhe.cuh:110, declared only): drop the last `drop` limbs of Q one at a time, rounding at every step;
+ * out: [2][L-drop][n].  drop = 0 copies. */
+void orc_bfv_mod_switch_to_level(const orc_bfv *c, const u64 *ct, u32 drop, u64 *out) {
+    u32 n = c->n, L = c->L;
+    u64 *cur = (u64 *)malloc((size_t)L * n * sizeof(u64)), *nxt = (u64 *)malloc((size_t)L * n * sizeof(u64));
+    for (int p = 0; p < 2; p++) {
+        memcpy(cur, ct + (size_t)p * L * n, (size_t)L * n * sizeof(u64));
+        for (u32 k = 0; k < drop; k++) { orc_modswitch_drop_last(nxt, cur, n, c->primes, L - k); u64 *t = cur; cur = nxt; nxt = t; }
+        memcpy(out + (size_t)p * (L - drop) * n, cur, (size_t)(L - drop) * n * sizeof(u64));
+    }
+    free(cur); free(nxt);
+}
+
 void orc_bfv_mod_switch_to_next(const orc_bfv *c, const u64 *ct, u64 *out) {
     u32 n = c->n, L = c->L;
     for (int p = 0; p < 2; p++) orc_modswitch_drop_last(out + (size_t)p * (L - 1) * n, ct + (size_t)p * L * n, n, c->primes, L);

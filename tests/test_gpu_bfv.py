@@ -423,3 +423,21 @@ def test_noise_budget_matches_exact_big_integer_value(fhe, oracle):
     assert np.allclose(got, want, rtol=0, atol=1e-6), (got, want)
     assert want[2] < min(want[0], want[1]) - 10 and want[2] > 0          # a product costs budget but leaves some
     assert got[3] == pytest.approx(math.log2(Q) - 1, abs=1e-9)
+
+
+@pytest.mark.gpu
+def test_mod_switch_to_level_vs_oracle(fhe, oracle):
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, "small")
+    n, t, L = p["n"], p["t"], p["L"]
+    sk, pk = g.keygen(81, 82)
+    m = np.random.default_rng(83).integers(0, t, (3, n), dtype=np.uint64)
+    ct = g.encrypt(84, to_device(m), pk)
+    h = to_host(ct)
+    for drop in (0, 1, 2, 3):
+        low = to_host(g.mod_switch_to_level(ct, drop))
+        assert low.shape == (3, 2, L - drop, n)
+        for b in range(3):
+            assert np.array_equal(low[b], o.mod_switch_to_level(h[b], drop)), (drop, b)
+    with pytest.raises(fhe.FheB200Error):
+        g.mod_switch_to_level(ct, L)

@@ -321,3 +321,30 @@ def test_multiply_then_relinearize_is_the_fused_multiply(oracle):
     lazy = o.relinearize((p01 + p23) % mods, rlk)
     want = (oracle.schoolbook_negacyclic(m[0], m[1], t) + oracle.schoolbook_negacyclic(m[2], m[3], t)) % np.uint64(t)
     assert np.array_equal(o.decrypt(lazy, sk), want)
+
+
+def test_mod_switch_to_level_is_repeated_drop_and_still_decrypts(oracle):
+    """orc_bfv_mod_switch_to_level(drop) == drop applications of the one-limb switch (each on the shorter chain), and the result
+    decrypts under the context built on the remaining limbs."""
+    from fhe_b200.params import bfv_preset
+    p = bfv_preset("small")
+    n, t, L = p["n"], p["t"], p["L"]
+    o = oracle.Bfv(n, L, p["R"], p["K"], p["dnum"], t, p["primes"], sigma=p["sigma"], hw=p["hamming_weight"])
+    _, sk = o.secret_keygen(5); pk = o.public_keygen(6, sk)
+    m = np.random.default_rng(9).integers(0, t, n, dtype=np.uint64)
+    ct = o.encrypt(7, m, pk)
+    assert np.array_equal(o.mod_switch_to_level(ct, 0), ct)
+    assert np.array_equal(o.mod_switch_to_level(ct, 1), o.mod_switch_to_next(ct))
+    for drop in (2, 3):
+        low = o.mod_switch_to_level(ct, drop)
+        assert low.shape == (2, L - drop, n)
+        step = ct
+        for k in range(drop):                      # one limb at a time through contexts of decreasing length
+            primes_k = list(p["primes"][:L - k]) + list(p["primes"][L:])
+            ok = oracle.Bfv(n, L - k, p["R"], p["K"], 1, t, primes_k, sigma=p["sigma"], hw=p["hamming_weight"])
+            step = ok.mod_switch_to_next(step)
+        assert np.array_equal(low, step)
+        primes = list(p["primes"][:L - drop]) + list(p["primes"][L:])
+        lo = oracle.Bfv(n, L - drop, p["R"], p["K"], 1, t, primes, sigma=p["sigma"], hw=p["hamming_weight"])
+        _, lsk = lo.secret_keygen(5)
+        assert np.array_equal(lo.decrypt(low, lsk), m)
