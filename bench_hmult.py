@@ -188,11 +188,93 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
             "rotate": {"value": B / (rot_ms / 1e3), "unit": "ops/s", "ms_per_op": rot_ms / B}}
 
 
+def run_hmult_limb_sharded(local_rank=0, preset="c4", batch=1, steps=20, dist=None, ctx=None, keys=None):
+    """ONE batch of ciphertext pairs multiplied by ALL ranks together (BASELINE.json config 4: limbs sharded over the GPUs):
+    fhe_b200_bfv_multiply_relin_sharded, NTT-domain work limb-sharded, base conversions coefficient-sharded, the four
+    transpositions per multiply stored by the producing kernels straight into the peers' buffers over NVLink (csrc/shard.cu).
+    Timed with CUDA events on every rank between barriers, max over ranks; every rank checks its coefficient block against the
+    plain single-GPU multiply of the same inputs, word for word."""
+    import numpy as np
+    import torch
+    import fhe_b200
+    from fhe_b200.engine import to_device
+    from fhe_b200.params import bfv_preset
+
+    torch.cuda.set_device(local_rank)
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    p = bfv_preset(preset)
+    n, L, t = p["n"], p["L"], p["t"]
+    g = ctx or fhe_b200.BfvContext(n, L, p["R"], p["K"], p["dnum"], t, p["primes"], p["sigma"], p["hamming_weight"], device=local_rank)
+    if keys is None:
+        sk, pk = g.keygen(1, 2)
+        rlk = g.relinkey_gen(3, sk)
+    else:
+        sk, pk, rlk = keys
+    rng = np.random.default_rng(5)
+    B = batch
+    m1 = rng.integers(0, t, (B, n), dtype=np.uint64); m2 = rng.integers(0, t, (B, n), dtype=np.uint64)
+    dev = f"cuda:{local_rank}"
+    ca = g.encrypt(10, to_device(m1, dev), pk); cb = g.encrypt(100, to_device(m2, dev), pk)
+    want = g.multiply(ca, cb, rlk)
+    # single-GPU rate of the same batch on this box (the denominator of the speed-up)
+    for _ in range(2):
+        g.multiply(ca, cb, rlk, out=want)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g.multiply(ca, cb, rlk, out=want)
+    e1.record(); torch.cuda.synchronize()
+    single_ms = e0.elapsed_time(e1) / steps
+    sh = fhe_b200.BfvShard(g, rank, world, max_batch=B)
+    sh.connect() if dist is not None else sh.connect([sh.handle()])
+    ks = sh.slice_key(rlk)
+    sa, sb = sh.shard_ct(ca), sh.shard_ct(cb)
+    out = torch.empty_like(sa)
+    lib = fhe_b200.load_library()
+    for _ in range(3):
+        sh.multiply(sa, sb, ks, out=out)
+    sh.check()
+    if dist is not None:
+        dist.barrier(); torch.cuda.synchronize()
+    l0 = lib.fhe_b200_launch_count()
+    e0.record()
+    for _ in range(steps):
+        sh.multiply(sa, sb, ks, out=out)
+    e1.record()
+    sh.check()
+    ms = e0.elapsed_time(e1)
+    launches = lib.fhe_b200_launch_count() - l0
+    ok = bool(torch.equal(out, sh.shard_ct(want)))
+    stat = torch.tensor([ms, 0.0 if ok else 1.0, float(sh.nvlink_bytes_per_op)], dtype=torch.float64, device=dev)
+    tot = stat.clone()
+    if dist is not None:
+        dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(stat[0])
+    per_op_s = ms / 1e3 / steps / B
+    nv_rank = float(stat[2]) * 1.0                     # bytes the busiest rank stores into its peers per ciphertext pair
+    res = {"metric": "BFV HMult+relinearize ops/s", "value": B * steps / (ms / 1e3), "unit": "ops/s", "n_gpus": world, "batch": B,
+           "steps": steps, "scaling": "strong", "parallelism": f"limb-sharded x{world} (one batch of {B} ciphertext pair(s) on all GPUs)",
+           "ms_per_op": ms / (B * steps), "single_gpu_same_batch_ops_s": B / (single_ms / 1e3),
+           "speedup_vs_single_gpu_same_batch": (single_ms / B) / (ms / (B * steps)),
+           "matches_single_gpu_bit_exact": float(stat[1]) == 0.0, "gpu_launches_per_op_per_rank": launches / steps,
+           "config": {"workload": f"config4: N={n}, L={L}, R={p['R']}, dnum={p['dnum']}, K={p['K']}, t={t}"},
+           "nvlink": {"bytes_per_op_all_ranks": float(tot[2]), "bytes_per_op_busiest_rank": nv_rank,
+                      "achieved_GBs_per_rank_out": nv_rank / per_op_s / 1e9, "peak_GBs_per_direction": 900.0,
+                      "frac": nv_rank / per_op_s / 1e9 / 900.0,
+                      "note": "stores of the producing kernels into peer buffers (no separate transfer step, no NCCL on the data path); "
+                              "an all-gather of the source limbs would move world x these bytes"}}
+    sh.close()
+    return res
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--preset", default="c4")
+    ap.add_argument("--limb-sharded", action="store_true")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:        # torchrun: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 bench_hmult.py
@@ -202,10 +284,11 @@ if __name__ == "__main__":
         torch.cuda.set_device(lr)
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-        res = run_hmult(a, lr, a.preset, a.batch, a.steps, dist=dist)
+        res = (run_hmult_limb_sharded(lr, a.preset, a.batch, a.steps, dist=dist) if a.limb_sharded
+               else run_hmult(a, lr, a.preset, a.batch, a.steps, dist=dist))
         if dist.get_rank() == 0:
             print(json.dumps(res), flush=True)
         dist.barrier()
         dist.destroy_process_group()
     else:
-        print(json.dumps(run_hmult(a, 0, a.preset, a.batch, a.steps)))
+        print(json.dumps(run_hmult_limb_sharded(0, a.preset, a.batch, a.steps) if a.limb_sharded else run_hmult(a, 0, a.preset, a.batch, a.steps)))

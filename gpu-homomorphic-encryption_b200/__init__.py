@@ -93,6 +93,15 @@ def load_library() -> C.CDLL:
         "fhe_b200_bfv_tensor": [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_ks_inner": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_multiply_relin_host": [_vp, _vp, _vp, _vp, _vp, C.c_uint32],
+        "fhe_b200_shard_create": [_vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(_vp)],
+        "fhe_b200_shard_destroy": [_vp],
+        "fhe_b200_shard_handle": [_vp, _vp],
+        "fhe_b200_shard_connect": [_vp, _vp],
+        "fhe_b200_shard_partition": [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+        "fhe_b200_shard_info": [_vp] + [C.POINTER(C.c_uint32)] * 6 + [u64p],
+        "fhe_b200_shard_slice_key": [_vp, _vp, _vp, _vp],
+        "fhe_b200_bfv_multiply_relin_sharded": [_vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp],
+        "fhe_b200_shard_check": [_vp, _vp],
         "fhe_b200_bfv_info": [_vp] + [C.POINTER(C.c_uint32)] * 5 + [u64p],
         "fhe_b200_bfv_plan": [_vp],
         "fhe_b200_gaussian_cdt": [C.c_double, u64p, C.c_uint32],
@@ -121,8 +130,8 @@ def check(rc: int) -> None:
         raise FheB200Error(f"libfhe_b200 error {rc}: {msg.decode() if msg else ''}")
 
 
-from .engine import (BfvContext, LinComb, NTTEngine, Plan, PolynomialOps, RNSContext, RNS_NTTEngine,  # noqa: E402
+from .engine import (BfvContext, BfvShard, LinComb, NTTEngine, Plan, PolynomialOps, RNSContext, RNS_NTTEngine,  # noqa: E402
                      gaussian_cdt, pinned_empty, wire_pack, wire_unpack, WIRE_KINDS)
 
 __all__ = ["load_library", "check", "FheB200Error", "Plan", "NTTEngine", "RNS_NTTEngine", "PolynomialOps",
-           "RNSContext", "LinComb", "BfvContext", "gaussian_cdt", "pinned_empty", "wire_pack", "wire_unpack", "WIRE_KINDS", "LIB_PATH", "HEADER_PATH"]
+           "RNSContext", "LinComb", "BfvContext", "BfvShard", "gaussian_cdt", "pinned_empty", "wire_pack", "wire_unpack", "WIRE_KINDS", "LIB_PATH", "HEADER_PATH"]

@@ -94,8 +94,20 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
 enum EwOp { EW_ADD = 0, EW_SUB, EW_MUL, EW_MAC, EW_MUL_SCALAR, EW_ADD_SCALAR, EW_NEG };
 int launch_elementwise(fhe_b200_plan* plan, EwOp op, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b,
                        const uint64_t* d_c, uint32_t batch, uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
+// Scatter form of the last inverse pass (limb-sharded execution): the coefficients of a limb are cut into 2^k blocks of `nc`
+// consecutive coefficients; block h of local limb l of polynomial p is written to
+//   base[h] + ((p * limbs_total + limb_off + l) * nc + (coefficient - h * nc)) * 8      (absolute addresses, possibly peer memory)
+struct BalScatter {
+    uint64_t base[16];
+    uint32_t log_blocks;            // log2 of the number of coefficient blocks (<= 4)
+    uint32_t limbs_total, limb_off, nc;
+};
 int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
-                   uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st);
+                   uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st,
+                   const BalScatter* scatter = nullptr);
+// inverse transform of [batch][limb_count][N] whose tile pass runs in place on d_buf and whose column pass scatters the result
+int launch_ntt_inverse_scatter(fhe_b200_plan* plan, uint64_t* d_buf, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,
+                               const BalScatter& scatter, cudaStream_t st);
 int launch_negacyclic_mul_fused(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, uint32_t batch,
                                 uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
 int check_range(const fhe_b200_plan* plan, uint32_t batch, uint32_t limb_begin, uint32_t limb_count);

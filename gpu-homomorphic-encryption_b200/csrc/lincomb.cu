@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
         u64 x = 0;
         if (i < a.S) {
             x = inb[(size_t)a.v.src_idx[i] * nn];
-            if (a.v.copy_out) a.v.copy_out[(size_t)b * a.v.copy_stride + (size_t)a.v.copy_idx[i] * nn + j] = x;
+            if (a.v.copy_out) {
+                if (a.v.copy_tab) reinterpret_cast<u64*>(a.v.copy_tab[2 * i])[(a.v.copy_poly0 + b) * a.v.copy_tab[2 * i + 1] + j] = x;
+                else a.v.copy_out[(size_t)b * a.v.copy_stride + (size_t)a.v.copy_idx[i] * nn + j] = x;
+            }
             if (a.use_pre) x = shoup_mul(x, sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
         }
         u64 ph, pl;
@@ -141,7 +144,8 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
                 r = barrett128(ph, pl, m, mh, ml);
                 if (a.v.add) r = add_mod(r, a.v.add[(size_t)b * a.v.add_stride + eo], m);
             }
-            a.v.out[(size_t)b * a.v.out_stride + (size_t)a.v.dst_idx[k] * nn + j] = r;
+            if (a.v.out_tab) reinterpret_cast<u64*>(a.v.out_tab[2 * k])[(a.v.out_poly0 + b) * a.v.out_tab[2 * k + 1] + j] = r;
+            else a.v.out[(size_t)b * a.v.out_stride + (size_t)a.v.dst_idx[k] * nn + j] = r;
         }
     }
 }
@@ -180,7 +184,7 @@ static int launch_tpc(uint32_t spt, const LcKernelArgs& a, dim3 grid, size_t sme
 }
 
 int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_t batch, cudaStream_t st) {
-    FHE_REQUIRE(lc && view.in && view.out, "lincomb: null argument");
+    FHE_REQUIRE(lc && view.in && (view.out || view.out_tab), "lincomb: null argument");
     FHE_REQUIRE(n >= 32 && (n & (n - 1)) == 0, "lincomb: n_coeffs must be a power of two >= 32");
     FHE_REQUIRE(!lc->use_extra || view.extra, "lincomb: this object needs the extra limbs (scale-and-round)");
     if (!batch) return 0;

@@ -43,6 +43,12 @@ struct LcView {
     // pass-through: the raw source limbs are also written to copy_out (limb copy_idx[i] of polynomial b at copy_out + b*copy_stride);
     // saves the separate device-to-device copy when the sources are part of the output polynomial (Q limbs next to the R limbs)
     uint64_t* copy_out = nullptr; size_t copy_stride = 0; const uint32_t* copy_idx = nullptr;
+    // scattered destinations (limb-sharded execution, shard.cu): when out_tab is set, target k of polynomial b is written to the
+    // ABSOLUTE address out_tab[2k] + ((out_poly0 + b) * out_tab[2k+1] + j) * 8 -- every target limb may live in a different
+    // buffer, e.g. the peer GPU that owns that limb (stores over NVLink).  copy_tab does the same for the pass-through limbs
+    // ([S] pairs; copy_out must still be non-null to enable the pass-through).  Device arrays of {address, words per polynomial}.
+    const uint64_t* out_tab = nullptr; size_t out_poly0 = 0;
+    const uint64_t* copy_tab = nullptr; size_t copy_poly0 = 0;
 };
 
 int lincomb_create(const LincombConsts& consts, int device, fhe_b200_lincomb** out);

@@ -72,21 +72,26 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
     constexpr int SP = 4 * KT;
     u64* sSrc = reinterpret_cast<u64*>(lc_smem + (size_t)a.NG * KT * 8 * 32 * sizeof(uint2));
     u64* sOff = sSrc + 5 * SP;                          // element offset of source limb i inside a polynomial
-    u64* sCpy = sOff + SP;                              // element offset of source limb i in the pass-through output
-    u64* sDst = sCpy + SP;                              // [6][T]: modulus, mu_hi, mu_lo, c, lam, epilogue scalar
-    u64* sIdx = sDst + 6 * (size_t)a.T;                 // [3][T]: element offsets of the target limb in out / extra / epilogue operands
+    u64* sCpy = sOff + SP;                              // [2][SP]: address of source limb i in the pass-through output (polynomial 0), words per polynomial
+    u64* sDst = sCpy + 2 * SP;                          // [6][T]: modulus, mu_hi, mu_lo, c, lam, epilogue scalar
+    u64* sIdx = sDst + 6 * (size_t)a.T;                 // [4][T]: address of the target limb in out (polynomial 0), element offsets in extra / epilogue operands, words per polynomial of out
     const size_t nn = (size_t)1 << a.logn;
     for (uint32_t i = threadIdx.x; i < (uint32_t)SP; i += blockDim.x) {
         const bool in = i < a.S;
         sSrc[i] = in ? a.src_mod[i] : 3; sSrc[SP + i] = in ? a.pre[i] : 0; sSrc[2 * SP + i] = in ? a.pre_s[i] : 0;
         sSrc[3 * SP + i] = in ? a.th_hi[i] : 0; sSrc[4 * SP + i] = in ? a.th_lo[i] : 0;
         sOff[i] = in ? (u64)a.v.src_idx[i] * nn : 0;
-        sCpy[i] = (in && a.v.copy_out) ? (u64)a.v.copy_idx[i] * nn : 0;
+        if (in && a.v.copy_out) {
+            if (a.v.copy_tab) { sCpy[SP + i] = a.v.copy_tab[2 * i + 1]; sCpy[i] = a.v.copy_tab[2 * i] + a.v.copy_poly0 * sCpy[SP + i] * 8; }
+            else { sCpy[SP + i] = a.v.copy_stride; sCpy[i] = (u64)(a.v.copy_out + (size_t)a.v.copy_idx[i] * nn); }
+        } else { sCpy[i] = 0; sCpy[SP + i] = 0; }
     }
     for (uint32_t k = threadIdx.x; k < a.T; k += blockDim.x) {
         sDst[k] = a.dst_mod[k]; sDst[a.T + k] = a.mu_hi[k]; sDst[2 * a.T + k] = a.mu_lo[k]; sDst[3 * a.T + k] = a.c[k];
         sDst[4 * a.T + k] = a.lam[k]; sDst[5 * a.T + k] = a.v.epi_scalar ? a.v.epi_scalar[k] : 0;
-        sIdx[k] = (u64)a.v.dst_idx[k] * nn; sIdx[a.T + k] = (u64)a.v.extra_idx[k] * nn; sIdx[2 * a.T + k] = (u64)a.v.epi_idx[k] * nn;
+        if (a.v.out_tab) { sIdx[3 * a.T + k] = a.v.out_tab[2 * k + 1]; sIdx[k] = a.v.out_tab[2 * k] + a.v.out_poly0 * sIdx[3 * a.T + k] * 8; }
+        else { sIdx[3 * a.T + k] = a.v.out_stride; sIdx[k] = (u64)(a.v.out + (size_t)a.v.dst_idx[k] * nn); }
+        sIdx[a.T + k] = (u64)a.v.extra_idx[k] * nn; sIdx[2 * a.T + k] = (u64)a.v.epi_idx[k] * nn;
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
         const uint32_t i = 4 * kt + q;
         if (i >= a.S) { x[kt][0] = 0; x[kt][1] = 0; }
         else if (a.v.copy_out) {
-            u64* o = a.v.copy_out + (size_t)b * a.v.copy_stride + sCpy[i] + j0;
+            u64* o = reinterpret_cast<u64*>(sCpy[i]) + (size_t)b * sCpy[SP + i] + j0;
             o[0] = x[kt][0]; o[8] = x[kt][1];
         }
         if (a.use_pre) {
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(512) lincomb_mma_kernel(const LcMmaArgs a) {
                 res = barrett128(ph, pl, m, mh, ml);
                 if (a.v.add) res = add_mod(res, ad[r], m);
             }
-            a.v.out[(size_t)b * a.v.out_stride + sIdx[k] + j] = res;
+            reinterpret_cast<u64*>(sIdx[k])[(size_t)b * sIdx[3 * a.T + k] + j] = res;
         }
     }
     __syncwarp();
@@ -235,7 +240,7 @@ void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<ui
 
 template <int KT>
 static int launch_kt(const LcMmaArgs& a, int sm_count, int device, cudaStream_t st) {
-    const size_t smem = (size_t)a.NG * KT * 8 * 32 * sizeof(uint2) + (size_t)(7 * 4 * KT + 9 * a.T) * sizeof(u64);
+    const size_t smem = (size_t)a.NG * KT * 8 * 32 * sizeof(uint2) + (size_t)(8 * 4 * KT + 10 * a.T) * sizeof(u64);
     FHE_REQUIRE(smem <= 220 * 1024, "lincomb (tensor-core path): fragment table of %zu bytes does not fit shared memory", smem);
     static size_t attr_smem[64] = {0};                   // per device ordinal: function attributes are per device
     if (smem > attr_smem[device & 63]) {

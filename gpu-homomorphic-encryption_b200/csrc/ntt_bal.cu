@@ -65,6 +65,43 @@ __global__ void __launch_bounds__(256, 4) bal_a_kernel(const BalArgs a) {
     }
 }
 
+// pass A' with scattered outputs (BalScatter, common.cuh): reads a.out (where pass B' left its result), writes block by block
+template <int KA, int HB, bool NEAR>
+__global__ void __launch_bounds__(256, 4) bal_a_scatter_kernel(const BalArgs a, const BalScatter sc) {
+    using A = BalA<KA, HB, NEAR>;
+    extern __shared__ __align__(128) unsigned char raw[];
+    u64* sbuf = reinterpret_cast<u64*>(raw);
+    Twiddle* stw = reinterpret_cast<Twiddle*>(raw + 4096 * sizeof(u64));
+    const uint32_t tid = threadIdx.x;
+    const uint32_t limb = a.l0 + blockIdx.x / a.ctas_per_limb, chunk = blockIdx.x % a.ctas_per_limb;
+    const uint32_t pl = a.limb_begin + limb;
+    if (tid < (1u << KA)) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(a.tw + (size_t)pl * a.n + tid));
+        *reinterpret_cast<ulonglong2*>(stw + tid) = v;
+    }
+    const LimbParams P = a.params[pl];
+    const uint32_t items = a.nb * A::CB;
+    uint32_t it = chunk * a.m_items;
+    const uint32_t end = min(items, it + a.m_items);
+    constexpr int BIN = BalB<HB, NEAR>::inv_out_bound();
+    const uint32_t log_rpb = KA - sc.log_blocks;                 // rows per coefficient block = 2^KA / blocks
+    __syncthreads();
+#pragma unroll 1
+    for (; it < end; it++) {
+        const uint32_t poly = a.b0 + it / A::CB, cb = it % A::CB;
+        const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)cb * A::C;
+        A::template inv_round2<BIN>(tid, a.out + off, sbuf, stw, P);
+        __syncthreads();
+        const size_t row0 = ((size_t)poly * sc.limbs_total + sc.limb_off + limb) * sc.nc + (size_t)cb * A::C;
+        auto put = [&](u32 row, u32 col, u64 v) {
+            const u32 h = row >> log_rpb, rr = row & ((1u << log_rpb) - 1);
+            reinterpret_cast<u64*>(sc.base[h])[row0 + ((size_t)rr << 8) + col] = v;
+        };
+        A::template inv_round1_put<BIN>(tid, put, sbuf, stw, P);
+        if (it + 1 < end) __syncthreads();
+    }
+}
+
 // CTA = kBalBWarps warps = kBalBPairs tile pairs x kBalBGroups polynomial groups: the warps of one pair share its staged
 // twiddle block (8 KiB): 4 x 8 KiB of twiddles + 8 x 4 KiB of exchange buffers = 64 KiB per CTA.  Two CTAs (16 warps, 128 registers) per
 // SM is the measured optimum at config 3: 0.645 / 0.611 ms per forward / inverse pass, against 0.666 / 0.618 with three CTAs at 80
@@ -122,12 +159,13 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
 
 #ifndef FHE_BAL_EXPERIMENT          // (tools/sass/balexp.cu instantiates single kernels for SASS accounting)
 template <int KA, int HB, bool NEAR>
-static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st) {
+static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st, const BalScatter* scatter) {
     using A = BalA<KA, HB, NEAR>;
     static PerDeviceOnce attr_once;
     if (attr_once.need(plan->device)) {
         FHE_CUDA(cudaFuncSetAttribute(bal_a_kernel<KA, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_a_kernel<KA, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
+        FHE_CUDA(cudaFuncSetAttribute(bal_a_scatter_kernel<KA, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
     }
@@ -170,7 +208,8 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
         if (prof) profile_begin(3, pls, st);
-        bal_a_kernel<KA, HB, NEAR, true><<<grid_a, 256, kBalASmem, st>>>(a);
+        if (scatter) bal_a_scatter_kernel<KA, HB, NEAR><<<grid_a, 256, kBalASmem, st>>>(a, *scatter);
+        else bal_a_kernel<KA, HB, NEAR, true><<<grid_a, 256, kBalASmem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
     }
@@ -178,12 +217,12 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
 }
 
 template <int HB, bool NEAR>
-static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cudaStream_t st) {
+static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cudaStream_t st, const BalScatter* scatter) {
     switch (plan->logn) {
-        case 13: return run_bal_chunk<5, HB, NEAR>(plan, a, inverse, st);
-        case 14: return run_bal_chunk<6, HB, NEAR>(plan, a, inverse, st);
-        case 15: return run_bal_chunk<7, HB, NEAR>(plan, a, inverse, st);
-        case 16: return run_bal_chunk<8, HB, NEAR>(plan, a, inverse, st);
+        case 13: return run_bal_chunk<5, HB, NEAR>(plan, a, inverse, st, scatter);
+        case 14: return run_bal_chunk<6, HB, NEAR>(plan, a, inverse, st, scatter);
+        case 15: return run_bal_chunk<7, HB, NEAR>(plan, a, inverse, st, scatter);
+        case 16: return run_bal_chunk<8, HB, NEAR>(plan, a, inverse, st, scatter);
     }
     set_error("balanced NTT: unsupported ring degree 2^%u", plan->logn);
     return FHE_B200_EINVAL;
@@ -191,7 +230,7 @@ static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cud
 
 // chunk = buffer limbs [l0, l0+nl) x polynomials [b0, b0+nb) of a [batch][limb_count][n] buffer
 int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
-                   uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st) {
+                   uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st, const BalScatter* scatter) {
     BalArgs a;
     a.out = d_out; a.in = d_in;
     a.tw = inverse ? plan->d_inv : plan->d_fwd;
@@ -200,9 +239,25 @@ int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, u
     a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin;
     a.l0 = l0; a.nl = nl; a.b0 = b0; a.nb = nb;
     a.m_items = 1; a.ctas_per_limb = 1; a.groups = 1;
-    return plan->near60 ? dispatch_bal<16, true>(plan, a, inverse, st)
-         : plan->hb == 16 ? dispatch_bal<16, false>(plan, a, inverse, st)
-                          : dispatch_bal<8, false>(plan, a, inverse, st);
+    return plan->near60 ? dispatch_bal<16, true>(plan, a, inverse, st, scatter)
+         : plan->hb == 16 ? dispatch_bal<16, false>(plan, a, inverse, st, scatter)
+                          : dispatch_bal<8, false>(plan, a, inverse, st, scatter);
+}
+
+int launch_ntt_inverse_scatter(fhe_b200_plan* plan, uint64_t* d_buf, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,
+                               const BalScatter& scatter, cudaStream_t st) {
+    FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
+    FHE_REQUIRE(plan->bal, "scatter transform: needs the balanced two-pass NTT (2^13 <= N <= 2^16)");
+    FHE_REQUIRE(scatter.log_blocks <= 4 && scatter.log_blocks + 8 <= plan->logn && (scatter.nc << scatter.log_blocks) == plan->n,
+                "scatter transform: bad coefficient blocks");
+    if (batch == 0 || limb_count == 0) return 0;
+    DeviceGuard dev_guard(plan->device);
+    // limbs in groups of at most 256 (grid size); all polynomials in one launch
+    for (uint32_t l0 = 0; l0 < limb_count; l0 += 256) {
+        const uint32_t nl = l0 + 256 <= limb_count ? 256 : limb_count - l0;
+        FHE_TRY(launch_ntt_bal(plan, d_buf, d_buf, limb_begin, limb_count, l0, nl, 0, batch, true, st, &scatter));
+    }
+    return 0;
 }
 #endif
 

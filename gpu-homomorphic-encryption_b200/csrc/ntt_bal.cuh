@@ -103,6 +103,19 @@ struct BalA {
 #pragma unroll
         for (int e = 0; e < 16; e++) g[at1(tid, e)] = normalize<HB, NEAR, kTQ>(x[e], P.q);
     }
+    // as inv_round1, but every output goes through put(row, column inside the item, value): row of the limb's 2^KA x 256 matrix.
+    // Used by the scatter form of the last inverse pass (limb-sharded execution): the rows of a coefficient block belong to the
+    // GPU that owns that block, and the store goes straight to its buffer.
+    template <int BIN, class PUT>
+    static FHE_HD void inv_round1_put(u32 tid, const PUT& put, const u64* s, const Twiddle* stw, const LimbParams& P) {
+        u64 x[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = s[(e << 8) | tid];
+        inv_stages<4, R1, HB, NEAR, true, inv_bound_after(BIN, 4, HB, NEAR)>(x, TwA1{stw}, P);
+#pragma unroll
+        for (int e = 0; e < 16; e++)
+            put((((u32)e & RM) << 4) | (tid >> 4), (((u32)e >> R1) << 4) + (tid & 15), normalize<HB, NEAR, kTQ>(x[e], P.q));
+    }
 };
 
 // =======================================================================================================================

@@ -528,3 +528,81 @@ class BfvContext:
             self.close()
         except Exception:
             pass
+
+
+SHARD_HANDLE_BYTES = 128
+
+
+def shard_partition(total: int, rank: int, world: int) -> tuple[int, int]:
+    """the limb block partition of the sharded path (host only): -> (begin, count)"""
+    b, c = C.c_uint32(), C.c_uint32()
+    check(load_library().fhe_b200_shard_partition(total, rank, world, C.byref(b), C.byref(c)))
+    return b.value, c.value
+
+
+class BfvShard:
+    """One rank of a limb-sharded BFV group (fhe_b200_shard, csrc/shard.cu): NTT-domain work limb-sharded, base conversions
+    coefficient-sharded, the transpositions done by the producing kernels' stores into the peers' buffers over NVLink.
+
+    Set-up is collective: every rank creates its object, the 128-byte handles are carried to every rank in rank order (pass
+    `handles=` explicitly, or let `connect()` all-gather them through torch.distributed), then `connect`.
+    Ciphertexts are sharded by coefficient block: [batch][2][L][N/world]; keys by limb: [dnum][2][cW][N]."""
+
+    def __init__(self, ctx: "BfvContext", rank: int, world: int, max_batch: int = 1):
+        self.lib = load_library()
+        self.ctx, self.rank, self.world, self.max_batch = ctx, int(rank), int(world), int(max_batch)
+        h = C.c_void_p()
+        check(self.lib.fhe_b200_shard_create(ctx.h, self.rank, self.world, self.max_batch, C.byref(h)))
+        self.h = h
+        v = [C.c_uint32() for _ in range(6)]
+        nb = C.c_uint64()
+        check(self.lib.fhe_b200_shard_info(self.h, *[C.byref(x) for x in v], C.byref(nb)))
+        (self.coeff_begin, self.coeff_count, self.key_limb_begin, self.key_limb_count, self.ext_limb_begin,
+         self.ext_limb_count) = (x.value for x in v)
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(SHARD_HANDLE_BYTES)
+        check(self.lib.fhe_b200_shard_handle(self.h, buf))
+        return buf.raw
+
+    def connect(self, handles=None, group=None):
+        if handles is None:
+            import torch.distributed as dist
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.handle(), group=group)
+        assert len(handles) == self.world and all(len(x) == SHARD_HANDLE_BYTES for x in handles)
+        blob = C.create_string_buffer(b"".join(handles), SHARD_HANDLE_BYTES * self.world)
+        check(self.lib.fhe_b200_shard_connect(self.h, blob))
+        nb = C.c_uint64()
+        check(self.lib.fhe_b200_shard_info(self.h, None, None, None, None, None, None, C.byref(nb)))
+        self.nvlink_bytes_per_op = nb.value
+        return self
+
+    def shard_ct(self, ct: torch.Tensor) -> torch.Tensor:
+        """full ciphertexts [B][2][L][N] -> this rank's coefficient block [B][2][L][N/world]"""
+        return ct[..., self.coeff_begin:self.coeff_begin + self.coeff_count].contiguous()
+
+    def slice_key(self, key: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.ctx.dnum, 2, self.key_limb_count, self.ctx.n), dtype=torch.int64, device=key.device)
+        check(self.lib.fhe_b200_shard_slice_key(self.h, _ptr(key), _ptr(out), _stream()))
+        return out
+
+    def multiply(self, a: torch.Tensor, b: torch.Tensor, key_slice: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        batch = a.numel() // (2 * self.ctx.L * self.coeff_count)
+        out = torch.empty_like(a) if out is None else out
+        check(self.lib.fhe_b200_bfv_multiply_relin_sharded(self.h, _ptr(a), _ptr(b), _ptr(key_slice), _ptr(out), batch, _stream()))
+        return out
+
+    def check(self):
+        check(self.lib.fhe_b200_shard_check(self.h, _stream()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fhe_b200_shard_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

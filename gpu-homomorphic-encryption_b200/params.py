@@ -77,6 +77,8 @@ def bfv_preset(name: str) -> dict:
         "c4": dict(n=1 << 16, L=24, R=25, K=8, dnum=3, t=65537, sigma=3.2, hamming_weight=64),
         # reduced shapes for fast parity tests
         "small": dict(n=1024, L=4, R=5, K=2, dnum=2, t=65537, sigma=3.2, hamming_weight=64),
+        # smallest ring the limb-sharded path supports (balanced two-pass NTT), limb counts that do not divide evenly by 2 / 4 ranks
+        "mid": dict(n=8192, L=6, R=7, K=3, dnum=2, t=65537, sigma=3.2, hamming_weight=64),
     }
     p = dict(presets[name])
     p["primes"] = prime_chain(p["L"] + p["R"])

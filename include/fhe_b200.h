@@ -230,6 +230,37 @@ int fhe_b200_bfv_mod_switch_to_level(fhe_b200_bfv* ctx, const uint64_t* d_ct, ui
 /* host-buffer variant of multiply_relin (copies in, computes, copies out; synchronous) */
 int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* ctx, const uint64_t* h_a, const uint64_t* h_b,
                                      const uint64_t* d_rlk, uint64_t* h_out, uint32_t batch);
+/* ---- limb-sharded multiply + relinearize over the GPUs of one NVLink domain (BASELINE.json config 4) -----------------------
+ * The reference only sketches multi-GPU execution ("limbs distributed over GPUs", docs/ARCHITECTURE.md:501-512, README.md:320).
+ * One shard object per GPU (rank) on top of that GPU's own BFV context (same parameters on every rank, world a power of two
+ * <= 16, N/world >= 256).  NTT-domain work runs limb-sharded (rank g owns a block of the L+R / L+K limbs), base conversions run
+ * coefficient-sharded (rank g owns coefficients [g N/world, (g+1) N/world)); the four transpositions per multiply are stores of
+ * the producing kernels straight into the peer's buffer over NVLink, ordered by epoch flags (csrc/shard.cu) -- no NCCL call and
+ * no host synchronisation on the data path.  Set-up: create on every rank, export the 128-byte handle, carry all handles to
+ * every rank in rank order (torch.distributed.all_gather_object, MPI, a pipe ...), connect.  Ranks may be processes (CUDA IPC)
+ * or several objects in one process (peer access; also several ranks on ONE device, which is how the single-GPU tests run it).
+ * Data: sharded ciphertext [batch][2][L][N/world] = the rank's coefficient block of every limb, coefficient form;
+ *       key slice [dnum][2][cW][N] = the rank's key limbs (fhe_b200_shard_slice_key).
+ * Every rank must issue the same sequence of sharded calls.  A rank whose peer never delivers gives up after
+ * FHE_B200_SHARD_TIMEOUT_MS (default 10 000) per wait and fhe_b200_shard_check reports it. */
+typedef struct fhe_b200_shard fhe_b200_shard;
+#define FHE_B200_SHARD_HANDLE_BYTES 128
+int fhe_b200_shard_create(fhe_b200_bfv* ctx, int rank, int world, uint32_t max_batch, fhe_b200_shard** out);
+int fhe_b200_shard_destroy(fhe_b200_shard* shard);
+int fhe_b200_shard_handle(const fhe_b200_shard* shard, void* h_handle);
+int fhe_b200_shard_connect(fhe_b200_shard* shard, const void* h_handles /* [world][128], rank order */);
+/* the block partition used for limbs: the first total % world ranks own one item more (host only, no GPU needed) */
+int fhe_b200_shard_partition(uint32_t total, uint32_t rank, uint32_t world, uint32_t* begin, uint32_t* count);
+/* this rank's coefficient block, key limbs (of L+K) and extended-basis limbs (of L+R); bytes it stores into other ranks per
+ * multiply of one ciphertext pair (any output may be NULL) */
+int fhe_b200_shard_info(const fhe_b200_shard* shard, uint32_t* coeff_begin, uint32_t* coeff_count, uint32_t* key_limb_begin,
+                        uint32_t* key_limb_count, uint32_t* ext_limb_begin, uint32_t* ext_limb_count, uint64_t* nvlink_bytes_per_op);
+int fhe_b200_shard_slice_key(const fhe_b200_shard* shard, const uint64_t* d_key, uint64_t* d_slice, void* stream);
+/* FHEContext::multiply + relinearize (src/fhe.cu:199-235) on sharded ciphertexts; same words as fhe_b200_bfv_multiply_relin */
+int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* shard, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_key_slice,
+                                        uint64_t* d_out, uint32_t batch, void* stream);
+/* synchronises `stream`; FHE_B200_ESTATE if a wait for a peer timed out since creation */
+int fhe_b200_shard_check(fhe_b200_shard* shard, void* stream);
 /* scheme constants for the compat layer and tests */
 int fhe_b200_bfv_info(const fhe_b200_bfv* ctx, uint32_t* n, uint32_t* L, uint32_t* R, uint32_t* K, uint32_t* dnum,
                       uint64_t* t);
