@@ -97,22 +97,54 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- reference arm
+WORKLOAD = ("config3: uint64[64][32][65536] per GPU, forward then inverse batched RNS-NTT "
+            "(4096 limb-transforms per step per GPU)")
+
+
+def config_dict(world):
+    """identical in both arms (the reference arm runs the same workload on the host cores)"""
+    return {"workload": WORKLOAD, "N": N, "limbs": LIMBS, "polys_per_gpu": POLYS, "parallelism": f"batch-sharded x{world}",
+            "l2_policy": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
+            "ntt_chunk_mb": int(os.environ.get("FHE_B200_NTT_CHUNK_MB", "1024"))}
+
+
+def _host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def _cpu_engine():
+    """the CPU port (oracle: Harvey lazy butterflies, Shoup twiddles, OpenMP over polynomial x limb), compiled -O3 -march=native on
+    this machine when gcc is there (oracle.use_native), else the portable build that ships with the snapshot"""
+    import oracle
+    native = oracle.use_native()
+    if not native:
+        oracle.build()
+    chain = oracle.prime_chain(LIMBS)
+    return oracle, oracle.RnsNtt(N, chain), chain, ("-O3 -march=native" if native else "-O3 -march=x86-64-v2")
+
+
 def run_reference(args, rank, world):
     """Times the CPU restatement (oracle port; the reference's own code for this path neither builds nor computes
-    a transform) on the box's host cores, all threads, bounded sample per step."""
+    a transform) on the box's host cores, all threads.  A step is the same workload as the GPU arm's -- all 64
+    polynomials forward and inverse -- unless the host is so small that a step would take more than ~2 s, in which case a step
+    is the largest whole number of polynomials that fits (stated in cpu_baseline.sample)."""
     if rank != 0:
         return
     import numpy as np
-    import oracle
-    oracle.build()
-    chain = oracle.prime_chain(LIMBS)
-    eng = oracle.RnsNtt(N, chain)
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    sample_polys = max(1, min(POLYS, threads // 8 if threads >= 16 else 1))
+    oracle, eng, chain, flags = _cpu_engine()
+    threads = _host_threads()       # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
     rng = np.random.default_rng(0x5EED0003)
-    data = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in chain]) for _ in range(sample_polys)])
-    flat = data.reshape(-1)
+    one = np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in chain])
+    probe = np.tile(one.reshape(-1), max(1, min(POLYS, threads)))
+    pp = probe.size // (LIMBS * N)
+    eng.run_inplace(probe, pp, False, threads); eng.run_inplace(probe, pp, True, threads)
+    t0 = time.perf_counter()
+    eng.run_inplace(probe, pp, False, threads); eng.run_inplace(probe, pp, True, threads)
+    per_poly = (time.perf_counter() - t0) / pp
+    sample_polys = int(max(1, min(POLYS, 2.0 / max(per_poly, 1e-6))))
+    if sample_polys >= POLYS // 2:
+        sample_polys = POLYS
+    flat = np.tile(one.reshape(-1), sample_polys)
     units = 2 * LIMBS * sample_polys
 
     def step():
@@ -125,17 +157,18 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
+    ok = bool(np.array_equal(flat, np.tile(one.reshape(-1), sample_polys)))
     value = units * args.steps / dt
-    sample = f"{sample_polys} of {POLYS} polynomials x {LIMBS} limbs, forward+inverse ({units} limb-transforms per step)"
+    sample = (f"{sample_polys} of {POLYS} polynomials x {LIMBS} limbs per step, forward+inverse ({units} limb-transforms per step), "
+              f"{threads} OpenMP threads, gcc {flags}; {1e9 / (value / threads * (N // 2) * LOGN):.2f} ns per butterfly per thread")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "config3: uint64[64][32][65536] fwd+inv RNS-NTT (bounded sample per step)",
-                   "N": N, "limbs": LIMBS, "polys": POLYS},
+        "config": config_dict(world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "roundtrip_bit_exact": ok,
         "note": "reference CUDA code does not build/compute (SURVEY section 0); this arm is the CPU oracle port, OpenMP over polynomial x limb",
     }
     print(json.dumps(line), flush=True)
@@ -144,13 +177,10 @@ def run_reference(args, rank, world):
 def cpu_baseline_sample():
     """bounded (~10 s) CPU sample of the same workload for the ours-arm JSON line (rank 0, N=1 only)."""
     import numpy as np
-    import oracle
-    oracle.build()
-    chain = oracle.prime_chain(LIMBS)
-    eng = oracle.RnsNtt(N, chain)
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    oracle, eng, chain, flags = _cpu_engine()
+    threads = _host_threads()
     rng = np.random.default_rng(0x5EED0003)
-    polys = 1
+    polys = max(1, min(POLYS, threads // 4))
     data = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in chain]) for _ in range(polys)])
     flat = data.reshape(-1)
     eng.run_inplace(flat, polys, False, threads); eng.run_inplace(flat, polys, True, threads)          # warm
@@ -159,12 +189,13 @@ def cpu_baseline_sample():
         eng.run_inplace(flat, polys, False, threads); eng.run_inplace(flat, polys, True, threads)
         reps += 1
         dt = time.perf_counter() - t0
-        if dt > 8.0 or reps >= 200:
+        if dt > 10.0 or reps >= 400:
             break
     units = reps * polys * 2 * LIMBS
-    return {"value": units / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{reps} x (1 polynomial x {LIMBS} limbs, forward+inverse) = {units} limb-transforms in {dt:.1f} s, "
-                      f"oracle Shoup/Harvey NTT with OpenMP"}
+    rate = units / dt
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{reps} x ({polys} polynomial(s) x {LIMBS} limbs, forward+inverse) = {units} limb-transforms in {dt:.1f} s, "
+                      f"oracle Harvey/Shoup NTT with OpenMP, gcc {flags}; {1e9 / (rate / threads * (N // 2) * LOGN):.2f} ns per butterfly per thread"}
 
 
 def bind_to_gpu_numa_node(gpu_index: int):
@@ -206,7 +237,6 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     lib = fhe_b200.load_library()
 
-    # deterministic prime chain, computed by the library's own host code via a throw-away import-free path
     from fhe_b200.params import prime_chain
     chain = prime_chain(LIMBS)
     plan = fhe_b200.Plan(N, chain, device=local_rank)
@@ -245,10 +275,24 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     launches = lib.fhe_b200_launch_count() - l0
     ms = e0.elapsed_time(e1)
+    # the same loop for at least 1.2 s, still under the clock sampler: the sustained figure (the K-step region above is ~50 ms)
+    sus_steps = max(args.steps, int(1.25e3 / max(ms / args.steps, 1e-3)) + 1)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record(stream)
+    for _ in range(sus_steps):
+        step()
+    s1.record(stream)
+    barrier()
+    sus_ms = s0.elapsed_time(s1)
     clocks = sampler.stop() if sampler else None
     ok = bool(torch.equal(x, ref))                       # forward+inverse is the identity: free correctness check
 
-    # per-kernel durations for the roofline (second pass, events around every launch, same stream)
+    # integer-pipe peaks of this very GPU, measured now (csrc/peaks.cu): the roofline denominators
+    lo_ops, wide_ops = C.c_double(), C.c_double()
+    fhe_b200.check(lib.fhe_b200_measure_int_peaks(local_rank, C.byref(lo_ops), C.byref(wide_ops), 5))
+
+    # per-kernel durations (second pass, events around every launch, same stream)
     lib.fhe_b200_profile_enable(1)
     psteps = min(args.steps, 5)
     for _ in range(psteps):
@@ -275,18 +319,37 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     e2e_ok = bool(np.array_equal(h, ref.cpu().numpy().view(np.uint64)))
+    del h
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, sus_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, sus_ms_max = float(t[0]), float(t[1]), float(t[2])
+
+    # secondary metric (BASELINE.json config 4) -- every rank takes part; rank 0 reports
+    hm, hm_ls = None, {}
+    if not args.no_hmult:
+        del x, ref
+        torch.cuda.empty_cache()
+        try:
+            from bench_hmult import run_hmult, run_hmult_limb_sharded
+            if world == 1:
+                hm = run_hmult(args, local_rank, batch=8)
+            else:
+                hm = run_hmult(args, local_rank, batch=8, steps=5, dist=dist, lite=True)
+                for b in (1, 4):
+                    try:
+                        hm_ls[f"batch{b}"] = run_hmult_limb_sharded(local_rank, "c4", b, 20, dist=dist)
+                    except Exception as ex:
+                        hm_ls[f"batch{b}"] = {"error": repr(ex)}
+        except Exception as ex:  # secondary metric must never take the headline line down
+            hm = {"error": repr(ex)}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         value = world * UNITS_PER_STEP * args.steps / (ms_max / 1e3)
+        sus_value = world * UNITS_PER_STEP * sus_steps / (sus_ms_max / 1e3)
         e2e_val = world * UNITS_PER_STEP * e2e_steps / (e2e_ms_max / 1e3)
-        # N = 2^16 runs as two balanced passes per direction (8 stages each; ntt_bal.cu): every launch reads and writes each limb
-        # once, i.e. moves the algorithmic 1 MiB per limb-transform it covers.  The dominant kernel is the slowest of the four.
         names = {"tile_fwd": "bal_b_kernel<8,16,near,fwd> (tile-pair pass)", "tile_inv": "bal_b_kernel<8,16,near,inv> (tile-pair pass)",
                  "row_fwd": "bal_a_kernel<8,16,near,fwd> (column pass)", "row_inv": "bal_a_kernel<8,16,near,inv> (column pass)"}
         if os.environ.get("FHE_B200_NTT_BAL", "1") == "0":
@@ -295,7 +358,6 @@ def run_ours(args, rank, local_rank, world):
         dom = max(kinds, key=lambda k: kinds[k][1])
         tl, tms, tu = kinds[dom]
         all_ms = sum(v[1] for v in kinds.values())
-        achieved = (tu * UNIT_BYTES / 1e9) / (tms / 1e3) if tms > 0 else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -303,48 +365,64 @@ def run_ours(args, rank, local_rank, world):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch", {}).get(dom)
             except Exception:
                 traffic = None
+        # ---- roofline.  The butterfly is bound by the FMA-heavy (IMAD) pipe (ncu: sm__pipe_fmaheavy_cycles_active 70-78 %, DRAM 38-47 %,
+        # profiles/r01_bal_ncu_summary.md), so the binding roofline is the integer one.  Algorithmic work of one butterfly = the IMAD-class
+        # instructions of the exact 64-bit Shoup multiply used: 5 IMAD.WIDE (32x32->64) + 4 IMAD (32x32->32) = 9 per lane
+        # (csrc/modarith.cuh shoup_mul_lazy3; SURVEY 8d counts 10 for the canonical form).  A limb-transform is (N/2) log2 N butterflies.
+        # peak = the rate at which this chip retires that 5:4 mix, from the two rates measured a moment ago:
+        #     peak = 9 / (5 / R_wide + 4 / R_lo)   IMAD-class thread-operations per second,
+        # achieved = butterflies/s * 9 for the dominant kernel (its own launch time); frac = achieved / peak.
+        r_lo, r_wide = lo_ops.value, wide_ops.value
+        bfly_per_unit = (N // 2) * LOGN
+        mix_peak = 9.0 / (5.0 / r_wide + 4.0 / r_lo)
+        passes_bfly = bfly_per_unit / 2.0                  # a launch covers half of the stages (8 of 16) of every limb-transform
+        dom_ops = (tu * passes_bfly * 9.0) / (tms / 1e3) if tms > 0 else None
+        step_ops = value / world * bfly_per_unit * 9.0
+        achieved_gbs = (tu * UNIT_BYTES / 1e9) / (tms / 1e3) if tms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "config3: uint64[64][32][65536] per GPU, forward then inverse batched RNS-NTT "
-                                   "(4096 limb-transforms per step per GPU)",
-                       "N": N, "limbs": LIMBS, "polys_per_gpu": POLYS, "parallelism": f"batch-sharded x{world}",
-                       "l2_policy": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
-                       "ntt_chunk_mb": int(os.environ.get("FHE_B200_NTT_CHUNK_MB", "1024"))},
+            "config": config_dict(world),
             "roundtrip_bit_exact": ok and e2e_ok,
+            "sustained": {"value": sus_value, "unit": UNIT, "steps": sus_steps, "seconds": sus_ms_max / 1e3,
+                          "note": "same loop run for >= 1.2 s right after the K timed steps, clocks sampled across both"},
             "clocks": clocks,
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": POLYS * LIMBS * N * 8,
                     "d2h_bytes_per_step": POLYS * LIMBS * N * 8, "steps": e2e_steps,
-                    "api": "fhe_b200_ntt_host (pinned host buffer, 3-stream chunk pipeline)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": names[dom], "peak_source": peak_src,
-                         "launches_profiled": tl, "avg_launch_ms": (tms / tl) if tl else None,
-                         "units_per_launch": (tu / tl) if tl else None, "bytes_per_unit": UNIT_BYTES,
+                    "api": "fhe_b200_ntt_host (pinned host buffer, 3-stream chunk pipeline)",
+                    "pcie_GBs_per_direction_per_gpu": e2e_val / world * UNIT_BYTES / 2 / 1e9,
+                    "note": "bound by the host link: every limb-transform moves 512 KiB in and 512 KiB out over PCIe; ranks of one node "
+                            "share the host's memory and root complexes, so this figure does not scale with the GPU count"},
+            "roofline": {"bound": "imad", "achieved": (dom_ops / 1e12) if dom_ops else None, "peak": mix_peak / 1e12, "unit": "T IMAD-class op/s",
+                         "frac": (dom_ops / mix_peak) if dom_ops else None, "traffic": traffic,
+                         "kernel": names[dom], "launches_profiled": tl, "avg_launch_ms": (tms / tl) if tl else None,
+                         "units_per_launch": (tu / tl) if tl else None,
                          "kernel_share_of_step": (tms / all_ms) if all_ms else None,
-                         "step_achieved_GBs": value * UNIT_BYTES / 1e9 / world,
-                         "step_frac": value * UNIT_BYTES / 1e9 / world / peak,
+                         "ops_per_butterfly": {"IMAD.WIDE": 5, "IMAD": 4}, "butterflies_per_limb_transform": bfly_per_unit,
+                         "measured_now": {"imad_lo_Tops": r_lo / 1e12, "imad_wide_Tops": r_wide / 1e12,
+                                          "how": "fhe_b200_measure_int_peaks: 8 independent chains per thread, 64 warps per SM, best of 5"},
+                         "peak_formula": "9 / (5 / imad_wide + 4 / imad_lo)",
+                         "whole_step": {"achieved": step_ops / 1e12, "frac": step_ops / mix_peak,
+                                        "peak_limb_transforms_s": mix_peak / 9.0 / bfly_per_unit},
+                         "survey_8d_formula": {"imad_ops_per_limb_transform": 10 * bfly_per_unit,
+                                               "frac_vs_imad_lo_peak": value / world * 10 * bfly_per_unit / r_lo,
+                                               "frac_vs_imad_wide_peak": value / world * 10 * bfly_per_unit / r_wide},
                          "per_kernel_ms": {k: v[1] / psteps for k, v in kinds.items()}},
+            # HBM view of the same numbers (not the binding roofline): algorithmic 1 MiB per limb-transform for the whole step;
+            # each of the two passes of a transform moves that 1 MiB once (ncu dram bytes per launch = `traffic`)
+            "hbm": {"peak": peak, "unit": "GB/s", "peak_source": peak_src, "bytes_per_unit": UNIT_BYTES,
+                    "step_achieved": value * UNIT_BYTES / 1e9 / world, "step_frac": value * UNIT_BYTES / 1e9 / world / peak,
+                    "dominant_kernel_achieved": achieved_gbs, "dominant_kernel_frac": (achieved_gbs / peak) if achieved_gbs else None,
+                    "wasted_traffic_vs_algorithmic": 2.0},
         }
-        # integer-pipe roofline (the binding one): 28 FMA-pipe cycles per warp-butterfly
-        # (5 IMAD.WIDE at 4 cycles, 4 IMAD.lo at 2 cycles per warp instruction per SM sub-partition; measured by
-        # tools/microbench2.cu), 4 sub-partitions per SM, at the SM clock sampled during the timed region
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        peak_bfly = 148 * 4 * 32 * sm_mhz * 1e6 / 28.0
-        bfly = value / world * (N // 2) * LOGN
-        line["int_pipe"] = {"bound": "imad", "achieved_Gbutterflies_s": bfly / 1e9, "peak_Gbutterflies_s": peak_bfly / 1e9,
-                            "frac": bfly / peak_bfly, "pipe_cycles_per_warp_butterfly": 28, "sm_mhz": sm_mhz,
-                            "peak_limb_transforms_s": peak_bfly / ((N // 2) * LOGN)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
-        if world == 1 and not args.no_hmult:
-            try:
-                from bench_hmult import run_hmult
-                line["hmult"] = run_hmult(args, local_rank, batch=8)
-            except Exception as ex:  # secondary metric must never take the headline line down
-                line["hmult"] = {"error": repr(ex)}
+        if hm is not None:
+            line["hmult"] = hm
+        if hm_ls:
+            line["hmult_limb_sharded"] = hm_ls
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

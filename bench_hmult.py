@@ -59,7 +59,7 @@ def _floor(n, L, R, K, dnum, ms_per_op, sms=148, mhz=1965.0):
             "floor_ms": ntt_ms + conv_ms, "frac": (ntt_ms + conv_ms) / ms_per_op}
 
 
-def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None):
+def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None, lite=False):
     """dist: an initialised torch.distributed module for the batch-sharded multi-GPU run (every rank multiplies its own `batch`
     ciphertext pairs with replicated keys -- no data-path collective; the timed region is bracketed by barriers, the time is the
     max over ranks and `value` the whole-job aggregate)."""
@@ -122,6 +122,18 @@ def run_hmult(args, local_rank=0, preset="c4", batch=None, steps=None, dist=None
         breakdown[name] = {"launches": n_l.value, "ms": round(t_ms.value, 4)}
     breakdown["whole_call_ms"] = round(e2.elapsed_time(e3), 4)
     lib.fhe_b200_profile_enable(0)
+    if lite:            # multi-GPU lines: the multiply itself plus its correctness check, nothing else
+        import oracle
+        from fhe_b200.engine import to_host as _th
+        dec = _th(g.decrypt(out, sk))
+        q0 = p["primes"][0]
+        r = oracle.negacyclic_mul_ntt(m1[0], m2[0], q0)
+        signed = np.where(r > np.uint64(q0 // 2), r.astype(np.int64) - np.int64(q0), r.astype(np.int64))
+        ok = bool(np.array_equal(dec[0], np.mod(signed, np.int64(t)).astype(np.uint64)))
+        return {"metric": "BFV HMult+relinearize ops/s", "value": world * B * K / (ms / 1e3), "unit": "ops/s", "n_gpus": world,
+                "batch_per_gpu": B, "steps": K, "scaling": "weak", "parallelism": f"batch-sharded x{world} (independent ciphertexts, no data-path collective)",
+                "ms_per_op": ms / (B * K), "config": {"workload": f"config4: N={n}, L={L}, R={p['R']}, dnum={p['dnum']}, K={p['K']}, t={t}"},
+                "decrypts_to_product": ok, "gpu_launches": int(launches), "kernel_ms_per_call": breakdown}
     # the other two operations of the path: public-key encryption and decryption of the same batch (device-resident, CUDA events)
     def timed(fn, reps=5):
         fn(); torch.cuda.synchronize()

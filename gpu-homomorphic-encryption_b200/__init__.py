@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
         "fhe_b200_bfv_tensor": [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_ks_inner": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_multiply_relin_host": [_vp, _vp, _vp, _vp, _vp, C.c_uint32],
+        "fhe_b200_measure_int_peaks": [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int],
         "fhe_b200_shard_create": [_vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(_vp)],
         "fhe_b200_shard_destroy": [_vp],
         "fhe_b200_shard_handle": [_vp, _vp],

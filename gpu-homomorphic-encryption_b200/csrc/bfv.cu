@@ -31,11 +31,12 @@ int ensure_words(uint64_t** buf, size_t* have, size_t need) {
 namespace fhe_b200 {
 
 // ---- sampling kernels ----------------------------------------------------------------------------------------------
-// small polynomial (ternary or Gaussian), expanded to residues for limbs [limb_begin, +limb_count); polynomial b uses seed+b
+// small polynomial (ternary or Gaussian), expanded to residues for limbs [limb_begin, +limb_count).  item0 < 0: one polynomial
+// keyed by the seed itself (keys); item0 >= 0: polynomial b is batch item item0 + b of the call and uses rng_item_seed(seed, item0 + b)
 template <int MODE>   // 0 ternary, 1 gaussian
 __global__ void __launch_bounds__(256) sample_small_kernel(u64* __restrict__ out, const LimbParams* __restrict__ params,
                                                            uint32_t logn, uint32_t limb_begin, uint32_t limb_count, uint32_t batch,
-                                                           u64 seed, u64 stream, u32 thr, const u64* __restrict__ cdt, u32 cdt_len) {
+                                                           u64 seed, long long item0, u64 stream, u32 thr, const u64* __restrict__ cdt, u32 cdt_len) {
     __shared__ u64 scdt[kMaxCdt];
     if (MODE == 1) { for (u32 i = threadIdx.x; i < cdt_len; i += blockDim.x) scdt[i] = cdt[i]; __syncthreads(); }
     const uint32_t n = 1u << logn;
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(256) sample_small_kernel(u64* __restrict__ out
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
         const uint32_t j = (uint32_t)(g & (n - 1));
         const size_t b = g >> logn;
-        const u64 r = rng_at(rng_key(seed + b, stream), j);
+        const u64 r = rng_at(rng_key(item0 < 0 ? seed : rng_item_seed(seed, (u64)item0 + b), stream), j);
         const int v = MODE == 0 ? ternary_from(r, thr) : gauss_from(r, scdt, cdt_len);
         for (uint32_t l = 0; l < limb_count; l++) out[(b * limb_count + l) * n + j] = small_to_residue(v, params[limb_begin + l].q);
     }
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) enc_mul_kernel(u64* __restrict__ ct, cons
 // c0 += e1 + delta*m ; c1 += e2   (coefficient form; e1, e2 regenerated from the counter generator)
 __global__ void __launch_bounds__(256) enc_finish_kernel(u64* __restrict__ ct, const u64* __restrict__ pt, const LimbParams* __restrict__ params,
                                                          const u64* __restrict__ delta, const u64* __restrict__ cdt, u32 cdt_len,
-                                                         uint32_t logn, uint32_t L, uint32_t batch, u64 seed) {
+                                                         uint32_t logn, uint32_t L, uint32_t batch, u64 seed, u64 item0) {
     __shared__ u64 scdt[kMaxCdt];
     for (u32 i = threadIdx.x; i < cdt_len; i += blockDim.x) scdt[i] = cdt[i];
     __syncthreads();
@@ -136,8 +137,9 @@ __global__ void __launch_bounds__(256) enc_finish_kernel(u64* __restrict__ ct, c
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
         const uint32_t j = (uint32_t)(g & (n - 1));
         const size_t b = g >> logn;
-        const int e1 = gauss_from(rng_at(rng_key(seed + b, 1), j), scdt, cdt_len);
-        const int e2 = gauss_from(rng_at(rng_key(seed + b, 2), j), scdt, cdt_len);
+        const u64 sd = rng_item_seed(seed, item0 + b);
+        const int e1 = gauss_from(rng_at(rng_key(sd, 1), j), scdt, cdt_len);
+        const int e2 = gauss_from(rng_at(rng_key(sd, 2), j), scdt, cdt_len);
         const u64 m = pt[g];
         for (uint32_t i = 0; i < L; i++) {
             const LimbParams P = params[i];
@@ -248,6 +250,25 @@ __global__ void __launch_bounds__(256) ks_inner_kernel(ulonglong2* __restrict__ 
         o1.x = barrett128(h1x, l1x, P.q, P.mu_hi, P.mu_lo); o1.y = barrett128(h1y, l1y, P.q, P.mu_hi, P.mu_lo);
         acc[v] = o0; acc[per + v] = o1;
     }
+}
+
+// The tensor product and the key-switch inner product run inside the tile passes (ntt_fused.cu) wherever the two-pass transform is
+// in use (2^13 <= N <= 2^16) and there are at most three digits; FHE_B200_FUSED_TILE=0 keeps the separate kernels (tests, A/B runs).
+static bool use_fused_tile(const fhe_b200_bfv* c) {
+    const char* e = getenv("FHE_B200_FUSED_TILE");
+    if (e && atoi(e) == 0) return false;
+    return fused_tile_supported(c->plan, c->dnum);
+}
+// forward transform, pointwise tensor product, inverse transform of  ext [4][B][A][N] (planes 0..3, or 0..1 when squaring)  ->  d [3][B][A][N]
+// planes [p0, p0 + np) of ext still need their forward transform when np > 0 (the split path transforms them on other streams)
+static int tensor_transform(fhe_b200_bfv* c, uint64_t* ext, uint64_t* d, uint32_t B, bool square, cudaStream_t st) {
+    const uint32_t A = c->L + c->R;
+    const size_t an = (size_t)A * c->n;
+    FusedTile t; t.in = ext; t.out = d; t.limb_begin = 0; t.limb_count = A; t.nb = B; t.square = square;
+    for (int p = 0; p < 4; p++) t.in_plane[p] = (size_t)p * B * an;
+    for (int q = 0; q < 3; q++) t.out_plane[q] = (size_t)q * B * an;
+    t.in_poly = an; t.out_poly = an;
+    return launch_fused_tile(c->plan, 0, t, st);
 }
 
 static inline uint32_t grid_for(const fhe_b200_bfv* c, size_t items) {
@@ -419,13 +440,13 @@ extern "C" int fhe_b200_bfv_keygen(fhe_b200_bfv* c, uint64_t seed_sk, uint64_t s
         FHE_LAUNCH_CHECK();
         FHE_CUDA(cudaFreeAsync(d_s, st));
     } else {
-        sample_small_kernel<0><<<grid_for(c, n), 256, 0, st>>>(d_sk, prm, c->logn, 0, A, 1, seed_sk, 0, c->thr, c->d_cdt, c->cdt_len);
+        sample_small_kernel<0><<<grid_for(c, n), 256, 0, st>>>(d_sk, prm, c->logn, 0, A, 1, seed_sk, -1, 0, c->thr, c->d_cdt, c->cdt_len);
         FHE_LAUNCH_CHECK();
     }
     FHE_TRY(launch_ntt(c->plan, d_sk, d_sk, 1, 0, A, false, st));
     // public key: e on stream 2, a on streams 16+i
     uint64_t* pk0 = d_pk; uint64_t* pk1 = d_pk + (size_t)L * n;
-    sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(pk0, prm, c->logn, 0, L, 1, seed_pk, 2, 0, c->d_cdt, c->cdt_len);
+    sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(pk0, prm, c->logn, 0, L, 1, seed_pk, -1, 2, 0, c->d_cdt, c->cdt_len);
     FHE_LAUNCH_CHECK();
     FHE_TRY(launch_ntt(c->plan, pk0, pk0, 1, 0, L, false, st));
     sample_uniform_kernel<<<grid_for(c, (size_t)L * n), 256, 0, st>>>(pk1, prm, c->logn, 0, L, seed_pk, 16);
@@ -444,7 +465,7 @@ extern "C" int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* c, uint64_t seed, const ui
     for (uint32_t d = 0; d < c->dnum; d++) {
         uint64_t* b = d_rlk + (size_t)(2 * d) * W * n; uint64_t* a = b + (size_t)W * n;
         const uint64_t base = 1024ull * (d + 1);
-        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, base + 512, 0, c->d_cdt, c->cdt_len);
+        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, -1, base + 512, 0, c->d_cdt, c->cdt_len);
         FHE_LAUNCH_CHECK();
         FHE_TRY(launch_ntt(c->plan, b, b, 1, 0, W, false, st));
         sample_uniform_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base);
@@ -490,19 +511,18 @@ extern "C" int fhe_b200_bfv_encrypt(fhe_b200_bfv* c, uint64_t seed, const uint64
     const LimbParams* prm = c->plan->d_params;
     const size_t ln = (size_t)L * n;
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, batch * ln));
-    // ciphertext b uses seed + b: a half that starts at polynomial `first` is seeded with seed + first
+    // ciphertext b is batch item b of this call: rng_item_seed(seed, b); a half that starts at polynomial `first` passes first on
     return fork_join_halves(c, batch, (cudaStream_t)stream, [&](uint32_t first, uint32_t cnt, cudaStream_t st) -> int {
         uint64_t* u = c->d_ws + (size_t)first * ln;
         uint64_t* ct = d_ct + (size_t)first * 2 * ln;
         const uint64_t* pt = d_pt + (size_t)first * n;
-        const uint64_t sd = seed + first;
-        sample_small_kernel<0><<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(u, prm, c->logn, 0, L, cnt, sd, 0, c->thr, c->d_cdt, c->cdt_len);
+        sample_small_kernel<0><<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(u, prm, c->logn, 0, L, cnt, seed, (long long)first, 0, c->thr, c->d_cdt, c->cdt_len);
         FHE_LAUNCH_CHECK();
         FHE_TRY(launch_ntt(c->plan, u, u, cnt, 0, L, false, st));
         enc_mul_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(ct, u, d_pk, prm, c->logn, L, cnt * ln);
         count_launch();
         FHE_TRY(launch_ntt(c->plan, ct, ct, 2 * cnt, 0, L, true, st));
-        enc_finish_kernel<<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(ct, pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, cnt, sd);
+        enc_finish_kernel<<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(ct, pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, cnt, seed, (uint64_t)first);
         FHE_LAUNCH_CHECK();
         return 0;
     });
@@ -652,7 +672,6 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
     const LimbParams* prm = c->plan->d_params;
     const size_t N = n, ln = (size_t)L * N, wn = (size_t)W * N;
     int rc = 0;
-    cudaError_t e = cudaSuccess;
     for (uint32_t dg = 0; dg < dnum && !rc; dg++) {
         uint64_t* D = dig + (size_t)dg * B * wn;
         // the digit's own limbs are written through by the conversion kernel (copy_idx = src_idx)
@@ -660,16 +679,28 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
         v.copy_out = D; v.copy_stride = wn;
         rc = lincomb_launch(c->modup[dg], v, n, B, st);
     }
-    if (e != cudaSuccess) { set_error("key_switch: device copy failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
-    if (!rc) rc = launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st);
-    if (!rc) {
-        const size_t per = B * wn / 2;
-        if (profile_on()) profile_begin(6, B, st);
-        ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn, 0, W, dnum, B);
-        if (profile_on()) profile_end(st);
-        count_launch();
+    if (use_fused_tile(c)) {
+        // column pass of the digits, then ONE kernel: tile pass of the digits, inner product with the key, inverse tile pass of the sums
+        if (!rc) rc = launch_ntt_pass_a(c->plan, dig, dig, dnum * B, 0, W, false, st);
+        if (!rc) {
+            FusedTile t; t.in = dig; t.out = acc; t.limb_begin = 0; t.limb_count = W; t.nb = B; t.dnum = dnum;
+            for (uint32_t d = 0; d < dnum; d++) t.in_plane[d] = (size_t)d * B * wn;
+            t.out_plane[0] = 0; t.out_plane[1] = (size_t)B * wn;
+            t.in_poly = wn; t.out_poly = wn; t.key = d_key; t.key_poly = wn;
+            rc = launch_fused_tile(c->plan, 1, t, st);
+        }
+        if (!rc) rc = launch_ntt_pass_a(c->plan, acc, acc, 2 * B, 0, W, true, st);
+    } else {
+        if (!rc) rc = launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st);
+        if (!rc) {
+            const size_t per = B * wn / 2;
+            if (profile_on()) profile_begin(6, B, st);
+            ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn, 0, W, dnum, B);
+            if (profile_on()) profile_end(st);
+            count_launch();
+        }
+        if (!rc) rc = launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st);
     }
-    if (!rc) rc = launch_ntt(c->plan, acc, acc, 2 * B, 0, W, true, st);
     if (addends_ready && cudaStreamWaitEvent(st, addends_ready, 0) != cudaSuccess && !rc) { set_error("key_switch: stream wait failed"); rc = FHE_B200_ECUDA; }
     for (int p = 0; p < 2 && !rc; p++) {
         const uint64_t* s = acc + (size_t)p * B * wn;
@@ -715,15 +746,21 @@ static int multiply_half(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d
         STEP(lincomb_launch(c->q2r, v, n, B, st));
     }
     // 2. NTT over Q u R, 3. tensor, 4. INTT
-    STEP(launch_ntt(c->plan, ext, ext, planes * B, 0, A, false, st));
-    if (!rc) {
-        const size_t per = B * an / 2;
-        if (profile_on()) profile_begin(5, B, st);
-        tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per, square ? 0 : 2 * per);
-        if (profile_on()) profile_end(st);
-        count_launch();
+    if (use_fused_tile(c)) {
+        STEP(launch_ntt_pass_a(c->plan, ext, ext, planes * B, 0, A, false, st));
+        STEP(tensor_transform(c, ext, d, B, square, st));
+        STEP(launch_ntt_pass_a(c->plan, d, d, 3 * B, 0, A, true, st));
+    } else {
+        STEP(launch_ntt(c->plan, ext, ext, planes * B, 0, A, false, st));
+        if (!rc) {
+            const size_t per = B * an / 2;
+            if (profile_on()) profile_begin(5, B, st);
+            tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per, square ? 0 : 2 * per);
+            if (profile_on()) profile_end(st);
+            count_launch();
+        }
+        STEP(launch_ntt(c->plan, d, d, 3 * B, 0, A, true, st));
     }
-    STEP(launch_ntt(c->plan, d, d, 3 * B, 0, A, true, st));
     // 5. round(t/Q .) in basis R, 6. exact conversion R -> Q
     if (!rc) { LcView v; v.in = d; v.in_stride = an; v.extra = d + ln; v.extra_stride = an; v.out = sR; v.out_stride = rn; rc = lincomb_launch(c->scale, v, n, 3 * B, st); }
     if (!rc) { LcView v; v.in = sR; v.in_stride = rn; v.out = sc; v.out_stride = ln; rc = lincomb_launch(c->r2q, v, n, 3 * B, st); }
@@ -761,6 +798,7 @@ static int multiply_one_split(fhe_b200_bfv* c, const uint64_t* d_a, const uint64
     uint64_t* ext = ws; uint64_t* d = ext + 4 * an; uint64_t* sR = d + 3 * an; uint64_t* sc = sR + 3 * rn; uint64_t* dig = sc + 3 * ln;
     uint64_t* acc = dig + (size_t)dnum * wn;
     int rc = 0;
+    const bool fused = use_fused_tile(c);
     auto extend = [&](int p0, cudaStream_t s) -> int {                 // planes p0, p0 + 1: exact Q -> R (Q limbs written through), forward NTT
         for (int p = p0; p < p0 + 2; p++) {
             const uint64_t* src = (p < 2 ? d_a : d_b) + (size_t)(p & 1) * ln;
@@ -768,11 +806,13 @@ static int multiply_one_split(fhe_b200_bfv* c, const uint64_t* d_a, const uint64
             LcView v; v.in = src; v.in_stride = 2 * ln; v.out = dst + ln; v.out_stride = an; v.copy_out = dst; v.copy_stride = an;
             FHE_TRY(lincomb_launch(c->q2r, v, n, 1, s));
         }
+        if (fused) return launch_ntt_pass_a(c->plan, ext + (size_t)p0 * an, ext + (size_t)p0 * an, 2, 0, A, false, s);
         return launch_ntt(c->plan, ext + (size_t)p0 * an, ext + (size_t)p0 * an, 2, 0, A, false, s);
     };
     auto descale = [&](uint32_t p0, uint32_t cnt, cudaStream_t s) -> int {      // planes [p0, p0 + cnt) of the tensor: INTT, round(t/Q .), R -> Q
         uint64_t* dp = d + (size_t)p0 * an;
-        FHE_TRY(launch_ntt(c->plan, dp, dp, cnt, 0, A, true, s));
+        if (fused) FHE_TRY(launch_ntt_pass_a(c->plan, dp, dp, cnt, 0, A, true, s));
+        else FHE_TRY(launch_ntt(c->plan, dp, dp, cnt, 0, A, true, s));
         { LcView v; v.in = dp; v.in_stride = an; v.extra = dp + ln; v.extra_stride = an; v.out = sR + (size_t)p0 * rn; v.out_stride = rn;
           FHE_TRY(lincomb_launch(c->scale, v, n, cnt, s)); }
         { LcView v; v.in = sR + (size_t)p0 * rn; v.in_stride = rn; v.out = sc + (size_t)p0 * ln; v.out_stride = ln;
@@ -786,7 +826,8 @@ static int multiply_one_split(fhe_b200_bfv* c, const uint64_t* d_a, const uint64
     if (!square) { rc = extend(2, sx); cudaEventRecord(c->mul_ev[0], sx); }
     if (!rc) rc = extend(0, st);
     if (!square) cudaStreamWaitEvent(st, c->mul_ev[0], 0);
-    if (!rc) {
+    if (!rc && fused) rc = tensor_transform(c, ext, d, 1, square, st);
+    else if (!rc) {
         const size_t per = an / 2;
         if (profile_on()) profile_begin(5, 1, st);
         tensor_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)d, (const ulonglong2*)ext, prm, c->logn, 0, A, per, square ? 0 : 2 * per);
@@ -878,7 +919,7 @@ extern "C" int fhe_b200_bfv_galoiskeygen(fhe_b200_bfv* c, uint64_t seed, uint32_
     for (uint32_t d = 0; d < c->dnum; d++) {
         uint64_t* b = d_gk + (size_t)(2 * d) * wn; uint64_t* a = b + wn;
         const uint64_t base = 1024ull * (d + 1);
-        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, base + 512, 0, c->d_cdt, c->cdt_len);
+        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, -1, base + 512, 0, c->d_cdt, c->cdt_len);
         FHE_LAUNCH_CHECK();
         FHE_TRY(launch_ntt(c->plan, b, b, 1, 0, W, false, st));
         sample_uniform_kernel<<<grid_for(c, wn), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base);

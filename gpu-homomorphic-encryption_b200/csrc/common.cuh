@@ -108,6 +108,22 @@ int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, u
 // inverse transform of [batch][limb_count][N] whose tile pass runs in place on d_buf and whose column pass scatters the result
 int launch_ntt_inverse_scatter(fhe_b200_plan* plan, uint64_t* d_buf, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,
                                const BalScatter& scatter, cudaStream_t st);
+// Fused tile passes of the BFV multiply (ntt_fused.cu): forward tile pass of the operands, pointwise work, inverse tile pass of the
+// results in one kernel.  The operands must have been through the forward COLUMN pass (launch_ntt_pass_a), the results still need
+// the inverse column pass (launch_ntt_pass_a with inverse = true, or the scatter form).  Element offsets: operand p of ciphertext b,
+// buffer limb l (plan limb limb_begin + l) at in + in_plane[p] + b * in_poly + l * N.
+struct FusedTile {
+    uint64_t* out = nullptr; const uint64_t* in = nullptr;
+    uint32_t limb_begin = 0, limb_count = 0, nb = 0;
+    size_t in_plane[4] = {0, 0, 0, 0}, in_poly = 0, out_plane[3] = {0, 0, 0}, out_poly = 0;
+    const uint64_t* key = nullptr; size_t key_poly = 0; uint32_t dnum = 0;     // inner product: key polynomial (d, c) at key + (2d + c) * key_poly + l * N
+    bool square = false;                                                       // tensor product of a ciphertext with itself: operands 0, 1 only
+};
+bool fused_tile_supported(const fhe_b200_plan* plan, uint32_t dnum);
+int launch_fused_tile(fhe_b200_plan* plan, int mode, const FusedTile& t, cudaStream_t st);
+// one pass of the balanced transform on its own: the column pass (first log N - 8 stages forward; last inverse) of [batch][limb_count][N]
+int launch_ntt_pass_a(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,
+                      bool inverse, cudaStream_t st, const BalScatter* scatter = nullptr);
 int launch_negacyclic_mul_fused(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, uint32_t batch,
                                 uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
 int check_range(const fhe_b200_plan* plan, uint32_t batch, uint32_t limb_begin, uint32_t limb_count);

@@ -240,7 +240,11 @@ FHE_HD u64 mix64(u64 z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
-FHE_HD u64 rng_key(u64 seed, u64 stream) { return mix64(seed + 0x9E3779B97F4A7C15ULL * (stream + 1)); }
+// Domain separation (so that no two of call seed, batch item, stream, index can alias): the seed is hashed BEFORE the stream offset is
+// added, and the seed of batch item b of a call is a hash of (call seed, b) in a domain of its own -- consecutive or G-spaced caller
+// seeds, consecutive streams and consecutive batch items all land on unrelated keys.
+FHE_HD u64 rng_key(u64 seed, u64 stream) { return mix64(mix64(seed) + 0x9E3779B97F4A7C15ULL * (stream + 1)); }
+FHE_HD u64 rng_item_seed(u64 seed, u64 item) { return mix64(mix64(seed ^ 0x6A09E667F3BCC909ULL) + 0x9E3779B97F4A7C15ULL * (item + 1)); }
 FHE_HD u64 rng_at(u64 key, u64 idx) { return mix64(key + 0x9E3779B97F4A7C15ULL * (idx + 1)); }
 
 }  // namespace fhe_b200

@@ -158,8 +158,11 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
 }
 
 #ifndef FHE_BAL_EXPERIMENT          // (tools/sass/balexp.cu instantiates single kernels for SASS accounting)
+int launch_ntt_bal_passes(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
+                          uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st, const BalScatter* scatter,
+                          bool only_a);
 template <int KA, int HB, bool NEAR>
-static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st, const BalScatter* scatter) {
+static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st, const BalScatter* scatter, bool only_a) {
     using A = BalA<KA, HB, NEAR>;
     static PerDeviceOnce attr_once;
     if (attr_once.need(plan->device)) {
@@ -198,15 +201,18 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
         bal_a_kernel<KA, HB, NEAR, false><<<grid_a, 256, kBalASmem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
+        if (only_a) return 0;
         if (prof) profile_begin(0, pls, st);
         bal_b_kernel<KA, HB, NEAR, false><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
     } else {
-        if (prof) profile_begin(1, pls, st);
-        bal_b_kernel<KA, HB, NEAR, true><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
-        if (prof) profile_end(st);
-        FHE_LAUNCH_CHECK();
+        if (!only_a) {
+            if (prof) profile_begin(1, pls, st);
+            bal_b_kernel<KA, HB, NEAR, true><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
+            if (prof) profile_end(st);
+            FHE_LAUNCH_CHECK();
+        }
         if (prof) profile_begin(3, pls, st);
         if (scatter) bal_a_scatter_kernel<KA, HB, NEAR><<<grid_a, 256, kBalASmem, st>>>(a, *scatter);
         else bal_a_kernel<KA, HB, NEAR, true><<<grid_a, 256, kBalASmem, st>>>(a);
@@ -217,12 +223,12 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
 }
 
 template <int HB, bool NEAR>
-static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cudaStream_t st, const BalScatter* scatter) {
+static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cudaStream_t st, const BalScatter* scatter, bool only_a) {
     switch (plan->logn) {
-        case 13: return run_bal_chunk<5, HB, NEAR>(plan, a, inverse, st, scatter);
-        case 14: return run_bal_chunk<6, HB, NEAR>(plan, a, inverse, st, scatter);
-        case 15: return run_bal_chunk<7, HB, NEAR>(plan, a, inverse, st, scatter);
-        case 16: return run_bal_chunk<8, HB, NEAR>(plan, a, inverse, st, scatter);
+        case 13: return run_bal_chunk<5, HB, NEAR>(plan, a, inverse, st, scatter, only_a);
+        case 14: return run_bal_chunk<6, HB, NEAR>(plan, a, inverse, st, scatter, only_a);
+        case 15: return run_bal_chunk<7, HB, NEAR>(plan, a, inverse, st, scatter, only_a);
+        case 16: return run_bal_chunk<8, HB, NEAR>(plan, a, inverse, st, scatter, only_a);
     }
     set_error("balanced NTT: unsupported ring degree 2^%u", plan->logn);
     return FHE_B200_EINVAL;
@@ -231,6 +237,12 @@ static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cud
 // chunk = buffer limbs [l0, l0+nl) x polynomials [b0, b0+nb) of a [batch][limb_count][n] buffer
 int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
                    uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st, const BalScatter* scatter) {
+    return launch_ntt_bal_passes(plan, d_out, d_in, limb_begin, limb_count, l0, nl, b0, nb, inverse, st, scatter, false);
+}
+
+int launch_ntt_bal_passes(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
+                          uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st, const BalScatter* scatter,
+                          bool only_a) {
     BalArgs a;
     a.out = d_out; a.in = d_in;
     a.tw = inverse ? plan->d_inv : plan->d_fwd;
@@ -239,9 +251,24 @@ int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, u
     a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin;
     a.l0 = l0; a.nl = nl; a.b0 = b0; a.nb = nb;
     a.m_items = 1; a.ctas_per_limb = 1; a.groups = 1;
-    return plan->near60 ? dispatch_bal<16, true>(plan, a, inverse, st, scatter)
-         : plan->hb == 16 ? dispatch_bal<16, false>(plan, a, inverse, st, scatter)
-                          : dispatch_bal<8, false>(plan, a, inverse, st, scatter);
+    return plan->near60 ? dispatch_bal<16, true>(plan, a, inverse, st, scatter, only_a)
+         : plan->hb == 16 ? dispatch_bal<16, false>(plan, a, inverse, st, scatter, only_a)
+                          : dispatch_bal<8, false>(plan, a, inverse, st, scatter, only_a);
+}
+
+// the column pass alone (the fused tile kernels of ntt_fused.cu do the rest): forward in -> out; inverse in place on d_out
+// (or scattered).  Limbs in groups of at most 256 (grid size), all polynomials in one launch.
+int launch_ntt_pass_a(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,
+                      bool inverse, cudaStream_t st, const BalScatter* scatter) {
+    FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
+    FHE_REQUIRE(plan->bal, "column pass: needs the balanced two-pass NTT (2^13 <= N <= 2^16)");
+    if (batch == 0 || limb_count == 0) return 0;
+    DeviceGuard dev_guard(plan->device);
+    for (uint32_t l0 = 0; l0 < limb_count; l0 += 256) {
+        const uint32_t nl = l0 + 256 <= limb_count ? 256 : limb_count - l0;
+        FHE_TRY(launch_ntt_bal_passes(plan, d_out, d_in, limb_begin, limb_count, l0, nl, 0, batch, inverse, st, scatter, true));
+    }
+    return 0;
 }
 
 int launch_ntt_inverse_scatter(fhe_b200_plan* plan, uint64_t* d_buf, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,

@@ -155,6 +155,31 @@ struct BalB {
         for (int k = 0; k < 8; k++)
             st2(s + (row | ((k ^ (lane & 7)) << 1)), normalize<HB, NEAR, BE>(x[2 * k], q), normalize<HB, NEAR, BE>(x[2 * k + 1], q));
     }
+    // forward round 2 with the sixteen canonical results left in registers (the lane's own row of the exchange buffer in,
+    // nothing written): the fused tile kernels (ntt_fused.cu) go on to the pointwise work from here
+    template <int B0>
+    static FHE_HD void fwd_phase2_regs(u32 lane, const u64* s, const Twiddle* sb, const LimbParams& P, u64 (&x)[16]) {
+        const u64 q = P.q;
+        row_load(lane, s, x);
+        constexpr int B1 = fwd_bound_after(B0, 4, HB, NEAR);
+        constexpr int BE = fwd_bound_after(B1, 4, HB, NEAR);
+        fwd_stages<4, 4, HB, NEAR, B1>(x, TwB2{sb, lane}, P);
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = normalize<HB, NEAR, BE>(x[e], q);
+    }
+    // the lane's own row (16 consecutive elements of the tile pair: lane * 16 ..) of a warp buffer
+    static FHE_HD void row_load(u32 lane, const u64* s, u64 (&x)[16]) {
+        const u32 row = lane << 4;
+#pragma unroll
+        for (int k = 0; k < 8; k++) ld2(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
+    }
+    static FHE_HD void row_store(u32 lane, u64* s, const u64 (&x)[16]) {
+        const u32 row = lane << 4;
+#pragma unroll
+        for (int k = 0; k < 8; k++) st2(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
+    }
+    // chunk k (elements 2k, 2k+1) of the lane's own row
+    static FHE_HD u64* row_chunk(u32 lane, u64* s, int k) { return s + ((lane << 4) | (((u32)k ^ (lane & 7)) << 1)); }
     static FHE_HD void fwd_phase3(u32 lane, u64* g, const u64* s) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -170,6 +195,11 @@ struct BalB {
             const u32 c = lane + 32 * i;
             u64 a, b; ldg2(g + 2 * c, a, b); st2(s + 2 * chunk_pos(c), a, b);
         }
+    }
+    // inverse round 1 on a row that is already in registers (canonical values); the result goes to the lane's own row of s
+    static FHE_HD void inv_phase2_regs(u32 lane, u64 (&x)[16], u64* s, const Twiddle* sb, const LimbParams& P) {
+        inv_stages<4, 4, HB, NEAR, false, 1>(x, TwB2{sb, lane}, P);
+        row_store(lane, s, x);
     }
     static FHE_HD void inv_phase2(u32 lane, u64* s, const Twiddle* sb, const LimbParams& P) {
         u64 x[16];

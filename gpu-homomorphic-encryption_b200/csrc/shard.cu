@@ -404,17 +404,25 @@ extern "C" int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* s, const uint
     FHE_TRY(shard_wait(s, 0, st));
     // own limbs: NTT, tensor product, inverse NTT whose last pass hands every coefficient block to its owner
     const uint32_t planes = square ? 2 : 4;
-    FHE_TRY(launch_ntt(c->plan, ext, ext, planes * B, ab, ca, false, st));
-    {
+    const bool fused = !(getenv("FHE_B200_FUSED_TILE") && atoi(getenv("FHE_B200_FUSED_TILE")) == 0);
+    BalScatter bs; memset(&bs, 0, sizeof(bs));
+    for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_d2);
+    bs.log_blocks = (uint32_t)s->logw; bs.limbs_total = A; bs.limb_off = ab; bs.nc = nc;
+    if (fused && fused_tile_supported(c->plan, dnum)) {
+        // column pass, then one kernel for tile pass x4 + tensor product + inverse tile pass x3, then the scattering column pass
+        FHE_TRY(launch_ntt_pass_a(c->plan, ext, ext, planes * B, ab, ca, false, st));
+        FusedTile t; t.in = ext; t.out = dl; t.limb_begin = ab; t.limb_count = ca; t.nb = B; t.square = square;
+        const size_t cn = (size_t)ca * N;
+        t.in_plane[0] = 0; t.in_plane[1] = cn; t.in_plane[2] = 2 * (size_t)B * cn; t.in_plane[3] = (2 * (size_t)B + 1) * cn; t.in_poly = 2 * cn;
+        t.out_plane[0] = 0; t.out_plane[1] = cn; t.out_plane[2] = 2 * cn; t.out_poly = 3 * cn;
+        FHE_TRY(launch_fused_tile(c->plan, 0, t, st));
+        FHE_TRY(launch_ntt_pass_a(c->plan, dl, dl, 3 * B, ab, ca, true, st, &bs));
+    } else {
+        FHE_TRY(launch_ntt(c->plan, ext, ext, planes * B, ab, ca, false, st));
         const size_t per = (size_t)B * ca * N / 2;
         shard_tensor_kernel<<<shard_grid(c, per), 256, 0, st>>>((ulonglong2*)dl, (const ulonglong2*)ext, prm, c->logn, ab, ca, B,
                                                                 square ? 0 : (size_t)B * 2 * ca * N / 2);
         FHE_LAUNCH_CHECK();
-    }
-    {
-        BalScatter bs; memset(&bs, 0, sizeof(bs));
-        for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_d2);
-        bs.log_blocks = (uint32_t)s->logw; bs.limbs_total = A; bs.limb_off = ab; bs.nc = nc;
         FHE_TRY(launch_ntt_inverse_scatter(c->plan, dl, 3 * B, ab, ca, bs, st));
     }
     FHE_TRY(shard_signal(s, 1, false, st));
@@ -432,17 +440,23 @@ extern "C" int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* s, const uint
     FHE_TRY(shard_signal(s, 2, false, st));
     FHE_TRY(shard_wait(s, 2, st));
     // own key limbs: NTT of the digits, inner product with the key slice, inverse NTT with the scattering last pass
-    FHE_TRY(launch_ntt(c->plan, dig, dig, dnum * B, wb, cw, false, st));
-    {
+    for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_acc2);
+    bs.limbs_total = W; bs.limb_off = wb;
+    if (fused && fused_tile_supported(c->plan, dnum)) {
+        FHE_TRY(launch_ntt_pass_a(c->plan, dig, dig, dnum * B, wb, cw, false, st));
+        FusedTile t; t.in = dig; t.out = accl; t.limb_begin = wb; t.limb_count = cw; t.nb = B; t.dnum = dnum;
+        const size_t cn = (size_t)cw * N;
+        for (uint32_t d = 0; d < dnum; d++) t.in_plane[d] = (size_t)d * cn;
+        t.in_poly = (size_t)dnum * cn; t.out_plane[0] = 0; t.out_plane[1] = cn; t.out_poly = 2 * cn;
+        t.key = d_key; t.key_poly = cn;
+        FHE_TRY(launch_fused_tile(c->plan, 1, t, st));
+        FHE_TRY(launch_ntt_pass_a(c->plan, accl, accl, 2 * B, wb, cw, true, st, &bs));
+    } else {
+        FHE_TRY(launch_ntt(c->plan, dig, dig, dnum * B, wb, cw, false, st));
         const size_t per = (size_t)B * cw * N / 2;
         shard_ks_inner_kernel<<<shard_grid(c, per), 256, 0, st>>>((ulonglong2*)accl, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn,
                                                                   wb, cw, dnum, B);
         FHE_LAUNCH_CHECK();
-    }
-    {
-        BalScatter bs; memset(&bs, 0, sizeof(bs));
-        for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_acc2);
-        bs.log_blocks = (uint32_t)s->logw; bs.limbs_total = W; bs.limb_off = wb; bs.nc = nc;
         FHE_TRY(launch_ntt_inverse_scatter(c->plan, accl, 2 * B, wb, cw, bs, st));
     }
     FHE_TRY(shard_signal(s, 3, false, st));

@@ -297,7 +297,12 @@ private:
         dst = src; src.components.clear();
     }
     void init_rng(uint64_t seed) { seed_ = seed; }
-    uint64_t next_seed() { seed_ += 0x9E3779B97F4A7C15ull; return seed_; }
+    // a hashed call counter: call k of this context gets mix(base seed, k); the library hashes the seed again per stream / batch item
+    uint64_t next_seed() {
+        uint64_t z = seed_ + 0x9E3779B97F4A7C15ull * ++calls_;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
     static uint256_t mul_small(const uint256_t& a, uint64_t m) {
         uint256_t r; unsigned __int128 c = 0;
         for (int i = 0; i < 4; i++) { c += (unsigned __int128)a.limbs[i] * m; r.limbs[i] = (uint64_t)c; c >>= 64; }
@@ -312,7 +317,7 @@ private:
     fhe_b200_bfv* ctx_ = nullptr;
     cudaStream_t stream_ = nullptr;
     int device_ = 0;
-    uint64_t seed_ = 0;
+    uint64_t seed_ = 0, calls_ = 0;
     detail::DeviceBuf scratch_;
 };
 

@@ -54,6 +54,11 @@ uint64_t fhe_b200_launch_count(void);
 int fhe_b200_profile_enable(int on);
 int fhe_b200_profile_read(int kind, uint64_t* launches, double* total_ms, uint64_t* limb_transforms);
 
+/* Integer-pipe peaks of `device`, measured now (csrc/peaks.cu): thread-level operations per second of IMAD (mad.lo.u32) and of
+ * IMAD.WIDE (mul.wide.u32) over the whole chip, best of `reps` launches each.  The butterfly of the transforms is bound by this
+ * pipe, and bench.py uses the two figures as its roofline denominators.  Synchronous; nothing in the reference corresponds. */
+int fhe_b200_measure_int_peaks(int device, double* imad_lo_ops, double* imad_wide_ops, int reps);
+
 /* ---- plan: N, the RNS moduli and their device-resident twiddle tables ------------------------------------
  * replaces NTTEngine::NTTEngine / precompute_twiddle_factors / find_primitive_root / mod_inverse
  * (src/ntt.cu:7-22,77-119) and RNS_NTTEngine::RNS_NTTEngine (src/ntt.cu:122-141).
@@ -165,7 +170,8 @@ int fhe_b200_bfv_keygen(fhe_b200_bfv* ctx, uint64_t seed_sk, uint64_t seed_pk, u
                         void* stream);
 /* FHEContext::relinkey_gen (src/fhe.cu:76-111) */
 int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* ctx, uint64_t seed, const uint64_t* d_sk, uint64_t* d_rlk, void* stream);
-/* FHEContext::encrypt (src/fhe.cu:138-169); batch plaintexts [batch][N] -> ciphertexts [batch][2][L][N]; ciphertext b uses seed + b */
+/* FHEContext::encrypt (src/fhe.cu:138-169); batch plaintexts [batch][N] -> ciphertexts [batch][2][L][N]; ciphertext b is batch item b
+ * of the call: its generator seed is a hash of (seed, b), see DESIGN.md "Randomness" */
 int fhe_b200_bfv_encrypt(fhe_b200_bfv* ctx, uint64_t seed, const uint64_t* d_pt, const uint64_t* d_pk,
                          uint64_t* d_ct, uint32_t batch, void* stream);
 /* FHEContext::decrypt (src/fhe.cu:171-185) */

@@ -33,6 +33,32 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+_NATIVE_LIB = os.path.join(_HERE, "_native", "liboracle_native.so")
+
+
+def build_native() -> str | None:
+    """The same sources compiled with -O3 -march=native ON THE MACHINE THAT RUNS THEM (bench.py's CPU baseline legs call this on
+    the GPU box; the file is neither committed nor shipped, since the build container's CPU may differ).  None if it fails."""
+    try:
+        os.makedirs(os.path.dirname(_NATIVE_LIB), exist_ok=True)
+        srcs = [os.path.join(_HERE, f) for f in ("orc_ntt.c", "orc_rns.c", "orc_bfv.c")]
+        subprocess.check_call(["/usr/bin/gcc", "-O3", "-march=native", "-funroll-loops", "-fopenmp", "-fPIC", "-std=gnu11", "-shared",
+                               "-o", _NATIVE_LIB] + srcs + ["-lm"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return _NATIVE_LIB
+    except Exception:
+        return None
+
+
+def use_native() -> bool:
+    """switch this process to the -march=native build (call before the first oracle call); False if it could not be built"""
+    global _LIB_PATH, _lib
+    path = build_native()
+    if not path:
+        return False
+    _LIB_PATH, _lib = path, None
+    return True
+
+
 _REF_ROOT = "/root/reference"
 _REF_LIB = os.path.join(_HERE, "_ref", "libref_kernels.so")
 
@@ -94,6 +120,9 @@ def lib():
         L.orc_inv_general.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_rng.restype = C.c_uint64
         L.orc_rng.argtypes = [C.c_uint64] * 3
+        for f in ("orc_rng_key_of", "orc_item_seed_of"):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_uint64] * 2
         L.orc_is_prime.argtypes = [C.c_uint64]
         L.orc_prime_chain.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, u64p]
         L.orc_ntt_tables.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, u64p, u64p]
@@ -204,6 +233,15 @@ def bitrev_perm(n: int) -> np.ndarray:
     for b in range(lg):
         r |= ((idx >> b) & 1) << (lg - 1 - b)
     return r
+
+
+def rng_key(seed: int, stream: int) -> int:
+    return int(lib().orc_rng_key_of(C.c_uint64(seed & (2**64 - 1)), C.c_uint64(stream & (2**64 - 1))))
+
+
+def item_seed(seed: int, item: int) -> int:
+    """seed of batch item `item` of a call seeded with `seed` (specification shared with the CUDA samplers)"""
+    return int(lib().orc_item_seed_of(C.c_uint64(seed & (2**64 - 1)), C.c_uint64(item)))
 
 
 class RnsNtt:
@@ -390,9 +428,10 @@ class Bfv:
         pt[: v.size] = v % np.uint64(self.t)
         return pt
 
-    def encrypt(self, seed, pt, pk):
+    def encrypt(self, seed, pt, pk, item=0):
+        """batch item `item` of an encrypt call seeded with `seed` (fhe_b200_bfv_encrypt: ciphertext b of the batch is item b)"""
         ct = np.zeros((2, self.L, self.n), np.uint64)
-        lib().orc_bfv_encrypt(C.c_void_p(self.h), C.c_uint64(seed), _p(_u64(pt)), _p(pk.reshape(-1)),
+        lib().orc_bfv_encrypt(C.c_void_p(self.h), C.c_uint64(item_seed(seed, item)), _p(_u64(pt)), _p(pk.reshape(-1)),
                               C.c_uint32(self.thr), _p(self.cdt), len(self.cdt), _p(ct.reshape(-1)))
         return ct
 

@@ -59,9 +59,15 @@ static inline u64 orc_mix64(u64 z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
+/* key(seed, stream) = mix64(mix64(seed) + G (stream + 1)): the seed is hashed before the stream offset is added, so G-spaced or
+ * consecutive seeds and consecutive streams cannot alias;  word idx = mix64(key + G (idx + 1)). */
+static inline u64 orc_rng_key(u64 seed, u64 stream) { return orc_mix64(orc_mix64(seed) + 0x9E3779B97F4A7C15ULL * (stream + 1)); }
 static inline u64 orc_rng64(u64 seed, u64 stream, u64 idx) {
-    u64 k = orc_mix64(seed + 0x9E3779B97F4A7C15ULL * (stream + 1));
-    return orc_mix64(k + 0x9E3779B97F4A7C15ULL * (idx + 1));
+    return orc_mix64(orc_rng_key(seed, stream) + 0x9E3779B97F4A7C15ULL * (idx + 1));
+}
+/* seed of batch item `item` of a call seeded with `seed` (a domain of its own) */
+static inline u64 orc_item_seed(u64 seed, u64 item) {
+    return orc_mix64(orc_mix64(seed ^ 0x6A09E667F3BCC909ULL) + 0x9E3779B97F4A7C15ULL * (item + 1));
 }
 
 #endif

@@ -229,20 +229,30 @@ void orc_rns_tables(u64 *tables, const u64 *moduli, u32 limbs, u32 n) {
         }
     }
 }
+/* Harvey's lazy butterflies (values kept in [0, 4q) forward / [0, 2q) inverse, one full reduction at the end): the form a tuned
+ * CPU library uses, so that the reported CPU baseline is not handicapped by per-butterfly conditional corrections.  q < 2^61. */
+static inline u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {          /* x*w mod q + {0, q}, for any 64-bit x */
+    u64 h = (u64)(((u128)x * ws) >> 64);
+    return x * w - h * q;
+}
 static void fwd_shoup(u64 *a, u32 n, u64 q, const u64 *w, const u64 *ws) {
+    const u64 q2 = 2 * q;
     u32 t = n >> 1;
     for (u32 m = 1; m < n; m <<= 1, t >>= 1)
         for (u32 i = 0; i < m; i++) {
             u64 W = w[m + i], Ws = ws[m + i];
             u64 *x = a + 2 * (size_t)i * t, *y = x + t;
             for (u32 j = 0; j < t; j++) {
-                u64 u = x[j], v = shoup_mul(y[j], W, Ws, q);
-                u64 s = u + v; x[j] = s >= q ? s - q : s;
-                y[j] = u >= v ? u - v : u + q - v;
+                u64 u = x[j]; u = u >= q2 ? u - q2 : u;
+                u64 v = shoup_lazy(y[j], W, Ws, q);
+                x[j] = u + v;
+                y[j] = u + q2 - v;
             }
         }
+    for (u32 j = 0; j < n; j++) { u64 u = a[j]; u = u >= q2 ? u - q2 : u; a[j] = u >= q ? u - q : u; }
 }
 static void inv_shoup(u64 *a, u32 n, u64 q, const u64 *w, const u64 *ws) {
+    const u64 q2 = 2 * q;
     u32 t = 1;
     for (u32 m = n >> 1; m >= 1; m >>= 1, t <<= 1)
         for (u32 i = 0; i < m; i++) {
@@ -250,12 +260,12 @@ static void inv_shoup(u64 *a, u32 n, u64 q, const u64 *w, const u64 *ws) {
             u64 *x = a + 2 * (size_t)i * t, *y = x + t;
             for (u32 j = 0; j < t; j++) {
                 u64 u = x[j], v = y[j];
-                u64 s = u + v; x[j] = s >= q ? s - q : s;
-                y[j] = shoup_mul(u >= v ? u - v : u + q - v, W, Ws, q);
+                u64 s = u + v; x[j] = s >= q2 ? s - q2 : s;
+                y[j] = shoup_lazy(u + q2 - v, W, Ws, q);
             }
         }
     u64 ninv = orc_invmod_prime(n % q, q), ninvs = (u64)((((u128)ninv) << 64) / q);
-    for (u32 j = 0; j < n; j++) a[j] = shoup_mul(a[j], ninv, ninvs, q);
+    for (u32 j = 0; j < n; j++) { u64 r = shoup_lazy(a[j], ninv, ninvs, q); a[j] = r >= q ? r - q : r; }
 }
 /* returns the number of OpenMP threads used */
 int orc_rns_ntt_batch(u64 *data, const u64 *tables, const u64 *moduli, u32 limbs, u32 n, u32 batch, int inverse, int threads) {
@@ -289,3 +299,5 @@ u64 orc_mul_mod(u64 a, u64 b, u64 q) { return orc_mulmod(a % q, b % q, q); }
 u64 orc_pow_mod(u64 a, u64 e, u64 q) { return orc_powmod(a, e, q); }
 u64 orc_inv_mod(u64 a, u64 q) { return orc_invmod_prime(a, q); }
 u64 orc_rng(u64 seed, u64 stream, u64 idx) { return orc_rng64(seed, stream, idx); }
+u64 orc_rng_key_of(u64 seed, u64 stream) { return orc_rng_key(seed, stream); }
+u64 orc_item_seed_of(u64 seed, u64 item) { return orc_item_seed(seed, item); }

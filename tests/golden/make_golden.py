@@ -59,7 +59,57 @@ def cases():
     return out
 
 
+def mix64(z):
+    z = z.astype(np.uint64)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def config3_input(chain, polys=64, limbs=32, n=1 << 16):
+    """BASELINE config 3 input uint64[polys][limbs][n]: x = mix64(0x5EED0003 + flat index) mod q_limb (host formula, so that the GPU
+    test and the oracle transform the very same gigabyte)"""
+    x = np.empty((polys, limbs, n), dtype=np.uint64)
+    j = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for b in range(polys):
+            for l in range(limbs):
+                x[b, l] = mix64(np.uint64(0x5EED0003) + np.uint64((b * limbs + l) * n) + j) % np.uint64(chain[l])
+    return x
+
+
+def slow_cases():
+    """full-size BASELINE configs 3 and 4: the oracle needs a minute and a few GiB here, so these digests are regenerated only on
+    request (python tests/golden/make_golden.py --slow) and checked by the GPU tests, not by the CPU suite."""
+    out = {}
+    chain = oracle.prime_chain(49)
+    x = config3_input(chain)
+    eng = oracle.RnsNtt(1 << 16, chain[:32])
+    flat = x.reshape(-1).copy()
+    eng.run_inplace(flat, 64, False, 0)
+    out["config3/forward_all_64x32"] = {"input": digest(x), "output": digest(flat)}
+    from importlib import import_module
+    p = import_module("fhe_b200.params").bfv_preset("c4")
+    o = oracle.Bfv(p["n"], p["L"], p["R"], p["K"], p["dnum"], p["t"], p["primes"], sigma=p["sigma"], hw=p["hamming_weight"])
+    _, sk = o.secret_keygen(31); pk = o.public_keygen(32, sk); rlk = o.relin_keygen(33, sk)
+    m1 = np.random.default_rng(34).integers(0, p["t"], p["n"], dtype=np.uint64)
+    m2 = np.random.default_rng(35).integers(0, p["t"], p["n"], dtype=np.uint64)
+    c1 = o.encrypt(36, m1, pk); c2 = o.encrypt(37, m2, pk)
+    prod, scaled = o.multiply_relin(c1, c2, rlk, want_scaled=True)
+    out["bfv_c4/sk"] = {"output": digest(sk)}; out["bfv_c4/pk"] = {"output": digest(pk)}; out["bfv_c4/rlk"] = {"output": digest(rlk)}
+    out["bfv_c4/encrypt"] = {"input": digest(m1), "output": digest(c1)}
+    out["bfv_c4/scaled_tensor"] = {"output": digest(scaled)}
+    out["bfv_c4/multiply_relin"] = {"output": digest(prod)}
+    out["bfv_c4/square"] = {"output": digest(o.multiply_relin(c1, c1, rlk))}
+    return out
+
+
 if __name__ == "__main__":
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = os.path.join(here, "golden.json")
     json.dump(cases(), open(p, "w"), indent=1, sort_keys=True)
     print("wrote", p)
+    if "--slow" in sys.argv:
+        p = os.path.join(here, "golden_slow.json")
+        json.dump(slow_cases(), open(p, "w"), indent=1, sort_keys=True)
+        print("wrote", p)

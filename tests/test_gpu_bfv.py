@@ -119,10 +119,10 @@ def test_bfv_keys_encrypt_decrypt_add_vs_oracle(fhe, oracle, preset, hw):
     m = rng.integers(0, t, (3, n), dtype=np.uint64)
     m[0, :4] = [5, 10, 15, 20]; m[0, 4:] = 0            # tests/test_fhe.cu:201
     m[1, :4] = [3, 6, 9, 12]; m[1, 4:] = 0              # tests/test_fhe.cu:202
-    ct = g.encrypt(500, to_device(m), pk)               # ciphertext b uses seed 500+b
+    ct = g.encrypt(500, to_device(m), pk)               # ciphertext b is batch item b of the call seeded 500
     h = to_host(ct)
     for b in range(3):
-        assert np.array_equal(h[b], o.encrypt(500 + b, m[b], opk)), b
+        assert np.array_equal(h[b], o.encrypt(500, m[b], opk, item=b)), b
     assert np.array_equal(to_host(g.decrypt(ct, sk)), m)
     s = g.add(ct[0:1].contiguous(), ct[1:2].contiguous())
     assert np.array_equal(to_host(s)[0], o.add(h[0], h[1]))
@@ -132,9 +132,11 @@ def test_bfv_keys_encrypt_decrypt_add_vs_oracle(fhe, oracle, preset, hw):
     assert [int(v) for v in g.decode(g.decrypt(g.encrypt(7, pt, pk), sk))[0, :4]] == [42, 100, 255, 1337]
 
 
-@pytest.mark.parametrize("preset", ["small", "c2"])
+@pytest.mark.parametrize("preset", ["small", "c2", "mid"])
 def test_bfv_multiply_relin_vs_oracle(fhe, oracle, preset):
-    """BASELINE.json config 2 (preset c2): every ciphertext word equals the oracle's; decrypts to the negacyclic product."""
+    """BASELINE.json config 2 (preset c2): every ciphertext word equals the oracle's; decrypts to the negacyclic product.
+    Preset mid (N = 8192) runs the two-pass transform, i.e. the fused tile kernels (tensor product and key-switch inner product
+    inside the tile passes, csrc/ntt_fused.cu)."""
     from fhe_b200.engine import to_device, to_host
     p, g, o = _setup(fhe, oracle, preset)
     n, t = p["n"], p["t"]
@@ -187,6 +189,48 @@ def test_bfv_config4_properties(fhe, oracle):
     assert np.array_equal(to_host(g.decrypt(out2, sk))[0], _exact_product_mod_t(oracle, m12, m2, t, q0))
     s = g.add(ca, cb)
     assert np.array_equal(to_host(g.decrypt(s, sk))[0], (m1 + m2) % np.uint64(t))
+
+
+def test_bfv_config4_every_word_vs_oracle_and_committed_digests(fhe, oracle):
+    """BASELINE.json config 4 at FULL size, word for word: keys, a ciphertext, the scaled tensor and the relinearised product equal
+    the oracle's (run here, ~10 s of host time) and the digests committed in tests/golden/golden_slow.json; the squaring path and
+    the separate (unfused) tensor / inner-product kernels give the same words."""
+    import hashlib, json, os
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, "c4")
+    n, t = p["n"], p["t"]
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_slow.json")))
+    dg = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint64).tobytes()).hexdigest()
+    sk, pk = g.keygen(31, 32); rlk = g.relinkey_gen(33, sk)
+    _, osk = o.secret_keygen(31); opk = o.public_keygen(32, osk); orlk = o.relin_keygen(33, osk)
+    assert np.array_equal(to_host(sk), osk) and np.array_equal(to_host(pk), opk) and np.array_equal(to_host(rlk), orlk)
+    assert dg(osk) == gold["bfv_c4/sk"]["output"] and dg(opk) == gold["bfv_c4/pk"]["output"] and dg(orlk) == gold["bfv_c4/rlk"]["output"]
+    m1 = np.random.default_rng(34).integers(0, t, n, dtype=np.uint64); m2 = np.random.default_rng(35).integers(0, t, n, dtype=np.uint64)
+    c1 = g.encrypt(36, to_device(m1[None]), pk); c2 = g.encrypt(37, to_device(m2[None]), pk)
+    h1, h2 = to_host(c1)[0], to_host(c2)[0]
+    assert np.array_equal(h1, o.encrypt(36, m1, opk)) and dg(h1) == gold["bfv_c4/encrypt"]["output"]
+    out, sc = g.multiply(c1, c2, rlk, want_scaled=True)
+    eo, es = o.multiply_relin(h1, h2, orlk, want_scaled=True)
+    assert np.array_equal(to_host(sc)[0], es) and dg(es) == gold["bfv_c4/scaled_tensor"]["output"]
+    assert np.array_equal(to_host(out)[0], eo) and dg(eo) == gold["bfv_c4/multiply_relin"]["output"]
+    assert dg(to_host(g.multiply(c1, c1, rlk))[0]) == gold["bfv_c4/square"]["output"]
+    # batch of three (halves of 2 and 1 on two streams) gives the same words per ciphertext
+    c3a = torch.cat([c1, c2, c1]); c3b = torch.cat([c2, c1, c1])
+    o3 = to_host(g.multiply(c3a, c3b, rlk))
+    assert np.array_equal(o3[0], eo) and np.array_equal(o3[1], eo) and dg(o3[2]) == gold["bfv_c4/square"]["output"]
+    os.environ["FHE_B200_FUSED_TILE"] = "0"            # the separate tensor / inner-product kernels (read at every call)
+    try:
+        lib = fhe.load_library()
+        l0 = lib.fhe_b200_launch_count()
+        out_sep = g.multiply(c1, c2, rlk)
+        sep = lib.fhe_b200_launch_count() - l0
+    finally:
+        del os.environ["FHE_B200_FUSED_TILE"]
+    l0 = lib.fhe_b200_launch_count()
+    out_fused = g.multiply(c1, c2, rlk)
+    fused = lib.fhe_b200_launch_count() - l0
+    assert torch.equal(out_sep, out) and torch.equal(out_fused, out)
+    assert fused < sep, (fused, sep)
 
 
 def test_limb_sharded_building_blocks_single_rank(fhe, oracle):
@@ -247,7 +291,7 @@ def test_plain_ops_and_batch_encoding_vs_oracle(fhe, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("preset", ["small", "c2"])
+@pytest.mark.parametrize("preset", ["small", "c2", "mid"])
 def test_galois_and_mod_switch_vs_oracle(fhe, oracle, preset):
     """'next' rows: Galois keys, automorphisms (rotate_rows / rotate_columns) and mod_switch_to_next, bit for bit
     against the oracle (keys, rotated ciphertexts, switched ciphertexts) and by definition after decryption."""

@@ -348,6 +348,26 @@ def test_config3_full_size_properties(fhe, oracle, chain):
 
 
 @pytest.mark.gpu
+def test_config3_whole_forward_output_digest(fhe, oracle, chain):
+    """BASELINE.json config 3: SHA-256 of the WHOLE forward output (2048 limb-polynomials, 1 GiB) equals the digest the oracle
+    produced once (tests/golden/make_golden.py --slow, committed in golden_slow.json) -- every word pinned, not a sample."""
+    import hashlib, importlib.util, json, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "golden_slow.json")))["config3/forward_all_64x32"]
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    x = mg.config3_input(chain)
+    assert mg.digest(x) == gold["input"]
+    plan = fhe.Plan(1 << 16, chain[:32])
+    d = torch.from_numpy(x.view(np.int64)).cuda()
+    plan.forward(d)
+    y = d.cpu().numpy().view(np.uint64)
+    assert hashlib.sha256(y.tobytes()).hexdigest() == gold["output"]
+    plan.inverse(d)
+    assert np.array_equal(d.cpu().numpy().view(np.uint64), x)
+
+
+@pytest.mark.gpu
 def test_two_devices_in_one_process(fhe, oracle):
     """plans, conversions and BFV contexts on two GPUs of one process (the C ABI takes a device ordinal): function attributes
     such as the dynamic shared-memory limit are per device.  Skipped on a single-GPU box."""

@@ -100,7 +100,9 @@ def test_samplers(oracle):
         return z ^ (z >> 31)
     G = 0x9E3779B97F4A7C15
     for seed, st, idx in [(0, 0, 0), (12345, 3, 99), (2**63, 1024, 2**40)]:
-        assert oracle.rng64(seed, st, idx) == mix(mix(seed + G * (st + 1)) + G * (idx + 1))
+        assert oracle.rng64(seed, st, idx) == mix(mix(mix(seed) + G * (st + 1)) + G * (idx + 1))
+        assert oracle.rng_key(seed, st) == mix(mix(seed) + G * (st + 1))
+        assert oracle.item_seed(seed, st) == mix(mix(seed ^ 0x6A09E667F3BCC909) + G * (st + 1))
     q = 0xFFFFFFFFFFC0001
     a = oracle.sample_uniform(8, q, 5, 16)
     for j in range(8):
@@ -348,3 +350,43 @@ def test_mod_switch_to_level_is_repeated_drop_and_still_decrypts(oracle):
         lo = oracle.Bfv(n, L - drop, p["R"], p["K"], 1, t, primes, sigma=p["sigma"], hw=p["hamming_weight"])
         _, lsk = lo.secret_keygen(5)
         assert np.array_equal(lo.decrypt(low, lsk), m)
+
+
+def test_generator_keys_never_alias_across_calls_items_and_streams(oracle):
+    """with key = mix64(seed + G (stream + 1)) a caller stepping its seed by G (the compat layer did) made
+    (seed_k, stream s) collide with (seed_k+1, stream s-1), and encrypt's seed + b made consecutive seeds overlap.  The keys are now
+    mix64(mix64(seed) + G (stream + 1)) with batch items in a domain of their own: every (call, item, stream) of a
+    keygen / relinkeygen / galoiskeygen / encrypt x k sequence must get its own key -- for G-spaced seeds and for consecutive seeds."""
+    G = 0x9E3779B97F4A7C15
+    L, W, dnum = 24, 32, 3
+    for step in (G, 1):
+        keys = {}
+
+        def use(tag, seed, stream):
+            k = oracle.rng_key(seed, stream)
+            assert k not in keys, (tag, keys[k])
+            keys[k] = tag
+
+        seed = 12345
+        calls = []
+        for call in range(40):
+            seed = (seed + step) & (2**64 - 1)
+            calls.append(seed)
+        it = iter(calls)
+        s_sk, s_pk, s_rlk, s_gk = next(it), next(it), next(it), next(it)
+        for st in (0, 1):
+            use(("sk", st), s_sk, st)
+        use(("pk_e",), s_pk, 2)
+        for i in range(L):
+            use(("pk_a", i), s_pk, 16 + i)
+        for name, sd in (("rlk", s_rlk), ("gk", s_gk)):
+            for d in range(dnum):
+                use((name, "e", d), sd, 1024 * (d + 1) + 512)
+                for i in range(W):
+                    use((name, "a", d, i), sd, 1024 * (d + 1) + i)
+        for call, sd in enumerate(it):                     # encrypt calls of batch 8
+            for b in range(8):
+                for st in (0, 1, 2):
+                    use(("enc", call, b, st), oracle.item_seed(sd, b), st)
+    # the old derivation would have failed this: (seed, stream s) == (seed + G, stream s - 1)
+    assert oracle.rng_key(7, 1) != oracle.rng_key((7 + G) & (2**64 - 1), 0)
