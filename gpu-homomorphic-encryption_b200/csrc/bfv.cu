@@ -252,11 +252,14 @@ __global__ void __launch_bounds__(256) ks_inner_kernel(ulonglong2* __restrict__ 
     }
 }
 
-// The tensor product and the key-switch inner product run inside the tile passes (ntt_fused.cu) wherever the two-pass transform is
-// in use (2^13 <= N <= 2^16) and there are at most three digits; FHE_B200_FUSED_TILE=0 keeps the separate kernels (tests, A/B runs).
+// FHE_B200_FUSED_TILE=1: the tensor product and the key-switch inner product run inside the tile passes (ntt_fused.cu; two-pass
+// transform, at most three digits).  Bit-identical, six launches fewer per multiply, and MEASURED SLOWER on the B200 (config 4,
+// batch 8: 1 303 against 1 474 multiplies/s): every kernel here is bound by the integer pipe, so the HBM round
+// trip the fusion removes was already hidden, while three 4 KiB buffers per warp plus both twiddle blocks leave one CTA of 8 warps
+// per SM and nothing for the other stream's conversion kernel to co-run with.  Hence opt-in; read at every call.
 static bool use_fused_tile(const fhe_b200_bfv* c) {
     const char* e = getenv("FHE_B200_FUSED_TILE");
-    if (e && atoi(e) == 0) return false;
+    if (!e || atoi(e) == 0) return false;
     return fused_tile_supported(c->plan, c->dnum);
 }
 // forward transform, pointwise tensor product, inverse transform of  ext [4][B][A][N] (planes 0..3, or 0..1 when squaring)  ->  d [3][B][A][N]

@@ -141,6 +141,21 @@ struct BalB {
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz((t << 8) | (e << 4) | j)] = x[e];
     }
+    // forward round 1 on a tile pair that a bulk copy has landed in s in natural order; the exchange layout overwrites it in place
+    // (every lane has read its sixteen inputs before any lane stores: the warp barrier in the middle)
+    template <int B0>
+    static FHE_HD void fwd_phase1_inplace(u32 lane, u64* s, const Twiddle* sb, const LimbParams& P) {
+        const u32 t = lane >> 4, j = lane & 15;
+        u64 x[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = s[(t << 8) | (e << 4) | j];
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        fwd_stages<4, 4, HB, NEAR, B0>(x, TwB1{sb + t * 16}, P);
+#pragma unroll
+        for (int e = 0; e < 16; e++) s[swz((t << 8) | (e << 4) | j)] = x[e];
+    }
     template <int B0>
     static FHE_HD void fwd_phase2(u32 lane, u64* s, const Twiddle* sb, const LimbParams& P) {
         u64 x[16];

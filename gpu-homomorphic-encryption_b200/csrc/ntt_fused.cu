@@ -33,32 +33,40 @@ struct FusedArgs {
     uint32_t dnum, square;
 };
 
-template <int PAIRS, int GROUPS> struct FusedCfg {
+// NBUF buffers of 4 KiB per warp: 4 = every operand of the tensor product has its own (batch >= 2: 8 warps, 192 KiB per CTA);
+// 3 = the fourth operand stays in registers (one ciphertext: 8 tile pairs per CTA, 224 KiB)
+template <int PAIRS, int GROUPS, int NBUF> struct FusedCfg {
     static constexpr int kWarps = PAIRS * GROUPS;
-    static constexpr size_t kBufBytes = (size_t)kWarps * 3 * 512 * sizeof(u64);
+    static constexpr size_t kBufBytes = (size_t)kWarps * NBUF * 512 * sizeof(u64);
     static constexpr size_t kTwBytes = (size_t)PAIRS * 2 * 512 * sizeof(Twiddle);
-    static constexpr size_t kSmem = kBufBytes + kTwBytes + PAIRS * 16;
+    static constexpr size_t kSmem = kBufBytes + kTwBytes + (PAIRS + 2 * kWarps) * 16;
 };
 
-// MODE 0: tensor product, MODE 1: key-switch inner product
-template <int KA, int HB, bool NEAR, int PAIRS, int GROUPS, int MODE>
+// MODE 0: tensor product, MODE 1: key-switch inner product.
+// The operands' tile pairs (4 KiB contiguous each) are fetched by bulk copies (TMA) straight into the warp's buffers: one exposed
+// load latency per ciphertext instead of one per operand, and no registers held across it.
+template <int KA, int HB, bool NEAR, int PAIRS, int GROUPS, int NBUF, int MODE>
 __global__ void __launch_bounds__(32 * PAIRS * GROUPS, 1) bal_fused_kernel(const FusedArgs a) {
     using B = BalB<HB, NEAR>;
-    using Cfg = FusedCfg<PAIRS, GROUPS>;
+    using Cfg = FusedCfg<PAIRS, GROUPS, NBUF>;
     extern __shared__ __align__(128) unsigned char raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pl_local = warp % PAIRS, gl = warp / PAIRS;
-    u64* buf = reinterpret_cast<u64*>(raw) + (size_t)warp * 3 * 512;
+    u64* buf = reinterpret_cast<u64*>(raw) + (size_t)warp * NBUF * 512;
     Twiddle* sbf = reinterpret_cast<Twiddle*>(raw + Cfg::kBufBytes) + (size_t)pl_local * 1024;
     Twiddle* sbi = sbf + 512;
     uint64_t* bars = reinterpret_cast<uint64_t*>(raw + Cfg::kBufBytes + Cfg::kTwBytes);
-    uint64_t* bar = bars + pl_local * 2;
+    uint64_t* bar = bars + pl_local * 2;                               // twiddle blocks of the pair
+    uint64_t* wbar0 = bars + 2 * PAIRS + warp * 4;                     // this warp's operand copies
+    uint64_t* wbar1 = wbar0 + 2;
     constexpr uint32_t pairs = 1u << (KA - 1), pair_blocks = pairs / PAIRS;
     const uint32_t gblocks = (a.groups + GROUPS - 1) / GROUPS;
     const uint32_t pb = blockIdx.x % pair_blocks, r = blockIdx.x / pair_blocks, gb = r % gblocks, limb = r / gblocks;
     const uint32_t pair = pb * PAIRS + pl_local, grp = gb * GROUPS + gl;
     const uint32_t pl = a.limb_begin + limb;
     if (threadIdx.x < PAIRS) mbar_init(bars + threadIdx.x * 2, 1);
+    if (lane == 0) { mbar_init(wbar0, 1); mbar_init(wbar1, 1); }
+    __syncthreads();
     if (threadIdx.x == 0) mbar_fence_init();
     __syncthreads();
     if (gl == 0 && lane == 0) {
@@ -70,33 +78,51 @@ __global__ void __launch_bounds__(32 * PAIRS * GROUPS, 1) bal_fused_kernel(const
     const LimbParams P = a.params[pl];
     const size_t limb_off = (size_t)limb * a.n + (size_t)pair * 512;
     constexpr int B0 = BalA<KA, HB, NEAR>::fwd_out_bound();
+    constexpr uint32_t kTile = 512 * sizeof(u64);
     u64* b0 = buf; u64* b1 = buf + 512; u64* b2 = buf + 1024;
-    mbar_wait(bar, 0);
+    uint32_t par0 = 0, par1 = 0;
+    bool first = true;
 #pragma unroll 1
     for (uint32_t ct = grp; ct < a.nb; ct += a.groups) {
         const uint64_t* in = a.in + (size_t)ct * a.in_poly + limb_off;
         uint64_t* out = a.out + (size_t)ct * a.out_poly + limb_off;
-        u64 x[16];
         if (MODE == 0) {
-            u64 y[16];                                   // the operand that stays in registers: b1 (a1 when squaring)
-            if (!a.square) {
+            const bool sq = a.square != 0;
+            const int staged = sq ? 2 : (NBUF == 4 ? 4 : 2);          // operands fetched now; with three buffers b0 follows b1 through b2
+            if (lane == 0) {
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(wbar0, staged * kTile);
+                for (int p = 0; p < staged; p++) bulk_copy_g2s(buf + p * 512, in + a.in_plane[p], kTile, wbar0);
+            }
+            u64 y[16];                                              // three buffers: b1 (a1 when squaring) stays in registers
+            if (NBUF == 3 && !sq) {
+                u64 x[16];
                 B::fwd_load(lane, in + a.in_plane[3], x);
+                if (first) mbar_wait(bar, 0);
                 B::template fwd_phase1<B0>(lane, x, b2, sbf, P);
                 __syncwarp();
                 B::template fwd_phase2_regs<B0>(lane, b2, sbf, P, y);
                 __syncwarp();
-                B::fwd_load(lane, in + a.in_plane[2], x);
-                B::template fwd_phase1<B0>(lane, x, b2, sbf, P);
+                if (lane == 0) {
+                    fence_proxy_async_smem();
+                    mbar_arrive_expect_tx(wbar1, kTile);
+                    bulk_copy_g2s(b2, in + a.in_plane[2], kTile, wbar1);
+                }
+            } else if (first) mbar_wait(bar, 0);
+            mbar_wait(wbar0, par0); par0 ^= 1;
+            B::template fwd_phase1_inplace<B0>(lane, b0, sbf, P);
+            B::template fwd_phase1_inplace<B0>(lane, b1, sbf, P);
+            if (!sq) {
+                if (NBUF == 3) { mbar_wait(wbar1, par1); par1 ^= 1; }
+                B::template fwd_phase1_inplace<B0>(lane, b2, sbf, P);
+                if (NBUF == 4) B::template fwd_phase1_inplace<B0>(lane, buf + 3 * 512, sbf, P);
             }
-            B::fwd_load(lane, in + a.in_plane[0], x);
-            B::template fwd_phase1<B0>(lane, x, b0, sbf, P);
-            B::fwd_load(lane, in + a.in_plane[1], x);
-            B::template fwd_phase1<B0>(lane, x, b1, sbf, P);
             __syncwarp();
             B::template fwd_phase2<B0>(lane, b0, sbf, P);
-            if (!a.square) {
+            if (!sq) {
                 B::template fwd_phase2<B0>(lane, b1, sbf, P);
                 B::template fwd_phase2<B0>(lane, b2, sbf, P);
+                if (NBUF == 4) B::template fwd_phase2<B0>(lane, buf + 3 * 512, sbf, P);
             } else {
                 B::template fwd_phase2_regs<B0>(lane, b1, sbf, P, y);
             }
@@ -104,11 +130,12 @@ __global__ void __launch_bounds__(32 * PAIRS * GROUPS, 1) bal_fused_kernel(const
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 u64 *p0 = B::row_chunk(lane, b0, k), *p1 = B::row_chunk(lane, b1, k), *p2 = B::row_chunk(lane, b2, k);
-                u64 a0x, a0y, a1x, a1y, c0x, c0y;
+                u64 a0x, a0y, a1x, a1y, c0x, c0y, c1x, c1y;
                 ld2(p0, a0x, a0y);
-                if (!a.square) { ld2(p1, a1x, a1y); ld2(p2, c0x, c0y); }
-                else { a1x = y[2 * k]; a1y = y[2 * k + 1]; c0x = a0x; c0y = a0y; }
-                const u64 c1x = y[2 * k], c1y = y[2 * k + 1];
+                if (!sq) {
+                    ld2(p1, a1x, a1y); ld2(p2, c0x, c0y);
+                    if (NBUF == 4) ld2(B::row_chunk(lane, buf + 3 * 512, k), c1x, c1y); else { c1x = y[2 * k]; c1y = y[2 * k + 1]; }
+                } else { a1x = y[2 * k]; a1y = y[2 * k + 1]; c0x = a0x; c0y = a0y; c1x = a1x; c1y = a1y; }
                 u64 hi, lo;
                 const u64 r0x = mul_mod(a0x, c0x, P), r0y = mul_mod(a0y, c0y, P);
                 const u64 r2x = mul_mod(a1x, c1x, P), r2y = mul_mod(a1y, c1y, P);
@@ -117,14 +144,18 @@ __global__ void __launch_bounds__(32 * PAIRS * GROUPS, 1) bal_fused_kernel(const
                 st2(p0, r0x, r0y); st2(p1, r1x, r1y); st2(p2, r2x, r2y);
             }
         } else {
-            // digits: all transformed in place in their buffers
-            for (uint32_t d = 0; d < a.dnum; d++) {
-                B::fwd_load(lane, in + a.in_plane[d], x);
-                B::template fwd_phase1<B0>(lane, x, buf + d * 512, sbf, P);
+            const uint64_t* kp = a.key + limb_off + (size_t)lane * 16;
+            if (lane == 0) {
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(wbar0, a.dnum * kTile);
+                for (uint32_t d = 0; d < a.dnum; d++) bulk_copy_g2s(buf + d * 512, in + a.in_plane[d], kTile, wbar0);
             }
+            for (uint32_t d = 0; d < 2 * a.dnum; d++) prefetch_l2(kp + (size_t)d * a.key_poly);      // the lane's 128 bytes of every key polynomial
+            if (first) mbar_wait(bar, 0);
+            mbar_wait(wbar0, par0); par0 ^= 1;
+            for (uint32_t d = 0; d < a.dnum; d++) B::template fwd_phase1_inplace<B0>(lane, buf + d * 512, sbf, P);
             __syncwarp();
             for (uint32_t d = 0; d < a.dnum; d++) B::template fwd_phase2<B0>(lane, buf + d * 512, sbf, P);
-            const uint64_t* kp = a.key + limb_off + (size_t)lane * 16;
 #pragma unroll 2
             for (int k = 0; k < 8; k++) {
                 u64 h0x = 0, l0x = 0, h0y = 0, l0y = 0, h1x = 0, l1x = 0, h1y = 0, l1y = 0;
@@ -140,6 +171,7 @@ __global__ void __launch_bounds__(32 * PAIRS * GROUPS, 1) bal_fused_kernel(const
                 st2(B::row_chunk(lane, b1, k), barrett128(h1x, l1x, P.q, P.mu_hi, P.mu_lo), barrett128(h1y, l1y, P.q, P.mu_hi, P.mu_lo));
             }
         }
+        first = false;
         // inverse tile pass of the results (2 or 3 polynomials), straight from the rows just written
         constexpr int NOUT = MODE == 0 ? 3 : 2;
 #pragma unroll
@@ -154,9 +186,10 @@ __global__ void __launch_bounds__(32 * PAIRS * GROUPS, 1) bal_fused_kernel(const
 template <int KA, int HB, bool NEAR, int MODE>
 static int run_fused(fhe_b200_plan* plan, FusedArgs a, cudaStream_t st) {
     static PerDeviceOnce attr_once;
+    constexpr int NB2 = MODE == 0 ? 4 : 3;           // buffers per warp of the two-group configuration
     if (attr_once.need(plan->device)) {
-        FHE_CUDA(cudaFuncSetAttribute(bal_fused_kernel<KA, HB, NEAR, 4, 2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedCfg<4, 2>::kSmem));
-        FHE_CUDA(cudaFuncSetAttribute(bal_fused_kernel<KA, HB, NEAR, 8, 1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedCfg<8, 1>::kSmem));
+        FHE_CUDA(cudaFuncSetAttribute(bal_fused_kernel<KA, HB, NEAR, 4, 2, NB2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedCfg<4, 2, NB2>::kSmem));
+        FHE_CUDA(cudaFuncSetAttribute(bal_fused_kernel<KA, HB, NEAR, 8, 1, 3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedCfg<8, 1, 3>::kSmem));
     }
     constexpr uint32_t pairs = 1u << (KA - 1);
     const bool prof = profile_on();
@@ -168,11 +201,11 @@ static int run_fused(fhe_b200_plan* plan, FusedArgs a, cudaStream_t st) {
         while (groups + 2 <= a.nb && (uint64_t)ctas * (groups / 2) < (uint64_t)2 * plan->sm_count) groups += 2;
         a.groups = groups;
         const uint32_t grid = a.limb_count * (pairs / 4) * ((groups + 1) / 2);
-        bal_fused_kernel<KA, HB, NEAR, 4, 2, MODE><<<grid, 256, FusedCfg<4, 2>::kSmem, st>>>(a);
+        bal_fused_kernel<KA, HB, NEAR, 4, 2, NB2, MODE><<<grid, 256, FusedCfg<4, 2, NB2>::kSmem, st>>>(a);
     } else {
         a.groups = 1;
         const uint32_t grid = a.limb_count * (pairs / 8);
-        bal_fused_kernel<KA, HB, NEAR, 8, 1, MODE><<<grid, 256, FusedCfg<8, 1>::kSmem, st>>>(a);
+        bal_fused_kernel<KA, HB, NEAR, 8, 1, 3, MODE><<<grid, 256, FusedCfg<8, 1, 3>::kSmem, st>>>(a);
     }
     if (prof) profile_end(st);
     FHE_LAUNCH_CHECK();

@@ -404,7 +404,7 @@ extern "C" int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* s, const uint
     FHE_TRY(shard_wait(s, 0, st));
     // own limbs: NTT, tensor product, inverse NTT whose last pass hands every coefficient block to its owner
     const uint32_t planes = square ? 2 : 4;
-    const bool fused = !(getenv("FHE_B200_FUSED_TILE") && atoi(getenv("FHE_B200_FUSED_TILE")) == 0);
+    const bool fused = getenv("FHE_B200_FUSED_TILE") && atoi(getenv("FHE_B200_FUSED_TILE")) != 0;      // opt-in, see bfv.cu use_fused_tile
     BalScatter bs; memset(&bs, 0, sizeof(bs));
     for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_d2);
     bs.log_blocks = (uint32_t)s->logw; bs.limbs_total = A; bs.limb_off = ab; bs.nc = nc;

@@ -34,4 +34,9 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// orders earlier generic-proxy accesses of shared memory (this thread's, and those it has synchronised with) before later
+// async-proxy writes (bulk copies) to the same addresses
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 }  // namespace fhe_b200

@@ -132,12 +132,15 @@ def test_bfv_keys_encrypt_decrypt_add_vs_oracle(fhe, oracle, preset, hw):
     assert [int(v) for v in g.decode(g.decrypt(g.encrypt(7, pt, pk), sk))[0, :4]] == [42, 100, 255, 1337]
 
 
-@pytest.mark.parametrize("preset", ["small", "c2", "mid"])
-def test_bfv_multiply_relin_vs_oracle(fhe, oracle, preset):
+@pytest.mark.parametrize("preset", ["small", "c2", "mid", "mid-fused"])
+def test_bfv_multiply_relin_vs_oracle(fhe, oracle, preset, monkeypatch):
     """BASELINE.json config 2 (preset c2): every ciphertext word equals the oracle's; decrypts to the negacyclic product.
-    Preset mid (N = 8192) runs the two-pass transform, i.e. the fused tile kernels (tensor product and key-switch inner product
-    inside the tile passes, csrc/ntt_fused.cu)."""
+    Preset mid (N = 8192) runs the two-pass transform; mid-fused the same with the fused tile kernels (tensor product and key-switch
+    inner product inside the tile passes, csrc/ntt_fused.cu, FHE_B200_FUSED_TILE=1)."""
     from fhe_b200.engine import to_device, to_host
+    if preset.endswith("-fused"):
+        monkeypatch.setenv("FHE_B200_FUSED_TILE", "1")
+        preset = preset[:-6]
     p, g, o = _setup(fhe, oracle, preset)
     n, t = p["n"], p["t"]
     sk, pk = g.keygen(21, 22); rlk = g.relinkey_gen(23, sk)
@@ -218,18 +221,20 @@ def test_bfv_config4_every_word_vs_oracle_and_committed_digests(fhe, oracle):
     c3a = torch.cat([c1, c2, c1]); c3b = torch.cat([c2, c1, c1])
     o3 = to_host(g.multiply(c3a, c3b, rlk))
     assert np.array_equal(o3[0], eo) and np.array_equal(o3[1], eo) and dg(o3[2]) == gold["bfv_c4/square"]["output"]
-    os.environ["FHE_B200_FUSED_TILE"] = "0"            # the separate tensor / inner-product kernels (read at every call)
+    lib = fhe.load_library()
+    l0 = lib.fhe_b200_launch_count()
+    out_sep = g.multiply(c1, c2, rlk)
+    sep = lib.fhe_b200_launch_count() - l0
+    os.environ["FHE_B200_FUSED_TILE"] = "1"            # tensor product and inner product inside the tile passes (read at every call)
     try:
-        lib = fhe.load_library()
         l0 = lib.fhe_b200_launch_count()
-        out_sep = g.multiply(c1, c2, rlk)
-        sep = lib.fhe_b200_launch_count() - l0
+        out_fused = g.multiply(c1, c2, rlk)
+        fused = lib.fhe_b200_launch_count() - l0
+        assert dg(to_host(g.multiply(c1, c1, rlk))[0]) == gold["bfv_c4/square"]["output"]
+        o3f = to_host(g.multiply(c3a, c3b, rlk))
     finally:
         del os.environ["FHE_B200_FUSED_TILE"]
-    l0 = lib.fhe_b200_launch_count()
-    out_fused = g.multiply(c1, c2, rlk)
-    fused = lib.fhe_b200_launch_count() - l0
-    assert torch.equal(out_sep, out) and torch.equal(out_fused, out)
+    assert torch.equal(out_sep, out) and torch.equal(out_fused, out) and np.array_equal(o3f, o3)
     assert fused < sep, (fused, sep)
 
 

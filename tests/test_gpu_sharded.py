@@ -55,9 +55,10 @@ def _run(shards, a, b, keys, streams, reps=1):
     return outs
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_virtual_ranks_equal_single_gpu(fhe, world, monkeypatch):
+@pytest.mark.parametrize("world,fused", [(1, "0"), (2, "0"), (4, "0"), (2, "1")])
+def test_virtual_ranks_equal_single_gpu(fhe, world, fused, monkeypatch):
     monkeypatch.setenv("FHE_B200_SHARD_TIMEOUT_MS", "3000")
+    monkeypatch.setenv("FHE_B200_FUSED_TILE", fused)
     B = 2
     p, ctxs, shards, rlk, ca, cb = _setup(fhe, "mid", world, B)
     want = ctxs[0].multiply(ca, cb, rlk)
