@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
         "fhe_b200_shard_info": [_vp] + [C.POINTER(C.c_uint32)] * 6 + [u64p],
         "fhe_b200_shard_slice_key": [_vp, _vp, _vp, _vp],
         "fhe_b200_bfv_multiply_relin_sharded": [_vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp],
+        "fhe_b200_bfv_multiply_relin_sharded_stage": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint32, _vp],
         "fhe_b200_shard_check": [_vp, _vp],
         "fhe_b200_bfv_info": [_vp] + [C.POINTER(C.c_uint32)] * 5 + [u64p],
         "fhe_b200_bfv_plan": [_vp],

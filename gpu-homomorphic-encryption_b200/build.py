@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libfhe_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"
 
-CU_SOURCES = ["ntt_kernels.cu", "ntt_bal.cu", "ntt_fused.cu", "elementwise.cu", "capi.cu", "lincomb.cu", "lincomb_mma.cu", "bfv.cu", "shard.cu", "peaks.cu"]
+CU_SOURCES = ["ntt_kernels.cu", "ntt_bal.cu", "ntt_fused.cu", "elementwise.cu", "capi.cu", "lincomb.cu", "lincomb_mma.cu", "lincomb_tc.cu", "bfv.cu", "shard.cu", "peaks.cu"]
 CPP_SOURCES = ["tables.cpp", "rns_consts.cpp", "wire.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]

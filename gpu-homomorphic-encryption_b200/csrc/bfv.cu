@@ -391,7 +391,7 @@ extern "C" int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t 
     cudaError_t e = cudaMalloc(&c->d_idx, idx.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemcpy(c->d_idx, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     // constants
-    std::vector<uint64_t> cst(L + W + L + kMaxCdt, 0);
+    std::vector<uint64_t> cst(L + W + L + kMaxCdt + L, 0);
     uint64_t q_mod_t = 1 % t;
     for (uint32_t i = 0; i < L; i++) q_mod_t = host::mulmod(q_mod_t, Q[i] % t, t);
     for (uint32_t i = 0; i < L; i++) {
@@ -402,6 +402,7 @@ extern "C" int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t 
         for (uint32_t k = 0; k < K; k++) pm = host::mulmod(pm, P[k] % qi, qi);
         cst[L + i] = pm;                                                           // P mod q_i (0 for the special limbs)
         cst[L + W + i] = host::invmod(pm, qi);                                     // P^-1 mod q_i
+        cst[L + W + L + kMaxCdt + i] = host::shoup(cst[L + W + i], qi);              // its Shoup companion (ModDown epilogue)
     }
     c->h_cdt.resize(kMaxCdt);
     c->cdt_len = host_gaussian_cdt((double)sigma, c->h_cdt.data(), kMaxCdt);
@@ -409,7 +410,7 @@ extern "C" int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t 
     if (e == cudaSuccess) e = cudaMalloc(&c->d_consts, cst.size() * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemcpy(c->d_consts, cst.data(), cst.size() * sizeof(uint64_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("bfv_create: device allocation failed: %s", cudaGetErrorString(e)); fhe_b200_bfv_destroy(c); return FHE_B200_ECUDA; }
-    c->d_delta = c->d_consts; c->d_pmodq = c->d_consts + L; c->d_pinv = c->d_consts + L + W; c->d_cdt = c->d_consts + L + W + L;
+    c->d_delta = c->d_consts; c->d_pmodq = c->d_consts + L; c->d_pinv = c->d_consts + L + W; c->d_cdt = c->d_consts + L + W + L; c->d_pinv_s = c->d_cdt + kMaxCdt;
     c->d_idx_p = c->d_idx;
     for (uint32_t d = 0; d < dnum; d++) { c->d_idx_grp.push_back(c->d_idx + off_grp[d]); c->d_idx_tgt.push_back(c->d_idx + off_tgt[d]); }
 #undef BFV_TRY
@@ -708,7 +709,7 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
     for (int p = 0; p < 2 && !rc; p++) {
         const uint64_t* s = acc + (size_t)p * B * wn;
         LcView v; v.in = s; v.in_stride = wn; v.src_idx = c->d_idx_p;
-        v.sub = s; v.sub_stride = wn; v.epi_scalar = c->d_pinv;
+        v.sub = s; v.sub_stride = wn; v.epi_scalar = c->d_pinv; v.epi_scalar_shoup = c->d_pinv_s;
         v.add = p ? add1 : add0; v.add_stride = p ? add1_stride : add0_stride;
         v.out = d_out + (size_t)p * ln; v.out_stride = 2 * ln;
         rc = lincomb_launch(c->moddown, v, n, B, st);

@@ -13,8 +13,8 @@ struct fhe_b200_bfv {
     fhe_b200_lincomb *q2r = nullptr, *scale = nullptr, *r2q = nullptr, *moddown = nullptr, *dec = nullptr;
     std::vector<fhe_b200_lincomb*> modup;                // [dnum]
     // device constants
-    uint64_t* d_consts = nullptr;                        // delta[L] | p_mod_q[L+K] (0 outside Q) | pinv_mod_q[L] | cdt[128]
-    const uint64_t *d_delta = nullptr, *d_pmodq = nullptr, *d_pinv = nullptr, *d_cdt = nullptr;
+    uint64_t* d_consts = nullptr;                        // delta[L] | p_mod_q[L+K] (0 outside Q) | pinv_mod_q[L] | cdt[128] | Shoup companions of pinv[L]
+    const uint64_t *d_delta = nullptr, *d_pmodq = nullptr, *d_pinv = nullptr, *d_pinv_s = nullptr, *d_cdt = nullptr;
     uint32_t cdt_len = 0;
     std::vector<uint64_t> h_cdt;
     uint32_t* d_idx = nullptr;                           // index maps for the lincomb views

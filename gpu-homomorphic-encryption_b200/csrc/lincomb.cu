@@ -208,6 +208,13 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     a.use_pre = lc->use_pre; a.use_extra = lc->use_extra; a.c_is_one = lc->use_pre ? 0 : 1;
     a.k_per_block = lc->T;
     a.total = (size_t)batch * n;
+    if (lc->use_tc && n % 128 == 0) {
+        const bool prof = profile_on();
+        if (prof) profile_begin(4, (uint64_t)batch * lc->S * lc->T, st);
+        const int rc = lincomb_tc_launch(lc, a.v, n, batch, st);
+        if (prof) profile_end(st);
+        return rc;
+    }
     if (lc->use_mma) {
         const bool prof = profile_on();
         if (prof) profile_begin(4, (uint64_t)batch * lc->S * lc->T, st);
@@ -316,6 +323,30 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
         if (e == cudaSuccess) e = cudaMemcpy(lc->d_bfrag, bf.data(), bf.size() * sizeof(uint2), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { set_error("lincomb: device allocation failed: %s", cudaGetErrorString(e)); cudaFree(lc->d_blob); delete lc; return FHE_B200_ECUDA; }
     }
+    // tcgen05 path: same Toeplitz GEMM, operands in shared memory, accumulators in TMEM
+    lc->use_tc = lc->use_mma && lincomb_tc_smem_bytes(S, T) <= 220 * 1024;
+    if (const char* ev = getenv("FHE_B200_LINCOMB_TC")) lc->use_tc = atoi(ev) != 0 && lincomb_tc_smem_bytes(S, T) <= 220 * 1024;
+    if (lc->use_tc) {
+        lc->tc_mont = !(getenv("FHE_B200_LINCOMB_TC_MONT") && atoi(getenv("FHE_B200_LINCOMB_TC_MONT")) == 0);
+        for (uint32_t k = 0; k < T; k++) lc->tc_mont = lc->tc_mont && (h.dst_mod[k] >> 60) == 0 && h.dst_mod[k] > (1ull << 60) - (1ull << 32);
+        std::vector<uint8_t> bm;
+        lincomb_tc_build_b(h, (S + 3) / 4, lc->tc_mont, bm);
+        e = cudaMalloc(&lc->d_tc_b, bm.size());
+        if (e == cudaSuccess) e = cudaMemcpy(lc->d_tc_b, bm.data(), bm.size(), cudaMemcpyHostToDevice);
+        if (lc->tc_mont) {
+            std::vector<uint64_t> mc(3 * (size_t)T);
+            for (uint32_t k = 0; k < T; k++) {
+                const uint64_t m = h.dst_mod[k];
+                uint64_t inv = m;                                    // Newton: m^-1 mod 2^64 (m odd; correct to 3 bits, doubles every step)
+                for (int it = 0; it < 6; it++) inv *= 2 - m * inv;
+                const uint64_t r64 = (uint64_t)((((unsigned __int128)1) << 64) % m);
+                mc[k] = 0 - inv; mc[T + k] = host::mulmod(h.c[k] % m, r64, m); mc[2 * (size_t)T + k] = host::mulmod(h.lam[k] % m, r64, m);
+            }
+            if (e == cudaSuccess) e = cudaMalloc(&lc->d_tc_mont, mc.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(lc->d_tc_mont, mc.data(), mc.size() * 8, cudaMemcpyHostToDevice);
+        }
+        if (e != cudaSuccess) { set_error("lincomb: device allocation failed: %s", cudaGetErrorString(e)); cudaFree(lc->d_blob); cudaFree(lc->d_bfrag); delete lc; return FHE_B200_ECUDA; }
+    }
     *out = lc;
     return 0;
 }
@@ -373,6 +404,8 @@ extern "C" int fhe_b200_lincomb_destroy(fhe_b200_lincomb* lc) {
     DeviceGuard dev_guard(lc->device);
     cudaFree(lc->d_blob);
     cudaFree(lc->d_bfrag);
+    cudaFree(lc->d_tc_b);
+    cudaFree(lc->d_tc_mont);
     delete lc;
     return 0;
 }

@@ -25,6 +25,14 @@ struct fhe_b200_lincomb {
     uint2* d_bfrag = nullptr;
     uint32_t mma_kt = 0;
     bool use_mma = false;                                       // default when S*T >= 64; FHE_B200_LINCOMB_MMA = 0 | 1 overrides
+    // tcgen05 / TMEM path (lincomb_tc.cu): B operand of the Toeplitz byte GEMM in the canonical shared-memory layout
+    uint8_t* d_tc_b = nullptr;
+    bool use_tc = false;                                        // when the operands fit shared memory; FHE_B200_LINCOMB_TC = 0 | 1 overrides
+    // Montgomery form of the tcgen05 path (every target modulus in (2^60 - 2^32, 2^60)): the matrix, c and lam carry a factor 2^64,
+    // the 128-bit sum is reduced by one Montgomery step (R = 2^64) instead of a 128-bit Barrett reduction.  [3][T]: -m^-1 mod 2^64,
+    // c * 2^64 mod m, lam * 2^64 mod m.  FHE_B200_LINCOMB_TC_MONT = 0 keeps the Barrett epilogue.
+    uint64_t* d_tc_mont = nullptr;
+    bool tc_mont = false;
 };
 
 namespace fhe_b200 {
@@ -40,6 +48,7 @@ struct LcView {
     const uint64_t* add = nullptr; size_t add_stride = 0;
     const uint32_t* epi_idx = nullptr;
     const uint64_t* epi_scalar = nullptr;                                                        // [T] device
+    const uint64_t* epi_scalar_shoup = nullptr;                                                  // [T] device, floor(epi_scalar * 2^64 / m): optional (cheaper product)
     // pass-through: the raw source limbs are also written to copy_out (limb copy_idx[i] of polynomial b at copy_out + b*copy_stride);
     // saves the separate device-to-device copy when the sources are part of the output polynomial (Q limbs next to the R limbs)
     uint64_t* copy_out = nullptr; size_t copy_stride = 0; const uint32_t* copy_idx = nullptr;
@@ -55,6 +64,10 @@ int lincomb_create(const LincombConsts& consts, int device, fhe_b200_lincomb** o
 int lincomb_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
 // tensor-core path; v must have every default (index maps, strides) filled in
 int lincomb_mma_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
+// tcgen05 path; n must be a multiple of 128
+int lincomb_tc_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
+size_t lincomb_tc_smem_bytes(uint32_t S, uint32_t T);
+void lincomb_tc_build_b(const LincombConsts& h, uint32_t KS, bool montgomery, std::vector<uint8_t>& out);
 uint32_t lincomb_mma_pad_kt(uint32_t S);
 void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<uint2>& out);
 

@@ -1,0 +1,349 @@
+// RNS linear combination with the matrix product on the 5th-generation tensor cores: tcgen05.mma.kind::i8, accumulators in TMEM.
+//
+// Same primitive, constants and bits as lincomb_kernel / lincomb_mma_kernel (replaces fast_base_conversion_kernel,
+// /root/reference/include/rns.cuh:116-125): residues and matrix entries are cut into bytes and the matrix is laid out
+// Toeplitz-fashion, so that ONE u8 x u8 -> s32 GEMM yields the partial sums p_c = sum over byte pairs of weight 2^(8c), c = 0..14, of
+// every 128-bit dot product (lincomb_mma.cu explains the decomposition).  What changes is who multiplies:
+//   lincomb_mma_kernel : mma.sync m16n8k32 -- a warp owns 16 coefficients, issues 300 blocking MMAs per tile and holds the
+//                        accumulators in registers; tensor pipe 38-43 % busy, the warp's scalar work waits behind its own MMAs;
+//   this kernel        : a group of four warps owns 128 coefficients (one TMEM lane each).  Every thread prepares the bytes of ITS
+//                        coefficient (x -> x * pre mod s, fixed-point overflow sum) and stores them as one row of the A operand in
+//                        shared memory (canonical K-major core-matrix layout, 16-byte stores, conflict-free); one elected thread
+//                        issues the MMAs (M = 128, N = 16 columns per target, 8 targets per chunk, K = 32 bytes per instruction)
+//                        against the B operand that the CTA keeps in shared memory for its whole life; the accumulators land in
+//                        the group's 128 TMEM columns and tcgen05.commit arrives on an mbarrier; each thread reads the sixteen
+//                        partial sums of a target for its coefficient with one tcgen05.ld (32x32b.x16), assembles the 128-bit
+//                        value, reduces and stores.  The tensor core works on one group's chunk while the other three groups of
+//                        the SM run their scalar work: nothing blocks behind an MMA, and loads / stores are 256 bytes per warp.
+// Persistent CTAs, one per SM: 4 groups x 128 threads, the whole TMEM (4 x 128 columns).
+#include "lincomb.cuh"
+#include "host_math.hpp"
+#include "tma.cuh"
+
+namespace fhe_b200 {
+
+constexpr int kTcGroups = 4;             // warp groups per CTA (each owns 128 TMEM columns)
+constexpr int kTcChunkTargets = 8;       // targets per MMA chunk: 8 x 16 columns = 128
+
+struct LcTcArgs {
+    const u64 *src_mod, *pre, *pre_s, *th_hi, *th_lo;      // [>= S]
+    const u64 *dst_mod, *mu_hi, *mu_lo, *c, *lam;          // [T]
+    const uint8_t* bmat;                                   // B operand, canonical layout per chunk (lincomb_tc_build_b)
+    const u64* mont;                                       // Montgomery form: [3][T] -m^-1 mod 2^64, c 2^64 mod m, lam 2^64 mod m
+    LcView v;
+    uint32_t S, T, KS, logn, use_pre, use_extra, c_is_one; // KS = k-steps of 32 bytes (4 sources each)
+    size_t tiles;                                          // batch * n / 128
+};
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: 8-row x 16-byte core matrices, rows 16 bytes apart;
+// sbo = bytes between 8-row groups, lbo = bytes between the two 16-byte K chunks of one instruction
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) |
+           (1ull << 46);                                   // descriptor version 1 (sm_100), base offset 0, layout type 0 = no swizzle
+}
+// instruction descriptor of kind::i8: D = s32, A = B = u8, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t tc_idesc(uint32_t n) {
+    return (2u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, u32 (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// sum_c p[c] * 2^(8c), c = 0..14 (p[15] = 0), every p[c] < 2^31, as a 128-bit value: see assemble128 in lincomb_mma.cu
+__device__ __forceinline__ void tc_assemble128(const u32 (&p)[16], u64& hi, u64& lo) {
+    u32 v0 = p[0], v1 = p[4], v2 = p[8], v3 = p[12];
+#pragma unroll
+    for (int r = 1; r < 4; r++) {
+        const u32 d0 = p[r], d1 = p[r + 4], d2 = p[r + 8], d3 = (r + 12 < 15) ? p[r + 12] : 0u;
+        const u32 w0 = d0 << (8 * r), w1 = __funnelshift_l(d0, d1, 8 * r), w2 = __funnelshift_l(d1, d2, 8 * r),
+                  w3 = __funnelshift_l(d2, d3, 8 * r);
+        asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, %3, %7;"
+            : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3) : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+    }
+    lo = ((u64)v1 << 32) | v0; hi = ((u64)v3 << 32) | v2;
+}
+
+// shared memory: B operand | A tiles (one per group) | per-source and per-target constants | barriers, TMEM base
+// MONT: every target modulus is in (2^60 - 2^32, 2^60); matrix, c and lam carry a factor 2^64 and the sum V is reduced by
+//   u = V_lo * (-m^-1) mod 2^64,  t = (V + u m) / 2^64 = V_hi + hi64(u m) + [V_lo != 0]  (= V 2^-64 mod m, below 8 m),
+// then one fold of the bits above 2^60 and one conditional subtraction: about twenty instructions against about forty-five of the
+// 128-bit Barrett reduction, and the same canonical residue.
+// KIND: 0 plain conversion, 1 scale-and-round (extra limb, whole integer I added), 2 conversion with the ModDown epilogue,
+//       3 anything else (flags read at run time)
+template <bool MONT, int KIND>
+__global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const LcTcArgs a) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    const uint32_t tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127, warp = tid >> 5, lane = tid & 31;
+    const uint32_t K = a.KS * 32;                                   // bytes of one A row
+    const uint32_t NT = (a.T + kTcChunkTargets - 1) / kTcChunkTargets;    // chunks
+    const size_t b_bytes = (size_t)K * a.T * 16;
+    unsigned char* sB = tc_smem;
+    unsigned char* sA = tc_smem + ((b_bytes + 127) & ~(size_t)127) + (size_t)grp * 128 * K;
+    u64* sC = reinterpret_cast<u64*>(tc_smem + ((b_bytes + 127) & ~(size_t)127) + (size_t)kTcGroups * 128 * K);
+    const uint32_t SP = a.KS * 4;
+    u64* sSrc = sC;                                                 // [5][SP]: modulus, pre, pre', theta hi / lo
+    u64* sOff = sSrc + 5 * SP;                                      // element offset of source limb i inside a polynomial
+    u64* sCpy = sOff + SP;                                          // [2][SP]: pass-through address of source i (polynomial 0), words per polynomial
+    u64* sDst = sCpy + 2 * SP;                                      // [7][T]: modulus, mu_hi (MONT: -m^-1), mu_lo, c, lam, epilogue scalar and its Shoup companion
+    u64* sIdx = sDst + 7 * (size_t)a.T;                             // [4][T]: out address (polynomial 0), extra / epilogue offsets, out words per polynomial
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sIdx + 4 * (size_t)a.T);     // one per group
+    uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + kTcGroups);
+    const size_t nn = (size_t)1 << a.logn;
+
+    {   // stage B and the constants
+        const uint4* src = reinterpret_cast<const uint4*>(a.bmat);
+        uint4* dst = reinterpret_cast<uint4*>(sB);
+        for (size_t i = tid; i < b_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    for (uint32_t i = tid; i < SP; i += blockDim.x) {
+        const bool in = i < a.S;
+        sSrc[i] = in ? a.src_mod[i] : 3; sSrc[SP + i] = in ? a.pre[i] : 0; sSrc[2 * SP + i] = in ? a.pre_s[i] : 0;
+        sSrc[3 * SP + i] = in ? a.th_hi[i] : 0; sSrc[4 * SP + i] = in ? a.th_lo[i] : 0;
+        sOff[i] = in ? (u64)a.v.src_idx[i] * nn : 0;
+        if (in && a.v.copy_out) {
+            if (a.v.copy_tab) { sCpy[SP + i] = a.v.copy_tab[2 * i + 1]; sCpy[i] = a.v.copy_tab[2 * i] + a.v.copy_poly0 * sCpy[SP + i] * 8; }
+            else { sCpy[SP + i] = a.v.copy_stride; sCpy[i] = (u64)(a.v.copy_out + (size_t)a.v.copy_idx[i] * nn); }
+        } else { sCpy[i] = 0; sCpy[SP + i] = 0; }
+    }
+    for (uint32_t k = tid; k < a.T; k += blockDim.x) {
+        sDst[k] = a.dst_mod[k]; sDst[a.T + k] = MONT ? a.mont[k] : a.mu_hi[k]; sDst[2 * a.T + k] = a.mu_lo[k];
+        sDst[3 * a.T + k] = MONT ? a.mont[a.T + k] : a.c[k]; sDst[4 * a.T + k] = MONT ? a.mont[2 * a.T + k] : a.lam[k];
+        sDst[5 * a.T + k] = a.v.epi_scalar ? a.v.epi_scalar[k] : 0; sDst[6 * a.T + k] = a.v.epi_scalar_shoup ? a.v.epi_scalar_shoup[k] : 0;
+        if (a.v.out_tab) { sIdx[3 * a.T + k] = a.v.out_tab[2 * k + 1]; sIdx[k] = a.v.out_tab[2 * k] + a.v.out_poly0 * sIdx[3 * a.T + k] * 8; }
+        else { sIdx[3 * a.T + k] = a.v.out_stride; sIdx[k] = (u64)(a.v.out + (size_t)a.v.dst_idx[k] * nn); }
+        sIdx[a.T + k] = (u64)a.v.extra_idx[k] * nn; sIdx[2 * a.T + k] = (u64)a.v.epi_idx[k] * nn;
+    }
+    if (tid < kTcGroups) mbar_init(bars + tid, 1);
+    if (warp == 0) {                                                // the whole TMEM: 512 columns, 128 per group
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_p)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) mbar_fence_init();
+    fence_proxy_async_smem();                                       // B was written with ordinary stores; the tensor core reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_base_p + grp * 128;               // this group's accumulator columns (lane field 0)
+    const uint32_t tmem_rd = tmem_d + ((warp & 3u) * 32u << 16);    // this warp's 32 lanes
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    uint32_t parity = 0;
+
+#pragma unroll 1
+    for (size_t tile = (size_t)blockIdx.x * kTcGroups + grp; tile < a.tiles; tile += (size_t)gridDim.x * kTcGroups) {
+        const size_t coef = tile * 128 + gtid;
+        const uint32_t b = (uint32_t)(coef >> a.logn);
+        const uint32_t j = (uint32_t)(coef & (nn - 1));
+        const u64* inb = a.v.in + (size_t)b * a.v.in_stride + j;
+
+        // ---- prologue: this coefficient's sources -> bytes of z (row gtid of A), fixed-point sum of z * theta
+        u64 f0 = 0, f1 = 0, f2 = 0;
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < SP; i0 += 8) {
+            u64 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) x[u] = (i0 + u < a.S) ? __ldcg(inb + sOff[i0 + u]) : 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t i = i0 + u;
+                if (i < SP) {
+                    if (i < a.S && a.v.copy_out) reinterpret_cast<u64*>(sCpy[i])[(size_t)b * sCpy[SP + i] + j] = x[u];
+                    if (a.use_pre) x[u] = shoup_mul(x[u], sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
+                    u64 ph, pl;
+                    mul128(x[u], sSrc[3 * SP + i], ph, pl);
+                    add192(f2, f1, f0, ph, pl);
+                    add192(f2, f1, f0, 0, mulhi64(x[u], sSrc[4 * SP + i]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2)
+                if (i0 + u < SP)                                    // sources i, i+1 = K bytes [8i, 8i+16) = K chunk i/2
+                    *reinterpret_cast<ulonglong2*>(sA + (size_t)((i0 + u) >> 1) * 2048 + gtid * 16) = make_ulonglong2(x[u], x[u + 1]);
+        }
+        add192(f2, f1, f0, 0, 1ull << 63);
+        const u64 I_hi = f2, I_lo = f1;
+        fence_proxy_async_smem();                                   // A row visible to the tensor core
+        tc_fence_before();
+        group_barrier(1 + grp);
+
+        // ---- chunks of eight targets: MMA into the group's TMEM columns, then every thread finishes its coefficient
+#pragma unroll 1
+        for (uint32_t ch = 0; ch < NT; ch++) {
+            const uint32_t k0 = ch * kTcChunkTargets;
+            const uint32_t cnt = min((uint32_t)kTcChunkTargets, a.T - k0);
+            const uint32_t ncol = cnt * 16;
+            if (gtid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = tc_idesc(ncol);
+                const uint32_t b_chunk = sB_addr + k0 * 16 * K;     // chunks are stored one after the other: K * 16 bytes per target
+                for (uint32_t ks = 0; ks < a.KS; ks++) {
+                    const uint64_t da = tc_smem_desc(sA_addr + ks * 2 * 2048, 2048, 128);
+                    const uint64_t db = tc_smem_desc(b_chunk + ks * 2 * ncol * 16, ncol * 16, 128);
+                    tc_mma_i8(tmem_d, da, db, idesc, ks > 0 ? 1u : 0u);
+                }
+                tc_commit(bars + grp);
+            }
+            mbar_wait(bars + grp, parity); parity ^= 1;
+            tc_fence_after();
+            // two targets per iteration: their reductions are independent chains, which keeps the four warps of a scheduler issuing
+            const bool use_extra = KIND == 3 ? a.use_extra != 0 : KIND == 1;
+            const bool c_is_one = KIND == 3 ? a.c_is_one != 0 : KIND == 1;
+            const bool has_sub = KIND == 3 ? a.v.sub != nullptr : KIND == 2;
+            auto operands = [&](uint32_t k, u64& ex, u64& su, u64& ad) {
+                ex = 0; su = 0; ad = 0;
+                if (use_extra) ex = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + k] + j];
+                if (has_sub) {
+                    const size_t eo = sIdx[2 * a.T + k] + j;
+                    su = a.v.sub[(size_t)b * a.v.sub_stride + eo];
+                    if (a.v.add) ad = a.v.add[(size_t)b * a.v.add_stride + eo];
+                }
+            };
+            auto finish = [&](uint32_t k, const u32 (&pc)[16], u64 ex, u64 su, u64 ad) {
+                const u64 m = sDst[k], mh = sDst[a.T + k];
+                u64 ah, al;
+                tc_assemble128(pc, ah, al);
+                u64 res;
+                if (MONT) {
+                    const u64 ck = sDst[3 * a.T + k];                // c 2^64 mod m (c = 1 for scale-and-round: the whole integer I is added)
+                    if (c_is_one) { mac128(ah, al, I_lo, ck); ah += I_hi * ck; }
+                    else {                                           // I < 64 (an overflow count): two 32 x 32 products
+                        const u64 t0 = (u64)(u32)I_lo * (u32)ck, t1 = (u64)(u32)I_lo * (u32)(ck >> 32);
+                        add128(ah, al, 0, t0); add128(ah, al, t1 >> 32, t1 << 32);
+                    }
+                    if (use_extra) mac128(ah, al, ex, sDst[4 * a.T + k]);
+                    const u64 u = al * mh;                           // mh = -m^-1 mod 2^64
+                    const u64 t = ah + mulhi64(u, m) + (al != 0 ? 1ull : 0ull);
+                    res = csub(near60_reduce(t, 0 - m), m);
+                } else {
+                    const u64 ml = sDst[2 * a.T + k];
+                    if (c_is_one) add128(ah, al, I_hi, I_lo); else mac128(ah, al, I_lo, sDst[3 * a.T + k]);
+                    if (use_extra) mac128(ah, al, ex, sDst[4 * a.T + k]);
+                    res = barrett128(ah, al, m, mh, ml);
+                }
+                if (has_sub) {
+                    const u64 d = sub_mod(su, res, m);
+                    if (MONT || a.v.epi_scalar_shoup) res = shoup_mul(d, sDst[5 * a.T + k], sDst[6 * a.T + k], m);     // (the launcher insists on the companion when MONT)
+                    else {
+                        u64 ph, pl;
+                        mul128(d, sDst[5 * a.T + k], ph, pl);
+                        res = barrett128(ph, pl, m, mh, sDst[2 * a.T + k]);
+                    }
+                    if (a.v.add) res = add_mod(res, ad, m);
+                }
+                reinterpret_cast<u64*>(sIdx[k])[(size_t)b * sIdx[3 * a.T + k] + j] = res;
+            };
+#pragma unroll 1
+            for (uint32_t tl = 0; tl + 1 < cnt; tl += 2) {
+                const uint32_t k = k0 + tl;
+                u32 p0[16], p1[16];
+                tc_ld16(tmem_rd + tl * 16, p0);
+                tc_ld16(tmem_rd + tl * 16 + 16, p1);
+                u64 ex0, su0, ad0, ex1, su1, ad1;                    // epilogue operands while the TMEM loads are in flight
+                operands(k, ex0, su0, ad0); operands(k + 1, ex1, su1, ad1);
+                tc_wait_ld();
+                finish(k, p0, ex0, su0, ad0);
+                finish(k + 1, p1, ex1, su1, ad1);
+            }
+            if (cnt & 1) {
+                const uint32_t k = k0 + cnt - 1;
+                u32 p0[16];
+                tc_ld16(tmem_rd + (cnt - 1) * 16, p0);
+                u64 ex0, su0, ad0;
+                operands(k, ex0, su0, ad0);
+                tc_wait_ld();
+                finish(k, p0, ex0, su0, ad0);
+            }
+            tc_fence_before();
+            group_barrier(1 + grp);                                 // every thread has read its accumulators: the next chunk may overwrite them
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_base_p) : "memory");
+    }
+}
+
+// host: B operand.  Chunk ch holds targets [8 ch, 8 ch + cnt): column n = tl * 16 + c carries byte (c - a) of M[i][k] in K row i * 8 + a.
+// Canonical K-major layout without swizzle: byte (n, kb) of a chunk at  (kb / 16) * (ncol * 16) + n * 16 + kb % 16.
+void lincomb_tc_build_b(const LincombConsts& h, uint32_t KS, bool montgomery, std::vector<uint8_t>& out) {
+    const uint32_t K = KS * 32;
+    std::vector<uint64_t> M(h.M);
+    if (montgomery)                                                  // entries times 2^64 mod m_k
+        for (uint32_t i = 0; i < h.S; i++)
+            for (uint32_t k = 0; k < h.T; k++) {
+                const uint64_t m = h.dst_mod[k];
+                M[(size_t)i * h.T + k] = host::mulmod(h.M[(size_t)i * h.T + k] % m, (uint64_t)((((unsigned __int128)1) << 64) % m), m);
+            }
+    out.assign((size_t)K * h.T * 16, 0);
+    size_t base = 0;
+    for (uint32_t k0 = 0; k0 < h.T; k0 += kTcChunkTargets) {
+        const uint32_t cnt = std::min<uint32_t>(kTcChunkTargets, h.T - k0), ncol = cnt * 16;
+        for (uint32_t tl = 0; tl < cnt; tl++)
+            for (uint32_t c = 0; c < 15; c++)
+                for (uint32_t kb = 0; kb < K; kb++) {
+                    const uint32_t i = kb / 8, aa = kb % 8;
+                    if (i >= h.S || c < aa || c - aa > 7) continue;
+                    const uint8_t v = (uint8_t)((M[(size_t)i * h.T + k0 + tl] >> (8 * (c - aa))) & 0xff);
+                    out[base + (size_t)(kb / 16) * (ncol * 16) + (size_t)(tl * 16 + c) * 16 + kb % 16] = v;
+                }
+        base += (size_t)K * ncol;
+    }
+}
+
+size_t lincomb_tc_smem_bytes(uint32_t S, uint32_t T) {
+    const uint32_t KS = (S + 3) / 4, K = KS * 32, SP = KS * 4;
+    const size_t b_bytes = (size_t)K * T * 16;
+    return ((b_bytes + 127) & ~(size_t)127) + (size_t)kTcGroups * 128 * K + (size_t)(8 * SP + 11 * T) * sizeof(u64) + kTcGroups * 8 + 16;
+}
+
+int lincomb_tc_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_t batch, cudaStream_t st) {
+    LcTcArgs a;
+    a.src_mod = lc->src_mod; a.pre = lc->pre; a.pre_s = lc->pre_s; a.th_hi = lc->th_hi; a.th_lo = lc->th_lo;
+    a.dst_mod = lc->dst_mod; a.mu_hi = lc->mu_hi; a.mu_lo = lc->mu_lo; a.c = lc->c; a.lam = lc->lam;
+    a.bmat = lc->d_tc_b; a.mont = lc->d_tc_mont;
+    a.v = view;
+    a.S = lc->S; a.T = lc->T; a.KS = (lc->S + 3) / 4; a.logn = host::ilog2(n);
+    a.use_pre = lc->use_pre; a.use_extra = lc->use_extra; a.c_is_one = lc->use_pre ? 0 : 1;
+    a.tiles = (size_t)batch * n / 128;
+    FHE_REQUIRE(!(lc->tc_mont && view.sub && !view.epi_scalar_shoup), "lincomb (tcgen05 path): the fused epilogue needs epi_scalar_shoup");
+    const size_t smem = lincomb_tc_smem_bytes(lc->S, lc->T);
+    static size_t attr_smem[64] = {0};
+    if (smem > attr_smem[lc->device & 63]) {
+#define TC_ATTR(M_, K_) FHE_CUDA(cudaFuncSetAttribute(lincomb_tc_kernel<M_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_ATTR(false, 0) TC_ATTR(false, 1) TC_ATTR(false, 2) TC_ATTR(false, 3) TC_ATTR(true, 0) TC_ATTR(true, 1) TC_ATTR(true, 2) TC_ATTR(true, 3)
+#undef TC_ATTR
+        attr_smem[lc->device & 63] = smem;
+    }
+    const size_t want = (a.tiles + kTcGroups - 1) / kTcGroups;
+    const unsigned grid = (unsigned)(want < (size_t)lc->sm_count ? want : (size_t)lc->sm_count);
+    const int kind = (!a.use_extra && !a.c_is_one && !view.sub) ? 0 : (a.use_extra && a.c_is_one && !view.sub) ? 1
+                   : (!a.use_extra && !a.c_is_one && view.sub) ? 2 : 3;
+#define TC_GO(M_, K_) lincomb_tc_kernel<M_, K_><<<grid, 128 * kTcGroups, smem, st>>>(a)
+    if (lc->tc_mont) { if (kind == 0) TC_GO(true, 0); else if (kind == 1) TC_GO(true, 1); else if (kind == 2) TC_GO(true, 2); else TC_GO(true, 3); }
+    else { if (kind == 0) TC_GO(false, 0); else if (kind == 1) TC_GO(false, 1); else if (kind == 2) TC_GO(false, 2); else TC_GO(false, 3); }
+#undef TC_GO
+    FHE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace fhe_b200

@@ -375,102 +375,138 @@ static inline uint32_t shard_grid(const fhe_b200_bfv* c, size_t items) {
     return (uint32_t)(w < cap ? (w ? w : 1) : cap);
 }
 
+// The multiply as five stages; stage k begins with the wait for phase k-1 and ends with the signal of phase k:
+//   0: Q -> R extension (scattered by limb)                          | signal 0
+//   1: wait 0 | NTT, tensor product, inverse NTT (scattered by coefficient block) | signal 1
+//   2: wait 1 | scale-and-round, R -> Q, ModUp (scattered by limb)               | signal 2
+//   3: wait 2 | NTT, key inner product, inverse NTT (scattered by coefficient block) | signal 3
+//   4: wait 3 | ModDown + add
 // d_a, d_b, d_out: sharded ciphertexts [batch][2][L][Nc]; d_key: this rank's key slice [dnum][2][cW][N]
-extern "C" int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* s, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_key,
-                                                   uint64_t* d_out, uint32_t batch, void* stream) {
-    FHE_REQUIRE(s && d_a && d_b && d_key && d_out, "bfv_multiply_relin_sharded: null argument");
-    FHE_REQUIRE(s->connected, "bfv_multiply_relin_sharded: the shard group is not connected (fhe_b200_shard_connect)");
-    FHE_REQUIRE(batch <= s->max_batch, "bfv_multiply_relin_sharded: batch %u exceeds the group's max_batch %u", batch, s->max_batch);
-    if (!batch) return 0;
+static int sharded_stage(fhe_b200_shard* s, int stage, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_key, uint64_t* d_out,
+                         uint32_t batch, cudaStream_t st) {
     fhe_b200_bfv* c = s->ctx;
-    cudaStream_t st = (cudaStream_t)stream;
-    DeviceGuard dev_guard(c->device);
-    const uint32_t L = c->L, R = c->R, K = c->K, A = L + R, W = L + K, dnum = c->dnum, B = batch, nc = s->nc;
+    const uint32_t L = c->L, R = c->R, A = L + R, W = L + c->K, dnum = c->dnum, B = batch, nc = s->nc;
     const size_t N = c->n, Nc = nc;
     const uint32_t ab = s->a_begin[s->rank], ca = s->a_begin[s->rank + 1] - ab, wb = s->w_begin[s->rank], cw = s->w_begin[s->rank + 1] - wb;
     const LimbParams* prm = c->plan->d_params;
     const bool square = d_a == d_b;
     uint64_t* ext = s->slab + s->off_ext; uint64_t* d2 = s->slab + s->off_d2; uint64_t* dig = s->slab + s->off_dig; uint64_t* acc2 = s->slab + s->off_acc2;
     uint64_t* dl = s->ws + s->off_d; uint64_t* sR = s->ws + s->off_sr; uint64_t* sc = s->ws + s->off_sc; uint64_t* accl = s->ws + s->off_acc;
-
-    // phase 0: exact extension Q -> Q u R of this rank's coefficients; every limb goes to its owner (Q limbs passed through)
-    for (int o = 0; o < (square ? 1 : 2); o++) {
-        LcView v; v.in = o ? d_b : d_a; v.in_stride = (size_t)L * Nc;
-        v.out_tab = s->tab_q2r_out; v.out_poly0 = (size_t)o * 2 * B;
-        v.copy_out = ext; v.copy_tab = s->tab_q2r_copy; v.copy_poly0 = (size_t)o * 2 * B;
-        FHE_TRY(lincomb_launch(c->q2r, v, nc, 2 * B, st));
-    }
-    FHE_TRY(shard_signal(s, 0, true, st));
-    FHE_TRY(shard_wait(s, 0, st));
-    // own limbs: NTT, tensor product, inverse NTT whose last pass hands every coefficient block to its owner
-    const uint32_t planes = square ? 2 : 4;
-    const bool fused = getenv("FHE_B200_FUSED_TILE") && atoi(getenv("FHE_B200_FUSED_TILE")) != 0;      // opt-in, see bfv.cu use_fused_tile
+    const bool fused = getenv("FHE_B200_FUSED_TILE") && atoi(getenv("FHE_B200_FUSED_TILE")) != 0 && fused_tile_supported(c->plan, dnum);   // opt-in, see bfv.cu
     BalScatter bs; memset(&bs, 0, sizeof(bs));
-    for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_d2);
-    bs.log_blocks = (uint32_t)s->logw; bs.limbs_total = A; bs.limb_off = ab; bs.nc = nc;
-    if (fused && fused_tile_supported(c->plan, dnum)) {
-        // column pass, then one kernel for tile pass x4 + tensor product + inverse tile pass x3, then the scattering column pass
-        FHE_TRY(launch_ntt_pass_a(c->plan, ext, ext, planes * B, ab, ca, false, st));
-        FusedTile t; t.in = ext; t.out = dl; t.limb_begin = ab; t.limb_count = ca; t.nb = B; t.square = square;
-        const size_t cn = (size_t)ca * N;
-        t.in_plane[0] = 0; t.in_plane[1] = cn; t.in_plane[2] = 2 * (size_t)B * cn; t.in_plane[3] = (2 * (size_t)B + 1) * cn; t.in_poly = 2 * cn;
-        t.out_plane[0] = 0; t.out_plane[1] = cn; t.out_plane[2] = 2 * cn; t.out_poly = 3 * cn;
-        FHE_TRY(launch_fused_tile(c->plan, 0, t, st));
-        FHE_TRY(launch_ntt_pass_a(c->plan, dl, dl, 3 * B, ab, ca, true, st, &bs));
-    } else {
-        FHE_TRY(launch_ntt(c->plan, ext, ext, planes * B, ab, ca, false, st));
-        const size_t per = (size_t)B * ca * N / 2;
-        shard_tensor_kernel<<<shard_grid(c, per), 256, 0, st>>>((ulonglong2*)dl, (const ulonglong2*)ext, prm, c->logn, ab, ca, B,
-                                                                square ? 0 : (size_t)B * 2 * ca * N / 2);
-        FHE_LAUNCH_CHECK();
-        FHE_TRY(launch_ntt_inverse_scatter(c->plan, dl, 3 * B, ab, ca, bs, st));
+    bs.log_blocks = (uint32_t)s->logw; bs.nc = nc;
+    switch (stage) {
+    case 0:
+        // exact extension Q -> Q u R of this rank's coefficients; every limb goes to its owner (Q limbs passed through)
+        for (int o = 0; o < (square ? 1 : 2); o++) {
+            LcView v; v.in = o ? d_b : d_a; v.in_stride = (size_t)L * Nc;
+            v.out_tab = s->tab_q2r_out; v.out_poly0 = (size_t)o * 2 * B;
+            v.copy_out = ext; v.copy_tab = s->tab_q2r_copy; v.copy_poly0 = (size_t)o * 2 * B;
+            FHE_TRY(lincomb_launch(c->q2r, v, nc, 2 * B, st));
+        }
+        return shard_signal(s, 0, true, st);
+    case 1: {
+        FHE_TRY(shard_wait(s, 0, st));
+        // own limbs: NTT, tensor product, inverse NTT whose last pass hands every coefficient block to its owner
+        const uint32_t planes = square ? 2 : 4;
+        for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_d2);
+        bs.limbs_total = A; bs.limb_off = ab;
+        if (fused) {
+            // column pass, then one kernel for tile pass x4 + tensor product + inverse tile pass x3, then the scattering column pass
+            FHE_TRY(launch_ntt_pass_a(c->plan, ext, ext, planes * B, ab, ca, false, st));
+            FusedTile t; t.in = ext; t.out = dl; t.limb_begin = ab; t.limb_count = ca; t.nb = B; t.square = square;
+            const size_t cn = (size_t)ca * N;
+            t.in_plane[0] = 0; t.in_plane[1] = cn; t.in_plane[2] = 2 * (size_t)B * cn; t.in_plane[3] = (2 * (size_t)B + 1) * cn; t.in_poly = 2 * cn;
+            t.out_plane[0] = 0; t.out_plane[1] = cn; t.out_plane[2] = 2 * cn; t.out_poly = 3 * cn;
+            FHE_TRY(launch_fused_tile(c->plan, 0, t, st));
+            FHE_TRY(launch_ntt_pass_a(c->plan, dl, dl, 3 * B, ab, ca, true, st, &bs));
+        } else {
+            FHE_TRY(launch_ntt(c->plan, ext, ext, planes * B, ab, ca, false, st));
+            const size_t per = (size_t)B * ca * N / 2;
+            shard_tensor_kernel<<<shard_grid(c, per), 256, 0, st>>>((ulonglong2*)dl, (const ulonglong2*)ext, prm, c->logn, ab, ca, B,
+                                                                    square ? 0 : (size_t)B * 2 * ca * N / 2);
+            FHE_LAUNCH_CHECK();
+            FHE_TRY(launch_ntt_inverse_scatter(c->plan, dl, 3 * B, ab, ca, bs, st));
+        }
+        return shard_signal(s, 1, false, st);
     }
-    FHE_TRY(shard_signal(s, 1, false, st));
-    FHE_TRY(shard_wait(s, 1, st));
-    // own coefficients: round(t/Q .) in basis R, exact conversion R -> Q, ModUp of d2 with every key limb going to its owner
-    { LcView v; v.in = d2; v.in_stride = (size_t)A * Nc; v.extra = d2 + (size_t)L * Nc; v.extra_stride = (size_t)A * Nc; v.out = sR; v.out_stride = (size_t)R * Nc;
-      FHE_TRY(lincomb_launch(c->scale, v, nc, 3 * B, st)); }
-    { LcView v; v.in = sR; v.in_stride = (size_t)R * Nc; v.out = sc; v.out_stride = (size_t)L * Nc;
-      FHE_TRY(lincomb_launch(c->r2q, v, nc, 3 * B, st)); }
-    for (uint32_t dg = 0; dg < dnum; dg++) {
-        LcView v; v.in = sc + 2 * (size_t)L * Nc; v.in_stride = 3 * (size_t)L * Nc; v.src_idx = c->d_idx_grp[dg];
-        v.out_tab = s->tab_up_out[dg]; v.copy_out = dig; v.copy_tab = s->tab_up_copy[dg];
-        FHE_TRY(lincomb_launch(c->modup[dg], v, nc, B, st));
+    case 2:
+        FHE_TRY(shard_wait(s, 1, st));
+        // own coefficients: round(t/Q .) in basis R, exact conversion R -> Q, ModUp of d2 with every key limb going to its owner
+        { LcView v; v.in = d2; v.in_stride = (size_t)A * Nc; v.extra = d2 + (size_t)L * Nc; v.extra_stride = (size_t)A * Nc; v.out = sR; v.out_stride = (size_t)R * Nc;
+          FHE_TRY(lincomb_launch(c->scale, v, nc, 3 * B, st)); }
+        { LcView v; v.in = sR; v.in_stride = (size_t)R * Nc; v.out = sc; v.out_stride = (size_t)L * Nc;
+          FHE_TRY(lincomb_launch(c->r2q, v, nc, 3 * B, st)); }
+        for (uint32_t dg = 0; dg < dnum; dg++) {
+            LcView v; v.in = sc + 2 * (size_t)L * Nc; v.in_stride = 3 * (size_t)L * Nc; v.src_idx = c->d_idx_grp[dg];
+            v.out_tab = s->tab_up_out[dg]; v.copy_out = dig; v.copy_tab = s->tab_up_copy[dg];
+            FHE_TRY(lincomb_launch(c->modup[dg], v, nc, B, st));
+        }
+        return shard_signal(s, 2, false, st);
+    case 3:
+        FHE_TRY(shard_wait(s, 2, st));
+        // own key limbs: NTT of the digits, inner product with the key slice, inverse NTT with the scattering last pass
+        for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_acc2);
+        bs.limbs_total = W; bs.limb_off = wb;
+        if (fused) {
+            FHE_TRY(launch_ntt_pass_a(c->plan, dig, dig, dnum * B, wb, cw, false, st));
+            FusedTile t; t.in = dig; t.out = accl; t.limb_begin = wb; t.limb_count = cw; t.nb = B; t.dnum = dnum;
+            const size_t cn = (size_t)cw * N;
+            for (uint32_t d = 0; d < dnum; d++) t.in_plane[d] = (size_t)d * cn;
+            t.in_poly = (size_t)dnum * cn; t.out_plane[0] = 0; t.out_plane[1] = cn; t.out_poly = 2 * cn;
+            t.key = d_key; t.key_poly = cn;
+            FHE_TRY(launch_fused_tile(c->plan, 1, t, st));
+            FHE_TRY(launch_ntt_pass_a(c->plan, accl, accl, 2 * B, wb, cw, true, st, &bs));
+        } else {
+            FHE_TRY(launch_ntt(c->plan, dig, dig, dnum * B, wb, cw, false, st));
+            const size_t per = (size_t)B * cw * N / 2;
+            shard_ks_inner_kernel<<<shard_grid(c, per), 256, 0, st>>>((ulonglong2*)accl, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn,
+                                                                      wb, cw, dnum, B);
+            FHE_LAUNCH_CHECK();
+            FHE_TRY(launch_ntt_inverse_scatter(c->plan, accl, 2 * B, wb, cw, bs, st));
+        }
+        return shard_signal(s, 3, false, st);
+    case 4:
+        FHE_TRY(shard_wait(s, 3, st));
+        // own coefficients: ModDown, added onto (d0, d1)
+        for (int p = 0; p < 2; p++) {
+            const uint64_t* a2 = acc2 + (size_t)p * W * Nc;
+            LcView v; v.in = a2; v.in_stride = 2 * (size_t)W * Nc; v.src_idx = c->d_idx_p;
+            v.sub = a2; v.sub_stride = 2 * (size_t)W * Nc; v.epi_scalar = c->d_pinv; v.epi_scalar_shoup = c->d_pinv_s;
+            v.add = sc + (size_t)p * L * Nc; v.add_stride = 3 * (size_t)L * Nc;
+            v.out = d_out + (size_t)p * L * Nc; v.out_stride = 2 * (size_t)L * Nc;
+            FHE_TRY(lincomb_launch(c->moddown, v, nc, B, st));
+        }
+        FHE_CUDA(cudaGetLastError());
+        return 0;
     }
-    FHE_TRY(shard_signal(s, 2, false, st));
-    FHE_TRY(shard_wait(s, 2, st));
-    // own key limbs: NTT of the digits, inner product with the key slice, inverse NTT with the scattering last pass
-    for (int r = 0; r < s->world; r++) bs.base[r] = (uint64_t)(uintptr_t)(s->peer[r] + s->off_acc2);
-    bs.limbs_total = W; bs.limb_off = wb;
-    if (fused && fused_tile_supported(c->plan, dnum)) {
-        FHE_TRY(launch_ntt_pass_a(c->plan, dig, dig, dnum * B, wb, cw, false, st));
-        FusedTile t; t.in = dig; t.out = accl; t.limb_begin = wb; t.limb_count = cw; t.nb = B; t.dnum = dnum;
-        const size_t cn = (size_t)cw * N;
-        for (uint32_t d = 0; d < dnum; d++) t.in_plane[d] = (size_t)d * cn;
-        t.in_poly = (size_t)dnum * cn; t.out_plane[0] = 0; t.out_plane[1] = cn; t.out_poly = 2 * cn;
-        t.key = d_key; t.key_poly = cn;
-        FHE_TRY(launch_fused_tile(c->plan, 1, t, st));
-        FHE_TRY(launch_ntt_pass_a(c->plan, accl, accl, 2 * B, wb, cw, true, st, &bs));
-    } else {
-        FHE_TRY(launch_ntt(c->plan, dig, dig, dnum * B, wb, cw, false, st));
-        const size_t per = (size_t)B * cw * N / 2;
-        shard_ks_inner_kernel<<<shard_grid(c, per), 256, 0, st>>>((ulonglong2*)accl, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn,
-                                                                  wb, cw, dnum, B);
-        FHE_LAUNCH_CHECK();
-        FHE_TRY(launch_ntt_inverse_scatter(c->plan, accl, 2 * B, wb, cw, bs, st));
-    }
-    FHE_TRY(shard_signal(s, 3, false, st));
-    FHE_TRY(shard_wait(s, 3, st));
-    // own coefficients: ModDown, added onto (d0, d1)
-    for (int p = 0; p < 2; p++) {
-        const uint64_t* a2 = acc2 + (size_t)p * W * Nc;
-        LcView v; v.in = a2; v.in_stride = 2 * (size_t)W * Nc; v.src_idx = c->d_idx_p;
-        v.sub = a2; v.sub_stride = 2 * (size_t)W * Nc; v.epi_scalar = c->d_pinv;
-        v.add = sc + (size_t)p * L * Nc; v.add_stride = 3 * (size_t)L * Nc;
-        v.out = d_out + (size_t)p * L * Nc; v.out_stride = 2 * (size_t)L * Nc;
-        FHE_TRY(lincomb_launch(c->moddown, v, nc, B, st));
-    }
-    (void)K;
-    FHE_CUDA(cudaGetLastError());
+    set_error("bfv_multiply_relin_sharded: stage %d outside [0, 4]", stage);
+    return FHE_B200_EINVAL;
+}
+
+static int sharded_check_args(fhe_b200_shard* s, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_key, uint64_t* d_out, uint32_t batch) {
+    FHE_REQUIRE(s && d_a && d_b && d_key && d_out, "bfv_multiply_relin_sharded: null argument");
+    FHE_REQUIRE(s->connected, "bfv_multiply_relin_sharded: the shard group is not connected (fhe_b200_shard_connect)");
+    FHE_REQUIRE(batch <= s->max_batch, "bfv_multiply_relin_sharded: batch %u exceeds the group's max_batch %u", batch, s->max_batch);
     return 0;
+}
+
+extern "C" int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* s, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_key,
+                                                   uint64_t* d_out, uint32_t batch, void* stream) {
+    FHE_TRY(sharded_check_args(s, d_a, d_b, d_key, d_out, batch));
+    if (!batch) return 0;
+    DeviceGuard dev_guard(s->ctx->device);
+    for (int stage = 0; stage < 5; stage++) FHE_TRY(sharded_stage(s, stage, d_a, d_b, d_key, d_out, batch, (cudaStream_t)stream));
+    return 0;
+}
+
+// One stage of the multiply (0..4, see sharded_stage).  For a host that drives SEVERAL ranks on ONE device (the single-GPU tests):
+// kernels that wait for one another must not be separate launches on one GPU -- nothing guarantees that they run at the same time --
+// so such a host issues stage k for every rank before stage k+1 for any rank, and every wait finds its flags already set.
+extern "C" int fhe_b200_bfv_multiply_relin_sharded_stage(fhe_b200_shard* s, int stage, const uint64_t* d_a, const uint64_t* d_b,
+                                                         const uint64_t* d_key, uint64_t* d_out, uint32_t batch, void* stream) {
+    FHE_TRY(sharded_check_args(s, d_a, d_b, d_key, d_out, batch));
+    if (!batch) return 0;
+    DeviceGuard dev_guard(s->ctx->device);
+    return sharded_stage(s, stage, d_a, d_b, d_key, d_out, batch, (cudaStream_t)stream);
 }

@@ -593,6 +593,12 @@ class BfvShard:
         check(self.lib.fhe_b200_bfv_multiply_relin_sharded(self.h, _ptr(a), _ptr(b), _ptr(key_slice), _ptr(out), batch, _stream()))
         return out
 
+    def multiply_stage(self, stage: int, a, b, key_slice, out):
+        """one stage (0..4) of multiply -- for driving several ranks on one device: stage k for every rank before stage k+1"""
+        batch = a.numel() // (2 * self.ctx.L * self.coeff_count)
+        check(self.lib.fhe_b200_bfv_multiply_relin_sharded_stage(self.h, stage, _ptr(a), _ptr(b), _ptr(key_slice), _ptr(out), batch, _stream()))
+        return out
+
     def check(self):
         check(self.lib.fhe_b200_shard_check(self.h, _stream()))
 

@@ -244,7 +244,8 @@ int fhe_b200_bfv_multiply_relin_host(fhe_b200_bfv* ctx, const uint64_t* h_a, con
  * the producing kernels straight into the peer's buffer over NVLink, ordered by epoch flags (csrc/shard.cu) -- no NCCL call and
  * no host synchronisation on the data path.  Set-up: create on every rank, export the 128-byte handle, carry all handles to
  * every rank in rank order (torch.distributed.all_gather_object, MPI, a pipe ...), connect.  Ranks may be processes (CUDA IPC)
- * or several objects in one process (peer access; also several ranks on ONE device, which is how the single-GPU tests run it).
+ * or several objects in one process (peer access; also several ranks on ONE device, which is how the single-GPU tests run it --
+ * stage by stage, see fhe_b200_bfv_multiply_relin_sharded_stage).
  * Data: sharded ciphertext [batch][2][L][N/world] = the rank's coefficient block of every limb, coefficient form;
  *       key slice [dnum][2][cW][N] = the rank's key limbs (fhe_b200_shard_slice_key).
  * Every rank must issue the same sequence of sharded calls.  A rank whose peer never delivers gives up after
@@ -265,6 +266,11 @@ int fhe_b200_shard_slice_key(const fhe_b200_shard* shard, const uint64_t* d_key,
 /* FHEContext::multiply + relinearize (src/fhe.cu:199-235) on sharded ciphertexts; same words as fhe_b200_bfv_multiply_relin */
 int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* shard, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_key_slice,
                                         uint64_t* d_out, uint32_t batch, void* stream);
+/* One stage (0..4) of the same multiply: stage k starts with the wait for the peers' phase k-1 and ends with this rank's signal of
+ * phase k.  Only for a host that drives several ranks on ONE device (the single-GPU tests): it must issue stage k for every rank
+ * before stage k+1 for any, so that no kernel ever spins on a flag that a later launch on the same GPU has to write. */
+int fhe_b200_bfv_multiply_relin_sharded_stage(fhe_b200_shard* shard, int stage, const uint64_t* d_a, const uint64_t* d_b,
+                                              const uint64_t* d_key_slice, uint64_t* d_out, uint32_t batch, void* stream);
 /* synchronises `stream`; FHE_B200_ESTATE if a wait for a peer timed out since creation */
 int fhe_b200_shard_check(fhe_b200_shard* shard, void* stream);
 /* scheme constants for the compat layer and tests */

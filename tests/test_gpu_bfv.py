@@ -21,14 +21,20 @@ def _rand_limbs(rng, mods, n, batch):
     return np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods]) for _ in range(batch)])
 
 
-@pytest.mark.parametrize("tpc", ["1", "2", "mma"])
+def _pick_lincomb_kernel(monkeypatch, tpc):
+    """IMAD kernel with one or two lanes per coefficient ("1", "2"), the mma.sync tensor-core kernel ("mma") or the tcgen05 / TMEM
+    kernel ("tc"; shapes whose operands do not fit shared memory fall back to mma.sync) -- read when the object is created"""
+    monkeypatch.setenv("FHE_B200_LINCOMB_MMA", "1" if tpc in ("mma", "tc") else "0")
+    monkeypatch.setenv("FHE_B200_LINCOMB_TC", "1" if tpc == "tc" else "0")
+    if tpc in ("1", "2"):
+        monkeypatch.setenv("FHE_B200_LINCOMB_TPC", tpc)
+
+
+@pytest.mark.parametrize("tpc", ["1", "2", "mma", "tc"])
 @pytest.mark.parametrize("S,T", [(1, 3), (2, 3), (4, 5), (8, 24), (24, 25), (25, 24), (9, 4), (30, 7), (33, 2), (49, 25), (62, 3)])
 def test_base_conversion_vs_oracle(fhe, oracle, chain, S, T, tpc, monkeypatch):
     from fhe_b200.engine import to_device, to_host
-    # IMAD kernel with one or two lanes per coefficient, or the tensor-core kernel (read when the object is created)
-    monkeypatch.setenv("FHE_B200_LINCOMB_MMA", "1" if tpc == "mma" else "0")
-    if tpc != "mma":
-        monkeypatch.setenv("FHE_B200_LINCOMB_TPC", tpc)
+    _pick_lincomb_kernel(monkeypatch, tpc)
     src, dst = chain[:S], chain[S:S + T]
     n, batch = 256, 3
     rng = np.random.default_rng(100 + S)
@@ -44,13 +50,11 @@ def test_base_conversion_vs_oracle(fhe, oracle, chain, S, T, tpc, monkeypatch):
         assert np.array_equal(cg[k], co[k]), k
 
 
-@pytest.mark.parametrize("tpc", ["1", "2", "mma"])
+@pytest.mark.parametrize("tpc", ["1", "2", "mma", "tc"])
 @pytest.mark.parametrize("L,R,t", [(1, 2, 65537), (2, 3, 65537), (4, 5, 786433), (24, 25, 65537), (3, 4, 1 << 20)])
 def test_scale_and_round_vs_oracle(fhe, oracle, chain, L, R, t, tpc, monkeypatch):
     from fhe_b200.engine import to_device, to_host
-    monkeypatch.setenv("FHE_B200_LINCOMB_MMA", "1" if tpc == "mma" else "0")
-    if tpc != "mma":
-        monkeypatch.setenv("FHE_B200_LINCOMB_TPC", tpc)
+    _pick_lincomb_kernel(monkeypatch, tpc)
     qs, ps = chain[:L], chain[L:L + R]
     n, batch = 512, 2
     rng = np.random.default_rng(200 + L)

@@ -1,7 +1,8 @@
 """Limb-sharded BFV multiply + relinearize (csrc/shard.cu, BASELINE.json config 4): sharded == single-GPU, word for word.
 
-* virtual ranks: `world` shard objects on ONE device in one process -- the same kernels, scatter tables, epoch flags and peer
-  stores as across GPUs (the "peer" buffers are in the same memory), so the driver's single-GPU test tier covers the logic;
+* virtual ranks: `world` shard objects on ONE device in one process, driven stage by stage -- the same kernels, scatter tables,
+  epoch flags and peer stores as across GPUs (the "peer" buffers are in the same memory), so the driver's single-GPU test tier
+  covers the logic without ever making one launch spin on a flag that a later launch on the same GPU writes;
 * processes: one rank per GPU under torch.distributed.run (CUDA IPC, stores over NVLink), skipped below 2 GPUs."""
 import os
 import subprocess
@@ -43,15 +44,17 @@ def _setup(fhe, preset, world, B, seed=7):
     return p, ctxs, shards, rlk, ca, cb
 
 
-def _run(shards, a, b, keys, streams, reps=1):
-    outs = [None] * len(shards)
+def _run(shards, a, b, keys, streams=None, reps=1):
+    """several ranks on ONE device: kernels that wait for one another must not be separate launches on one GPU (nothing guarantees
+    that they run at the same time), so stage k is issued for every rank before stage k+1 for any rank, all on one stream --
+    every wait finds its flags set.  The kernels, scatter tables, peer stores and epoch logic are those of the multi-GPU run."""
+    outs = [torch.empty_like(x) for x in a]
     for _ in range(reps):
-        for r, s in enumerate(shards):                      # asynchronous: every rank's work is queued on its own stream
-            with torch.cuda.stream(streams[r]):
-                outs[r] = s.multiply(a[r], b[r], keys[r], out=outs[r])
-    for r, s in enumerate(shards):
-        with torch.cuda.stream(streams[r]):
-            s.check()
+        for stage in range(5):
+            for r, s in enumerate(shards):
+                s.multiply_stage(stage, a[r], b[r], keys[r], outs[r])
+    for s in shards:
+        s.check()
     return outs
 
 
@@ -64,7 +67,7 @@ def test_virtual_ranks_equal_single_gpu(fhe, world, fused, monkeypatch):
     want = ctxs[0].multiply(ca, cb, rlk)
     want_sq = ctxs[0].multiply(ca, ca, rlk)
     torch.cuda.synchronize()
-    streams = [torch.cuda.Stream() for _ in range(world)]
+    streams = None
     keys = [s.slice_key(rlk) for s in shards]
     a = [s.shard_ct(ca) for s in shards]; b = [s.shard_ct(cb) for s in shards]
     torch.cuda.synchronize()
