@@ -108,7 +108,7 @@ def load_library() -> C.CDLL:
         "fhe_b200_bfv_plan": [_vp],
         "fhe_b200_gaussian_cdt": [C.c_double, u64p, C.c_uint32],
         "fhe_b200_wire_pack": [C.c_uint32] * 4 + [C.c_int, C.c_uint32, u64p, u64p, _vp],
-        "fhe_b200_wire_unpack": [_vp, C.c_size_t, u64p] + [C.POINTER(C.c_uint32)] * 4 + [C.POINTER(C.c_int),
+        "fhe_b200_wire_unpack": [_vp, C.c_size_t, u64p, C.c_uint32] + [C.POINTER(C.c_uint32)] * 4 + [C.POINTER(C.c_int),
                                  C.POINTER(C.c_uint32), u64p],
     }
     lib.fhe_b200_wire_size.argtypes = [C.c_uint32] * 3

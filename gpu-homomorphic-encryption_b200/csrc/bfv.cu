@@ -487,7 +487,7 @@ extern "C" int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* c, uint64_t seed, const ui
 // half with the IMAD-bound transforms of the other.  FHE_B200_HMULT_STREAMS=1 keeps everything on the caller's stream.
 template <class F>
 static int fork_join_halves(fhe_b200_bfv* c, uint32_t batch, cudaStream_t st, F&& f) {
-    static const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;
+    const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;      // read at every call
     if (batch < 2 || env_streams < 2) return f(0u, batch, st);
     for (int i = 0; i < 2; i++) {
         if (!c->mul_stream[i]) FHE_CUDA(cudaStreamCreateWithFlags(&c->mul_stream[i], cudaStreamNonBlocking));
@@ -496,13 +496,20 @@ static int fork_join_halves(fhe_b200_bfv* c, uint32_t batch, cudaStream_t st, F&
     if (!c->mul_fork) FHE_CUDA(cudaEventCreateWithFlags(&c->mul_fork, cudaEventDisableTiming));
     const uint32_t b0 = (batch + 1) / 2, cnt[2] = {b0, batch - b0}, first[2] = {0, b0};
     FHE_CUDA(cudaEventRecord(c->mul_fork, st));
+    // from here to the joins nothing returns early: whatever was queued on an internal stream is joined back into the caller's
     int rc = 0;
+    bool forked[2] = {false, false};
     for (int i = 0; i < 2 && !rc; i++) {
-        FHE_CUDA(cudaStreamWaitEvent(c->mul_stream[i], c->mul_fork, 0));
+        if (cudaStreamWaitEvent(c->mul_stream[i], c->mul_fork, 0) != cudaSuccess) { set_error("fork: cudaStreamWaitEvent failed"); rc = FHE_B200_ECUDA; break; }
+        forked[i] = true;
         rc = f(first[i], cnt[i], c->mul_stream[i]);
-        FHE_CUDA(cudaEventRecord(c->mul_join[i], c->mul_stream[i]));
     }
-    for (int i = 0; i < 2; i++) if (c->mul_join[i]) cudaStreamWaitEvent(st, c->mul_join[i], 0);      // joined even after an error
+    for (int i = 0; i < 2; i++) {
+        if (!forked[i]) continue;
+        if (cudaEventRecord(c->mul_join[i], c->mul_stream[i]) != cudaSuccess || cudaStreamWaitEvent(st, c->mul_join[i], 0) != cudaSuccess) {
+            if (!rc) { set_error("join: recording or waiting for the internal stream failed"); rc = FHE_B200_ECUDA; }
+        }
+    }
     return rc;
 }
 
@@ -860,7 +867,7 @@ static int multiply_core(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d
     DeviceGuard dev_guard(c->device);
     FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, multiply_ws_words(c, batch)));
     const size_t ct = 2 * (size_t)c->L * c->n, ct3 = 3 * (size_t)c->L * c->n;
-    static const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;
+    const int env_streams = getenv("FHE_B200_HMULT_STREAMS") ? atoi(getenv("FHE_B200_HMULT_STREAMS")) : 2;
     if (batch == 1 && env_streams >= 2) return multiply_one_split(c, d_a, d_b, d_rlk, d_out, d_scaled, c->d_ws, st);
     return fork_join_halves(c, batch, st, [&](uint32_t first, uint32_t cnt, cudaStream_t s) -> int {
         const size_t o = first;
@@ -961,6 +968,7 @@ extern "C" int fhe_b200_bfv_apply_galois(fhe_b200_bfv* c, const uint64_t* d_ct, 
 extern "C" int fhe_b200_bfv_mod_switch_to_next(fhe_b200_bfv* c, const uint64_t* d_ct, uint64_t* d_out, uint32_t batch, void* stream) {
     FHE_REQUIRE(c && d_ct && d_out, "bfv_mod_switch_to_next: null argument");
     FHE_REQUIRE(c->L >= 2, "bfv_mod_switch_to_next: the ciphertext modulus has a single limb");
+    FHE_REQUIRE(d_out != d_ct, "bfv_mod_switch_to_next: the output is compacted ([..][L-1][N]) and must not alias the input");
     // both components of every ciphertext: [2 batch][L][N] -> [2 batch][L-1][N]
     return fhe_b200_modswitch_drop_last(c->plan, d_out, d_ct, 2 * batch, 0, c->L, stream);
 }
@@ -972,10 +980,11 @@ extern "C" int fhe_b200_bfv_mod_switch_to_level(fhe_b200_bfv* c, const uint64_t*
                                                 void* stream) {
     FHE_REQUIRE(c && d_ct && d_out, "bfv_mod_switch_to_level: null argument");
     FHE_REQUIRE(drop < c->L, "bfv_mod_switch_to_level: cannot drop %u of %u limbs", drop, c->L);
+    FHE_REQUIRE(d_out != d_ct || drop == 0, "bfv_mod_switch_to_level: the output is compacted and must not alias the input");
     if (!batch) return 0;
     DeviceGuard dev_guard(c->device);
     const size_t pn = (size_t)2 * batch * c->n;                       // words per limb over all components
-    if (drop == 0) { FHE_CUDA(cudaMemcpyAsync(d_out, d_ct, pn * c->L * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0; }
+    if (drop == 0) { if (d_out != d_ct) FHE_CUDA(cudaMemcpyAsync(d_out, d_ct, pn * c->L * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0; }
     if (drop > 1) FHE_TRY(ensure_words(&c->d_ws, &c->ws_words, 2 * pn * (c->L - 1)));
     const uint64_t* cur = d_ct;
     for (uint32_t k = 0; k < drop; k++) {

@@ -105,7 +105,6 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
     p->hb = lazy_headroom(h_moduli, n_limbs);
     p->near60 = all_near60(h_moduli, n_limbs);
     if (getenv("FHE_B200_NO_NEAR60")) p->near60 = false;
-    if (const char* e = getenv("FHE_B200_NTT_FUSED")) p->fused = atoi(e) != 0;
     p->bal = bal_supported((int)p->logn);
     if (const char* e = getenv("FHE_B200_NTT_BAL")) p->bal = p->bal && atoi(e) != 0;
     if (const char* e = getenv("FHE_B200_NTT_CHUNK_MB")) { long mb = atol(e); if (mb > 0) p->chunk_bytes = (size_t)mb << 20; }
@@ -157,7 +156,6 @@ extern "C" int fhe_b200_plan_create(uint32_t n, const uint64_t* h_moduli, uint32
 extern "C" int fhe_b200_plan_destroy(fhe_b200_plan* p) {
     if (!p) return 0;
     DeviceGuard dev_guard(p->device);
-    release_fused_scratch(p);
     cudaFree(p->d_fwd); cudaFree(p->d_inv); cudaFree(p->d_params);
     cudaFree(p->d_fwd_bal); cudaFree(p->d_inv_bal);
     cudaFree(p->d_fwd_p12); cudaFree(p->d_fwd_p3); cudaFree(p->d_inv_p12); cudaFree(p->d_inv_p3);
@@ -229,7 +227,7 @@ extern "C" int fhe_b200_negacyclic_mul(fhe_b200_plan* plan, uint64_t* d_out, con
     // N <= 4096: one fused kernel (both forward transforms, the pointwise product and the inverse in shared memory) while the
     // grid is small enough that its single CTA per SM does not cost throughput; FHE_B200_MUL_FUSED = 0 | 1 overrides
     if (plan->logn <= 12) {
-        static const int env = getenv("FHE_B200_MUL_FUSED") ? atoi(getenv("FHE_B200_MUL_FUSED")) : -1;
+        const int env = getenv("FHE_B200_MUL_FUSED") ? atoi(getenv("FHE_B200_MUL_FUSED")) : -1;
         const bool fused = env >= 0 ? env != 0 : (size_t)batch * limb_count <= (size_t)4 * plan->sm_count;
         if (fused) return launch_negacyclic_mul_fused(plan, d_out, d_a, d_b, batch, limb_begin, limb_count, st);
     }
@@ -257,6 +255,7 @@ extern "C" int fhe_b200_ntt_host(fhe_b200_plan* plan, uint64_t* h_data, uint32_t
     size_t polys_per_chunk = (64u << 20) / poly_bytes; if (!polys_per_chunk) polys_per_chunk = 1;
     const size_t need = polys_per_chunk * poly_bytes;
     if (plan->stage_bytes < need) {
+        plan->stage_bytes = 0;                          // nothing usable until all three buffers exist again (an allocation may fail midway)
         for (int i = 0; i < 3; i++) {
             if (plan->d_stage[i]) { cudaFree(plan->d_stage[i]); plan->d_stage[i] = nullptr; }
             if (!plan->hs[i]) FHE_CUDA(cudaStreamCreateWithFlags(&plan->hs[i], cudaStreamNonBlocking));

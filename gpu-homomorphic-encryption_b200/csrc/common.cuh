@@ -65,7 +65,6 @@ struct fhe_b200_plan {
     uint32_t n = 0, logn = 0, limbs = 0;
     int device = 0;
     int hb = 16;                                   // lazy head-room (16: all q < 2^60, 8: all q < 2^61)
-    bool fused = false;                            // N > 4096: single persistent row+tile kernel (FHE_B200_NTT_FUSED=1); default two passes
     bool near60 = false;                           // every q in (2^60 - 2^32, 2^60): cheap range reduction (near60_reduce)
     std::vector<uint64_t> moduli;
     fhe_b200::Twiddle* d_fwd = nullptr;            // [limbs][n]
@@ -127,5 +126,4 @@ int launch_ntt_pass_a(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in
 int launch_negacyclic_mul_fused(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, uint32_t batch,
                                 uint32_t limb_begin, uint32_t limb_count, cudaStream_t st);
 int check_range(const fhe_b200_plan* plan, uint32_t batch, uint32_t limb_begin, uint32_t limb_count);
-void release_fused_scratch(const fhe_b200_plan* plan);
 }  // namespace fhe_b200

@@ -432,6 +432,7 @@ extern "C" int fhe_b200_modswitch_drop_last(fhe_b200_plan* plan, uint64_t* d_out
     FHE_REQUIRE(plan && d_out && d_in, "modswitch_drop_last: null argument");
     FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
     FHE_REQUIRE(limb_count >= 2 && limb_count <= 64, "modswitch_drop_last: needs 2..64 limbs");
+    FHE_REQUIRE(d_out != d_in, "modswitch_drop_last: the output is compacted ([batch][limbs-1][N]) and must not alias the input");
     const size_t total = (size_t)batch * (limb_count - 1) * plan->n;
     if (!total) return 0;
     DeviceGuard dev_guard(plan->device);
@@ -441,7 +442,11 @@ extern "C" int fhe_b200_modswitch_drop_last(fhe_b200_plan* plan, uint64_t* d_out
     for (uint32_t i = 0; i + 1 < limb_count; i++) { const uint64_t qi = plan->moduli[limb_begin + i]; h_inv[i] = host::invmod(ql % qi, qi); }
     uint64_t* d_inv = nullptr;
     FHE_CUDA(cudaMallocAsync(&d_inv, 64 * sizeof(uint64_t), st));
-    FHE_CUDA(cudaMemcpyAsync(d_inv, h_inv, (limb_count - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (cudaMemcpyAsync(d_inv, h_inv, (limb_count - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaFreeAsync(d_inv, st);                      // the stream-ordered temporary is released on the error path too
+        set_error("modswitch_drop_last: uploading the constants failed");
+        return FHE_B200_ECUDA;
+    }
     const size_t w = (total + 255) / 256;
     const uint32_t grid = (uint32_t)(w < (size_t)plan->sm_count * 16 ? w : (size_t)plan->sm_count * 16);
     modswitch_drop_last_kernel<<<grid, 256, 0, st>>>(d_out, d_in, plan->d_params, d_inv, plan->logn, limb_begin, limb_count, total);

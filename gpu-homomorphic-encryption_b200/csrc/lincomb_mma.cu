@@ -256,7 +256,7 @@ static int launch_kt(const LcMmaArgs& a, int sm_count, int device, cudaStream_t 
     if (!one) {
         FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lincomb_mma_kernel<KT>, 256, smem));
         if (per_sm < 1) per_sm = 1;
-        static const char* ev = getenv("FHE_B200_LINCOMB_CTAS");             // experiments: cap the resident CTAs per SM
+        const char* ev = getenv("FHE_B200_LINCOMB_CTAS");             // experiments: cap the resident CTAs per SM
         if (ev && atoi(ev) > 0 && atoi(ev) < per_sm) per_sm = atoi(ev);
     }
     const size_t cap = (size_t)sm_count * (one ? 1 : per_sm);

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
     uint32_t parity = 0;
 
 #pragma unroll 1
-    for (size_t tile = (size_t)blockIdx.x * kTcGroups + grp; tile < a.tiles; tile += (size_t)gridDim.x * kTcGroups) {
+    for (size_t tile = (size_t)blockIdx.x + (size_t)gridDim.x * grp; tile < a.tiles; tile += (size_t)gridDim.x * kTcGroups) {     // CTAs first, then groups: few tiles spread over many SMs
         const size_t coef = tile * 128 + gtid;
         const uint32_t b = (uint32_t)(coef >> a.logn);
         const uint32_t j = (uint32_t)(coef & (nn - 1));
@@ -334,8 +334,7 @@ int lincomb_tc_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint
 #undef TC_ATTR
         attr_smem[lc->device & 63] = smem;
     }
-    const size_t want = (a.tiles + kTcGroups - 1) / kTcGroups;
-    const unsigned grid = (unsigned)(want < (size_t)lc->sm_count ? want : (size_t)lc->sm_count);
+    const unsigned grid = (unsigned)(a.tiles < (size_t)lc->sm_count ? a.tiles : (size_t)lc->sm_count);
     const int kind = (!a.use_extra && !a.c_is_one && !view.sub) ? 0 : (a.use_extra && a.c_is_one && !view.sub) ? 1
                    : (!a.use_extra && !a.c_is_one && view.sub) ? 2 : 3;
 #define TC_GO(M_, K_) lincomb_tc_kernel<M_, K_><<<grid, 128 * kTcGroups, smem, st>>>(a)

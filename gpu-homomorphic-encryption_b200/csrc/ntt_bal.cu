@@ -178,7 +178,7 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
     // the hardware CTA scheduler overlaps the load, compute and store phases of neighbouring items better than a loop does)
     const uint32_t items_per_limb = a.nb * A::CB;
     uint32_t m = 1;
-    static const int env_m = getenv("FHE_B200_BAL_M") ? atoi(getenv("FHE_B200_BAL_M")) : 0;          // experiments
+    const int env_m = getenv("FHE_B200_BAL_M") ? atoi(getenv("FHE_B200_BAL_M")) : 0;          // experiments
     if (env_m > 0) m = (uint32_t)env_m;
     a.m_items = m;
     a.ctas_per_limb = (items_per_limb + m - 1) / m;
@@ -189,7 +189,7 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
     constexpr uint32_t pairs = 1u << (KA - 1);
     const uint32_t lp = a.nl * pairs;
     uint32_t groups = (4u * kBalBMinBlocks * sms * kBalBWarps + lp - 1) / lp;
-    static const int env_g = getenv("FHE_B200_BAL_GROUPS") ? atoi(getenv("FHE_B200_BAL_GROUPS")) : 0;
+    const int env_g = getenv("FHE_B200_BAL_GROUPS") ? atoi(getenv("FHE_B200_BAL_GROUPS")) : 0;
     if (env_g > 0) groups = (uint32_t)env_g;
     groups = (groups + kBalBGroups - 1) / kBalBGroups * kBalBGroups;       // whole CTAs (a CTA spans kBalBGroups groups)
     groups = groups < 1 ? 1 : (groups > a.nb ? a.nb : groups);

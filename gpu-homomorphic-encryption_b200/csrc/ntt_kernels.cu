@@ -6,21 +6,13 @@
 //               prefetching the next polynomial's tile while it finishes the current one.
 //   row item  : (limb, polynomial, column block): V adjacent columns x 2^K1 rows per thread, registers only.
 //
-// N <= 4096: tile items only (one kernel).  N > 4096, two strategies:
-//   two-pass (default): row kernel then tile kernel (per chunk of plan->chunk_bytes).  Both passes are bound by the IMAD pipe
-//                     at the same per-stage rate (measured), so hiding the row pass's HBM traffic buys nothing today.
-//   fused (FHE_B200_NTT_FUSED=1): ONE persistent kernel.  CTAs draw items from an ordered list through an atomic ticket; row items of a
-//                     group are listed a couple of groups ahead of the tile items that consume them, and a per-(limb, group)
-//                     counter in global memory tells a tile item when its rows are done.  The intermediate is therefore still
-//                     L2-resident when it is read back (HBM sees each limb once in, once out), and the HBM-bound row work
-//                     overlaps the IMAD-bound tile work of other CTAs on the same SM.  Waiting items only ever wait for
-//                     lower tickets, which are held by running CTAs that never wait themselves: no deadlock.
-//                     Measured 5% slower than two-pass at config 3; kept because it touches HBM once per limb.
+// N <= 4096: tile items only (one kernel).  N > 4096 (where the balanced passes of ntt_bal.cu do not apply): row kernel then tile
+// kernel (per chunk of plan->chunk_bytes).  Both passes are bound by the IMAD pipe at the same per-stage rate (measured).  (A
+// persistent single-kernel variant with release/acquire counters between row and tile items was measured 5% slower at config 3 in
+// round 1 and has been removed.)
 #include "common.cuh"
 #include "ntt_core.cuh"
 #include "tma.cuh"
-#include <map>
-#include <mutex>
 
 namespace fhe_b200 {
 
@@ -38,12 +30,6 @@ struct NttArgs {
     uint32_t b0, nb;             // chunk: polynomials [b0, b0+nb)
     uint32_t groups;             // two-pass tile kernel: CTAs per (limb, tile); CTA g handles polynomials b0+g, b0+g+groups, ...
     uint32_t tiles, p3n;
-    // fused kernel
-    const uint32_t* work;        // item list
-    uint32_t n_items;
-    uint32_t pg;                 // polynomials per group
-    uint32_t n_groups;           // groups per limb
-    uint32_t* sync;              // [0] ticket, [1] error flag, [2 + limb * n_groups + group] completion counters
 };
 
 // (limb, tile/column-block, polynomial or group) from a linear CTA index, innermost fastest
@@ -222,175 +208,6 @@ __global__ void __launch_bounds__(kRowThreads) ntt_row_inv_kernel(const NttArgs 
     row_inv_item<LB, K1, HB, NEAR, V>(a, limb, a.b0 + poly, cb);
 }
 
-// ================================================ fused persistent kernel ==============================================
-// item code: bit 31 = consumer (waits for its group's counter), bit 30 = tile item (else row item),
-//            bits 29..22 limb (buffer-relative), bits 21..11 group, bits 10..0 unit (tile index, or poly-in-group * RB + column block)
-constexpr uint32_t kItemConsumer = 1u << 31, kItemTile = 1u << 30;
-__host__ __device__ inline uint32_t item_code(bool consumer, bool tile, uint32_t limb, uint32_t group, uint32_t unit) {
-    return (consumer ? kItemConsumer : 0) | (tile ? kItemTile : 0) | (limb << 22) | (group << 11) | unit;
-}
-
-template <int LB, int K1, int HB, bool NEAR, bool INVERSE>
-__global__ void __launch_bounds__(kRowThreads, 2) ntt_fused_kernel(const NttArgs a) {
-    static_assert((1 << (LB - 4)) == kRowThreads, "fused kernel needs 256-thread tile CTAs (LB = 12)");
-    constexpr int V = (K1 >= 5) ? 1 : 2;
-    constexpr uint32_t RB = (1u << LB) / (V * kRowThreads);       // row items per (limb, polynomial)
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    using SM = TileSmem<LB>;
-    uint32_t* s_scr = SM::scratch(smem_raw);
-    if (threadIdx.x == 0) { mbar_init(SM::bar(smem_raw), 1); mbar_fence_init(); }
-    __syncthreads();
-    uint32_t parity = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_scr[0] = atomicAdd(&a.sync[0], 1u);
-        __syncthreads();
-        const uint32_t ticket = s_scr[0];
-        if (ticket >= a.n_items) break;
-        const uint32_t code = a.work[ticket];
-        const uint32_t limb = a.l0 + ((code >> 22) & 0xffu), grp = (code >> 11) & 0x7ffu, unit = code & 0x7ffu;
-        const bool is_tile = (code & kItemTile) != 0;
-        uint32_t* counter = &a.sync[2 + ((code >> 22) & 0xffu) * a.n_groups + grp];
-        const uint32_t p0 = a.b0 + grp * a.pg;
-        const uint32_t p1 = min(a.b0 + a.nb, p0 + a.pg);
-        if (code & kItemConsumer) {
-            // wait until every producer item of this (limb, group) has published its stores
-            const uint32_t need = INVERSE ? (1u << K1) : (p1 - p0) * RB;
-            if (threadIdx.x == 0) {
-                uint32_t spins = 0, seen;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-                    if (seen >= need) break;
-                    __nanosleep(64);
-                } while (++spins < (1u << 26));
-                if (seen < need) atomicExch(&a.sync[1], 1u);          // give up loudly instead of hanging the GPU
-            }
-            __syncthreads();
-        }
-        if (is_tile) {
-            if (!INVERSE) tile_fwd_item<LB, K1, HB, NEAR>(a, smem_raw, limb, unit, p0, p1, 1, parity);
-            else tile_inv_item<LB, K1, HB, NEAR>(a, smem_raw, limb, unit, p0, p1, 1, parity);
-            parity ^= 1;
-        } else {
-            const uint32_t poly = p0 + unit / RB, cb = unit % RB;
-            if (!INVERSE) row_fwd_item<LB, K1, HB, NEAR, V>(a, limb, poly, cb);
-            else row_inv_item<LB, K1, HB, NEAR, V>(a, limb, poly, cb);
-        }
-        if (!(code & kItemConsumer)) {
-            // producer: make this CTA's stores visible GPU-wide, then count the item as done
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        }
-        __syncthreads();
-    }
-}
-
-// ---- host side of the fused kernel: item list and synchronisation words, cached per (stream, shape) -----------------
-struct FusedScratch {
-    uint32_t* d_work = nullptr; size_t work_cap = 0;
-    uint32_t* d_sync = nullptr; size_t sync_cap = 0;
-    uint64_t key = 0;            // shape the cached item list was built for
-    uint32_t n_items = 0;
-};
-static std::mutex g_fused_mu;
-static std::map<std::pair<const void*, const void*>, FusedScratch> g_fused;    // (plan, stream) -> scratch
-
-// Scheduling parameters (tunable from the environment for experiments):
-//   pg   polynomials per group (a tile item runs them back to back on one staged twiddle block)
-//   lbk  limbs per block: one "step" = the producers of one group for every limb of the block (lbk * pg * N * 8 bytes)
-//   lead steps between a group's producers and its consumers.  (lead + 1) steps must stay L2 resident.
-struct FusedSched { uint32_t pg = 4, lbk = 8, lead = 2; };
-static FusedSched fused_sched() {
-    static FusedSched s = [] {
-        FusedSched v;
-        if (const char* e = getenv("FHE_B200_FUSED_PG")) v.pg = (uint32_t)atoi(e);
-        if (const char* e = getenv("FHE_B200_FUSED_LBK")) v.lbk = (uint32_t)atoi(e);
-        if (const char* e = getenv("FHE_B200_FUSED_LEAD")) v.lead = (uint32_t)atoi(e);
-        if (v.pg < 1) v.pg = 1; if (v.pg > 16) v.pg = 16; if (v.lbk < 1) v.lbk = 1; if (v.lead < 1) v.lead = 1;
-        return v;
-    }();
-    return s;
-}
-
-// Ticket order: limb blocks one after another; inside a block, step g lists the producers of group g for every limb of the
-// block, then the consumers of group g - lead for every limb.  A consumer's producers are therefore at least
-// lead * (items per step) tickets behind it and have normally finished by the time a CTA draws the consumer.
-static void build_items(std::vector<uint32_t>& w, uint32_t nl, uint32_t nb, uint32_t tiles, uint32_t RB, bool inverse, const FusedSched& sc) {
-    const uint32_t pg = sc.pg, G = (nb + pg - 1) / pg;
-    auto polys = [&](uint32_t g) { return (g + 1) * pg <= nb ? pg : nb - g * pg; };
-    for (uint32_t lb0 = 0; lb0 < nl; lb0 += sc.lbk) {
-        const uint32_t lb1 = lb0 + sc.lbk < nl ? lb0 + sc.lbk : nl;
-        auto emit = [&](uint32_t g, bool consumer) {
-            const bool tile = inverse ? !consumer : consumer;
-            for (uint32_t l = lb0; l < lb1; l++) {
-                const uint32_t cnt = tile ? tiles : polys(g) * RB;
-                for (uint32_t u = 0; u < cnt; u++) w.push_back(item_code(consumer, tile, l, g, u));
-            }
-        };
-        for (uint32_t g = 0; g < G + sc.lead; g++) {
-            if (g < G) emit(g, false);
-            if (g >= sc.lead) emit(g - sc.lead, true);
-        }
-    }
-}
-
-template <int LB, int K1, int HB, bool NEAR>
-static int run_fused(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t st) {
-    constexpr int V = (K1 >= 5) ? 1 : 2;
-    constexpr uint32_t RB = (1u << LB) / (V * kRowThreads);
-    const FusedSched sc = fused_sched();
-    const uint32_t G = (a.nb + sc.pg - 1) / sc.pg;
-    FHE_REQUIRE(a.nl <= 256 && G <= 2048, "fused NTT: at most 256 limbs and 16384 polynomials per launch");
-    FusedScratch* fs;
-    {
-        std::lock_guard<std::mutex> lk(g_fused_mu);
-        fs = &g_fused[std::make_pair((const void*)plan, (const void*)st)];
-    }
-    const uint64_t key = ((uint64_t)a.nl << 40) | ((uint64_t)a.nb << 8) | (inverse ? 1u : 0u) | 2u;
-    const size_t sync_words = 2 + (size_t)a.nl * G;
-    if (fs->sync_cap < sync_words) {
-        if (fs->d_sync) FHE_CUDA(cudaFree(fs->d_sync));
-        FHE_CUDA(cudaMalloc(&fs->d_sync, sync_words * sizeof(uint32_t)));
-        fs->sync_cap = sync_words;
-    }
-    if (fs->key != key) {
-        std::vector<uint32_t> w;
-        build_items(w, a.nl, a.nb, 1u << K1, RB, inverse, sc);
-        if (fs->work_cap < w.size()) {
-            if (fs->d_work) FHE_CUDA(cudaFree(fs->d_work));
-            FHE_CUDA(cudaMalloc(&fs->d_work, w.size() * sizeof(uint32_t)));
-            fs->work_cap = w.size();
-        }
-        FHE_CUDA(cudaMemcpyAsync(fs->d_work, w.data(), w.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        FHE_CUDA(cudaStreamSynchronize(st));          // w is a stack-owned host vector
-        fs->key = key; fs->n_items = (uint32_t)w.size();
-    }
-    FHE_CUDA(cudaMemsetAsync(fs->d_sync, 0, sync_words * sizeof(uint32_t), st));
-    a.work = fs->d_work; a.n_items = fs->n_items; a.pg = sc.pg; a.n_groups = G; a.sync = fs->d_sync;
-    constexpr size_t smem = TileSmem<LB>::total;
-    static PerDeviceOnce attr_once;
-    if (attr_once.need(plan->device)) {
-        FHE_CUDA(cudaFuncSetAttribute(ntt_fused_kernel<LB, K1, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FHE_CUDA(cudaFuncSetAttribute(ntt_fused_kernel<LB, K1, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    const uint32_t grid = (uint32_t)std::min<size_t>((size_t)2 * plan->sm_count, fs->n_items);
-    const bool prof = profile_on();
-    if (prof) profile_begin(inverse ? 1 : 0, (uint64_t)a.nl * a.nb, st);
-    if (!inverse) ntt_fused_kernel<LB, K1, HB, NEAR, false><<<grid, kRowThreads, smem, st>>>(a);
-    else ntt_fused_kernel<LB, K1, HB, NEAR, true><<<grid, kRowThreads, smem, st>>>(a);
-    if (prof) profile_end(st);
-    FHE_LAUNCH_CHECK();
-    return 0;
-}
-
-void release_fused_scratch(const fhe_b200_plan* plan) {
-    std::lock_guard<std::mutex> lk(g_fused_mu);
-    for (auto it = g_fused.begin(); it != g_fused.end();) {
-        if (it->first.first == (const void*)plan) { cudaFree(it->second.d_work); cudaFree(it->second.d_sync); it = g_fused.erase(it); }
-        else ++it;
-    }
-}
-
 // ================================================ fused negacyclic product (N <= 4096) ===================================
 // out = INTT(NTT(a) . NTT(b)) of one limb-polynomial per CTA, everything in shared memory: replaces the five launches (and the
 // two device allocations) of NTTEngine::multiply, /root/reference/src/ntt.cu:49-75, for the sizes where a transform is a single
@@ -495,9 +312,6 @@ template <int LB, int K1, int HB, bool NEAR>
 static int run_chunk(fhe_b200_plan* plan, NttArgs a, bool inverse, cudaStream_t st) {
     constexpr int V = (K1 >= 5) ? 1 : 2;
     const int sm_count = plan->sm_count;
-    if constexpr (K1 > 0 && LB == 12) {
-        if (plan->fused) return run_fused<LB, K1, HB, NEAR>(plan, a, inverse, st);
-    }
     const uint32_t pls = a.nl * a.nb;
     const bool prof = profile_on();
     // tile pass: one CTA per (limb, tile, group); a CTA reuses its staged twiddles for every polynomial of its group.
@@ -571,7 +385,6 @@ int launch_ntt(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint3
     a.p12 = inverse ? plan->d_inv_p12 : plan->d_fwd_p12;
     a.p3 = inverse ? plan->d_inv_p3 : plan->d_fwd_p3;
     a.tiles = plan->tiles; a.p3n = (uint32_t)plan->p3_entries; a.groups = 1;
-    a.work = nullptr; a.n_items = 0; a.pg = 0; a.n_groups = 0; a.sync = nullptr;
     a.params = plan->d_params;
     a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin;
     const size_t pl_bytes = (size_t)plan->n * sizeof(uint64_t);

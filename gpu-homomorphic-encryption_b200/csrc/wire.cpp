@@ -60,9 +60,11 @@ extern "C" int fhe_b200_wire_pack(uint32_t kind, uint32_t n, uint32_t limbs, uin
     return 0;
 }
 
-/* h_words_out may be NULL to read the header only; h_moduli (optional) is checked against the stored hash */
-extern "C" int fhe_b200_wire_unpack(const uint8_t* h_in, size_t len, const uint64_t* h_moduli, uint32_t* kind, uint32_t* n, uint32_t* limbs,
-                                    uint32_t* polys, int* ntt_form, uint32_t* galois_elt, uint64_t* h_words_out) {
+/* h_words_out may be NULL to read the header only; h_moduli[n_moduli] (optional) is the caller's chain: the header's limb count must
+ * equal n_moduli (checked BEFORE h_moduli is read: the header is untrusted), the chain's hash must match, and every payload word of
+ * limb i must be below h_moduli[i] */
+extern "C" int fhe_b200_wire_unpack(const uint8_t* h_in, size_t len, const uint64_t* h_moduli, uint32_t n_moduli, uint32_t* kind, uint32_t* n,
+                                    uint32_t* limbs, uint32_t* polys, int* ntt_form, uint32_t* galois_elt, uint64_t* h_words_out) {
     if (!h_in || len < 64) { set_error("wire_unpack: buffer shorter than the header"); return FHE_B200_EINVAL; }
     if (memcmp(h_in, kMagic, 8) != 0) { set_error("wire_unpack: bad magic"); return FHE_B200_EINVAL; }
     if (get32(h_in + 8) != 1) { set_error("wire_unpack: unsupported version %u", get32(h_in + 8)); return FHE_B200_EINVAL; }
@@ -71,6 +73,7 @@ extern "C" int fhe_b200_wire_unpack(const uint8_t* h_in, size_t len, const uint6
     if (k < 1 || k > 5 || !dims_ok(nn, ll, pp) || words != (uint64_t)nn * ll * pp) { set_error("wire_unpack: inconsistent header"); return FHE_B200_EINVAL; }
     if (len != 64 + words * 8) { set_error("wire_unpack: %zu bytes given, header says %llu", len, (unsigned long long)(64 + words * 8)); return FHE_B200_EINVAL; }
     if (h_moduli) {
+        if (ll != n_moduli) { set_error("wire_unpack: the object has %u limbs, the caller's chain %u", ll, n_moduli); return FHE_B200_ESTATE; }
         uint8_t mb[8]; uint64_t mh = 0xcbf29ce484222325ull;
         for (uint32_t i = 0; i < ll; i++) { put64(mb, h_moduli[i]); mh = fnv1a(mb, 8, mh); }
         if (mh != get64(h_in + 40)) { set_error("wire_unpack: the object was produced for a different modulus chain"); return FHE_B200_ESTATE; }
@@ -80,6 +83,9 @@ extern "C" int fhe_b200_wire_unpack(const uint8_t* h_in, size_t len, const uint6
     if (h_words_out) {
         if (fnv1a(h_in + 64, words * 8) != get64(h_in + 56)) { set_error("wire_unpack: payload checksum mismatch"); return FHE_B200_ESTATE; }
         for (uint64_t i = 0; i < words; i++) h_words_out[i] = get64(h_in + 64 + 8 * i);
+        if (h_moduli)                                   // residues must be reduced: limb-major [polys][limbs][n]
+            for (uint64_t i = 0; i < words; i++)
+                if (h_words_out[i] >= h_moduli[(i / nn) % ll]) { set_error("wire_unpack: word %llu is not reduced modulo its limb", (unsigned long long)i); return FHE_B200_ESTATE; }
     }
     return 0;
 }

@@ -86,10 +86,11 @@ def wire_unpack(blob: bytes, moduli=None):
     f = [C.c_uint32() for _ in range(4)]
     nf, ge = C.c_int(), C.c_uint32()
     refs = [C.byref(x) for x in f] + [C.byref(nf), C.byref(ge)]
-    check(lib.fhe_b200_wire_unpack(buf.ctypes.data, len(blob), mp, *refs, None))
+    nm = len(m) if m is not None else 0
+    check(lib.fhe_b200_wire_unpack(buf.ctypes.data, len(blob), mp, nm, *refs, None))
     kind, n, limbs, polys = (x.value for x in f)
     out = np.empty((polys, limbs, n), dtype=np.uint64)
-    check(lib.fhe_b200_wire_unpack(buf.ctypes.data, len(blob), mp, *refs, out.ctypes.data_as(u64p)))
+    check(lib.fhe_b200_wire_unpack(buf.ctypes.data, len(blob), mp, nm, *refs, out.ctypes.data_as(u64p)))
     names = {v: k for k, v in WIRE_KINDS.items()}
     return {"kind": names[kind], "n": n, "limbs": limbs, "polys": polys, "ntt_form": bool(nf.value), "galois_elt": ge.value}, out
 

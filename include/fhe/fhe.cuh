@@ -6,6 +6,8 @@
 // relinearize() performs hybrid key switching instead of dropping c2.  Polynomials of keys and ciphertexts are RNS
 // polynomials (Polynomial::rns, limb-major uint64_t [L][N]); plaintexts keep the reference's uint256_t coefficients.
 #pragma once
+#include <random>
+#include <cstdlib>
 #include <algorithm>
 #include <cstdio>
 #include <map>
@@ -85,7 +87,11 @@ public:
         params_.ntt_engine = new NTTEngine(params_.n, params_.modulus_chain[0]);
         params_.poly_ops = new PolynomialOps(params_.n, params_.modulus_chain[0], params_.ntt_engine);
         detail::check_cuda(cudaStreamCreate(&stream_), "cudaStreamCreate");
-        init_rng(12345);
+        // seeds: fresh OS entropy for every call (the secret key's seed is its own draw, never derived from a seed that also generates
+        // public values); init_rng(seed) switches to a reproducible sequence for tests.  NOTE the generator behind the C ABI is a
+        // counter-based splitmix64 hash keyed by 64 bits per call -- a placeholder like the reference's samplers
+        // (/root/reference/src/fhe.cu:238-257), not a CSPRNG: see DESIGN.md "Randomness" before using keys outside tests.
+        if (const char* e = std::getenv("FHE_B200_DETERMINISTIC_SEED")) init_rng(std::strtoull(e, nullptr, 0));
     }
     ~FHEContext() {
         delete params_.rns_ctx; delete params_.poly_ops; delete params_.ntt_engine;
@@ -296,9 +302,11 @@ private:
         if (!dst.components.empty()) { synchronize(); release(dst); }
         dst = src; src.components.clear();
     }
-    void init_rng(uint64_t seed) { seed_ = seed; }
-    // a hashed call counter: call k of this context gets mix(base seed, k); the library hashes the seed again per stream / batch item
+    void init_rng(uint64_t seed) { seed_ = seed; calls_ = 0; deterministic_ = true; }
+    // deterministic mode: a hashed call counter -- call k of this context gets mix(base seed, k); the library hashes the seed again
+    // per stream / batch item.  Default mode: 64 fresh bits from the OS per call.
     uint64_t next_seed() {
+        if (!deterministic_) { std::random_device rd; return ((uint64_t)rd() << 32) | (uint64_t)rd(); }
         uint64_t z = seed_ + 0x9E3779B97F4A7C15ull * ++calls_;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         return z ^ (z >> 31);
@@ -318,6 +326,7 @@ private:
     cudaStream_t stream_ = nullptr;
     int device_ = 0;
     uint64_t seed_ = 0, calls_ = 0;
+    bool deterministic_ = false;
     detail::DeviceBuf scratch_;
 };
 

@@ -280,13 +280,13 @@ fhe_b200_plan* fhe_b200_bfv_plan(fhe_b200_bfv* ctx);
 /* ---- wire format for keys / ciphertexts / plaintexts in HOST buffers (csrc/wire.cpp documents the 64-byte header) ---------
  * The reference declares no serialisation.  kind: 1 ciphertext, 2 public key, 3 secret key, 4 key-switching
  * key (relinearisation / Galois), 5 plaintext.  payload = uint64 [polys][limbs][n], little-endian, with FNV-1a checksums of
- * the payload and of the modulus chain; unpack verifies both (h_moduli may be NULL to skip the chain check, h_words_out NULL to
- * read the header only). */
+ * the payload and of the modulus chain; unpack verifies both, that the header's limb count equals n_moduli and that every word is reduced
+ * modulo its limb (h_moduli may be NULL to skip the chain checks, h_words_out NULL to read the header only). */
 size_t fhe_b200_wire_size(uint32_t n, uint32_t limbs, uint32_t polys);
 int fhe_b200_wire_pack(uint32_t kind, uint32_t n, uint32_t limbs, uint32_t polys, int ntt_form, uint32_t galois_elt,
                        const uint64_t* h_moduli, const uint64_t* h_words, uint8_t* h_out);
-int fhe_b200_wire_unpack(const uint8_t* h_in, size_t len, const uint64_t* h_moduli, uint32_t* kind, uint32_t* n, uint32_t* limbs,
-                         uint32_t* polys, int* ntt_form, uint32_t* galois_elt, uint64_t* h_words_out);
+int fhe_b200_wire_unpack(const uint8_t* h_in, size_t len, const uint64_t* h_moduli, uint32_t n_moduli, uint32_t* kind, uint32_t* n,
+                         uint32_t* limbs, uint32_t* polys, int* ntt_form, uint32_t* galois_elt, uint64_t* h_words_out);
 /* the Gaussian CDT the samplers use (<= 128 entries); returns the length */
 int fhe_b200_gaussian_cdt(double sigma, uint64_t* h_cdt, uint32_t cap);
 

@@ -72,6 +72,26 @@ def build_ref() -> str | None:
     return _REF_LIB if os.path.exists(_REF_LIB) else None
 
 
+_REF_NTT_LIB = os.path.join(_HERE, "_ref", "libref_ntt.so")
+_ref_ntt_lib = None
+
+
+def ref_time_poly(what: str, q: int, count: int, reps: int = 20):
+    """milliseconds per call of the REFERENCE's own kernel on cuda:0 (oracle/ref_ntt_kernels.cu): "pointwise_mul"
+    (ntt_pointwise_mul_kernel), "poly_add" (poly_add_kernel) over `count` coefficients, or "ntt_forward" (NTTEngine::forward's two
+    launches, count <= 1024).  None when oracle/_ref was never built or the launch is illegal in the reference."""
+    global _ref_ntt_lib
+    if _ref_ntt_lib is None:
+        if not os.path.exists(_REF_NTT_LIB):
+            return None
+        _ref_ntt_lib = C.CDLL(_REF_NTT_LIB)
+        _ref_ntt_lib.ref_time_poly_kernel.restype = C.c_int
+        _ref_ntt_lib.ref_time_poly_kernel.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
+    ms = C.c_float()
+    rc = _ref_ntt_lib.ref_time_poly_kernel({"pointwise_mul": 0, "poly_add": 1, "ntt_forward": 2}[what], C.c_uint64(q), count, reps, C.byref(ms))
+    return float(ms.value) if rc == 0 else None
+
+
 _ref_lib = None
 
 

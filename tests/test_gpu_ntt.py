@@ -42,14 +42,13 @@ def test_forward_inverse_vs_oracle(fhe, oracle, chain, logn, limbs, batch):
     assert np.array_equal(to_host(d), y)          # input untouched
 
 
-@pytest.mark.parametrize("env", [{"FHE_B200_NTT_BAL": "0"}, {"FHE_B200_NTT_BAL": "0", "FHE_B200_NTT_FUSED": "1"}, {"FHE_B200_NO_NEAR60": "1"},
+@pytest.mark.parametrize("env", [{"FHE_B200_NTT_BAL": "0"}, {"FHE_B200_NO_NEAR60": "1"},
                                  {"FHE_B200_NTT_BAL": "0", "FHE_B200_NO_NEAR60": "1"}, {"FHE_B200_NTT_CHUNK_MB": "1"},
-                                 {"FHE_B200_NTT_BAL": "0", "FHE_B200_NTT_CHUNK_MB": "1"},
-                                 {"FHE_B200_NTT_BAL": "0", "FHE_B200_NTT_FUSED": "1", "FHE_B200_FUSED_PG": "3", "FHE_B200_FUSED_LBK": "2", "FHE_B200_FUSED_LEAD": "1"}])
+                                 {"FHE_B200_NTT_BAL": "0", "FHE_B200_NTT_CHUNK_MB": "1"}])
 def test_alternative_code_paths(fhe, oracle, chain, env, monkeypatch):
-    """the row+tile two-pass strategy (FHE_B200_NTT_BAL=0), its fused persistent variant, chunked launches and the generic
-    (non near-2^60) reduction are selected per plan from the environment; they must give the same bits as the default
-    balanced / near-2^60 path."""
+    """the row+tile two-pass strategy (FHE_B200_NTT_BAL=0), chunked launches and the generic (non near-2^60) reduction are selected
+    PER PLAN from the environment when the plan is created (so setting them here, before Plan(), really switches the path); they
+    must give the same bits as the default balanced / near-2^60 path."""
     from fhe_b200.engine import to_device, to_host
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -97,25 +96,6 @@ def test_balanced_passes_ragged_batches_and_limb_ranges(fhe, oracle, chain, logn
         assert np.array_equal(y[1, l], oracle.ntt_forward(x[1, l], q))
     plan.inverse(d, limb_begin=2)
     assert np.array_equal(to_host(d), x)
-
-
-def test_fused_scheduler_ragged_groups_and_many_limbs(fhe, oracle, chain, monkeypatch):
-    from fhe_b200.engine import to_device, to_host
-    monkeypatch.setenv("FHE_B200_NTT_FUSED", "1")
-    monkeypatch.setenv("FHE_B200_NTT_BAL", "0")
-    n, mods = 1 << 13, chain[:7]
-    rng = np.random.default_rng(78)
-    for batch in (1, 3, 8, 9, 17):
-        x = _rand(rng, mods, n, batch)
-        plan = fhe.Plan(n, mods)
-        d = to_device(x); out = torch.empty_like(d)
-        plan.forward(d, out=out)
-        y = to_host(out)
-        for b in {0, batch - 1}:
-            for l, q in enumerate(mods):
-                assert np.array_equal(y[b, l], oracle.ntt_forward(x[b, l], q)), (batch, b, l)
-        plan.inverse(out)
-        assert np.array_equal(to_host(out), x)
 
 
 def test_tables_match_oracle(fhe, oracle, chain):

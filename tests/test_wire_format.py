@@ -39,7 +39,7 @@ def test_ciphertext_batch_shape():
     assert np.array_equal(got.reshape(3, 2, 3, 64), w.reshape(3, 2, 3, 64))
 
 
-@pytest.mark.parametrize("damage", ["magic", "version", "short", "long", "payload", "header", "chain", "wrap"])
+@pytest.mark.parametrize("damage", ["magic", "version", "short", "long", "payload", "header", "chain", "wrap", "more_limbs", "unreduced"])
 def test_rejects_damaged_objects(damage):
     chain, w = _sample()
     blob = bytearray(fhe_b200.wire_pack("public_key", w, chain))
@@ -61,6 +61,13 @@ def test_rejects_damaged_objects(damage):
         struct.pack_into("<Q", blob, 48, ((1 << 31) * (1 << 31) * (4 * 64 * 3 * 4)) % (1 << 64))
     elif damage == "chain":
         use_chain = oracle.prime_chain(4)[1:]
+    elif damage == "more_limbs":                       # a forged header with more limbs than the caller's chain must be
+        big = np.zeros((1, 8, 64), dtype=np.uint64)    # refused before the chain is read (it used to be hashed out of bounds)
+        blob = bytearray(fhe_b200.wire_pack("public_key", big, oracle.prime_chain(8)))
+        use_chain = chain                              # 3 moduli
+    elif damage == "unreduced":                        # a payload word that is not below its limb's modulus
+        w2 = w.copy(); w2.reshape(-1)[5] = np.uint64(2**64 - 1)
+        blob = bytearray(fhe_b200.wire_pack("public_key", w2, chain))
     with pytest.raises(fhe_b200.FheB200Error):
         fhe_b200.wire_unpack(bytes(blob), use_chain)
 
@@ -68,5 +75,5 @@ def test_rejects_damaged_objects(damage):
 def test_pack_rejects_bad_arguments():
     lib = fhe_b200.load_library()
     assert lib.fhe_b200_wire_pack(9, 64, 1, 1, 0, 0, None, None, None) != 0
-    assert lib.fhe_b200_wire_unpack(None, 0, None, None, None, None, None, None, None, None) != 0
+    assert lib.fhe_b200_wire_unpack(None, 0, None, 0, None, None, None, None, None, None, None) != 0
     assert b"wire" in lib.fhe_b200_last_error()
