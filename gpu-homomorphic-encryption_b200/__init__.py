@@ -74,6 +74,7 @@ def load_library() -> C.CDLL:
         "fhe_b200_modswitch_drop_last": [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
         "fhe_b200_bfv_create": [C.c_uint32] * 5 + [C.c_uint64, u64p, C.c_float, C.c_uint32, C.c_int, C.POINTER(_vp)],
         "fhe_b200_bfv_destroy": [_vp],
+        "fhe_b200_bfv_set_rng_key": [_vp, C.c_char_p],
         "fhe_b200_bfv_keygen": [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp],
         "fhe_b200_bfv_relinkeygen": [_vp, C.c_uint64, _vp, _vp, _vp],
         "fhe_b200_bfv_encrypt": [_vp, C.c_uint64, _vp, _vp, _vp, C.c_uint32, _vp],

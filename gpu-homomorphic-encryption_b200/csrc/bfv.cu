@@ -36,7 +36,8 @@ namespace fhe_b200 {
 template <int MODE>   // 0 ternary, 1 gaussian
 __global__ void __launch_bounds__(256) sample_small_kernel(u64* __restrict__ out, const LimbParams* __restrict__ params,
                                                            uint32_t logn, uint32_t limb_begin, uint32_t limb_count, uint32_t batch,
-                                                           u64 seed, long long item0, u64 stream, u32 thr, const u64* __restrict__ cdt, u32 cdt_len) {
+                                                           u64 seed, long long item0, u64 stream, u32 thr, const u64* __restrict__ cdt, u32 cdt_len,
+                                                           const RngKey rk) {
     __shared__ u64 scdt[kMaxCdt];
     if (MODE == 1) { for (u32 i = threadIdx.x; i < cdt_len; i += blockDim.x) scdt[i] = cdt[i]; __syncthreads(); }
     const uint32_t n = 1u << logn;
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(256) sample_small_kernel(u64* __restrict__ out
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
         const uint32_t j = (uint32_t)(g & (n - 1));
         const size_t b = g >> logn;
-        const u64 r = rng_at(rng_key(item0 < 0 ? seed : rng_item_seed(seed, (u64)item0 + b), stream), j);
+        const u64 r = rng_word(rk, item0 < 0 ? seed : rng_item_seed(seed, (u64)item0 + b), stream, j);
         const int v = MODE == 0 ? ternary_from(r, thr) : gauss_from(r, scdt, cdt_len);
         for (uint32_t l = 0; l < limb_count; l++) out[(b * limb_count + l) * n + j] = small_to_residue(v, params[limb_begin + l].q);
     }
@@ -59,15 +60,14 @@ __global__ void __launch_bounds__(256) expand_small_kernel(u64* __restrict__ out
 }
 // uniform residues: limb l uses stream stream_base + l
 __global__ void __launch_bounds__(256) sample_uniform_kernel(u64* __restrict__ out, const LimbParams* __restrict__ params, uint32_t logn,
-                                                             uint32_t limb_begin, uint32_t limb_count, u64 seed, u64 stream_base) {
+                                                             uint32_t limb_begin, uint32_t limb_count, u64 seed, u64 stream_base, const RngKey rk) {
     const uint32_t n = 1u << logn;
     const size_t total = (size_t)limb_count * n;
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
         const uint32_t j = (uint32_t)(g & (n - 1));
         const uint32_t l = (uint32_t)(g >> logn);
         const LimbParams P = params[limb_begin + l];
-        const u64 key = rng_key(seed, stream_base + l);
-        out[g] = barrett128(rng_at(key, 2ull * j), rng_at(key, 2ull * j + 1), P.q, P.mu_hi, P.mu_lo);
+        out[g] = barrett128(rng_word(rk, seed, stream_base + l, 2ull * j), rng_word(rk, seed, stream_base + l, 2ull * j + 1), P.q, P.mu_hi, P.mu_lo);
     }
 }
 
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) enc_mul_kernel(u64* __restrict__ ct, cons
 // c0 += e1 + delta*m ; c1 += e2   (coefficient form; e1, e2 regenerated from the counter generator)
 __global__ void __launch_bounds__(256) enc_finish_kernel(u64* __restrict__ ct, const u64* __restrict__ pt, const LimbParams* __restrict__ params,
                                                          const u64* __restrict__ delta, const u64* __restrict__ cdt, u32 cdt_len,
-                                                         uint32_t logn, uint32_t L, uint32_t batch, u64 seed, u64 item0) {
+                                                         uint32_t logn, uint32_t L, uint32_t batch, u64 seed, u64 item0, const RngKey rk) {
     __shared__ u64 scdt[kMaxCdt];
     for (u32 i = threadIdx.x; i < cdt_len; i += blockDim.x) scdt[i] = cdt[i];
     __syncthreads();
@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(256) enc_finish_kernel(u64* __restrict__ ct, c
         const uint32_t j = (uint32_t)(g & (n - 1));
         const size_t b = g >> logn;
         const u64 sd = rng_item_seed(seed, item0 + b);
-        const int e1 = gauss_from(rng_at(rng_key(sd, 1), j), scdt, cdt_len);
-        const int e2 = gauss_from(rng_at(rng_key(sd, 2), j), scdt, cdt_len);
+        const int e1 = gauss_from(rng_word(rk, sd, 1, j), scdt, cdt_len);
+        const int e2 = gauss_from(rng_word(rk, sd, 2, j), scdt, cdt_len);
         const u64 m = pt[g];
         for (uint32_t i = 0; i < L; i++) {
             const LimbParams P = params[i];
@@ -280,16 +280,15 @@ static inline uint32_t grid_for(const fhe_b200_bfv* c, size_t items) {
 }
 
 // host twin of the hamming-weight ternary sampler
-static void host_ternary_hw(std::vector<int8_t>& s, uint32_t n, u64 seed, u64 stream, uint32_t hw) {
+static void host_ternary_hw(std::vector<int8_t>& s, uint32_t n, u64 seed, u64 stream, uint32_t hw, const RngKey& rk) {
     std::vector<uint32_t> perm(n);
     for (uint32_t j = 0; j < n; j++) perm[j] = j;
     s.assign(n, 0);
     if (hw > n) hw = n;
-    const u64 k0 = rng_key(seed, stream), k1 = rng_key(seed, stream + 1);
     for (uint32_t i = 0; i < hw; i++) {
-        const uint32_t j = i + (uint32_t)(rng_at(k0, i) % (n - i));
+        const uint32_t j = i + (uint32_t)(rng_word(rk, seed, stream, i) % (n - i));
         const uint32_t tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
-        s[perm[i]] = (rng_at(k1, i) & 1) ? -1 : 1;
+        s[perm[i]] = (rng_word(rk, seed, stream + 1, i) & 1) ? -1 : 1;
     }
 }
 
@@ -418,6 +417,17 @@ extern "C" int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t 
     return 0;
 }
 
+// 256-bit key for the ChaCha20 generator (NULL: back to the reproducible splitmix generator of the tests).  With a key set, the
+// 64-bit seeds of keygen / encrypt / ... only separate calls; the randomness is as good as the key (take it from the OS).
+extern "C" int fhe_b200_bfv_set_rng_key(fhe_b200_bfv* c, const uint8_t* h_key32) {
+    FHE_REQUIRE(c, "bfv_set_rng_key: null context");
+    if (!h_key32) { c->rng.on = 0; for (int i = 0; i < 8; i++) c->rng.k[i] = 0; return 0; }
+    for (int i = 0; i < 8; i++)
+        c->rng.k[i] = (uint32_t)h_key32[4 * i] | ((uint32_t)h_key32[4 * i + 1] << 8) | ((uint32_t)h_key32[4 * i + 2] << 16) | ((uint32_t)h_key32[4 * i + 3] << 24);
+    c->rng.on = 1;
+    return 0;
+}
+
 extern "C" int fhe_b200_bfv_info(const fhe_b200_bfv* c, uint32_t* n, uint32_t* L, uint32_t* R, uint32_t* K, uint32_t* dnum, uint64_t* t) {
     FHE_REQUIRE(c, "bfv_info: null context");
     if (n) *n = c->n; if (L) *L = c->L; if (R) *R = c->R; if (K) *K = c->K; if (dnum) *dnum = c->dnum; if (t) *t = c->t;
@@ -435,7 +445,7 @@ extern "C" int fhe_b200_bfv_keygen(fhe_b200_bfv* c, uint64_t seed_sk, uint64_t s
     // secret: stream 0 (signs: stream 1 when a hamming weight is set)
     if (c->hw) {
         std::vector<int8_t> s;
-        host_ternary_hw(s, n, seed_sk, 0, c->hw);
+        host_ternary_hw(s, n, seed_sk, 0, c->hw, c->rng);
         int8_t* d_s = nullptr;
         FHE_CUDA(cudaMallocAsync(&d_s, n, st));
         FHE_CUDA(cudaMemcpyAsync(d_s, s.data(), n, cudaMemcpyHostToDevice, st));
@@ -444,16 +454,16 @@ extern "C" int fhe_b200_bfv_keygen(fhe_b200_bfv* c, uint64_t seed_sk, uint64_t s
         FHE_LAUNCH_CHECK();
         FHE_CUDA(cudaFreeAsync(d_s, st));
     } else {
-        sample_small_kernel<0><<<grid_for(c, n), 256, 0, st>>>(d_sk, prm, c->logn, 0, A, 1, seed_sk, -1, 0, c->thr, c->d_cdt, c->cdt_len);
+        sample_small_kernel<0><<<grid_for(c, n), 256, 0, st>>>(d_sk, prm, c->logn, 0, A, 1, seed_sk, -1, 0, c->thr, c->d_cdt, c->cdt_len, c->rng);
         FHE_LAUNCH_CHECK();
     }
     FHE_TRY(launch_ntt(c->plan, d_sk, d_sk, 1, 0, A, false, st));
     // public key: e on stream 2, a on streams 16+i
     uint64_t* pk0 = d_pk; uint64_t* pk1 = d_pk + (size_t)L * n;
-    sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(pk0, prm, c->logn, 0, L, 1, seed_pk, -1, 2, 0, c->d_cdt, c->cdt_len);
+    sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(pk0, prm, c->logn, 0, L, 1, seed_pk, -1, 2, 0, c->d_cdt, c->cdt_len, c->rng);
     FHE_LAUNCH_CHECK();
     FHE_TRY(launch_ntt(c->plan, pk0, pk0, 1, 0, L, false, st));
-    sample_uniform_kernel<<<grid_for(c, (size_t)L * n), 256, 0, st>>>(pk1, prm, c->logn, 0, L, seed_pk, 16);
+    sample_uniform_kernel<<<grid_for(c, (size_t)L * n), 256, 0, st>>>(pk1, prm, c->logn, 0, L, seed_pk, 16, c->rng);
     FHE_LAUNCH_CHECK();
     pk_finish_kernel<<<grid_for(c, (size_t)L * n), 256, 0, st>>>(pk0, pk1, d_sk, prm, c->logn, (size_t)L * n);
     FHE_LAUNCH_CHECK();
@@ -469,10 +479,10 @@ extern "C" int fhe_b200_bfv_relinkeygen(fhe_b200_bfv* c, uint64_t seed, const ui
     for (uint32_t d = 0; d < c->dnum; d++) {
         uint64_t* b = d_rlk + (size_t)(2 * d) * W * n; uint64_t* a = b + (size_t)W * n;
         const uint64_t base = 1024ull * (d + 1);
-        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, -1, base + 512, 0, c->d_cdt, c->cdt_len);
+        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, -1, base + 512, 0, c->d_cdt, c->cdt_len, c->rng);
         FHE_LAUNCH_CHECK();
         FHE_TRY(launch_ntt(c->plan, b, b, 1, 0, W, false, st));
-        sample_uniform_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base);
+        sample_uniform_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base, c->rng);
         FHE_LAUNCH_CHECK();
         rlk_finish_kernel<<<grid_for(c, (size_t)W * n), 256, 0, st>>>(b, a, d_sk, nullptr, prm, c->d_pmodq, c->logn, d * c->alpha, (d + 1) * c->alpha, (size_t)W * n);
         FHE_LAUNCH_CHECK();
@@ -527,13 +537,13 @@ extern "C" int fhe_b200_bfv_encrypt(fhe_b200_bfv* c, uint64_t seed, const uint64
         uint64_t* u = c->d_ws + (size_t)first * ln;
         uint64_t* ct = d_ct + (size_t)first * 2 * ln;
         const uint64_t* pt = d_pt + (size_t)first * n;
-        sample_small_kernel<0><<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(u, prm, c->logn, 0, L, cnt, seed, (long long)first, 0, c->thr, c->d_cdt, c->cdt_len);
+        sample_small_kernel<0><<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(u, prm, c->logn, 0, L, cnt, seed, (long long)first, 0, c->thr, c->d_cdt, c->cdt_len, c->rng);
         FHE_LAUNCH_CHECK();
         FHE_TRY(launch_ntt(c->plan, u, u, cnt, 0, L, false, st));
         enc_mul_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(ct, u, d_pk, prm, c->logn, L, cnt * ln);
         count_launch();
         FHE_TRY(launch_ntt(c->plan, ct, ct, 2 * cnt, 0, L, true, st));
-        enc_finish_kernel<<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(ct, pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, cnt, seed, (uint64_t)first);
+        enc_finish_kernel<<<grid_for(c, (size_t)cnt * n), 256, 0, st>>>(ct, pt, prm, c->d_delta, c->d_cdt, c->cdt_len, c->logn, L, cnt, seed, (uint64_t)first, c->rng);
         FHE_LAUNCH_CHECK();
         return 0;
     });
@@ -930,10 +940,10 @@ extern "C" int fhe_b200_bfv_galoiskeygen(fhe_b200_bfv* c, uint64_t seed, uint32_
     for (uint32_t d = 0; d < c->dnum; d++) {
         uint64_t* b = d_gk + (size_t)(2 * d) * wn; uint64_t* a = b + wn;
         const uint64_t base = 1024ull * (d + 1);
-        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, -1, base + 512, 0, c->d_cdt, c->cdt_len);
+        sample_small_kernel<1><<<grid_for(c, n), 256, 0, st>>>(b, prm, c->logn, 0, W, 1, seed, -1, base + 512, 0, c->d_cdt, c->cdt_len, c->rng);
         FHE_LAUNCH_CHECK();
         FHE_TRY(launch_ntt(c->plan, b, b, 1, 0, W, false, st));
-        sample_uniform_kernel<<<grid_for(c, wn), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base);
+        sample_uniform_kernel<<<grid_for(c, wn), 256, 0, st>>>(a, prm, c->logn, 0, W, seed, base, c->rng);
         FHE_LAUNCH_CHECK();
         rlk_finish_kernel<<<grid_for(c, wn), 256, 0, st>>>(b, a, d_sk, sg, prm, c->d_pmodq, c->logn, d * c->alpha, (d + 1) * c->alpha, wn);
         FHE_LAUNCH_CHECK();

@@ -8,6 +8,7 @@ struct fhe_b200_bfv {
     uint64_t t = 0;
     int device = 0;
     uint32_t hw = 0, thr = 1u << 31;
+    fhe_b200::RngKey rng = {{0, 0, 0, 0, 0, 0, 0, 0}, 0};   // on = 0: reproducible splitmix generator; fhe_b200_bfv_set_rng_key switches to ChaCha20
     std::vector<uint64_t> primes;
     fhe_b200_plan* plan = nullptr;                       // all L+R primes
     fhe_b200_lincomb *q2r = nullptr, *scale = nullptr, *r2q = nullptr, *moddown = nullptr, *dec = nullptr;

@@ -250,23 +250,26 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                 }
                 reinterpret_cast<u64*>(sIdx[k])[(size_t)b * sIdx[3 * a.T + k] + j] = res;
             };
+            // the epilogue operands (extra limb, ModDown minuend / addend) of a pair are loaded one pair ahead: their latency hides
+            // behind the previous pair's reductions
+            u64 ex0 = 0, su0 = 0, ad0 = 0, ex1 = 0, su1 = 0, ad1 = 0;
+            if (cnt >= 2) { operands(k0, ex0, su0, ad0); operands(k0 + 1, ex1, su1, ad1); }
 #pragma unroll 1
             for (uint32_t tl = 0; tl + 1 < cnt; tl += 2) {
                 const uint32_t k = k0 + tl;
                 u32 p0[16], p1[16];
                 tc_ld16(tmem_rd + tl * 16, p0);
                 tc_ld16(tmem_rd + tl * 16 + 16, p1);
-                u64 ex0, su0, ad0, ex1, su1, ad1;                    // epilogue operands while the TMEM loads are in flight
-                operands(k, ex0, su0, ad0); operands(k + 1, ex1, su1, ad1);
+                const u64 cex0 = ex0, csu0 = su0, cad0 = ad0, cex1 = ex1, csu1 = su1, cad1 = ad1;
+                if (tl + 3 < cnt) { operands(k + 2, ex0, su0, ad0); operands(k + 3, ex1, su1, ad1); }
                 tc_wait_ld();
-                finish(k, p0, ex0, su0, ad0);
-                finish(k + 1, p1, ex1, su1, ad1);
+                finish(k, p0, cex0, csu0, cad0);
+                finish(k + 1, p1, cex1, csu1, cad1);
             }
             if (cnt & 1) {
                 const uint32_t k = k0 + cnt - 1;
                 u32 p0[16];
                 tc_ld16(tmem_rd + (cnt - 1) * 16, p0);
-                u64 ex0, su0, ad0;
                 operands(k, ex0, su0, ad0);
                 tc_wait_ld();
                 finish(k, p0, ex0, su0, ad0);

@@ -247,4 +247,37 @@ FHE_HD u64 rng_key(u64 seed, u64 stream) { return mix64(mix64(seed) + 0x9E3779B9
 FHE_HD u64 rng_item_seed(u64 seed, u64 item) { return mix64(mix64(seed ^ 0x6A09E667F3BCC909ULL) + 0x9E3779B97F4A7C15ULL * (item + 1)); }
 FHE_HD u64 rng_at(u64 key, u64 idx) { return mix64(key + 0x9E3779B97F4A7C15ULL * (idx + 1)); }
 
+// ---- keyed generator for keys that leave the test bench: ChaCha20 (RFC 8439 block function) ------------------------------------
+// The splitmix generator above is a reproducible counter hash keyed by 64 bits -- fine for tests and benchmarks, NOT for real keys.
+// With a 256-bit key set on the context (fhe_b200_bfv_set_rng_key) every random word comes from ChaCha20 instead:
+//   block counter = idx / 8, nonce = (seed low, seed high, stream), word idx % 8 of the 64-byte block (little-endian pairs);
+// the caller's 64-bit seed then only separates calls (a nonce) and need not be secret.  Same samplers, same streams.
+struct RngKey { u32 k[8]; u32 on; };
+FHE_HD u32 rotl32(u32 x, int n) { return (x << n) | (x >> (32 - n)); }
+#define FHE_QR(a, b, c, d) a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); a += b; d ^= a; d = rotl32(d, 8); c += d; b ^= c; b = rotl32(b, 7);
+FHE_HD u64 chacha20_word(const RngKey& rk, u32 counter, u32 n0, u32 n1, u32 n2, u32 word) {
+    const u32 i0 = 0x61707865u, i1 = 0x3320646eu, i2 = 0x79622d32u, i3 = 0x6b206574u;
+    u32 x0 = i0, x1 = i1, x2 = i2, x3 = i3, x4 = rk.k[0], x5 = rk.k[1], x6 = rk.k[2], x7 = rk.k[3], x8 = rk.k[4], x9 = rk.k[5],
+        x10 = rk.k[6], x11 = rk.k[7], x12 = counter, x13 = n0, x14 = n1, x15 = n2;
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        FHE_QR(x0, x4, x8, x12) FHE_QR(x1, x5, x9, x13) FHE_QR(x2, x6, x10, x14) FHE_QR(x3, x7, x11, x15)
+        FHE_QR(x0, x5, x10, x15) FHE_QR(x1, x6, x11, x12) FHE_QR(x2, x7, x8, x13) FHE_QR(x3, x4, x9, x14)
+    }
+    x0 += i0; x1 += i1; x2 += i2; x3 += i3; x4 += rk.k[0]; x5 += rk.k[1]; x6 += rk.k[2]; x7 += rk.k[3];
+    x8 += rk.k[4]; x9 += rk.k[5]; x10 += rk.k[6]; x11 += rk.k[7]; x12 += counter; x13 += n0; x14 += n1; x15 += n2;
+    u32 lo, hi;
+    switch (word & 7u) {
+        case 0: lo = x0; hi = x1; break;   case 1: lo = x2; hi = x3; break;   case 2: lo = x4; hi = x5; break;   case 3: lo = x6; hi = x7; break;
+        case 4: lo = x8; hi = x9; break;   case 5: lo = x10; hi = x11; break; case 6: lo = x12; hi = x13; break; default: lo = x14; hi = x15; break;
+    }
+    return ((u64)hi << 32) | lo;
+}
+#undef FHE_QR
+// word idx of stream `stream` of the call / batch item seeded `seed`: the one entry point of every sampler
+FHE_HD u64 rng_word(const RngKey& rk, u64 seed, u64 stream, u64 idx) {
+    if (!rk.on) return rng_at(rng_key(seed, stream), idx);
+    return chacha20_word(rk, (u32)(idx >> 3), (u32)seed, (u32)(seed >> 32), (u32)stream, (u32)idx);
+}
+
 }  // namespace fhe_b200

@@ -378,6 +378,11 @@ class BfvContext:
 
     def _empty(self, *shape): return torch.empty(shape, dtype=torch.int64, device=self.dev)
 
+    def set_rng_key(self, key32: bytes | None):
+        """256-bit key -> samplers draw from ChaCha20 (production); None -> the reproducible splitmix generator (tests)"""
+        assert key32 is None or len(key32) == 32
+        check(self.lib.fhe_b200_bfv_set_rng_key(self.h, key32))
+
     def keygen(self, seed_sk, seed_pk):
         sk = self._empty(self.L + self.R, self.n); pk = self._empty(2, self.L, self.n)
         check(self.lib.fhe_b200_bfv_keygen(self.h, seed_sk, seed_pk, _ptr(sk), _ptr(pk), _stream()))

@@ -87,11 +87,15 @@ public:
         params_.ntt_engine = new NTTEngine(params_.n, params_.modulus_chain[0]);
         params_.poly_ops = new PolynomialOps(params_.n, params_.modulus_chain[0], params_.ntt_engine);
         detail::check_cuda(cudaStreamCreate(&stream_), "cudaStreamCreate");
-        // seeds: fresh OS entropy for every call (the secret key's seed is its own draw, never derived from a seed that also generates
-        // public values); init_rng(seed) switches to a reproducible sequence for tests.  NOTE the generator behind the C ABI is a
-        // counter-based splitmix64 hash keyed by 64 bits per call -- a placeholder like the reference's samplers
-        // (/root/reference/src/fhe.cu:238-257), not a CSPRNG: see DESIGN.md "Randomness" before using keys outside tests.
+        // randomness: by default a 256-bit ChaCha20 key from the OS (fhe_b200_bfv_set_rng_key) and a fresh 64-bit nonce per call (the
+        // secret key's is its own draw); init_rng(seed) or FHE_B200_DETERMINISTIC_SEED switch to the reproducible splitmix generator
+        // the tests and the CPU oracle share (DESIGN.md "Randomness").
         if (const char* e = std::getenv("FHE_B200_DETERMINISTIC_SEED")) init_rng(std::strtoull(e, nullptr, 0));
+        else {                  // production default: ChaCha20 keyed with 256 bits from the OS
+            std::random_device rd; uint8_t key[32];
+            for (int i = 0; i < 32; i += 4) { const uint32_t w = rd(); key[i] = (uint8_t)w; key[i + 1] = (uint8_t)(w >> 8); key[i + 2] = (uint8_t)(w >> 16); key[i + 3] = (uint8_t)(w >> 24); }
+            detail::check(fhe_b200_bfv_set_rng_key(ctx_, key), "set_rng_key");
+        }
     }
     ~FHEContext() {
         delete params_.rns_ctx; delete params_.poly_ops; delete params_.ntt_engine;
@@ -302,7 +306,7 @@ private:
         if (!dst.components.empty()) { synchronize(); release(dst); }
         dst = src; src.components.clear();
     }
-    void init_rng(uint64_t seed) { seed_ = seed; calls_ = 0; deterministic_ = true; }
+    void init_rng(uint64_t seed) { seed_ = seed; calls_ = 0; deterministic_ = true; fhe_b200_bfv_set_rng_key(ctx_, nullptr); }
     // deterministic mode: a hashed call counter -- call k of this context gets mix(base seed, k); the library hashes the seed again
     // per stream / batch item.  Default mode: 64 fresh bits from the OS per call.
     uint64_t next_seed() {

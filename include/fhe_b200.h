@@ -165,6 +165,11 @@ int fhe_b200_bfv_create(uint32_t n, uint32_t L, uint32_t R, uint32_t K, uint32_t
                         const uint64_t* h_moduli, float sigma, uint32_t hamming_weight, int device,
                         fhe_b200_bfv** out);
 int fhe_b200_bfv_destroy(fhe_b200_bfv* ctx);
+/* Randomness.  By default every sampler draws from a reproducible counter hash (splitmix64) keyed by the call's 64-bit seed: right
+ * for tests and benchmarks, NOT for keys that matter.  fhe_b200_bfv_set_rng_key gives the context a 256-bit key (take it from the
+ * OS); from then on every random word is ChaCha20(key; nonce = call seed and stream; counter = word index / 8) and the 64-bit seeds
+ * only separate calls.  NULL switches back.  (The reference's samplers are placeholders seeded by rand(), src/fhe.cu:238-257.) */
+int fhe_b200_bfv_set_rng_key(fhe_b200_bfv* ctx, const uint8_t* h_key32);
 /* FHEContext::keygen (src/fhe.cu:54-74) */
 int fhe_b200_bfv_keygen(fhe_b200_bfv* ctx, uint64_t seed_sk, uint64_t seed_pk, uint64_t* d_sk, uint64_t* d_pk,
                         void* stream);

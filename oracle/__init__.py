@@ -255,6 +255,24 @@ def bitrev_perm(n: int) -> np.ndarray:
     return r
 
 
+def set_rng_key(key32: bytes | None):
+    """mirror of fhe_b200_bfv_set_rng_key: 32-byte key -> every sampler draws from ChaCha20; None -> the splitmix generator"""
+    L = lib()
+    L.orc_set_rng_key.argtypes = [C.c_char_p]
+    L.orc_set_rng_key.restype = None
+    assert key32 is None or len(key32) == 32
+    L.orc_set_rng_key(key32)
+
+
+def chacha20_block(key_words, counter, nonce_words):
+    """RFC 8439 block function -> 16 uint32 words (known-answer test of the restatement)"""
+    L = lib()
+    k = (C.c_uint32 * 8)(*key_words); nn = (C.c_uint32 * 3)(*nonce_words); out = (C.c_uint32 * 16)()
+    L.orc_chacha20_block_raw.restype = None
+    L.orc_chacha20_block_raw(k, C.c_uint32(counter), nn, out)
+    return [int(v) for v in out]
+
+
 def rng_key(seed: int, stream: int) -> int:
     return int(lib().orc_rng_key_of(C.c_uint64(seed & (2**64 - 1)), C.c_uint64(stream & (2**64 - 1))))
 

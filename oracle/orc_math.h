@@ -62,7 +62,33 @@ static inline u64 orc_mix64(u64 z) {
 /* key(seed, stream) = mix64(mix64(seed) + G (stream + 1)): the seed is hashed before the stream offset is added, so G-spaced or
  * consecutive seeds and consecutive streams cannot alias;  word idx = mix64(key + G (idx + 1)). */
 static inline u64 orc_rng_key(u64 seed, u64 stream) { return orc_mix64(orc_mix64(seed) + 0x9E3779B97F4A7C15ULL * (stream + 1)); }
+/* Keyed mode (test infrastructure mirror of fhe_b200_bfv_set_rng_key): when a 256-bit key is set (orc_set_rng_key), word idx is
+ * word idx % 8 of the ChaCha20 block (RFC 8439 block function, 20 rounds) with counter idx / 8 and nonce (seed low, seed high, stream). */
+extern u32 orc_chacha_key[8];
+extern int orc_chacha_on;
+static inline u32 orc_rotl32(u32 x, int n) { return (x << n) | (x >> (32 - n)); }
+static inline void orc_chacha20_block(const u32 key[8], u32 counter, const u32 nonce[3], u32 out[16]) {
+    u32 st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                  counter, nonce[0], nonce[1], nonce[2]};
+    u32 x[16];
+    for (int i = 0; i < 16; i++) x[i] = st[i];
+#define ORC_QR(a, b, c, d) x[a] += x[b]; x[d] = orc_rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = orc_rotl32(x[b] ^ x[c], 12); \
+                           x[a] += x[b]; x[d] = orc_rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = orc_rotl32(x[b] ^ x[c], 7);
+    for (int r = 0; r < 10; r++) {
+        ORC_QR(0, 4, 8, 12) ORC_QR(1, 5, 9, 13) ORC_QR(2, 6, 10, 14) ORC_QR(3, 7, 11, 15)
+        ORC_QR(0, 5, 10, 15) ORC_QR(1, 6, 11, 12) ORC_QR(2, 7, 8, 13) ORC_QR(3, 4, 9, 14)
+    }
+#undef ORC_QR
+    for (int i = 0; i < 16; i++) out[i] = x[i] + st[i];
+}
 static inline u64 orc_rng64(u64 seed, u64 stream, u64 idx) {
+    if (orc_chacha_on) {
+        const u32 nonce[3] = {(u32)seed, (u32)(seed >> 32), (u32)stream};
+        u32 o[16];
+        orc_chacha20_block(orc_chacha_key, (u32)(idx >> 3), nonce, o);
+        const u32 w = (u32)idx & 7u;
+        return ((u64)o[2 * w + 1] << 32) | o[2 * w];
+    }
     return orc_mix64(orc_rng_key(seed, stream) + 0x9E3779B97F4A7C15ULL * (idx + 1));
 }
 /* seed of batch item `item` of a call seeded with `seed` (a domain of its own) */

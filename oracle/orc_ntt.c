@@ -298,6 +298,16 @@ u64 orc_sub_mod(u64 a, u64 b, u64 q) { return orc_submod(a % q, b % q, q); }
 u64 orc_mul_mod(u64 a, u64 b, u64 q) { return orc_mulmod(a % q, b % q, q); }
 u64 orc_pow_mod(u64 a, u64 e, u64 q) { return orc_powmod(a, e, q); }
 u64 orc_inv_mod(u64 a, u64 q) { return orc_invmod_prime(a, q); }
+u32 orc_chacha_key[8];
+int orc_chacha_on = 0;
+/* key32 = NULL: back to the splitmix generator */
+void orc_set_rng_key(const unsigned char *key32) {
+    orc_chacha_on = key32 != NULL;
+    for (int i = 0; i < 8; i++)
+        orc_chacha_key[i] = key32 ? ((u32)key32[4 * i] | ((u32)key32[4 * i + 1] << 8) | ((u32)key32[4 * i + 2] << 16) | ((u32)key32[4 * i + 3] << 24)) : 0;
+}
+/* RFC 8439 block function on explicit inputs (known-answer test) */
+void orc_chacha20_block_raw(const u32 *key, u32 counter, const u32 *nonce, u32 *out) { orc_chacha20_block(key, counter, nonce, out); }
 u64 orc_rng(u64 seed, u64 stream, u64 idx) { return orc_rng64(seed, stream, idx); }
 u64 orc_rng_key_of(u64 seed, u64 stream) { return orc_rng_key(seed, stream); }
 u64 orc_item_seed_of(u64 seed, u64 item) { return orc_item_seed(seed, item); }

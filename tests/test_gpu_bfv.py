@@ -494,3 +494,35 @@ def test_mod_switch_to_level_vs_oracle(fhe, oracle):
             assert np.array_equal(low[b], o.mod_switch_to_level(h[b], drop)), (drop, b)
     with pytest.raises(fhe.FheB200Error):
         g.mod_switch_to_level(ct, L)
+
+
+@pytest.mark.parametrize("hw", [64, 0])
+def test_keyed_chacha20_generator_vs_oracle(fhe, oracle, hw):
+    """fhe_b200_bfv_set_rng_key: with a 256-bit key every sampler (host Fisher-Yates secret, device ternary / Gaussian / uniform,
+    the errors regenerated inside encrypt) draws from ChaCha20; keys and ciphertexts equal the oracle's keyed mode word for word,
+    differ from the splitmix mode, and switching the key off restores the reproducible generator."""
+    from fhe_b200.engine import to_device, to_host
+    p, g, o = _setup(fhe, oracle, "small", hw)
+    n, t = p["n"], p["t"]
+    key = bytes((7 * i + 3) & 0xFF for i in range(32))
+    sk0, pk0 = g.keygen(11, 12)
+    m = np.random.default_rng(5).integers(0, t, (3, n), dtype=np.uint64)
+    try:
+        g.set_rng_key(key); oracle.set_rng_key(key)
+        sk, pk = g.keygen(11, 12)
+        _, osk = o.secret_keygen(11); opk = o.public_keygen(12, osk)
+        assert np.array_equal(to_host(sk), osk) and np.array_equal(to_host(pk), opk)
+        assert not np.array_equal(to_host(sk), to_host(sk0)) and not np.array_equal(to_host(pk), to_host(pk0))
+        rlk = g.relinkey_gen(13, sk)
+        assert np.array_equal(to_host(rlk), o.relin_keygen(13, osk))
+        ct = g.encrypt(500, to_device(m), pk)
+        h = to_host(ct)
+        for b in range(3):
+            assert np.array_equal(h[b], o.encrypt(500, m[b], opk, item=b)), b
+        assert np.array_equal(to_host(g.decrypt(ct, sk)), m)
+        prod = g.multiply(ct[0:1].contiguous(), ct[1:2].contiguous(), rlk)
+        assert np.array_equal(to_host(g.decrypt(prod, sk))[0], oracle.schoolbook_negacyclic(m[0], m[1], t))
+    finally:
+        g.set_rng_key(None); oracle.set_rng_key(None)
+    sk1, pk1 = g.keygen(11, 12)
+    assert torch.equal(sk1, sk0) and torch.equal(pk1, pk0)

@@ -390,3 +390,23 @@ def test_generator_keys_never_alias_across_calls_items_and_streams(oracle):
                     use(("enc", call, b, st), oracle.item_seed(sd, b), st)
     # the old derivation would have failed this: (seed, stream s) == (seed + G, stream s - 1)
     assert oracle.rng_key(7, 1) != oracle.rng_key((7 + G) & (2**64 - 1), 0)
+
+
+def test_chacha20_block_known_answer_and_keyed_samplers(oracle):
+    """the keyed generator (mirror of fhe_b200_bfv_set_rng_key): RFC 8439 section 2.3.2 block test vector, and the samplers switch to
+    it and back"""
+    key = [int.from_bytes(bytes(range(4 * i, 4 * i + 4)), "little") for i in range(8)]
+    out = oracle.chacha20_block(key, 1, [0x09000000, 0x4A000000, 0x00000000])
+    assert out == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3, 0xC7F4D1C7, 0x0368C033, 0x9AAA2204, 0x4E6CD4C3,
+                   0x466482D2, 0x09AA9F07, 0x05D7C214, 0xA2028BD9, 0xD19C12B5, 0xB94E16DE, 0xE883D0CB, 0x4E3C50A2]
+    plain = oracle.sample_ternary(256, 7, 0)
+    try:
+        oracle.set_rng_key(bytes(range(32)))
+        # nonce (seed low, seed high, stream) = (0x09000000, 0x4a000000, 0), counter 1 = words 8..15
+        seed = 0x4A00000009000000
+        assert [oracle.rng64(seed, 0, 8 + w) for w in range(8)] == [(out[2 * w + 1] << 32) | out[2 * w] for w in range(8)]
+        keyed = oracle.sample_ternary(256, 7, 0)
+        assert not np.array_equal(keyed, plain) and set(np.unique(keyed)) <= {-1, 0, 1}
+    finally:
+        oracle.set_rng_key(None)
+    assert np.array_equal(oracle.sample_ternary(256, 7, 0), plain)
