@@ -392,8 +392,8 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": POLYS * LIMBS * N * 8,
                     "d2h_bytes_per_step": POLYS * LIMBS * N * 8, "steps": e2e_steps,
                     "api": "fhe_b200_ntt_host (pinned host buffer, 3-stream chunk pipeline)",
-                    "pcie_GBs_per_direction_per_gpu": e2e_val / world * UNIT_BYTES / 2 / 1e9,
-                    "note": "bound by the host link: every limb-transform moves 512 KiB in and 512 KiB out over PCIe; ranks of one node "
+                    "pcie_GBs_per_direction_per_gpu": e2e_val / world * (UNIT_BYTES / 4) / 1e9,    # a step moves every limb once in and once out for TWO transforms
+                    "note": "bound by the host link: every limb is copied in (512 KiB), transformed forward and back, and copied out (512 KiB); ranks of one node "
                             "share the host's memory and root complexes, so this figure does not scale with the GPU count"},
             "roofline": {"bound": "imad", "achieved": (dom_ops / 1e12) if dom_ops else None, "peak": mix_peak / 1e12, "unit": "T IMAD-class op/s",
                          "frac": (dom_ops / mix_peak) if dom_ops else None, "traffic": traffic,
