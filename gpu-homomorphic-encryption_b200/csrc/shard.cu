@@ -168,6 +168,11 @@ struct fhe_b200_shard {
     const uint64_t *tab_q2r_out = nullptr, *tab_q2r_copy = nullptr;
     std::vector<const uint64_t*> tab_up_out, tab_up_copy;
     unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+    // CUDA graphs of whole multiplies, keyed by the argument tuple (the flags are device-side epochs, so a graph replays correctly):
+    // at one ciphertext pair per multiply a rank's 27 kernels are 5-15 us each and the launch gaps are a fifth of the time
+    struct GraphKey { const void *a, *b, *key; void* out; uint32_t batch; int fused; };
+    struct GraphEntry { GraphKey k; cudaGraphExec_t exec; uint32_t seen; };
+    std::vector<GraphEntry> graphs;
     uint64_t nvlink_words_per_op = 0;                                         // words this rank stores into OTHER ranks per multiply (batch 1)
 };
 
@@ -187,6 +192,7 @@ extern "C" int fhe_b200_shard_destroy(fhe_b200_shard* s) {
     if (!s) return 0;
     DeviceGuard dev_guard(s->ctx->device);
     cudaDeviceSynchronize();
+    for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int r = 0; r < s->world; r++) if (s->opened[r] && s->peer[r]) cudaIpcCloseMemHandle(s->peer[r]);
     cudaFree(s->slab); cudaFree(s->ws); cudaFree(s->d_tabs);
     delete s;
@@ -496,7 +502,42 @@ extern "C" int fhe_b200_bfv_multiply_relin_sharded(fhe_b200_shard* s, const uint
     FHE_TRY(sharded_check_args(s, d_a, d_b, d_key, d_out, batch));
     if (!batch) return 0;
     DeviceGuard dev_guard(s->ctx->device);
-    for (int stage = 0; stage < 5; stage++) FHE_TRY(sharded_stage(s, stage, d_a, d_b, d_key, d_out, batch, (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    // The second call with the same arguments captures the five stages into a CUDA graph; later calls replay it (FHE_B200_SHARD_GRAPH=0:
+    // always launch kernel by kernel).  The first call runs eagerly, so one-off work (function attributes, allocations) is never captured.
+    const char* ge = getenv("FHE_B200_SHARD_GRAPH");
+    const bool want_graph = !(ge && atoi(ge) == 0) && st != nullptr;
+    const char* fe = getenv("FHE_B200_FUSED_TILE");
+    const fhe_b200_shard::GraphKey key{d_a, d_b, d_key, d_out, batch, (fe && atoi(fe) != 0) ? 1 : 0};
+    fhe_b200_shard::GraphEntry* ent = nullptr;
+    if (want_graph) {
+        for (auto& g : s->graphs)
+            if (g.k.a == key.a && g.k.b == key.b && g.k.key == key.key && g.k.out == key.out && g.k.batch == key.batch && g.k.fused == key.fused) { ent = &g; break; }
+        if (!ent) {
+            if (s->graphs.size() >= 16) { for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec); s->graphs.clear(); }
+            s->graphs.push_back({key, nullptr, 0});
+            ent = &s->graphs.back();
+        }
+        if (ent->exec) { FHE_CUDA(cudaGraphLaunch(ent->exec, st)); count_launch(); return 0; }
+        if (++ent->seen == 2) {
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                int rc = 0;
+                for (int stage = 0; stage < 5 && !rc; stage++) rc = sharded_stage(s, stage, d_a, d_b, d_key, d_out, batch, st);
+                const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (!rc && ce == cudaSuccess && graph && cudaGraphInstantiate(&ent->exec, graph, 0) == cudaSuccess) {
+                    cudaGraphDestroy(graph);
+                    FHE_CUDA(cudaGraphLaunch(ent->exec, st)); count_launch();
+                    return 0;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                ent->exec = nullptr; ent->seen = 1000;              // capture not possible here: stay with plain launches for this key
+                cudaGetLastError();
+                if (rc) return rc;
+            } else cudaGetLastError();
+        }
+    }
+    for (int stage = 0; stage < 5; stage++) FHE_TRY(sharded_stage(s, stage, d_a, d_b, d_key, d_out, batch, st));
     return 0;
 }
 

@@ -41,10 +41,18 @@ def main():
     sa, sb = sh.shard_ct(ca), sh.shard_ct(cb)
     ok = True
     out = None
-    for _ in range(a.reps):                     # back to back, no barrier: exercises the buffer-reuse ordering
+    for _ in range(a.reps):                     # back to back, no barrier: exercises the buffer-reuse ordering (default stream: kernel by kernel)
         out = sh.multiply(sa, sb, ks, out=out)
     sh.check()
     ok = ok and bool(torch.equal(out, sh.shard_ct(want)))
+    torch.cuda.synchronize()
+    with torch.cuda.stream(torch.cuda.Stream()):        # a real stream: eager, captured into a CUDA graph, replayed twice
+        out2 = torch.zeros_like(out)
+        for _ in range(4):
+            out2.zero_()
+            sh.multiply(sa, sb, ks, out=out2)
+        sh.check()
+        ok = ok and bool(torch.equal(out2, sh.shard_ct(want)))
     sq = sh.multiply(sa, sa, ks)                # squaring path
     sh.check()
     ok = ok and bool(torch.equal(sq, sh.shard_ct(g.multiply(ca, ca, rlk))))
