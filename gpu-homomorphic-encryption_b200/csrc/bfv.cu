@@ -560,14 +560,17 @@ extern "C" int fhe_b200_bfv_decrypt(fhe_b200_bfv* c, const uint64_t* d_ct, const
     return fork_join_halves(c, batch, (cudaStream_t)stream, [&](uint32_t first, uint32_t cnt, cudaStream_t st) -> int {
         uint64_t* x = c->d_ws + (size_t)first * ln;
         const uint64_t* ct = d_ct + (size_t)first * 2 * ln;
-        // x = c1 (strided gather), then x = INTT(NTT(x) * s) + c0
-        cudaError_t e = cudaMemcpy2DAsync(x, ln * 8, ct + ln, 2 * ln * 8, ln * 8, cnt, cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) { set_error("bfv_decrypt: gather failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
-        FHE_TRY(launch_ntt(c->plan, x, x, cnt, 0, L, false, st));
+        // x = NTT(c1) read straight out of the interleaved ciphertexts (no gather copy where the two-pass transform applies),
+        // x = INTT(x * s); c0 is added inside the decoding conversion's prologue
+        if (c->plan->bal) FHE_TRY(launch_ntt_strided_in(c->plan, x, ct + ln, 2 * ln, cnt, 0, L, false, st));
+        else {
+            cudaError_t e = cudaMemcpy2DAsync(x, ln * 8, ct + ln, 2 * ln * 8, ln * 8, cnt, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { set_error("bfv_decrypt: gather failed: %s", cudaGetErrorString(e)); return FHE_B200_ECUDA; }
+            FHE_TRY(launch_ntt(c->plan, x, x, cnt, 0, L, false, st));
+        }
         dec_mul_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(x, d_sk, prm, c->logn, L, cnt * ln); count_launch();
         FHE_TRY(launch_ntt(c->plan, x, x, cnt, 0, L, true, st));
-        dec_add_kernel<<<grid_for(c, cnt * ln), 256, 0, st>>>(x, ct, prm, c->logn, L, cnt * ln); count_launch();
-        LcView v; v.in = x; v.out = d_pt + (size_t)first * n;
+        LcView v; v.in = x; v.in_add = ct; v.in_add_stride = 2 * ln; v.out = d_pt + (size_t)first * n;
         FHE_TRY(lincomb_launch(c->dec, v, n, cnt, st));
         FHE_CUDA(cudaGetLastError());
         return 0;

@@ -104,6 +104,8 @@ struct BalScatter {
 int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
                    uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st,
                    const BalScatter* scatter = nullptr);
+int launch_ntt_strided_in(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, size_t in_poly_stride, uint32_t batch,
+                          uint32_t limb_begin, uint32_t limb_count, bool inverse, cudaStream_t st);
 // inverse transform of [batch][limb_count][N] whose tile pass runs in place on d_buf and whose column pass scatters the result
 int launch_ntt_inverse_scatter(fhe_b200_plan* plan, uint64_t* d_buf, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,
                                const BalScatter& scatter, cudaStream_t st);

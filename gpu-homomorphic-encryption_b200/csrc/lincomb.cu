@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcKernelArgs a) {
         u64 x = 0;
         if (i < a.S) {
             x = inb[(size_t)a.v.src_idx[i] * nn];
+            if (a.v.in_add) x = add_mod(x, a.v.in_add[(size_t)b * a.v.in_add_stride + j + (size_t)a.v.src_idx[i] * nn], sSrc[i]);
             if (a.v.copy_out) {
                 if (a.v.copy_tab) reinterpret_cast<u64*>(a.v.copy_tab[2 * i])[(a.v.copy_poly0 + b) * a.v.copy_tab[2 * i + 1] + j] = x;
                 else a.v.copy_out[(size_t)b * a.v.copy_stride + (size_t)a.v.copy_idx[i] * nn + j] = x;
@@ -208,14 +209,15 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& view, uint32_t n, uint32_
     a.use_pre = lc->use_pre; a.use_extra = lc->use_extra; a.c_is_one = lc->use_pre ? 0 : 1;
     a.k_per_block = lc->T;
     a.total = (size_t)batch * n;
-    if (lc->use_tc && n % 128 == 0) {
+    if (!a.v.in_add_stride) a.v.in_add_stride = a.v.in_stride;
+    if (lc->use_tc && n % 128 == 0 && !a.v.in_add) {
         const bool prof = profile_on();
         if (prof) profile_begin(4, (uint64_t)batch * lc->S * lc->T, st);
         const int rc = lincomb_tc_launch(lc, a.v, n, batch, st);
         if (prof) profile_end(st);
         return rc;
     }
-    if (lc->use_mma) {
+    if (lc->use_mma && !a.v.in_add) {
         const bool prof = profile_on();
         if (prof) profile_begin(4, (uint64_t)batch * lc->S * lc->T, st);
         const int rc = lincomb_mma_launch(lc, a.v, n, batch, st);

@@ -56,6 +56,9 @@ struct LcView {
     // ABSOLUTE address out_tab[2k] + ((out_poly0 + b) * out_tab[2k+1] + j) * 8 -- every target limb may live in a different
     // buffer, e.g. the peer GPU that owns that limb (stores over NVLink).  copy_tab does the same for the pass-through limbs
     // ([S] pairs; copy_out must still be non-null to enable the pass-through).  Device arrays of {address, words per polynomial}.
+    // a second input added to the first modulo the source moduli before anything else (same limb map as `in`): decryption's c0 + c1 s.
+    // IMAD kernel only (lincomb_launch routes such calls there).
+    const uint64_t* in_add = nullptr; size_t in_add_stride = 0;
     const uint64_t* out_tab = nullptr; size_t out_poly0 = 0;
     const uint64_t* copy_tab = nullptr; size_t copy_poly0 = 0;
 };

@@ -23,6 +23,7 @@ struct BalArgs {
     uint32_t l0, nl, b0, nb;     // chunk: buffer limbs [l0, l0+nl), polynomials [b0, b0+nb)
     uint32_t m_items, ctas_per_limb;   // pass A: items per CTA, CTAs per limb
     uint32_t groups;             // pass B: warps per (limb, tile pair); warp g handles polynomials b0+g, b0+g+groups, ...
+    size_t in_poly_stride;       // elements between polynomials of `in` (the first pass of a transform reads `in`); out: limb_count * n
 };
 
 constexpr size_t kBalASmem = 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256, 4) bal_a_kernel(const BalArgs a) {
         const uint32_t poly = a.b0 + it / A::CB, cb = it % A::CB;
         const size_t off = ((size_t)poly * a.limb_count + limb) * a.n + (size_t)cb * A::C;
         if (!INV) {
-            A::fwd_round1(tid, a.in + off, sbuf, stw, P);
+            A::fwd_round1(tid, a.in + ((size_t)poly * a.in_poly_stride + (size_t)limb * a.n + (size_t)cb * A::C), sbuf, stw, P);
             __syncthreads();
             A::fwd_round2(tid, a.out + off, sbuf, stw, P);
         } else {
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
             __syncwarp();
             B::fwd_phase3(lane, a.out + off, s);
         } else {
-            B::inv_phase1(lane, a.in + off, s);
+            B::inv_phase1(lane, a.in + (poly * a.in_poly_stride + limb_off), s);
             __syncwarp();
             B::inv_phase2(lane, s, sb, P);
             __syncwarp();
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
 int launch_ntt_bal_passes(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
                           uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st, const BalScatter* scatter,
                           bool only_a);
+extern thread_local size_t g_in_poly_stride_fwd;
 template <int KA, int HB, bool NEAR>
 static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStream_t st, const BalScatter* scatter, bool only_a) {
     using A = BalA<KA, HB, NEAR>;
@@ -235,6 +237,28 @@ static int dispatch_bal(fhe_b200_plan* plan, const BalArgs& a, bool inverse, cud
 }
 
 // chunk = buffer limbs [l0, l0+nl) x polynomials [b0, b0+nb) of a [batch][limb_count][n] buffer
+// polynomial stride of the INPUT of the transform being launched (elements; 0 = dense).  Set by launch_ntt_strided_in around its call.
+thread_local size_t g_in_poly_stride_fwd = 0;
+#define g_in_poly_stride g_in_poly_stride_fwd
+
+// out-of-place transform whose input polynomials are `in_poly_stride` elements apart (e.g. one component of interleaved
+// ciphertexts): saves the gather copy.  Balanced two-pass sizes only; out is dense [batch][limb_count][N].
+int launch_ntt_strided_in(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, size_t in_poly_stride, uint32_t batch,
+                          uint32_t limb_begin, uint32_t limb_count, bool inverse, cudaStream_t st) {
+    FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
+    FHE_REQUIRE(plan->bal && d_out != d_in, "strided transform: needs the balanced two-pass NTT and distinct buffers");
+    if (batch == 0 || limb_count == 0) return 0;
+    DeviceGuard dev_guard(plan->device);
+    g_in_poly_stride = in_poly_stride;
+    int rc = 0;
+    for (uint32_t l0 = 0; l0 < limb_count && !rc; l0 += 256) {
+        const uint32_t nl = l0 + 256 <= limb_count ? 256 : limb_count - l0;
+        rc = launch_ntt_bal_passes(plan, d_out, d_in, limb_begin, limb_count, l0, nl, 0, batch, inverse, st, nullptr, false);
+    }
+    g_in_poly_stride = 0;
+    return rc;
+}
+
 int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, uint32_t limb_begin, uint32_t limb_count,
                    uint32_t l0, uint32_t nl, uint32_t b0, uint32_t nb, bool inverse, cudaStream_t st, const BalScatter* scatter) {
     return launch_ntt_bal_passes(plan, d_out, d_in, limb_begin, limb_count, l0, nl, b0, nb, inverse, st, scatter, false);
@@ -251,6 +275,7 @@ int launch_ntt_bal_passes(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* 
     a.n = plan->n; a.limb_count = limb_count; a.limb_begin = limb_begin;
     a.l0 = l0; a.nl = nl; a.b0 = b0; a.nb = nb;
     a.m_items = 1; a.ctas_per_limb = 1; a.groups = 1;
+    a.in_poly_stride = g_in_poly_stride ? g_in_poly_stride : (size_t)limb_count * plan->n;
     return plan->near60 ? dispatch_bal<16, true>(plan, a, inverse, st, scatter, only_a)
          : plan->hb == 16 ? dispatch_bal<16, false>(plan, a, inverse, st, scatter, only_a)
                           : dispatch_bal<8, false>(plan, a, inverse, st, scatter, only_a);
