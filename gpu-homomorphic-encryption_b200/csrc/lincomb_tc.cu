@@ -15,6 +15,11 @@
 //                        partial sums of a target for its coefficient with one tcgen05.ld (32x32b.x16), assembles the 128-bit
 //                        value, reduces and stores.  The tensor core works on one group's chunk while the other three groups of
 //                        the SM run their scalar work: nothing blocks behind an MMA, and loads / stores are 256 bytes per warp.
+// The fixed-point sum that yields the rounded integer I rides on the same GEMM: two pseudo-targets in front of the real ones carry
+// theta_hi and theta_lo as their "matrix entries", so the tensor core returns H = sum z_i th_hi_i and G = sum z_i th_lo_i exactly; the
+// specification wants sum floor(z_i th_lo_i / 2^64), which is (G - F) / 2^64 with F = sum (z_i th_lo_i mod 2^64) -- and since G = F modulo
+// 2^64, all a thread has to compute is the number of carries of that sum of low words: one mul.lo and one add-with-carry per source
+// instead of a 128-bit product, a mul.hi and two 192-bit additions.  Same I, bit for bit, as lincomb_kernel / lincomb_mma_kernel.
 // Persistent CTAs, one per SM: 4 groups x 128 threads, the whole TMEM (4 x 128 columns).
 #include "lincomb.cuh"
 #include "host_math.hpp"
@@ -82,6 +87,20 @@ __device__ __forceinline__ void tc_assemble128(const u32 (&p)[16], u64& hi, u64&
     lo = ((u64)v1 << 32) | v0; hi = ((u64)v3 << 32) | v2;
 }
 
+// the same sum as 160 bits (five 32-bit words): the pseudo-targets' entries are full 64-bit words, so the sum can pass 2^128
+__device__ __forceinline__ void tc_assemble160(const u32 (&p)[16], u64& w2, u64& w1, u64& w0) {
+    u32 v0 = p[0], v1 = p[4], v2 = p[8], v3 = p[12], v4 = 0;
+#pragma unroll
+    for (int r = 1; r < 4; r++) {
+        const u32 d0 = p[r], d1 = p[r + 4], d2 = p[r + 8], d3 = (r + 12 < 15) ? p[r + 12] : 0u;
+        const u32 x0 = d0 << (8 * r), x1 = __funnelshift_l(d0, d1, 8 * r), x2 = __funnelshift_l(d1, d2, 8 * r),
+                  x3 = __funnelshift_l(d2, d3, 8 * r), x4 = d3 >> (32 - 8 * r);
+        asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, %4, %9;"
+            : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3), "+r"(v4) : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4));
+    }
+    w0 = ((u64)v1 << 32) | v0; w1 = ((u64)v3 << 32) | v2; w2 = v4;
+}
+
 // shared memory: B operand | A tiles (one per group) | per-source and per-target constants | barriers, TMEM base
 // MONT: every target modulus is in (2^60 - 2^32, 2^60); matrix, c and lam carry a factor 2^64 and the sum V is reduced by
 //   u = V_lo * (-m^-1) mod 2^64,  t = (V + u m) / 2^64 = V_hi + hi64(u m) + [V_lo != 0]  (= V 2^-64 mod m, below 8 m),
@@ -94,8 +113,9 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
     extern __shared__ __align__(128) unsigned char tc_smem[];
     const uint32_t tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127, warp = tid >> 5, lane = tid & 31;
     const uint32_t K = a.KS * 32;                                   // bytes of one A row
-    const uint32_t NT = (a.T + kTcChunkTargets - 1) / kTcChunkTargets;    // chunks
-    const size_t b_bytes = (size_t)K * a.T * 16;
+    const uint32_t TS = a.T + 2;                                    // column slots: theta_hi, theta_lo, then the targets
+    const uint32_t NT = (TS + kTcChunkTargets - 1) / kTcChunkTargets;     // chunks
+    const size_t b_bytes = (size_t)K * TS * 16;
     unsigned char* sB = tc_smem;
     unsigned char* sA = tc_smem + ((b_bytes + 127) & ~(size_t)127) + (size_t)grp * 128 * K;
     u64* sC = reinterpret_cast<u64*>(tc_smem + ((b_bytes + 127) & ~(size_t)127) + (size_t)kTcGroups * 128 * K);
@@ -155,7 +175,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
         const u64* inb = a.v.in + (size_t)b * a.v.in_stride + j;
 
         // ---- prologue: this coefficient's sources -> bytes of z (row gtid of A), fixed-point sum of z * theta
-        u64 f0 = 0, f1 = 0, f2 = 0;
+        u64 facc = 0; u32 fcnt = 0;                                 // sum of the low words of z * theta_lo, and its carries
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < SP; i0 += 8) {
             u64 x[8];
@@ -167,10 +187,8 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                 if (i < SP) {
                     if (i < a.S && a.v.copy_out) reinterpret_cast<u64*>(sCpy[i])[(size_t)b * sCpy[SP + i] + j] = x[u];
                     if (a.use_pre) x[u] = shoup_mul(x[u], sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
-                    u64 ph, pl;
-                    mul128(x[u], sSrc[3 * SP + i], ph, pl);
-                    add192(f2, f1, f0, ph, pl);
-                    add192(f2, f1, f0, 0, mulhi64(x[u], sSrc[4 * SP + i]));
+                    const u64 lo = x[u] * sSrc[4 * SP + i];
+                    asm("add.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+l"(facc), "+r"(fcnt) : "l"(lo));
                 }
             }
 #pragma unroll
@@ -178,8 +196,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                 if (i0 + u < SP)                                    // sources i, i+1 = K bytes [8i, 8i+16) = K chunk i/2
                     *reinterpret_cast<ulonglong2*>(sA + (size_t)((i0 + u) >> 1) * 2048 + gtid * 16) = make_ulonglong2(x[u], x[u + 1]);
         }
-        add192(f2, f1, f0, 0, 1ull << 63);
-        const u64 I_hi = f2, I_lo = f1;
+        u64 I_hi = 0, I_lo = 0;                                     // known after the first chunk (the two pseudo-targets)
         fence_proxy_async_smem();                                   // A row visible to the tensor core
         tc_fence_before();
         group_barrier(1 + grp);
@@ -187,13 +204,13 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
         // ---- chunks of eight targets: MMA into the group's TMEM columns, then every thread finishes its coefficient
 #pragma unroll 1
         for (uint32_t ch = 0; ch < NT; ch++) {
-            const uint32_t k0 = ch * kTcChunkTargets;
-            const uint32_t cnt = min((uint32_t)kTcChunkTargets, a.T - k0);
+            const uint32_t s0 = ch * kTcChunkTargets;               // first column slot of the chunk; slot s >= 2 is target s - 2
+            const uint32_t cnt = min((uint32_t)kTcChunkTargets, TS - s0);
             const uint32_t ncol = cnt * 16;
             if (gtid == 0) {
                 tc_fence_after();
                 const uint32_t idesc = tc_idesc(ncol);
-                const uint32_t b_chunk = sB_addr + k0 * 16 * K;     // chunks are stored one after the other: K * 16 bytes per target
+                const uint32_t b_chunk = sB_addr + s0 * 16 * K;     // chunks are stored one after the other: K * 16 bytes per slot
                 for (uint32_t ks = 0; ks < a.KS; ks++) {
                     const uint64_t da = tc_smem_desc(sA_addr + ks * 2 * 2048, 2048, 128);
                     const uint64_t db = tc_smem_desc(b_chunk + ks * 2 * ncol * 16, ncol * 16, 128);
@@ -253,10 +270,29 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
             // the epilogue operands (extra limb, ModDown minuend / addend) of a pair are loaded one pair ahead: their latency hides
             // behind the previous pair's reductions
             u64 ex0 = 0, su0 = 0, ad0 = 0, ex1 = 0, su1 = 0, ad1 = 0;
-            if (cnt >= 2) { operands(k0, ex0, su0, ad0); operands(k0 + 1, ex1, su1, ad1); }
+            uint32_t tl = 0;
+            if (ch == 0) {
+                // slots 0, 1: H = sum z theta_hi, G = sum z theta_lo (exact, 160 bits each).  sum floor(z theta_lo / 2^64) = (G >> 64) - carries of the
+                // threads' sum of low words (G = that sum modulo 2^64);  f = H + that + 2^63,  I = f >> 64.
+                u32 p0[16], p1[16];
+                tc_ld16(tmem_rd, p0);
+                tc_ld16(tmem_rd + 16, p1);
+                if (cnt >= 4) { operands(0, ex0, su0, ad0); operands(1, ex1, su1, ad1); }
+                tc_wait_ld();
+                u64 h2, h1, h0, g2, g1, g0;
+                tc_assemble160(p0, h2, h1, h0);
+                tc_assemble160(p1, g2, g1, g0);
+                u64 e1 = g2, e0 = g1;
+                asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u64 %1, %1, 0;" : "+l"(e0), "+l"(e1) : "l"((u64)fcnt));
+                add192(h2, h1, h0, e1, e0);
+                add192(h2, h1, h0, 0, 1ull << 63);
+                I_hi = h2; I_lo = h1;
+                (void)g0;
+                tl = 2;
+            } else if (cnt >= 2) { operands(s0 - 2, ex0, su0, ad0); operands(s0 - 1, ex1, su1, ad1); }
 #pragma unroll 1
-            for (uint32_t tl = 0; tl + 1 < cnt; tl += 2) {
-                const uint32_t k = k0 + tl;
+            for (; tl + 1 < cnt; tl += 2) {
+                const uint32_t k = s0 + tl - 2;
                 u32 p0[16], p1[16];
                 tc_ld16(tmem_rd + tl * 16, p0);
                 tc_ld16(tmem_rd + tl * 16 + 16, p1);
@@ -266,10 +302,10 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                 finish(k, p0, cex0, csu0, cad0);
                 finish(k + 1, p1, cex1, csu1, cad1);
             }
-            if (cnt & 1) {
-                const uint32_t k = k0 + cnt - 1;
+            if (tl < cnt) {                                          // an odd slot left over
+                const uint32_t k = s0 + tl - 2;
                 u32 p0[16];
-                tc_ld16(tmem_rd + (cnt - 1) * 16, p0);
+                tc_ld16(tmem_rd + tl * 16, p0);
                 operands(k, ex0, su0, ad0);
                 tc_wait_ld();
                 finish(k, p0, ex0, su0, ad0);
@@ -297,16 +333,21 @@ void lincomb_tc_build_b(const LincombConsts& h, uint32_t KS, bool montgomery, st
                 const uint64_t m = h.dst_mod[k];
                 M[(size_t)i * h.T + k] = host::mulmod(h.M[(size_t)i * h.T + k] % m, (uint64_t)((((unsigned __int128)1) << 64) % m), m);
             }
-    out.assign((size_t)K * h.T * 16, 0);
+    // column slots: 0 = theta_hi, 1 = theta_lo (raw 64-bit words: the overflow sum), 2 + k = target k
+    const uint32_t TS = h.T + 2;
+    auto entry = [&](uint32_t i, uint32_t slot) -> uint64_t {
+        return slot == 0 ? h.th_hi[i] : slot == 1 ? h.th_lo[i] : M[(size_t)i * h.T + (slot - 2)];
+    };
+    out.assign((size_t)K * TS * 16, 0);
     size_t base = 0;
-    for (uint32_t k0 = 0; k0 < h.T; k0 += kTcChunkTargets) {
-        const uint32_t cnt = std::min<uint32_t>(kTcChunkTargets, h.T - k0), ncol = cnt * 16;
+    for (uint32_t s0 = 0; s0 < TS; s0 += kTcChunkTargets) {
+        const uint32_t cnt = std::min<uint32_t>(kTcChunkTargets, TS - s0), ncol = cnt * 16;
         for (uint32_t tl = 0; tl < cnt; tl++)
             for (uint32_t c = 0; c < 15; c++)
                 for (uint32_t kb = 0; kb < K; kb++) {
                     const uint32_t i = kb / 8, aa = kb % 8;
                     if (i >= h.S || c < aa || c - aa > 7) continue;
-                    const uint8_t v = (uint8_t)((M[(size_t)i * h.T + k0 + tl] >> (8 * (c - aa))) & 0xff);
+                    const uint8_t v = (uint8_t)((entry(i, s0 + tl) >> (8 * (c - aa))) & 0xff);
                     out[base + (size_t)(kb / 16) * (ncol * 16) + (size_t)(tl * 16 + c) * 16 + kb % 16] = v;
                 }
         base += (size_t)K * ncol;
@@ -315,7 +356,7 @@ void lincomb_tc_build_b(const LincombConsts& h, uint32_t KS, bool montgomery, st
 
 size_t lincomb_tc_smem_bytes(uint32_t S, uint32_t T) {
     const uint32_t KS = (S + 3) / 4, K = KS * 32, SP = KS * 4;
-    const size_t b_bytes = (size_t)K * T * 16;
+    const size_t b_bytes = (size_t)K * (T + 2) * 16;
     return ((b_bytes + 127) & ~(size_t)127) + (size_t)kTcGroups * 128 * K + (size_t)(8 * SP + 11 * T) * sizeof(u64) + kTcGroups * 8 + 16;
 }
 
