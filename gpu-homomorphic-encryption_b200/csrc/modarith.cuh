@@ -179,6 +179,10 @@ FHE_HD u64 shoup_mul_lazy3(u64 x, u64 w, u64 ws, u64 nq) {
 #endif
 }
 
+// (For q = 2^60 - delta the partial product h0 * n1 of h * nq is a shift, h0 * 0xF0000000 = -(h0 << 28) mod 2^32, which would leave
+// 5 WIDE + 3 lo = 26 cycles of the FMA pipe.  Built and measured in round 2: bit-exact and 4 % SLOWER -- the SHF, LOP3 and IADD3 that
+// replace the IMAD cost more issue time than the two pipe cycles saved; see "issue-cost model" in DESIGN.md.)
+
 // (hi:lo) mod q for any 128-bit input; mu = floor(2^128/q), q < 2^63.
 // Quotient estimate from the three high partial products; it is low by at most 3, fixed by two conditional
 // subtractions (2q then q).  Needs 4q < 2^64.
@@ -200,20 +204,39 @@ FHE_HD u64 barrett128(u64 hi, u64 lo, u64 q, u64 mu_hi, u64 mu_lo) {
 // nq = 2^64 - q, whose low word is delta.
 FHE_HD u64 near60_reduce(u64 x, u64 nq) {
 #if defined(__CUDA_ARCH__)
+    // Written word by word: the product has no addend and the high word gets a third (opaque zero) addend.  The natural form --
+    // IMAD.WIDE with the masked x as its 64-bit addend -- is split by ptxas into WIDE + IADD3 + IMAD.X whenever the two words of
+    // the addend do not already sit in an aligned register pair (6 instead of 4 cycles of the binding pipe); a three-input
+    // IADD3.X cannot become an IMAD.X, and the extra IADD3 is on the ALU pipe, which has slack.
     u64 r;
     asm("{\n\t"
-        ".reg .u32 x0, x1, k, n0, n1;\n\t"
-        ".reg .u64 m;\n\t"
+        ".reg .u32 x0, x1, k, n0, n1, p0, p1;\n\t"
+        ".reg .u64 p;\n\t"
         "mov.b64 {x0, x1}, %1;\n\t"
         "mov.b64 {n0, n1}, %2;\n\t"
         "shr.u32 k, x1, 28;\n\t"
         "and.b32 x1, x1, 0x0fffffff;\n\t"
-        "mov.b64 m, {x0, x1};\n\t"
-        "mad.wide.u32 %0, k, n0, m;\n\t"
-        "}" : "=l"(r) : "l"(x), "l"(nq));
+        "mul.wide.u32 p, k, n0;\n\t"
+        "mov.b64 {p0, p1}, p;\n\t"
+        "add.cc.u32 x0, x0, p0;\n\t"
+        "addc.u32 x1, x1, p1;\n\t"
+        "add.u32 x1, x1, %3;\n\t"
+        "mov.b64 %0, {x0, x1};\n\t"
+        "}" : "=l"(r) : "l"(x), "l"(nq), "r"((u32)kOpaqueZero));
     return r;
 #else
     return (x & 0x0fffffffffffffffULL) + (x >> 60) * (u64)(u32)nq;
+#endif
+}
+
+// x - q if x >= q else x, for x < 2^63 + q: the difference's sign decides (one ISETP instead of a 64-bit compare), and the
+// subtraction has a third (opaque zero) addend so that it stays on the ALU pipe
+FHE_HD u64 csub_sign(u64 x, u64 q) {
+#if defined(__CUDA_ARCH__)
+    const u64 t = x - q + kOpaqueZero;
+    return (long long)t < 0 ? x : t;
+#else
+    return csub(x, q);
 #endif
 }
 

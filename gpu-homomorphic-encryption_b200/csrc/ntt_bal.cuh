@@ -80,8 +80,7 @@ struct BalA {
 #pragma unroll
         for (int rl = 0; rl < 16; rl++) x[rl] = s[(e1 << 8) | (rl << 4) | ct];
         fwd_stages<4, 4, HB, NEAR, fwd_bound_after(1, R1, HB, NEAR)>(x, TwA2{stw, (1u << R1) + (e1 & RM)}, P);
-#pragma unroll
-        for (int rl = 0; rl < 16; rl++) g[at2(tid, rl)] = x[rl];
+        stg16o<Stride16::Of<256>>(g + at2(tid, 0), x);
     }
 
     // inverse: round 2' (low row bits) first, entry bound BIN = what pass B' leaves; then round 1' ends the transform (N^-1 folded)
@@ -101,7 +100,8 @@ struct BalA {
         for (int e = 0; e < 16; e++) x[e] = s[(e << 8) | tid];
         inv_stages<4, R1, HB, NEAR, true, inv_bound_after(BIN, 4, HB, NEAR)>(x, TwA1{stw}, P);
 #pragma unroll
-        for (int e = 0; e < 16; e++) g[at1(tid, e)] = normalize<HB, NEAR, kTQ>(x[e], P.q);
+        for (int e = 0; e < 16; e++) x[e] = normalize_last<HB, NEAR, R1>(x[e], e, P.q);
+        stg16o<Off1>(g + at1(tid, 0), x);
     }
     // as inv_round1, but every output goes through put(row, column inside the item, value): row of the limb's 2^KA x 256 matrix.
     // Used by the scatter form of the last inverse pass (limb-sharded execution): the rows of a coefficient block belong to the
@@ -114,7 +114,7 @@ struct BalA {
         inv_stages<4, R1, HB, NEAR, true, inv_bound_after(BIN, 4, HB, NEAR)>(x, TwA1{stw}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++)
-            put((((u32)e & RM) << 4) | (tid >> 4), (((u32)e >> R1) << 4) + (tid & 15), normalize<HB, NEAR, kTQ>(x[e], P.q));
+            put((((u32)e & RM) << 4) | (tid >> 4), (((u32)e >> R1) << 4) + (tid & 15), normalize_last<HB, NEAR, R1>(x[e], e, P.q));
     }
 };
 
@@ -168,7 +168,7 @@ struct BalB {
         fwd_stages<4, 4, HB, NEAR, B1>(x, TwB2{sb, lane}, P);
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            st2(s + (row | ((k ^ (lane & 7)) << 1)), normalize<HB, NEAR, BE>(x[2 * k], q), normalize<HB, NEAR, BE>(x[2 * k + 1], q));
+            st2s(s + (row | ((k ^ (lane & 7)) << 1)), normalize<HB, NEAR, BE>(x[2 * k], q), normalize<HB, NEAR, BE>(x[2 * k + 1], q));
     }
     // forward round 2 with the sixteen canonical results left in registers (the lane's own row of the exchange buffer in,
     // nothing written): the fused tile kernels (ntt_fused.cu) go on to the pointwise work from here
@@ -223,7 +223,7 @@ struct BalB {
         for (int k = 0; k < 8; k++) ld2(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
         inv_stages<4, 4, HB, NEAR, false, 1>(x, TwB2{sb, lane}, P);
 #pragma unroll
-        for (int k = 0; k < 8; k++) st2(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
+        for (int k = 0; k < 8; k++) st2s(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
     }
     static FHE_HD void inv_phase3(u32 lane, u64* g, const u64* s, const Twiddle* sb, const LimbParams& P) {
         const u32 t = lane >> 4, j = lane & 15;

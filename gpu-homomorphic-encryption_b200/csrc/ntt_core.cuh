@@ -71,6 +71,15 @@ FHE_HD void st2(u64* p, u64 a, u64 b) {
     p[0] = a; p[1] = b;
 #endif
 }
+// the same two elements as two 8-byte stores: a 16-byte store wants its four words in an aligned register quad, and for values that
+// come out of three-input adds or selects ptxas gathers them there with moves -- which it issues as IMAD.MOV on the binding pipe
+FHE_HD void st2s(u64* p, u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.volatile.shared.u64 [%0], %1;\n\tst.volatile.shared.u64 [%0+8], %2;" :: "r"((u32)__cvta_generic_to_shared(p)), "l"(a), "l"(b) : "memory");
+#else
+    st2(p, a, b);
+#endif
+}
 
 // Global loads of polynomial data go to L2 only (ld.global.cg): the data is streamed (no L1 reuse), and in the fused
 // row+tile kernel another SM may have rewritten a line that this SM's L1 still holds from the row pass.
@@ -116,6 +125,29 @@ FHE_HD void ldg16o(const u64* base, u64 (&x)[16]) {
 }
 template <int STRIDE>
 FHE_HD void ldg16(const u64* base, u64 (&x)[16]) { ldg16o<Stride16::Of<STRIDE>>(base, x); }
+
+// Sixteen stores base[OFF::at(e)] = x[e] with the element offsets as immediates of ONE base register pair: written as g[f(tid, e)]
+// the compiler rebuilds a 64-bit address per store (LOP3, IADD3, IADD3.X, LEA, LEA.HI.X: two issue cycles per butterfly of the column pass)
+template <class OFF>
+FHE_HD void stg16o(u64* base, const u64 (&x)[16]) {
+#if defined(__CUDA_ARCH__)
+    asm volatile(
+        "st.global.u64 [%16+%17], %0;\n\t"  "st.global.u64 [%16+%18], %1;\n\t"  "st.global.u64 [%16+%19], %2;\n\t"
+        "st.global.u64 [%16+%20], %3;\n\t"  "st.global.u64 [%16+%21], %4;\n\t"  "st.global.u64 [%16+%22], %5;\n\t"
+        "st.global.u64 [%16+%23], %6;\n\t"  "st.global.u64 [%16+%24], %7;\n\t"  "st.global.u64 [%16+%25], %8;\n\t"
+        "st.global.u64 [%16+%26], %9;\n\t"  "st.global.u64 [%16+%27], %10;\n\t" "st.global.u64 [%16+%28], %11;\n\t"
+        "st.global.u64 [%16+%29], %12;\n\t" "st.global.u64 [%16+%30], %13;\n\t" "st.global.u64 [%16+%31], %14;\n\t"
+        "st.global.u64 [%16+%32], %15;"
+        :: "l"(x[0]), "l"(x[1]), "l"(x[2]), "l"(x[3]), "l"(x[4]), "l"(x[5]), "l"(x[6]), "l"(x[7]), "l"(x[8]), "l"(x[9]),
+           "l"(x[10]), "l"(x[11]), "l"(x[12]), "l"(x[13]), "l"(x[14]), "l"(x[15]),
+           "l"(base), "n"(OFF::at(0) * 8), "n"(OFF::at(1) * 8), "n"(OFF::at(2) * 8), "n"(OFF::at(3) * 8), "n"(OFF::at(4) * 8),
+           "n"(OFF::at(5) * 8), "n"(OFF::at(6) * 8), "n"(OFF::at(7) * 8), "n"(OFF::at(8) * 8), "n"(OFF::at(9) * 8), "n"(OFF::at(10) * 8),
+           "n"(OFF::at(11) * 8), "n"(OFF::at(12) * 8), "n"(OFF::at(13) * 8), "n"(OFF::at(14) * 8), "n"(OFF::at(15) * 8)
+        : "memory");
+#else
+    for (int e = 0; e < 16; e++) base[OFF::at(e)] = x[e];
+#endif
+}
 
 // bounds in units of q; the twiddle product is lazy in [0, kTQ q) (shoup_mul_lazy3).
 // NEAR: every modulus q satisfies 2^60 - 2^32 < q < 2^60, so near60_reduce brings anything below 16q under 2q.
@@ -239,12 +271,20 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
 // bring a value bounded by B*q into [0, q)
 template <int HB, bool NEAR, int B>
 FHE_HD u64 normalize(u64 x, u64 q) {
-    if (NEAR && B > 2) return csub(near60_reduce(x, 0 - q), q);
+    if (NEAR && B > 2) return csub_sign(near60_reduce(x, 0 - q), q);
     if (HB >= 16 && B > 8) x = csub(x, 8 * q);
     if (HB >= 8 && B > 4) x = csub(x, 4 * q);
     if (B > 2) x = csub(x, 2 * q);
     if (B > 1) x = csub(x, q);
     return x;
+}
+
+// Canonical form of output e of inv_stages<LE, R, ..., LAST = true>: the last stage leaves a scaled sum (scale_ninv: in (0, 2q)) where
+// bit R-1 of e is clear -- one conditional subtraction -- and a lazy product in [0, 3q) where it is set.
+template <int HB, bool NEAR, int R>
+FHE_HD u64 normalize_last(u64 x, int e, u64 q) {
+    if (!((e >> (R - 1)) & 1)) return NEAR ? csub_sign(x, q) : csub(x, q);
+    return normalize<HB, NEAR, kTQ>(x, q);
 }
 
 // =====================================================================================================
@@ -373,7 +413,7 @@ struct TileInv {
         inv_stages<4, 4, HB, NEAR, LAST, inv_bound_after(1, R3 + 4, HB, NEAR)>(x, TwP1{s12}, P);
         // LAST: fully reduce.  Otherwise leave the lazy bound for pass A' (it starts from out_bound()).
 #pragma unroll
-        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize<HB, NEAR, kTQ>(x[e], P.q) : x[e];
+        for (int e = 0; e < 16; e++) g[(e << (LB - 4)) | tid] = LAST ? normalize_last<HB, NEAR, 4>(x[e], e, P.q) : x[e];
     }
     template <bool LAST>
     static FHE_HD void phase4(u32 tid, u64* g, const u64* s, const Twiddle* s12, const LimbParams& P) {
@@ -422,8 +462,8 @@ struct RowPass {
         for (int c = 0; c < V; c++) inv_stages<K1, K1, HB, NEAR, true, B0>(x[c], TwGlobal<0>{tw, 1u}, P);
 #pragma unroll
         for (int r = 0; r < NA; r++) {
-            if (V == 2) st2(g + (size_t)r * NB + col, normalize<HB, NEAR, kTQ>(x[0][r], P.q), normalize<HB, NEAR, kTQ>(x[V - 1][r], P.q));
-            else g[(size_t)r * NB + col] = normalize<HB, NEAR, kTQ>(x[0][r], P.q);
+            if (V == 2) st2(g + (size_t)r * NB + col, normalize_last<HB, NEAR, K1>(x[0][r], r, P.q), normalize_last<HB, NEAR, K1>(x[V - 1][r], r, P.q));
+            else g[(size_t)r * NB + col] = normalize_last<HB, NEAR, K1>(x[0][r], r, P.q);
         }
     }
 };

@@ -27,5 +27,10 @@ for f,c in funcs.items():
     heavy4=c['IMAD.WIDE']+c['IMAD.HI']; heavy2=c['IMAD']+c['IMAD.MOV']+c['IMAD.X']+c['IMAD.IADD']+c['IMAD.SHL']+c['HFMA2']+c['FMUL']+c['FFMA']
     alu=sum(c[k] for k in ['IADD3','LOP3','SHF','ISETP','SEL','LEA','MOV','VIADD','PRMT','PLOP3','IABS','CS2R','VIMNMX'])
     tot=sum(c.values())
-    print(f"{f[:70]}\n  total={tot} ({tot/nb:.1f}/bfly) heavy_cycles={4*heavy4+2*heavy2} ({(4*heavy4+2*heavy2)/nb:.1f}/bfly) alu={alu} ({alu/nb:.1f}/bfly)")
+    one=c['IADD3']+c['VIADD']; two=alu-one
+    mem=sum(v for k,v in c.items() if k in ('LDS','STS','LDG','STG','LDL','STL','LDC','LDCU','ATOMS','RED','SYNCS','UBLKCP'))
+    rest=tot-(heavy4+heavy2+alu+mem)
+    cost=4*heavy4+2*heavy2+one+2*two+mem+rest
+    print(f"{f[:70]}\n  ISSUE-COST model (WIDE/HI 4, IMAD* 2, IADD3 1, other ALU 2, rest 1): {cost} ({cost/nb:.1f}/bfly)  [fma {4*heavy4+2*heavy2}, iadd3 {one}, alu2 {2*two}, mem {mem}, rest {rest}]")
+    print(f"  total={tot} ({tot/nb:.1f}/bfly) heavy_cycles={4*heavy4+2*heavy2} ({(4*heavy4+2*heavy2)/nb:.1f}/bfly) alu={alu} ({alu/nb:.1f}/bfly)")
     print('  '+' '.join(f"{k}:{v}" for k,v in c.most_common(24)))
