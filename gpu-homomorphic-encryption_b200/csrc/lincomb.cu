@@ -325,27 +325,27 @@ int lincomb_create(const LincombConsts& h, int device, fhe_b200_lincomb** out) {
         if (e == cudaSuccess) e = cudaMemcpy(lc->d_bfrag, bf.data(), bf.size() * sizeof(uint2), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { set_error("lincomb: device allocation failed: %s", cudaGetErrorString(e)); cudaFree(lc->d_blob); delete lc; return FHE_B200_ECUDA; }
     }
-    // tcgen05 path: same Toeplitz GEMM, operands in shared memory, accumulators in TMEM
-    lc->use_tc = lc->use_mma && lincomb_tc_smem_bytes(S, T) <= 220 * 1024;
-    if (const char* ev = getenv("FHE_B200_LINCOMB_TC")) lc->use_tc = atoi(ev) != 0 && lincomb_tc_smem_bytes(S, T) <= 220 * 1024;
+    // tcgen05 path: the byte GEMM with operands in shared memory and accumulators in TMEM (lincomb_tc.cu)
+    bool fold = !(getenv("FHE_B200_LINCOMB_TC_FOLD") && atoi(getenv("FHE_B200_LINCOMB_TC_FOLD")) == 0);
+    for (uint32_t k = 0; k < T; k++) fold = fold && (h.dst_mod[k] >> 60) == 0 && h.dst_mod[k] > (1ull << 60) - (1ull << 32);
+    if (fold && lincomb_tc_smem_bytes(S, T, true) > 220 * 1024) fold = false;
+    lc->use_tc = lc->use_mma && lincomb_tc_smem_bytes(S, T, fold) <= 220 * 1024;
+    if (const char* ev = getenv("FHE_B200_LINCOMB_TC")) lc->use_tc = atoi(ev) != 0 && lincomb_tc_smem_bytes(S, T, fold) <= 220 * 1024;
     if (lc->use_tc) {
-        lc->tc_mont = !(getenv("FHE_B200_LINCOMB_TC_MONT") && atoi(getenv("FHE_B200_LINCOMB_TC_MONT")) == 0);
-        for (uint32_t k = 0; k < T; k++) lc->tc_mont = lc->tc_mont && (h.dst_mod[k] >> 60) == 0 && h.dst_mod[k] > (1ull << 60) - (1ull << 32);
+        lc->tc_fold = fold;
         std::vector<uint8_t> bm;
-        lincomb_tc_build_b(h, (S + 3) / 4, lc->tc_mont, bm);
+        lincomb_tc_build_b(h, (S + 3) / 4, lc->tc_fold, bm);
         e = cudaMalloc(&lc->d_tc_b, bm.size());
         if (e == cudaSuccess) e = cudaMemcpy(lc->d_tc_b, bm.data(), bm.size(), cudaMemcpyHostToDevice);
-        if (lc->tc_mont) {
-            std::vector<uint64_t> mc(3 * (size_t)T);
+        if (lc->tc_fold) {
+            std::vector<uint64_t> fc(T);
             for (uint32_t k = 0; k < T; k++) {
-                const uint64_t m = h.dst_mod[k];
-                uint64_t inv = m;                                    // Newton: m^-1 mod 2^64 (m odd; correct to 3 bits, doubles every step)
-                for (int it = 0; it < 6; it++) inv *= 2 - m * inv;
-                const uint64_t r64 = (uint64_t)((((unsigned __int128)1) << 64) % m);
-                mc[k] = 0 - inv; mc[T + k] = host::mulmod(h.c[k] % m, r64, m); mc[2 * (size_t)T + k] = host::mulmod(h.lam[k] % m, r64, m);
+                uint64_t hi, lo;
+                host::frac128(h.lam[k] % h.dst_mod[k], h.dst_mod[k], hi, lo);      // floor(lam 2^128 / m): the high word is the Shoup companion
+                fc[k] = hi;
             }
-            if (e == cudaSuccess) e = cudaMalloc(&lc->d_tc_mont, mc.size() * 8);
-            if (e == cudaSuccess) e = cudaMemcpy(lc->d_tc_mont, mc.data(), mc.size() * 8, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&lc->d_tc_fold, fc.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(lc->d_tc_fold, fc.data(), fc.size() * 8, cudaMemcpyHostToDevice);
         }
         if (e != cudaSuccess) { set_error("lincomb: device allocation failed: %s", cudaGetErrorString(e)); cudaFree(lc->d_blob); cudaFree(lc->d_bfrag); delete lc; return FHE_B200_ECUDA; }
     }
@@ -407,7 +407,7 @@ extern "C" int fhe_b200_lincomb_destroy(fhe_b200_lincomb* lc) {
     cudaFree(lc->d_blob);
     cudaFree(lc->d_bfrag);
     cudaFree(lc->d_tc_b);
-    cudaFree(lc->d_tc_mont);
+    cudaFree(lc->d_tc_fold);
     delete lc;
     return 0;
 }

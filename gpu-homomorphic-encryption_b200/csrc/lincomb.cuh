@@ -28,11 +28,11 @@ struct fhe_b200_lincomb {
     // tcgen05 / TMEM path (lincomb_tc.cu): B operand of the Toeplitz byte GEMM in the canonical shared-memory layout
     uint8_t* d_tc_b = nullptr;
     bool use_tc = false;                                        // when the operands fit shared memory; FHE_B200_LINCOMB_TC = 0 | 1 overrides
-    // Montgomery form of the tcgen05 path (every target modulus in (2^60 - 2^32, 2^60)): the matrix, c and lam carry a factor 2^64,
-    // the 128-bit sum is reduced by one Montgomery step (R = 2^64) instead of a 128-bit Barrett reduction.  [3][T]: -m^-1 mod 2^64,
-    // c * 2^64 mod m, lam * 2^64 mod m.  FHE_B200_LINCOMB_TC_MONT = 0 keeps the Barrett epilogue.
-    uint64_t* d_tc_mont = nullptr;
-    bool tc_mont = false;
+    // FOLD form of the tcgen05 path (every target modulus in (2^60 - 2^32, 2^60)): eight columns per target carrying the bytes of
+    // M[i][k] * 2^(8a) mod m_k, an 82-bit sum folded at 2^60 (lincomb_tc.cu).  [T]: Shoup companion of lam.
+    // FHE_B200_LINCOMB_TC_FOLD = 0 keeps the Toeplitz form with the 128-bit Barrett epilogue (the form of every other modulus).
+    uint64_t* d_tc_fold = nullptr;
+    bool tc_fold = false;
 };
 
 namespace fhe_b200 {
@@ -69,8 +69,8 @@ int lincomb_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t b
 int lincomb_mma_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
 // tcgen05 path; n must be a multiple of 128
 int lincomb_tc_launch(fhe_b200_lincomb* lc, const LcView& v, uint32_t n, uint32_t batch, cudaStream_t st);
-size_t lincomb_tc_smem_bytes(uint32_t S, uint32_t T);
-void lincomb_tc_build_b(const LincombConsts& h, uint32_t KS, bool montgomery, std::vector<uint8_t>& out);
+size_t lincomb_tc_smem_bytes(uint32_t S, uint32_t T, bool fold);
+void lincomb_tc_build_b(const LincombConsts& h, uint32_t KS, bool fold, std::vector<uint8_t>& out);
 uint32_t lincomb_mma_pad_kt(uint32_t S);
 void lincomb_mma_build_bfrag(const LincombConsts& h, uint32_t KT, std::vector<uint2>& out);
 

@@ -23,14 +23,16 @@ def _rand_limbs(rng, mods, n, batch):
 
 def _pick_lincomb_kernel(monkeypatch, tpc):
     """IMAD kernel with one or two lanes per coefficient ("1", "2"), the mma.sync tensor-core kernel ("mma") or the tcgen05 / TMEM
-    kernel ("tc"; shapes whose operands do not fit shared memory fall back to mma.sync) -- read when the object is created"""
-    monkeypatch.setenv("FHE_B200_LINCOMB_MMA", "1" if tpc in ("mma", "tc") else "0")
-    monkeypatch.setenv("FHE_B200_LINCOMB_TC", "1" if tpc == "tc" else "0")
+    kernel ("tc": eight folded columns per target where every target is a chain prime; "tcb": its Toeplitz form with the 128-bit Barrett
+    epilogue, the one other moduli get; shapes whose operands do not fit shared memory fall back to mma.sync) -- read when the object is created"""
+    monkeypatch.setenv("FHE_B200_LINCOMB_MMA", "1" if tpc in ("mma", "tc", "tcb") else "0")
+    monkeypatch.setenv("FHE_B200_LINCOMB_TC", "1" if tpc in ("tc", "tcb") else "0")
+    monkeypatch.setenv("FHE_B200_LINCOMB_TC_FOLD", "0" if tpc == "tcb" else "1")
     if tpc in ("1", "2"):
         monkeypatch.setenv("FHE_B200_LINCOMB_TPC", tpc)
 
 
-@pytest.mark.parametrize("tpc", ["1", "2", "mma", "tc"])
+@pytest.mark.parametrize("tpc", ["1", "2", "mma", "tc", "tcb"])
 @pytest.mark.parametrize("S,T", [(1, 3), (2, 3), (4, 5), (8, 24), (24, 25), (25, 24), (9, 4), (30, 7), (33, 2), (49, 25), (62, 3)])
 def test_base_conversion_vs_oracle(fhe, oracle, chain, S, T, tpc, monkeypatch):
     from fhe_b200.engine import to_device, to_host
@@ -50,7 +52,7 @@ def test_base_conversion_vs_oracle(fhe, oracle, chain, S, T, tpc, monkeypatch):
         assert np.array_equal(cg[k], co[k]), k
 
 
-@pytest.mark.parametrize("tpc", ["1", "2", "mma", "tc"])
+@pytest.mark.parametrize("tpc", ["1", "2", "mma", "tc", "tcb"])
 @pytest.mark.parametrize("L,R,t", [(1, 2, 65537), (2, 3, 65537), (4, 5, 786433), (24, 25, 65537), (3, 4, 1 << 20)])
 def test_scale_and_round_vs_oracle(fhe, oracle, chain, L, R, t, tpc, monkeypatch):
     from fhe_b200.engine import to_device, to_host
