@@ -135,35 +135,42 @@ __device__ __forceinline__ void tc_assemble160(const u32 (&p)[16], u64& w2, u64&
 // p_0 + p_4 2^32 -- the 64-bit addend of the first IMAD.WIDE.  With every p_b < 2^25:
 //   lo = p0 + p4 2^32 + p1 2^8 + p2 2^16 + p3 2^24 (+ x0 y0)  < 2^58,      hi = p5 2^8 + p6 2^16 + p7 2^24 (+ x0 y1)  < 2^50,
 //   V  = lo + hi 2^32.   (x0, y1:y0) is an optional small product riding on the same chains: the overflow count times c_k.
-__device__ __forceinline__ void tc_assemble_fold(const u32 (&r)[8], u32 x0, u64 y, u64& lo, u64& hi) {
+// The weights 2^8, 2^16, 2^24 come in registers (256 + an opaque zero ...): as literals ptxas rewrites every IMAD.WIDE into
+// IMAD.SHL + IMAD.HI + a three-input add, ten issue cycles instead of four.
+struct TcW { u32 w8, w16, w24; };
+__device__ __forceinline__ TcW tc_weights() {
+    const u32 z = (u32)kOpaqueZero;
+    return TcW{256u + z, 65536u + z, 16777216u + z};
+}
+__device__ __forceinline__ void tc_assemble_fold(const u32 (&r)[8], const TcW& w, u32 x0, u64 y, u64& lo, u64& hi) {
     asm("{\n\t"
         ".reg .u64 a, g;\n\t"
         ".reg .u32 y0, y1;\n\t"
         "mov.b64 {y0, y1}, %11;\n\t"
         "mov.b64 a, {%2, %3};\n\t"
-        "mad.wide.u32 a, %4, 256, a;\n\t"
-        "mad.wide.u32 a, %6, 65536, a;\n\t"
-        "mad.wide.u32 a, %8, 16777216, a;\n\t"
+        "mad.wide.u32 a, %4, %12, a;\n\t"
+        "mad.wide.u32 a, %6, %13, a;\n\t"
+        "mad.wide.u32 a, %8, %14, a;\n\t"
         "mad.wide.u32 %0, %10, y0, a;\n\t"
-        "mul.wide.u32 g, %5, 256;\n\t"
-        "mad.wide.u32 g, %7, 65536, g;\n\t"
-        "mad.wide.u32 g, %9, 16777216, g;\n\t"
+        "mul.wide.u32 g, %5, %12;\n\t"
+        "mad.wide.u32 g, %7, %13, g;\n\t"
+        "mad.wide.u32 g, %9, %14, g;\n\t"
         "mad.wide.u32 %1, %10, y1, g;\n\t"
         "}" : "=&l"(lo), "=&l"(hi)
-        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(x0), "l"(y));
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(x0), "l"(y), "r"(w.w8), "r"(w.w16), "r"(w.w24));
 }
-__device__ __forceinline__ void tc_assemble_fold(const u32 (&r)[8], u64& lo, u64& hi) {
+__device__ __forceinline__ void tc_assemble_fold(const u32 (&r)[8], const TcW& w, u64& lo, u64& hi) {
     asm("{\n\t"
         ".reg .u64 a, g;\n\t"
         "mov.b64 a, {%2, %3};\n\t"
-        "mad.wide.u32 a, %4, 256, a;\n\t"
-        "mad.wide.u32 a, %6, 65536, a;\n\t"
-        "mad.wide.u32 %0, %8, 16777216, a;\n\t"
-        "mul.wide.u32 g, %5, 256;\n\t"
-        "mad.wide.u32 g, %7, 65536, g;\n\t"
-        "mad.wide.u32 %1, %9, 16777216, g;\n\t"
+        "mad.wide.u32 a, %4, %10, a;\n\t"
+        "mad.wide.u32 a, %6, %11, a;\n\t"
+        "mad.wide.u32 %0, %8, %12, a;\n\t"
+        "mul.wide.u32 g, %5, %10;\n\t"
+        "mad.wide.u32 g, %7, %11, g;\n\t"
+        "mad.wide.u32 %1, %9, %12, g;\n\t"
         "}" : "=&l"(lo), "=&l"(hi)
-        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(w.w8), "r"(w.w16), "r"(w.w24));
 }
 // V = lo + hi 2^32 (+ e0 + e1 2^64) as three words, folded at 2^60: (V mod 2^60) + (V >> 60) delta, below 2m for V < 2^88
 __device__ __forceinline__ u64 tc_fold60(u64 lo, u64 hi, u64 e0, u32 e1, u32 delta) {
@@ -274,6 +281,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
     const uint32_t tmem_rd = tmem_d + ((warp & 3u) * 32u << 16);    // this warp's 32 lanes
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     uint32_t parity = 0;
+    const TcW wts = tc_weights();
     const bool use_extra = KIND == 3 ? a.use_extra != 0 : KIND == 1;
     const bool c_is_one = KIND == 3 ? a.c_is_one != 0 : KIND == 1;
     const bool has_sub = KIND == 3 ? a.v.sub != nullptr : KIND == 2;
@@ -284,14 +292,31 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
         const uint32_t b = (uint32_t)(coef >> a.logn);
         const uint32_t j = (uint32_t)(coef & (nn - 1));
         const u64* inb = a.v.in + (size_t)b * a.v.in_stride + j;
+        // the ModDown operands (minuend / addend) start their way to L2 now, a whole prologue ahead of their loads
+        if (has_sub)
+            for (uint32_t k = 0; k < a.T; k++) {
+                prefetch_l2(a.v.sub + (size_t)b * a.v.sub_stride + sIdx[2 * a.T + k] + j);
+                if (a.v.add) prefetch_l2(a.v.add + (size_t)b * a.v.add_stride + sIdx[2 * a.T + k] + j);
+            }
+        // FOLD form: the extra limbs of a whole chunk of targets are loaded into registers a phase ahead (the prologue's registers are
+        // free by then): one pair ahead -- the Toeplitz form's scheme -- left a third of the scale-and-round kernel's cycles waiting for them
+        u64 exv[16];
+        auto load_extras = [&](uint32_t first, uint32_t count) {
+            if (FOLD && KIND == 1) {
+#pragma unroll
+                for (int t = 0; t < 16; t++)
+                    if ((uint32_t)t < count) exv[t] = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + first + t] + j];
+            }
+        };
 
         // ---- prologue: this coefficient's sources -> bytes of z (row gtid of A), fixed-point sum of z * theta
         u64 facc = 0; u32 fcnt = 0;                                 // sum of the low words of z * theta_lo, and its carries
-#pragma unroll 1
-        for (uint32_t i0 = 0; i0 < SP; i0 += 8) {
-            u64 x[8];
+        // batches of eight sources, the loads of the next batch in flight while this one is multiplied (two register sets)
+        auto load8 = [&](u64 (&x)[8], uint32_t i0) {
 #pragma unroll
             for (int u = 0; u < 8; u++) x[u] = (i0 + u < a.S) ? __ldcg(inb + sOff[i0 + u]) : 0;
+        };
+        auto work8 = [&](u64 (&x)[8], uint32_t i0) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const uint32_t i = i0 + u;
@@ -306,8 +331,20 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
             for (int u = 0; u < 8; u += 2)
                 if (i0 + u < SP)                                    // sources i, i+1 = K bytes [8i, 8i+16) = K chunk i/2
                     *reinterpret_cast<ulonglong2*>(sA + (size_t)((i0 + u) >> 1) * 2048 + gtid * 16) = make_ulonglong2(x[u], x[u + 1]);
+        };
+        {
+            u64 xa[8], xb[8];
+            load8(xa, 0);
+#pragma unroll 1
+            for (uint32_t i0 = 0; i0 < SP; i0 += 16) {
+                if (i0 + 8 < SP) load8(xb, i0 + 8);
+                work8(xa, i0);
+                if (i0 + 16 < SP) load8(xa, i0 + 16);
+                if (i0 + 8 < SP) work8(xb, i0 + 8);
+            }
         }
         u64 I_hi = 0, I_lo = 0;                                     // known after the first chunk (the two pseudo-targets)
+        load_extras(0, min(tc_first(FOLD), a.T));
         fence_proxy_async_smem();                                   // A row visible to the tensor core
         tc_fence_before();
         group_barrier(1 + grp);
@@ -335,7 +372,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
             tc_fence_after();
             auto operands = [&](uint32_t k, u64& ex, u64& su, u64& ad) {
                 ex = 0; su = 0; ad = 0;
-                if (use_extra) ex = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + k] + j];
+                if (!(FOLD && KIND == 1) && use_extra) ex = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + k] + j];
                 if (has_sub) {
                     const size_t eo = sIdx[2 * a.T + k] + j;
                     su = a.v.sub[(size_t)b * a.v.sub_stride + eo];
@@ -376,7 +413,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                 const u32 delta = (u32)(0 - m);                      // 2^60 - m: the low word of 2^64 - m
                 u64 lo, hi, r;
                 if (c_is_one) {                                      // scale-and-round: the whole integer I (65 bits) and extra * lam join V
-                    tc_assemble_fold(pc, lo, hi);
+                    tc_assemble_fold(pc, wts, lo, hi);
                     u64 e0 = I_lo; u32 e1 = (u32)I_hi;
                     if (use_extra) {
                         const u64 e = shoup_mul_lazy3(ex, sDst[4 * a.T + k], sDst[a.T + k], 0 - m);      // below 3m
@@ -384,7 +421,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                     }
                     r = tc_fold60(lo, hi, e0, e1, delta);
                 } else {                                             // conversion: I < 64 (an overflow count) times c_k rides on the assembly
-                    tc_assemble_fold(pc, (u32)I_lo, sDst[3 * a.T + k], lo, hi);
+                    tc_assemble_fold(pc, wts, (u32)I_lo, sDst[3 * a.T + k], lo, hi);
                     if (use_extra) {
                         const u64 e = shoup_mul_lazy3(ex, sDst[4 * a.T + k], sDst[a.T + k], 0 - m);
                         r = tc_fold60(lo, hi, e, 0u, delta);
@@ -414,42 +451,67 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                 (void)g0;
             }
             // two targets per iteration: their reductions are independent chains, which keeps the four warps of a scheduler issuing
-            uint32_t tl = 0;
-#pragma unroll 1
-            for (; tl + 1 < cnt; tl += 2) {
-                const uint32_t k = t0 + tl;
-                const u64 cex0 = ex0, csu0 = su0, cad0 = ad0, cex1 = ex1, csu1 = su1, cad1 = ad1;
-                if (FOLD) {
-                    u32 p0[8], p1[8];
-                    tc_ld8(tmem_rd + col0 + tl * 8, p0);
-                    tc_ld8(tmem_rd + col0 + tl * 8 + 8, p1);
-                    if (tl + 3 < cnt) { operands(k + 2, ex0, su0, ad0); operands(k + 3, ex1, su1, ad1); }
-                    tc_wait_ld();
-                    finish8(k, p0, cex0, csu0, cad0);
-                    finish8(k + 1, p1, cex1, csu1, cad1);
-                } else {
-                    u32 p0[16], p1[16];
-                    tc_ld16(tmem_rd + col0 + tl * 16, p0);
-                    tc_ld16(tmem_rd + col0 + tl * 16 + 16, p1);
-                    if (tl + 3 < cnt) { operands(k + 2, ex0, su0, ad0); operands(k + 3, ex1, su1, ad1); }
-                    tc_wait_ld();
-                    finish16(k, p0, cex0, csu0, cad0);
-                    finish16(k + 1, p1, cex1, csu1, cad1);
+            if (FOLD && KIND == 1) {                                 // unrolled: exv is indexed statically
+#pragma unroll
+                for (int tl = 0; tl < 16; tl += 2) {
+                    const uint32_t k = t0 + tl;
+                    if ((uint32_t)tl + 1 < cnt) {
+                        const u64 csu0 = su0, cad0 = ad0, csu1 = su1, cad1 = ad1;
+                        u32 p0[8], p1[8];
+                        tc_ld8(tmem_rd + col0 + tl * 8, p0);
+                        tc_ld8(tmem_rd + col0 + tl * 8 + 8, p1);
+                        if ((uint32_t)tl + 3 < cnt) { operands(k + 2, ex0, su0, ad0); operands(k + 3, ex1, su1, ad1); }
+                        tc_wait_ld();
+                        finish8(k, p0, exv[tl], csu0, cad0);
+                        finish8(k + 1, p1, exv[tl + 1], csu1, cad1);
+                    } else if ((uint32_t)tl < cnt) {                 // an odd target left over
+                        operands(k, ex0, su0, ad0);
+                        u32 p0[8];
+                        tc_ld8(tmem_rd + col0 + tl * 8, p0);
+                        tc_wait_ld();
+                        finish8(k, p0, exv[tl], su0, ad0);
+                    }
                 }
-            }
-            if (tl < cnt) {                                          // an odd target left over
-                const uint32_t k = t0 + tl;
-                operands(k, ex0, su0, ad0);
-                if (FOLD) {
-                    u32 p0[8];
-                    tc_ld8(tmem_rd + col0 + tl * 8, p0);
-                    tc_wait_ld();
-                    finish8(k, p0, ex0, su0, ad0);
-                } else {
-                    u32 p0[16];
-                    tc_ld16(tmem_rd + col0 + tl * 16, p0);
-                    tc_wait_ld();
-                    finish16(k, p0, ex0, su0, ad0);
+                // the next chunk's extra limbs: in flight across the barrier and the tensor core's work
+                if (ch + 1 < NT) load_extras(t0 + cnt, min(tc_later(FOLD), a.T - t0 - cnt));
+            } else {
+                uint32_t tl = 0;
+#pragma unroll 1
+                for (; tl + 1 < cnt; tl += 2) {
+                    const uint32_t k = t0 + tl;
+                    const u64 cex0 = ex0, csu0 = su0, cad0 = ad0, cex1 = ex1, csu1 = su1, cad1 = ad1;
+                    if (FOLD) {
+                        u32 p0[8], p1[8];
+                        tc_ld8(tmem_rd + col0 + tl * 8, p0);
+                        tc_ld8(tmem_rd + col0 + tl * 8 + 8, p1);
+                        if (tl + 3 < cnt) { operands(k + 2, ex0, su0, ad0); operands(k + 3, ex1, su1, ad1); }
+                        tc_wait_ld();
+                        finish8(k, p0, cex0, csu0, cad0);
+                        finish8(k + 1, p1, cex1, csu1, cad1);
+                    } else {
+                        u32 p0[16], p1[16];
+                        tc_ld16(tmem_rd + col0 + tl * 16, p0);
+                        tc_ld16(tmem_rd + col0 + tl * 16 + 16, p1);
+                        if (tl + 3 < cnt) { operands(k + 2, ex0, su0, ad0); operands(k + 3, ex1, su1, ad1); }
+                        tc_wait_ld();
+                        finish16(k, p0, cex0, csu0, cad0);
+                        finish16(k + 1, p1, cex1, csu1, cad1);
+                    }
+                }
+                if (tl < cnt) {                                      // an odd target left over
+                    const uint32_t k = t0 + tl;
+                    operands(k, ex0, su0, ad0);
+                    if (FOLD) {
+                        u32 p0[8];
+                        tc_ld8(tmem_rd + col0 + tl * 8, p0);
+                        tc_wait_ld();
+                        finish8(k, p0, ex0, su0, ad0);
+                    } else {
+                        u32 p0[16];
+                        tc_ld16(tmem_rd + col0 + tl * 16, p0);
+                        tc_wait_ld();
+                        finish16(k, p0, ex0, su0, ad0);
+                    }
                 }
             }
             t0 += cnt; b_off += K * ncol;
