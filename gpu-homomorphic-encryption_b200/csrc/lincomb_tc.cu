@@ -30,6 +30,7 @@
 // accumulators are p_b = sum z_ia byte_b(F) < 2^25 and V = sum_b p_b 2^(8b) < 2^82: six IMAD.WIDE assemble it, and because
 // 2^60 = delta (mod m) one more folds it below 2m:  V = (V mod 2^60) + (V >> 60) delta.  No Montgomery factor, no 128-bit product:
 // about 60 issue cycles per target instead of about 105, two chunks of targets per tile instead of four for Q -> R.
+#include <type_traits>
 #include "lincomb.cuh"
 #include "host_math.hpp"
 #include "tma.cuh"
@@ -235,10 +236,9 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
     unsigned char* sA = tc_smem + ((b_bytes + 127) & ~(size_t)127) + (size_t)grp * 128 * K;
     u64* sC = reinterpret_cast<u64*>(tc_smem + ((b_bytes + 127) & ~(size_t)127) + (size_t)kTcGroups * 128 * K);
     const uint32_t SP = a.KS * 4;
-    u64* sSrc = sC;                                                 // [5][SP]: modulus, pre, pre', theta hi / lo
-    u64* sOff = sSrc + 5 * SP;                                      // element offset of source limb i inside a polynomial
-    u64* sCpy = sOff + SP;                                          // [2][SP]: pass-through address of source i (polynomial 0), words per polynomial
-    u64* sDst = sCpy + 2 * SP;                                      // [7][T]: modulus, mu_hi (FOLD: Shoup companion of lam), mu_lo, c, lam, epilogue scalar and its Shoup companion
+    u64* sSrc = sC;                                                 // [SP] records of 8 words: modulus, pre | pre', theta_lo | element offset of the limb inside a
+                                                                    // polynomial, 0 | pass-through address (polynomial 0), words per polynomial -- read as 16-byte pairs
+    u64* sDst = sSrc + 8 * SP;                                      // [7][T]: modulus, mu_hi (FOLD: Shoup companion of lam), mu_lo, c, lam, epilogue scalar and its Shoup companion
     u64* sIdx = sDst + 7 * (size_t)a.T;                             // [4][T]: out address (polynomial 0), extra / epilogue offsets, out words per polynomial
     uint64_t* bars = reinterpret_cast<uint64_t*>(sIdx + 4 * (size_t)a.T);     // one per group
     uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + kTcGroups);
@@ -251,13 +251,13 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
     }
     for (uint32_t i = tid; i < SP; i += blockDim.x) {
         const bool in = i < a.S;
-        sSrc[i] = in ? a.src_mod[i] : 3; sSrc[SP + i] = in ? a.pre[i] : 0; sSrc[2 * SP + i] = in ? a.pre_s[i] : 0;
-        sSrc[3 * SP + i] = in ? a.th_hi[i] : 0; sSrc[4 * SP + i] = in ? a.th_lo[i] : 0;
-        sOff[i] = in ? (u64)a.v.src_idx[i] * nn : 0;
+        u64* rec = sSrc + 8 * (size_t)i;
+        rec[0] = in ? a.src_mod[i] : 3; rec[1] = in ? a.pre[i] : 0; rec[2] = in ? a.pre_s[i] : 0; rec[3] = in ? a.th_lo[i] : 0;
+        rec[4] = in ? (u64)a.v.src_idx[i] * nn : 0; rec[5] = 0; rec[6] = 0; rec[7] = 0;
         if (in && a.v.copy_out) {
-            if (a.v.copy_tab) { sCpy[SP + i] = a.v.copy_tab[2 * i + 1]; sCpy[i] = a.v.copy_tab[2 * i] + a.v.copy_poly0 * sCpy[SP + i] * 8; }
-            else { sCpy[SP + i] = a.v.copy_stride; sCpy[i] = (u64)(a.v.copy_out + (size_t)a.v.copy_idx[i] * nn); }
-        } else { sCpy[i] = 0; sCpy[SP + i] = 0; }
+            if (a.v.copy_tab) { rec[7] = a.v.copy_tab[2 * i + 1]; rec[6] = a.v.copy_tab[2 * i] + a.v.copy_poly0 * rec[7] * 8; }
+            else { rec[7] = a.v.copy_stride; rec[6] = (u64)(a.v.copy_out + (size_t)a.v.copy_idx[i] * nn); }
+        }
     }
     for (uint32_t k = tid; k < a.T; k += blockDim.x) {
         sDst[k] = a.dst_mod[k]; sDst[a.T + k] = FOLD ? a.fold[k] : a.mu_hi[k]; sDst[2 * a.T + k] = a.mu_lo[k];
@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
     const bool use_extra = KIND == 3 ? a.use_extra != 0 : KIND == 1;
     const bool c_is_one = KIND == 3 ? a.c_is_one != 0 : KIND == 1;
     const bool has_sub = KIND == 3 ? a.v.sub != nullptr : KIND == 2;
+    const bool do_copy = a.v.copy_out != nullptr;
 
 #pragma unroll 1
     for (size_t tile = (size_t)blockIdx.x + (size_t)gridDim.x * grp; tile < a.tiles; tile += (size_t)gridDim.x * kTcGroups) {     // CTAs first, then groups: few tiles spread over many SMs
@@ -314,23 +315,33 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
         // batches of eight sources, the loads of the next batch in flight while this one is multiplied (two register sets)
         auto load8 = [&](u64 (&x)[8], uint32_t i0) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) x[u] = (i0 + u < a.S) ? __ldcg(inb + sOff[i0 + u]) : 0;
+            for (int u = 0; u < 8; u++) x[u] = (i0 + u < a.S) ? __ldcg(inb + sSrc[8 * (i0 + u) + 4]) : 0;
         };
-        auto work8 = [&](u64 (&x)[8], uint32_t i0) {
+        // FULL: all eight sources of the batch exist (no per-source tests); the flags are uniform
+        auto work8 = [&](u64 (&x)[8], uint32_t i0, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const uint32_t i = i0 + u;
-                if (i < SP) {
-                    if (i < a.S && a.v.copy_out) reinterpret_cast<u64*>(sCpy[i])[(size_t)b * sCpy[SP + i] + j] = x[u];
-                    if (a.use_pre) x[u] = shoup_mul(x[u], sSrc[SP + i], sSrc[2 * SP + i], sSrc[i]);
-                    const u64 lo = x[u] * sSrc[4 * SP + i];
+                if (FULL || i < SP) {
+                    const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(sSrc + 8 * i);          // modulus, pre
+                    const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(sSrc + 8 * i + 2);      // pre', theta_lo
+                    if (do_copy && (FULL || i < a.S)) {
+                        const ulonglong2 c67 = *reinterpret_cast<const ulonglong2*>(sSrc + 8 * i + 6);  // pass-through address, words per polynomial
+                        reinterpret_cast<u64*>(c67.x)[(size_t)b * c67.y + j] = x[u];
+                    }
+                    if (a.use_pre) x[u] = csub_sign(shoup_mul_lazy(x[u], c01.y, c23.x, c01.x), c01.x);
+                    const u64 lo = x[u] * c23.y;
                     asm("add.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+l"(facc), "+r"(fcnt) : "l"(lo));
                 }
             }
 #pragma unroll
             for (int u = 0; u < 8; u += 2)
-                if (i0 + u < SP)                                    // sources i, i+1 = K bytes [8i, 8i+16) = K chunk i/2
+                if (FULL || i0 + u < SP)                            // sources i, i+1 = K bytes [8i, 8i+16) = K chunk i/2
                     *reinterpret_cast<ulonglong2*>(sA + (size_t)((i0 + u) >> 1) * 2048 + gtid * 16) = make_ulonglong2(x[u], x[u + 1]);
+        };
+        auto work = [&](u64 (&x)[8], uint32_t i0) {
+            if (i0 + 8 <= a.S) work8(x, i0, std::true_type{}); else work8(x, i0, std::false_type{});
         };
         {
             u64 xa[8], xb[8];
@@ -338,9 +349,9 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
 #pragma unroll 1
             for (uint32_t i0 = 0; i0 < SP; i0 += 16) {
                 if (i0 + 8 < SP) load8(xb, i0 + 8);
-                work8(xa, i0);
+                work(xa, i0);
                 if (i0 + 16 < SP) load8(xa, i0 + 16);
-                if (i0 + 8 < SP) work8(xb, i0 + 8);
+                if (i0 + 8 < SP) work(xb, i0 + 8);
             }
         }
         u64 I_hi = 0, I_lo = 0;                                     // known after the first chunk (the two pseudo-targets)
