@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
     const bool c_is_one = KIND == 3 ? a.c_is_one != 0 : KIND == 1;
     const bool has_sub = KIND == 3 ? a.v.sub != nullptr : KIND == 2;
     const bool do_copy = a.v.copy_out != nullptr;
+    constexpr bool PRE = FOLD && (KIND == 1 || KIND == 2);          // epilogue operand prefetched a chunk ahead (opv)
 
 #pragma unroll 1
     for (size_t tile = (size_t)blockIdx.x + (size_t)gridDim.x * grp; tile < a.tiles; tile += (size_t)gridDim.x * kTcGroups) {     // CTAs first, then groups: few tiles spread over many SMs
@@ -293,20 +294,23 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
         const uint32_t b = (uint32_t)(coef >> a.logn);
         const uint32_t j = (uint32_t)(coef & (nn - 1));
         const u64* inb = a.v.in + (size_t)b * a.v.in_stride + j;
-        // the ModDown operands (minuend / addend) start their way to L2 now, a whole prologue ahead of their loads
+        // the ModDown operands that are loaded pair by pair (minuend / addend) start their way to L2 now, a whole prologue ahead
         if (has_sub)
             for (uint32_t k = 0; k < a.T; k++) {
-                prefetch_l2(a.v.sub + (size_t)b * a.v.sub_stride + sIdx[2 * a.T + k] + j);
+                if (!PRE) prefetch_l2(a.v.sub + (size_t)b * a.v.sub_stride + sIdx[2 * a.T + k] + j);
                 if (a.v.add) prefetch_l2(a.v.add + (size_t)b * a.v.add_stride + sIdx[2 * a.T + k] + j);
             }
-        // FOLD form: the extra limbs of a whole chunk of targets are loaded into registers a phase ahead (the prologue's registers are
-        // free by then): one pair ahead -- the Toeplitz form's scheme -- left a third of the scale-and-round kernel's cycles waiting for them
-        u64 exv[16];
+        // FOLD form, scale-and-round and ModDown: the epilogue operand of a whole chunk of targets (extra limb / minuend) is loaded into
+        // registers a phase ahead (the prologue's registers are free by then): one pair ahead -- the Toeplitz form's scheme -- left a third
+        // of the scale-and-round kernel's cycles waiting for them
+        u64 opv[16];
         auto load_extras = [&](uint32_t first, uint32_t count) {
-            if (FOLD && KIND == 1) {
+            if (PRE) {
 #pragma unroll
                 for (int t = 0; t < 16; t++)
-                    if ((uint32_t)t < count) exv[t] = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + first + t] + j];
+                    if ((uint32_t)t < count)
+                        opv[t] = KIND == 1 ? a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + first + t] + j]
+                                           : a.v.sub[(size_t)b * a.v.sub_stride + sIdx[2 * a.T + first + t] + j];
             }
         };
 
@@ -383,10 +387,10 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
             tc_fence_after();
             auto operands = [&](uint32_t k, u64& ex, u64& su, u64& ad) {
                 ex = 0; su = 0; ad = 0;
-                if (!(FOLD && KIND == 1) && use_extra) ex = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + k] + j];
+                if (!PRE && use_extra) ex = a.v.extra[(size_t)b * a.v.extra_stride + sIdx[a.T + k] + j];
                 if (has_sub) {
                     const size_t eo = sIdx[2 * a.T + k] + j;
-                    su = a.v.sub[(size_t)b * a.v.sub_stride + eo];
+                    if (!PRE) su = a.v.sub[(size_t)b * a.v.sub_stride + eo];
                     if (a.v.add) ad = a.v.add[(size_t)b * a.v.add_stride + eo];
                 }
             };
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                 (void)g0;
             }
             // two targets per iteration: their reductions are independent chains, which keeps the four warps of a scheduler issuing
-            if (FOLD && KIND == 1) {                                 // unrolled: exv is indexed statically
+            if (PRE) {                                               // unrolled: opv is indexed statically
 #pragma unroll
                 for (int tl = 0; tl < 16; tl += 2) {
                     const uint32_t k = t0 + tl;
@@ -473,14 +477,14 @@ __global__ void __launch_bounds__(128 * kTcGroups, 1) lincomb_tc_kernel(const Lc
                         tc_ld8(tmem_rd + col0 + tl * 8 + 8, p1);
                         if ((uint32_t)tl + 3 < cnt) { operands(k + 2, ex0, su0, ad0); operands(k + 3, ex1, su1, ad1); }
                         tc_wait_ld();
-                        finish8(k, p0, exv[tl], csu0, cad0);
-                        finish8(k + 1, p1, exv[tl + 1], csu1, cad1);
+                        finish8(k, p0, KIND == 1 ? opv[tl] : 0, KIND == 2 ? opv[tl] : csu0, cad0);
+                        finish8(k + 1, p1, KIND == 1 ? opv[tl + 1] : 0, KIND == 2 ? opv[tl + 1] : csu1, cad1);
                     } else if ((uint32_t)tl < cnt) {                 // an odd target left over
                         operands(k, ex0, su0, ad0);
                         u32 p0[8];
                         tc_ld8(tmem_rd + col0 + tl * 8, p0);
                         tc_wait_ld();
-                        finish8(k, p0, exv[tl], su0, ad0);
+                        finish8(k, p0, KIND == 1 ? opv[tl] : 0, KIND == 2 ? opv[tl] : su0, ad0);
                     }
                 }
                 // the next chunk's extra limbs: in flight across the barrier and the tensor core's work
