@@ -715,7 +715,7 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
         }
         if (!rc) rc = launch_ntt_pass_a(c->plan, acc, acc, 2 * B, 0, W, true, st);
     } else {
-        if (!rc) rc = launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st);
+        if (!rc) { ScopedLazyForward lazy(true); rc = launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st); }    // ks_inner_kernel reduces 128-bit sums
         if (!rc) {
             const size_t per = B * wn / 2;
             if (profile_on()) profile_begin(6, B, st);
@@ -775,7 +775,7 @@ static int multiply_half(fhe_b200_bfv* c, const uint64_t* d_a, const uint64_t* d
         STEP(tensor_transform(c, ext, d, B, square, st));
         STEP(launch_ntt_pass_a(c->plan, d, d, 3 * B, 0, A, true, st));
     } else {
-        STEP(launch_ntt(c->plan, ext, ext, planes * B, 0, A, false, st));
+        { ScopedLazyForward lazy(true); STEP(launch_ntt(c->plan, ext, ext, planes * B, 0, A, false, st)); }               // tensor_kernel reduces 128-bit products
         if (!rc) {
             const size_t per = B * an / 2;
             if (profile_on()) profile_begin(5, B, st);
@@ -831,6 +831,7 @@ static int multiply_one_split(fhe_b200_bfv* c, const uint64_t* d_a, const uint64
             FHE_TRY(lincomb_launch(c->q2r, v, n, 1, s));
         }
         if (fused) return launch_ntt_pass_a(c->plan, ext + (size_t)p0 * an, ext + (size_t)p0 * an, 2, 0, A, false, s);
+        ScopedLazyForward lazy(true);                                       // tensor_kernel reduces 128-bit products
         return launch_ntt(c->plan, ext + (size_t)p0 * an, ext + (size_t)p0 * an, 2, 0, A, false, s);
     };
     auto descale = [&](uint32_t p0, uint32_t cnt, cudaStream_t s) -> int {      // planes [p0, p0 + cnt) of the tensor: INTT, round(t/Q .), R -> Q

@@ -107,6 +107,14 @@ int launch_ntt_bal(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, u
 int launch_ntt_strided_in(fhe_b200_plan* plan, uint64_t* d_out, const uint64_t* d_in, size_t in_poly_stride, uint32_t batch,
                           uint32_t limb_begin, uint32_t limb_count, bool inverse, cudaStream_t st);
 // inverse transform of [batch][limb_count][N] whose tile pass runs in place on d_buf and whose column pass scatters the result
+// Forward transforms of the balanced two-pass sizes launched inside this scope leave their results lazy, in [0, 8q) instead of [0, q)
+// (ntt_bal.cuh, BalB::fwd_phase2): only for consumers that reduce 128-bit products of them anyway.  Other sizes are unaffected.
+extern thread_local bool g_fwd_lazy_out;
+struct ScopedLazyForward {
+    bool prev;
+    explicit ScopedLazyForward(bool on) : prev(g_fwd_lazy_out) { g_fwd_lazy_out = on; }
+    ~ScopedLazyForward() { g_fwd_lazy_out = prev; }
+};
 int launch_ntt_inverse_scatter(fhe_b200_plan* plan, uint64_t* d_buf, uint32_t batch, uint32_t limb_begin, uint32_t limb_count,
                                const BalScatter& scatter, cudaStream_t st);
 // Fused tile passes of the BFV multiply (ntt_fused.cu): forward tile pass of the operands, pointwise work, inverse tile pass of the

@@ -26,6 +26,9 @@ struct BalArgs {
     size_t in_poly_stride;       // elements between polynomials of `in` (the first pass of a transform reads `in`); out: limb_count * n
 };
 
+// forward transforms launched while this is set leave their results lazy (below 8q, see BalB::fwd_phase2); set by ScopedLazyForward
+thread_local bool g_fwd_lazy_out = false;
+
 constexpr size_t kBalASmem = 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
 constexpr int kBalBPairs = 4, kBalBGroups = 2, kBalBWarps = kBalBPairs * kBalBGroups, kBalBMinBlocks = 2;
 constexpr size_t kBalBSmem = kBalBWarps * 512 * sizeof(u64) + kBalBPairs * (512 * sizeof(Twiddle) + 16);
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256, 4) bal_a_scatter_kernel(const BalArgs a, 
 // twiddle block (8 KiB): 4 x 8 KiB of twiddles + 8 x 4 KiB of exchange buffers = 64 KiB per CTA.  Two CTAs (16 warps, 128 registers) per
 // SM is the measured optimum at config 3: 0.645 / 0.611 ms per forward / inverse pass, against 0.666 / 0.618 with three CTAs at 80
 // registers, 0.655 / 0.599 with five 128-thread CTAs at 96, 0.717 / 0.657 with four CTAs at 64 (spills).
-template <int KA, int HB, bool NEAR, bool INV>
+template <int KA, int HB, bool NEAR, bool INV, bool LAZY = false>
 __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(const BalArgs a) {
     using B = BalB<HB, NEAR>;
     extern __shared__ __align__(128) unsigned char raw[];
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
             B::fwd_load(lane, a.out + off, x);
             B::template fwd_phase1<B0>(lane, x, s, sb, P);
             __syncwarp();
-            B::template fwd_phase2<B0>(lane, s, sb, P);
+            B::template fwd_phase2<B0, LAZY>(lane, s, sb, P);
             __syncwarp();
             B::fwd_phase3(lane, a.out + off, s);
         } else {
@@ -173,6 +176,7 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
         FHE_CUDA(cudaFuncSetAttribute(bal_a_scatter_kernel<KA, HB, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalASmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
         FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
+        FHE_CUDA(cudaFuncSetAttribute(bal_b_kernel<KA, HB, NEAR, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalBSmem));
     }
     const uint32_t sms = (uint32_t)plan->sm_count;
     const uint64_t pls = (uint64_t)a.nl * a.nb;
@@ -205,7 +209,8 @@ static int run_bal_chunk(fhe_b200_plan* plan, BalArgs a, bool inverse, cudaStrea
         FHE_LAUNCH_CHECK();
         if (only_a) return 0;
         if (prof) profile_begin(0, pls, st);
-        bal_b_kernel<KA, HB, NEAR, false><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
+        if (g_fwd_lazy_out) bal_b_kernel<KA, HB, NEAR, false, true><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
+        else bal_b_kernel<KA, HB, NEAR, false><<<grid_b, 32 * kBalBWarps, kBalBSmem, st>>>(a);
         if (prof) profile_end(st);
         FHE_LAUNCH_CHECK();
     } else {

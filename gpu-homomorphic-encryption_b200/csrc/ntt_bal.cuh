@@ -156,7 +156,10 @@ struct BalB {
 #pragma unroll
         for (int e = 0; e < 16; e++) s[swz((t << 8) | (e << 4) | j)] = x[e];
     }
-    template <int B0>
+    // LAZY: the results stay in [0, fwd_lazy_bound() q) instead of being brought into [0, q) -- for consumers that multiply them with a
+    // 128-bit Barrett reduction anyway (tensor product, key-switch inner product): a range reduction and a conditional subtraction
+    // per element less
+    template <int B0, bool LAZY = false>
     static FHE_HD void fwd_phase2(u32 lane, u64* s, const Twiddle* sb, const LimbParams& P) {
         u64 x[16];
         const u64 q = P.q;
@@ -167,9 +170,13 @@ struct BalB {
         constexpr int BE = fwd_bound_after(B1, 4, HB, NEAR);
         fwd_stages<4, 4, HB, NEAR, B1>(x, TwB2{sb, lane}, P);
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            st2s(s + (row | ((k ^ (lane & 7)) << 1)), normalize<HB, NEAR, BE>(x[2 * k], q), normalize<HB, NEAR, BE>(x[2 * k + 1], q));
+        for (int k = 0; k < 8; k++) {
+            if (LAZY) st2s(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
+            else st2s(s + (row | ((k ^ (lane & 7)) << 1)), normalize<HB, NEAR, BE>(x[2 * k], q), normalize<HB, NEAR, BE>(x[2 * k + 1], q));
+        }
     }
+    template <int B0>
+    static FHE_HDC int fwd_lazy_bound() { return fwd_bound_after(fwd_bound_after(B0, 4, HB, NEAR), 4, HB, NEAR); }
     // forward round 2 with the sixteen canonical results left in registers (the lane's own row of the exchange buffer in,
     // nothing written): the fused tile kernels (ntt_fused.cu) go on to the pointwise work from here
     template <int B0>
