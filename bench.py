@@ -291,6 +291,9 @@ def run_ours(args, rank, local_rank, world):
     # integer-pipe peaks of this very GPU, measured now (csrc/peaks.cu): the roofline denominators
     lo_ops, wide_ops = C.c_double(), C.c_double()
     fhe_b200.check(lib.fhe_b200_measure_int_peaks(local_rank, C.byref(lo_ops), C.byref(wide_ops), 5))
+    loop_bfly = C.c_double()                                 # the butterfly alone, operands in registers: ceiling of the instruction mix
+    lib.fhe_b200_measure_butterfly_loop.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.c_int]
+    fhe_b200.check(lib.fhe_b200_measure_butterfly_loop(local_rank, int(chain[0]), int(chain[0]) // 3, C.byref(loop_bfly), 5))
 
     # per-kernel durations (second pass, events around every launch, same stream)
     lib.fhe_b200_profile_enable(1)
@@ -404,6 +407,11 @@ def run_ours(args, rank, local_rank, world):
                          "measured_now": {"imad_lo_Tops": r_lo / 1e12, "imad_wide_Tops": r_wide / 1e12,
                                           "how": "fhe_b200_measure_int_peaks: 8 independent chains per thread, 64 warps per SM, best of 5"},
                          "peak_formula": "9 / (5 / imad_wide + 4 / imad_lo)",
+                         "register_only_butterfly_loop": {
+                             "Gbutterflies_s": loop_bfly.value / 1e9, "frac_of_peak": loop_bfly.value * 9 / mix_peak,
+                             "whole_step_frac_of_loop": (step_ops / 9.0) / loop_bfly.value if loop_bfly.value else None,
+                             "how": "fhe_b200_measure_butterfly_loop: 4 forward stages on 16 register-resident values per thread, same multiply, bounds "
+                                    "and reductions as the passes, no memory traffic; what the carry / butterfly additions cost on top of the multiplier"},
                          "whole_step": {"achieved": step_ops / 1e12, "frac": step_ops / mix_peak,
                                         "peak_limb_transforms_s": mix_peak / 9.0 / bfly_per_unit},
                          "survey_8d_formula": {"imad_ops_per_limb_transform": 10 * bfly_per_unit,

@@ -58,6 +58,10 @@ int fhe_b200_profile_read(int kind, uint64_t* launches, double* total_ms, uint64
  * IMAD.WIDE (mul.wide.u32) over the whole chip, best of `reps` launches each.  The butterfly of the transforms is bound by this
  * pipe, and bench.py uses the two figures as its roofline denominators.  Synchronous; nothing in the reference corresponds. */
 int fhe_b200_measure_int_peaks(int device, double* imad_lo_ops, double* imad_wide_ops, int reps);
+/* The transforms' own lazy butterfly (same multiply, bounds and range reductions) in a loop that never leaves the registers: lazy
+ * butterflies per second over the whole chip, best of `reps` launches -- the practical ceiling of the instruction mix, which bench.py
+ * prints beside the IMAD roofline.  q: a modulus in (2^60 - 2^32, 2^60); w < q.  Synchronous. */
+int fhe_b200_measure_butterfly_loop(int device, uint64_t q, uint64_t w, double* butterflies_per_s, int reps);
 
 /* ---- plan: N, the RNS moduli and their device-resident twiddle tables ------------------------------------
  * replaces NTTEngine::NTTEngine / precompute_twiddle_factors / find_primitive_root / mod_inverse
