@@ -37,7 +37,8 @@ def _compile(src, verbose):
     obj = os.path.join(OBJ, os.path.basename(src) + ".o")
     if not _stale(obj, [src] + _deps()):
         return obj
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
+    extra = os.environ.get("FHE_B200_NVCC_EXTRA", "").split()          # experiments: extra -D flags (force a rebuild when changing them)
+    cmd = [NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

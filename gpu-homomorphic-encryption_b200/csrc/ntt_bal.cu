@@ -30,7 +30,10 @@ struct BalArgs {
 thread_local bool g_fwd_lazy_out = false;
 
 constexpr size_t kBalASmem = 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
-constexpr int kBalBPairs = 4, kBalBGroups = 2, kBalBWarps = kBalBPairs * kBalBGroups, kBalBMinBlocks = 2;
+#ifndef FHE_BAL_B_MINBLOCKS
+#define FHE_BAL_B_MINBLOCKS 2
+#endif
+constexpr int kBalBPairs = 4, kBalBGroups = 2, kBalBWarps = kBalBPairs * kBalBGroups, kBalBMinBlocks = FHE_BAL_B_MINBLOCKS;
 constexpr size_t kBalBSmem = kBalBWarps * 512 * sizeof(u64) + kBalBPairs * (512 * sizeof(Twiddle) + 16);
 
 template <int KA, int HB, bool NEAR, bool INV>
