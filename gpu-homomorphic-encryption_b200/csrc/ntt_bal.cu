@@ -33,7 +33,13 @@ constexpr size_t kBalASmem = 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
 #ifndef FHE_BAL_B_MINBLOCKS
 #define FHE_BAL_B_MINBLOCKS 2
 #endif
-constexpr int kBalBPairs = 4, kBalBGroups = 2, kBalBWarps = kBalBPairs * kBalBGroups, kBalBMinBlocks = FHE_BAL_B_MINBLOCKS;
+#ifndef FHE_BAL_B_PAIRS
+#define FHE_BAL_B_PAIRS 4
+#endif
+#ifndef FHE_BAL_B_GROUPS
+#define FHE_BAL_B_GROUPS 2
+#endif
+constexpr int kBalBPairs = FHE_BAL_B_PAIRS, kBalBGroups = FHE_BAL_B_GROUPS, kBalBWarps = kBalBPairs * kBalBGroups, kBalBMinBlocks = FHE_BAL_B_MINBLOCKS;
 constexpr size_t kBalBSmem = kBalBWarps * 512 * sizeof(u64) + kBalBPairs * (512 * sizeof(Twiddle) + 16);
 
 template <int KA, int HB, bool NEAR, bool INV>
