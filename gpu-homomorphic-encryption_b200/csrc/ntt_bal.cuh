@@ -89,7 +89,7 @@ struct BalA {
         u64 x[16];
         const u32 e1 = tid >> 4, ct = tid & 15;
         ldg16<256>(g + at2(tid, 0), x);
-        inv_stages<4, 4, HB, NEAR, false, BIN>(x, TwA2{stw, (1u << R1) + (e1 & RM)}, P);
+        inv_round16<4, HB, NEAR, false, BIN, kInvCap3>(x, TwA2{stw, (1u << R1) + (e1 & RM)}, P);
 #pragma unroll
         for (int rl = 0; rl < 16; rl++) s[(e1 << 8) | (rl << 4) | ct] = x[rl];
     }
@@ -98,7 +98,7 @@ struct BalA {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[(e << 8) | tid];
-        inv_stages<4, R1, HB, NEAR, true, inv_bound_after(BIN, 4, HB, NEAR)>(x, TwA1{stw}, P);
+        inv_round16<R1, HB, NEAR, true, inv_round16_out(4, HB, NEAR, false, BIN, kInvCap3), HB / 2>(x, TwA1{stw}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = normalize_last<HB, NEAR, R1>(x[e], e, P.q);
         stg16o<Off1>(g + at1(tid, 0), x);
@@ -111,7 +111,7 @@ struct BalA {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[(e << 8) | tid];
-        inv_stages<4, R1, HB, NEAR, true, inv_bound_after(BIN, 4, HB, NEAR)>(x, TwA1{stw}, P);
+        inv_round16<R1, HB, NEAR, true, inv_round16_out(4, HB, NEAR, false, BIN, kInvCap3), HB / 2>(x, TwA1{stw}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++)
             put((((u32)e & RM) << 4) | (tid >> 4), (((u32)e >> R1) << 4) + (tid & 15), normalize_last<HB, NEAR, R1>(x[e], e, P.q));
@@ -220,7 +220,7 @@ struct BalB {
     }
     // inverse round 1 on a row that is already in registers (canonical values); the result goes to the lane's own row of s
     static FHE_HD void inv_phase2_regs(u32 lane, u64 (&x)[16], u64* s, const Twiddle* sb, const LimbParams& P) {
-        inv_stages<4, 4, HB, NEAR, false, 1>(x, TwB2{sb, lane}, P);
+        inv_round16<4, HB, NEAR, false, 1, kInvCap1>(x, TwB2{sb, lane}, P);
         row_store(lane, s, x);
     }
     static FHE_HD void inv_phase2(u32 lane, u64* s, const Twiddle* sb, const LimbParams& P) {
@@ -228,7 +228,7 @@ struct BalB {
         const u32 row = lane << 4;
 #pragma unroll
         for (int k = 0; k < 8; k++) ld2(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
-        inv_stages<4, 4, HB, NEAR, false, 1>(x, TwB2{sb, lane}, P);
+        inv_round16<4, HB, NEAR, false, 1, kInvCap1>(x, TwB2{sb, lane}, P);
 #pragma unroll
         for (int k = 0; k < 8; k++) st2s(s + (row | ((k ^ (lane & 7)) << 1)), x[2 * k], x[2 * k + 1]);
     }
@@ -237,11 +237,11 @@ struct BalB {
         u64 x[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = s[swz((t << 8) | (e << 4) | j)];
-        inv_stages<4, 4, HB, NEAR, false, inv_bound_after(1, 4, HB, NEAR)>(x, TwB1{sb + t * 16}, P);
+        inv_round16<4, HB, NEAR, false, inv_round16_out(4, HB, NEAR, false, 1, kInvCap1), kInvCap2>(x, TwB1{sb + t * 16}, P);
 #pragma unroll
         for (int e = 0; e < 16; e++) g[(t << 8) | (e << 4) | j] = x[e];
     }
-    static FHE_HDC int inv_out_bound() { return inv_bound_after(1, 8, HB, NEAR); }
+    static FHE_HDC int inv_out_bound() { return inv_round16_out(4, HB, NEAR, false, inv_round16_out(4, HB, NEAR, false, 1, kInvCap1), kInvCap2); }
 };
 
 }  // namespace fhe_b200

@@ -268,6 +268,81 @@ FHE_HD void inv_stages(u64 (&x)[1 << LE], const TW& tw, const LimbParams& P) {
     }
 }
 
+// ---- inverse stages on sixteen values with PER-ELEMENT lazy bounds (moduli just below 2^60) ---------------------------------------
+// inv_stages tracks one bound for all values, so every sum is range-reduced every other stage (T < 3q: 3 -> 6 -> 12 -> reduce).  But a
+// value's bound is decided by its own history -- 3 after a twiddle product, the sum of its two inputs' bounds after an addition, and the
+// two inputs of a butterfly always share their history -- and the history is the index: after the stage with stride st, element e holds a
+// sum if bit st of e is clear, a product if it is set.  Tracking the sixteen bounds separately (four bits each, packed in a 64-bit
+// template constant) only the sums that would pass HB/2 are reduced: 40 instead of 56 reductions per sixteen values per 2^16-point
+// transform, 18 instead of 32 in the inverse column pass.  Bounds become uniform again where the values change threads: the last stage
+// of a round reduces what is above CAP, and the next round starts from the largest bound left.
+FHE_HDC int bs_get(u64 bs, int e) { return (int)((bs >> (4 * e)) & 15u) + 1; }
+FHE_HDC u64 bs_put(u64 bs, int e, int b) { return (bs & ~(15ull << (4 * e))) | ((u64)(b - 1) << (4 * e)); }
+FHE_HDC u64 bs_all(int b) { u64 r = 0; for (int e = 0; e < 16; e++) r = bs_put(r, e, b); return r; }
+FHE_HDC int bs_max(u64 bs) { int m = 1; for (int e = 0; e < 16; e++) m = bs_get(bs, e) > m ? bs_get(bs, e) : m; return m; }
+// bounds after one Gentleman-Sande stage with stride st: sums above `limit` are range-reduced (near60_reduce: below 2q); `scaled`: the
+// last stage of the whole transform, whose sums go through scale_ninv (below 2q)
+FHE_HDC u64 bs_gs_stage(u64 bs, int st, int limit, bool scaled) {
+    u64 r = bs;
+    for (int e = 0; e < 16; e++)
+        if (!(e & st)) {
+            int sum = bs_get(bs, e) + bs_get(bs, e + st);
+            if (scaled || sum > limit) sum = 2;
+            r = bs_put(r, e, sum); r = bs_put(r, e + st, kTQ);
+        }
+    return r;
+}
+FHE_HDC u64 bs_gs_round(u64 bs, int R, int HB, int cap, bool last) {
+    for (int V = R - 1; V >= 0; V--) bs = bs_gs_stage(bs, 1 << (R - 1 - V), V == 0 ? cap : HB / 2, last && V == 0);
+    return bs;
+}
+template <int R, int HB, bool LAST, u64 BS, int CAP, class TW, int V = R - 1>
+FHE_HD void inv_stages16(u64 (&x)[16], const TW& tw, const LimbParams& P) {
+    if constexpr (V >= 0) {
+        constexpr int st = 1 << (R - 1 - V);
+        constexpr int sh = 4 - R + V;
+        constexpr bool last = LAST && (V == 0);
+        constexpr int limit = (V == 0) ? CAP : HB / 2;
+        constexpr int BM = bs_max(BS);                          // every value is below BM q: the offset of the differences
+        static_assert(2 * BM <= HB && CAP <= HB / 2, "inverse stage would overflow 64 bits");
+        const u64 q = P.q, nq = 0 - q;
+        const u64 bq = (BM % kTQ == 0) ? (u64)(BM / kTQ) * P.tq : (u64)BM * q;
+#pragma unroll
+        for (int key = 0; key < (1 << sh); key++) {
+            Twiddle w;
+            if (last) { w.w = P.w1ninv; w.ws = P.w1ninv_s; }
+            else w = tw.get(V, key);
+#pragma unroll
+            for (int j = 0; j < st; j++) {
+                const int e = (key << (R - V)) | j;
+                const int bsum = bs_get(BS, e) + bs_get(BS, e + st);   // a constant once the loops are unrolled
+                const u64 X = x[e], Y = x[e + st];
+                FHE_BOUND(X, bs_get(BS, e), q); FHE_BOUND(Y, bs_get(BS, e + st), q); FHE_BOUND((unsigned __int128)X + Y, HB, q);
+                u64 S = add3z(X, Y);
+                const u64 D = X + bq - Y;
+                if (last) S = scale_ninv(S, P.nm, q);
+                else if (bsum > limit) S = near60_reduce(S, nq);
+                x[e] = S;
+                x[e + st] = shoup_mul_lazy3(D, w.w, w.ws, nq);
+                FHE_BOUND(x[e], bs_get(bs_gs_stage(BS, st, limit, last), e), q); FHE_BOUND(x[e + st], kTQ, q);
+            }
+        }
+        inv_stages16<R, HB, LAST, bs_gs_stage(BS, st, limit, last), CAP, TW, V - 1>(x, tw, P);
+    }
+}
+// One inverse round (R <= 4 stages) on sixteen values from a uniform entry bound BIN: per-element tracking for the near-2^60 moduli,
+// inv_stages otherwise.  inv_round16_out = the largest bound it leaves (kTQ when LAST).
+template <int R, int HB, bool NEAR, bool LAST, int BIN, int CAP, class TW>
+FHE_HD void inv_round16(u64 (&x)[16], const TW& tw, const LimbParams& P) {
+    if constexpr (NEAR) inv_stages16<R, HB, LAST, bs_all(BIN), CAP>(x, tw, P);
+    else inv_stages<4, R, HB, NEAR, LAST, BIN>(x, tw, P);
+}
+FHE_HDC int inv_round16_out(int R, int HB, bool NEAR, bool LAST, int bin, int cap) {
+    return NEAR ? bs_max(bs_gs_round(bs_all(bin), R, HB, cap, LAST)) : (LAST ? kTQ : inv_bound_after(bin, R, HB, NEAR));
+}
+// what may stay lazy at the end of the first, second and third round of a four-round inverse (found by enumeration for 4 x 4 stages)
+constexpr int kInvCap1 = 4, kInvCap2 = 4, kInvCap3 = 8;
+
 // bring a value bounded by B*q into [0, q)
 template <int HB, bool NEAR, int B>
 FHE_HD u64 normalize(u64 x, u64 q) {

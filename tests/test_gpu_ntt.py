@@ -388,3 +388,19 @@ def test_two_devices_in_one_process(fhe, oracle):
         dec = to_host(g.decrypt(out, sk))[0]
     assert np.array_equal(dec, oracle.schoolbook_negacyclic(m[0], m[1], p["t"]))
     assert torch.cuda.current_device() == 0
+
+
+def test_measured_integer_peaks_and_butterfly_loop(fhe, chain):
+    """The roofline denominators bench.py measures in its own run (csrc/peaks.cu): IMAD and IMAD.WIDE rates, and the engine's own lazy
+    butterfly in a register-only loop, which cannot beat the mix of the two it is made of (5 IMAD.WIDE + 4 IMAD per butterfly)."""
+    import ctypes as C
+    lib = fhe.load_library()
+    lo, wide, loop = C.c_double(), C.c_double(), C.c_double()
+    fhe.check(lib.fhe_b200_measure_int_peaks(0, C.byref(lo), C.byref(wide), 3))
+    lib.fhe_b200_measure_butterfly_loop.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.c_int]
+    fhe.check(lib.fhe_b200_measure_butterfly_loop(0, int(chain[0]), int(chain[0]) // 3, C.byref(loop), 3))
+    assert lo.value > 5e12 and wide.value > 2e12 and lo.value > wide.value
+    mix = 1.0 / (5.0 / wide.value + 4.0 / lo.value)                      # butterflies/s if the multiplier were all there is
+    assert 0.5 * mix < loop.value <= 1.02 * mix
+    with pytest.raises(fhe.FheB200Error):
+        fhe.check(lib.fhe_b200_measure_butterfly_loop(0, 12289, 3, C.byref(loop), 1))   # not a chain prime
