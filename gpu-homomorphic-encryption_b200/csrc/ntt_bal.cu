@@ -40,7 +40,9 @@ constexpr size_t kBalASmem = 4096 * sizeof(u64) + 256 * sizeof(Twiddle);
 #define FHE_BAL_B_GROUPS 2
 #endif
 constexpr int kBalBPairs = FHE_BAL_B_PAIRS, kBalBGroups = FHE_BAL_B_GROUPS, kBalBWarps = kBalBPairs * kBalBGroups, kBalBMinBlocks = FHE_BAL_B_MINBLOCKS;
-constexpr size_t kBalBSmem = kBalBWarps * 512 * sizeof(u64) + kBalBPairs * (512 * sizeof(Twiddle) + 16);
+// per warp: the 4 KiB exchange buffer and a 4 KiB staging buffer that the next polynomial's tile pair is bulk-copied into while this one is
+// transformed, with two mbarriers; per pair: the 8 KiB twiddle block and its mbarrier
+constexpr size_t kBalBSmem = kBalBWarps * (2 * 512 * sizeof(u64) + 16) + kBalBPairs * (512 * sizeof(Twiddle) + 16);
 
 template <int KA, int HB, bool NEAR, bool INV>
 __global__ void __launch_bounds__(256, 4) bal_a_kernel(const BalArgs a) {
@@ -125,15 +127,19 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
     extern __shared__ __align__(128) unsigned char raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pl_local = warp % kBalBPairs, gl = warp / kBalBPairs;       // pair and group inside the CTA
-    u64* s = reinterpret_cast<u64*>(raw) + warp * 512;
-    Twiddle* sb = reinterpret_cast<Twiddle*>(raw + kBalBWarps * 512 * sizeof(u64)) + pl_local * 512;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(raw + kBalBWarps * 512 * sizeof(u64) + kBalBPairs * 512 * sizeof(Twiddle)) + pl_local * 2;
+    u64* s = reinterpret_cast<u64*>(raw) + warp * 512;                         // exchange buffer
+    u64* stg = reinterpret_cast<u64*>(raw) + (kBalBWarps + warp) * 512;        // staging buffer (bulk copies land here)
+    unsigned char* after = raw + 2 * kBalBWarps * 512 * sizeof(u64);
+    Twiddle* sb = reinterpret_cast<Twiddle*>(after) + pl_local * 512;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(after + kBalBPairs * 512 * sizeof(Twiddle)) + pl_local * 2;
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(after + kBalBPairs * (512 * sizeof(Twiddle) + 16)) + warp * 2;   // this warp's two barriers
     constexpr uint32_t pairs = 1u << (KA - 1), pair_blocks = pairs / kBalBPairs;
     const uint32_t gblocks = (a.groups + kBalBGroups - 1) / kBalBGroups;
     const uint32_t pb = blockIdx.x % pair_blocks, r = blockIdx.x / pair_blocks, gb = r % gblocks, limb = a.l0 + r / gblocks;
     const uint32_t pair = pb * kBalBPairs + pl_local, grp = gb * kBalBGroups + gl;
     const uint32_t pl = a.limb_begin + limb;
-    if (threadIdx.x < kBalBPairs) mbar_init(reinterpret_cast<uint64_t*>(raw + kBalBWarps * 512 * sizeof(u64) + kBalBPairs * 512 * sizeof(Twiddle)) + threadIdx.x * 2, 1);
+    if (threadIdx.x < kBalBPairs) mbar_init(reinterpret_cast<uint64_t*>(after + kBalBPairs * 512 * sizeof(Twiddle)) + threadIdx.x * 2, 1);
+    if (lane < 2) mbar_init(wbar + lane, 1);
     if (threadIdx.x == 0) mbar_fence_init();
     __syncthreads();
     if (gl == 0 && lane == 0) {
@@ -145,28 +151,56 @@ __global__ void __launch_bounds__(32 * kBalBWarps, kBalBMinBlocks) bal_b_kernel(
     const size_t limb_off = (size_t)limb * a.n + (size_t)pair * 512;
     const size_t poly_stride = (size_t)a.limb_count * a.n;
     constexpr int B0 = BalA<KA, HB, NEAR>::fwd_out_bound();
-    mbar_wait(bar, 0);
-    // (issuing a polynomial's global loads early -- before the wait, or before the previous copy-out -- was measured slower:
-    //  0.701 ms against 0.646 ms per forward pass at config 3; the 16 live values cost more than the latency they hide)
+    const uint32_t first = a.b0 + grp, end = a.b0 + a.nb;
+    // A polynomial's tile pair is 4 KiB of contiguous global memory: one bulk copy (TMA) brings it into shared memory while the warp
+    // transforms the previous one -- the load latency costs no registers and no issue slots.  (Loading it early into registers was
+    // measured slower: 0.701 ms against 0.646 ms per forward pass at config 3.)
+    auto fetch = [&](u64* dst, uint64_t* wb, const u64* src) {      // called by the whole warp after its last read of dst
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wb, 512 * sizeof(u64));
+            bulk_copy_g2s(dst, src, 512 * sizeof(u64), wb);
+        }
+    };
+    if (!INV) {
+        // forward: round 1 takes its sixteen values out of the staging buffer, which is then free for the next polynomial
+        if (first < end) fetch(stg, wbar, a.out + first * poly_stride + limb_off);
+        mbar_wait(bar, 0);
+        uint32_t it = 0;
 #pragma unroll 1
-    for (uint32_t poly = a.b0 + grp; poly < a.b0 + a.nb; poly += a.groups) {
-        const size_t off = poly * poly_stride + limb_off;
-        if (!INV) {
+        for (uint32_t poly = first; poly < end; poly += a.groups, it++) {
+            const size_t off = poly * poly_stride + limb_off;
             u64 x[16];
-            B::fwd_load(lane, a.out + off, x);
+            mbar_wait(wbar, it & 1);
+            B::fwd_load_staged(lane, stg, x);
+            const size_t nxt = (size_t)poly + a.groups;
+            if (nxt < end) fetch(stg, wbar, a.out + nxt * poly_stride + limb_off);
             B::template fwd_phase1<B0>(lane, x, s, sb, P);
             __syncwarp();
             B::template fwd_phase2<B0, LAZY>(lane, s, sb, P);
             __syncwarp();
             B::fwd_phase3(lane, a.out + off, s);
-        } else {
-            B::inv_phase1(lane, a.in + (poly * a.in_poly_stride + limb_off), s);
             __syncwarp();
+        }
+    } else {
+        // inverse: one staging buffer; the re-layout into the exchange buffer frees it for the next polynomial
+        if (first < end) fetch(stg, wbar, a.in + (first * a.in_poly_stride + limb_off));
+        mbar_wait(bar, 0);
+        uint32_t it = 0;
+#pragma unroll 1
+        for (uint32_t poly = first; poly < end; poly += a.groups, it++) {
+            const size_t off = poly * poly_stride + limb_off;
+            mbar_wait(wbar, it & 1);
+            B::inv_phase1_staged(lane, stg, s);
+            const size_t nxt = (size_t)poly + a.groups;
+            if (nxt < end) fetch(stg, wbar, a.in + (nxt * a.in_poly_stride + limb_off));
+            else __syncwarp();
             B::inv_phase2(lane, s, sb, P);
             __syncwarp();
             B::inv_phase3(lane, a.out + off, s, sb, P);
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 

@@ -134,6 +134,12 @@ struct BalB {
         const u32 t = lane >> 4, j = lane & 15;
         ldg16<16>(g + ((t << 8) | j), x);
     }
+    // the same sixteen values from a tile pair that a bulk copy has landed in shared memory in natural order (st)
+    static FHE_HD void fwd_load_staged(u32 lane, const u64* st, u64 (&x)[16]) {
+        const u32 t = lane >> 4, j = lane & 15;
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = st[(t << 8) | (e << 4) | j];
+    }
     template <int B0>
     static FHE_HD void fwd_phase1(u32 lane, u64 (&x)[16], u64* s, const Twiddle* sb, const LimbParams& P) {
         const u32 t = lane >> 4, j = lane & 15;
@@ -216,6 +222,14 @@ struct BalB {
         for (int i = 0; i < 8; i++) {
             const u32 c = lane + 32 * i;
             u64 a, b; ldg2(g + 2 * c, a, b); st2(s + 2 * chunk_pos(c), a, b);
+        }
+    }
+    // the same re-layout from a tile pair that a bulk copy has landed in shared memory in natural order (st)
+    static FHE_HD void inv_phase1_staged(u32 lane, const u64* st, u64* s) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 c = lane + 32 * i;
+            u64 a, b; ld2(st + 2 * c, a, b); st2(s + 2 * chunk_pos(c), a, b);
         }
     }
     // inverse round 1 on a row that is already in registers (canonical values); the result goes to the lane's own row of s
