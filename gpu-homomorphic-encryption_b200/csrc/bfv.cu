@@ -230,26 +230,54 @@ __global__ void __launch_bounds__(256) tensor_kernel(ulonglong2* __restrict__ d,
     }
 }
 // key-switch inner product: acc[c][b][i] = sum_dg dig[dg][b][i] * rlk[dg][c][i]    (W = L+K limbs, NTT form)
+// A thread owns vector r of the polynomials and a run of `bpt` batch items: the 2 dnum key vectors of r -- six of the eleven 16-byte
+// accesses per item when every item fetched them itself -- are loaded once (dnum <= 4: registers) and reused for the whole run.
 __global__ void __launch_bounds__(256) ks_inner_kernel(ulonglong2* __restrict__ acc, const ulonglong2* __restrict__ dig,
                                                        const ulonglong2* __restrict__ rlk, const LimbParams* __restrict__ params,
-                                                       uint32_t logn, uint32_t limb_begin, uint32_t W, uint32_t dnum, uint32_t batch) {
+                                                       uint32_t logn, uint32_t limb_begin, uint32_t W, uint32_t dnum, uint32_t batch, uint32_t bpt) {
     const size_t wn = ((size_t)W << logn) / 2;              // vectors per polynomial
     const size_t per = wn * batch;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < per; v += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t runs = (batch + bpt - 1) / bpt;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < wn * runs; v += (size_t)gridDim.x * blockDim.x) {
         const size_t r = v % wn;
+        const uint32_t b0 = (uint32_t)(v / wn) * bpt, b1 = min(batch, b0 + bpt);
         const LimbParams P = params[limb_begin + ((2 * r) >> logn)];
-        u64 h0x = 0, l0x = 0, h0y = 0, l0y = 0, h1x = 0, l1x = 0, h1y = 0, l1y = 0;
-        for (uint32_t dg = 0; dg < dnum; dg++) {
-            const ulonglong2 x = dig[dg * per + v];
-            const ulonglong2 kb = rlk[(size_t)(2 * dg) * wn + r], ka = rlk[(size_t)(2 * dg + 1) * wn + r];
-            mac128(h0x, l0x, x.x, kb.x); mac128(h0y, l0y, x.y, kb.y);
-            mac128(h1x, l1x, x.x, ka.x); mac128(h1y, l1y, x.y, ka.y);
+        ulonglong2 kb[4], ka[4];
+        if (dnum <= 4) {
+#pragma unroll
+            for (int dg = 0; dg < 4; dg++)
+                if ((uint32_t)dg < dnum) { kb[dg] = rlk[(size_t)(2 * dg) * wn + r]; ka[dg] = rlk[(size_t)(2 * dg + 1) * wn + r]; }
         }
-        ulonglong2 o0, o1;
-        o0.x = barrett128(h0x, l0x, P.q, P.mu_hi, P.mu_lo); o0.y = barrett128(h0y, l0y, P.q, P.mu_hi, P.mu_lo);
-        o1.x = barrett128(h1x, l1x, P.q, P.mu_hi, P.mu_lo); o1.y = barrett128(h1y, l1y, P.q, P.mu_hi, P.mu_lo);
-        acc[v] = o0; acc[per + v] = o1;
+        for (uint32_t b = b0; b < b1; b++) {
+            const size_t o = (size_t)b * wn + r;
+            u64 h0x = 0, l0x = 0, h0y = 0, l0y = 0, h1x = 0, l1x = 0, h1y = 0, l1y = 0;
+            if (dnum <= 4) {
+#pragma unroll
+                for (int dg = 0; dg < 4; dg++)
+                    if ((uint32_t)dg < dnum) {
+                        const ulonglong2 x = dig[dg * per + o];
+                        mac128(h0x, l0x, x.x, kb[dg].x); mac128(h0y, l0y, x.y, kb[dg].y);
+                        mac128(h1x, l1x, x.x, ka[dg].x); mac128(h1y, l1y, x.y, ka[dg].y);
+                    }
+            } else {
+                for (uint32_t dg = 0; dg < dnum; dg++) {
+                    const ulonglong2 x = dig[dg * per + o];
+                    const ulonglong2 k0 = rlk[(size_t)(2 * dg) * wn + r], k1 = rlk[(size_t)(2 * dg + 1) * wn + r];
+                    mac128(h0x, l0x, x.x, k0.x); mac128(h0y, l0y, x.y, k0.y);
+                    mac128(h1x, l1x, x.x, k1.x); mac128(h1y, l1y, x.y, k1.y);
+                }
+            }
+            ulonglong2 o0, o1;
+            o0.x = barrett128(h0x, l0x, P.q, P.mu_hi, P.mu_lo); o0.y = barrett128(h0y, l0y, P.q, P.mu_hi, P.mu_lo);
+            o1.x = barrett128(h1x, l1x, P.q, P.mu_hi, P.mu_lo); o1.y = barrett128(h1y, l1y, P.q, P.mu_hi, P.mu_lo);
+            acc[o] = o0; acc[per + o] = o1;
+        }
     }
+}
+// batch items per thread: whole runs where one polynomial alone fills the GPU, one item otherwise (small rings live on the batch)
+static inline uint32_t ks_inner_bpt(int sm_count, size_t vectors_per_poly, uint32_t batch) {
+    if (vectors_per_poly < (size_t)sm_count * 16 * 256 / 2 || batch < 2) return 1;
+    return batch < 8 ? batch : 8;
 }
 
 // FHE_B200_FUSED_TILE=1: the tensor product and the key-switch inner product run inside the tile passes (ntt_fused.cu; two-pass
@@ -717,9 +745,10 @@ static int key_switch(fhe_b200_bfv* c, const uint64_t* x, size_t x_stride, const
     } else {
         if (!rc) { ScopedLazyForward lazy(true); rc = launch_ntt(c->plan, dig, dig, dnum * B, 0, W, false, st); }    // ks_inner_kernel reduces 128-bit sums
         if (!rc) {
-            const size_t per = B * wn / 2;
+            const uint32_t bpt = ks_inner_bpt(c->plan->sm_count, wn / 2, B);
+            const size_t per = (wn / 2) * ((B + bpt - 1) / bpt);
             if (profile_on()) profile_begin(6, B, st);
-            ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn, 0, W, dnum, B);
+            ks_inner_kernel<<<grid_for(c, per), 256, 0, st>>>((ulonglong2*)acc, (const ulonglong2*)dig, (const ulonglong2*)d_key, prm, c->logn, 0, W, dnum, B, bpt);
             if (profile_on()) profile_end(st);
             count_launch();
         }
@@ -1065,12 +1094,14 @@ extern "C" int fhe_b200_bfv_ks_inner(fhe_b200_plan* plan, uint64_t* d_acc, const
                                      uint32_t batch, uint32_t limb_begin, uint32_t limb_count, void* stream) {
     FHE_REQUIRE(plan && d_acc && d_dig && d_key && dnum >= 1, "bfv_ks_inner: bad argument");
     FHE_TRY(check_range(plan, batch, limb_begin, limb_count));
-    const size_t per = (size_t)batch * limb_count * plan->n / 2;
-    if (!per) return 0;
+    if (!((size_t)batch * limb_count)) return 0;
     DeviceGuard dev_guard(plan->device);
+    const size_t vpp = (size_t)limb_count * plan->n / 2;
+    const uint32_t bpt = ks_inner_bpt(plan->sm_count, vpp, batch);
+    const size_t per = vpp * ((batch + bpt - 1) / bpt);
     const size_t w = (per + 255) / 256, cap = (size_t)plan->sm_count * 16;
     ks_inner_kernel<<<(uint32_t)(w < cap ? w : cap), 256, 0, (cudaStream_t)stream>>>((ulonglong2*)d_acc, (const ulonglong2*)d_dig, (const ulonglong2*)d_key,
-                                                                                   plan->d_params, plan->logn, limb_begin, limb_count, dnum, batch);
+                                                                                   plan->d_params, plan->logn, limb_begin, limb_count, dnum, batch, bpt);
     FHE_LAUNCH_CHECK();
     return 0;
 }
