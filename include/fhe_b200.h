@@ -9,7 +9,8 @@
  * Conventions
  *   - every function returns 0 on success, a negative FHE_B200_E* code on failure; fhe_b200_last_error() gives
  *     the message for the calling thread.  Nothing throws, no C++ type crosses the boundary.
- *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are host pointers.
+ *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are host pointers.  Device buffers of polynomials must be
+ *     16-byte aligned (the kernels use 16-byte accesses and bulk copies; anything from cudaMalloc, or offset by whole limbs, is).
  *   - `stream` is a cudaStream_t passed as void*; all device work is asynchronous and ordered on that stream.  BFV calls on
  *     two or more ciphertexts (and a single multiply) fork part of their work onto streams owned by the context and join it
  *     back before the call's work completes on `stream`, so callers need no extra synchronisation (FHE_B200_HMULT_STREAMS=1
