@@ -3,6 +3,7 @@
 // lazy-reduction bounds can be validated against the oracle in the GPU-less container.  Not a product path:
 // nothing in the C-ABI library references this file.
 #include <vector>
+#include <cstdlib>
 #include <cstring>
 #include "ntt_core.cuh"
 #include "ntt_bal.cuh"
@@ -115,7 +116,15 @@ static void bal_limb(u64* d, const Twiddle* tw, const LimbParams& P, int inverse
         for (u32 p = 0; p < pairs; p++) {
             u64* g = d + (size_t)p * 512;
             const Twiddle* sb = blocks.data() + (size_t)p * 512;
-            for (u32 l = 0; l < 32; l++) { u64 x[16]; B::fwd_load(l, g, x); B::template fwd_phase1<B0>(l, x, sw.data(), sb, P); }
+            // the kernel's bulk copy lands the tile pair in a staging buffer in natural order; round 1 reads its values from there
+            std::vector<u64> stg(g, g + 512);
+            for (u32 l = 0; l < 32; l++) {
+                u64 x[16], y[16];
+                B::fwd_load_staged(l, stg.data(), x);
+                B::fwd_load(l, g, y);                                   // (the direct global loads of the fused kernels: same values)
+                for (int e = 0; e < 16; e++) if (x[e] != y[e]) std::abort();
+                B::template fwd_phase1<B0>(l, x, sw.data(), sb, P);
+            }
             for (u32 l = 0; l < 32; l++) B::template fwd_phase2<B0>(l, sw.data(), sb, P);
             for (u32 l = 0; l < 32; l++) B::fwd_phase3(l, g, sw.data());
         }
@@ -123,7 +132,12 @@ static void bal_limb(u64* d, const Twiddle* tw, const LimbParams& P, int inverse
         for (u32 p = 0; p < pairs; p++) {
             u64* g = d + (size_t)p * 512;
             const Twiddle* sb = blocks.data() + (size_t)p * 512;
-            for (u32 l = 0; l < 32; l++) B::inv_phase1(l, g, sw.data());
+            {   // staged re-layout (what the kernel does after its bulk copy) against the direct one
+                std::vector<u64> stg(g, g + 512), sw2(512);
+                for (u32 l = 0; l < 32; l++) B::inv_phase1_staged(l, stg.data(), sw.data());
+                for (u32 l = 0; l < 32; l++) B::inv_phase1(l, g, sw2.data());
+                if (sw2 != sw) std::abort();
+            }
             for (u32 l = 0; l < 32; l++) B::inv_phase2(l, sw.data(), sb, P);
             for (u32 l = 0; l < 32; l++) B::inv_phase3(l, g, sw.data(), sb, P);
         }
