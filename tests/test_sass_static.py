@@ -20,6 +20,8 @@ def _sass(path):
 
 
 def test_base_conversion_is_tcgen05_and_tile_pass_fetches_by_tma():
+    if not os.path.exists(os.path.join(OBJ, "lincomb_tc.cu.o")):
+        pytest.skip("objects not built (run __graft_entry__.build() first)")
     tc = _sass(os.path.join(OBJ, "lincomb_tc.cu.o"))
     assert "UTCIMMA" in tc and "LDTM" in tc and "UTCBAR" in tc          # tcgen05.mma, tcgen05.ld, tcgen05.commit
     assert not re.search(r"\b[HI]MMA\.", tc)                            # no warp-level mma.sync in the tcgen05 kernel
